@@ -1,0 +1,262 @@
+"""ctypes binding of the CPU oracle (oracle/libsdorb_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs as the checker / reported CPU baseline.  The product package (sdslam_b200) never
+imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libsdorb_oracle.so")
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+MATCH_DTYPE = np.dtype([("best_idx", "<i4"), ("best_dist", "<i4"), ("second_dist", "<i4"), ("accepted", "<i4")])
+GEOM_DTYPE = np.dtype([(n, "<i4") for n in ("width", "height", "n_desired", "level_cols", "level_rows", "cell_w",
+                                             "cell_h", "n_features_cell", "scaled_patch_size")])
+assert KP_DTYPE.itemsize == 28
+
+
+class Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("th_fast", C.c_int)]
+
+
+class Dump(C.Structure):
+    _fields_ = [("pyramid", C.c_void_p), ("blurred", C.c_void_p), ("level_count", C.c_void_p),
+                ("raw_cell_count", C.c_void_p), ("raw_cell_cap", C.c_int32), ("raw_kps", C.c_void_p),
+                ("raw_kps_cap", C.c_int32), ("raw_kps_total", C.c_int32), ("n_to_retain_cap", C.c_int32),
+                ("n_to_retain", C.c_void_p)]
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("sdorb_oracle.cc", "sdorb_oracle.h", "orb_pattern.inc", "Makefile")]
+    if force or not os.path.exists(_SO) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        L = _lib
+        vp, i, sz, f = C.c_void_p, C.c_int, C.c_size_t, C.c_float
+        L.orc_resize_linear_8u.argtypes = [vp, i, i, sz, vp, i, i, sz]
+        L.orc_copy_make_border_reflect101.argtypes = [vp, i, i, sz, vp, sz, i]
+        L.orc_fast.argtypes = [vp, i, i, sz, i, i, vp, i]
+        L.orc_fast.restype = i
+        L.orc_fast_score_map.argtypes = [vp, i, i, sz, i, vp, sz]
+        L.orc_gaussian_blur_7x7_s2.argtypes = [vp, i, i, sz, vp, sz]
+        L.orc_fast_atan2.argtypes = [f, f]
+        L.orc_fast_atan2.restype = f
+        L.orc_retain_best.argtypes = [vp, i, i]
+        L.orc_retain_best.restype = i
+        L.orc_retain_best_idx.argtypes = [vp, i, i, vp]
+        L.orc_retain_best_idx.restype = i
+        L.orc_sincosf_restated.argtypes = [f, C.POINTER(f), C.POINTER(f)]
+        L.orc_sincosf_mismatches.argtypes = [C.c_uint32, C.c_uint32, i]
+        L.orc_sincosf_mismatches.restype = C.c_uint64
+        L.orc_pattern_rotate.argtypes = [i, i, f, f, C.POINTER(i), C.POINTER(i)]
+        L.orc_create.argtypes = [C.POINTER(Params)]
+        L.orc_create.restype = vp
+        L.orc_destroy.argtypes = [vp]
+        L.orc_get_tables.argtypes = [vp] * 7
+        L.orc_level_geometry.argtypes = [vp, i, i, vp]
+        L.orc_extract.argtypes = [vp, vp, i, i, sz, vp, vp, i, C.POINTER(Dump)]
+        L.orc_extract.restype = i
+        L.orc_extract_many.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, i]
+        L.orc_extract_many.restype = C.c_long
+        L.orc_descriptor_distance.argtypes = [vp, vp]
+        L.orc_descriptor_distance.restype = i
+        L.orc_match_best2.argtypes = [vp, i, vp, i, f, i, vp]
+        L.orc_match_greedy.argtypes = [vp, i, vp, i, f, i, vp]
+        L.orc_match_many.argtypes = [vp, vp, vp, vp, i, i, i, f, i, i, vp]
+        L.orc_hamming_matrix.argtypes = [vp, i, vp, i, vp]
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+def _u8(img):
+    img = np.asarray(img)
+    assert img.dtype == np.uint8 and img.ndim == 2 and img.strides[1] == 1
+    return img
+
+
+# ---------------------------------------------------------------- primitives
+def resize_linear(img, dw, dh):
+    img = _u8(img)
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_8u(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), dw, dh, out.strides[0])
+    return out
+
+
+def border_reflect101(img, b):
+    img = _u8(img)
+    out = np.empty((img.shape[0] + 2 * b, img.shape[1] + 2 * b), np.uint8)
+    lib().orc_copy_make_border_reflect101(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), out.strides[0], b)
+    return out
+
+
+def fast(img, th, nonmax=True):
+    img = _u8(img)
+    cap = max(1, img.size)
+    out = np.zeros(cap, KP_DTYPE)
+    n = lib().orc_fast(_p(img), img.shape[1], img.shape[0], img.strides[0], th, int(nonmax), _p(out), cap)
+    return out[:n]
+
+
+def fast_score_map(img, th):
+    img = _u8(img)
+    out = np.zeros(img.shape, np.uint8)
+    lib().orc_fast_score_map(_p(img), img.shape[1], img.shape[0], img.strides[0], th, _p(out), out.strides[0])
+    return out
+
+
+def gaussian_blur(img):
+    img = _u8(img)
+    out = np.empty(img.shape, np.uint8)
+    lib().orc_gaussian_blur_7x7_s2(_p(img), img.shape[1], img.shape[0], img.strides[0], _p(out), out.strides[0])
+    return out
+
+
+def fast_atan2(y, x):
+    return lib().orc_fast_atan2(float(y), float(x))
+
+
+def retain_best_order(responses, n):
+    r = np.ascontiguousarray(responses, np.float32)
+    order = np.empty(len(r), np.int32)
+    m = lib().orc_retain_best_idx(_p(r), len(r), n, _p(order))
+    return order[:m]
+
+
+def sincosf_restated(x):
+    s, c = C.c_float(), C.c_float()
+    lib().orc_sincosf_restated(float(x), C.byref(s), C.byref(c))
+    return s.value, c.value
+
+
+def sincosf_mismatches(lo, hi, nthreads=8):
+    lo_bits = int(np.float32(lo).view(np.uint32))
+    hi_bits = int(np.float32(hi).view(np.uint32))
+    return int(lib().orc_sincosf_mismatches(lo_bits, hi_bits, nthreads))
+
+
+def pattern_rotate(px, py, a, b):
+    r, c = C.c_int(), C.c_int()
+    lib().orc_pattern_rotate(px, py, float(a), float(b), C.byref(r), C.byref(c))
+    return r.value, c.value
+
+
+# ---------------------------------------------------------------- extractor
+class Extractor:
+    """Oracle twin of SD_SLAM::ORBextractor(nfeatures, scaleFactor, nlevels, thFAST)."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, th_fast=20):
+        self.params = Params(nfeatures, scale_factor, nlevels, th_fast)
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = lib().orc_create(C.byref(self.params))
+        if not self._h:
+            raise ValueError("bad oracle parameters")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            lib().orc_destroy(self._h)
+            self._h = None
+
+    def tables(self):
+        n = self.nlevels
+        sf, inv, s2, is2 = (np.empty(n, np.float32) for _ in range(4))
+        npl, umax = np.empty(n, np.int32), np.empty(16, np.int32)
+        lib().orc_get_tables(self._h, _p(sf), _p(inv), _p(s2), _p(is2), _p(npl), _p(umax))
+        return dict(scale=sf, inv_scale=inv, sigma2=s2, inv_sigma2=is2, n_per_level=npl, umax=umax)
+
+    def geometry(self, w, h):
+        g = np.zeros(self.nlevels, GEOM_DTYPE)
+        lib().orc_level_geometry(self._h, w, h, _p(g))
+        return g
+
+    def extract(self, img, dump=False):
+        """Returns (kps, desc) or, with dump=True, (kps, desc, stages dict)."""
+        img = _u8(img)
+        h, w = img.shape
+        cap = max(self.nfeatures, 1)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        d = None
+        keep = {}
+        if dump:
+            g = self.geometry(w, h)
+            npx = int(sum(max(int(a), 0) * max(int(b), 0) for a, b in zip(g["width"], g["height"])))
+            ncell = int(sum(max(int(a), 0) * max(int(b), 0) for a, b in zip(g["level_cols"], g["level_rows"])))
+            keep = dict(pyramid=np.zeros(npx, np.uint8), blurred=np.zeros(npx, np.uint8),
+                        level_count=np.zeros(self.nlevels, np.int32), raw_cell_count=np.zeros(max(ncell, 1), np.int32),
+                        raw_kps=np.zeros(max(npx // 4 + 16, 16), KP_DTYPE), n_to_retain=np.zeros(max(ncell, 1), np.int32))
+            d = Dump(_p(keep["pyramid"]), _p(keep["blurred"]), _p(keep["level_count"]), _p(keep["raw_cell_count"]),
+                     len(keep["raw_cell_count"]), _p(keep["raw_kps"]), len(keep["raw_kps"]), 0,
+                     len(keep["n_to_retain"]), _p(keep["n_to_retain"]))
+        n = lib().orc_extract(self._h, _p(img), w, h, img.strides[0], _p(kps), _p(desc), cap,
+                              C.byref(d) if d is not None else None)
+        if n < 0:
+            raise RuntimeError("oracle: cell ROI outside the level image (the reference throws cv::Exception)")
+        assert n <= cap
+        if not dump:
+            return kps[:n], desc[:n]
+        keep["raw_kps"] = keep["raw_kps"][:d.raw_kps_total]
+        keep["geometry"] = g
+        return kps[:n], desc[:n], keep
+
+    def extract_many(self, imgs, nthreads=1, want_outputs=True):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        nf, h, w = imgs.shape
+        cap = max(self.nfeatures, 1)
+        kps = np.zeros((nf, cap), KP_DTYPE) if want_outputs else None
+        desc = np.zeros((nf, cap, 32), np.uint8) if want_outputs else None
+        counts = np.zeros(nf, np.int32)
+        lib().orc_extract_many(self._h, _p(imgs), nf, w, h, nthreads, _p(kps), _p(desc), _p(counts), cap)
+        return kps, desc, counts
+
+
+# ---------------------------------------------------------------- matcher
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def match_best2(A, B, ratio=0.75, th_low=50, greedy=False):
+    A = np.ascontiguousarray(A, np.uint8).reshape(-1, 32)
+    B = np.ascontiguousarray(B, np.uint8).reshape(-1, 32)
+    out = np.zeros(len(A), MATCH_DTYPE)
+    fn = lib().orc_match_greedy if greedy else lib().orc_match_best2
+    fn(_p(A), len(A), _p(B), len(B), ratio, th_low, _p(out))
+    return out
+
+
+def match_many(A, nA, B, nB, ratio=0.75, th_low=50, nthreads=1):
+    A = np.ascontiguousarray(A, np.uint8)
+    B = np.ascontiguousarray(B, np.uint8)
+    npairs, sa, sb = A.shape[0], A.shape[1], B.shape[1]
+    nA = np.ascontiguousarray(nA, np.int32)
+    nB = np.ascontiguousarray(nB, np.int32)
+    out = np.zeros((npairs, sa), MATCH_DTYPE)
+    lib().orc_match_many(_p(A), _p(nA), _p(B), _p(nB), npairs, sa, sb, ratio, th_low, nthreads, _p(out))
+    return out
+
+
+def hamming_matrix(A, B):
+    A = np.ascontiguousarray(A, np.uint8).reshape(-1, 32)
+    B = np.ascontiguousarray(B, np.uint8).reshape(-1, 32)
+    out = np.zeros((len(A), len(B)), np.uint16)
+    lib().orc_hamming_matrix(_p(A), len(A), _p(B), len(B), _p(out))
+    return out

@@ -1,0 +1,913 @@
+/*
+ * sdorb_oracle.cc -- CPU oracle for the SD-SLAM ORB front-end.
+ *
+ * TEST INFRASTRUCTURE ONLY (see sdorb_oracle.h).  Nothing here is shipped or measured as the
+ * product; libsdorb.so never links this file.
+ *
+ * What it restates, and where the behaviour comes from (paths relative to /root/reference):
+ *   - ORBextractor ctor tables            src/ORBextractor.cc:406-457
+ *   - ComputePyramid                      src/ORBextractor.cc:680-700
+ *   - ComputeKeyPoints (grid, FAST, quota, retainBest)   src/ORBextractor.cc:466-610
+ *   - IC_Angle / computeOrientation       src/ORBextractor.cc:78-102, 459-464
+ *   - computeOrbDescriptor                src/ORBextractor.cc:105-143
+ *   - operator()                          src/ORBextractor.cc:620-678
+ *   - DescriptorDistance                  src/ORBmatcher.cc:1459-1473
+ *   - best / second-best update rule      src/ORBmatcher.cc:1239-1265
+ * The pixel arithmetic lives in OpenCV (not vendored by the reference); the restatements below follow
+ * the published OpenCV 4.13 algorithms (imgproc resize.cpp fixed-point INTER_LINEAR, features2d
+ * fast.cpp / fast_score.cpp, smooth fixed-point Gaussian, core mathfuncs fastAtan2,
+ * keypoint.cpp retainBest) and are pinned bit-for-bit against Python cv2 4.13.0 in tests/.
+ *
+ * Build: g++ -O2 -std=c++17 -ffp-contract=off (see Makefile).  -ffp-contract=off matters: every
+ * fused multiply-add the reference's build performs is written as an explicit fmaf() here.
+ */
+#include "sdorb_oracle.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+namespace {
+
+/* ------------------------------------------------------------------ rounding helpers */
+/* cvRound(float|double) = SSE cvtss2si / cvtsd2si = round-half-to-even in the default FP mode. */
+inline int cv_round(float v) { return (int)lrintf(v); }
+inline int cv_round(double v) { return (int)lrint(v); }
+inline int cv_floor(double v) {
+  int i = (int)v;
+  return i - (i > v);
+}
+inline int cv_ceil(double v) {
+  int i = (int)v;
+  return i + (i < v);
+}
+inline short sat_short(float v) {
+  int i = cv_round(v);
+  return (short)(i < SHRT_MIN ? SHRT_MIN : i > SHRT_MAX ? SHRT_MAX : i);
+}
+
+/* ------------------------------------------------------------------ cv::resize INTER_LINEAR, 8UC1 */
+/* OpenCV imgproc/resize.cpp: resizeGeneric_ with HResizeLinear<uchar,int,short,2048> and
+ * VResizeLinear<uchar,int,short,FixedPtCast<int,uchar,22>>.  (The "scale exactly 2 => INTER_AREA fast"
+ * shortcut of cv::resize gives (a+b+c+d+2)>>2, which is what these formulas produce for that case too.) */
+void resize_linear_8u(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep) {
+  if (sw <= 0 || sh <= 0 || dw <= 0 || dh <= 0) return;
+  const double inv_scale_x = (double)dw / sw, inv_scale_y = (double)dh / sh;
+  const double scale_x = 1. / inv_scale_x, scale_y = 1. / inv_scale_y;
+  std::vector<int> xofs(dw), xofs1(dw);
+  std::vector<short> alpha(2 * dw);
+  for (int dx = 0; dx < dw; dx++) {
+    float fx = (float)((dx + 0.5) * scale_x - 0.5);
+    int sx = cv_floor(fx);
+    fx -= sx;
+    if (sx < 0) {
+      fx = 0;
+      sx = 0;
+    }
+    if (sx >= sw - 1) {
+      fx = 0;
+      sx = sw - 1;
+    }
+    xofs[dx] = sx;
+    xofs1[dx] = std::min(sx + 1, sw - 1);
+    alpha[2 * dx] = sat_short((1.f - fx) * 2048.f);
+    alpha[2 * dx + 1] = sat_short(fx * 2048.f);
+  }
+  std::vector<int> row0(dw), row1(dw);
+  int cached0 = -1, cached1 = -1;
+  auto hresize = [&](int sy, std::vector<int>& out) {
+    const uint8_t* S = src + (size_t)sy * sstep;
+    for (int dx = 0; dx < dw; dx++) out[dx] = S[xofs[dx]] * alpha[2 * dx] + S[xofs1[dx]] * alpha[2 * dx + 1];
+  };
+  auto clip = [](int x, int a, int b) { return x >= a ? (x < b ? x : b - 1) : a; };
+  for (int dy = 0; dy < dh; dy++) {
+    float fy = (float)((dy + 0.5) * scale_y - 0.5);
+    int sy = cv_floor(fy);
+    fy -= sy;
+    const int b0 = sat_short((1.f - fy) * 2048.f), b1 = sat_short(fy * 2048.f);
+    const int sy0 = clip(sy, 0, sh), sy1 = clip(sy + 1, 0, sh);
+    if (sy0 == cached1) {
+      std::swap(row0, row1);
+      std::swap(cached0, cached1);
+    }
+    if (sy0 != cached0) {
+      hresize(sy0, row0);
+      cached0 = sy0;
+    }
+    if (sy1 == cached0) {
+      row1 = row0;
+      cached1 = sy1;
+    } else if (sy1 != cached1) {
+      hresize(sy1, row1);
+      cached1 = sy1;
+    }
+    uint8_t* D = dst + (size_t)dy * dstep;
+    for (int x = 0; x < dw; x++) {
+      int v = (((b0 * (row0[x] >> 4)) >> 16) + ((b1 * (row1[x] >> 4)) >> 16) + 2) >> 2;
+      D[x] = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+    }
+  }
+}
+
+/* cv::borderInterpolate(p, len, BORDER_REFLECT_101) */
+inline int reflect101(int p, int len) {
+  if ((unsigned)p < (unsigned)len) return p;
+  if (len == 1) return 0;
+  do {
+    if (p < 0)
+      p = -p;
+    else
+      p = 2 * (len - 1) - p;
+  } while ((unsigned)p >= (unsigned)len);
+  return p;
+}
+
+void copy_make_border_reflect101(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep, int b) {
+  for (int y = -b; y < h + b; y++) {
+    const uint8_t* S = src + (size_t)reflect101(y, h) * sstep;
+    uint8_t* D = dst + (size_t)(y + b) * dstep;
+    for (int x = -b; x < w + b; x++) D[x + b] = S[reflect101(x, w)];
+  }
+}
+
+/* ------------------------------------------------------------------ cv::FAST TYPE_9_16 */
+const int kRingDx[16] = {0, 1, 2, 3, 3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1};
+const int kRingDy[16] = {3, 3, 2, 1, 0, -1, -2, -3, -3, -3, -2, -1, 0, 1, 2, 3};
+
+/* features2d/fast_score.cpp cornerScore<16>: largest threshold for which the pixel stays a corner. */
+inline int corner_score16(const uint8_t* p, const int* ofs, int threshold) {
+  int d[25];
+  const int v = p[0];
+  for (int k = 0; k < 25; k++) d[k] = v - p[ofs[k & 15]];
+  int a0 = threshold;
+  for (int k = 0; k < 16; k += 2) {
+    int a = std::min(d[k + 1], d[k + 2]);
+    a = std::min(a, d[k + 3]);
+    if (a <= a0) continue;
+    a = std::min(a, d[k + 4]);
+    a = std::min(a, d[k + 5]);
+    a = std::min(a, d[k + 6]);
+    a = std::min(a, d[k + 7]);
+    a = std::min(a, d[k + 8]);
+    a0 = std::max(a0, std::min(a, d[k]));
+    a0 = std::max(a0, std::min(a, d[k + 9]));
+  }
+  int b0 = -a0;
+  for (int k = 0; k < 16; k += 2) {
+    int b = std::max(d[k + 1], d[k + 2]);
+    b = std::max(b, d[k + 3]);
+    b = std::max(b, d[k + 4]);
+    b = std::max(b, d[k + 5]);
+    if (b >= b0) continue;
+    b = std::max(b, d[k + 6]);
+    b = std::max(b, d[k + 7]);
+    b = std::max(b, d[k + 8]);
+    b0 = std::min(b0, std::max(b, d[k]));
+    b0 = std::min(b0, std::max(b, d[k + 9]));
+  }
+  return -b0 - 1;
+}
+
+/* FAST-9 segment test of features2d/fast.cpp (FAST_t<16>): 9 contiguous ring pixels all darker than
+ * v-th or all brighter than v+th. */
+inline bool is_corner16(const uint8_t* p, const int* ofs, int threshold) {
+  const int v = p[0];
+  const int lo = v - threshold, hi = v + threshold;
+  int cd = 0, cb = 0;
+  for (int k = 0; k < 25; k++) {
+    const int x = p[ofs[k & 15]];
+    if (x < lo) {
+      if (++cd > 8) return true;
+    } else
+      cd = 0;
+    if (x > hi) {
+      if (++cb > 8) return true;
+    } else
+      cb = 0;
+  }
+  return false;
+}
+
+void fast_score_map(const uint8_t* img, int w, int h, size_t step, int th, uint8_t* score, size_t sstep) {
+  th = std::min(std::max(th, 0), 255);
+  for (int y = 0; y < h; y++) memset(score + (size_t)y * sstep, 0, (size_t)std::max(w, 0));
+  int ofs[16];
+  for (int k = 0; k < 16; k++) ofs[k] = kRingDy[k] * (int)step + kRingDx[k];
+  /* fast.cpp threshold_tab: 1 = darker than v-th, 2 = brighter than v+th; the antipodal-pair pretest
+   * rejects most pixels before the full segment test (same decisions, fewer loads). */
+  uint8_t tab[512];
+  for (int i = -255; i <= 255; i++) tab[i + 255] = (uint8_t)(i < -th ? 1 : i > th ? 2 : 0);
+  for (int y = 3; y < h - 3; y++)
+    for (int x = 3; x < w - 3; x++) {
+      const uint8_t* p = img + (size_t)y * step + x;
+      const uint8_t* t = tab - p[0] + 255;
+      int d = t[p[ofs[0]]] | t[p[ofs[8]]];
+      if (d == 0) continue;
+      d &= t[p[ofs[2]]] | t[p[ofs[10]]];
+      d &= t[p[ofs[4]]] | t[p[ofs[12]]];
+      d &= t[p[ofs[6]]] | t[p[ofs[14]]];
+      if (d == 0) continue;
+      d &= t[p[ofs[1]]] | t[p[ofs[9]]];
+      d &= t[p[ofs[3]]] | t[p[ofs[11]]];
+      d &= t[p[ofs[5]]] | t[p[ofs[13]]];
+      d &= t[p[ofs[7]]] | t[p[ofs[15]]];
+      if (d == 0) continue;
+      if (is_corner16(p, ofs, th)) score[(size_t)y * sstep + x] = (uint8_t)corner_score16(p, ofs, th);
+    }
+}
+
+void fast_detect(const uint8_t* img, int w, int h, size_t step, int th, bool nonmax, std::vector<orc_keypoint>& out) {
+  out.clear();
+  if (w < 7 || h < 7) return;
+  std::vector<uint8_t> score((size_t)w * h);
+  fast_score_map(img, w, h, step, th, score.data(), (size_t)w);
+  /* corner flags must be tracked separately from the score: a corner whose score is 0 (only possible
+   * for th == 0) is still a corner, and never survives the strict '>' non-max test. */
+  th = std::min(std::max(th, 0), 255);
+  int ofs[16];
+  for (int k = 0; k < 16; k++) ofs[k] = kRingDy[k] * (int)step + kRingDx[k];
+  for (int y = 3; y < h - 3; y++) {
+    const uint8_t* pr = &score[(size_t)(y - 1) * w];
+    const uint8_t* cr = &score[(size_t)y * w];
+    const uint8_t* nr = &score[(size_t)(y + 1) * w];
+    for (int x = 3; x < w - 3; x++) {
+      const int s = cr[x];
+      bool keep;
+      if (s == 0) {
+        if (nonmax || !is_corner16(img + (size_t)y * step + x, ofs, th)) continue;
+        keep = true;
+      } else {
+        keep = !nonmax || (s > cr[x + 1] && s > cr[x - 1] && s > pr[x - 1] && s > pr[x] && s > pr[x + 1] &&
+                           s > nr[x - 1] && s > nr[x] && s > nr[x + 1]);
+      }
+      /* without non-max suppression OpenCV never computes the score: response stays 0 */
+      if (keep) out.push_back(orc_keypoint{(float)x, (float)y, 7.f, -1.f, nonmax ? (float)s : 0.f, 0, -1});
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ KeyPointsFilter::retainBest */
+struct ResponseGreater {
+  bool operator()(const orc_keypoint& a, const orc_keypoint& b) const { return a.response > b.response; }
+};
+void retain_best(std::vector<orc_keypoint>& v, int n) {
+  if (n >= 0 && v.size() > (size_t)n) {
+    if (n == 0) {
+      v.clear();
+      return;
+    }
+    std::nth_element(v.begin(), v.begin() + n - 1, v.end(), ResponseGreater());
+    const float ambiguous = v[n - 1].response;
+    auto new_end = std::partition(v.begin() + n, v.end(), [ambiguous](const orc_keypoint& k) { return k.response >= ambiguous; });
+    v.resize(new_end - v.begin());
+  }
+}
+
+/* ------------------------------------------------------------------ cv::fastAtan2 (scalar, degrees) */
+float fast_atan2(float y, float x) {
+  static const float scale = (float)(180 / 3.1415926535897932384626433832795);
+  static const float p1 = 0.9997878412794807f * scale, p3 = -0.3258083974640975f * scale,
+                     p5 = 0.1555786518463281f * scale, p7 = -0.04432655554792128f * scale;
+  const float ax = std::fabs(x), ay = std::fabs(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = ay / (ax + (float)DBL_EPSILON);
+    c2 = c * c;
+    a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  } else {
+    c = ax / (ay + (float)DBL_EPSILON);
+    c2 = c * c;
+    a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+  }
+  if (x < 0) a = 180.f - a;
+  if (y < 0) a = 360.f - a;
+  return a;
+}
+
+/* ------------------------------------------------------------------ cv::GaussianBlur 7x7 sigma 2, 8U */
+/* OpenCV 4.x 8U path: fixed-point separable filter, 8.8 kernel {18,34,48,56,48,34,18}/256,
+ * horizontal pass kept in 16 bits, vertical pass in 32 bits, one rounding at the end. */
+void gaussian_blur_7x7_s2(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep) {
+  static const int k[7] = {18, 34, 48, 56, 48, 34, 18};
+  if (w <= 0 || h <= 0) return;
+  std::vector<uint32_t> hbuf((size_t)w * h);
+  for (int y = 0; y < h; y++) {
+    const uint8_t* S = src + (size_t)y * sstep;
+    for (int x = 0; x < w; x++) {
+      uint32_t acc = 0;
+      for (int i = 0; i < 7; i++) acc += k[i] * S[reflect101(x + i - 3, w)];
+      hbuf[(size_t)y * w + x] = acc;
+    }
+  }
+  for (int y = 0; y < h; y++) {
+    uint8_t* D = dst + (size_t)y * dstep;
+    const uint32_t* r[7];
+    for (int j = 0; j < 7; j++) r[j] = &hbuf[(size_t)reflect101(y + j - 3, h) * w];
+    for (int x = 0; x < w; x++) {
+      uint32_t acc = 0;
+      for (int j = 0; j < 7; j++) acc += k[j] * r[j][x];
+      D[x] = (uint8_t)((acc + 32768u) >> 16);
+    }
+  }
+}
+
+/* ------------------------------------------------------------------ glibc sincosf, restated */
+/* glibc 2.39 sysdeps/ieee754/flt-32/s_sincosf.c (the ARM optimized-routines algorithm): double
+ * polynomial after a fast range reduction by pi/2.  Only the |x| < 120 paths are needed: the argument
+ * is angle*pi/180 with angle in [0, 360].  Written with plain double mul/add (no contraction). */
+struct SinCosTab {
+  double sign[4];
+  double hpi_inv, hpi, c0, c1, c2, c3, c4, s1, s2, s3;
+};
+const SinCosTab kSinCos[2] = {
+    {{1.0, -1.0, -1.0, 1.0}, 0x1.45F306DC9C883p+23, 0x1.921FB54442D18p0, 0x1p0, -0x1.ffffffd0c621cp-2,
+     0x1.55553e1068f19p-5, -0x1.6c087e89a359dp-10, 0x1.99343027bf8c3p-16, -0x1.555545995a603p-3,
+     0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13},
+    {{1.0, -1.0, -1.0, 1.0}, 0x1.45F306DC9C883p+23, 0x1.921FB54442D18p0, -0x1p0, 0x1.ffffffd0c621cp-2,
+     -0x1.55553e1068f19p-5, 0x1.6c087e89a359dp-10, -0x1.99343027bf8c3p-16, -0x1.555545995a603p-3,
+     0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13}};
+
+inline uint32_t abstop12(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  return (u >> 20) & 0x7ff;
+}
+
+inline void sincosf_poly(double x, double x2, const SinCosTab* p, int n, float* sinp, float* cosp) {
+  const double x4 = x2 * x2;
+  const double x3 = x2 * x;
+  const double c2 = p->c3 + x2 * p->c4;
+  const double s1 = p->s2 + x2 * p->s3;
+  float* tmp = (n & 1) ? cosp : sinp;
+  cosp = (n & 1) ? sinp : cosp;
+  sinp = tmp;
+  const double c1 = p->c0 + x2 * p->c1;
+  const double x5 = x3 * x2;
+  const double x6 = x4 * x2;
+  const double s = x + x3 * p->s1;
+  const double c = c1 + x4 * p->c2;
+  *sinp = (float)(s + x5 * s1);
+  *cosp = (float)(c + x6 * c2);
+}
+
+void sincosf_restated(float y, float* sinp, float* cosp) {
+  double x = y;
+  const SinCosTab* p = &kSinCos[0];
+  if (abstop12(y) < abstop12(0x1.921FB6p-1f)) { /* |y| < pi/4 */
+    const double x2 = x * x;
+    if (abstop12(y) < abstop12(0x1p-12f)) {
+      *sinp = y;
+      *cosp = 1.0f;
+      return;
+    }
+    sincosf_poly(x, x2, p, 0, sinp, cosp);
+  } else if (abstop12(y) < abstop12(120.0f)) {
+    const double r = x * p->hpi_inv;
+    const int n = ((int32_t)r + 0x800000) >> 24;
+    x = x - n * p->hpi;
+    const double s = p->sign[n & 3];
+    if (n & 2) p = &kSinCos[1];
+    sincosf_poly(x * s, x * x, p, n, sinp, cosp);
+  } else {
+    sincosf(y, sinp, cosp); /* outside the range the extractor can produce */
+  }
+}
+
+/* ------------------------------------------------------------------ the extractor */
+const int PATCH_SIZE = 31;
+const int HALF_PATCH_SIZE = 15;
+const int EDGE_THRESHOLD = 19;
+
+const int8_t kPattern[1024] = {
+#include "orb_pattern.inc"
+};
+
+}  // namespace
+
+struct orc_extractor {
+  int nfeatures;
+  double scaleFactor; /* the member is a double initialised from a float (src/ORBextractor.h:78) */
+  int nlevels;
+  int thFAST;
+  std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
+  std::vector<int> mnFeaturesPerLevel, umax;
+};
+
+namespace {
+
+/* src/ORBextractor.cc:406-457 */
+void build_tables(orc_extractor& e) {
+  const int nlevels = e.nlevels;
+  e.mvScaleFactor.resize(nlevels);
+  e.mvLevelSigma2.resize(nlevels);
+  e.mvScaleFactor[0] = 1.0f;
+  e.mvLevelSigma2[0] = 1.0f;
+  for (int i = 1; i < nlevels; i++) {
+    e.mvScaleFactor[i] = (float)(e.mvScaleFactor[i - 1] * e.scaleFactor);
+    e.mvLevelSigma2[i] = e.mvScaleFactor[i] * e.mvScaleFactor[i];
+  }
+  e.mvInvScaleFactor.resize(nlevels);
+  e.mvInvLevelSigma2.resize(nlevels);
+  for (int i = 0; i < nlevels; i++) {
+    e.mvInvScaleFactor[i] = 1.0f / e.mvScaleFactor[i];
+    e.mvInvLevelSigma2[i] = 1.0f / e.mvLevelSigma2[i];
+  }
+  e.mnFeaturesPerLevel.resize(nlevels);
+  float factor = (float)(1.0f / e.scaleFactor);
+  float nDesiredFeaturesPerScale = e.nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)nlevels));
+  int sumFeatures = 0;
+  for (int level = 0; level < nlevels - 1; level++) {
+    e.mnFeaturesPerLevel[level] = cv_round(nDesiredFeaturesPerScale);
+    sumFeatures += e.mnFeaturesPerLevel[level];
+    nDesiredFeaturesPerScale *= factor;
+  }
+  e.mnFeaturesPerLevel[nlevels - 1] = std::max(e.nfeatures - sumFeatures, 0);
+
+  e.umax.resize(HALF_PATCH_SIZE + 1);
+  int v, v0, vmax = cv_floor(HALF_PATCH_SIZE * sqrt(2.f) / 2 + 1);
+  int vmin = cv_ceil(HALF_PATCH_SIZE * sqrt(2.f) / 2);
+  const double hp2 = HALF_PATCH_SIZE * HALF_PATCH_SIZE;
+  for (v = 0; v <= vmax; ++v) e.umax[v] = cv_round(sqrt(hp2 - v * v));
+  for (v = HALF_PATCH_SIZE, v0 = 0; v >= vmin; --v) {
+    while (e.umax[v0] == e.umax[v0 + 1]) ++v0;
+    e.umax[v] = v0;
+    ++v0;
+  }
+}
+
+struct Image {
+  std::vector<uint8_t> buf; /* padded by EDGE_THRESHOLD on every side, like the reference's temp Mat */
+  int w = 0, h = 0;
+  size_t step = 0;
+  uint8_t* inner() { return buf.data() + EDGE_THRESHOLD * step + EDGE_THRESHOLD; }
+  const uint8_t* inner() const { return buf.data() + EDGE_THRESHOLD * step + EDGE_THRESHOLD; }
+};
+
+void level_size(const orc_extractor& e, int level, int w0, int h0, int* w, int* h) {
+  const float scale = e.mvInvScaleFactor[level];
+  *w = cv_round((float)w0 * scale);
+  *h = cv_round((float)h0 * scale);
+}
+
+/* src/ORBextractor.cc:680-700 */
+/* Returns false where cv::resize would throw (a level of zero width or height). */
+bool compute_pyramid(const orc_extractor& e, const uint8_t* img, int w0, int h0, size_t step0, std::vector<Image>& pyr) {
+  pyr.resize(e.nlevels);
+  for (int level = 0; level < e.nlevels; ++level) {
+    Image& L = pyr[level];
+    level_size(e, level, w0, h0, &L.w, &L.h);
+    L.step = (size_t)std::max(L.w, 0) + 2 * EDGE_THRESHOLD;
+    L.buf.assign(L.step * ((size_t)std::max(L.h, 0) + 2 * EDGE_THRESHOLD), 0);
+    if (L.w <= 0 || L.h <= 0) return false;
+    if (level != 0) {
+      const Image& P = pyr[level - 1];
+      resize_linear_8u(P.inner(), P.w, P.h, P.step, L.inner(), L.w, L.h, L.step);
+      copy_make_border_reflect101(L.inner(), L.w, L.h, L.step, L.buf.data(), L.step, EDGE_THRESHOLD);
+    } else {
+      copy_make_border_reflect101(img, w0, h0, step0, L.buf.data(), L.step, EDGE_THRESHOLD);
+    }
+  }
+  return true;
+}
+
+/* src/ORBextractor.cc:78-102 */
+float ic_angle(const uint8_t* center, int step, const std::vector<int>& u_max) {
+  int m_01 = 0, m_10 = 0;
+  for (int u = -HALF_PATCH_SIZE; u <= HALF_PATCH_SIZE; ++u) m_10 += u * center[u];
+  for (int v = 1; v <= HALF_PATCH_SIZE; ++v) {
+    int v_sum = 0;
+    const int d = u_max[v];
+    for (int u = -d; u <= d; ++u) {
+      const int val_plus = center[u + v * step], val_minus = center[u - v * step];
+      v_sum += (val_plus - val_minus);
+      m_10 += u * (val_plus + val_minus);
+    }
+    m_01 += v * v_sum;
+  }
+  return fast_atan2((float)m_01, (float)m_10);
+}
+
+/* The reference evaluates  cvRound(px*b + py*a)  and  cvRound(px*a - py*b)  in float
+ * (src/ORBextractor.cc:115-117).  Built with its own flags (-O3 -march=native, CMakeLists.txt:39-40)
+ * on an FMA host g++ contracts these to fma(px, b, py*a) and fma(px, a, -(py*b)); that form is frozen
+ * here (tests/test_oracle_primitives.py compiles the verbatim expression with those flags and compares). */
+inline void pattern_rotate(int px, int py, float a, float b, int* drow, int* dcol) {
+  const float fx = (float)px, fy = (float)py;
+  *drow = cv_round(fmaf(fx, b, fy * a));
+  *dcol = cv_round(fmaf(fx, a, -(fy * b)));
+}
+
+const float kFactorPI = (float)(3.1415926535897932384626433832795 / 180.f);
+
+/* src/ORBextractor.cc:105-143 */
+void orb_descriptor(const orc_keypoint& kpt, const uint8_t* img, int step, uint8_t* desc) {
+  const float angle = kpt.angle * kFactorPI;
+  float a, b;
+  sincosf(angle, &b, &a); /* a = cos, b = sin: g++ merges the reference's cos()/sin() pair into sincosf */
+  const uint8_t* center = img + (ptrdiff_t)cv_round(kpt.y) * step + cv_round(kpt.x);
+  const int8_t* pat = kPattern;
+  for (int i = 0; i < 32; ++i, pat += 32) {
+    int val = 0;
+    for (int bit = 0; bit < 8; ++bit) {
+      int r0, c0, r1, c1;
+      pattern_rotate(pat[4 * bit + 0], pat[4 * bit + 1], a, b, &r0, &c0);
+      pattern_rotate(pat[4 * bit + 2], pat[4 * bit + 3], a, b, &r1, &c1);
+      const int t0 = center[r0 * step + c0], t1 = center[r1 * step + c1];
+      val |= (t0 < t1) << bit;
+    }
+    desc[i] = (uint8_t)val;
+  }
+}
+
+struct LevelGrid {
+  int nDesired, levelCols, levelRows, W, H, cellW, cellH, nCells, nfeaturesCell, scaledPatchSize;
+};
+
+/* src/ORBextractor.cc:469-488, 580.  levelCols==0 makes the reference divide by zero and convert inf to
+ * int (undefined, but harmless: its loops then run zero times); such a level simply yields nothing. */
+LevelGrid level_grid(const orc_extractor& e, int level, int w0, int h0, int lw, int lh) {
+  LevelGrid g{};
+  const float imageRatio = (float)w0 / h0;
+  g.nDesired = e.mnFeaturesPerLevel[level];
+  g.levelCols = (int)std::sqrt((float)g.nDesired / (5 * imageRatio));
+  g.levelRows = (int)(imageRatio * g.levelCols);
+  g.W = (lw - EDGE_THRESHOLD) - EDGE_THRESHOLD;
+  g.H = (lh - EDGE_THRESHOLD) - EDGE_THRESHOLD;
+  g.nCells = g.levelRows * g.levelCols;
+  if (g.levelCols > 0 && g.levelRows > 0) {
+    g.cellW = (int)std::ceil((float)g.W / g.levelCols);
+    g.cellH = (int)std::ceil((float)g.H / g.levelRows);
+    g.nfeaturesCell = (int)std::ceil((float)g.nDesired / g.nCells);
+  }
+  g.scaledPatchSize = (int)(PATCH_SIZE * e.mvScaleFactor[level]);
+  return g;
+}
+
+/* src/ORBextractor.cc:466-610.  Returns false when a cell ROI leaves the level image (cv::Exception). */
+bool compute_keypoints(const orc_extractor& e, const std::vector<Image>& pyr, int w0, int h0,
+                       std::vector<std::vector<orc_keypoint>>& all, orc_dump* dump, int* raw_cell_pos, int* raw_kp_pos) {
+  all.assign(e.nlevels, {});
+  for (int level = 0; level < e.nlevels; ++level) {
+    const Image& L = pyr[level];
+    const LevelGrid g = level_grid(e, level, w0, h0, L.w, L.h);
+    const int levelRows = g.levelRows, levelCols = g.levelCols;
+    if (levelRows <= 0 || levelCols <= 0) continue;
+    const int nCells = g.nCells, nfeaturesCell = g.nfeaturesCell, cellW = g.cellW, cellH = g.cellH;
+    const int minBorderX = EDGE_THRESHOLD, minBorderY = EDGE_THRESHOLD;
+    const int maxBorderX = L.w - EDGE_THRESHOLD, maxBorderY = L.h - EDGE_THRESHOLD;
+
+    std::vector<std::vector<orc_keypoint>> cellKeyPoints((size_t)nCells);
+    std::vector<int> nToRetain(nCells, 0), nTotal(nCells, 0);
+    std::vector<char> bNoMore(nCells, 0);
+    std::vector<int> iniXCol(levelCols), iniYRow(levelRows);
+    int nNoMore = 0, nToDistribute = 0;
+
+    float hY = (float)(cellH + 6);
+    for (int i = 0; i < levelRows; i++) {
+      const float iniY = (float)(minBorderY + i * cellH - 3);
+      iniYRow[i] = (int)iniY;
+      if (i == levelRows - 1) {
+        hY = maxBorderY + 3 - iniY;
+        if (hY <= 0) continue;
+      }
+      float hX = (float)(cellW + 6);
+      for (int j = 0; j < levelCols; j++) {
+        float iniX;
+        if (i == 0) {
+          iniX = (float)(minBorderX + j * cellW - 3);
+          iniXCol[j] = (int)iniX;
+        } else {
+          iniX = (float)iniXCol[j];
+        }
+        if (j == levelCols - 1) {
+          hX = maxBorderX + 3 - iniX;
+          if (hX <= 0) continue;
+        }
+        const int y0 = (int)iniY, y1 = (int)(iniY + hY), x0 = (int)iniX, x1 = (int)(iniX + hX);
+        /* Mat::rowRange / colRange assertions */
+        if (!(0 <= y0 && y0 <= y1 && y1 <= L.h && 0 <= x0 && x0 <= x1 && x1 <= L.w)) return false;
+        /* A non-empty cell whose detectable rectangle passes maxBorder (possible only when
+         * (levelRows-1)*cellH > H, i.e. a level a few pixels larger than the border) yields keypoints
+         * whose rotated pattern is read outside the blurred level image: undefined behaviour in the
+         * reference, so no result is defined.  Reported as a geometry error as well. */
+        if (x1 - x0 >= 7 && y1 - y0 >= 7 && (x1 - 3 > maxBorderX || y1 - 3 > maxBorderY)) return false;
+        std::vector<orc_keypoint>& cell = cellKeyPoints[(size_t)i * levelCols + j];
+        fast_detect(L.inner() + (size_t)y0 * L.step + x0, x1 - x0, y1 - y0, L.step, e.thFAST, true, cell);
+        const int nKeys = (int)cell.size();
+        nTotal[i * levelCols + j] = nKeys;
+        if (nKeys > nfeaturesCell) {
+          nToRetain[i * levelCols + j] = nfeaturesCell;
+          bNoMore[i * levelCols + j] = 0;
+        } else {
+          nToRetain[i * levelCols + j] = nKeys;
+          nToDistribute += nfeaturesCell - nKeys;
+          bNoMore[i * levelCols + j] = 1;
+          nNoMore++;
+        }
+      }
+    }
+
+    const int cell_base = *raw_cell_pos;
+    *raw_cell_pos += nCells;
+    if (dump) {
+      for (int c = 0; c < nCells; c++) {
+        if (dump->raw_cell_count && cell_base + c < dump->raw_cell_cap) dump->raw_cell_count[cell_base + c] = nTotal[c];
+        for (const orc_keypoint& k : cellKeyPoints[c]) {
+          if (dump->raw_kps && *raw_kp_pos < dump->raw_kps_cap) dump->raw_kps[*raw_kp_pos] = k;
+          ++*raw_kp_pos;
+        }
+      }
+    }
+
+    while (nToDistribute > 0 && nNoMore < nCells) {
+      const int nNewFeaturesCell = nfeaturesCell + (int)std::ceil((float)nToDistribute / (nCells - nNoMore));
+      nToDistribute = 0;
+      for (int c = 0; c < nCells; c++) {
+        if (!bNoMore[c]) {
+          if (nTotal[c] > nNewFeaturesCell) {
+            nToRetain[c] = nNewFeaturesCell;
+            bNoMore[c] = 0;
+          } else {
+            nToRetain[c] = nTotal[c];
+            nToDistribute += nNewFeaturesCell - nTotal[c];
+            bNoMore[c] = 1;
+            nNoMore++;
+          }
+        }
+      }
+    }
+    if (dump && dump->n_to_retain)
+      for (int c = 0; c < nCells; c++)
+        if (cell_base + c < dump->n_to_retain_cap) dump->n_to_retain[cell_base + c] = nToRetain[c];
+
+    std::vector<orc_keypoint>& keypoints = all[level];
+    keypoints.reserve((size_t)std::max(g.nDesired, 0) * 2);
+    for (int i = 0; i < levelRows; i++)
+      for (int j = 0; j < levelCols; j++) {
+        std::vector<orc_keypoint>& keysCell = cellKeyPoints[(size_t)i * levelCols + j];
+        retain_best(keysCell, nToRetain[i * levelCols + j]);
+        if ((int)keysCell.size() > nToRetain[i * levelCols + j]) keysCell.resize(nToRetain[i * levelCols + j]);
+        for (orc_keypoint& k : keysCell) {
+          k.x += iniXCol[j];
+          k.y += iniYRow[i];
+          k.octave = level;
+          k.size = (float)g.scaledPatchSize;
+          keypoints.push_back(k);
+        }
+      }
+    if ((int)keypoints.size() > g.nDesired) {
+      retain_best(keypoints, g.nDesired);
+      keypoints.resize(g.nDesired);
+    }
+  }
+  for (int level = 0; level < e.nlevels; ++level) {
+    const Image& L = pyr[level];
+    for (orc_keypoint& k : all[level])
+      k.angle = ic_angle(L.inner() + (ptrdiff_t)cv_round(k.y) * L.step + cv_round(k.x), (int)L.step, e.umax);
+  }
+  return true;
+}
+
+/* src/ORBextractor.cc:620-678 */
+int extract(const orc_extractor& e, const uint8_t* img, int w, int h, size_t step, orc_keypoint* kps, uint8_t* desc,
+            int cap, orc_dump* dump) {
+  if (!img || w <= 0 || h <= 0) return 0;
+  std::vector<Image> pyr;
+  if (!compute_pyramid(e, img, w, h, step, pyr)) return -1;
+  if (dump && dump->pyramid) {
+    uint8_t* o = dump->pyramid;
+    for (const Image& L : pyr)
+      for (int y = 0; y < L.h; y++, o += L.w) memcpy(o, L.inner() + (size_t)y * L.step, (size_t)L.w);
+  }
+  std::vector<std::vector<orc_keypoint>> all;
+  int raw_cell_pos = 0, raw_kp_pos = 0;
+  if (!compute_keypoints(e, pyr, w, h, all, dump, &raw_cell_pos, &raw_kp_pos)) return -1;
+  if (dump) dump->raw_kps_total = raw_kp_pos;
+
+  int n = 0;
+  uint8_t* bo = dump ? dump->blurred : nullptr;
+  for (int level = 0; level < e.nlevels; ++level) {
+    std::vector<orc_keypoint>& keypoints = all[level];
+    const Image& L = pyr[level];
+    if (dump && dump->level_count) dump->level_count[level] = (int)keypoints.size();
+    std::vector<uint8_t> work;
+    if (!keypoints.empty() || bo) {
+      work.resize((size_t)std::max(L.w, 0) * std::max(L.h, 0));
+      if (L.w > 0 && L.h > 0) gaussian_blur_7x7_s2(L.inner(), L.w, L.h, L.step, work.data(), (size_t)L.w);
+      if (bo) {
+        memcpy(bo, work.data(), work.size());
+        bo += work.size();
+      }
+    }
+    if (keypoints.empty()) continue;
+    const float scale = e.mvScaleFactor[level];
+    for (orc_keypoint& k : keypoints) {
+      uint8_t d[32];
+      orb_descriptor(k, work.data(), L.w, d);
+      if (level != 0) {
+        k.x *= scale;
+        k.y *= scale;
+      }
+      if (n < cap) {
+        if (kps) kps[n] = k;
+        if (desc) memcpy(desc + (size_t)n * 32, d, 32);
+      }
+      ++n;
+    }
+  }
+  return n;
+}
+
+inline int descriptor_distance(const uint8_t* a, const uint8_t* b) {
+  /* src/ORBmatcher.cc:1459-1473, verbatim arithmetic */
+  int dist = 0;
+  for (int i = 0; i < 8; i++) {
+    uint32_t wa, wb;
+    memcpy(&wa, a + 4 * i, 4);
+    memcpy(&wb, b + 4 * i, 4);
+    unsigned int v = wa ^ wb;
+    v = v - ((v >> 1) & 0x55555555);
+    v = (v & 0x33333333) + ((v >> 2) & 0x33333333);
+    dist += (((v + (v >> 4)) & 0xF0F0F0F) * 0x1010101) >> 24;
+  }
+  return dist;
+}
+
+void match_best2(const uint8_t* A, int nA, const uint8_t* B, int nB, float ratio, int th_low, orc_match* out,
+                 bool greedy) {
+  std::vector<char> matched((size_t)std::max(nB, 0), 0);
+  for (int i = 0; i < nA; i++) {
+    int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+    for (int j = 0; j < nB; j++) {
+      if (greedy && matched[j]) continue;
+      const int dist = descriptor_distance(A + (size_t)i * 32, B + (size_t)j * 32);
+      if (dist < bestDist1) {
+        bestDist2 = bestDist1;
+        bestDist1 = dist;
+        bestIdx2 = j;
+      } else if (dist < bestDist2) {
+        bestDist2 = dist;
+      }
+    }
+    int ok = 0;
+    if (bestDist1 < th_low && (float)bestDist1 < ratio * (float)bestDist2) {
+      ok = 1;
+      if (greedy) matched[bestIdx2] = 1;
+    }
+    out[i] = orc_match{bestIdx2, bestDist1, bestDist2, ok};
+  }
+}
+
+template <class F>
+void parallel_for(int n, int nthreads, F f) {
+  nthreads = std::max(1, std::min(nthreads, n));
+  if (nthreads == 1) {
+    for (int i = 0; i < n; i++) f(i);
+    return;
+  }
+  std::atomic<int> next(0);
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++)
+    th.emplace_back([&] {
+      for (int i; (i = next.fetch_add(1)) < n;) f(i);
+    });
+  for (auto& t : th) t.join();
+}
+
+}  // namespace
+
+/* ================================================================== C interface */
+extern "C" {
+
+void orc_resize_linear_8u(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh, size_t dstep) {
+  resize_linear_8u(src, sw, sh, sstep, dst, dw, dh, dstep);
+}
+void orc_copy_make_border_reflect101(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep, int border) {
+  copy_make_border_reflect101(src, w, h, sstep, dst, dstep, border);
+}
+int orc_fast(const uint8_t* img, int w, int h, size_t step, int th, int nonmax, orc_keypoint* out, int cap) {
+  std::vector<orc_keypoint> v;
+  fast_detect(img, w, h, step, th, nonmax != 0, v);
+  for (int i = 0; i < (int)v.size() && i < cap; i++) out[i] = v[i];
+  return (int)v.size();
+}
+void orc_fast_score_map(const uint8_t* img, int w, int h, size_t step, int th, uint8_t* score, size_t score_step) {
+  fast_score_map(img, w, h, step, th, score, score_step);
+}
+void orc_gaussian_blur_7x7_s2(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep) {
+  gaussian_blur_7x7_s2(src, w, h, sstep, dst, dstep);
+}
+float orc_fast_atan2(float y, float x) { return fast_atan2(y, x); }
+int orc_retain_best(orc_keypoint* kps, int count, int n) {
+  std::vector<orc_keypoint> v(kps, kps + count);
+  retain_best(v, n);
+  std::copy(v.begin(), v.end(), kps);
+  return (int)v.size();
+}
+int orc_retain_best_idx(const float* response, int count, int n, int32_t* order_out) {
+  std::vector<orc_keypoint> v((size_t)count);
+  for (int i = 0; i < count; i++) v[i] = orc_keypoint{0, 0, 0, 0, response[i], 0, i};
+  retain_best(v, n);
+  for (size_t i = 0; i < v.size(); i++) order_out[i] = v[i].class_id;
+  return (int)v.size();
+}
+void orc_sincosf_restated(float x, float* s, float* c) { sincosf_restated(x, s, c); }
+uint64_t orc_sincosf_mismatches(uint32_t lo_bits, uint32_t hi_bits, int nthreads) {
+  nthreads = std::max(1, nthreads);
+  std::atomic<uint64_t> bad(0);
+  const uint64_t total = (uint64_t)hi_bits - lo_bits + 1;
+  const int chunks = nthreads * 16;
+  parallel_for(chunks, nthreads, [&](int c) {
+    const uint64_t b = lo_bits + total * c / chunks, e = lo_bits + total * (c + 1) / chunks;
+    uint64_t local = 0;
+    for (uint64_t u = b; u < e; u++) {
+      const uint32_t bits = (uint32_t)u;
+      float x, s0, c0, s1, c1;
+      memcpy(&x, &bits, 4);
+      sincosf(x, &s0, &c0);
+      sincosf_restated(x, &s1, &c1);
+      local += (memcmp(&s0, &s1, 4) != 0) || (memcmp(&c0, &c1, 4) != 0);
+    }
+    bad += local;
+  });
+  return bad.load();
+}
+void orc_pattern_rotate(int px, int py, float a, float b, int* drow, int* dcol) { pattern_rotate(px, py, a, b, drow, dcol); }
+
+orc_extractor* orc_create(const orc_params* p) {
+  if (!p || p->nlevels <= 0 || p->nfeatures < 0) return nullptr;
+  orc_extractor* e = new orc_extractor;
+  e->nfeatures = p->nfeatures;
+  e->scaleFactor = p->scale_factor;
+  e->nlevels = p->nlevels;
+  e->thFAST = p->th_fast;
+  build_tables(*e);
+  return e;
+}
+void orc_destroy(orc_extractor* e) { delete e; }
+void orc_get_tables(const orc_extractor* e, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int* n_per_level, int* umax) {
+  for (int i = 0; i < e->nlevels; i++) {
+    if (scale) scale[i] = e->mvScaleFactor[i];
+    if (inv_scale) inv_scale[i] = e->mvInvScaleFactor[i];
+    if (sigma2) sigma2[i] = e->mvLevelSigma2[i];
+    if (inv_sigma2) inv_sigma2[i] = e->mvInvLevelSigma2[i];
+    if (n_per_level) n_per_level[i] = e->mnFeaturesPerLevel[i];
+  }
+  if (umax)
+    for (int i = 0; i <= HALF_PATCH_SIZE; i++) umax[i] = e->umax[i];
+}
+void orc_level_geometry(const orc_extractor* e, int w, int h, orc_level_geom* out) {
+  for (int l = 0; l < e->nlevels; l++) {
+    int lw, lh;
+    level_size(*e, l, w, h, &lw, &lh);
+    const LevelGrid g = level_grid(*e, l, w, h, lw, lh);
+    out[l] = orc_level_geom{lw, lh, g.nDesired, g.levelCols, g.levelRows, g.cellW, g.cellH, g.nfeaturesCell, g.scaledPatchSize};
+  }
+}
+int orc_extract(const orc_extractor* e, const uint8_t* img, int w, int h, size_t step, orc_keypoint* kps, uint8_t* desc,
+                int cap, orc_dump* dump) {
+  return extract(*e, img, w, h, step, kps, desc, cap, dump);
+}
+long orc_extract_many(const orc_extractor* e, const uint8_t* imgs, int nframes, int w, int h, int nthreads,
+                      orc_keypoint* kps, uint8_t* desc, int32_t* counts, int cap) {
+  std::atomic<long> total(0);
+  parallel_for(nframes, nthreads, [&](int f) {
+    std::vector<orc_keypoint> k((size_t)cap);
+    std::vector<uint8_t> d((size_t)cap * 32);
+    const int n = extract(*e, imgs + (size_t)f * w * h, w, h, (size_t)w, k.data(), d.data(), cap, nullptr);
+    const int m = std::max(0, std::min(n, cap));
+    if (kps) std::copy(k.begin(), k.begin() + m, kps + (size_t)f * cap);
+    if (desc) memcpy(desc + (size_t)f * cap * 32, d.data(), (size_t)m * 32);
+    if (counts) counts[f] = n;
+    total += std::max(n, 0);
+  });
+  return total.load();
+}
+
+int orc_descriptor_distance(const uint8_t* a, const uint8_t* b) { return descriptor_distance(a, b); }
+void orc_match_best2(const uint8_t* A, int nA, const uint8_t* B, int nB, float ratio, int th_low, orc_match* out) {
+  match_best2(A, nA, B, nB, ratio, th_low, out, false);
+}
+void orc_match_greedy(const uint8_t* A, int nA, const uint8_t* B, int nB, float ratio, int th_low, orc_match* out) {
+  match_best2(A, nA, B, nB, ratio, th_low, out, true);
+}
+void orc_match_many(const uint8_t* A, const int32_t* nA, const uint8_t* B, const int32_t* nB, int npairs, int strideA_rows,
+                    int strideB_rows, float ratio, int th_low, int nthreads, orc_match* out) {
+  parallel_for(npairs, nthreads, [&](int p) {
+    match_best2(A + (size_t)p * strideA_rows * 32, nA[p], B + (size_t)p * strideB_rows * 32, nB[p], ratio, th_low,
+                out + (size_t)p * strideA_rows, false);
+  });
+}
+void orc_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out) {
+  for (int i = 0; i < nA; i++)
+    for (int j = 0; j < nB; j++) out[(size_t)i * nB + j] = (uint16_t)descriptor_distance(A + (size_t)i * 32, B + (size_t)j * 32);
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+/*
+ * sdorb_oracle.h -- C interface of the CPU oracle.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This is a CPU restatement of the reference's ORB front-end
+ * (SD-SLAM src/ORBextractor.cc, src/ORBmatcher.cc) and of the OpenCV 4.13 / glibc / libstdc++
+ * primitives it calls.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it; the product (libsdorb.so) never links, loads or calls it.
+ *
+ * Parity pin: the reference has no tests or golden vectors and cannot be
+ * compiled here (no OpenCV C++ headers).  Every primitive below is therefore pinned against the
+ * only importable implementation of the arithmetic of record, Python cv2 4.13.0
+ * (tests/test_oracle_primitives.py), and the whole operator() against an independent Python
+ * assembly of cv2 calls (tests/test_oracle_e2e.py) whose outputs are committed under
+ * tests/golden/.
+ */
+#ifndef SDORB_ORACLE_H
+#define SDORB_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Binary-compatible with cv::KeyPoint (28 bytes). */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} orc_keypoint;
+
+typedef struct {
+  int nfeatures;
+  float scale_factor;
+  int nlevels;
+  int th_fast;
+} orc_params;
+
+/* ---- OpenCV / libc primitive restatements (each validated against cv2 4.13) ---- */
+void orc_resize_linear_8u(const uint8_t* src, int sw, int sh, size_t sstep, uint8_t* dst, int dw, int dh,
+                          size_t dstep);
+void orc_copy_make_border_reflect101(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep,
+                                     int border);
+/* cv::FAST(img, kps, th, nonmax=true); returns count (may exceed cap; only cap are written). */
+int orc_fast(const uint8_t* img, int w, int h, size_t step, int th, int nonmax, orc_keypoint* out, int cap);
+/* cornerScore<16>() at every pixel that is a FAST-9 corner for `th`, else 0 (border 3 px = 0). */
+void orc_fast_score_map(const uint8_t* img, int w, int h, size_t step, int th, uint8_t* score, size_t score_step);
+void orc_gaussian_blur_7x7_s2(const uint8_t* src, int w, int h, size_t sstep, uint8_t* dst, size_t dstep);
+float orc_fast_atan2(float y, float x);
+/* KeyPointsFilter::retainBest(v, n) using the real std::nth_element / std::partition; returns new size. */
+int orc_retain_best(orc_keypoint* kps, int count, int n);
+/* Same selection on bare float responses carrying an index payload (for the introselect twin tests). */
+int orc_retain_best_idx(const float* response, int count, int n, int32_t* order_out);
+/* glibc sincosf restated in double arithmetic (what the CUDA library evaluates on device). */
+void orc_sincosf_restated(float x, float* s, float* c);
+/* Returns number of floats in [lo_bits, hi_bits] (as IEEE bit patterns) where restated != libm sincosf. */
+uint64_t orc_sincosf_mismatches(uint32_t lo_bits, uint32_t hi_bits, int nthreads);
+/* rBRIEF sample offset: (cvRound(x*b + y*a), cvRound(x*a - y*b)) with the frozen FMA contraction. */
+void orc_pattern_rotate(int px, int py, float a, float b, int* drow, int* dcol);
+
+/* ---- ORBextractor restatement ---- */
+typedef struct orc_extractor orc_extractor;
+orc_extractor* orc_create(const orc_params* p);
+void orc_destroy(orc_extractor* e);
+/* tables: each array has nlevels entries; umax has 16. Any pointer may be NULL. */
+void orc_get_tables(const orc_extractor* e, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
+                    int* n_per_level, int* umax);
+/* level geometry (ComputePyramid sizes + ComputeKeyPoints grid) for an input of w x h */
+typedef struct {
+  int width, height;       /* level image size */
+  int n_desired;           /* mnFeaturesPerLevel[level] */
+  int level_cols, level_rows;
+  int cell_w, cell_h;
+  int n_features_cell;
+  int scaled_patch_size;
+} orc_level_geom;
+void orc_level_geometry(const orc_extractor* e, int w, int h, orc_level_geom* out /* nlevels */);
+
+/* Optional stage dump of one extraction.  All pointers may be NULL (then that stage is not dumped).
+ * pyramid / blurred: tightly packed levels (width*height bytes each, level after level).
+ * raw_*: FAST keypoints per cell before any selection, in emission order (cell-local coordinates),
+ *        flattened level-major then cell row-major; raw_cell_count has one entry per cell. */
+typedef struct {
+  uint8_t* pyramid;
+  uint8_t* blurred;
+  int32_t* level_count;     /* nlevels: selected keypoints per level */
+  int32_t* raw_cell_count;  /* sum over levels of level_rows*level_cols entries */
+  int32_t raw_cell_cap;     /* capacity of raw_cell_count */
+  orc_keypoint* raw_kps;
+  int32_t raw_kps_cap;
+  int32_t raw_kps_total;    /* out */
+  int32_t n_to_retain_cap;
+  int32_t* n_to_retain;     /* same indexing as raw_cell_count */
+} orc_dump;
+
+/* ORBextractor::operator(): returns number of keypoints (<= cap written), or <0 on geometry error
+ * (the reference would throw cv::Exception for an out-of-range cell ROI).  desc: n x 32 bytes. */
+int orc_extract(const orc_extractor* e, const uint8_t* img, int w, int h, size_t step, orc_keypoint* kps,
+                uint8_t* desc, int cap, orc_dump* dump);
+/* Frame-parallel driver for the CPU baseline: frames are w*h tightly packed; returns total keypoints. */
+long orc_extract_many(const orc_extractor* e, const uint8_t* imgs, int nframes, int w, int h, int nthreads,
+                      orc_keypoint* kps /* nframes*cap or NULL */, uint8_t* desc /* or NULL */,
+                      int32_t* counts /* or NULL */, int cap);
+
+/* ---- ORBmatcher restatement ---- */
+int orc_descriptor_distance(const uint8_t* a, const uint8_t* b);
+typedef struct {
+  int32_t best_idx;   /* -1 if no candidate */
+  int32_t best_dist;  /* 256 if none */
+  int32_t second_dist;
+  int32_t accepted;   /* best_dist < th_low && (float)best_dist < ratio*(float)second_dist */
+} orc_match;
+/* For each of nA queries scan all nB train rows in ascending order with the reference update rule. */
+void orc_match_best2(const uint8_t* descA, int nA, const uint8_t* descB, int nB, float ratio, int th_low,
+                     orc_match* out);
+/* SearchByPoints-style greedy variant: train rows already matched are skipped for later queries. */
+void orc_match_greedy(const uint8_t* descA, int nA, const uint8_t* descB, int nB, float ratio, int th_low,
+                      orc_match* out);
+void orc_match_many(const uint8_t* descA, const int32_t* nA, const uint8_t* descB, const int32_t* nB, int npairs,
+                    int strideA_rows, int strideB_rows, float ratio, int th_low, int nthreads, orc_match* out);
+void orc_hamming_matrix(const uint8_t* descA, int nA, const uint8_t* descB, int nB, uint16_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
