@@ -1,0 +1,175 @@
+/*
+ * sdorb.h -- C ABI of libsdorb.so: the B200-native (sm_100a) ORB front-end of SD-SLAM.
+ *
+ * This is the drop-in boundary for ONE hot path of pasensio97/SDslam (SD-SLAM):
+ *   SD_SLAM::ORBextractor::operator()          /root/reference/src/ORBextractor.cc:620-678
+ *   SD_SLAM::ORBmatcher::DescriptorDistance    /root/reference/src/ORBmatcher.cc:1459-1473
+ *     batched in the shape of its hottest caller, the best / second-best scan of
+ *     ORBmatcher::SearchByPoints               /root/reference/src/ORBmatcher.cc:1239-1265
+ * The reference has no FFI layer; its boundary is the C++ class SD_SLAM::ORBextractor
+ * (src/ORBextractor.h:34-90).  include/ORBextractor.h re-creates that class surface on top of the
+ * functions below, so Frame / Tracking / Initializer keep compiling unchanged.
+ *
+ * Conventions: plain pointers and sizes only; every function returns SDORB_OK (0) or a negative
+ * SDORB_ERR_* code and never throws.  There is no CPU fallback: if CUDA fails the call fails.
+ * A handle owns one CUDA stream and all scratch memory; it is not re-entrant (use one handle per
+ * thread / per GPU).  Results are bit-identical to the reference on the same input bytes: keypoint
+ * x, y, size, response, octave and order; angle; descriptors; Hamming distances and match indices.
+ */
+#ifndef SDORB_H
+#define SDORB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SDORB_API __attribute__((visibility("default")))
+#else
+#define SDORB_API
+#endif
+
+#define SDORB_OK 0
+#define SDORB_ERR_BAD_ARG (-1)   /* null pointer, non-positive size, image larger than max_width/height */
+#define SDORB_ERR_CAPACITY (-2)  /* caller's output capacity is smaller than nfeatures */
+#define SDORB_ERR_CUDA (-3)      /* a CUDA call failed; see sdorb_last_cuda_error() */
+#define SDORB_ERR_GEOMETRY (-4)  /* a cell ROI leaves its level image: the reference throws cv::Exception
+                                    (or reads out of bounds) for this image size / parameter set */
+#define SDORB_ERR_NOMEM (-5)     /* device or pinned-host allocation failed */
+#define SDORB_ERR_OVERFLOW (-6)  /* an internal fixed-capacity list overflowed (results invalid) */
+#define SDORB_ERR_UNSUPPORTED (-7)
+
+/* where the image / result buffers of a batch call live */
+#define SDORB_MEM_HOST 0   /* host memory: the call copies in and out and returns when results are on the host */
+#define SDORB_MEM_DEVICE 1 /* device memory of the handle's GPU: the call only enqueues work on `stream` */
+
+typedef struct sdorb_handle sdorb_handle;
+
+/* Mirrors ORBextractor(int nfeatures, float scaleFactor, int nlevels, int thFAST)
+ * (src/ORBextractor.h:38, src/ORBextractor.cc:406-407) plus the resources of the GPU handle. */
+typedef struct {
+  int nfeatures;
+  float scale_factor;
+  int nlevels;
+  int th_fast;      /* the reference's single FAST threshold (thFAST / north-star iniThFAST) */
+  int min_th_fast;  /* -1 = reference behaviour (no fallback threshold exists in SD-SLAM).  >= 0 is the
+                       ORB-SLAM2-style mode, which this reference does not contain: SDORB_ERR_UNSUPPORTED */
+  int device;       /* CUDA device ordinal; -1 = the calling thread's current device */
+  int max_width, max_height; /* largest image the handle will be given (<= 4095 each) */
+  int max_batch;    /* frames processed per internal pass; device scratch is sized for this many */
+} sdorb_params;
+
+/* Binary-compatible with cv::KeyPoint (28 bytes): pt.x, pt.y, size, angle, response, octave, class_id. */
+typedef struct {
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+} sdorb_keypoint;
+
+/* Destination of one pyramid level (src/ORBextractor.cc:684-686: imagePyramid[l] is a view into a buffer
+ * padded by 19 px).  `data` points at the level's pixel (0,0); the callee writes width*height bytes with
+ * the given row stride and, when `border` > 0, also fills `border` pixels around it with BORDER_REFLECT_101
+ * (the caller must own that margin). */
+typedef struct {
+  uint8_t* data;
+  int width, height;
+  size_t stride;
+  int border;
+} sdorb_pyr_view;
+
+/* Result of the best / second-best scan for one query descriptor (src/ORBmatcher.cc:1239-1265). */
+typedef struct {
+  int32_t best_idx;    /* first index of the minimum distance, -1 if there was no candidate */
+  int32_t best_dist;   /* 256 if none */
+  int32_t second_dist; /* second smallest distance (may equal best_dist), 256 if none */
+  int32_t accepted;    /* best_dist < th_low && (float)best_dist < ratio * (float)second_dist */
+} sdorb_match;
+
+/* ---- lifetime ---- */
+SDORB_API int sdorb_create(const sdorb_params* params, sdorb_handle** out);
+SDORB_API void sdorb_destroy(sdorb_handle* h);
+SDORB_API const char* sdorb_strerror(int code);
+/* Text of the last CUDA error seen by this handle ("" if none). */
+SDORB_API const char* sdorb_last_cuda_error(const sdorb_handle* h);
+
+/* ---- ORBextractor getters (src/ORBextractor.h:48-70): arrays of nlevels entries, any may be NULL ---- */
+SDORB_API int sdorb_get_tables(const sdorb_handle* h, float* scale_factors, float* inv_scale_factors, float* level_sigma2,
+                     float* inv_level_sigma2, int* n_features_per_level);
+/* Upper bound of keypoints per frame = sum of the per-level targets (normally == nfeatures; the rounding of
+ * src/ORBextractor.cc:428-434 can exceed it by a few).  Output capacities must be at least this. */
+SDORB_API int sdorb_max_keypoints(const sdorb_handle* h);
+/* Size of pyramid level `level` for a width x height input (src/ORBextractor.cc:683). */
+SDORB_API int sdorb_level_size(const sdorb_handle* h, int width, int height, int level, int* level_width, int* level_height);
+
+/* ---- ORBextractor::operator() for one host image (src/ORBextractor.cc:620-678, call site src/Frame.cc:195) ----
+ * image: 8-bit gray, `stride` bytes per row.  keypoints / descriptors: caller-allocated, capacity >= nfeatures
+ * entries / rows of 32 bytes.  pyramid: NULL or nlevels views to receive the image pyramid.  Blocks until the
+ * results are in host memory.  An empty image (NULL / zero size) returns SDORB_OK with *count untouched,
+ * like the reference's early return (src/ORBextractor.cc:622-623). */
+SDORB_API int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, size_t stride,
+                  sdorb_keypoint* keypoints, uint8_t* descriptors, int capacity, int* count,
+                  const sdorb_pyr_view* pyramid);
+
+/* ---- the same operator over a batch of equally sized frames ----
+ * images: frame f starts at images + f*frame_stride, rows `row_stride` bytes apart.
+ * keypoints: [nframes][capacity]; descriptors: [nframes][capacity][32]; counts: [nframes]; capacity >= nfeatures.
+ * mem = SDORB_MEM_DEVICE: all four buffers are device pointers on the handle's GPU, work is enqueued on
+ *   `stream` (a cudaStream_t passed as void*, NULL = the handle's own stream) and the call returns without
+ *   synchronising; sdorb_batch_status() reports deferred errors after the stream is synchronised.
+ * mem = SDORB_MEM_HOST: buffers are host pointers (pinned memory gives full copy speed); the call stages
+ *   frames through the GPU in passes of max_batch, overlapping copies with kernels, and returns when all
+ *   results are on the host. */
+SDORB_API int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height,
+                        size_t row_stride, size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors,
+                        int32_t* counts, int capacity, int mem, void* stream);
+/* After synchronising: SDORB_OK, or the first deferred device-side error (SDORB_ERR_OVERFLOW / _CUDA). */
+SDORB_API int sdorb_batch_status(sdorb_handle* h);
+
+/* ---- ORBmatcher::DescriptorDistance, batched ----
+ * For pair p, every query row i < nA[p] of descA + p*strideA_rows*32 is compared against all rows j < nB[p] of
+ * descB + p*strideB_rows*32 in ascending j with the reference's update rule
+ *   if (d < best1) { best2 = best1; best1 = d; idx = j; } else if (d < best2) best2 = d;
+ * out: [npairs][strideA_rows] (entries i >= nA[p] are not written).  mem / stream as above. */
+SDORB_API int sdorb_match_batch(sdorb_handle* h, const uint8_t* descA, const int32_t* nA, int strideA_rows,
+                      const uint8_t* descB, const int32_t* nB, int strideB_rows, int npairs, float ratio,
+                      int th_low, sdorb_match* out, int mem, void* stream);
+/* SearchByPoints' greedy form (src/ORBmatcher.cc:1228-1270): queries are visited in order and a train row that
+ * has been accepted by an earlier query is skipped by later ones (vbMatched2). */
+SDORB_API int sdorb_match_greedy_batch(sdorb_handle* h, const uint8_t* descA, const int32_t* nA, int strideA_rows,
+                             const uint8_t* descB, const int32_t* nB, int strideB_rows, int npairs, float ratio,
+                             int th_low, sdorb_match* out, int mem, void* stream);
+/* Full distance matrix out[i*nB + j] = DescriptorDistance(A_i, B_j) for one pair. */
+SDORB_API int sdorb_hamming_matrix(sdorb_handle* h, const uint8_t* descA, int nA, const uint8_t* descB, int nB,
+                         uint16_t* out, int mem, void* stream);
+
+/* ---- host helper used by the C++ shim: BORDER_REFLECT_101 margin around a level (src/ORBextractor.cc:692-696) ---- */
+SDORB_API void sdorb_fill_border_reflect101(uint8_t* level_origin, int width, int height, size_t stride, int border);
+
+/* ---- instrumentation (bench.py / tests) ---- */
+#define SDORB_STAGE_PYRAMID 0
+#define SDORB_STAGE_FAST 1
+#define SDORB_STAGE_SELECT 2
+#define SDORB_STAGE_BLUR 3
+#define SDORB_STAGE_DESCRIBE 4
+#define SDORB_STAGE_MATCH 5
+#define SDORB_NUM_STAGES 6
+/* When enabled, every stage of the device path is bracketed by CUDA events on the launching stream. */
+SDORB_API int sdorb_set_profiling(sdorb_handle* h, int enabled);
+/* Synchronises, then returns accumulated milliseconds and kernel-launch counts per stage since the last reset. */
+SDORB_API int sdorb_get_stage_times(sdorb_handle* h, double* ms, int64_t* launches, int reset);
+/* Total kernels this handle has launched since creation. */
+SDORB_API int64_t sdorb_kernel_launches(const sdorb_handle* h);
+/* Copies an intermediate of the most recent pass to the host (parity tests): what = SDORB_DBG_*;
+ * returns bytes written or a negative error. */
+#define SDORB_DBG_PYRAMID_LEVEL 0 /* width*height bytes of frame `frame`, level `level`, rows packed */
+#define SDORB_DBG_BLURRED_LEVEL 1
+#define SDORB_DBG_CELL_COUNTS 2   /* int32 per cell of the level (row-major cells): FAST keypoints after NMS */
+#define SDORB_DBG_LEVEL_SELECTED 3 /* uint32 (y<<20 | x<<8 | score) per selected keypoint of the level, in order */
+SDORB_API int64_t sdorb_debug_read(sdorb_handle* h, int what, int frame, int level, void* dst, size_t capacity);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SDORB_H */

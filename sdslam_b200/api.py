@@ -1,0 +1,269 @@
+"""Host-side mirror of the reference interface over the C ABI (include/sdorb.h) via ctypes.
+
+`ORBextractor` keeps the reference's constructor / call surface
+(/root/reference/src/ORBextractor.h:38-70: ORBextractor(nfeatures, scaleFactor, nlevels, thFAST),
+operator()(image, mask, keypoints, descriptors, imagePyramid), the six getters) and adds the batched entry
+points that make the GPU worthwhile.  `ORBmatcher.DescriptorDistance` mirrors src/ORBmatcher.h:43.
+
+Everything here goes through libsdorb.so; there is no Python or CPU implementation of the path.  If the
+library is missing it is built with nvcc, and if that fails the import raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "<f4"), ("angle", "<f4"), ("response", "<f4"),
+                     ("octave", "<i4"), ("class_id", "<i4")])
+MATCH_DTYPE = np.dtype([("best_idx", "<i4"), ("best_dist", "<i4"), ("second_dist", "<i4"), ("accepted", "<i4")])
+MEM_HOST, MEM_DEVICE = 0, 1
+STAGES = ("pyramid", "fast", "select", "blur", "describe", "match")
+DBG_PYRAMID_LEVEL, DBG_BLURRED_LEVEL, DBG_CELL_COUNTS, DBG_LEVEL_SELECTED = 0, 1, 2, 3
+EDGE_THRESHOLD = 19
+
+
+class SdorbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sdorb error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _Params(C.Structure):
+    _fields_ = [("nfeatures", C.c_int), ("scale_factor", C.c_float), ("nlevels", C.c_int), ("th_fast", C.c_int),
+                ("min_th_fast", C.c_int), ("device", C.c_int), ("max_width", C.c_int), ("max_height", C.c_int),
+                ("max_batch", C.c_int)]
+
+
+class _PyrView(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_int), ("height", C.c_int), ("stride", C.c_size_t),
+                ("border", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads (building if necessary) libsdorb.so.  Raises if the CUDA library cannot be produced."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = _build.build()
+    L = C.CDLL(so)
+    vp, i, sz, f, i64 = C.c_void_p, C.c_int, C.c_size_t, C.c_float, C.c_int64
+    L.sdorb_create.argtypes = [C.POINTER(_Params), C.POINTER(vp)]
+    L.sdorb_destroy.argtypes = [vp]
+    L.sdorb_destroy.restype = None
+    L.sdorb_strerror.argtypes = [i]
+    L.sdorb_strerror.restype = C.c_char_p
+    L.sdorb_last_cuda_error.argtypes = [vp]
+    L.sdorb_last_cuda_error.restype = C.c_char_p
+    L.sdorb_get_tables.argtypes = [vp] * 6
+    L.sdorb_max_keypoints.argtypes = [vp]
+    L.sdorb_level_size.argtypes = [vp, i, i, i, C.POINTER(i), C.POINTER(i)]
+    L.sdorb_extract.argtypes = [vp, vp, i, i, sz, vp, vp, i, C.POINTER(i), vp]
+    L.sdorb_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, vp, vp, vp, i, i, vp]
+    L.sdorb_batch_status.argtypes = [vp]
+    L.sdorb_match_batch.argtypes = [vp, vp, vp, i, vp, vp, i, i, f, i, vp, i, vp]
+    L.sdorb_match_greedy_batch.argtypes = [vp, vp, vp, i, vp, vp, i, i, f, i, vp, i, vp]
+    L.sdorb_hamming_matrix.argtypes = [vp, vp, i, vp, i, vp, i, vp]
+    L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
+    L.sdorb_fill_border_reflect101.restype = None
+    L.sdorb_set_profiling.argtypes = [vp, i]
+    L.sdorb_get_stage_times.argtypes = [vp, vp, vp, i]
+    L.sdorb_kernel_launches.argtypes = [vp]
+    L.sdorb_kernel_launches.restype = i64
+    L.sdorb_debug_read.argtypes = [vp, i, i, i, vp, sz]
+    L.sdorb_debug_read.restype = i64
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if hasattr(a, "data_ptr"):  # torch tensor
+        return C.c_void_p(a.data_ptr())
+    return C.c_void_p(int(a))
+
+
+class ORBextractor:
+    """SD_SLAM::ORBextractor on a B200.  One instance = one GPU handle (not thread-safe, like one CUDA stream)."""
+
+    HARRIS_SCORE, FAST_SCORE = 0, 1  # src/ORBextractor.h:36
+
+    def __init__(self, nfeatures, scaleFactor, nlevels, thFAST, minThFAST=None, device=-1, max_width=1920,
+                 max_height=1088, max_batch=64):
+        # The north-star 5-argument form (iniThFAST, minThFAST) maps iniThFAST -> thFAST; SD-SLAM has no
+        # fallback threshold, so minThFAST is accepted and ignored.
+        self._h = C.c_void_p()
+        self.nfeatures, self.scaleFactor, self.nlevels, self.thFAST = nfeatures, scaleFactor, nlevels, thFAST
+        self.max_batch = max_batch
+        p = _Params(nfeatures, scaleFactor, nlevels, thFAST, -1, device, max_width, max_height, max_batch)
+        self._check(lib().sdorb_create(C.byref(p), C.byref(self._h)))
+        self.max_keypoints = lib().sdorb_max_keypoints(self._h)
+        n = nlevels
+        self._sf, self._isf, self._s2, self._is2 = (np.empty(n, np.float32) for _ in range(4))
+        self._npl = np.empty(n, np.int32)
+        self._check(lib().sdorb_get_tables(self._h, _ptr(self._sf), _ptr(self._isf), _ptr(self._s2), _ptr(self._is2),
+                                            _ptr(self._npl)))
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            lib().sdorb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = lib().sdorb_strerror(rc).decode()
+            if rc == -3 and self._h.value:
+                msg += " (" + lib().sdorb_last_cuda_error(self._h).decode() + ")"
+            raise SdorbError(rc, msg)
+
+    # ---- getters, src/ORBextractor.h:48-70
+    def GetLevels(self):
+        return self.nlevels
+
+    def GetScaleFactor(self):
+        return float(np.float32(self.scaleFactor))
+
+    def GetScaleFactors(self):
+        return self._sf.copy()
+
+    def GetInverseScaleFactors(self):
+        return self._isf.copy()
+
+    def GetScaleSigmaSquares(self):
+        return self._s2.copy()
+
+    def GetInverseScaleSigmaSquares(self):
+        return self._is2.copy()
+
+    def features_per_level(self):
+        return self._npl.copy()
+
+    def level_size(self, width, height, level):
+        w, h = C.c_int(), C.c_int()
+        self._check(lib().sdorb_level_size(self._h, width, height, level, C.byref(w), C.byref(h)))
+        return w.value, h.value
+
+    # ---- operator()(image, mask, keypoints, descriptors, imagePyramid), src/ORBextractor.cc:620-678
+    def __call__(self, image, mask=None, want_pyramid=True):
+        """Returns (keypoints[KP_DTYPE], descriptors[N,32] uint8, pyramid list).  `mask` is ignored, as in the
+        reference.  An empty image returns (None, None, None): the reference leaves its outputs untouched."""
+        image = np.asarray(image)
+        if image.size == 0:
+            return None, None, None
+        assert image.dtype == np.uint8 and image.ndim == 2 and image.strides[1] == 1, "CV_8UC1 image expected"
+        h, w = image.shape
+        cap = max(self.max_keypoints, 1)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        views, pyr, padded = None, None, []
+        if want_pyramid:
+            views = (_PyrView * self.nlevels)()
+            pyr = []
+            for l in range(self.nlevels):
+                lw, lh = self.level_size(w, h, l)
+                buf = np.zeros((max(lh, 0) + 2 * EDGE_THRESHOLD, max(lw, 0) + 2 * EDGE_THRESHOLD), np.uint8)
+                inner = buf[EDGE_THRESHOLD:EDGE_THRESHOLD + lh, EDGE_THRESHOLD:EDGE_THRESHOLD + lw]
+                padded.append(buf)
+                pyr.append(inner)  # a view into the padded buffer, like imagePyramid[l] in the reference
+                views[l] = _PyrView(inner.ctypes.data if inner.size else None, lw, lh, buf.strides[0], EDGE_THRESHOLD)
+        self._check(lib().sdorb_extract(self._h, _ptr(image), w, h, image.strides[0], _ptr(kps), _ptr(desc), cap,
+                                         C.byref(n), C.cast(views, C.c_void_p) if views is not None else None))
+        return kps[:n.value], desc[:n.value], pyr
+
+    def extract_batch_host(self, images, keypoints=None, descriptors=None, counts=None):
+        """images: uint8 [F,H,W] host array (or pinned torch CPU tensor).  Returns (kps[F,cap], desc[F,cap,32], counts[F])."""
+        nf, h, w = images.shape
+        cap = max(self.max_keypoints, 1)
+        is_t = hasattr(images, "data_ptr")
+        if keypoints is None:
+            keypoints = np.zeros((nf, cap), KP_DTYPE)
+            descriptors = np.zeros((nf, cap, 32), np.uint8)
+            counts = np.zeros(nf, np.int32)
+        row = images.stride(1) if is_t else images.strides[1]
+        frame = images.stride(0) if is_t else images.strides[0]
+        self._check(lib().sdorb_extract_batch(self._h, _ptr(images), nf, w, h, row, frame, _ptr(keypoints),
+                                               _ptr(descriptors), _ptr(counts), cap, MEM_HOST, None))
+        return keypoints, descriptors, counts
+
+    def extract_batch_device(self, images, keypoints, descriptors, counts, stream=None):
+        """All arguments are torch CUDA tensors on this handle's device: images uint8 [F,H,W]; keypoints
+        [F,cap,7] float32 (cv::KeyPoint layout, octave / class_id as int bits); descriptors uint8 [F,cap,32];
+        counts int32 [F].  Work is enqueued on `stream` (a raw cudaStream_t int; None = torch's current)."""
+        import torch
+        nf, h, w = images.shape
+        cap = keypoints.shape[1]
+        if stream is None:
+            stream = torch.cuda.current_stream(images.device).cuda_stream
+        self._check(lib().sdorb_extract_batch(self._h, _ptr(images), nf, w, h, images.stride(1), images.stride(0),
+                                               _ptr(keypoints), _ptr(descriptors), _ptr(counts), cap, MEM_DEVICE,
+                                               C.c_void_p(stream)))
+
+    def batch_status(self):
+        self._check(lib().sdorb_batch_status(self._h))
+
+    # ---- matcher entry points live on the handle (they share its stream and scratch)
+    def match_batch(self, descA, nA, descB, nB, ratio=0.75, th_low=50, out=None, device=False, stream=None, greedy=False):
+        npairs, sa = descA.shape[0], descA.shape[1]
+        sb = descB.shape[1]
+        if out is None:
+            assert not device
+            out = np.zeros((npairs, sa), MATCH_DTYPE)
+        fn = lib().sdorb_match_greedy_batch if greedy else lib().sdorb_match_batch
+        if device and stream is None:
+            import torch
+            stream = torch.cuda.current_stream(descA.device).cuda_stream
+        self._check(fn(self._h, _ptr(descA), _ptr(nA), sa, _ptr(descB), _ptr(nB), sb, npairs, ratio, th_low, _ptr(out),
+                       MEM_DEVICE if device else MEM_HOST, C.c_void_p(stream) if stream else None))
+        return out
+
+    def hamming_matrix(self, A, B):
+        A = np.ascontiguousarray(A, np.uint8).reshape(-1, 32)
+        B = np.ascontiguousarray(B, np.uint8).reshape(-1, 32)
+        out = np.zeros((len(A), len(B)), np.uint16)
+        self._check(lib().sdorb_hamming_matrix(self._h, _ptr(A), len(A), _ptr(B), len(B), _ptr(out), MEM_HOST, None))
+        return out
+
+    # ---- instrumentation
+    def set_profiling(self, on):
+        self._check(lib().sdorb_set_profiling(self._h, int(on)))
+
+    def stage_times(self, reset=True):
+        ms = np.zeros(len(STAGES), np.float64)
+        launches = np.zeros(len(STAGES), np.int64)
+        self._check(lib().sdorb_get_stage_times(self._h, _ptr(ms), _ptr(launches), int(reset)))
+        return dict(zip(STAGES, ms.tolist())), dict(zip(STAGES, launches.tolist()))
+
+    def kernel_launches(self):
+        return int(lib().sdorb_kernel_launches(self._h))
+
+    def debug_read(self, what, frame, level, nbytes, dtype=np.uint8):
+        buf = np.zeros(max(nbytes, 4), np.uint8)
+        n = lib().sdorb_debug_read(self._h, what, frame, level, _ptr(buf), buf.size)
+        if n < 0:
+            self._check(int(n))
+        return buf[:n].view(dtype)
+
+
+class ORBmatcher:
+    """The static distance of src/ORBmatcher.h:43 plus its batched forms, bound to one extractor handle."""
+    TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # src/ORBmatcher.cc:36-38
+
+    def __init__(self, extractor, nnratio=0.6):
+        self.ex, self.nnratio = extractor, nnratio
+
+    def DescriptorDistance(self, a, b):
+        return int(self.ex.hamming_matrix(np.asarray(a).reshape(1, 32), np.asarray(b).reshape(1, 32))[0, 0])
+
+    def match(self, descA, nA, descB, nB, greedy=False, **kw):
+        return self.ex.match_batch(descA, nA, descB, nB, ratio=kw.pop("ratio", self.nnratio), th_low=kw.pop("th_low", self.TH_LOW),
+                                   greedy=greedy, **kw)

@@ -1,0 +1,61 @@
+"""Builds sdslam_b200/libsdorb.so (CUDA kernels + C ABI) in-tree with nvcc for sm_100a.
+
+nvcc cross-compiles without a GPU; the .so is git-ignored but travels to the GPU box with the snapshot.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+SO = os.path.join(HERE, "libsdorb.so")
+SOURCES = ["sdorb_api.cu", "kernels_image.cu", "kernels_fast.cu", "kernels_select.cu", "kernels_describe.cu",
+           "kernels_match.cu", "geometry.cc"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
+              "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden", "-Xptxas", "-v"]
+
+
+def _nvcc():
+    for c in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if c and (os.path.sep not in c or os.path.exists(c)):
+            return c
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build():
+    if not os.path.exists(SO):
+        return True
+    t = os.path.getmtime(SO)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "sdorb.h"), __file__]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    if not force and not needs_build():
+        return SO
+    objs = []
+    bdir = os.path.join(HERE, "build")
+    os.makedirs(bdir, exist_ok=True)
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(bdir, os.path.splitext(src)[0] + ".o")
+        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    log = []
+    for src, p in procs:
+        out, _ = p.communicate()
+        log.append("== %s\n%s" % (src, out))
+        if p.returncode != 0:
+            sys.stderr.write("\n".join(log))
+            raise RuntimeError("nvcc failed on " + src)
+    with open(os.path.join(bdir, "ptxas.log"), "w") as f:
+        f.write("\n".join(log))
+    if verbose:
+        print("\n".join(log))
+    subprocess.check_call([_nvcc(), "-shared", "-o", SO] + objs + ["-Xlinker", "--exclude-libs,ALL"])
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,54 @@
+// kernels.cuh -- launchers of the sm_100a kernels of libsdorb (one family per step of
+// ORBextractor::operator(), /root/reference/src/ORBextractor.cc:620-678, plus the batched DescriptorDistance).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "sdorb_internal.h"
+
+namespace sdorb {
+
+// Where the planes of a batch live.  Level 0 is the caller's image (or a staged copy); levels >= 1 and all
+// blurred levels are level-major scratch: level l of frame f starts at base + lv[l].plane_base * batch_cap + f * lv[l].plane_bytes.
+struct BatchPlanes {
+  const uint8_t* img0;       // level 0, frame 0
+  int64_t img0_frame_stride; // bytes between frames of level 0
+  int img0_pitch;            // bytes between rows of level 0
+  uint8_t* pyr;              // scratch: unblurred levels (slot 0 = staged level 0 when used)
+  uint8_t* blur;             // scratch: blurred levels
+  int batch_cap;             // frames the scratch was sized for
+};
+
+struct SelectBuffers {
+  int32_t* cell_count;  // [batch][cells_total]
+  uint32_t* cell_list;  // [batch][list_total]
+  uint32_t* sel;        // [batch][sel_total]  selected entries, level-major, in output order
+  int32_t* sel_count;   // [batch][nlevels]
+  int32_t* error_flag;  // device int: set to SDORB_ERR_OVERFLOW magnitude when a fixed-capacity list overflows
+};
+
+// ComputePyramid: level l from level l-1 for every frame (cv::resize INTER_LINEAR fixed point).
+void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level, const BatchPlanes& p,
+                         const ResizeTap* d_taps, int nframes, cudaStream_t s);
+// cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101), 8-bit fixed point, all levels of all frames in one launch.
+void launch_blur_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s);
+// cv::FAST(cell, thFAST, nonmax=true) for every cell of every level of every frame, one launch; appends
+// SDORB_ENTRY(y, x, score) to the cell lists in arbitrary order (the select kernel sorts them).
+void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b,
+                     int nframes, cudaStream_t s);
+// Quota redistribution + retainBest per cell + retainBest per level.
+void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const SelectBuffers& b, int nframes, cudaStream_t s);
+// IC_Angle + rBRIEF descriptor + output assembly (coordinate scaling, cv::KeyPoint layout).
+void launch_describe(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b,
+                     const int* d_umax, void* kps_out, uint8_t* desc_out, int32_t* counts_out, int capacity,
+                     int nframes, cudaStream_t s);
+// Batched DescriptorDistance with best / second-best tracking.
+void launch_match(const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* B, const int32_t* nB, int strideB,
+                  int npairs, float ratio, int th_low, void* out, cudaStream_t s);
+void launch_match_greedy(const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* B, const int32_t* nB,
+                         int strideB, int npairs, float ratio, int th_low, void* out, cudaStream_t s);
+void launch_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out, cudaStream_t s);
+
+size_t select_smem_bytes(const FrameGeom& g);
+int configure_kernels();  // one-time cudaFuncSetAttribute calls; returns cudaError_t as int
+
+}  // namespace sdorb

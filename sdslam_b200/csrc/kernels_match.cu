@@ -1,0 +1,150 @@
+// kernels_match.cu -- ORBmatcher::DescriptorDistance batched as Hamming matching, for sm_100a.
+//
+// Reference: /root/reference/src/ORBmatcher.cc:1459-1473 (256-bit Hamming distance as eight 32-bit SWAR popcounts,
+// == __popc) and the best / second-best scan of SearchByPoints (:1239-1265):
+//     if (d < best1) { best2 = best1; best1 = d; idx = j; } else if (d < best2) best2 = d;
+// with j ascending, so the FIRST minimal index wins ties.  Bound: the integer popc pipe, not memory (64 KB in,
+// 16 KB out per 1000x1000 pair).  One thread owns one query row (8 registers); train rows stream through shared
+// memory and are read as broadcasts.  (distance << 16 | j) packs value and index so a single integer min keeps
+// the first-minimum rule; the runner-up needs only  best2 = min(best2, max(d, best1)).
+#include "kernels.cuh"
+
+namespace sdorb {
+
+struct MatchOut {
+  int32_t best_idx, best_dist, second_dist, accepted;
+};
+
+constexpr int M_THREADS = 128;
+constexpr int M_TILE = 256;  // train rows staged per step (8 KB)
+
+__device__ __forceinline__ int hamming256(const uint32_t q[8], const uint4 lo, const uint4 hi) {
+  return __popc(q[0] ^ lo.x) + __popc(q[1] ^ lo.y) + __popc(q[2] ^ lo.z) + __popc(q[3] ^ lo.w) +
+         __popc(q[4] ^ hi.x) + __popc(q[5] ^ hi.y) + __popc(q[6] ^ hi.z) + __popc(q[7] ^ hi.w);
+}
+
+__device__ __forceinline__ int accept_rule(int best1, int best2, float ratio, int th_low) {
+  return (best1 < th_low && (float)best1 < __fmul_rn(ratio, (float)best2)) ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(M_THREADS) match_kernel(const uint8_t* __restrict__ A, const int32_t* __restrict__ nA,
+                                                          int strideA, const uint8_t* __restrict__ B,
+                                                          const int32_t* __restrict__ nB, int strideB, float ratio,
+                                                          int th_low, MatchOut* __restrict__ out) {
+  __shared__ uint4 s_b[M_TILE * 2];
+  const int pair = blockIdx.y;
+  const int na = nA[pair], nb = nB[pair];
+  const int qi = blockIdx.x * M_THREADS + threadIdx.x;
+  if (blockIdx.x * M_THREADS >= na) return;
+  const bool active = qi < na;
+  uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (active) {
+    const uint4* qa = reinterpret_cast<const uint4*>(A + ((int64_t)pair * strideA + qi) * 32);
+    const uint4 lo = qa[0], hi = qa[1];
+    q[0] = lo.x; q[1] = lo.y; q[2] = lo.z; q[3] = lo.w;
+    q[4] = hi.x; q[5] = hi.y; q[6] = hi.z; q[7] = hi.w;
+  }
+  int best1 = (256 << 16) | 0xFFFF;  // distance << 16 | index
+  int best2 = 256;
+  const uint4* bsrc = reinterpret_cast<const uint4*>(B + (int64_t)pair * strideB * 32);
+  for (int j0 = 0; j0 < nb; j0 += M_TILE) {
+    const int cnt = min(M_TILE, nb - j0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * 2; i += M_THREADS) s_b[i] = bsrc[(int64_t)j0 * 2 + i];
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < cnt; ++j) {
+      const int d = hamming256(q, s_b[2 * j], s_b[2 * j + 1]);
+      best2 = min(best2, max(d, best1 >> 16));
+      best1 = min(best1, (d << 16) | (j0 + j));
+    }
+  }
+  if (active) {
+    MatchOut o;
+    o.best_dist = best1 >> 16;
+    o.best_idx = o.best_dist < 256 ? (best1 & 0xFFFF) : -1;
+    o.second_dist = best2;
+    o.accepted = accept_rule(o.best_dist, best2, ratio, th_low);
+    out[(int64_t)pair * strideA + qi] = o;
+  }
+}
+
+// SearchByPoints' greedy form: queries in order; a train row accepted by an earlier query is masked for later
+// ones (vbMatched2, src/ORBmatcher.cc:1228, 1245, 1267).  Sequential over queries by nature: one warp per pair,
+// lanes split the train rows, (distance<<16 | j) min-reduced across the warp, runner-up merged alongside.
+__global__ void __launch_bounds__(32) match_greedy_kernel(const uint8_t* __restrict__ A, const int32_t* __restrict__ nA,
+                                                          int strideA, const uint8_t* __restrict__ B,
+                                                          const int32_t* __restrict__ nB, int strideB, float ratio,
+                                                          int th_low, MatchOut* __restrict__ out) {
+  extern __shared__ uint32_t s_matched[];  // bitset over train rows
+  const int pair = blockIdx.x, lane = threadIdx.x;
+  const int na = nA[pair], nb = nB[pair];
+  for (int i = lane; i < (nb + 31) / 32; i += 32) s_matched[i] = 0;
+  __syncwarp();
+  const uint4* bsrc = reinterpret_cast<const uint4*>(B + (int64_t)pair * strideB * 32);
+  for (int qi = 0; qi < na; ++qi) {
+    const uint4* qa = reinterpret_cast<const uint4*>(A + ((int64_t)pair * strideA + qi) * 32);
+    const uint4 lo = qa[0], hi = qa[1];
+    const uint32_t q[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    int best1 = (256 << 16) | 0xFFFF, best2 = 256;
+    for (int j = lane; j < nb; j += 32) {
+      if ((s_matched[j >> 5] >> (j & 31)) & 1u) continue;
+      const int d = hamming256(q, bsrc[2 * j], bsrc[2 * j + 1]);
+      best2 = min(best2, max(d, best1 >> 16));
+      best1 = min(best1, (d << 16) | j);
+    }
+    // merge (best1, best2) pairs: the two smallest distances of the union, first index on ties
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int ob1 = __shfl_xor_sync(0xffffffffu, best1, o), ob2 = __shfl_xor_sync(0xffffffffu, best2, o);
+      const int lo1 = min(best1, ob1), hi1 = max(best1, ob1);
+      best2 = min(min(best2, ob2), hi1 >> 16);
+      best1 = lo1;
+    }
+    const int bd = best1 >> 16;
+    const int ok = accept_rule(bd, best2, ratio, th_low);
+    if (lane == 0) {
+      MatchOut r;
+      r.best_dist = bd;
+      r.best_idx = bd < 256 ? (best1 & 0xFFFF) : -1;
+      r.second_dist = best2;
+      r.accepted = ok;
+      out[(int64_t)pair * strideA + qi] = r;
+      if (ok) s_matched[(best1 & 0xFFFF) >> 5] |= 1u << (best1 & 31);
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(256) hamming_matrix_kernel(const uint8_t* __restrict__ A, int nA,
+                                                             const uint8_t* __restrict__ B, int nB,
+                                                             uint16_t* __restrict__ out) {
+  const int j = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  if (j >= nB) return;
+  const uint4* qa = reinterpret_cast<const uint4*>(A + (int64_t)i * 32);
+  const uint4 lo = qa[0], hi = qa[1];
+  const uint32_t q[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  const uint4* b = reinterpret_cast<const uint4*>(B + (int64_t)j * 32);
+  out[(int64_t)i * nB + j] = (uint16_t)hamming256(q, b[0], b[1]);
+}
+
+void launch_match(const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* B, const int32_t* nB, int strideB,
+                  int npairs, float ratio, int th_low, void* out, cudaStream_t s) {
+  if (npairs <= 0 || strideA <= 0) return;
+  dim3 grid((strideA + M_THREADS - 1) / M_THREADS, npairs);
+  match_kernel<<<grid, M_THREADS, 0, s>>>(A, nA, strideA, B, nB, strideB, ratio, th_low, (MatchOut*)out);
+}
+
+void launch_match_greedy(const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* B, const int32_t* nB,
+                         int strideB, int npairs, float ratio, int th_low, void* out, cudaStream_t s) {
+  if (npairs <= 0) return;
+  const size_t smem = sizeof(uint32_t) * (size_t)((strideB + 31) / 32 + 1);
+  match_greedy_kernel<<<npairs, 32, smem, s>>>(A, nA, strideA, B, nB, strideB, ratio, th_low, (MatchOut*)out);
+}
+
+void launch_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out, cudaStream_t s) {
+  if (nA <= 0 || nB <= 0) return;
+  hamming_matrix_kernel<<<dim3((nB + 255) / 256, nA), 256, 0, s>>>(A, nA, B, nB, out);
+}
+
+}  // namespace sdorb

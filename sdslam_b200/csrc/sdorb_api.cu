@@ -1,0 +1,694 @@
+// sdorb_api.cu -- the C ABI of libsdorb.so (include/sdorb.h): handle, scratch memory, stream pipelines.
+//
+// A handle owns a compute stream, two copy streams and all device scratch.  The device-memory entry points only
+// enqueue kernels; the host-memory entry points stage frames through the GPU in passes of max_batch frames with
+// H2D copy / kernels / D2H copy of consecutive passes overlapped on three streams.  There is no CPU path: any
+// CUDA failure is returned as SDORB_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sdorb.h"
+#include "geometry.h"
+#include "kernels.cuh"
+
+using namespace sdorb;
+
+struct StageEvent {
+  int stage;
+  cudaEvent_t a, b;
+};
+
+struct sdorb_handle {
+  sdorb_params prm{};
+  Tables tables;
+  int device = 0;
+  cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2]{}, ev_compute[2]{}, ev_out[2]{};
+  // geometry of the current image size
+  int gw = 0, gh = 0;
+  FrameGeom geom{};
+  FrameGeom* d_geom = nullptr;
+  ResizeTap* d_taps = nullptr;
+  int* d_umax = nullptr;
+  // scratch for max_batch frames of the current geometry
+  uint8_t *d_pyr = nullptr, *d_blur = nullptr;
+  uint8_t* d_stage_in[2] = {nullptr, nullptr};
+  int32_t *d_cell_count = nullptr, *d_sel_count = nullptr, *d_error = nullptr;
+  uint32_t *d_cell_list = nullptr, *d_sel = nullptr;
+  // output staging for the host path (2 slots)
+  sdorb_keypoint* d_kps[2] = {nullptr, nullptr};
+  uint8_t* d_desc[2] = {nullptr, nullptr};
+  int32_t* d_counts[2] = {nullptr, nullptr};
+  int out_cap = 0;
+  // matcher temporaries (host path)
+  void* d_match_buf = nullptr;
+  size_t match_buf_bytes = 0;
+  // bookkeeping
+  int64_t launches = 0;
+  int64_t stage_launches[SDORB_NUM_STAGES] = {0};
+  double stage_ms[SDORB_NUM_STAGES] = {0};
+  bool profiling = false;
+  std::vector<StageEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
+  int deferred_error = 0;
+  std::string cuda_error;
+};
+
+namespace {
+
+#define CU(call)                                                                       \
+  do {                                                                                 \
+    cudaError_t e_ = (call);                                                           \
+    if (e_ != cudaSuccess) {                                                           \
+      h->cuda_error = std::string(#call) + ": " + cudaGetErrorString(e_);              \
+      return e_ == cudaErrorMemoryAllocation ? SDORB_ERR_NOMEM : SDORB_ERR_CUDA;       \
+    }                                                                                  \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~DeviceGuard() {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+  }
+};
+
+template <class T>
+void dfree(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+void free_geometry_scratch(sdorb_handle* h) {
+  dfree(h->d_geom);
+  dfree(h->d_taps);
+  dfree(h->d_pyr);
+  dfree(h->d_blur);
+  dfree(h->d_stage_in[0]);
+  dfree(h->d_stage_in[1]);
+  dfree(h->d_cell_count);
+  dfree(h->d_cell_list);
+  dfree(h->d_sel);
+  dfree(h->d_sel_count);
+  for (int i = 0; i < 2; ++i) {
+    dfree(h->d_kps[i]);
+    dfree(h->d_desc[i]);
+    dfree(h->d_counts[i]);
+  }
+  h->gw = h->gh = 0;
+  h->out_cap = 0;
+}
+
+int geom_err(int e) {
+  switch (e) {
+    case 0: return SDORB_OK;
+    case -4: return SDORB_ERR_GEOMETRY;
+    case -7: return SDORB_ERR_UNSUPPORTED;
+    default: return SDORB_ERR_BAD_ARG;
+  }
+}
+
+// (Re)build geometry and scratch for a width x height input.
+int ensure_geometry(sdorb_handle* h, int width, int height) {
+  if (width == h->gw && height == h->gh) return SDORB_OK;
+  if (width <= 0 || height <= 0 || width > h->prm.max_width || height > h->prm.max_height) return SDORB_ERR_BAD_ARG;
+  FrameGeom g;
+  std::vector<ResizeTap> taps;
+  const int ge = build_frame_geom(h->tables, h->prm.nfeatures, h->prm.th_fast, width, height, &g, &taps);
+  if (ge) return geom_err(ge);
+  CU(cudaStreamSynchronize(h->s_compute));
+  free_geometry_scratch(h);
+  const size_t B = (size_t)h->prm.max_batch;
+  CU(cudaMalloc(&h->d_geom, sizeof(FrameGeom)));
+  CU(cudaMemcpy(h->d_geom, &g, sizeof(FrameGeom), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&h->d_taps, sizeof(ResizeTap) * std::max<size_t>(taps.size(), 1)));
+  if (!taps.empty()) CU(cudaMemcpy(h->d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&h->d_pyr, (size_t)g.plane_total * B + 256));
+  CU(cudaMalloc(&h->d_blur, (size_t)g.plane_total * B + 256));
+  CU(cudaMalloc(&h->d_cell_count, sizeof(int32_t) * std::max<size_t>((size_t)g.cells_total * B, 1)));
+  CU(cudaMalloc(&h->d_cell_list, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
+  CU(cudaMalloc(&h->d_sel, sizeof(uint32_t) * std::max<size_t>((size_t)g.sel_total * B, 1)));
+  CU(cudaMalloc(&h->d_sel_count, sizeof(int32_t) * (size_t)g.nlevels * B));
+  h->geom = g;
+  h->gw = width;
+  h->gh = height;
+  return SDORB_OK;
+}
+
+int ensure_host_staging(sdorb_handle* h, int capacity) {
+  const size_t B = (size_t)h->prm.max_batch;
+  if (!h->d_stage_in[0]) {
+    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_stage_in[i], (size_t)h->geom.lv[0].plane_bytes * B + 256));
+  }
+  if (h->out_cap != capacity) {
+    for (int i = 0; i < 2; ++i) {
+      dfree(h->d_kps[i]);
+      dfree(h->d_desc[i]);
+      dfree(h->d_counts[i]);
+      CU(cudaMalloc(&h->d_kps[i], sizeof(sdorb_keypoint) * (size_t)capacity * B));
+      CU(cudaMalloc(&h->d_desc[i], (size_t)32 * capacity * B));
+      CU(cudaMalloc(&h->d_counts[i], sizeof(int32_t) * B));
+    }
+    h->out_cap = capacity;
+  }
+  return SDORB_OK;
+}
+
+cudaEvent_t take_event(sdorb_handle* h) {
+  if (!h->event_pool.empty()) {
+    cudaEvent_t e = h->event_pool.back();
+    h->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+
+struct StageScope {
+  sdorb_handle* h;
+  cudaStream_t s;
+  int stage;
+  cudaEvent_t a = nullptr;
+  StageScope(sdorb_handle* h_, cudaStream_t s_, int stage_) : h(h_), s(s_), stage(stage_) {
+    if (h->profiling) {
+      a = take_event(h);
+      cudaEventRecord(a, s);
+    }
+  }
+  void launched(int n = 1) {
+    h->launches += n;
+    h->stage_launches[stage] += n;
+  }
+  ~StageScope() {
+    if (h->profiling) {
+      cudaEvent_t b = take_event(h);
+      cudaEventRecord(b, s);
+      h->pending.push_back(StageEvent{stage, a, b});
+    }
+  }
+};
+
+// Enqueue ORBextractor::operator() for `n` frames (n <= max_batch) whose level 0 is described by `planes`.
+int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts,
+                 int capacity, cudaStream_t s) {
+  const FrameGeom& g = h->geom;
+  planes.pyr = h->d_pyr;
+  planes.blur = h->d_blur;
+  planes.batch_cap = h->prm.max_batch;
+  SelectBuffers sb{h->d_cell_count, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error};
+  {
+    StageScope st(h, s, SDORB_STAGE_PYRAMID);
+    for (int l = 1; l < g.nlevels; ++l) {
+      launch_resize_level(h->d_geom, g, l, planes, h->d_taps, n, s);
+      st.launched();
+    }
+  }
+  {
+    StageScope st(h, s, SDORB_STAGE_FAST);
+    CU(cudaMemsetAsync(h->d_cell_count, 0, sizeof(int32_t) * std::max<size_t>((size_t)g.cells_total * n, 1), s));
+    if (g.tiles_total_fast > 0) {
+      launch_fast_all(h->d_geom, g, planes, sb, n, s);
+      st.launched();
+    }
+  }
+  {
+    StageScope st(h, s, SDORB_STAGE_SELECT);
+    launch_select(h->d_geom, g, sb, n, s);
+    st.launched();
+  }
+  {
+    StageScope st(h, s, SDORB_STAGE_BLUR);
+    launch_blur_all(h->d_geom, g, planes, n, s);
+    st.launched();
+  }
+  {
+    StageScope st(h, s, SDORB_STAGE_DESCRIBE);
+    launch_describe(h->d_geom, g, planes, sb, h->d_umax, d_kps, d_desc, d_counts, capacity, n, s);
+    st.launched();
+  }
+  CU(cudaGetLastError());
+  return SDORB_OK;
+}
+
+int check_deferred(sdorb_handle* h) {
+  int flag = 0;
+  CU(cudaMemcpy(&flag, h->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+  if (flag) {
+    h->deferred_error = -flag;
+    int zero = 0;
+    CU(cudaMemcpy(h->d_error, &zero, sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return SDORB_OK;
+}
+
+bool aligned16(const void* p, size_t a, size_t b) { return ((uintptr_t)p % 16 == 0) && (a % 16 == 0) && (b % 16 == 0); }
+
+}  // namespace
+
+extern "C" {
+
+const char* sdorb_strerror(int code) {
+  switch (code) {
+    case SDORB_OK: return "ok";
+    case SDORB_ERR_BAD_ARG: return "bad argument";
+    case SDORB_ERR_CAPACITY: return "output capacity too small";
+    case SDORB_ERR_CUDA: return "CUDA error";
+    case SDORB_ERR_GEOMETRY: return "cell ROI outside the level image (the reference throws / reads out of bounds)";
+    case SDORB_ERR_NOMEM: return "out of device or pinned memory";
+    case SDORB_ERR_OVERFLOW: return "internal list overflow";
+    case SDORB_ERR_UNSUPPORTED: return "unsupported configuration";
+    default: return "unknown error";
+  }
+}
+
+const char* sdorb_last_cuda_error(const sdorb_handle* h) { return h ? h->cuda_error.c_str() : ""; }
+
+int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
+  if (!params || !out) return SDORB_ERR_BAD_ARG;
+  *out = nullptr;
+  if (params->nfeatures < 0 || params->nlevels <= 0 || params->nlevels > SDORB_MAX_LEVELS || params->max_batch <= 0 ||
+      params->max_batch > 65535 || params->max_width <= 0 || params->max_height <= 0 ||
+      params->max_width > SDORB_MAX_DIM || params->max_height > SDORB_MAX_DIM || !(params->scale_factor > 0.f))
+    return SDORB_ERR_BAD_ARG;
+  if (params->min_th_fast >= 0) return SDORB_ERR_UNSUPPORTED;  // ORB-SLAM2 ini/min mode is not part of this reference
+  sdorb_handle* h = new (std::nothrow) sdorb_handle;
+  if (!h) return SDORB_ERR_NOMEM;
+  h->prm = *params;
+  int dev = params->device;
+  if (dev < 0 && cudaGetDevice(&dev) != cudaSuccess) {
+    delete h;
+    return SDORB_ERR_CUDA;
+  }
+  h->device = dev;
+  build_tables(params->nfeatures, params->scale_factor, params->nlevels, &h->tables);
+  auto fail = [&](int code) {
+    sdorb_destroy(h);
+    return code;
+  };
+  DeviceGuard guard(dev);
+  if (cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&h->ev_compute[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  }
+  if (cudaMalloc(&h->d_umax, sizeof(int) * 16) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
+  if (cudaMemcpy(h->d_umax, h->tables.umax, sizeof(int) * 16, cudaMemcpyHostToDevice) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (cudaMalloc(&h->d_error, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
+  if (cudaMemset(h->d_error, 0, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (configure_kernels() != 0) return fail(SDORB_ERR_CUDA);
+  *out = h;
+  return SDORB_OK;
+}
+
+void sdorb_destroy(sdorb_handle* h) {
+  if (!h) return;
+  {
+    DeviceGuard guard(h->device);
+    if (h->s_compute) cudaStreamSynchronize(h->s_compute);
+    if (h->s_in) cudaStreamSynchronize(h->s_in);
+    if (h->s_out) cudaStreamSynchronize(h->s_out);
+    free_geometry_scratch(h);
+    dfree(h->d_umax);
+    dfree(h->d_error);
+    if (h->d_match_buf) cudaFree(h->d_match_buf);
+    for (auto& p : h->pending) {
+      cudaEventDestroy(p.a);
+      cudaEventDestroy(p.b);
+    }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+      if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
+      if (h->ev_compute[i]) cudaEventDestroy(h->ev_compute[i]);
+      if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+    }
+    if (h->s_compute) cudaStreamDestroy(h->s_compute);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
+  }
+  delete h;
+}
+
+int sdorb_get_tables(const sdorb_handle* h, float* sf, float* isf, float* s2, float* is2, int* npl) {
+  if (!h) return SDORB_ERR_BAD_ARG;
+  for (int i = 0; i < h->tables.nlevels; ++i) {
+    if (sf) sf[i] = h->tables.scale[i];
+    if (isf) isf[i] = h->tables.inv_scale[i];
+    if (s2) s2[i] = h->tables.sigma2[i];
+    if (is2) is2[i] = h->tables.inv_sigma2[i];
+    if (npl) npl[i] = h->tables.n_per_level[i];
+  }
+  return SDORB_OK;
+}
+
+int sdorb_max_keypoints(const sdorb_handle* h) {
+  if (!h) return SDORB_ERR_BAD_ARG;
+  int s = 0;
+  for (int v : h->tables.n_per_level) s += std::max(v, 0);
+  return s;
+}
+
+int sdorb_level_size(const sdorb_handle* h, int width, int height, int level, int* lw, int* lh) {
+  if (!h || level < 0 || level >= h->tables.nlevels || !lw || !lh) return SDORB_ERR_BAD_ARG;
+  level_size(h->tables, level, width, height, lw, lh);
+  return SDORB_OK;
+}
+
+int sdorb_batch_status(sdorb_handle* h) {
+  if (!h) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  const int rc = check_deferred(h);
+  if (rc) return rc;
+  const int e = h->deferred_error;
+  h->deferred_error = 0;
+  return e;
+}
+
+int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height, size_t row_stride,
+                        size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts,
+                        int capacity, int mem, void* stream) {
+  if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nframes == 0) return SDORB_OK;
+  if (!images || !keypoints || !descriptors || !counts || width <= 0 || height <= 0 || row_stride < (size_t)width ||
+      (nframes > 1 && frame_stride < row_stride * (size_t)(height - 1) + (size_t)width))
+    return SDORB_ERR_BAD_ARG;
+  if (capacity < sdorb_max_keypoints(h)) return SDORB_ERR_CAPACITY;
+  DeviceGuard guard(h->device);
+  int rc = ensure_geometry(h, width, height);
+  if (rc) return rc;
+  const int B = h->prm.max_batch;
+  const LevelGeom& L0 = h->geom.lv[0];
+
+  if (mem == SDORB_MEM_DEVICE) {
+    cudaStream_t s = stream ? (cudaStream_t)stream : h->s_compute;
+    const bool direct = aligned16(images, row_stride, frame_stride);
+    for (int f0 = 0; f0 < nframes; f0 += B) {
+      const int n = std::min(B, nframes - f0);
+      BatchPlanes pl{};
+      if (direct) {
+        pl.img0 = images + (size_t)f0 * frame_stride;
+        pl.img0_frame_stride = (int64_t)frame_stride;
+        pl.img0_pitch = (int)row_stride;
+      } else {
+        // unaligned caller layout: repack level 0 into the pitch-aligned scratch plane
+        for (int f = 0; f < n; ++f)
+          CU(cudaMemcpy2DAsync(h->d_pyr + (size_t)f * L0.plane_bytes, L0.pitch, images + (size_t)(f0 + f) * frame_stride,
+                               row_stride, width, height, cudaMemcpyDeviceToDevice, s));
+        pl.img0 = h->d_pyr;
+        pl.img0_frame_stride = L0.plane_bytes;
+        pl.img0_pitch = L0.pitch;
+      }
+      rc = enqueue_pass(h, pl, n, keypoints + (size_t)f0 * capacity, descriptors + (size_t)f0 * capacity * 32, counts + f0,
+                        capacity, s);
+      if (rc) return rc;
+    }
+    return SDORB_OK;
+  }
+
+  // host path: three-stream pipeline over passes of max_batch frames
+  rc = ensure_host_staging(h, capacity);
+  if (rc) return rc;
+  int pass = 0;
+  for (int f0 = 0; f0 < nframes; f0 += B, ++pass) {
+    const int n = std::min(B, nframes - f0), slot = pass & 1;
+    if (pass >= 2) CU(cudaStreamWaitEvent(h->s_in, h->ev_compute[slot], 0));
+    if (frame_stride == row_stride * (size_t)height) {
+      CU(cudaMemcpy2DAsync(h->d_stage_in[slot], L0.pitch, images + (size_t)f0 * frame_stride, row_stride, width,
+                           (size_t)height * n, cudaMemcpyHostToDevice, h->s_in));
+    } else {
+      for (int f = 0; f < n; ++f)
+        CU(cudaMemcpy2DAsync(h->d_stage_in[slot] + (size_t)f * L0.plane_bytes, L0.pitch,
+                             images + (size_t)(f0 + f) * frame_stride, row_stride, width, height, cudaMemcpyHostToDevice,
+                             h->s_in));
+    }
+    CU(cudaEventRecord(h->ev_in[slot], h->s_in));
+    CU(cudaStreamWaitEvent(h->s_compute, h->ev_in[slot], 0));
+    if (pass >= 2) CU(cudaStreamWaitEvent(h->s_compute, h->ev_out[slot], 0));
+    BatchPlanes pl{};
+    pl.img0 = h->d_stage_in[slot];
+    pl.img0_frame_stride = L0.plane_bytes;
+    pl.img0_pitch = L0.pitch;
+    rc = enqueue_pass(h, pl, n, h->d_kps[slot], h->d_desc[slot], h->d_counts[slot], capacity, h->s_compute);
+    if (rc) return rc;
+    CU(cudaEventRecord(h->ev_compute[slot], h->s_compute));
+    CU(cudaStreamWaitEvent(h->s_out, h->ev_compute[slot], 0));
+    CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, h->d_kps[slot], sizeof(sdorb_keypoint) * (size_t)capacity * n,
+                       cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaMemcpyAsync(descriptors + (size_t)f0 * capacity * 32, h->d_desc[slot], (size_t)32 * capacity * n,
+                       cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaMemcpyAsync(counts + f0, h->d_counts[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->s_out));
+    CU(cudaEventRecord(h->ev_out[slot], h->s_out));
+  }
+  CU(cudaStreamSynchronize(h->s_out));
+  CU(cudaStreamSynchronize(h->s_compute));
+  rc = check_deferred(h);
+  if (rc) return rc;
+  if (h->deferred_error) {
+    const int e = h->deferred_error;
+    h->deferred_error = 0;
+    return e;
+  }
+  return SDORB_OK;
+}
+
+void sdorb_fill_border_reflect101(uint8_t* origin, int width, int height, size_t stride, int border) {
+  if (!origin || width <= 0 || height <= 0 || border <= 0) return;
+  auto refl = [](int p, int len) {
+    if (len == 1) return 0;
+    while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+  };
+  for (int y = 0; y < height; ++y) {
+    uint8_t* row = origin + (ptrdiff_t)y * (ptrdiff_t)stride;
+    for (int x = 1; x <= border; ++x) {
+      row[-x] = row[refl(-x, width)];
+      row[width - 1 + x] = row[refl(width - 1 + x, width)];
+    }
+  }
+  for (int y = 1; y <= border; ++y) {
+    memcpy(origin - (ptrdiff_t)y * (ptrdiff_t)stride - border, origin + (ptrdiff_t)refl(-y, height) * (ptrdiff_t)stride - border,
+           (size_t)width + 2 * (size_t)border);
+    memcpy(origin + (ptrdiff_t)(height - 1 + y) * (ptrdiff_t)stride - border,
+           origin + (ptrdiff_t)refl(height - 1 + y, height) * (ptrdiff_t)stride - border, (size_t)width + 2 * (size_t)border);
+  }
+}
+
+int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, size_t stride, sdorb_keypoint* keypoints,
+                  uint8_t* descriptors, int capacity, int* count, const sdorb_pyr_view* pyramid) {
+  if (!h) return SDORB_ERR_BAD_ARG;
+  if (!image || width <= 0 || height <= 0) return SDORB_OK;  // empty image: outputs untouched (src/ORBextractor.cc:622-623)
+  if (!keypoints || !descriptors || !count) return SDORB_ERR_BAD_ARG;
+  int32_t n = 0;
+  int rc = sdorb_extract_batch(h, image, 1, width, height, stride, stride * (size_t)height, keypoints, descriptors, &n,
+                               capacity, SDORB_MEM_HOST, nullptr);
+  if (rc) return rc;
+  *count = n;
+  if (pyramid) {
+    DeviceGuard guard(h->device);
+    for (int l = 0; l < h->geom.nlevels; ++l) {
+      const LevelGeom& L = h->geom.lv[l];
+      const sdorb_pyr_view& v = pyramid[l];
+      if (!v.data) continue;
+      if (v.width != L.w || v.height != L.h || v.stride < (size_t)L.w) return SDORB_ERR_BAD_ARG;
+      const uint8_t* src = l == 0 ? h->d_stage_in[0] : h->d_pyr + (size_t)L.plane_base * h->prm.max_batch;
+      CU(cudaMemcpy2D(v.data, v.stride, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
+      if (v.border > 0) sdorb_fill_border_reflect101(v.data, L.w, L.h, v.stride, v.border);
+    }
+  }
+  return SDORB_OK;
+}
+
+static int match_common(sdorb_handle* h, const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* Bm,
+                        const int32_t* nB, int strideB, int npairs, float ratio, int th_low, sdorb_match* out, int mem,
+                        void* stream, bool greedy) {
+  if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (npairs == 0) return SDORB_OK;
+  if (!A || !nA || !Bm || !nB || !out || strideA <= 0 || strideB <= 0 || strideB > 65535) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  const uint8_t *dA = A, *dB = Bm;
+  const int32_t *dnA = nA, *dnB = nB;
+  sdorb_match* dout = out;
+  const size_t bytesA = (size_t)npairs * strideA * 32, bytesB = (size_t)npairs * strideB * 32;
+  const size_t bytesN = sizeof(int32_t) * (size_t)npairs, bytesO = sizeof(sdorb_match) * (size_t)npairs * strideA;
+  if (mem == SDORB_MEM_HOST) {
+    for (int p = 0; p < npairs; ++p)
+      if (nA[p] < 0 || nA[p] > strideA || nB[p] < 0 || nB[p] > strideB) return SDORB_ERR_BAD_ARG;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    const size_t need = up(bytesA) + up(bytesB) + 2 * up(bytesN) + up(bytesO);
+    if (need > h->match_buf_bytes) {
+      if (h->d_match_buf) cudaFree(h->d_match_buf);
+      h->d_match_buf = nullptr;
+      h->match_buf_bytes = 0;
+      CU(cudaMalloc(&h->d_match_buf, need));
+      h->match_buf_bytes = need;
+    }
+    uint8_t* base = (uint8_t*)h->d_match_buf;
+    uint8_t* pA = base;
+    uint8_t* pB = pA + up(bytesA);
+    int32_t* pnA = (int32_t*)(pB + up(bytesB));
+    int32_t* pnB = (int32_t*)((uint8_t*)pnA + up(bytesN));
+    dout = (sdorb_match*)((uint8_t*)pnB + up(bytesN));
+    CU(cudaMemcpyAsync(pA, A, bytesA, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pB, Bm, bytesB, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pnA, nA, bytesN, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(pnB, nB, bytesN, cudaMemcpyHostToDevice, s));
+    dA = pA;
+    dB = pB;
+    dnA = pnA;
+    dnB = pnB;
+  } else if (((uintptr_t)A | (uintptr_t)Bm) % 16) {
+    return SDORB_ERR_BAD_ARG;  // descriptor slabs must be 16-byte aligned on the device
+  }
+  {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    if (greedy)
+      launch_match_greedy(dA, dnA, strideA, dB, dnB, strideB, npairs, ratio, th_low, dout, s);
+    else
+      launch_match(dA, dnA, strideA, dB, dnB, strideB, npairs, ratio, th_low, dout, s);
+    st.launched();
+  }
+  CU(cudaGetLastError());
+  if (mem == SDORB_MEM_HOST) {
+    CU(cudaMemcpyAsync(out, dout, bytesO, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  return SDORB_OK;
+}
+
+int sdorb_match_batch(sdorb_handle* h, const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* Bm,
+                      const int32_t* nB, int strideB, int npairs, float ratio, int th_low, sdorb_match* out, int mem,
+                      void* stream) {
+  return match_common(h, A, nA, strideA, Bm, nB, strideB, npairs, ratio, th_low, out, mem, stream, false);
+}
+
+int sdorb_match_greedy_batch(sdorb_handle* h, const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* Bm,
+                             const int32_t* nB, int strideB, int npairs, float ratio, int th_low, sdorb_match* out,
+                             int mem, void* stream) {
+  return match_common(h, A, nA, strideA, Bm, nB, strideB, npairs, ratio, th_low, out, mem, stream, true);
+}
+
+int sdorb_hamming_matrix(sdorb_handle* h, const uint8_t* A, int nA, const uint8_t* Bm, int nB, uint16_t* out, int mem,
+                         void* stream) {
+  if (!h || nA < 0 || nB < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nA == 0 || nB == 0) return SDORB_OK;
+  if (!A || !Bm || !out) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (((uintptr_t)A | (uintptr_t)Bm) % 16) return SDORB_ERR_BAD_ARG;
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_hamming_matrix(A, nA, Bm, nB, out, s);
+    st.launched();
+    CU(cudaGetLastError());
+    return SDORB_OK;
+  }
+  uint8_t *dA = nullptr, *dB = nullptr;
+  uint16_t* dO = nullptr;
+  CU(cudaMalloc(&dA, (size_t)nA * 32));
+  CU(cudaMalloc(&dB, (size_t)nB * 32));
+  CU(cudaMalloc(&dO, sizeof(uint16_t) * (size_t)nA * nB));
+  int rc = SDORB_OK;
+  auto step = [&](cudaError_t e) {
+    if (e != cudaSuccess && rc == SDORB_OK) {
+      h->cuda_error = cudaGetErrorString(e);
+      rc = SDORB_ERR_CUDA;
+    }
+  };
+  step(cudaMemcpyAsync(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice, s));
+  step(cudaMemcpyAsync(dB, Bm, (size_t)nB * 32, cudaMemcpyHostToDevice, s));
+  {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_hamming_matrix(dA, nA, dB, nB, dO, s);
+    st.launched();
+  }
+  step(cudaGetLastError());
+  step(cudaMemcpyAsync(out, dO, sizeof(uint16_t) * (size_t)nA * nB, cudaMemcpyDeviceToHost, s));
+  step(cudaStreamSynchronize(s));
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dO);
+  return rc;
+}
+
+int sdorb_set_profiling(sdorb_handle* h, int enabled) {
+  if (!h) return SDORB_ERR_BAD_ARG;
+  h->profiling = enabled != 0;
+  return SDORB_OK;
+}
+
+int sdorb_get_stage_times(sdorb_handle* h, double* ms, int64_t* launches, int reset) {
+  if (!h) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  CU(cudaDeviceSynchronize());
+  for (auto& p : h->pending) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) h->stage_ms[p.stage] += t;
+    h->event_pool.push_back(p.a);
+    h->event_pool.push_back(p.b);
+  }
+  h->pending.clear();
+  for (int i = 0; i < SDORB_NUM_STAGES; ++i) {
+    if (ms) ms[i] = h->stage_ms[i];
+    if (launches) launches[i] = h->stage_launches[i];
+    if (reset) {
+      h->stage_ms[i] = 0;
+      h->stage_launches[i] = 0;
+    }
+  }
+  return SDORB_OK;
+}
+
+int64_t sdorb_kernel_launches(const sdorb_handle* h) { return h ? h->launches : 0; }
+
+int64_t sdorb_debug_read(sdorb_handle* h, int what, int frame, int level, void* dst, size_t capacity) {
+  if (!h || !dst || h->gw == 0 || frame < 0 || frame >= h->prm.max_batch || level < 0 || level >= h->geom.nlevels)
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  CU(cudaDeviceSynchronize());
+  const FrameGeom& g = h->geom;
+  const LevelGeom& L = g.lv[level];
+  const size_t B = (size_t)h->prm.max_batch;
+  switch (what) {
+    case SDORB_DBG_PYRAMID_LEVEL:
+    case SDORB_DBG_BLURRED_LEVEL: {
+      const size_t bytes = (size_t)L.w * L.h;
+      if (capacity < bytes) return SDORB_ERR_CAPACITY;
+      const uint8_t* base = what == SDORB_DBG_BLURRED_LEVEL ? h->d_blur : h->d_pyr;
+      if (what == SDORB_DBG_PYRAMID_LEVEL && level == 0) return SDORB_ERR_UNSUPPORTED;  // level 0 is the caller's image
+      CU(cudaMemcpy2D(dst, L.w, base + (size_t)L.plane_base * B + (size_t)frame * L.plane_bytes, L.pitch, L.w, L.h,
+                      cudaMemcpyDeviceToHost));
+      return (int64_t)bytes;
+    }
+    case SDORB_DBG_CELL_COUNTS: {
+      const size_t n = (L.cols > 0 && L.rows > 0) ? (size_t)L.cols * L.rows : 0;
+      if (capacity < n * 4) return SDORB_ERR_CAPACITY;
+      if (n) CU(cudaMemcpy(dst, h->d_cell_count + (size_t)frame * g.cells_total + L.cell_base, n * 4, cudaMemcpyDeviceToHost));
+      return (int64_t)(n * 4);
+    }
+    case SDORB_DBG_LEVEL_SELECTED: {
+      int32_t n = 0;
+      CU(cudaMemcpy(&n, h->d_sel_count + (size_t)frame * g.nlevels + level, 4, cudaMemcpyDeviceToHost));
+      if (capacity < (size_t)n * 4) return SDORB_ERR_CAPACITY;
+      if (n) CU(cudaMemcpy(dst, h->d_sel + (size_t)frame * g.sel_total + L.sel_base, (size_t)n * 4, cudaMemcpyDeviceToHost));
+      return (int64_t)n * 4;
+    }
+    default: return SDORB_ERR_BAD_ARG;
+  }
+}
+
+}  // extern "C"
