@@ -1,0 +1,407 @@
+#!/usr/bin/env python3
+"""bench.py -- the headline metric of BASELINE.json on this repo's CUDA path and on the CPU reference arm.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            (N > 1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                            (the CPU path on the box's host cores)
+
+Metric: ORB extract+describe frames/s on 640x480 frames, 1000 keypoints, 8 levels, scale 1.2, FAST 20
+(SD-SLAM ORBextractor::operator(), /root/reference/src/ORBextractor.cc:620-678), plus Hamming pairs/s of the batched
+ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1459-1473) as a side figure.
+
+A step = one pass of the hot path over one batch of synthetic frames per GPU (weak scaling: every rank owns a full
+batch; frames are independent, there is no collective in the loop, one NCCL gather of result slabs at the end).
+  value : frames/s with the frames resident in HBM, timed with CUDA events on the launching stream, max over ranks
+  e2e   : the same batch through the C ABI with HOST buffers (sdorb_extract_batch, SDORB_MEM_HOST): pinned host
+          frames -> H2D -> kernels -> D2H of keypoints / descriptors / counts inside the timed region
+  roofline : the dominant kernel's algorithmic bytes / its CUDA-event time, against MEASURED_PEAKS.json
+  cpu_baseline : the CPU oracle (port of the reference path; the reference itself cannot be compiled here)
+                 on the host cores, bounded sample
+Only the cpu_baseline / --impl reference legs touch oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ORB extract+describe frames/s (640x480, 1k kp)"
+WORKLOADS = {
+    # name: (width, height, nfeatures, scale, nlevels, thFAST, frames per GPU per step)
+    "C3_tum_640x480_1000kp_8lv": (640, 480, 1000, 1.2, 8, 20, 4096),
+    "C2_euroc_752x480_1000kp_8lv": (752, 480, 1000, 1.2, 8, 20, 2048),
+    "C5_1080p_4000kp_12lv": (1920, 1080, 4000, 1.2, 12, 20, 256),
+}
+DISTINCT = 64  # distinct generator frames; the rest of the batch are column-rotated copies (distinct bytes, same statistics)
+
+
+def make_frames(nframes, w, h, start=0):
+    """Deterministic batch: frame i = smooth_noise(start + i % DISTINCT) rotated by 8*(i // DISTINCT) columns."""
+    from sdslam_b200 import synth
+    base = synth.frames(min(DISTINCT, nframes), w, h, start=start)
+    out = np.empty((nframes, h, w), np.uint8)
+    for i in range(nframes):
+        out[i] = np.roll(base[i % len(base)], 8 * (i // len(base)), axis=1)
+    return out
+
+
+def level_pixels(geom):
+    return [int(g["width"]) * int(g["height"]) for g in geom]
+
+
+def stage_bytes_per_frame(geom, nkp):
+    """Algorithmic bytes per frame of every stage (SURVEY section 8d / DESIGN.md): each stage reads its input once
+    and writes its output once."""
+    px = level_pixels(geom)
+    P = sum(px)
+    return {
+        "pyramid": (P - px[-1]) + (P - px[0]),
+        "fast": P,
+        "blur": 2 * P,
+        # latency-bound stages, listed for completeness (no roofline claim): packed entries in / out
+        "select": 8 * nkp,
+        "describe": nkp * (749 + 512 + 60),
+    }
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def mark(self):
+        return time.time()
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        rows = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.15] or self.rows
+        for _, line in rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_peak():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------- CPU legs
+def native_oracle():
+    """The oracle rebuilt on this box with the reference's flags (-O3 -march=native, CMakeLists.txt:39-40; contraction
+    stays off because the oracle spells every FMA out).  Falls back to the portable build."""
+    from oracle import binding as orc
+    from sdslam_b200 import synth
+    img = synth.smooth_noise(0, 320, 240)
+    k0, d0 = orc.Extractor(500, 1.2, 4, 20).extract(img)
+    native = orc.use_native()
+    if native:
+        k1, d1 = orc.Extractor(500, 1.2, 4, 20).extract(img)
+        assert k0.tobytes() == k1.tobytes() and d0.tobytes() == d1.tobytes(), "native oracle build changed results"
+    return native
+
+
+def cpu_extract_rate(params, frames, nthreads):
+    from oracle import binding as orc
+    e = orc.Extractor(*params)
+    e.extract_many(frames[:min(len(frames), nthreads)], nthreads=nthreads, want_outputs=False)  # warm caches / threads
+    t = time.perf_counter()
+    _, _, counts = e.extract_many(frames, nthreads=nthreads, want_outputs=False)
+    dt = time.perf_counter() - t
+    return len(frames) / dt, int(counts.sum())
+
+
+def cpu_match_rate(nthreads, npairs, rng):
+    from oracle import binding as orc
+    A = rng.integers(0, 256, (npairs, 1000, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (npairs, 1000, 32), dtype=np.uint8)
+    n = np.full(npairs, 1000, np.int32)
+    t = time.perf_counter()
+    orc.match_many(A, n, B, n, nthreads=nthreads)
+    return npairs * 1e6 / (time.perf_counter() - t)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path on the host cores.  The reference binary
+    cannot be compiled in this image (no OpenCV C++ / Eigen / Pangolin), so this is the oracle port, frame-parallel
+    over all host threads.  Rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    w, h, nf, sf, nl, th, _ = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    per_step = max(2 * cores, 32)
+    frames = make_frames(per_step, w, h)
+    native_oracle()
+    for _ in range(args.warmup):
+        cpu_extract_rate((nf, sf, nl, th), frames[:cores], cores)
+    t = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        _, n = cpu_extract_rate((nf, sf, nl, th), frames, cores)
+        total += n
+    dt = time.perf_counter() - t
+    fps = args.steps * per_step / dt
+    sample = "%d frames per step (2 per host thread), oracle port, %d threads frame-parallel" % (per_step, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "width": w, "height": h, "nfeatures": nf, "scale_factor": sf, "nlevels": nl,
+                       "th_fast": th, "frames_per_step": per_step},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "keypoints_per_frame": total / max(1, args.steps * per_step)}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sdslam_b200 import api, sharding
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w, h, nf, sf, nl, th, frames_per_gpu = WORKLOADS[args.workload]
+    if args.frames:
+        frames_per_gpu = args.frames
+    params = (nf, sf, nl, th)
+
+    # ---- inputs: pinned host batch (the e2e leg reads it) and its device copy (the resident leg reads that)
+    host_np = make_frames(frames_per_gpu, w, h, start=rank * DISTINCT)
+    host = torch.from_numpy(host_np).pin_memory()
+    dimgs = host.to(dev, non_blocking=True)
+    ex = api.ORBextractor(*params, device=local, max_width=w, max_height=h, max_batch=args.pass_frames)
+    cap = ex.max_keypoints
+    kps = torch.zeros((frames_per_gpu, cap, 7), dtype=torch.float32, device=dev)
+    desc = torch.zeros((frames_per_gpu, cap, 32), dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(frames_per_gpu, dtype=torch.int32, device=dev)
+    stream = torch.cuda.Stream(dev)  # non-default: the events below and the kernels share it
+    geom = api.host_level_geometry(*params, w, h)
+    sbytes = stage_bytes_per_frame(geom, cap)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        ex.extract_batch_device(dimgs, kps, desc, cnt, stream=stream.cuda_stream)
+
+    with torch.cuda.stream(stream):
+        for _ in range(max(args.warmup, 3)):
+            step_resident()
+    barrier()
+    ex.batch_status()
+
+    # ---- timed region 1: frames resident in HBM
+    sampler = ClockSampler(local) if rank == 0 else None
+    ex.set_profiling(True)
+    ex.stage_times(reset=True)
+    launches0 = ex.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t_mark0 = time.time()
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            step_resident()
+        e1.record(stream)
+    barrier()
+    t_mark1 = time.time()
+    ms_total = e0.elapsed_time(e1)
+    stage_ms, stage_launches = ex.stage_times(reset=True)
+    ex.set_profiling(False)
+    launches = ex.kernel_launches() - launches0
+    ex.batch_status()
+    clocks = sampler.stop(t_mark0, t_mark1) if sampler else None
+    tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_total_max = float(tmax.item())
+    mean_kp = float(cnt.float().mean().item())
+
+    # ---- timed region 2: end to end through the C ABI with host buffers
+    hk = torch.zeros((frames_per_gpu, cap, 7), dtype=torch.float32).pin_memory()
+    hd = torch.zeros((frames_per_gpu, cap, 32), dtype=torch.uint8).pin_memory()
+    hc = torch.zeros(frames_per_gpu, dtype=torch.int32).pin_memory()
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+
+    def step_e2e():
+        ex.extract_batch_host(host, hk.numpy().view(api.KP_DTYPE).reshape(frames_per_gpu, cap), hd.numpy(), hc.numpy())
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()  # returns when the results are in host memory
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    same = bool((hc.numpy() == cnt.cpu().numpy()).all()) and hd.numpy()[:8].tobytes() == desc[:8].cpu().numpy().tobytes()
+
+    # ---- Hamming side figure: frame pairs (2k, 2k+1) of this batch, best / second-best, ratio 0.75, TH_LOW 50
+    npairs = frames_per_gpu // 2
+    dA, dB = desc[0::2].contiguous(), desc[1::2].contiguous()
+    nA, nB = cnt[0::2].contiguous(), cnt[1::2].contiguous()
+    mout = torch.zeros((npairs, cap, 4), dtype=torch.int32, device=dev)
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ex.match_batch(dA, nA, dB, nB, out=mout, device=True, stream=stream.cuda_stream)
+        m0.record(stream)
+        for _ in range(5):
+            ex.match_batch(dA, nA, dB, nB, out=mout, device=True, stream=stream.cuda_stream)
+        m1.record(stream)
+    barrier()
+    match_ms = m0.elapsed_time(m1) / 5
+    pairs = float((nA.double() * nB.double()).sum().item())
+    tm = torch.tensor([match_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    pairs_per_s = world * pairs / (float(tm.item()) * 1e-3)
+
+    # ---- the one collective of the job: gather the result slabs of (a slice of) the batch on rank 0 over NCCL
+    gather_ms = None
+    if world > 1:
+        gn = min(frames_per_gpu, 512)
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        got = sharding.gather_slabs([kps[:gn], desc[:gn], cnt[:gn]], gn * world)
+        g1.record()
+        torch.cuda.synchronize(dev)
+        gather_ms = g0.elapsed_time(g1)
+        if rank == 0:
+            assert got[0].shape[0] == gn * world and torch.equal(got[2][:gn], cnt[:gn])
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nframes_total = frames_per_gpu * args.steps
+        stages = {}
+        for s in ("pyramid", "fast", "select", "blur", "describe"):
+            ms = stage_ms[s]
+            gbs = sbytes[s] * nframes_total / (ms * 1e-3) / 1e9 if ms > 0 else None
+            stages[s] = {"ms_per_step": ms / args.steps, "launches_per_step": stage_launches[s] / args.steps,
+                         "bytes_per_frame": sbytes[s], "gbs": gbs, "frac": gbs / peak if gbs else None}
+        hbm_stages = ("pyramid", "fast", "blur")
+        dom = max(hbm_stages, key=lambda s: stage_ms[s])
+        kernel_name = {"pyramid": "resize_level_kernel", "fast": "fast_all_kernel", "blur": "blur_all_kernel"}[dom]
+        n_launch = max(1, stage_launches[dom])
+        avg_launch_s = stage_ms[dom] * 1e-3 / n_launch
+        bytes_per_launch = sbytes[dom] * nframes_total / n_launch
+        achieved = bytes_per_launch / avg_launch_s / 1e9
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = prof.get(kernel_name, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": world * frames_per_gpu * args.steps / (ms_total_max * 1e-3), "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": args.workload, "width": w, "height": h, "nfeatures": nf, "scale_factor": sf, "nlevels": nl,
+                       "th_fast": th, "frames_per_gpu_per_step": frames_per_gpu, "frames_per_pass": args.pass_frames,
+                       "generator": "smooth_noise, %d distinct frames per rank + column rotations" % DISTINCT,
+                       "l2": "batch (%.0f MB of frames per step) larger than the 126 MB L2; no flush" % (frames_per_gpu * w * h / 1e6),
+                       "sharding": "frame-wise, no collective in the loop; final NCCL gather timed separately"},
+            "e2e": {"value": world * frames_per_gpu * e2e_steps / e2e_s, "unit": "frames/s", "steps": e2e_steps,
+                    "h2d_bytes_per_step": int(host.numel()), "d2h_bytes_per_step": int(hk.numel() * 4 + hd.numel() + hc.numel() * 4),
+                    "matches_resident_run": same},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
+                         "frac_of_nominal_8000": achieved / 8000.0},
+            "stages": stages,
+            "keypoints_per_frame": mean_kp,
+            "hamming": {"value": pairs_per_s, "unit": "pairs/s", "pairs_per_frame_pair": pairs / max(npairs, 1),
+                        "frame_pairs_per_gpu": npairs, "ms": float(tm.item())},
+            "gather_ms": gather_ms,
+        }
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            native_oracle()
+            sample_n = max(2 * cores, 32)
+            fps_n, _ = cpu_extract_rate(params, host_np[:sample_n], cores)
+            fps_1, _ = cpu_extract_rate(params, host_np[:16], 1)
+            ham_n = cpu_match_rate(cores, max(cores, 8), np.random.default_rng(0))
+            line["cpu_baseline"] = {"value": fps_n, "unit": "frames/s", "cores": cores, "kind": "port",
+                                    "sample": "first %d frames of the same batch, oracle port, %d threads frame-parallel" % (sample_n, cores),
+                                    "value_1core": fps_1, "sample_1core": "first 16 frames, 1 thread (the reference's execution model)",
+                                    "hamming_pairs_per_s": ham_n}
+        print(json.dumps(line))
+    ex.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C3_tum_640x480_1000kp_8lv", choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default: the workload's)")
+    ap.add_argument("--pass-frames", type=int, default=512, help="frames per internal pass of the library (max_batch)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

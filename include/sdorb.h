@@ -144,8 +144,26 @@ SDORB_API int sdorb_match_greedy_batch(sdorb_handle* h, const uint8_t* descA, co
 SDORB_API int sdorb_hamming_matrix(sdorb_handle* h, const uint8_t* descA, int nA, const uint8_t* descB, int nB,
                          uint16_t* out, int mem, void* stream);
 
-/* ---- host helper used by the C++ shim: BORDER_REFLECT_101 margin around a level (src/ORBextractor.cc:692-696) ---- */
+/* ---- host helpers (pure CPU table arithmetic, usable without a CUDA device) ---- */
+/* BORDER_REFLECT_101 margin around a level (src/ORBextractor.cc:692-696), used by the C++ shim. */
 SDORB_API void sdorb_fill_border_reflect101(uint8_t* level_origin, int width, int height, size_t stride, int border);
+/* The constructor tables of src/ORBextractor.cc:406-457 without creating a handle: four float arrays and
+ * mnFeaturesPerLevel of nlevels entries each, umax of 16 entries.  Any pointer may be NULL. */
+SDORB_API int sdorb_host_tables(int nfeatures, float scale_factor, int nlevels, float* scale_factors,
+                      float* inv_scale_factors, float* level_sigma2, float* inv_level_sigma2,
+                      int* n_features_per_level, int* umax);
+/* Level size (src/ORBextractor.cc:683) and cell grid (src/ORBextractor.cc:469-488) of every level for a
+ * width x height input.  Returns SDORB_ERR_GEOMETRY where the reference would throw (see above). */
+typedef struct {
+  int width, height;   /* level image size */
+  int n_desired;       /* mnFeaturesPerLevel[level] */
+  int level_cols, level_rows;
+  int cell_w, cell_h;
+  int n_features_cell;
+  int scaled_patch_size;
+} sdorb_level_geom;
+SDORB_API int sdorb_host_level_geometry(int nfeatures, float scale_factor, int nlevels, int th_fast, int width,
+                              int height, sdorb_level_geom* out /* nlevels entries */);
 
 /* ---- instrumentation (bench.py / tests) ---- */
 #define SDORB_STAGE_PYRAMID 0

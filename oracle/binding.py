@@ -39,13 +39,38 @@ def build(force=False):
     return _SO
 
 
+def build_native():
+    """The same oracle compiled on THIS machine with the reference's optimisation flags (-O3 -march=native,
+    /root/reference/CMakeLists.txt:39-40) for the CPU baseline timing.  -ffp-contract=off stays: every FMA the
+    reference build contracts is an explicit fmaf() in the source, so results are unchanged (checked by the caller)."""
+    out_dir = os.path.join(_HERE, "_native")
+    os.makedirs(out_dir, exist_ok=True)
+    so = os.path.join(out_dir, "libsdorb_oracle_native.so")
+    subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math",
+                           "-pthread", "-shared", "-o", so, os.path.join(_HERE, "sdorb_oracle.cc"), "-lm"])
+    return so
+
+
+def use_native():
+    """Switch this module to the -march=native build (bench.py CPU legs).  Returns True when it is in use."""
+    global _lib, _SO
+    try:
+        so = build_native()
+    except Exception:
+        return False
+    _SO = so
+    _lib = None
+    lib(path=so)
+    return True
+
+
 _lib = None
 
 
-def lib():
+def lib(path=None):
     global _lib
     if _lib is None:
-        _lib = C.CDLL(build())
+        _lib = C.CDLL(path or build())
         L = _lib
         vp, i, sz, f = C.c_void_p, C.c_int, C.c_size_t, C.c_float
         L.orc_resize_linear_8u.argtypes = [vp, i, i, sz, vp, i, i, sz]

@@ -70,6 +70,8 @@ def lib():
     L.sdorb_hamming_matrix.argtypes = [vp, vp, i, vp, i, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
     L.sdorb_fill_border_reflect101.restype = None
+    L.sdorb_host_tables.argtypes = [i, f, i] + [vp] * 6
+    L.sdorb_host_level_geometry.argtypes = [i, f, i, i, i, i, vp]
     L.sdorb_set_profiling.argtypes = [vp, i]
     L.sdorb_get_stage_times.argtypes = [vp, vp, vp, i]
     L.sdorb_kernel_launches.argtypes = [vp]
@@ -88,6 +90,30 @@ def _ptr(a):
     if hasattr(a, "data_ptr"):  # torch tensor
         return C.c_void_p(a.data_ptr())
     return C.c_void_p(int(a))
+
+
+GEOM_DTYPE = np.dtype([(n, "<i4") for n in ("width", "height", "n_desired", "level_cols", "level_rows", "cell_w",
+                                             "cell_h", "n_features_cell", "scaled_patch_size")])
+
+
+def host_tables(nfeatures, scaleFactor, nlevels):
+    """The constructor tables (src/ORBextractor.cc:406-457) computed on the host; needs no GPU."""
+    sf, isf, s2, is2 = (np.empty(nlevels, np.float32) for _ in range(4))
+    npl, umax = np.empty(nlevels, np.int32), np.empty(16, np.int32)
+    rc = lib().sdorb_host_tables(nfeatures, scaleFactor, nlevels, _ptr(sf), _ptr(isf), _ptr(s2), _ptr(is2), _ptr(npl),
+                                 _ptr(umax))
+    if rc:
+        raise SdorbError(rc, lib().sdorb_strerror(rc).decode())
+    return dict(scale=sf, inv_scale=isf, sigma2=s2, inv_sigma2=is2, n_per_level=npl, umax=umax)
+
+
+def host_level_geometry(nfeatures, scaleFactor, nlevels, thFAST, width, height):
+    """Level sizes and cell grids (src/ORBextractor.cc:469-488, 683) for one input size; needs no GPU."""
+    g = np.zeros(nlevels, GEOM_DTYPE)
+    rc = lib().sdorb_host_level_geometry(nfeatures, scaleFactor, nlevels, thFAST, width, height, _ptr(g))
+    if rc:
+        raise SdorbError(rc, lib().sdorb_strerror(rc).decode())
+    return g
 
 
 class ORBextractor:

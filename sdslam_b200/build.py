@@ -53,7 +53,8 @@ def build(force=False, verbose=False):
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    subprocess.check_call([_nvcc(), "-shared", "-o", SO] + objs + ["-Xlinker", "--exclude-libs,ALL"])
+    subprocess.check_call([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", SO] + objs +
+                          ["-Xlinker", "--exclude-libs,ALL"])
     return SO
 
 

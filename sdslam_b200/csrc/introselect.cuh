@@ -82,6 +82,9 @@ SDORB_HD void nth_element_resp(uint32_t* a, int first, int nth, int last) {
   int depth = 2 * lg;
   while (last - first > 3) {
     if (depth == 0) {
+#ifdef SDORB_INTROSELECT_TRACE
+      SDORB_INTROSELECT_TRACE;
+#endif
       heap_select(a, first, nth + 1, last);
       swap_u32(a, first, nth);
       return;

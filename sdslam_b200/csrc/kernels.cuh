@@ -19,7 +19,8 @@ struct BatchPlanes {
 };
 
 struct SelectBuffers {
-  int32_t* cell_count;  // [batch][cells_total]
+  int32_t* cell_count;  // [batch][cells_total]  append counters of the FAST kernel; zero between passes
+  int32_t* cell_seen;   // [batch][cells_total]  copy of the counters of the last pass, written by the select kernel
   uint32_t* cell_list;  // [batch][list_total]
   uint32_t* sel;        // [batch][sel_total]  selected entries, level-major, in output order
   int32_t* sel_count;   // [batch][nlevels]

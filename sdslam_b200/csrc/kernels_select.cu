@@ -68,9 +68,15 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const FrameGeom* __
     if (tid == 0) *out_count = 0;
     return;
   }
-  const int32_t* cnt = buf.cell_count + (int64_t)frame * geom->cells_total + L.cell_base;
+  int32_t* cnt = buf.cell_count + (int64_t)frame * geom->cells_total + L.cell_base;
+  int32_t* seen = buf.cell_seen + (int64_t)frame * geom->cells_total + L.cell_base;
   uint32_t* lists = buf.cell_list + (int64_t)frame * geom->list_total + L.list_base;
-  for (int c = tid; c < n_cells; c += SEL_THREADS) n_total[c] = min(cnt[c], L.list_cap_cell);
+  for (int c = tid; c < n_cells; c += SEL_THREADS) {
+    const int n = cnt[c];
+    n_total[c] = min(n, L.list_cap_cell);
+    seen[c] = n;  // what FAST found (parity tests read this)
+    cnt[c] = 0;   // re-arm the append counters for the next pass: the FAST stage stays a single kernel
+  }
   __syncthreads();
 
   if (tid == 0) {

@@ -39,7 +39,7 @@ struct sdorb_handle {
   // scratch for max_batch frames of the current geometry
   uint8_t *d_pyr = nullptr, *d_blur = nullptr;
   uint8_t* d_stage_in[2] = {nullptr, nullptr};
-  int32_t *d_cell_count = nullptr, *d_sel_count = nullptr, *d_error = nullptr;
+  int32_t *d_cell_count = nullptr, *d_cell_seen = nullptr, *d_sel_count = nullptr, *d_error = nullptr;
   uint32_t *d_cell_list = nullptr, *d_sel = nullptr;
   // output staging for the host path (2 slots)
   sdorb_keypoint* d_kps[2] = {nullptr, nullptr};
@@ -98,6 +98,7 @@ void free_geometry_scratch(sdorb_handle* h) {
   dfree(h->d_stage_in[0]);
   dfree(h->d_stage_in[1]);
   dfree(h->d_cell_count);
+  dfree(h->d_cell_seen);
   dfree(h->d_cell_list);
   dfree(h->d_sel);
   dfree(h->d_sel_count);
@@ -136,7 +137,11 @@ int ensure_geometry(sdorb_handle* h, int width, int height) {
   if (!taps.empty()) CU(cudaMemcpy(h->d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice));
   CU(cudaMalloc(&h->d_pyr, (size_t)g.plane_total * B + 256));
   CU(cudaMalloc(&h->d_blur, (size_t)g.plane_total * B + 256));
-  CU(cudaMalloc(&h->d_cell_count, sizeof(int32_t) * std::max<size_t>((size_t)g.cells_total * B, 1)));
+  const size_t cells_bytes = sizeof(int32_t) * std::max<size_t>((size_t)g.cells_total * B, 1);
+  CU(cudaMalloc(&h->d_cell_count, cells_bytes));
+  CU(cudaMalloc(&h->d_cell_seen, cells_bytes));
+  CU(cudaMemset(h->d_cell_count, 0, cells_bytes));  // the select kernel re-zeroes what the FAST kernel counted
+  CU(cudaMemset(h->d_cell_seen, 0, cells_bytes));
   CU(cudaMalloc(&h->d_cell_list, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
   CU(cudaMalloc(&h->d_sel, sizeof(uint32_t) * std::max<size_t>((size_t)g.sel_total * B, 1)));
   CU(cudaMalloc(&h->d_sel_count, sizeof(int32_t) * (size_t)g.nlevels * B));
@@ -207,7 +212,7 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
   planes.pyr = h->d_pyr;
   planes.blur = h->d_blur;
   planes.batch_cap = h->prm.max_batch;
-  SelectBuffers sb{h->d_cell_count, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error};
+  SelectBuffers sb{h->d_cell_count, h->d_cell_seen, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error};
   {
     StageScope st(h, s, SDORB_STAGE_PYRAMID);
     for (int l = 1; l < g.nlevels; ++l) {
@@ -217,7 +222,6 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
   }
   {
     StageScope st(h, s, SDORB_STAGE_FAST);
-    CU(cudaMemsetAsync(h->d_cell_count, 0, sizeof(int32_t) * std::max<size_t>((size_t)g.cells_total * n, 1), s));
     if (g.tiles_total_fast > 0) {
       launch_fast_all(h->d_geom, g, planes, sb, n, s);
       st.launched();
@@ -487,6 +491,40 @@ void sdorb_fill_border_reflect101(uint8_t* origin, int width, int height, size_t
   }
 }
 
+int sdorb_host_tables(int nfeatures, float scale_factor, int nlevels, float* sf, float* isf, float* s2, float* is2,
+                      int* npl, int* umax) {
+  if (nfeatures < 0 || nlevels <= 0 || nlevels > SDORB_MAX_LEVELS || !(scale_factor > 0.f)) return SDORB_ERR_BAD_ARG;
+  Tables t;
+  build_tables(nfeatures, scale_factor, nlevels, &t);
+  for (int i = 0; i < nlevels; ++i) {
+    if (sf) sf[i] = t.scale[i];
+    if (isf) isf[i] = t.inv_scale[i];
+    if (s2) s2[i] = t.sigma2[i];
+    if (is2) is2[i] = t.inv_sigma2[i];
+    if (npl) npl[i] = t.n_per_level[i];
+  }
+  if (umax)
+    for (int i = 0; i <= SDORB_HALF_PATCH; ++i) umax[i] = t.umax[i];
+  return SDORB_OK;
+}
+
+int sdorb_host_level_geometry(int nfeatures, float scale_factor, int nlevels, int th_fast, int width, int height,
+                              sdorb_level_geom* out) {
+  if (!out || nfeatures < 0 || nlevels <= 0 || nlevels > SDORB_MAX_LEVELS || !(scale_factor > 0.f))
+    return SDORB_ERR_BAD_ARG;
+  Tables t;
+  build_tables(nfeatures, scale_factor, nlevels, &t);
+  FrameGeom g;
+  std::vector<ResizeTap> taps;
+  const int ge = build_frame_geom(t, nfeatures, th_fast, width, height, &g, &taps);
+  if (ge) return geom_err(ge);
+  for (int l = 0; l < nlevels; ++l) {
+    const LevelGeom& L = g.lv[l];
+    out[l] = sdorb_level_geom{L.w, L.h, L.n_desired, L.cols, L.rows, L.cell_w, L.cell_h, L.n_features_cell, L.scaled_patch_size};
+  }
+  return SDORB_OK;
+}
+
 int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, size_t stride, sdorb_keypoint* keypoints,
                   uint8_t* descriptors, int capacity, int* count, const sdorb_pyr_view* pyramid) {
   if (!h) return SDORB_ERR_BAD_ARG;
@@ -677,7 +715,7 @@ int64_t sdorb_debug_read(sdorb_handle* h, int what, int frame, int level, void* 
     case SDORB_DBG_CELL_COUNTS: {
       const size_t n = (L.cols > 0 && L.rows > 0) ? (size_t)L.cols * L.rows : 0;
       if (capacity < n * 4) return SDORB_ERR_CAPACITY;
-      if (n) CU(cudaMemcpy(dst, h->d_cell_count + (size_t)frame * g.cells_total + L.cell_base, n * 4, cudaMemcpyDeviceToHost));
+      if (n) CU(cudaMemcpy(dst, h->d_cell_seen + (size_t)frame * g.cells_total + L.cell_base, n * 4, cudaMemcpyDeviceToHost));
       return (int64_t)(n * 4);
     }
     case SDORB_DBG_LEVEL_SELECTED: {

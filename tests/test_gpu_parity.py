@@ -1,0 +1,390 @@
+"""Parity of the CUDA path (libsdorb.so, called through its C ABI via ctypes) with the CPU oracle and the committed
+cv2-generated fixtures.  Bit-exact everywhere: keypoint x / y / size / angle / response / octave / class_id and their
+ORDER, descriptors, pyramid bytes (the bar of BASELINE.md section 6; the 1e-3 degree angle tolerance of the north
+star is met with 0).  Needs a B200: run with  pytest -m gpu.
+"""
+import ctypes as C
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import binding as orc
+from sdslam_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+CASES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")) if "hamming" not in p)
+C1 = (1000, 1.2, 8, 20)
+
+
+def kp_view(a):
+    return np.ascontiguousarray(a).view(api.KP_DTYPE)
+
+
+def assert_same(ok, od, gk, gd, what=""):
+    assert len(ok) == len(gk), "%s: %d oracle vs %d gpu keypoints" % (what, len(ok), len(gk))
+    for f in api.KP_DTYPE.names:
+        bad = np.flatnonzero(ok[f] != gk[f])
+        assert len(bad) == 0, "%s: kp.%s differs at %s (first: oracle %r gpu %r)" % (what, f, bad[:5], ok[f][bad[0]], gk[f][bad[0]])
+    assert ok.tobytes() == gk.tobytes()
+    assert np.array_equal(od, gd), "%s: %d descriptor rows differ" % (what, int((od != gd).any(axis=1).sum()))
+
+
+@pytest.fixture(scope="module")
+def ex_c1():
+    e = api.ORBextractor(*C1, max_width=752, max_height=480, max_batch=8)
+    yield e
+    e.close()
+
+
+# ------------------------------------------------------------------ fixtures made with real cv2
+@pytest.mark.parametrize("name", CASES)
+def test_golden_fixture(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    p = g["params"]
+    params = (int(p[0]), float(p[1]), int(p[2]), int(p[3]))
+    img = g["image"]
+    ex = api.ORBextractor(*params, max_width=img.shape[1], max_height=img.shape[0], max_batch=2)
+    k, d, pyr = ex(img)
+    assert_same(g["kps"].astype(api.KP_DTYPE), g["desc"].reshape(-1, 32), k, d, name)
+    assert len(pyr) == params[2]
+    for lvl, ((h, w), sha) in enumerate(zip(g["pyramid_shape"], g["pyramid_sha256"])):
+        assert pyr[lvl].shape == (int(h), int(w))
+        assert hashlib.sha256(np.ascontiguousarray(pyr[lvl]).tobytes()).hexdigest() == str(sha), "pyramid level %d" % lvl
+    ex.close()
+
+
+# ------------------------------------------------------------------ stage by stage against the oracle
+@pytest.mark.parametrize("label,img,params", [
+    ("c1_smooth", synth.smooth_noise(40), C1),
+    ("c1_rects", synth.rects(41), C1),
+    ("c0_default", synth.smooth_noise(42), (1000, 2.0, 5, 20)),
+    ("c2", synth.smooth_noise(43, 752, 480), C1),
+    ("ini_2000", synth.smooth_noise(44), (2000, 1.2, 8, 20)),
+    ("odd_size", synth.smooth_noise(45, 333, 257), (700, 1.2, 6, 12)),
+    ("portrait", synth.smooth_noise(46, 240, 400), (400, 1.3, 5, 20)),
+    ("c5_small", synth.smooth_noise(47, 960, 540), (4000, 1.2, 12, 20)),
+    ("noise_th7", np.random.default_rng(48).integers(0, 256, (300, 400), dtype=np.uint8), (1500, 1.2, 8, 7)),
+    ("th_high", np.random.default_rng(49).integers(0, 256, (240, 320), dtype=np.uint8), (500, 1.2, 4, 140)),
+])
+def test_stages_match_oracle(label, img, params):
+    h, w = img.shape
+    o = orc.Extractor(*params)
+    ok, od, st = o.extract(img, dump=True)
+    ex = api.ORBextractor(*params, max_width=w, max_height=h, max_batch=3)
+    gk, gd, pyr = ex(img)
+    off = cell_off = 0
+    for l, g in enumerate(st["geometry"]):
+        lw, lh = int(g["width"]), int(g["height"])
+        n = lw * lh
+        assert np.array_equal(st["pyramid"][off:off + n].reshape(lh, lw), pyr[l]), "%s pyramid level %d" % (label, l)
+        nc = max(int(g["level_cols"]), 0) * max(int(g["level_rows"]), 0)
+        okl = ok[ok["octave"] == l]
+        if len(okl):  # the reference only blurs levels that have keypoints; the device blurs all of them
+            bl = ex.debug_read(api.DBG_BLURRED_LEVEL, 0, l, n).reshape(lh, lw)
+            assert np.array_equal(st["blurred"][off:off + n].reshape(lh, lw), bl), "%s blurred level %d" % (label, l)
+        if nc:
+            cc = ex.debug_read(api.DBG_CELL_COUNTS, 0, l, nc * 4, np.int32)
+            assert np.array_equal(cc, st["raw_cell_count"][cell_off:cell_off + nc]), "%s FAST counts level %d" % (label, l)
+        sel = ex.debug_read(api.DBG_LEVEL_SELECTED, 0, l, 4 * max(int(g["n_desired"]), 1), np.uint32)
+        assert len(sel) == len(okl) == int(st["level_count"][l])
+        off += n
+        cell_off += nc
+    assert_same(ok, od, gk, gd, label)
+    ex.close()
+
+
+# ------------------------------------------------------------------ entry-point equivalence
+def test_batch_host_equals_single_and_oracle(ex_c1):
+    imgs = synth.frames(5, 640, 480, start=60)
+    imgs[3] = synth.rects(3)
+    kps, desc, cnt = ex_c1.extract_batch_host(imgs)
+    o = orc.Extractor(*C1)
+    for f in range(len(imgs)):
+        ok, od = o.extract(imgs[f])
+        assert_same(ok, od, kps[f, :cnt[f]], desc[f, :cnt[f]], "batch frame %d" % f)
+        sk, sd, _ = ex_c1(imgs[f], want_pyramid=False)
+        assert sk.tobytes() == ok.tobytes() and np.array_equal(sd, od)
+
+
+def test_batch_larger_than_max_batch_and_ragged_tail(ex_c1):
+    """19 frames through passes of max_batch=8 (two full passes + a tail of 3), three-stream pipeline."""
+    base = synth.frames(4, 640, 480, start=70)
+    imgs = np.concatenate([base] * 5)[:19]
+    kps, desc, cnt = ex_c1.extract_batch_host(imgs)
+    for f in range(19):
+        assert cnt[f] == cnt[f % 4] and kps[f].tobytes() == kps[f % 4].tobytes() and desc[f].tobytes() == desc[f % 4].tobytes()
+    o = orc.Extractor(*C1)
+    ok, od = o.extract(base[2])
+    assert_same(ok, od, kps[18, :cnt[18]], desc[18, :cnt[18]])
+
+
+def test_device_entry_point_equals_host_entry_point(ex_c1):
+    torch = pytest.importorskip("torch")
+    imgs = synth.frames(6, 640, 480, start=80)
+    hk, hd, hc = ex_c1.extract_batch_host(imgs)
+    dev = torch.device("cuda:0")
+    cap = ex_c1.max_keypoints
+    t_img = torch.from_numpy(imgs).to(dev)
+    k = torch.zeros((6, cap, 7), dtype=torch.float32, device=dev)
+    d = torch.zeros((6, cap, 32), dtype=torch.uint8, device=dev)
+    c = torch.zeros(6, dtype=torch.int32, device=dev)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        ex_c1.extract_batch_device(t_img, k, d, c, stream=s.cuda_stream)
+    s.synchronize()
+    ex_c1.batch_status()
+    assert np.array_equal(c.cpu().numpy(), hc)
+    for f in range(6):
+        n = int(hc[f])
+        assert kp_view(k[f, :n].cpu().numpy()).reshape(-1).tobytes() == hk[f, :n].tobytes()
+        assert np.array_equal(d[f, :n].cpu().numpy(), hd[f, :n])
+
+
+def test_strided_and_unaligned_inputs(ex_c1):
+    """cv::Mat inputs may be ROIs: row stride > width, base pointer not 16-byte aligned."""
+    big = np.zeros((500, 700), np.uint8)
+    img = synth.smooth_noise(90)
+    big[7:487, 13:653] = img
+    view = big[7:487, 13:653]
+    assert view.strides[0] == 700 and view.ctypes.data % 4 != 0
+    k, d, _ = ex_c1(view, want_pyramid=False)
+    ok, od = orc.Extractor(*C1).extract(img)
+    assert_same(ok, od, k, d, "strided view")
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    t = torch.zeros((2, 480, 651), dtype=torch.uint8, device=dev)  # odd pitch: the library repacks level 0
+    t[:, :, :640] = torch.from_numpy(np.stack([img, img])).to(dev)
+    cap = ex_c1.max_keypoints
+    kk = torch.zeros((2, cap, 7), dtype=torch.float32, device=dev)
+    dd = torch.zeros((2, cap, 32), dtype=torch.uint8, device=dev)
+    cc = torch.zeros(2, dtype=torch.int32, device=dev)
+    ex_c1.extract_batch_device(t[:, :, :640], kk, dd, cc)
+    torch.cuda.synchronize()
+    ex_c1.batch_status()
+    for f in range(2):
+        assert int(cc[f]) == len(ok)
+        assert kp_view(kk[f, :len(ok)].cpu().numpy()).reshape(-1).tobytes() == ok.tobytes()
+        assert np.array_equal(dd[f, :len(ok)].cpu().numpy(), od)
+
+
+def test_geometry_switch_on_one_handle(ex_c1):
+    """One handle serves different image sizes (Tracking feeds whatever the camera delivers)."""
+    o = orc.Extractor(*C1)
+    for i, (w, h) in enumerate([(640, 480), (752, 480), (320, 240), (640, 480)]):
+        img = synth.smooth_noise(100 + i, w, h)
+        k, d, pyr = ex_c1(img)
+        ok, od = o.extract(img)
+        assert_same(ok, od, k, d, "%dx%d" % (w, h))
+
+
+# ------------------------------------------------------------------ edge cases of the reference
+def test_empty_image_leaves_outputs_untouched(ex_c1):
+    assert ex_c1(np.zeros((0, 0), np.uint8)) == (None, None, None)  # src/ORBextractor.cc:622-623
+    n = C.c_int(1234)
+    rc = api.lib().sdorb_extract(ex_c1._h, None, 0, 0, 0, None, None, 0, C.byref(n), None)
+    assert rc == 0 and n.value == 1234
+
+
+def test_zero_corner_images(ex_c1):
+    for img in (np.full((480, 640), 0, np.uint8), np.full((480, 640), 255, np.uint8), np.tile(np.arange(640, dtype=np.uint8), (480, 1))):
+        k, d, pyr = ex_c1(img)
+        ok, od = orc.Extractor(*C1).extract(img)
+        assert len(k) == len(ok) and (len(ok) == 0 or k.tobytes() == ok.tobytes())
+        assert d.shape == (len(ok), 32)
+
+
+def test_fewer_corners_than_quota():
+    img = np.full((240, 320), 90, np.uint8)
+    img[60:100, 80:140] = 200
+    img[150:190, 200:260] = 10
+    params = (500, 1.2, 6, 20)
+    ex = api.ORBextractor(*params, max_width=320, max_height=240, max_batch=1)
+    k, d, _ = ex(img)
+    ok, od = orc.Extractor(*params).extract(img)
+    assert 0 < len(ok) < 500
+    assert_same(ok, od, k, d)
+    ex.close()
+
+
+def test_massive_response_ties():
+    """Every corner of a regular dot grid has the same response, so all trims cut inside a tie."""
+    img = np.full((300, 400), 60, np.uint8)
+    img[10::6, 10::6] = 250
+    params = (300, 1.2, 4, 20)
+    ex = api.ORBextractor(*params, max_width=400, max_height=300, max_batch=1)
+    k, d, _ = ex(img)
+    ok, od = orc.Extractor(*params).extract(img)
+    assert len(ok) > 100 and len(np.unique(ok[ok["octave"] == 0]["response"])) <= 2
+    assert_same(ok, od, k, d)
+    ex.close()
+
+
+def test_too_small_image_is_geometry_error():
+    ex = api.ORBextractor(*C1, max_width=64, max_height=64, max_batch=1)
+    with pytest.raises(api.SdorbError) as e:
+        ex(np.zeros((30, 40), np.uint8))
+    assert e.value.code == -4  # the reference throws cv::Exception; the oracle reports the same
+    with pytest.raises(RuntimeError):
+        orc.Extractor(*C1).extract(np.zeros((30, 40), np.uint8))
+    ex.close()
+
+
+def test_error_codes(ex_c1):
+    img = synth.smooth_noise(0)
+    L = api.lib()
+    k = np.zeros(10, api.KP_DTYPE)
+    d = np.zeros((10, 32), np.uint8)
+    n = C.c_int(0)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.sdorb_extract(ex_c1._h, p(img), 640, 480, 640, p(k), p(d), 10, C.byref(n), None) == -2  # capacity
+    big = np.zeros((481, 800), np.uint8)
+    assert L.sdorb_extract(ex_c1._h, p(big), 800, 481, 800, p(k), p(d), 10, C.byref(n), None) in (-1, -2)
+    kk = np.zeros(1000, api.KP_DTYPE)
+    dd = np.zeros((1000, 32), np.uint8)
+    assert L.sdorb_extract(ex_c1._h, p(big), 800, 481, 800, p(kk), p(dd), 1000, C.byref(n), None) == -1  # > max_width
+    assert L.sdorb_extract(ex_c1._h, p(img), 640, 480, 100, p(kk), p(dd), 1000, C.byref(n), None) == -1  # stride < width
+
+
+def test_getters_match_oracle(ex_c1):
+    t = orc.Extractor(*C1).tables()
+    assert ex_c1.GetLevels() == 8 and ex_c1.GetScaleFactor() == float(np.float32(1.2))
+    assert ex_c1.GetScaleFactors().tobytes() == t["scale"].tobytes()
+    assert ex_c1.GetInverseScaleFactors().tobytes() == t["inv_scale"].tobytes()
+    assert ex_c1.GetScaleSigmaSquares().tobytes() == t["sigma2"].tobytes()
+    assert ex_c1.GetInverseScaleSigmaSquares().tobytes() == t["inv_sigma2"].tobytes()
+    assert ex_c1.features_per_level().tolist() == t["n_per_level"].tolist()
+
+
+def test_pyramid_output_has_reflect101_border(ex_c1):
+    """imagePyramid[l] is a view into a buffer padded by 19 px of BORDER_REFLECT_101 (src/ORBextractor.cc:684-696)."""
+    img = synth.smooth_noise(110)
+    _, _, pyr = ex_c1(img)
+    for l, lvl in enumerate(pyr):
+        padded = lvl.base if lvl.base is not None else None
+        assert padded is not None and padded.shape == (lvl.shape[0] + 38, lvl.shape[1] + 38)
+        assert np.array_equal(padded, orc.border_reflect101(np.ascontiguousarray(lvl), 19)), "level %d" % l
+    assert np.array_equal(pyr[0], img)
+
+
+# ------------------------------------------------------------------ full-size, size-independent properties
+def test_full_size_batch_properties():
+    """256 frames of the C3 shape: every frame yields exactly 1000 keypoints; the run is idempotent; a frame's
+    result does not depend on its batch neighbours; all keypoints respect the 19-px edge and level-major order."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    base = synth.frames(8, 640, 480, start=200)
+    imgs = torch.from_numpy(np.concatenate([base] * 32)).to(dev)
+    ex = api.ORBextractor(*C1, max_width=640, max_height=480, max_batch=256)
+    cap = ex.max_keypoints
+    outs = []
+    for _ in range(2):
+        k = torch.zeros((256, cap, 7), dtype=torch.float32, device=dev)
+        d = torch.zeros((256, cap, 32), dtype=torch.uint8, device=dev)
+        c = torch.zeros(256, dtype=torch.int32, device=dev)
+        ex.extract_batch_device(imgs, k, d, c)
+        torch.cuda.synchronize()
+        ex.batch_status()
+        outs.append((k.cpu().numpy(), d.cpu().numpy(), c.cpu().numpy()))
+    (k1, d1, c1), (k2, d2, c2) = outs
+    assert (c1 == 1000).all()
+    assert k1.tobytes() == k2.tobytes() and d1.tobytes() == d2.tobytes() and np.array_equal(c1, c2)
+    for f in range(8, 256):
+        assert k1[f].tobytes() == k1[f % 8].tobytes() and d1[f].tobytes() == d1[f % 8].tobytes()
+    o = orc.Extractor(*C1)
+    for f in (0, 5):
+        ok, od = o.extract(base[f])
+        assert_same(ok, od, kp_view(k1[f]).reshape(-1)[:1000], d1[f, :1000], "frame %d" % f)
+    kv = kp_view(k1).reshape(256, cap)
+    assert (np.diff(kv["octave"], axis=1) >= 0).all()
+    sf = ex.GetScaleFactors()
+    x0, y0 = kv["x"] / sf[kv["octave"]], kv["y"] / sf[kv["octave"]]
+    assert (x0 > 18.99).all() and (y0 > 18.99).all()
+    ex.close()
+
+
+# ------------------------------------------------------------------ ORBmatcher::DescriptorDistance batched
+def test_hamming_matrix_golden(ex_c1):
+    g = np.load(os.path.join(GOLD, "hamming_96x80.npz"))
+    assert np.array_equal(ex_c1.hamming_matrix(g["A"], g["B"]), g["dist"])
+    m = api.ORBmatcher(ex_c1)
+    assert m.DescriptorDistance(g["A"][7], g["B"][5]) == 0
+    assert m.DescriptorDistance(np.zeros(32, np.uint8), np.full(32, 255, np.uint8)) == 256
+
+
+def test_match_batch_equals_oracle_ragged(ex_c1):
+    rng = np.random.default_rng(5)
+    npairs, sa, sb = 7, 300, 260
+    A = rng.integers(0, 256, (npairs, sa, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (npairs, sb, 32), dtype=np.uint8)
+    for p in range(npairs):  # near-duplicates so that some matches pass TH_LOW and the ratio test
+        idx = rng.integers(0, sb, 40)
+        flip = rng.integers(0, 256, (40, 32), dtype=np.uint8) & rng.integers(0, 256, (40, 32), dtype=np.uint8) & rng.integers(0, 256, (40, 32), dtype=np.uint8) & 0x11
+        A[p, :40] = B[p, idx] ^ flip
+    B[2, 17] = B[2, 3]  # exact duplicate train rows: first index wins
+    A[2, 0] = B[2, 3]
+    nA = np.array([300, 0, 299, 1, 128, 129, 257], np.int32)
+    nB = np.array([260, 100, 259, 260, 0, 1, 2], np.int32)
+    for ratio, th in ((0.75, 50), (0.6, 100), (0.9, 256)):
+        got = ex_c1.match_batch(A, nA, B, nB, ratio=ratio, th_low=th)
+        exp = orc.match_many(A, nA, B, nB, ratio=ratio, th_low=th)
+        for p in range(npairs):
+            assert got[p, :nA[p]].tobytes() == exp[p, :nA[p]].tobytes(), "pair %d ratio %g" % (p, ratio)
+    got = ex_c1.match_batch(A, nA, B, nB)
+    assert got[2, 0]["best_idx"] == 3 and got[2, 0]["best_dist"] == 0 and got[2, 0]["second_dist"] == 0
+    assert (got[4, :128]["best_idx"] == -1).all() and (got[4, :128]["best_dist"] == 256).all()
+    assert got["accepted"].sum() > 50
+
+
+def test_match_greedy_equals_oracle(ex_c1):
+    """SearchByPoints' vbMatched2 rule (src/ORBmatcher.cc:1228-1270)."""
+    rng = np.random.default_rng(6)
+    A = rng.integers(0, 256, (3, 200, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (3, 180, 32), dtype=np.uint8)
+    A[:, :60] = B[:, rng.integers(0, 180, 60)] ^ (rng.integers(0, 256, (3, 60, 32), dtype=np.uint8) & 0x21)
+    A[1, 100:130] = A[1, 10:40]  # several queries want the same train row
+    nA = np.array([200, 200, 150], np.int32)
+    nB = np.array([180, 170, 180], np.int32)
+    got = ex_c1.match_batch(A, nA, B, nB, ratio=0.9, th_low=60, greedy=True)
+    for p in range(3):
+        exp = orc.match_best2(A[p, :nA[p]], B[p, :nB[p]], ratio=0.9, th_low=60, greedy=True)
+        assert got[p, :nA[p]].tobytes() == exp.tobytes()
+    plain = ex_c1.match_batch(A, nA, B, nB, ratio=0.9, th_low=60)
+    assert plain.tobytes() != got.tobytes()  # the greedy mask changed something
+
+
+def test_match_full_size_properties(ex_c1):
+    """1000 x 1000 (the BASELINE C4 shape) on real ORB descriptors: best/second-best agree with the distance matrix,
+    and matching a set against itself returns the identity with distance 0."""
+    imgs = synth.frames(2, 640, 480, start=300)
+    k, d, c = ex_c1.extract_batch_host(imgs)
+    assert (c == 1000).all()
+    A, B = d[0:1], d[1:2]
+    n = np.array([1000], np.int32)
+    m = ex_c1.match_batch(A, n, B, n)[0]
+    dist = ex_c1.hamming_matrix(A[0], B[0]).astype(np.int32)
+    assert np.array_equal(dist, orc.hamming_matrix(A[0], B[0]))
+    assert np.array_equal(dist, ex_c1.hamming_matrix(B[0], A[0]).T)
+    assert np.array_equal(m["best_idx"], dist.argmin(axis=1)) and np.array_equal(m["best_dist"], dist.min(axis=1))
+    assert np.array_equal(m["second_dist"], np.sort(dist, axis=1)[:, 1])
+    assert m.tobytes() == orc.match_best2(A[0], B[0]).tobytes()
+    self_m = ex_c1.match_batch(A, n, A, n)[0]
+    dself = ex_c1.hamming_matrix(A[0], A[0])
+    assert (np.diag(dself) == 0).all() and (self_m["best_dist"] == 0).all()
+    assert np.array_equal(self_m["best_idx"], dself.argmin(axis=1))
+
+
+def test_kernel_launch_accounting(ex_c1):
+    before = ex_c1.kernel_launches()
+    ex_c1(synth.smooth_noise(0), want_pyramid=False)
+    assert ex_c1.kernel_launches() - before >= 5
+    ex_c1.set_profiling(True)
+    ex_c1.stage_times(reset=True)
+    ex_c1(synth.smooth_noise(0), want_pyramid=False)
+    ms, launches = ex_c1.stage_times()
+    ex_c1.set_profiling(False)
+    assert all(ms[s] > 0 for s in ("pyramid", "fast", "select", "blur", "describe"))
+    assert launches["fast"] >= 1 and launches["pyramid"] >= 1
