@@ -195,8 +195,8 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
     // flattened tile tables
     L.tile_base_fast = tile_fast;
     if (any_detect) {
-      L.tiles_x_fast = (L.det_x1 - 16 + SDORB_FAST_TW - 1) / SDORB_FAST_TW;
-      L.tiles_y_fast = (L.det_y1 - 16 + SDORB_FAST_TH - 1) / SDORB_FAST_TH;
+      L.tiles_x_fast = (L.det_x1 - 18 + SDORB_FAST_TW - 1) / SDORB_FAST_TW;
+      L.tiles_y_fast = (L.det_y1 - SDORB_EDGE + SDORB_FAST_TH - 1) / SDORB_FAST_TH;
     }
     tile_fast += L.tiles_x_fast * L.tiles_y_fast;
     L.tile_base_blur = tile_blur;

@@ -2,91 +2,157 @@
 //
 // Reference: ComputeKeyPoints runs cv::FAST separately on every grid cell of every level
 // (/root/reference/src/ORBextractor.cc:495-536).  Restated per pixel (OpenCV features2d/fast.cpp, fast_score.cpp):
-//   d[k] = v - ring[k];  A = max over the 16 nine-pixel arcs of min(d),  B = max over arcs of min(-d)
-//   corner  <=>  max(A,B) > th ;  score = max(A,B) - 1 ;  keypoint <=> score strictly greater than the 8
+//   A  = max over the 16 nine-pixel arcs of  min (v - ring),   B' = max over arcs of  min (ring - v)
+//   corner  <=>  max(A,B') > th ;  score = max(A,B') - 1 ;  keypoint <=> score strictly greater than the 8
 //   neighbouring scores, where neighbours outside the cell's own detectable rectangle count as 0.
-// The score does not depend on the cell, so one kernel scores whole-level tiles and applies the cell rule
-// only in the non-max test.  Keypoints are appended to per-cell lists as SDORB_ENTRY(y,x,score); the order of
-// appends is arbitrary, the selection kernel sorts each list back into FAST's row-major emission order.
+// The score does not depend on the cell, so one kernel scores whole-level tiles and applies the cell rule only in the
+// non-max test.  Keypoints are appended to per-cell lists as SDORB_ENTRY(y,x,score) in arbitrary order; the selection
+// kernel sorts each list back into FAST's row-major emission order.
 //
-// Work per tile (128x32 outputs, 256 threads), three phases separated by block barriers:
-//   A  SWAR pre-test on 4 pixels per 32-bit word: VABSDIFF4 against the 4 compass ring pixels; any 9-arc
-//      contains one pixel of {0,8} and one of {4,12}, so  (|d0|>th or |d8|>th) and (|d4|>th or |d12|>th)
-//      is necessary.  Survivors are compacted into a shared-memory candidate list.
-//   B  one thread per candidate: the exact score with 3-input min/max (VIMNMX3) over the ring.
-//   C  one thread per candidate: cell-bounded strict non-max test on the shared score tile, append.
+// The synthetic benchmark frames are corner-dense (17 % of all pixels are FAST corners, 70 % pass the usual compass
+// pre-test), so the kernel scores DENSELY and branch-free instead of compacting candidates:
+//   * one thread owns one 32-bit word = 4 pixels; a warp owns 128 pixels of one row; everything is read from a
+//     shared-memory tile as aligned words and shuffled into place with PRMT;
+//   * min(v - r) over an arc is v - max(r) over the arc, so the arc minima / maxima are taken on the ring bytes
+//     themselves, two pixels at a time in 16-bit lanes (VIMNMX.U16x2, 3-input forms): 80 min/max + 16 PRMT per pixel pair;
+//     each lane carries its byte twice (value * 257), so lane order == byte order and no masking is needed;
+//   * scores are kept as t = max(score + 1 - th, 0) in one byte per pixel; the 3x3 strict non-max test runs on the
+//     same packed lanes with per-column / per-row cell-boundary masks;
+//   * survivors are compacted warp-wise into a tile list, counted per cell in shared memory and appended to the global
+//     cell lists with one atomicAdd per (tile, cell).
+// A cheap 4-pixel SWAR compass test (VABSDIFF4) is kept only to skip pixel pairs no lane of the warp needs (flat image
+// regions).  The kernel is bound by the integer ALU pipe (min/max, PRMT), not by HBM: see DESIGN.md.
 #include "kernels.cuh"
 
 namespace sdorb {
 
-constexpr int TW = SDORB_FAST_TW, TH = SDORB_FAST_TH;
-constexpr int PW = TW + 8;   // staged pixel columns x0-4 .. x0+TW+3
-constexpr int PH = TH + 8;   // staged pixel rows    y0-4 .. y0+TH+3
-constexpr int SW = TW + 2;   // scored columns x0-1 .. x0+TW
-constexpr int SH = TH + 2;
-constexpr int SP = 132;      // score tile pitch
+constexpr int OW = SDORB_FAST_TW, OH = SDORB_FAST_TH;  // output pixels per tile: 124 x 30
+constexpr int SWORDS = 32;                             // scored words per row (128 px: outputs + 2 px on each side)
+constexpr int SROWS = OH + 2;                          // scored rows (outputs + 1 on each side)
+constexpr int PWORDS = SWORDS + 2;                     // staged pixel words per row (scored +- 4 px)
+constexpr int PROWS = SROWS + 6;                       // staged pixel rows (scored +- 3)
+constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in words (one zero word on each side)
 constexpr int NT = 256;
+constexpr int KEPT_CAP = (OW / 2 + 1) * (OH / 2 + 1);  // strict 3x3 NMS leaves at most one keypoint per 2x2 block
+constexpr int MAX_LOCAL_CELLS = 32;
 
-// per-byte (a > th) in bit 7 of each byte; C and hi prepared by the caller from th
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+
+// per-byte (a > th) in bit 7 of each byte; C prepared by the caller from th
 __device__ __forceinline__ uint32_t gt_th(uint32_t a, uint32_t C, bool th_high) {
   const uint32_t t = (a & 0x7f7f7f7fu) + C;
   return th_high ? (t & a) : (t | a);
 }
 
-__device__ __forceinline__ int corner_strength(const uint8_t* c, int pitch) {
-  // ring in OpenCV order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-  const int v = c[0];
-  int d[16];
-  d[0] = v - c[3 * pitch];
-  d[1] = v - c[3 * pitch + 1];
-  d[2] = v - c[2 * pitch + 2];
-  d[3] = v - c[pitch + 3];
-  d[4] = v - c[3];
-  d[5] = v - c[-pitch + 3];
-  d[6] = v - c[-2 * pitch + 2];
-  d[7] = v - c[-3 * pitch + 1];
-  d[8] = v - c[-3 * pitch];
-  d[9] = v - c[-3 * pitch - 1];
-  d[10] = v - c[-2 * pitch - 2];
-  d[11] = v - c[-pitch - 3];
-  d[12] = v - c[-3];
-  d[13] = v - c[pitch - 3];
-  d[14] = v - c[2 * pitch - 2];
-  d[15] = v - c[3 * pitch - 1];
-  int lo3[16], hi3[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    lo3[k] = __vimin3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
-    hi3[k] = __vimax3_s32(d[k], d[(k + 1) & 15], d[(k + 2) & 15]);
+// Packed pair (pixels 2p, 2p+1 of the word) of the bytes at horizontal offset dx in a row given as three words
+// (previous, own, next word): lane = byte * 257.
+template <int P, int DX>
+__device__ __forceinline__ uint32_t pair_at(const uint32_t w0, const uint32_t w1, const uint32_t w2) {
+  constexpr int i = 4 + 2 * P + DX;  // byte index in the 12-byte window
+  static_assert(i >= 1 && i <= 9, "offset out of window");
+  if (i <= 6) {
+    constexpr uint32_t s = i, sel = s | (s << 4) | ((s + 1) << 8) | ((s + 1) << 12);
+    return prmt(w0, w1, sel);
+  } else {
+    constexpr uint32_t s = i - 4, sel = s | (s << 4) | ((s + 1) << 8) | ((s + 1) << 12);
+    return prmt(w1, w2, sel);
   }
-  int A = -256, B = 256;
-#pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    A = max(A, __vimin3_s32(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]));  // min over arc k..k+8
-    B = min(B, __vimax3_s32(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]));  // max over arc k..k+8
-  }
-  return max(A, -B);
 }
 
-__global__ void __launch_bounds__(NT) fast_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, SelectBuffers buf) {
-  __shared__ __align__(16) uint8_t s_pix[PH][PW];
-  __shared__ __align__(16) uint8_t s_score[SH][SP];
-  __shared__ uint16_t s_cand[SW * SH];
-  __shared__ int s_ncand;
+// t = max(cornerScore + 1 - th, 0) for the two pixels of pair P, as two 16-bit lanes.  W[dy+3][0..2] are the staged
+// words of rows y-3..y+3 (previous / own / next word).
+template <int P>
+__device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const uint32_t th2) {
+  uint32_t r[16];
+  // ring in OpenCV order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
+  r[0] = pair_at<P, 0>(W[6][0], W[6][1], W[6][2]);
+  r[1] = pair_at<P, 1>(W[6][0], W[6][1], W[6][2]);
+  r[2] = pair_at<P, 2>(W[5][0], W[5][1], W[5][2]);
+  r[3] = pair_at<P, 3>(W[4][0], W[4][1], W[4][2]);
+  r[4] = pair_at<P, 3>(W[3][0], W[3][1], W[3][2]);
+  r[5] = pair_at<P, 3>(W[2][0], W[2][1], W[2][2]);
+  r[6] = pair_at<P, 2>(W[1][0], W[1][1], W[1][2]);
+  r[7] = pair_at<P, 1>(W[0][0], W[0][1], W[0][2]);
+  r[8] = pair_at<P, 0>(W[0][0], W[0][1], W[0][2]);
+  r[9] = pair_at<P, -1>(W[0][0], W[0][1], W[0][2]);
+  r[10] = pair_at<P, -2>(W[1][0], W[1][1], W[1][2]);
+  r[11] = pair_at<P, -3>(W[2][0], W[2][1], W[2][2]);
+  r[12] = pair_at<P, -3>(W[3][0], W[3][1], W[3][2]);
+  r[13] = pair_at<P, -3>(W[4][0], W[4][1], W[4][2]);
+  r[14] = pair_at<P, -2>(W[5][0], W[5][1], W[5][2]);
+  r[15] = pair_at<P, -1>(W[6][0], W[6][1], W[6][2]);
+  uint32_t lo3[16], hi3[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    lo3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+    hi3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+  }
+  uint32_t amin[16], amax[16];  // min / max of the ring over the arc k..k+8
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    amin[k] = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
+    amax[k] = __vimax3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+  }
+  uint32_t X = amax[15], Y = amin[15];  // X = min over arcs of the arc maximum, Y = max over arcs of the arc minimum
+#pragma unroll
+  for (int k = 0; k < 14; k += 2) {
+    X = __vimin3_u16x2(X, amax[k], amax[k + 1]);
+    Y = __vimax3_u16x2(Y, amin[k], amin[k + 1]);
+  }
+  X = __vminu2(X, amax[14]);
+  Y = __vmaxu2(Y, amin[14]);
+  // A = v - X, B' = Y - v per lane, biased by 256 so that the lanes never borrow
+  const uint32_t Xc = prmt(X, 0u, 0x4341), Yc = prmt(Y, 0u, 0x4341);
+  const uint32_t Vc = prmt(W[3][1], 0u, P == 0 ? 0x4140 : 0x4342);
+  const uint32_t A = Vc + 0x01000100u - Xc, B = Yc + 0x01000100u - Vc;
+  const uint32_t m = __vmaxu2(A, B);          // max(A, B') + 256
+  return __vmaxu2(m, th2) - th2;              // (max(A,B') - th) if positive, else 0;  th2 = (th + 256) per lane
+}
+
+struct Keep2 {
+  bool x, y;
+};
+
+// Strict 3x3 non-max test of the two pixels of pair P on packed score lanes (lane = byte * 257).  T[0..2] are the
+// score words of rows y-1, y, y+1 (previous / own / next word); lm / rm zero the neighbours that lie in another cell.
+template <int P>
+__device__ __forceinline__ Keep2 nms_pair(const uint32_t (&T)[3][3], const uint32_t lm, const uint32_t rm) {
+  const uint32_t c = pair_at<P, 0>(T[1][0], T[1][1], T[1][2]);
+  const uint32_t l = pair_at<P, -1>(T[1][0], T[1][1], T[1][2]) & lm, r = pair_at<P, 1>(T[1][0], T[1][1], T[1][2]) & rm;
+  const uint32_t u = pair_at<P, 0>(T[0][0], T[0][1], T[0][2]), d = pair_at<P, 0>(T[2][0], T[2][1], T[2][2]);
+  const uint32_t ul = pair_at<P, -1>(T[0][0], T[0][1], T[0][2]) & lm, ur = pair_at<P, 1>(T[0][0], T[0][1], T[0][2]) & rm;
+  const uint32_t dl = pair_at<P, -1>(T[2][0], T[2][1], T[2][2]) & lm, dr = pair_at<P, 1>(T[2][0], T[2][1], T[2][2]) & rm;
+  const uint32_t m1 = __vimax3_u16x2(l, r, u), m2 = __vimax3_u16x2(ul, ur, d), m3 = __vimax3_u16x2(dl, dr, m1);
+  const uint32_t nb = __vmaxu2(m2, m3);
+  const uint32_t diff = c - __vminu2(c, nb);  // lane != 0  <=>  centre strictly greater than all eight neighbours
+  Keep2 k;
+  k.x = (diff & 0xFFFFu) != 0;
+  k.y = (diff >> 16) != 0;
+  return k;
+}
+
+__global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, SelectBuffers buf) {
+  __shared__ __align__(16) uint32_t s_pix[PROWS][PWORDS];
+  __shared__ __align__(16) uint32_t s_t[SROWS][TWORDS];
+  __shared__ uint32_t s_kept[KEPT_CAP];
+  __shared__ int s_cell_cnt[MAX_LOCAL_CELLS], s_cell_base[MAX_LOCAL_CELLS];
+  __shared__ int s_nkept;
   __shared__ int s_level;
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     int l = 0;
     while (l + 1 < geom->nlevels && (int)blockIdx.x >= geom->lv[l + 1].tile_base_fast) ++l;
     s_level = l;
-    s_ncand = 0;
+    s_nkept = 0;
   }
+  if (tid < MAX_LOCAL_CELLS) s_cell_cnt[tid] = 0;
   __syncthreads();
   const int level = s_level;
   const LevelGeom& L = geom->lv[level];
   const int frame = blockIdx.y;
   const int t = blockIdx.x - L.tile_base_fast;
-  const int x0 = 16 + (t % L.tiles_x_fast) * TW, y0 = 16 + (t / L.tiles_x_fast) * TH;
+  const int a = 16 + (t % L.tiles_x_fast) * OW;            // first scored column (multiple of 4); outputs are [a+2, a+2+OW)
+  const int b = SDORB_EDGE + (t / L.tiles_x_fast) * OH;    // first output row; scored rows are [b-1, b+OH+1)
   const int w = L.w, h = L.h;
   const int th = geom->th_fast;
   int pitch;
@@ -99,106 +165,178 @@ __global__ void __launch_bounds__(NT) fast_all_kernel(const FrameGeom* __restric
     src = p.pyr + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
   }
 
-  // ---- stage pixels, clear scores
-  for (int i = tid; i < PH * (PW / 4); i += NT) {
-    const int r = i / (PW / 4), k = i % (PW / 4);
-    const int gy = y0 - 4 + r, gx = x0 - 4 + 4 * k;
+  // ---- stage pixels: rows b-4 .. b+OH+3, columns a-4 .. a+131 as aligned words; zero outside the image
+  for (int i = tid; i < PROWS * PWORDS; i += NT) {
+    const int r = i / PWORDS, k = i - r * PWORDS;
+    const int gy = b - 4 + r, gx = a - 4 + 4 * k;
     uint32_t v = 0;
-    if (gy >= 0 && gy < h) {
+    if (gy >= 0 && gy < h && gx < w) {
       const uint8_t* row = src + (int64_t)gy * pitch;
       if (gx + 4 <= w) {
         v = *reinterpret_cast<const uint32_t*>(row + gx);
       } else {
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          if (gx + b < w) v |= (uint32_t)row[gx + b] << (8 * b);
+        for (int q = 0; q < 4; ++q)
+          if (gx + q < w) v |= (uint32_t)row[gx + q] << (8 * q);
       }
     }
-    *reinterpret_cast<uint32_t*>(&s_pix[r][4 * k]) = v;
+    s_pix[r][k] = v;
   }
-  for (int i = tid; i < SH * SP / 4; i += NT) reinterpret_cast<uint32_t*>(&s_score[0][0])[i] = 0;
+  if (tid < SROWS) {
+    s_t[tid][0] = 0;
+    s_t[tid][TWORDS - 1] = 0;
+  }
   __syncthreads();
 
-  // ---- phase A: compass pre-test, 4 pixels per word.  Scored pixels: x in [x0-1, x0+TW+1) and inside
-  // the level's detectable area [19, det_x1) x [19, det_y1).
+  // ---- per-thread column constants: this lane owns pixels x = xw .. xw+3 in every row it touches
+  const int xw = a + 4 * lane;
+  const int vx1 = L.det_x1, vy1 = L.det_y1;  // detectable area is [19, det_x1) x [19, det_y1)
+  uint32_t valid_cols = 0;   // byte mask: pixel may carry a score
+  uint32_t out_cols = 0;     // bit q: pixel xw+q is an output column of this tile
+  uint32_t lm[2] = {0, 0}, rm[2] = {0, 0};  // 16-bit lane masks: left / right neighbour lies in the same cell
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int x = xw + q;
+    if (x >= SDORB_EDGE && x < vx1) {
+      valid_cols |= 0xFFu << (8 * q);
+      if (x >= a + 2 && x < a + 2 + OW) out_cols |= 1u << q;
+      const int cj = min((x - SDORB_EDGE) / L.cell_w, L.cols - 1);
+      const int cx0 = SDORB_EDGE + cj * L.cell_w;
+      const int cx1 = (cj == L.cols - 1) ? L.max_bx : cx0 + L.cell_w;
+      if (x - 1 >= cx0) lm[q >> 1] |= 0xFFFFu << (16 * (q & 1));
+      if (x + 1 < cx1) rm[q >> 1] |= 0xFFFFu << (16 * (q & 1));
+    }
+  }
   const bool th_high = th >= 128;
   const uint32_t C = (uint32_t)(127 - (th_high ? th - 128 : th)) * 0x01010101u;
-  const int vx0 = max(x0 - 1, SDORB_EDGE), vx1 = min(x0 + TW + 1, L.det_x1);
-  const int vy0 = max(y0 - 1, SDORB_EDGE), vy1 = min(y0 + TH + 1, L.det_y1);
-  for (int i = tid; i < SH * (PW / 4); i += NT) {
-    const int r = i / (PW / 4) + 3, k = i % (PW / 4);  // staged row r, word k
-    const int gy = y0 - 4 + r, gx = x0 - 4 + 4 * k;
-    if (gy < vy0 || gy >= vy1 || gx + 3 < vx0 || gx >= vx1) continue;
-    const uint32_t* rowc = reinterpret_cast<const uint32_t*>(&s_pix[r][0]);
-    const uint32_t c = rowc[k];
-    const uint32_t up = reinterpret_cast<const uint32_t*>(&s_pix[r - 3][0])[k];
-    const uint32_t dn = reinterpret_cast<const uint32_t*>(&s_pix[r + 3][0])[k];
-    const uint32_t wl = k > 0 ? rowc[k - 1] : 0u, wr = k + 1 < PW / 4 ? rowc[k + 1] : 0u;
-    const uint32_t lf = __byte_perm(wl, c, 0x4321);  // pixels x-3 .. x
-    const uint32_t rt = __byte_perm(c, wr, 0x6543);  // pixels x+3 .. x+6
-    const uint32_t fv = gt_th(__vabsdiffu4(up, c), C, th_high) | gt_th(__vabsdiffu4(dn, c), C, th_high);
-    const uint32_t fh = gt_th(__vabsdiffu4(lf, c), C, th_high) | gt_th(__vabsdiffu4(rt, c), C, th_high);
-    uint32_t m = fv & fh & 0x80808080u;
-    if (m == 0) continue;
-    // drop lanes outside the valid column range
-    int nb = 0;
-    uint16_t ids[4];
+  const uint32_t th2 = (uint32_t)(th + 256) * 0x00010001u;
+
+  // ---- phase S: dense scores.  Warp `warp` owns scored rows warp, warp+8, ...; scored row sr is image row b-1+sr
+  // and staged row sr+3; lane k owns scored word k = staged word k+1.
+  for (int sr = warp; sr < SROWS; sr += NT / 32) {
+    const int gy = b - 1 + sr;
+    uint32_t T = 0;
+    if (gy >= SDORB_EDGE && gy < vy1) {  // warp-uniform
+      uint32_t W[7][3];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int x = gx + b;
-      if (((m >> (8 * b + 7)) & 1u) && x >= vx0 && x < vx1) ids[nb++] = (uint16_t)((r << 8) | (4 * k + b));
+      for (int dy = 0; dy < 7; ++dy) {
+        W[dy][0] = s_pix[sr + dy][lane];
+        W[dy][1] = s_pix[sr + dy][lane + 1];
+        W[dy][2] = s_pix[sr + dy][lane + 2];
+      }
+      // compass pre-test on 4 pixels: a 9-arc contains one of ring {0,8} and one of ring {4,12}
+      const uint32_t c = W[3][1];
+      const uint32_t lf = prmt(W[3][0], c, 0x4321), rt = prmt(c, W[3][2], 0x6543);
+      const uint32_t fv = gt_th(__vabsdiffu4(W[0][1], c), C, th_high) | gt_th(__vabsdiffu4(W[6][1], c), C, th_high);
+      const uint32_t fh = gt_th(__vabsdiffu4(lf, c), C, th_high) | gt_th(__vabsdiffu4(rt, c), C, th_high);
+      const uint32_t cand = fv & fh & 0x80808080u & valid_cols;
+      uint32_t t0 = 0, t1 = 0;
+      if (__any_sync(0xffffffffu, cand & 0x00008080u)) t0 = score_pair<0>(W, th2);
+      if (__any_sync(0xffffffffu, cand & 0x80800000u)) t1 = score_pair<1>(W, th2);
+      T = prmt(t0, t1, 0x6420) & valid_cols;
     }
-    if (nb) {
-      const int base = atomicAdd(&s_ncand, nb);
-      for (int b = 0; b < nb; ++b) s_cand[base + b] = ids[b];
+    s_t[sr][lane + 1] = T;
+  }
+  __syncthreads();
+
+  // ---- phase N: cell-bounded strict non-max suppression on the score tile; survivors go to the tile list
+  for (int orow = warp; orow < OH; orow += NT / 32) {
+    const int sr = orow + 1, y = b + orow;
+    const uint32_t cw = s_t[sr][lane + 1];
+    uint32_t kept = 0;
+    if (__any_sync(0xffffffffu, cw != 0) ) {
+      if (y < vy1) {
+        const int ci = min((y - SDORB_EDGE) / L.cell_h, L.rows - 1);
+        const int cy0 = SDORB_EDGE + ci * L.cell_h;
+        const int cy1 = (ci == L.rows - 1) ? L.max_by : cy0 + L.cell_h;
+        const bool u_ok = y - 1 >= cy0, d_ok = y + 1 < cy1;
+        uint32_t Tn[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          Tn[0][j] = u_ok ? s_t[sr - 1][lane + j] : 0u;
+          Tn[1][j] = s_t[sr][lane + j];
+          Tn[2][j] = d_ok ? s_t[sr + 1][lane + j] : 0u;
+        }
+        const Keep2 k0 = nms_pair<0>(Tn, lm[0], rm[0]);
+        const Keep2 k1 = nms_pair<1>(Tn, lm[1], rm[1]);
+        kept = ((uint32_t)k0.x | ((uint32_t)k0.y << 1) | ((uint32_t)k1.x << 2) | ((uint32_t)k1.y << 3)) & out_cols;
+      }
+    }
+    while (true) {
+      const bool active = kept != 0;
+      const uint32_t bal = __ballot_sync(0xffffffffu, active);
+      if (bal == 0) break;
+      int base = 0;
+      if (lane == __ffs(bal) - 1) base = atomicAdd(&s_nkept, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
+      if (active) {
+        const int q = __ffs(kept) - 1;
+        const int tq = (cw >> (8 * q)) & 0xFF;
+        const int idx = base + __popc(bal & ((1u << lane) - 1u));
+        if (idx < KEPT_CAP) s_kept[idx] = SDORB_ENTRY(y, xw + q, tq + th - 1);
+        kept &= kept - 1;
+      }
     }
   }
   __syncthreads();
-  const int ncand = s_ncand;
 
-  // ---- phase B: exact score per candidate
-  for (int i = tid; i < ncand; i += NT) {
-    const int id = s_cand[i];
-    const int r = id >> 8, cx = id & 0xFF;
-    const int m = corner_strength(&s_pix[r][cx], PW);
-    if (m > th) s_score[r - 3][cx - 3] = (uint8_t)(m - 1);
-  }
-  __syncthreads();
-
-  // ---- phase C: cell-bounded strict non-max suppression, append to the cell list
-  for (int i = tid; i < ncand; i += NT) {
-    const int id = s_cand[i];
-    const int r = id >> 8, cx = id & 0xFF;
-    const int sy = r - 3, sx = cx - 3;  // score-tile coordinates; (1,1) is pixel (x0,y0)
-    if (sy < 1 || sy > TH || sx < 1 || sx > TW) continue;
-    const int s = s_score[sy][sx];
-    if (s == 0) continue;
-    const int x = x0 - 1 + sx, y = y0 - 1 + sy;
-    int cj = (x - SDORB_EDGE) / L.cell_w, ci = (y - SDORB_EDGE) / L.cell_h;
-    cj = min(cj, L.cols - 1);
-    ci = min(ci, L.rows - 1);
-    const int cx0 = SDORB_EDGE + cj * L.cell_w, cy0 = SDORB_EDGE + ci * L.cell_h;
-    const int cx1 = (cj == L.cols - 1) ? L.max_bx : cx0 + L.cell_w;
-    const int cy1 = (ci == L.rows - 1) ? L.max_by : cy0 + L.cell_h;
-    const bool l_ok = x - 1 >= cx0, r_ok = x + 1 < cx1, u_ok = y - 1 >= cy0, d_ok = y + 1 < cy1;
-    bool keep = true;
-    keep &= !l_ok || s > s_score[sy][sx - 1];
-    keep &= !r_ok || s > s_score[sy][sx + 1];
-    keep &= !u_ok || s > s_score[sy - 1][sx];
-    keep &= !d_ok || s > s_score[sy + 1][sx];
-    keep &= !(u_ok && l_ok) || s > s_score[sy - 1][sx - 1];
-    keep &= !(u_ok && r_ok) || s > s_score[sy - 1][sx + 1];
-    keep &= !(d_ok && l_ok) || s > s_score[sy + 1][sx - 1];
-    keep &= !(d_ok && r_ok) || s > s_score[sy + 1][sx + 1];
-    if (!keep) continue;
-    const int cell = ci * L.cols + cj;
-    int32_t* cnt = buf.cell_count + (int64_t)frame * geom->cells_total + L.cell_base + cell;
-    const int slot = atomicAdd(cnt, 1);
-    if (slot < L.list_cap_cell) {
-      uint32_t* list = buf.cell_list + (int64_t)frame * geom->list_total + L.list_base + (int64_t)cell * L.list_cap_cell;
-      list[slot] = SDORB_ENTRY(y, x, s);
-    } else {
-      atomicExch(buf.error_flag, 6);
+  // ---- phase A: count per cell in shared memory, reserve list ranges with one global atomic per (tile, cell), write
+  const int n = min(s_nkept, KEPT_CAP);
+  if (n == 0) return;
+  const int ox0 = max(a + 2, SDORB_EDGE), oy0 = b;
+  const int ox1 = min(a + 2 + OW, vx1) - 1, oy1 = min(b + OH, vy1) - 1;  // last output pixel that can hold a keypoint
+  const int cj0 = min((ox0 - SDORB_EDGE) / L.cell_w, L.cols - 1), ci0 = min((oy0 - SDORB_EDGE) / L.cell_h, L.rows - 1);
+  const int cj1 = min((max(ox1, ox0) - SDORB_EDGE) / L.cell_w, L.cols - 1), ci1 = min((max(oy1, oy0) - SDORB_EDGE) / L.cell_h, L.rows - 1);
+  const int ncx = cj1 - cj0 + 1, ncy = ci1 - ci0 + 1;
+  int32_t* counts = buf.cell_count + (int64_t)frame * geom->cells_total + L.cell_base;
+  uint32_t* lists = buf.cell_list + (int64_t)frame * geom->list_total + L.list_base;
+  if (ncx * ncy <= MAX_LOCAL_CELLS) {
+    // entries are re-read in the same order by the same threads, so the local rank can live in a register
+    int rank[(KEPT_CAP + NT - 1) / NT];
+    int lcell[(KEPT_CAP + NT - 1) / NT];
+#pragma unroll
+    for (int it = 0; it < (KEPT_CAP + NT - 1) / NT; ++it) {
+      const int i = tid + it * NT;
+      if (i < n) {
+        const uint32_t e = s_kept[i];
+        const int cj = min((SDORB_ENTRY_X(e) - SDORB_EDGE) / L.cell_w, L.cols - 1);
+        const int ci = min((SDORB_ENTRY_Y(e) - SDORB_EDGE) / L.cell_h, L.rows - 1);
+        lcell[it] = (ci - ci0) * ncx + (cj - cj0);
+        rank[it] = atomicAdd(&s_cell_cnt[lcell[it]], 1);
+      }
+    }
+    __syncthreads();
+    if (tid < ncx * ncy) {
+      const int c = s_cell_cnt[tid];
+      const int cell = (ci0 + tid / ncx) * L.cols + (cj0 + tid % ncx);
+      s_cell_base[tid] = c ? atomicAdd(counts + cell, c) : 0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < (KEPT_CAP + NT - 1) / NT; ++it) {
+      const int i = tid + it * NT;
+      if (i < n) {
+        const int lc = lcell[it];
+        const int cell = (ci0 + lc / ncx) * L.cols + (cj0 + lc % ncx);
+        const int slot = s_cell_base[lc] + rank[it];
+        if (slot < L.list_cap_cell)
+          lists[(int64_t)cell * L.list_cap_cell + slot] = s_kept[i];
+        else
+          atomicExch(buf.error_flag, 6);
+      }
+    }
+  } else {
+    // very small cells (more than MAX_LOCAL_CELLS under one tile): append directly
+    for (int i = tid; i < n; i += NT) {
+      const uint32_t e = s_kept[i];
+      const int cj = min((SDORB_ENTRY_X(e) - SDORB_EDGE) / L.cell_w, L.cols - 1);
+      const int ci = min((SDORB_ENTRY_Y(e) - SDORB_EDGE) / L.cell_h, L.rows - 1);
+      const int cell = ci * L.cols + cj;
+      const int slot = atomicAdd(counts + cell, 1);
+      if (slot < L.list_cap_cell)
+        lists[(int64_t)cell * L.list_cap_cell + slot] = e;
+      else
+        atomicExch(buf.error_flag, 6);
     }
   }
 }

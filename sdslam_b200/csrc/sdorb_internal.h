@@ -9,10 +9,11 @@
 #define SDORB_MAX_DIM 4095   // keypoint entries pack y:12 | x:12 | score:8
 #define SDORB_MAX_CELLS_PER_LEVEL 4096
 
-// Tile shapes of the all-level launches.  FAST tiles start at (16,16): the first detectable pixel is 19 and
-// its ring reaches 16, which keeps every tile row 4-byte aligned.
-#define SDORB_FAST_TW 128
-#define SDORB_FAST_TH 32
+// Tile shapes of the all-level launches.  A FAST tile scores 128 x 32 pixels starting at column 16 + 124*tx (a
+// multiple of 4, so every staged row is word aligned) and row 18 + 30*ty, and emits keypoints for the inner
+// 124 x 30 pixels starting at (18 + 124*tx, 19 + 30*ty); the first detectable pixel is (19,19).
+#define SDORB_FAST_TW 124
+#define SDORB_FAST_TH 30
 #define SDORB_BLUR_TW 128
 #define SDORB_BLUR_TH 32
 

@@ -32,8 +32,11 @@ def main():
     kps = torch.zeros((a.frames, cap, 7), dtype=torch.float32, device=dev)
     desc = torch.zeros((a.frames, cap, 32), dtype=torch.uint8, device=dev)
     cnt = torch.zeros(a.frames, dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(st)
+    sh = st.cuda_stream
     for _ in range(2):
-        ex.extract_batch_device(imgs, kps, desc, cnt)
+        ex.extract_batch_device(imgs, kps, desc, cnt, stream=sh)
     torch.cuda.synchronize()
     ex.batch_status()
     ex.set_profiling(True)
@@ -42,7 +45,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.iters):
-        ex.extract_batch_device(imgs, kps, desc, cnt)
+        ex.extract_batch_device(imgs, kps, desc, cnt, stream=sh)
     e1.record()
     torch.cuda.synchronize()
     ms, launches = ex.stage_times()
@@ -56,11 +59,11 @@ def main():
     nA = torch.full((a.frames // 2,), cap, dtype=torch.int32, device=dev)
     out = torch.zeros((a.frames // 2, cap, 4), dtype=torch.int32, device=dev)
     dA, dB = desc[0::2].contiguous(), desc[1::2].contiguous()
-    ex.match_batch(dA, cnt[0::2].contiguous(), dB, cnt[1::2].contiguous(), out=out, device=True)
+    ex.match_batch(dA, cnt[0::2].contiguous(), dB, cnt[1::2].contiguous(), out=out, device=True, stream=sh)
     torch.cuda.synchronize()
     e0.record()
     for _ in range(a.iters):
-        ex.match_batch(dA, cnt[0::2].contiguous(), dB, cnt[1::2].contiguous(), out=out, device=True)
+        ex.match_batch(dA, cnt[0::2].contiguous(), dB, cnt[1::2].contiguous(), out=out, device=True, stream=sh)
     e1.record()
     torch.cuda.synchronize()
     tm = e0.elapsed_time(e1) / a.iters
