@@ -108,7 +108,7 @@ static void resize_axis(int src, int dst, bool horizontal, ResizeTap* out) {
 }
 
 int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int height, FrameGeom* g,
-                     std::vector<ResizeTap>* taps) {
+                     std::vector<ResizeTap>* taps, std::vector<ResizeGroup>* groups) {
   if (width <= 0 || height <= 0 || width > SDORB_MAX_DIM || height > SDORB_MAX_DIM) return -1;
   *g = FrameGeom{};
   g->nlevels = t.nlevels;
@@ -117,6 +117,7 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
   g->nfeatures = nfeatures;
   g->th_fast = std::min(std::max(th_fast, 0), 255);  // cv::FAST clamps the threshold
   taps->clear();
+  if (groups) groups->clear();
   const float ratio = (float)width / height;
   int cell_base = 0, sel_base = 0, tile_fast = 0, tile_blur = 0;
   int64_t list_base = 0, plane_base = 0;
@@ -212,6 +213,33 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
       L.coef_y_base = (int)taps->size();
       taps->resize(taps->size() + L.h);
       resize_axis(P.h, L.h, false, taps->data() + L.coef_y_base);
+      // four destination pixels per group, all taps inside one 8-byte source window
+      L.group_base = -1;
+      if (groups) {
+        const ResizeTap* tx = taps->data() + L.coef_x_base;
+        const int ngroups = (L.w + 3) / 4;
+        std::vector<ResizeGroup> gs(ngroups);
+        bool fits = true;
+        for (int gi = 0; gi < ngroups && fits; ++gi) {
+          ResizeGroup& G = gs[gi];
+          G.pad_ = 0;
+          G.src_x = tx[4 * gi].s0;
+          uint32_t sel[2] = {0, 0};
+          for (int i = 0; i < 4; ++i) {
+            const ResizeTap& tp = tx[std::min(4 * gi + i, L.w - 1)];
+            const int o0 = (int)tp.s0 - G.src_x, o1 = (int)tp.s1 - G.src_x;
+            if (o0 < 0 || o1 < 0 || o0 > 7 || o1 > 7 || tp.c0 < 0 || tp.c1 < 0) fits = false;
+            sel[i >> 1] |= ((uint32_t)(o0 & 7) | ((uint32_t)(o1 & 7) << 4)) << (8 * (i & 1));
+            G.coef[i] = (uint32_t)(uint16_t)tp.c0 | ((uint32_t)(uint16_t)tp.c1 << 16);
+          }
+          G.sel01 = sel[0];
+          G.sel23 = sel[1];
+        }
+        if (fits) {
+          L.group_base = (int)groups->size();
+          groups->insert(groups->end(), gs.begin(), gs.end());
+        }
+      }
     }
   }
   g->cells_total = cell_base;

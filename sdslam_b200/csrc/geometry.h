@@ -17,6 +17,6 @@ void build_tables(int nfeatures, float scale_factor, int nlevels, Tables* t);
 void level_size(const Tables& t, int level, int width, int height, int* lw, int* lh);
 // Returns 0, or the negated SDORB_ERR_* magnitude (-1 bad arg, -4 geometry, -7 unsupported).
 int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int height, FrameGeom* g,
-                     std::vector<ResizeTap>* taps);
+                     std::vector<ResizeTap>* taps, std::vector<ResizeGroup>* groups = nullptr);
 
 }  // namespace sdorb

@@ -29,7 +29,7 @@ struct SelectBuffers {
 
 // ComputePyramid: level l from level l-1 for every frame (cv::resize INTER_LINEAR fixed point).
 void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level, const BatchPlanes& p,
-                         const ResizeTap* d_taps, int nframes, cudaStream_t s);
+                         const ResizeTap* d_taps, const ResizeGroup* d_groups, int nframes, cudaStream_t s);
 // cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101), 8-bit fixed point, all levels of all frames in one launch.
 void launch_blur_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s);
 // cv::FAST(cell, thFAST, nonmax=true) for every cell of every level of every frame, one launch; appends

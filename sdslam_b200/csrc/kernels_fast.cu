@@ -33,7 +33,7 @@ constexpr int PWORDS = SWORDS + 2;                     // staged pixel words per
 constexpr int PROWS = SROWS + 6;                       // staged pixel rows (scored +- 3)
 constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in words (one zero word on each side)
 constexpr int NT = 256;
-constexpr int KEPT_CAP = (OW / 2 + 1) * (OH / 2 + 1);  // strict 3x3 NMS leaves at most one keypoint per 2x2 block
+constexpr int KEPT_CAP = 1024;  // one keypoint per 2x2 block inside a cell (930 for the tile) plus cell-boundary extras; overflow is flagged
 constexpr int MAX_LOCAL_CELLS = 32;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
@@ -109,14 +109,10 @@ __device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const 
   return __vmaxu2(m, th2) - th2;              // (max(A,B') - th) if positive, else 0;  th2 = (th + 256) per lane
 }
 
-struct Keep2 {
-  bool x, y;
-};
-
 // Strict 3x3 non-max test of the two pixels of pair P on packed score lanes (lane = byte * 257).  T[0..2] are the
 // score words of rows y-1, y, y+1 (previous / own / next word); lm / rm zero the neighbours that lie in another cell.
 template <int P>
-__device__ __forceinline__ Keep2 nms_pair(const uint32_t (&T)[3][3], const uint32_t lm, const uint32_t rm) {
+__device__ __forceinline__ uint32_t nms_pair(const uint32_t (&T)[3][3], const uint32_t lm, const uint32_t rm) {
   const uint32_t c = pair_at<P, 0>(T[1][0], T[1][1], T[1][2]);
   const uint32_t l = pair_at<P, -1>(T[1][0], T[1][1], T[1][2]) & lm, r = pair_at<P, 1>(T[1][0], T[1][1], T[1][2]) & rm;
   const uint32_t u = pair_at<P, 0>(T[0][0], T[0][1], T[0][2]), d = pair_at<P, 0>(T[2][0], T[2][1], T[2][2]);
@@ -125,10 +121,7 @@ __device__ __forceinline__ Keep2 nms_pair(const uint32_t (&T)[3][3], const uint3
   const uint32_t m1 = __vimax3_u16x2(l, r, u), m2 = __vimax3_u16x2(ul, ur, d), m3 = __vimax3_u16x2(dl, dr, m1);
   const uint32_t nb = __vmaxu2(m2, m3);
   const uint32_t diff = c - __vminu2(c, nb);  // lane != 0  <=>  centre strictly greater than all eight neighbours
-  Keep2 k;
-  k.x = (diff & 0xFFFFu) != 0;
-  k.y = (diff >> 16) != 0;
-  return k;
+  return ((diff & 0xFFFFu) != 0 ? 1u : 0u) | ((diff >> 16) != 0 ? 2u : 0u);
 }
 
 __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, SelectBuffers buf) {
@@ -136,6 +129,7 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
   __shared__ __align__(16) uint32_t s_t[SROWS][TWORDS];
   __shared__ uint32_t s_kept[KEPT_CAP];
   __shared__ int s_cell_cnt[MAX_LOCAL_CELLS], s_cell_base[MAX_LOCAL_CELLS];
+  __shared__ uint32_t s_rowflags[OH];
   __shared__ int s_nkept;
   __shared__ int s_level;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -185,6 +179,17 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
   if (tid < SROWS) {
     s_t[tid][0] = 0;
     s_t[tid][TWORDS - 1] = 0;
+  }
+  if (tid < OH) {  // which vertical neighbours of output row tid lie in the same cell (0 for rows below the detectable area)
+    const int y = b + tid;
+    uint32_t f = 0;
+    if (y < L.det_y1) {
+      const int ci = min((y - SDORB_EDGE) / L.cell_h, L.rows - 1);
+      const int cy0 = SDORB_EDGE + ci * L.cell_h;
+      const int cy1 = (ci == L.rows - 1) ? L.max_by : cy0 + L.cell_h;
+      f = (y - 1 >= cy0 ? 1u : 0u) | (y + 1 < cy1 ? 2u : 0u);
+    }
+    s_rowflags[tid] = f;
   }
   __syncthreads();
 
@@ -243,38 +248,31 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
   for (int orow = warp; orow < OH; orow += NT / 32) {
     const int sr = orow + 1, y = b + orow;
     const uint32_t cw = s_t[sr][lane + 1];
-    uint32_t kept = 0;
-    if (__any_sync(0xffffffffu, cw != 0) ) {
-      if (y < vy1) {
-        const int ci = min((y - SDORB_EDGE) / L.cell_h, L.rows - 1);
-        const int cy0 = SDORB_EDGE + ci * L.cell_h;
-        const int cy1 = (ci == L.rows - 1) ? L.max_by : cy0 + L.cell_h;
-        const bool u_ok = y - 1 >= cy0, d_ok = y + 1 < cy1;
-        uint32_t Tn[3][3];
+    if (!__any_sync(0xffffffffu, cw != 0)) continue;
+    const uint32_t rowflags = s_rowflags[orow];  // bit 0: row above is in the same cell, bit 1: row below is
+    uint32_t Tn[3][3];
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          Tn[0][j] = u_ok ? s_t[sr - 1][lane + j] : 0u;
-          Tn[1][j] = s_t[sr][lane + j];
-          Tn[2][j] = d_ok ? s_t[sr + 1][lane + j] : 0u;
-        }
-        const Keep2 k0 = nms_pair<0>(Tn, lm[0], rm[0]);
-        const Keep2 k1 = nms_pair<1>(Tn, lm[1], rm[1]);
-        kept = ((uint32_t)k0.x | ((uint32_t)k0.y << 1) | ((uint32_t)k1.x << 2) | ((uint32_t)k1.y << 3)) & out_cols;
-      }
+    for (int j = 0; j < 3; ++j) {
+      Tn[0][j] = (rowflags & 1u) ? s_t[sr - 1][lane + j] : 0u;
+      Tn[1][j] = s_t[sr][lane + j];
+      Tn[2][j] = (rowflags & 2u) ? s_t[sr + 1][lane + j] : 0u;
     }
-    while (true) {
-      const bool active = kept != 0;
-      const uint32_t bal = __ballot_sync(0xffffffffu, active);
-      if (bal == 0) break;
-      int base = 0;
-      if (lane == __ffs(bal) - 1) base = atomicAdd(&s_nkept, __popc(bal));
-      base = __shfl_sync(0xffffffffu, base, __ffs(bal) - 1);
-      if (active) {
-        const int q = __ffs(kept) - 1;
-        const int tq = (cw >> (8 * q)) & 0xFF;
-        const int idx = base + __popc(bal & ((1u << lane) - 1u));
-        if (idx < KEPT_CAP) s_kept[idx] = SDORB_ENTRY(y, xw + q, tq + th - 1);
-        kept &= kept - 1;
+    const uint32_t kept = (nms_pair<0>(Tn, lm[0], rm[0]) | (nms_pair<1>(Tn, lm[1], rm[1]) << 2)) & out_cols;
+    // warp-wide exclusive prefix sum of the per-lane survivor counts (0..4: pixels on either side of a cell boundary
+    // do not suppress each other) from three ballots, one shared-memory atomic per row
+    const int cnt = __popc(kept);
+    const uint32_t c0 = __ballot_sync(0xffffffffu, cnt & 1), c1 = __ballot_sync(0xffffffffu, cnt & 2),
+                   c2 = __ballot_sync(0xffffffffu, cnt & 4);
+    if ((c0 | c1 | c2) == 0) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_nkept, __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cnt) {
+      const uint32_t lt = (1u << lane) - 1u;
+      int idx = base + __popc(c0 & lt) + 2 * __popc(c1 & lt) + 4 * __popc(c2 & lt);
+      for (uint32_t m = kept; m; m &= m - 1, ++idx) {
+        const int q = __ffs(m) - 1;
+        if (idx < KEPT_CAP) s_kept[idx] = SDORB_ENTRY(y, xw + q, (int)((cw >> (8 * q)) & 0xFFu) + th - 1);
       }
     }
   }
@@ -283,6 +281,7 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
   // ---- phase A: count per cell in shared memory, reserve list ranges with one global atomic per (tile, cell), write
   const int n = min(s_nkept, KEPT_CAP);
   if (n == 0) return;
+  if (tid == 0 && s_nkept > KEPT_CAP) atomicExch(buf.error_flag, 6);  // only possible with cells a few pixels wide
   const int ox0 = max(a + 2, SDORB_EDGE), oy0 = b;
   const int ox1 = min(a + 2 + OW, vx1) - 1, oy1 = min(b + OH, vy1) - 1;  // last output pixel that can hold a keypoint
   const int cj0 = min((ox0 - SDORB_EDGE) / L.cell_w, L.cols - 1), ci0 = min((oy0 - SDORB_EDGE) / L.cell_h, L.rows - 1);

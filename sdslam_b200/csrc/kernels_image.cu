@@ -5,7 +5,12 @@
 //     horizontal pass in int32, vertical pass  (((b0*(H0>>4))>>16) + ((b1*(H1>>4))>>16) + 2) >> 2.
 //   * cv::GaussianBlur 7x7 sigma 2 BORDER_REFLECT_101 (src/ORBextractor.cc:660): 8.8 kernel
 //     {18,34,48,56,48,34,18}, 16-bit horizontal pass, 32-bit vertical pass, (v + 2^15) >> 16.
-// Both are HBM-bound byte kernels: one read and one write of every level pixel.
+// Both are byte kernels that read and write every level pixel once.  To get near the HBM roofline the integer work
+// per pixel has to be a handful of instructions, so both use the byte dot-product unit:
+//   resize : the 8 source bytes holding all taps of 4 destination pixels are funnel-shifted into place, one PRMT
+//            gathers (s0, s1) of two pixels and IDP.2A multiplies them with the (c0, c1) coefficient pair;
+//   blur   : the horizontal 7-tap filter of a pixel is two IDP.4A over byte quadruples cut out with PRMT, the
+//            vertical one four IDP.2A over vertically paired 16-bit sums, with the rounding constant as accumulator.
 #include "kernels.cuh"
 
 namespace sdorb {
@@ -21,9 +26,71 @@ __device__ __forceinline__ const uint8_t* level_plane(const BatchPlanes& p, cons
 }
 
 // ------------------------------------------------------------------------------------------------ resize
-// One thread = 4 consecutive output pixels of one row (one 32-bit store).  Grid: (x groups, rows, frames).
-__global__ void __launch_bounds__(256) resize_level_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
-                                                           const ResizeTap* __restrict__ taps) {
+constexpr int RZ_ROWS = 8;  // consecutive destination rows per thread (a source row feeds two destination rows)
+
+// horizontal pass of one source row for four destination pixels
+__device__ __forceinline__ void resize_hrow(const uint8_t* __restrict__ row, int base, int last_word, int shift,
+                                            const ResizeGroup& G, int (&hv)[4]) {
+  const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row + min(base, last_word));
+  const uint32_t w1 = *reinterpret_cast<const uint32_t*>(row + min(base + 4, last_word));
+  const uint32_t w2 = *reinterpret_cast<const uint32_t*>(row + min(base + 8, last_word));
+  const uint32_t lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+  const uint32_t p01 = __byte_perm(lo, hi, G.sel01), p23 = __byte_perm(lo, hi, G.sel23);
+  hv[0] = (int)__dp2a_lo(G.coef[0], p01, 0u);
+  hv[1] = (int)__dp2a_hi(G.coef[1], p01, 0u);
+  hv[2] = (int)__dp2a_lo(G.coef[2], p23, 0u);
+  hv[3] = (int)__dp2a_hi(G.coef[3], p23, 0u);
+}
+
+// One thread = 4 consecutive destination pixels x RZ_ROWS consecutive rows.  Block (32, 4): 128 x 32 pixels.
+__global__ void __launch_bounds__(128) resize_level_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
+                                                           const ResizeTap* __restrict__ taps,
+                                                           const ResizeGroup* __restrict__ groups) {
+  const LevelGeom& D = geom->lv[level];
+  const LevelGeom& S = geom->lv[level - 1];
+  const int gi = blockIdx.x * 32 + threadIdx.x;
+  const int x4 = gi * 4;
+  const int y0 = (blockIdx.y * 4 + threadIdx.y) * RZ_ROWS;
+  const int frame = blockIdx.z;
+  if (x4 >= D.w || y0 >= D.h) return;
+  int spitch;
+  const uint8_t* src = level_plane(p, S, level - 1, frame, &spitch);
+  uint8_t* dst = p.pyr + D.plane_base * p.batch_cap + (int64_t)frame * D.plane_bytes;
+  const ResizeGroup G = groups[D.group_base + gi];
+  const int base = G.src_x & ~3, shift = (G.src_x & 3) * 8, last_word = (S.w - 1) & ~3;
+  const ResizeTap* ty = taps + D.coef_y_base;
+  int h1[4] = {0, 0, 0, 0};
+  int have = -1;  // source row currently held in h1
+  const int y1 = min(y0 + RZ_ROWS, D.h);
+  for (int y = y0; y < y1; ++y) {
+    const ResizeTap t = ty[y];
+    int h0[4];
+    if ((int)t.s0 == have) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h0[i] = h1[i];
+    } else {
+      resize_hrow(src + (int64_t)t.s0 * spitch, base, last_word, shift, G, h0);
+    }
+    if (t.s1 != t.s0) resize_hrow(src + (int64_t)t.s1 * spitch, base, last_word, shift, G, h1);
+    else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) h1[i] = h0[i];
+    }
+    have = t.s1;
+    uint32_t out = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      int v = (((t.c0 * (h0[i] >> 4)) >> 16) + ((t.c1 * (h1[i] >> 4)) >> 16) + 2) >> 2;
+      v = min(max(v, 0), 255);
+      out |= (uint32_t)v << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(dst + (int64_t)y * D.pitch + x4) = out;  // pitch is a multiple of 128: padding absorbs the tail
+  }
+}
+
+// Generic path for scale factors whose taps do not fit the 8-byte window (scale > ~2): one thread = 4 pixels of one row.
+__global__ void __launch_bounds__(256) resize_level_generic_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
+                                                                   const ResizeTap* __restrict__ taps) {
   const LevelGeom& D = geom->lv[level];
   const LevelGeom& S = geom->lv[level - 1];
   const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
@@ -47,15 +114,21 @@ __global__ void __launch_bounds__(256) resize_level_kernel(const FrameGeom* __re
     v = min(max(v, 0), 255);
     out |= (uint32_t)v << (8 * i);
   }
-  *reinterpret_cast<uint32_t*>(dst + (int64_t)y * D.pitch + x4) = out;  // pitch is a multiple of 128: padding absorbs the tail
+  *reinterpret_cast<uint32_t*>(dst + (int64_t)y * D.pitch + x4) = out;
 }
 
 void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level, const BatchPlanes& p,
-                         const ResizeTap* d_taps, int nframes, cudaStream_t s) {
+                         const ResizeTap* d_taps, const ResizeGroup* d_groups, int nframes, cudaStream_t s) {
   const LevelGeom& D = g.lv[level];
-  dim3 block(64, 4);
-  dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, nframes);
-  resize_level_kernel<<<grid, block, 0, s>>>(d_geom, level, p, d_taps);
+  if (D.group_base >= 0) {
+    dim3 block(32, 4);
+    dim3 grid((D.w + 127) / 128, (D.h + 4 * RZ_ROWS - 1) / (4 * RZ_ROWS), nframes);
+    resize_level_kernel<<<grid, block, 0, s>>>(d_geom, level, p, d_taps, d_groups);
+  } else {
+    dim3 block(64, 4);
+    dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, nframes);
+    resize_level_generic_kernel<<<grid, block, 0, s>>>(d_geom, level, p, d_taps);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ blur
@@ -68,13 +141,16 @@ __device__ __forceinline__ int reflect101(int p, int len) {
   return p;
 }
 
-constexpr int BTW = SDORB_BLUR_TW, BTH = SDORB_BLUR_TH;
-constexpr int B_SRC_W = BTW + 8;   // bytes per staged source row: x0-4 .. x0+TW+3
-constexpr int B_ROWS = BTH + 6;
+constexpr int BTW = SDORB_BLUR_TW, BTH = SDORB_BLUR_TH;  // 128 x 32 output pixels per block
+constexpr int B_WORDS = BTW / 4;        // output words per row
+constexpr int B_SRC_WORDS = B_WORDS + 2;  // staged source words per row: x0-4 .. x0+TW+3
+constexpr int B_ROWS = BTH + 6;         // staged rows: y0-3 .. y0+TH+2
+constexpr int B_VROWS = 4;              // output rows per thread in the vertical pass
+static_assert(BTW == 128 && (BTH % B_VROWS) == 0 && (BTH / B_VROWS) * B_WORDS == 256, "blur tiling assumes 256 threads");
 
 __global__ void __launch_bounds__(256) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p) {
-  __shared__ __align__(16) uint8_t s_src[B_ROWS][B_SRC_W];
-  __shared__ __align__(16) uint16_t s_h[B_ROWS][BTW];
+  __shared__ __align__(16) uint32_t s_src[B_ROWS][B_SRC_WORDS];
+  __shared__ __align__(16) uint2 s_h[B_ROWS][B_WORDS];  // horizontal sums, four 16-bit values per entry
   __shared__ int s_level;
   const int tid = threadIdx.x;
   if (tid == 0) {
@@ -93,8 +169,8 @@ __global__ void __launch_bounds__(256) blur_all_kernel(const FrameGeom* __restri
   const uint8_t* src = level_plane(p, L, level, frame, &spitch);
 
   // stage rows y0-3 .. y0+TH+2 (reflected), columns x0-4 .. x0+TW+3 as 32-bit words
-  for (int i = tid; i < B_ROWS * (B_SRC_W / 4); i += 256) {
-    const int r = i / (B_SRC_W / 4), k = i % (B_SRC_W / 4);
+  for (int i = tid; i < B_ROWS * B_SRC_WORDS; i += 256) {
+    const int r = i / B_SRC_WORDS, k = i - r * B_SRC_WORDS;
     const int gy = reflect101(y0 - 3 + r, h);
     const int gx = x0 - 4 + 4 * k;
     const uint8_t* row = src + (int64_t)gy * spitch;
@@ -106,46 +182,53 @@ __global__ void __launch_bounds__(256) blur_all_kernel(const FrameGeom* __restri
 #pragma unroll
       for (int b = 0; b < 4; ++b) v |= (uint32_t)row[reflect101(gx + b, w)] << (8 * b);
     }
-    *reinterpret_cast<uint32_t*>(&s_src[r][4 * k]) = v;
+    s_src[r][k] = v;
   }
   __syncthreads();
-  // horizontal pass: 4 pixels per thread-iteration
-  for (int i = tid; i < B_ROWS * (BTW / 4); i += 256) {
-    const int r = i / (BTW / 4), k = i % (BTW / 4);
-    const uint32_t* wp = reinterpret_cast<const uint32_t*>(&s_src[r][4 * k]);  // tile px 4k..4k+3 live at byte 4k+4
-    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-    int b[12];
+
+  // horizontal pass: H[x] = sum_i K[i] * src[x + i - 3]; the seven taps of a pixel are two byte quadruples
+  constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);  // taps -3..0
+  constexpr uint32_t KB = 48u | (34u << 8) | (18u << 16);                // taps +1..+3 (+4 unused)
+  for (int i = tid; i < B_ROWS * B_WORDS; i += 256) {
+    const int r = i / B_WORDS, k = i - r * B_WORDS;
+    const uint32_t w0 = s_src[r][k], w1 = s_src[r][k + 1], w2 = s_src[r][k + 2];  // px x-4..x-1 | x..x+3 | x+4..x+7
+    const uint32_t h0 = __dp4a(__byte_perm(w0, w1, 0x4321), KA, __dp4a(__byte_perm(w1, w2, 0x4321), KB, 0u));
+    const uint32_t h1 = __dp4a(__byte_perm(w0, w1, 0x5432), KA, __dp4a(__byte_perm(w1, w2, 0x5432), KB, 0u));
+    const uint32_t h2 = __dp4a(__byte_perm(w0, w1, 0x6543), KA, __dp4a(__byte_perm(w1, w2, 0x6543), KB, 0u));
+    const uint32_t h3 = __dp4a(w1, KA, __dp4a(w2, KB, 0u));
+    s_h[r][k] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+  }
+  __syncthreads();
+
+  // vertical pass: thread = one word column x B_VROWS output rows; V[y] = sum_j K[j] * H[y + j - 3] over row pairs
+  const int k = tid & (B_WORDS - 1), g = tid / B_WORDS;
+  const int gx = x0 + 4 * k;
+  if (gx >= w) return;
+  uint2 hv[B_VROWS + 6];
+#pragma unroll
+  for (int j = 0; j < B_VROWS + 6; ++j) hv[j] = s_h[g * B_VROWS + j][k];
+  uint8_t* dst = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
+  constexpr uint32_t K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8);
+#pragma unroll
+  for (int o = 0; o < B_VROWS; ++o) {
+    const int gy = y0 + g * B_VROWS + o;
+    if (gy >= h) continue;
+    uint32_t acc[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      b[q] = (w0 >> (8 * q)) & 0xFF;
-      b[4 + q] = (w1 >> (8 * q)) & 0xFF;
-      b[8 + q] = (w2 >> (8 * q)) & 0xFF;
+      const uint32_t sel = (q & 1) ? 0x7632u : 0x5410u;
+      const uint32_t a0 = q < 2 ? hv[o].x : hv[o].y, a1 = q < 2 ? hv[o + 1].x : hv[o + 1].y;
+      const uint32_t a2 = q < 2 ? hv[o + 2].x : hv[o + 2].y, a3 = q < 2 ? hv[o + 3].x : hv[o + 3].y;
+      const uint32_t a4 = q < 2 ? hv[o + 4].x : hv[o + 4].y, a5 = q < 2 ? hv[o + 5].x : hv[o + 5].y;
+      const uint32_t a6 = q < 2 ? hv[o + 6].x : hv[o + 6].y;
+      uint32_t v = __dp2a_lo(__byte_perm(a0, a1, sel), K01, 32768u);
+      v = __dp2a_lo(__byte_perm(a2, a3, sel), K23, v);
+      v = __dp2a_lo(__byte_perm(a4, a5, sel), K45, v);
+      v = __dp2a_lo(a6, (q & 1) ? (18u << 8) : 18u, v);
+      acc[q] = v;
     }
-    uint32_t o[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      o[q] = 18 * (b[q + 1] + b[q + 7]) + 34 * (b[q + 2] + b[q + 6]) + 48 * (b[q + 3] + b[q + 5]) + 56 * b[q + 4];
-    *reinterpret_cast<uint2*>(&s_h[r][4 * k]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
-  }
-  __syncthreads();
-  // vertical pass
-  uint8_t* dst = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
-  for (int i = tid; i < BTH * (BTW / 4); i += 256) {
-    const int r = i / (BTW / 4), k = i % (BTW / 4);
-    const int gy = y0 + r, gx = x0 + 4 * k;
-    if (gy >= h || gx >= w) continue;
-    uint32_t acc[4] = {0, 0, 0, 0};
-    const int kw[7] = {18, 34, 48, 56, 48, 34, 18};
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-      const uint2 v = *reinterpret_cast<const uint2*>(&s_h[r + j][4 * k]);
-      acc[0] += kw[j] * (v.x & 0xFFFF);
-      acc[1] += kw[j] * (v.x >> 16);
-      acc[2] += kw[j] * (v.y & 0xFFFF);
-      acc[3] += kw[j] * (v.y >> 16);
-    }
-    const uint32_t out = ((acc[0] + 32768u) >> 16) | (((acc[1] + 32768u) >> 16) << 8) |
-                         (((acc[2] + 32768u) >> 16) << 16) | (((acc[3] + 32768u) >> 16) << 24);
+    // byte 2 of each accumulator is (v + 2^15) >> 16 (v < 2^24)
+    const uint32_t out = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
     *reinterpret_cast<uint32_t*>(dst + (int64_t)gy * L.pitch + gx) = out;
   }
 }

@@ -35,6 +35,7 @@ struct sdorb_handle {
   FrameGeom geom{};
   FrameGeom* d_geom = nullptr;
   ResizeTap* d_taps = nullptr;
+  ResizeGroup* d_groups = nullptr;
   int* d_umax = nullptr;
   // scratch for max_batch frames of the current geometry
   uint8_t *d_pyr = nullptr, *d_blur = nullptr;
@@ -93,6 +94,7 @@ void dfree(T*& p) {
 void free_geometry_scratch(sdorb_handle* h) {
   dfree(h->d_geom);
   dfree(h->d_taps);
+  dfree(h->d_groups);
   dfree(h->d_pyr);
   dfree(h->d_blur);
   dfree(h->d_stage_in[0]);
@@ -126,7 +128,8 @@ int ensure_geometry(sdorb_handle* h, int width, int height) {
   if (width <= 0 || height <= 0 || width > h->prm.max_width || height > h->prm.max_height) return SDORB_ERR_BAD_ARG;
   FrameGeom g;
   std::vector<ResizeTap> taps;
-  const int ge = build_frame_geom(h->tables, h->prm.nfeatures, h->prm.th_fast, width, height, &g, &taps);
+  std::vector<ResizeGroup> groups;
+  const int ge = build_frame_geom(h->tables, h->prm.nfeatures, h->prm.th_fast, width, height, &g, &taps, &groups);
   if (ge) return geom_err(ge);
   CU(cudaStreamSynchronize(h->s_compute));
   free_geometry_scratch(h);
@@ -135,6 +138,9 @@ int ensure_geometry(sdorb_handle* h, int width, int height) {
   CU(cudaMemcpy(h->d_geom, &g, sizeof(FrameGeom), cudaMemcpyHostToDevice));
   CU(cudaMalloc(&h->d_taps, sizeof(ResizeTap) * std::max<size_t>(taps.size(), 1)));
   if (!taps.empty()) CU(cudaMemcpy(h->d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&h->d_groups, sizeof(ResizeGroup) * std::max<size_t>(groups.size(), 1)));
+  if (!groups.empty())
+    CU(cudaMemcpy(h->d_groups, groups.data(), sizeof(ResizeGroup) * groups.size(), cudaMemcpyHostToDevice));
   CU(cudaMalloc(&h->d_pyr, (size_t)g.plane_total * B + 256));
   CU(cudaMalloc(&h->d_blur, (size_t)g.plane_total * B + 256));
   const size_t cells_bytes = sizeof(int32_t) * std::max<size_t>((size_t)g.cells_total * B, 1);
@@ -216,7 +222,7 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
   {
     StageScope st(h, s, SDORB_STAGE_PYRAMID);
     for (int l = 1; l < g.nlevels; ++l) {
-      launch_resize_level(h->d_geom, g, l, planes, h->d_taps, n, s);
+      launch_resize_level(h->d_geom, g, l, planes, h->d_taps, h->d_groups, n, s);
       st.launched();
     }
   }

@@ -48,7 +48,7 @@ struct LevelGeom {
   int scaled_patch_size; // (int)(31 * mvScaleFactor[level])
   float scale;           // mvScaleFactor[level]
   int coef_x_base, coef_y_base;  // offsets into the resize coefficient tables (entries), levels >= 1
-  int pad_;
+  int group_base;        // first ResizeGroup of this level (levels >= 1), -1 when the 8-byte window does not fit (scale > ~2)
 };
 
 struct FrameGeom {
@@ -69,4 +69,13 @@ struct FrameGeom {
 struct ResizeTap {
   uint16_t s0, s1;
   int16_t c0, c1;
+};
+// Horizontal taps of four consecutive destination pixels, prepared for PRMT + IDP.2A: the eight source bytes starting
+// at src_x hold every tap of the group; sel01 / sel23 gather (s0, s1) of pixels 0,1 / 2,3 into one word each and
+// coef[i] = c0 | c1 << 16 of pixel i.
+struct ResizeGroup {
+  int32_t src_x;
+  uint32_t sel01, sel23;
+  uint32_t coef[4];
+  int32_t pad_;
 };
