@@ -186,6 +186,10 @@ SDORB_API int64_t sdorb_kernel_launches(const sdorb_handle* h);
 #define SDORB_DBG_CELL_COUNTS 2   /* int32 per cell of the level (row-major cells): FAST keypoints after NMS */
 #define SDORB_DBG_LEVEL_SELECTED 3 /* uint32 (y<<20 | x<<8 | score) per selected keypoint of the level, in order */
 SDORB_API int64_t sdorb_debug_read(sdorb_handle* h, int what, int frame, int level, void* dst, size_t capacity);
+/* Runs the device implementation of std::nth_element(e, e + nth, e + n, response >) -- the ordering core of
+ * KeyPointsFilter::retainBest (src/ORBextractor.cc:586, 602) -- on n packed entries (low 8 bits = response) in host
+ * memory, in place (parity tests against the real libstdc++ algorithm). */
+SDORB_API int sdorb_debug_nth_element(sdorb_handle* h, uint32_t* entries, int n, int nth);
 
 #ifdef __cplusplus
 }

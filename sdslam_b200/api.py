@@ -78,6 +78,7 @@ def lib():
     L.sdorb_kernel_launches.restype = i64
     L.sdorb_debug_read.argtypes = [vp, i, i, i, vp, sz]
     L.sdorb_debug_read.restype = i64
+    L.sdorb_debug_nth_element.argtypes = [vp, vp, i, i]
     _lib = L
     return L
 
@@ -271,6 +272,12 @@ class ORBextractor:
 
     def kernel_launches(self):
         return int(lib().sdorb_kernel_launches(self._h))
+
+    def debug_nth_element(self, entries, nth):
+        """std::nth_element(e, e+nth, end, response >) as the selection kernel does it; returns the permuted copy."""
+        e = np.ascontiguousarray(entries, np.uint32).copy()
+        self._check(lib().sdorb_debug_nth_element(self._h, _ptr(e), len(e), nth))
+        return e
 
     def debug_read(self, what, frame, level, nbytes, dtype=np.uint8):
         buf = np.zeros(max(nbytes, 4), np.uint8)

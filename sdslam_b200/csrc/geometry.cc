@@ -147,6 +147,8 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
       L.cell_w = (int)std::ceil((float)W / L.cols);
       L.cell_h = (int)std::ceil((float)H / L.rows);
       L.n_features_cell = (int)std::ceil((float)L.n_desired / (L.rows * L.cols));
+      L.cell_w_magic = L.cell_w >= 2 ? (uint32_t)(0x100000000ull / (uint64_t)L.cell_w) + 1u : 0u;
+      L.cell_h_magic = L.cell_h >= 2 ? (uint32_t)(0x100000000ull / (uint64_t)L.cell_h) + 1u : 0u;
       // Walk the cell ROIs exactly like the reference loop (:495-532) to validate them and to find the
       // detectable rectangle of the last row / column.
       int cap = 0;
@@ -196,7 +198,7 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
     // flattened tile tables
     L.tile_base_fast = tile_fast;
     if (any_detect) {
-      L.tiles_x_fast = (L.det_x1 - 18 + SDORB_FAST_TW - 1) / SDORB_FAST_TW;
+      L.tiles_x_fast = (L.det_x1 - 16 + SDORB_FAST_TW - 1) / SDORB_FAST_TW;
       L.tiles_y_fast = (L.det_y1 - SDORB_EDGE + SDORB_FAST_TH - 1) / SDORB_FAST_TH;
     }
     tile_fast += L.tiles_x_fast * L.tiles_y_fast;

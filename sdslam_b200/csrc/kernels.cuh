@@ -15,13 +15,13 @@ struct BatchPlanes {
   int img0_pitch;            // bytes between rows of level 0
   uint8_t* pyr;              // scratch: unblurred levels (slot 0 = staged level 0 when used)
   uint8_t* blur;             // scratch: blurred levels
+  uint8_t* nms;              // scratch: keypoint map (one byte per pixel: FAST score + 1 - th after non-max suppression, else 0)
   int batch_cap;             // frames the scratch was sized for
 };
 
 struct SelectBuffers {
-  int32_t* cell_count;  // [batch][cells_total]  append counters of the FAST kernel; zero between passes
-  int32_t* cell_seen;   // [batch][cells_total]  copy of the counters of the last pass, written by the select kernel
-  uint32_t* cell_list;  // [batch][list_total]
+  int32_t* cell_seen;   // [batch][cells_total]  FAST keypoints per cell of the last pass (written by the select kernel)
+  uint32_t* cell_list;  // [batch][list_total]   overflow scratch for cells too large for shared memory
   uint32_t* sel;        // [batch][sel_total]  selected entries, level-major, in output order
   int32_t* sel_count;   // [batch][nlevels]
   int32_t* error_flag;  // device int: set to SDORB_ERR_OVERFLOW magnitude when a fixed-capacity list overflows
@@ -32,12 +32,14 @@ void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level,
                          const ResizeTap* d_taps, const ResizeGroup* d_groups, int nframes, cudaStream_t s);
 // cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101), 8-bit fixed point, all levels of all frames in one launch.
 void launch_blur_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s);
-// cv::FAST(cell, thFAST, nonmax=true) for every cell of every level of every frame, one launch; appends
-// SDORB_ENTRY(y, x, score) to the cell lists in arbitrary order (the select kernel sorts them).
-void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b,
-                     int nframes, cudaStream_t s);
+// cv::FAST(cell, thFAST, nonmax=true) for every cell of every level of every frame, one launch; writes the keypoint
+// map BatchPlanes::nms.
+void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s);
 // Quota redistribution + retainBest per cell + retainBest per level.
-void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const SelectBuffers& b, int nframes, cudaStream_t s);
+void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b, int nframes,
+                   cudaStream_t s);
+// Test hook: std::nth_element(a, a + nth, a + n, response >) as the selection kernel performs it (one warp).
+void launch_debug_nth_element(uint32_t* d_entries, int n, int nth, cudaStream_t s);
 // IC_Angle + rBRIEF descriptor + output assembly (coordinate scaling, cv::KeyPoint layout).
 void launch_describe(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b,
                      const int* d_umax, void* kps_out, uint8_t* desc_out, int32_t* counts_out, int capacity,

@@ -6,8 +6,9 @@
 //   corner  <=>  max(A,B') > th ;  score = max(A,B') - 1 ;  keypoint <=> score strictly greater than the 8
 //   neighbouring scores, where neighbours outside the cell's own detectable rectangle count as 0.
 // The score does not depend on the cell, so one kernel scores whole-level tiles and applies the cell rule only in the
-// non-max test.  Keypoints are appended to per-cell lists as SDORB_ENTRY(y,x,score) in arbitrary order; the selection
-// kernel sorts each list back into FAST's row-major emission order.
+// non-max test.  The result is a dense keypoint map per level: one byte per pixel, t = score + 1 - th for a keypoint
+// and 0 elsewhere.  The selection kernel walks every cell rectangle of the map in row-major order, which IS cv::FAST's
+// emission order -- no atomics, no lists to sort, no capacity to overflow, and a bit-identical result on every run.
 //
 // The synthetic benchmark frames are corner-dense (17 % of all pixels are FAST corners, 70 % pass the usual compass
 // pre-test), so the kernel scores DENSELY and branch-free instead of compacting candidates:
@@ -18,23 +19,20 @@
 //     each lane carries its byte twice (value * 257), so lane order == byte order and no masking is needed;
 //   * scores are kept as t = max(score + 1 - th, 0) in one byte per pixel; the 3x3 strict non-max test runs on the
 //     same packed lanes with per-column / per-row cell-boundary masks;
-//   * survivors are compacted warp-wise into a tile list, counted per cell in shared memory and appended to the global
-//     cell lists with one atomicAdd per (tile, cell).
+//   * survivors are written back as map words (coalesced 120-byte row segments).
 // A cheap 4-pixel SWAR compass test (VABSDIFF4) is kept only to skip pixel pairs no lane of the warp needs (flat image
 // regions).  The kernel is bound by the integer ALU pipe (min/max, PRMT), not by HBM: see DESIGN.md.
 #include "kernels.cuh"
 
 namespace sdorb {
 
-constexpr int OW = SDORB_FAST_TW, OH = SDORB_FAST_TH;  // output pixels per tile: 124 x 30
-constexpr int SWORDS = 32;                             // scored words per row (128 px: outputs + 2 px on each side)
+constexpr int OW = SDORB_FAST_TW, OH = SDORB_FAST_TH;  // output pixels per tile: 120 x 30 (30 whole words per row)
+constexpr int SWORDS = 32;                             // scored words per row (128 px: outputs + one word on each side)
 constexpr int SROWS = OH + 2;                          // scored rows (outputs + 1 on each side)
 constexpr int PWORDS = SWORDS + 2;                     // staged pixel words per row (scored +- 4 px)
 constexpr int PROWS = SROWS + 6;                       // staged pixel rows (scored +- 3)
 constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in words (one zero word on each side)
 constexpr int NT = 256;
-constexpr int KEPT_CAP = 1024;  // one keypoint per 2x2 block inside a cell (930 for the tile) plus cell-boundary extras; overflow is flagged
-constexpr int MAX_LOCAL_CELLS = 32;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 
@@ -124,28 +122,27 @@ __device__ __forceinline__ uint32_t nms_pair(const uint32_t (&T)[3][3], const ui
   return ((diff & 0xFFFFu) != 0 ? 1u : 0u) | ((diff >> 16) != 0 ? 2u : 0u);
 }
 
-__global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, SelectBuffers buf) {
+__device__ __forceinline__ int div_magic(int n, int d, uint32_t magic) {  // n / d for 0 <= n < 65536 (see geometry.cc)
+  return d == 1 ? n : (int)__umulhi((uint32_t)n, magic);
+}
+
+__global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p) {
   __shared__ __align__(16) uint32_t s_pix[PROWS][PWORDS];
   __shared__ __align__(16) uint32_t s_t[SROWS][TWORDS];
-  __shared__ uint32_t s_kept[KEPT_CAP];
-  __shared__ int s_cell_cnt[MAX_LOCAL_CELLS], s_cell_base[MAX_LOCAL_CELLS];
   __shared__ uint32_t s_rowflags[OH];
-  __shared__ int s_nkept;
   __shared__ int s_level;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     int l = 0;
     while (l + 1 < geom->nlevels && (int)blockIdx.x >= geom->lv[l + 1].tile_base_fast) ++l;
     s_level = l;
-    s_nkept = 0;
   }
-  if (tid < MAX_LOCAL_CELLS) s_cell_cnt[tid] = 0;
   __syncthreads();
   const int level = s_level;
   const LevelGeom& L = geom->lv[level];
   const int frame = blockIdx.y;
   const int t = blockIdx.x - L.tile_base_fast;
-  const int a = 16 + (t % L.tiles_x_fast) * OW;            // first scored column (multiple of 4); outputs are [a+2, a+2+OW)
+  const int a = 12 + (t % L.tiles_x_fast) * OW;            // first scored column (multiple of 4); outputs are [a+4, a+4+OW)
   const int b = SDORB_EDGE + (t / L.tiles_x_fast) * OH;    // first output row; scored rows are [b-1, b+OH+1)
   const int w = L.w, h = L.h;
   const int th = geom->th_fast;
@@ -159,22 +156,25 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
     src = p.pyr + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
   }
 
-  // ---- stage pixels: rows b-4 .. b+OH+3, columns a-4 .. a+131 as aligned words; zero outside the image
-  for (int i = tid; i < PROWS * PWORDS; i += NT) {
-    const int r = i / PWORDS, k = i - r * PWORDS;
-    const int gy = b - 4 + r, gx = a - 4 + 4 * k;
-    uint32_t v = 0;
-    if (gy >= 0 && gy < h && gx < w) {
-      const uint8_t* row = src + (int64_t)gy * pitch;
-      if (gx + 4 <= w) {
-        v = *reinterpret_cast<const uint32_t*>(row + gx);
-      } else {
+  // ---- stage pixels: rows b-4 .. b+OH+3, columns a-4 .. a+131 as aligned words, one warp per row; zero outside the image
+  for (int r = warp; r < PROWS; r += NT / 32) {
+    const int gy = b - 4 + r;
+    const uint8_t* row = src + (int64_t)gy * pitch;
+    const bool row_ok = gy >= 0 && gy < h;
+    for (int k = lane; k < PWORDS; k += 32) {
+      const int gx = a - 4 + 4 * k;
+      uint32_t v = 0;
+      if (row_ok && gx < w) {
+        if (gx + 4 <= w) {
+          v = *reinterpret_cast<const uint32_t*>(row + gx);
+        } else {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (gx + q < w) v |= (uint32_t)row[gx + q] << (8 * q);
+          for (int q = 0; q < 4; ++q)
+            if (gx + q < w) v |= (uint32_t)row[gx + q] << (8 * q);
+        }
       }
+      s_pix[r][k] = v;
     }
-    s_pix[r][k] = v;
   }
   if (tid < SROWS) {
     s_t[tid][0] = 0;
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
     const int y = b + tid;
     uint32_t f = 0;
     if (y < L.det_y1) {
-      const int ci = min((y - SDORB_EDGE) / L.cell_h, L.rows - 1);
+      const int ci = min(div_magic(y - SDORB_EDGE, L.cell_h, L.cell_h_magic), L.rows - 1);
       const int cy0 = SDORB_EDGE + ci * L.cell_h;
       const int cy1 = (ci == L.rows - 1) ? L.max_by : cy0 + L.cell_h;
       f = (y - 1 >= cy0 ? 1u : 0u) | (y + 1 < cy1 ? 2u : 0u);
@@ -196,20 +196,26 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
   // ---- per-thread column constants: this lane owns pixels x = xw .. xw+3 in every row it touches
   const int xw = a + 4 * lane;
   const int vx1 = L.det_x1, vy1 = L.det_y1;  // detectable area is [19, det_x1) x [19, det_y1)
-  uint32_t valid_cols = 0;   // byte mask: pixel may carry a score
-  uint32_t out_cols = 0;     // bit q: pixel xw+q is an output column of this tile
+  uint32_t valid_cols = 0;                  // byte mask: pixel may carry a score
   uint32_t lm[2] = {0, 0}, rm[2] = {0, 0};  // 16-bit lane masks: left / right neighbour lies in the same cell
+  {
+    const int xs = max(xw, SDORB_EDGE);
+    int cj = min(div_magic(xs - SDORB_EDGE, L.cell_w, L.cell_w_magic), L.cols - 1);
+    int cx0 = SDORB_EDGE + cj * L.cell_w;
+    int cx1 = (cj == L.cols - 1) ? L.max_bx : cx0 + L.cell_w;
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int x = xw + q;
-    if (x >= SDORB_EDGE && x < vx1) {
-      valid_cols |= 0xFFu << (8 * q);
-      if (x >= a + 2 && x < a + 2 + OW) out_cols |= 1u << q;
-      const int cj = min((x - SDORB_EDGE) / L.cell_w, L.cols - 1);
-      const int cx0 = SDORB_EDGE + cj * L.cell_w;
-      const int cx1 = (cj == L.cols - 1) ? L.max_bx : cx0 + L.cell_w;
-      if (x - 1 >= cx0) lm[q >> 1] |= 0xFFFFu << (16 * (q & 1));
-      if (x + 1 < cx1) rm[q >> 1] |= 0xFFFFu << (16 * (q & 1));
+    for (int q = 0; q < 4; ++q) {
+      const int x = xw + q;
+      if (x >= SDORB_EDGE && x < vx1) {
+        if (x >= cx1) {  // stepped into the next cell
+          ++cj;
+          cx0 = cx1;
+          cx1 = (cj == L.cols - 1) ? L.max_bx : cx0 + L.cell_w;
+        }
+        valid_cols |= 0xFFu << (8 * q);
+        if (x - 1 >= cx0) lm[q >> 1] |= 0xFFFFu << (16 * (q & 1));
+        if (x + 1 < cx1) rm[q >> 1] |= 0xFFFFu << (16 * (q & 1));
+      }
     }
   }
   const bool th_high = th >= 128;
@@ -244,106 +250,33 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
   }
   __syncthreads();
 
-  // ---- phase N: cell-bounded strict non-max suppression on the score tile; survivors go to the tile list
+  // ---- phase N: cell-bounded strict non-max suppression on the score tile; the survivors' t bytes go to the map
+  uint8_t* map = p.nms + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
+  const bool out_lane = lane >= 1 && lane <= OW / 4 && xw < L.pitch;
   for (int orow = warp; orow < OH; orow += NT / 32) {
     const int sr = orow + 1, y = b + orow;
+    if (y >= h) break;
     const uint32_t cw = s_t[sr][lane + 1];
-    if (!__any_sync(0xffffffffu, cw != 0)) continue;
-    const uint32_t rowflags = s_rowflags[orow];  // bit 0: row above is in the same cell, bit 1: row below is
-    uint32_t Tn[3][3];
+    uint32_t keep_bytes = 0;
+    if (__any_sync(0xffffffffu, cw != 0)) {
+      const uint32_t rowflags = s_rowflags[orow];  // bit 0: row above is in the same cell, bit 1: row below is
+      uint32_t Tn[3][3];
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      Tn[0][j] = (rowflags & 1u) ? s_t[sr - 1][lane + j] : 0u;
-      Tn[1][j] = s_t[sr][lane + j];
-      Tn[2][j] = (rowflags & 2u) ? s_t[sr + 1][lane + j] : 0u;
-    }
-    const uint32_t kept = (nms_pair<0>(Tn, lm[0], rm[0]) | (nms_pair<1>(Tn, lm[1], rm[1]) << 2)) & out_cols;
-    // warp-wide exclusive prefix sum of the per-lane survivor counts (0..4: pixels on either side of a cell boundary
-    // do not suppress each other) from three ballots, one shared-memory atomic per row
-    const int cnt = __popc(kept);
-    const uint32_t c0 = __ballot_sync(0xffffffffu, cnt & 1), c1 = __ballot_sync(0xffffffffu, cnt & 2),
-                   c2 = __ballot_sync(0xffffffffu, cnt & 4);
-    if ((c0 | c1 | c2) == 0) continue;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&s_nkept, __popc(c0) + 2 * __popc(c1) + 4 * __popc(c2));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (cnt) {
-      const uint32_t lt = (1u << lane) - 1u;
-      int idx = base + __popc(c0 & lt) + 2 * __popc(c1 & lt) + 4 * __popc(c2 & lt);
-      for (uint32_t m = kept; m; m &= m - 1, ++idx) {
-        const int q = __ffs(m) - 1;
-        if (idx < KEPT_CAP) s_kept[idx] = SDORB_ENTRY(y, xw + q, (int)((cw >> (8 * q)) & 0xFFu) + th - 1);
+      for (int j = 0; j < 3; ++j) {
+        Tn[0][j] = (rowflags & 1u) ? s_t[sr - 1][lane + j] : 0u;
+        Tn[1][j] = s_t[sr][lane + j];
+        Tn[2][j] = (rowflags & 2u) ? s_t[sr + 1][lane + j] : 0u;
       }
+      const uint32_t kept = nms_pair<0>(Tn, lm[0], rm[0]) | (nms_pair<1>(Tn, lm[1], rm[1]) << 2);
+      keep_bytes = ((kept * 0x00204081u) & 0x01010101u) * 0xFFu;  // bit q -> byte q
     }
-  }
-  __syncthreads();
-
-  // ---- phase A: count per cell in shared memory, reserve list ranges with one global atomic per (tile, cell), write
-  const int n = min(s_nkept, KEPT_CAP);
-  if (n == 0) return;
-  if (tid == 0 && s_nkept > KEPT_CAP) atomicExch(buf.error_flag, 6);  // only possible with cells a few pixels wide
-  const int ox0 = max(a + 2, SDORB_EDGE), oy0 = b;
-  const int ox1 = min(a + 2 + OW, vx1) - 1, oy1 = min(b + OH, vy1) - 1;  // last output pixel that can hold a keypoint
-  const int cj0 = min((ox0 - SDORB_EDGE) / L.cell_w, L.cols - 1), ci0 = min((oy0 - SDORB_EDGE) / L.cell_h, L.rows - 1);
-  const int cj1 = min((max(ox1, ox0) - SDORB_EDGE) / L.cell_w, L.cols - 1), ci1 = min((max(oy1, oy0) - SDORB_EDGE) / L.cell_h, L.rows - 1);
-  const int ncx = cj1 - cj0 + 1, ncy = ci1 - ci0 + 1;
-  int32_t* counts = buf.cell_count + (int64_t)frame * geom->cells_total + L.cell_base;
-  uint32_t* lists = buf.cell_list + (int64_t)frame * geom->list_total + L.list_base;
-  if (ncx * ncy <= MAX_LOCAL_CELLS) {
-    // entries are re-read in the same order by the same threads, so the local rank can live in a register
-    int rank[(KEPT_CAP + NT - 1) / NT];
-    int lcell[(KEPT_CAP + NT - 1) / NT];
-#pragma unroll
-    for (int it = 0; it < (KEPT_CAP + NT - 1) / NT; ++it) {
-      const int i = tid + it * NT;
-      if (i < n) {
-        const uint32_t e = s_kept[i];
-        const int cj = min((SDORB_ENTRY_X(e) - SDORB_EDGE) / L.cell_w, L.cols - 1);
-        const int ci = min((SDORB_ENTRY_Y(e) - SDORB_EDGE) / L.cell_h, L.rows - 1);
-        lcell[it] = (ci - ci0) * ncx + (cj - cj0);
-        rank[it] = atomicAdd(&s_cell_cnt[lcell[it]], 1);
-      }
-    }
-    __syncthreads();
-    if (tid < ncx * ncy) {
-      const int c = s_cell_cnt[tid];
-      const int cell = (ci0 + tid / ncx) * L.cols + (cj0 + tid % ncx);
-      s_cell_base[tid] = c ? atomicAdd(counts + cell, c) : 0;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int it = 0; it < (KEPT_CAP + NT - 1) / NT; ++it) {
-      const int i = tid + it * NT;
-      if (i < n) {
-        const int lc = lcell[it];
-        const int cell = (ci0 + lc / ncx) * L.cols + (cj0 + lc % ncx);
-        const int slot = s_cell_base[lc] + rank[it];
-        if (slot < L.list_cap_cell)
-          lists[(int64_t)cell * L.list_cap_cell + slot] = s_kept[i];
-        else
-          atomicExch(buf.error_flag, 6);
-      }
-    }
-  } else {
-    // very small cells (more than MAX_LOCAL_CELLS under one tile): append directly
-    for (int i = tid; i < n; i += NT) {
-      const uint32_t e = s_kept[i];
-      const int cj = min((SDORB_ENTRY_X(e) - SDORB_EDGE) / L.cell_w, L.cols - 1);
-      const int ci = min((SDORB_ENTRY_Y(e) - SDORB_EDGE) / L.cell_h, L.rows - 1);
-      const int cell = ci * L.cols + cj;
-      const int slot = atomicAdd(counts + cell, 1);
-      if (slot < L.list_cap_cell)
-        lists[(int64_t)cell * L.list_cap_cell + slot] = e;
-      else
-        atomicExch(buf.error_flag, 6);
-    }
+    if (out_lane) *reinterpret_cast<uint32_t*>(map + (int64_t)y * L.pitch + xw) = cw & keep_bytes;
   }
 }
 
-void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b,
-                     int nframes, cudaStream_t s) {
+void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s) {
   if (g.tiles_total_fast == 0) return;
-  fast_all_kernel<<<dim3(g.tiles_total_fast, nframes), NT, 0, s>>>(d_geom, p, b);
+  fast_all_kernel<<<dim3(g.tiles_total_fast, nframes), NT, 0, s>>>(d_geom, p);
 }
 
 }  // namespace sdorb

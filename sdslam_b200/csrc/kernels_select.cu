@@ -4,11 +4,24 @@
 //   1. per-cell quota nfeaturesCell with iterative redistribution of the deficit of poor cells (:538-575);
 //   2. per cell  KeyPointsFilter::retainBest(cell, nToRetain) + resize(nToRetain)  (:583-588);
 //   3. cells concatenated row-major, then  retainBest(level, nDesired) + resize  (:601-604).
-// retainBest's survivors and their ORDER are defined by libstdc++'s nth_element (see introselect.cuh); the
-// order is part of the output (keypoints and descriptor rows follow it), so it is reproduced move for move.
-// nth_element is inherently sequential per list, but there are cells x levels x frames independent lists:
-// one CTA handles one (level, frame); its warps take the cells, each sorting its cell list back into FAST's
-// emission order (bitonic network on the unique (y,x) keys) before one lane replays the introselect.
+// retainBest's survivors and their ORDER are defined by libstdc++'s nth_element (see introselect.cuh); the order is
+// part of the output (keypoints and descriptor rows follow it), so it is reproduced move for move.
+//
+// Two kernels.  gather_cells_kernel: one warp per (cell, frame) walks the cell rectangle of the FAST kernel's keypoint
+// map in row-major order -- cv::FAST's emission order -- and compacts the keypoints into the cell's list with ballot /
+// popc prefix sums (no atomics: the lists are bit-identical on every run).  The walk is pure memory latency, so it
+// lives in its own register-light kernel that fills the SMs with warps.  select_kernel: one CTA per (level, frame)
+// computes the quotas, and its warps load the lists into shared memory and trim them.
+//
+// nth_element is sequential as written, but its cost is all in the Hoare partition, and that parallelises exactly:
+// with pivot response p, the left scan stops at elements with response <= p, the right scan at elements with
+// response >= p, and the t-th left stopper L_t is swapped with the t-th right stopper R_t for as long as L_t < R_t.
+// So one warp pass ranks the stoppers of the range (ballot + popc), T = #{t : L_t < R_t} pairs are swapped in
+// parallel and the cut is min(L_T, R_{T-1}) -- the element moves of std::__unguarded_partition, in n/32 steps.
+// Median-of-three, the depth limit with its heap-select fallback and the final insertion sort stay on one lane.
+// tests/test_gpu_parity.py::test_warp_nth_element_equals_std checks the routine against the real std::nth_element.
+#include <climits>
+
 #include "introselect.cuh"
 #include "kernels.cuh"
 
@@ -16,36 +29,192 @@ namespace sdorb {
 
 constexpr int SEL_THREADS = 256;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
-constexpr int SEL_WORK_CAP = 1024;  // entries of per-warp shared scratch; larger cell lists are handled in place in global memory
+constexpr int SEL_WORK_CAP = 1024;  // entries of per-warp shared scratch; larger lists fall back to global memory + one lane
 
-__device__ __forceinline__ void cmp_swap(uint32_t* a, int i, int j) {
-  const uint32_t x = a[i], y = a[j];
-  if (x > y) {
-    a[i] = y;
-    a[j] = x;
+// std::nth_element(a + first, a + nth, a + last, response >) by one warp; indices must stay below 65536.
+__device__ void warp_nth_element(uint32_t* a, int first, int nth, int last, int lane, uint16_t* Lidx, uint16_t* Ridx) {
+  if (first == last || nth == last) return;
+  int n = last - first, lg = 0;
+  while (n > 1) {
+    n >>= 1;
+    ++lg;
   }
-}
-
-// Ascending bitonic sort of a[0..n) by one warp; slots >= n act as +infinity and are never touched.
-__device__ void warp_sort(uint32_t* a, int n, int lane) {
-  if (n < 2) return;
-  int P = 2;
-  while (P < n) P <<= 1;
-  for (int k = 2; k <= P; k <<= 1) {
-    const int half = k >> 1;
-    for (int t = lane; t < (P >> 1); t += 32) {
-      const int blk = t / half, off = t - blk * half;
-      const int i = blk * k + off, j = blk * k + (k - 1 - off);
-      if (j < n) cmp_swap(a, i, j);
-    }
-    __syncwarp();
-    for (int s = k >> 2; s > 0; s >>= 1) {
-      for (int t = lane; t < (P >> 1); t += 32) {
-        const int i = ((t & ~(s - 1)) << 1) | (t & (s - 1)), j = i | s;
-        if (j < n) cmp_swap(a, i, j);
+  int depth = 2 * lg;
+  const uint32_t lt = (1u << lane) - 1u;
+  while (last - first > 3) {
+    if (depth == 0) {
+      if (lane == 0) {
+        heap_select(a, first, nth + 1, last);
+        swap_u32(a, first, nth);
       }
       __syncwarp();
+      return;
     }
+    --depth;
+    if (lane == 0) {  // __move_median_to_first(first, first+1, mid, last-1)
+      const int x = first + 1, y = first + (last - first) / 2, z = last - 1;
+      if (resp_gt(a[x], a[y])) {
+        if (resp_gt(a[y], a[z]))
+          swap_u32(a, first, y);
+        else if (resp_gt(a[x], a[z]))
+          swap_u32(a, first, z);
+        else
+          swap_u32(a, first, x);
+      } else if (resp_gt(a[x], a[z]))
+        swap_u32(a, first, x);
+      else if (resp_gt(a[y], a[z]))
+        swap_u32(a, first, z);
+      else
+        swap_u32(a, first, y);
+    }
+    __syncwarp();
+    const uint32_t p = a[first] & 0xFFu;
+    // rank the stoppers: left scan (first, last) stops at response <= p, right scan [first, last) at response >= p
+    int nl = 0, nr = 0;
+    for (int base = first; base < last; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < last;
+      const uint32_t v = valid ? (a[i] & 0xFFu) : 0u;
+      const bool is_l = valid && i > first && v <= p;
+      const bool is_r = valid && v >= p;
+      const uint32_t bl = __ballot_sync(0xffffffffu, is_l), br = __ballot_sync(0xffffffffu, is_r);
+      if (is_l) Lidx[nl + __popc(bl & lt)] = (uint16_t)i;
+      if (is_r) Ridx[nr + __popc(br & lt)] = (uint16_t)i;  // ascending; R_t = Ridx[nr - 1 - t]
+      nl += __popc(bl);
+      nr += __popc(br);
+    }
+    __syncwarp();
+    const int m = min(nl, nr);
+    int T = 0;  // number of swaps: L_t < R_t is monotone in t
+    for (int base = 0; base < m; base += 32) {
+      const int t = base + lane;
+      const bool ok = t < m && Lidx[t] < Ridx[nr - 1 - t];
+      const uint32_t bb = __ballot_sync(0xffffffffu, ok);
+      T += __popc(bb);
+      if (bb != 0xffffffffu) break;
+    }
+    for (int t = lane; t < T; t += 32) swap_u32(a, Lidx[t], Ridx[nr - 1 - t]);
+    int cut = T < nl ? (int)Lidx[T] : INT_MAX;
+    if (T > 0) cut = min(cut, (int)Ridx[nr - T]);
+    __syncwarp();
+    if (cut <= nth)
+      first = cut;
+    else
+      last = cut;
+  }
+  if (lane == 0) {  // __insertion_sort(first, last) on at most three elements
+    for (int i = first + 1; i < last; ++i) {
+      const uint32_t val = a[i];
+      if (resp_gt(val, a[first])) {
+        for (int k = i; k > first; --k) a[k] = a[k - 1];
+        a[first] = val;
+      } else {
+        int k = i;
+        while (resp_gt(val, a[k - 1])) {
+          a[k] = a[k - 1];
+          --k;
+        }
+        a[k] = val;
+      }
+    }
+  }
+  __syncwarp();
+}
+
+struct CellRect {
+  int x0, x1, y0, y1;  // detectable rectangle [x0, x1) x [y0, y1) of the cell (empty when the reference skips it)
+};
+
+__device__ __forceinline__ CellRect cell_rect(const LevelGeom& L, int ci, int cj) {
+  CellRect r;
+  r.x0 = SDORB_EDGE + cj * L.cell_w;
+  r.x1 = (cj == L.cols - 1) ? L.max_bx : r.x0 + L.cell_w;
+  r.y0 = SDORB_EDGE + ci * L.cell_h;
+  r.y1 = (ci == L.rows - 1) ? L.max_by : r.y0 + L.cell_h;
+  // cv::FAST needs a 7 x 7 ROI: a last column / row narrower than that yields nothing (src/ORBextractor.cc:509-532)
+  r.x1 = min(r.x1, L.det_x1);
+  r.y1 = min(r.y1, L.det_y1);
+  if (r.x1 <= r.x0 || r.y1 <= r.y0) r.x1 = r.x0, r.y1 = r.y0;
+  return r;
+}
+
+// Walks the cell rectangle of the keypoint map in row-major order and writes SDORB_ENTRY(y, x, score) of every keypoint
+// to dst in that order; returns their number.  Item i of the walk is word (i % nwords) of row (i / nwords); a warp
+// takes 32 * U consecutive items per step with all U loads in flight before the first is consumed.
+template <int U>
+__device__ int scan_cell(const uint8_t* __restrict__ map, int pitch, const CellRect& r, int th, int lane, uint32_t* dst, int cap) {
+  if (r.x1 <= r.x0) return 0;
+  const int w0 = r.x0 >> 2, nwords = ((r.x1 - 1) >> 2) - w0 + 1;
+  const int items = nwords * (r.y1 - r.y0);
+  const bool small = items < 65536;
+  const uint32_t magic = nwords >= 2 ? 0xFFFFFFFFu / (uint32_t)nwords + 1u : 0u;  // i / nwords == umulhi(i, magic) for i < 65536
+  const uint32_t lt = (1u << lane) - 1u;
+  int count = 0;
+  for (int base = 0; base < items; base += 32 * U) {
+    uint32_t v[U];
+    int xs[U], ys[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = base + 32 * u + lane;
+      v[u] = 0;
+      xs[u] = ys[u] = 0;
+      if (i < items) {
+        const int row = nwords == 1 ? i : (small ? (int)__umulhi((uint32_t)i, magic) : i / nwords);
+        const int xw = (w0 + i - row * nwords) << 2, y = r.y0 + row;
+        uint32_t t = *reinterpret_cast<const uint32_t*>(map + (int64_t)y * pitch + xw);
+        if (xw < r.x0) t &= 0xFFFFFFFFu << (8 * (r.x0 - xw));
+        if (xw + 4 > r.x1) t &= 0xFFFFFFFFu >> (8 * (xw + 4 - r.x1));
+        v[u] = t;
+        xs[u] = xw;
+        ys[u] = y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (base + 32 * u >= items) break;  // warp-uniform
+      const uint32_t nz = (((v[u] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v[u]) & 0x80808080u;  // bit 7 of every non-zero byte
+      const int c = __popc(nz);
+      const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2),
+                     b2 = __ballot_sync(0xffffffffu, c & 4);
+      if (b0 | b1 | b2) {
+        int idx = count + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
+        for (uint32_t m = nz; m; m &= m - 1, ++idx) {
+          const int q = (__ffs(m) - 1) >> 3;
+          if (idx < cap) dst[idx] = SDORB_ENTRY(ys[u], xs[u] + q, (int)((v[u] >> (8 * q)) & 0xFFu) + th - 1);
+        }
+        count += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+      }
+    }
+  }
+  return count;
+}
+
+constexpr int GATHER_WARPS = 4;
+
+__global__ void __launch_bounds__(GATHER_WARPS * 32) gather_cells_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p,
+                                                                         SelectBuffers buf) {
+  const int lane = threadIdx.x & 31;
+  const int gcell = blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);  // cell index over all levels of the frame
+  const int frame = blockIdx.y;
+  if (gcell >= geom->cells_total) return;
+  int level = 0;
+  while (level + 1 < geom->nlevels && gcell >= geom->lv[level + 1].cell_base) ++level;
+  // levels without cells share the cell_base of the next level: skip forward to the one that owns gcell
+  while (!(geom->lv[level].cols > 0 && geom->lv[level].rows > 0)) --level;
+  const LevelGeom& L = geom->lv[level];
+  const int c = gcell - L.cell_base;
+  int32_t* seen = buf.cell_seen + (int64_t)frame * geom->cells_total + gcell;
+  if (L.list_cap_cell == 0) {
+    if (lane == 0) *seen = 0;
+    return;
+  }
+  const uint8_t* map = p.nms + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
+  uint32_t* list = buf.cell_list + (int64_t)frame * geom->list_total + L.list_base + (int64_t)c * L.list_cap_cell;
+  const CellRect r = cell_rect(L, c / L.cols, c % L.cols);
+  const int n = scan_cell<8>(map, L.pitch, r, geom->th_fast, lane, list, L.list_cap_cell);
+  if (lane == 0) {
+    *seen = n;
+    if (n > L.list_cap_cell) atomicExch(buf.error_flag, 6);  // cannot happen: the capacity bounds what strict NMS leaves
   }
 }
 
@@ -57,6 +226,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const FrameGeom* __
   int* offs = n_retain + max_cells;  // max_cells + 1 entries
   uint32_t* lvl = smem + 3 * max_cells + 1;
   uint32_t* work = lvl + lvl_cap;
+  uint16_t* idx_scratch = reinterpret_cast<uint16_t*>(work + SEL_WARPS * SEL_WORK_CAP);
   __shared__ int s_total;
 
   const int level = blockIdx.x, frame = blockIdx.y;
@@ -68,15 +238,11 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const FrameGeom* __
     if (tid == 0) *out_count = 0;
     return;
   }
-  int32_t* cnt = buf.cell_count + (int64_t)frame * geom->cells_total + L.cell_base;
-  int32_t* seen = buf.cell_seen + (int64_t)frame * geom->cells_total + L.cell_base;
+  const int32_t* seen = buf.cell_seen + (int64_t)frame * geom->cells_total + L.cell_base;
   uint32_t* lists = buf.cell_list + (int64_t)frame * geom->list_total + L.list_base;
-  for (int c = tid; c < n_cells; c += SEL_THREADS) {
-    const int n = cnt[c];
-    n_total[c] = min(n, L.list_cap_cell);
-    seen[c] = n;  // what FAST found (parity tests read this)
-    cnt[c] = 0;   // re-arm the append counters for the next pass: the FAST stage stays a single kernel
-  }
+
+  // keypoints per cell, counted by gather_cells_kernel
+  for (int c = tid; c < n_cells; c += SEL_THREADS) n_total[c] = min(seen[c], L.list_cap_cell);
   __syncthreads();
 
   if (tid == 0) {
@@ -129,22 +295,29 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const FrameGeom* __
   }
   __syncthreads();
 
-  // per-cell retainBest
+  // pass 2: gather each cell in emission order, retainBest, append the survivors to the level list
   uint32_t* wbuf = work + warp * SEL_WORK_CAP;
+  uint16_t* Lidx = idx_scratch + warp * 2 * SEL_WORK_CAP;
+  uint16_t* Ridx = Lidx + SEL_WORK_CAP;
   for (int c = warp; c < n_cells; c += SEL_WARPS) {
     const int n = n_total[c], r = n_retain[c];
     if (r == 0) continue;
+    const bool in_smem = n <= SEL_WORK_CAP;
     uint32_t* list = lists + (int64_t)c * L.list_cap_cell;
     uint32_t* a = list;
-    if (n <= SEL_WORK_CAP) {
+    if (in_smem) {
       a = wbuf;
-      for (int i = lane; i < n; i += 32) a[i] = list[i];
+      const int m = n > r ? n : r;  // an untrimmed cell only needs its first r (== n) entries
+      for (int i = lane; i < m; i += 32) a[i] = list[i];
       __syncwarp();
     }
-    warp_sort(a, n, lane);
     if (n > r) {
-      if (lane == 0) nth_element_resp(a, 0, r - 1, n);
-      __syncwarp();
+      if (in_smem) {
+        warp_nth_element(a, 0, r - 1, n, lane, Lidx, Ridx);
+      } else {
+        if (lane == 0) nth_element_resp(a, 0, r - 1, n);
+        __syncwarp();
+      }
     }
     const int o = offs[c];
     for (int i = lane; i < r; i += 32)
@@ -158,7 +331,13 @@ __global__ void __launch_bounds__(SEL_THREADS) select_kernel(const FrameGeom* __
   int keep = total;
   if (total > L.n_desired) {
     keep = L.n_desired;
-    if (tid == 0 && keep > 0) nth_element_resp(lvl, 0, keep - 1, total);
+    if (keep > 0 && warp == 0) {
+      if (total <= SEL_WORK_CAP) {
+        warp_nth_element(lvl, 0, keep - 1, total, lane, Lidx, Ridx);
+      } else if (lane == 0) {
+        nth_element_resp(lvl, 0, keep - 1, total);
+      }
+    }
     __syncthreads();
   }
   uint32_t* sel = buf.sel + (int64_t)frame * geom->sel_total + L.sel_base;
@@ -182,13 +361,36 @@ static void select_caps(const FrameGeom& g, int* max_cells, int* lvl_cap) {
 size_t select_smem_bytes(const FrameGeom& g) {
   int mc, lc;
   select_caps(g, &mc, &lc);
-  return sizeof(uint32_t) * ((size_t)3 * mc + 1 + lc + (size_t)SEL_WARPS * SEL_WORK_CAP);
+  return sizeof(uint32_t) * ((size_t)3 * mc + 1 + lc + (size_t)SEL_WARPS * SEL_WORK_CAP) +
+         sizeof(uint16_t) * (size_t)SEL_WARPS * 2 * SEL_WORK_CAP + 16;
 }
 
-void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const SelectBuffers& b, int nframes, cudaStream_t s) {
+void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b, int nframes,
+                   cudaStream_t s) {
   int mc, lc;
   select_caps(g, &mc, &lc);
+  if (g.cells_total > 0)
+    gather_cells_kernel<<<dim3((g.cells_total + GATHER_WARPS - 1) / GATHER_WARPS, nframes), GATHER_WARPS * 32, 0, s>>>(d_geom, p, b);
   select_kernel<<<dim3(g.nlevels, nframes), SEL_THREADS, select_smem_bytes(g), s>>>(d_geom, b, mc, lc);
+}
+
+// ---- test hook
+__global__ void __launch_bounds__(32) debug_nth_element_kernel(uint32_t* entries, int n, int nth) {
+  __shared__ uint32_t a[SEL_WORK_CAP];
+  __shared__ uint16_t li[SEL_WORK_CAP], ri[SEL_WORK_CAP];
+  const int lane = threadIdx.x;
+  if (n > SEL_WORK_CAP) {
+    if (lane == 0) nth_element_resp(entries, 0, nth, n);
+    return;
+  }
+  for (int i = lane; i < n; i += 32) a[i] = entries[i];
+  __syncwarp();
+  warp_nth_element(a, 0, nth, n, lane, li, ri);
+  for (int i = lane; i < n; i += 32) entries[i] = a[i];
+}
+
+void launch_debug_nth_element(uint32_t* d_entries, int n, int nth, cudaStream_t s) {
+  debug_nth_element_kernel<<<1, 32, 0, s>>>(d_entries, n, nth);
 }
 
 int configure_kernels() {

@@ -38,9 +38,9 @@ struct sdorb_handle {
   ResizeGroup* d_groups = nullptr;
   int* d_umax = nullptr;
   // scratch for max_batch frames of the current geometry
-  uint8_t *d_pyr = nullptr, *d_blur = nullptr;
+  uint8_t *d_pyr = nullptr, *d_blur = nullptr, *d_nms = nullptr;
   uint8_t* d_stage_in[2] = {nullptr, nullptr};
-  int32_t *d_cell_count = nullptr, *d_cell_seen = nullptr, *d_sel_count = nullptr, *d_error = nullptr;
+  int32_t *d_cell_seen = nullptr, *d_sel_count = nullptr, *d_error = nullptr;
   uint32_t *d_cell_list = nullptr, *d_sel = nullptr;
   // output staging for the host path (2 slots)
   sdorb_keypoint* d_kps[2] = {nullptr, nullptr};
@@ -97,9 +97,9 @@ void free_geometry_scratch(sdorb_handle* h) {
   dfree(h->d_groups);
   dfree(h->d_pyr);
   dfree(h->d_blur);
+  dfree(h->d_nms);
   dfree(h->d_stage_in[0]);
   dfree(h->d_stage_in[1]);
-  dfree(h->d_cell_count);
   dfree(h->d_cell_seen);
   dfree(h->d_cell_list);
   dfree(h->d_sel);
@@ -143,10 +143,9 @@ int ensure_geometry(sdorb_handle* h, int width, int height) {
     CU(cudaMemcpy(h->d_groups, groups.data(), sizeof(ResizeGroup) * groups.size(), cudaMemcpyHostToDevice));
   CU(cudaMalloc(&h->d_pyr, (size_t)g.plane_total * B + 256));
   CU(cudaMalloc(&h->d_blur, (size_t)g.plane_total * B + 256));
+  CU(cudaMalloc(&h->d_nms, (size_t)g.plane_total * B + 256));
   const size_t cells_bytes = sizeof(int32_t) * std::max<size_t>((size_t)g.cells_total * B, 1);
-  CU(cudaMalloc(&h->d_cell_count, cells_bytes));
   CU(cudaMalloc(&h->d_cell_seen, cells_bytes));
-  CU(cudaMemset(h->d_cell_count, 0, cells_bytes));  // the select kernel re-zeroes what the FAST kernel counted
   CU(cudaMemset(h->d_cell_seen, 0, cells_bytes));
   CU(cudaMalloc(&h->d_cell_list, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
   CU(cudaMalloc(&h->d_sel, sizeof(uint32_t) * std::max<size_t>((size_t)g.sel_total * B, 1)));
@@ -217,8 +216,9 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
   const FrameGeom& g = h->geom;
   planes.pyr = h->d_pyr;
   planes.blur = h->d_blur;
+  planes.nms = h->d_nms;
   planes.batch_cap = h->prm.max_batch;
-  SelectBuffers sb{h->d_cell_count, h->d_cell_seen, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error};
+  SelectBuffers sb{h->d_cell_seen, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error};
   {
     StageScope st(h, s, SDORB_STAGE_PYRAMID);
     for (int l = 1; l < g.nlevels; ++l) {
@@ -229,14 +229,14 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
   {
     StageScope st(h, s, SDORB_STAGE_FAST);
     if (g.tiles_total_fast > 0) {
-      launch_fast_all(h->d_geom, g, planes, sb, n, s);
+      launch_fast_all(h->d_geom, g, planes, n, s);
       st.launched();
     }
   }
   {
     StageScope st(h, s, SDORB_STAGE_SELECT);
-    launch_select(h->d_geom, g, sb, n, s);
-    st.launched();
+    launch_select(h->d_geom, g, planes, sb, n, s);
+    st.launched(g.cells_total > 0 ? 2 : 1);  // gather_cells_kernel + select_kernel
   }
   {
     StageScope st(h, s, SDORB_STAGE_BLUR);
@@ -698,6 +698,23 @@ int sdorb_get_stage_times(sdorb_handle* h, double* ms, int64_t* launches, int re
 }
 
 int64_t sdorb_kernel_launches(const sdorb_handle* h) { return h ? h->launches : 0; }
+
+int sdorb_debug_nth_element(sdorb_handle* h, uint32_t* entries, int n, int nth) {
+  if (!h || !entries || n <= 0 || nth < 0 || nth >= n || n > 65535) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  uint32_t* d = nullptr;
+  CU(cudaMalloc(&d, sizeof(uint32_t) * (size_t)n));
+  int rc = SDORB_OK;
+  if (cudaMemcpy(d, entries, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) rc = SDORB_ERR_CUDA;
+  if (rc == SDORB_OK) {
+    launch_debug_nth_element(d, n, nth, h->s_compute);
+    h->launches += 1;
+    if (cudaStreamSynchronize(h->s_compute) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = SDORB_ERR_CUDA;
+  }
+  if (rc == SDORB_OK && cudaMemcpy(entries, d, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SDORB_ERR_CUDA;
+  cudaFree(d);
+  return rc;
+}
 
 int64_t sdorb_debug_read(sdorb_handle* h, int what, int frame, int level, void* dst, size_t capacity) {
   if (!h || !dst || h->gw == 0 || frame < 0 || frame >= h->prm.max_batch || level < 0 || level >= h->geom.nlevels)

@@ -9,10 +9,10 @@
 #define SDORB_MAX_DIM 4095   // keypoint entries pack y:12 | x:12 | score:8
 #define SDORB_MAX_CELLS_PER_LEVEL 4096
 
-// Tile shapes of the all-level launches.  A FAST tile scores 128 x 32 pixels starting at column 16 + 124*tx (a
-// multiple of 4, so every staged row is word aligned) and row 18 + 30*ty, and emits keypoints for the inner
-// 124 x 30 pixels starting at (18 + 124*tx, 19 + 30*ty); the first detectable pixel is (19,19).
-#define SDORB_FAST_TW 124
+// Tile shapes of the all-level launches.  A FAST tile scores 128 x 32 pixels starting at column 12 + 120*tx (a
+// multiple of 4, so every staged row is word aligned) and row 18 + 30*ty, and writes the keypoint map for the inner
+// 120 x 30 pixels (30 whole words per row) starting at (16 + 120*tx, 19 + 30*ty); the first detectable pixel is (19,19).
+#define SDORB_FAST_TW 120
 #define SDORB_FAST_TH 30
 #define SDORB_BLUR_TW 128
 #define SDORB_BLUR_TH 32
@@ -32,6 +32,7 @@ struct LevelGeom {
   int n_desired;         // mnFeaturesPerLevel[level]
   int cols, rows;        // levelCols, levelRows  (0 => the level produces nothing)
   int cell_w, cell_h;    // cellW, cellH
+  uint32_t cell_w_magic, cell_h_magic;  // floor(2^32 / d) + 1: n / d == umulhi(n, magic) for n < 65536, d >= 2
   int n_features_cell;   // nfeaturesCell
   int max_bx, max_by;    // maxBorderX / maxBorderY  (= w-19, h-19)
   int last_x0, last_y0;  // first detectable x / y of the last cell column / row

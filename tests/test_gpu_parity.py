@@ -270,6 +270,37 @@ def test_pyramid_output_has_reflect101_border(ex_c1):
     assert np.array_equal(pyr[0], img)
 
 
+# ------------------------------------------------------------------ the selection order: device nth_element vs libstdc++
+def _std_nth_element(entries, nth):
+    """Ground truth from the real std::nth_element (oracle retainBest with n = nth + 1 keeps the arrangement of the
+    first nth + 1 elements; the tail order is checked through the full-permutation harness on the CPU)."""
+    order = orc.retain_best_order((entries & 0xFF).astype(np.float32), nth + 1)
+    return entries[order]
+
+
+def test_warp_nth_element_equals_std(ex_c1):
+    """The warp-parallel Hoare partition must leave the first nth + 1 elements exactly where libstdc++ leaves them
+    (that prefix, in that order, is what retainBest + resize keeps)."""
+    rng = np.random.default_rng(123)
+    cases = []
+    for n in (2, 3, 4, 5, 8, 31, 32, 33, 64, 100, 257, 400, 777, 1024):
+        for distinct in (1, 2, 5, 40, 255):
+            e = (np.arange(n, dtype=np.uint32) << 8) | rng.integers(1, distinct + 1, n).astype(np.uint32)
+            for nth in sorted({0, n // 7, n // 2, n - 2} & set(range(n - 1))):
+                cases.append((e, nth))
+    base = np.arange(600, dtype=np.uint32)
+    for pat in (base % 200 + 1, (600 - base) % 200 + 1, np.minimum(base, 600 - base) % 250 + 1):
+        cases.append(((base << 8) | pat.astype(np.uint32), 150))
+        cases.append(((base << 8) | pat.astype(np.uint32), 3))
+    big = (np.arange(3000, dtype=np.uint32) << 8) | rng.integers(1, 60, 3000).astype(np.uint32)  # > shared capacity: one-lane path
+    cases.append((big, 700))
+    for e, nth in cases:
+        got = ex_c1.debug_nth_element(e, nth)
+        exp = _std_nth_element(e, nth)
+        assert sorted(got.tolist()) == sorted(e.tolist())
+        assert np.array_equal(got[:nth + 1], exp[:nth + 1]), "n=%d nth=%d" % (len(e), nth)
+
+
 # ------------------------------------------------------------------ full-size, size-independent properties
 def test_full_size_batch_properties():
     """256 frames of the C3 shape: every frame yields exactly 1000 keypoints; the run is idempotent; a frame's
