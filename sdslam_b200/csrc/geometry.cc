@@ -119,7 +119,7 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
   taps->clear();
   if (groups) groups->clear();
   const float ratio = (float)width / height;
-  int cell_base = 0, sel_base = 0, tile_fast = 0, tile_blur = 0;
+  int cell_base = 0, sel_base = 0, tile_fast = 0, tile_fastn = 0, tile_blur = 0;
   int64_t list_base = 0, plane_base = 0;
   for (int l = 0; l < t.nlevels; ++l) {
     LevelGeom& L = g->lv[l];
@@ -197,11 +197,27 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
     if (!any_detect) L.det_x1 = L.det_y1 = 0;
     // flattened tile tables
     L.tile_base_fast = tile_fast;
+    L.tile_base_fastn = tile_fastn;
     if (any_detect) {
-      L.tiles_x_fast = (L.det_x1 - 16 + SDORB_FAST_TW - 1) / SDORB_FAST_TW;
+      // full tiles emit 120 columns each from column 16 on; the remainder goes to one column of narrow tiles
+      const int span = L.det_x1 - 16, rest = span % SDORB_FAST_TW;
+      L.tiles_x_fast = span / SDORB_FAST_TW;
       L.tiles_y_fast = (L.det_y1 - SDORB_EDGE + SDORB_FAST_TH - 1) / SDORB_FAST_TH;
+      if (rest > 0) {
+        L.fastn_words = 32;
+        for (int nw = 4; nw < 32; nw *= 2)
+          if ((nw - 2) * 4 >= rest) {
+            L.fastn_words = nw;
+            break;
+          }
+        if (L.fastn_words == 32) {  // too wide for a narrow tile: one more full tile
+          L.fastn_words = 0;
+          ++L.tiles_x_fast;
+        }
+      }
     }
     tile_fast += L.tiles_x_fast * L.tiles_y_fast;
+    tile_fastn += L.fastn_words ? L.tiles_y_fast : 0;
     L.tile_base_blur = tile_blur;
     L.tiles_x_blur = (L.w + SDORB_BLUR_TW - 1) / SDORB_BLUR_TW;
     L.tiles_y_blur = (L.h + SDORB_BLUR_TH - 1) / SDORB_BLUR_TH;
@@ -249,6 +265,7 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
   g->list_total = list_base;
   g->plane_total = plane_base;
   g->tiles_total_fast = tile_fast;
+  g->tiles_total_fastn = tile_fastn;
   g->tiles_total_blur = tile_blur;
   return 0;
 }

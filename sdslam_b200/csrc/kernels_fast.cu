@@ -32,7 +32,7 @@ constexpr int SROWS = OH + 2;                          // scored rows (outputs +
 constexpr int PWORDS = SWORDS + 2;                     // staged pixel words per row (scored +- 4 px)
 constexpr int PROWS = SROWS + 6;                       // staged pixel rows (scored +- 3)
 constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in words (one zero word on each side)
-constexpr int NT = 256;
+constexpr int NT = 64;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 
@@ -126,24 +126,23 @@ __device__ __forceinline__ int div_magic(int n, int d, uint32_t magic) {  // n /
   return d == 1 ? n : (int)__umulhi((uint32_t)n, magic);
 }
 
-__global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p) {
-  __shared__ __align__(16) uint32_t s_pix[PROWS][PWORDS];
-  __shared__ __align__(16) uint32_t s_t[SROWS][TWORDS];
-  __shared__ uint32_t s_rowflags[OH];
-  __shared__ int s_level;
+// One tile.  NARROW = false: 32 scored words per row, one warp per row (all index arithmetic folds to constants).
+// NARROW = true: the last tile column of a level, fast_last_words (4, 8 or 16) words per row, 32 / nw rows per warp step.
+template <bool NARROW>
+__device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, const BatchPlanes& p, const int level, const LevelGeom& L,
+                                          uint32_t (&s_pix)[PROWS][PWORDS], uint32_t (&s_t)[SROWS][TWORDS], uint32_t (&s_rowflags)[OH]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) {
-    int l = 0;
-    while (l + 1 < geom->nlevels && (int)blockIdx.x >= geom->lv[l + 1].tile_base_fast) ++l;
-    s_level = l;
-  }
-  __syncthreads();
-  const int level = s_level;
-  const LevelGeom& L = geom->lv[level];
   const int frame = blockIdx.y;
-  const int t = blockIdx.x - L.tile_base_fast;
-  const int a = 12 + (t % L.tiles_x_fast) * OW;            // first scored column (multiple of 4); outputs are [a+4, a+4+OW)
-  const int b = SDORB_EDGE + (t / L.tiles_x_fast) * OH;    // first output row; scored rows are [b-1, b+OH+1)
+  const int t = (int)blockIdx.x - (NARROW ? L.tile_base_fastn : L.tile_base_fast);
+  const int tx = NARROW ? L.tiles_x_fast : t % L.tiles_x_fast;  // the narrow tile follows the level's full tiles
+  const int ty = NARROW ? t : t / L.tiles_x_fast;
+  // A tile scores nw words per row: 32 (one warp per row), or fewer in the last tile column, where a warp then takes
+  // 32 / nw rows per step so that no lane scores columns beyond the detectable area.
+  const int nw = NARROW ? L.fastn_words : SWORDS;
+  const int lg = NARROW ? 31 - __clz(nw) : 5, rps = 32 >> lg;  // rows per warp step
+  const int k = lane & (nw - 1), sub = lane >> lg;             // this lane's scored word and its row within the step
+  const int a = 12 + tx * OW;                              // first scored column (multiple of 4); outputs are words 1 .. nw-2
+  const int b = SDORB_EDGE + ty * OH;                      // first output row; scored rows are [b-1, b+OH+1)
   const int w = L.w, h = L.h;
   const int th = geom->th_fast;
   int pitch;
@@ -156,13 +155,13 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
     src = p.pyr + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
   }
 
-  // ---- stage pixels: rows b-4 .. b+OH+3, columns a-4 .. a+131 as aligned words, one warp per row; zero outside the image
+  // ---- stage pixels: rows b-4 .. b+OH+3, columns a-4 .. a+4*nw+3 as aligned words, one warp per row; zero outside the image
   for (int r = warp; r < PROWS; r += NT / 32) {
     const int gy = b - 4 + r;
     const uint8_t* row = src + (int64_t)gy * pitch;
     const bool row_ok = gy >= 0 && gy < h;
-    for (int k = lane; k < PWORDS; k += 32) {
-      const int gx = a - 4 + 4 * k;
+    for (int kk = lane; kk < nw + 2; kk += 32) {
+      const int gx = a - 4 + 4 * kk;
       uint32_t v = 0;
       if (row_ok && gx < w) {
         if (gx + 4 <= w) {
@@ -173,12 +172,12 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
             if (gx + q < w) v |= (uint32_t)row[gx + q] << (8 * q);
         }
       }
-      s_pix[r][k] = v;
+      s_pix[r][kk] = v;
     }
   }
   if (tid < SROWS) {
     s_t[tid][0] = 0;
-    s_t[tid][TWORDS - 1] = 0;
+    s_t[tid][nw + 1] = 0;
   }
   if (tid < OH) {  // which vertical neighbours of output row tid lie in the same cell (0 for rows below the detectable area)
     const int y = b + tid;
@@ -194,7 +193,7 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
   __syncthreads();
 
   // ---- per-thread column constants: this lane owns pixels x = xw .. xw+3 in every row it touches
-  const int xw = a + 4 * lane;
+  const int xw = a + 4 * k;
   const int vx1 = L.det_x1, vy1 = L.det_y1;  // detectable area is [19, det_x1) x [19, det_y1)
   uint32_t valid_cols = 0;                  // byte mask: pixel may carry a score
   uint32_t lm[2] = {0, 0}, rm[2] = {0, 0};  // 16-bit lane masks: left / right neighbour lies in the same cell
@@ -222,61 +221,84 @@ __global__ void __launch_bounds__(NT, 2) fast_all_kernel(const FrameGeom* __rest
   const uint32_t C = (uint32_t)(127 - (th_high ? th - 128 : th)) * 0x01010101u;
   const uint32_t th2 = (uint32_t)(th + 256) * 0x00010001u;
 
-  // ---- phase S: dense scores.  Warp `warp` owns scored rows warp, warp+8, ...; scored row sr is image row b-1+sr
-  // and staged row sr+3; lane k owns scored word k = staged word k+1.
-  for (int sr = warp; sr < SROWS; sr += NT / 32) {
+  // ---- phase S: dense scores.  Scored row sr is image row b-1+sr and staged row sr+3; scored word k is staged word k+1.
+  for (int base = 0; base < SROWS; base += (NT / 32) * rps) {
+    const int sr = base + warp * rps + sub;
     const int gy = b - 1 + sr;
+    const bool in_tile = sr < SROWS;
+    const bool active = in_tile && gy >= SDORB_EDGE && gy < vy1;
     uint32_t T = 0;
-    if (gy >= SDORB_EDGE && gy < vy1) {  // warp-uniform
+    if (__any_sync(0xffffffffu, active)) {
+      const int srl = min(sr, SROWS - 1);
       uint32_t W[7][3];
 #pragma unroll
       for (int dy = 0; dy < 7; ++dy) {
-        W[dy][0] = s_pix[sr + dy][lane];
-        W[dy][1] = s_pix[sr + dy][lane + 1];
-        W[dy][2] = s_pix[sr + dy][lane + 2];
+        W[dy][0] = s_pix[srl + dy][k];
+        W[dy][1] = s_pix[srl + dy][k + 1];
+        W[dy][2] = s_pix[srl + dy][k + 2];
       }
-      // compass pre-test on 4 pixels: a 9-arc contains one of ring {0,8} and one of ring {4,12}
+      // compass pre-test on 4 pixels (a 9-arc contains one of ring {0,8} and one of ring {4,12}): lets the warp skip the
+      // pixel pairs that no lane needs (flat image regions)
+      const uint32_t live = active ? valid_cols : 0u;
       const uint32_t c = W[3][1];
       const uint32_t lf = prmt(W[3][0], c, 0x4321), rt = prmt(c, W[3][2], 0x6543);
       const uint32_t fv = gt_th(__vabsdiffu4(W[0][1], c), C, th_high) | gt_th(__vabsdiffu4(W[6][1], c), C, th_high);
       const uint32_t fh = gt_th(__vabsdiffu4(lf, c), C, th_high) | gt_th(__vabsdiffu4(rt, c), C, th_high);
-      const uint32_t cand = fv & fh & 0x80808080u & valid_cols;
+      const uint32_t cand = fv & fh & 0x80808080u & live;
       uint32_t t0 = 0, t1 = 0;
       if (__any_sync(0xffffffffu, cand & 0x00008080u)) t0 = score_pair<0>(W, th2);
       if (__any_sync(0xffffffffu, cand & 0x80800000u)) t1 = score_pair<1>(W, th2);
-      T = prmt(t0, t1, 0x6420) & valid_cols;
+      T = prmt(t0, t1, 0x6420) & live;
     }
-    s_t[sr][lane + 1] = T;
+    if (in_tile) s_t[sr][k + 1] = T;
   }
   __syncthreads();
 
   // ---- phase N: cell-bounded strict non-max suppression on the score tile; the survivors' t bytes go to the map
   uint8_t* map = p.nms + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
-  const bool out_lane = lane >= 1 && lane <= OW / 4 && xw < L.pitch;
-  for (int orow = warp; orow < OH; orow += NT / 32) {
-    const int sr = orow + 1, y = b + orow;
-    if (y >= h) break;
-    const uint32_t cw = s_t[sr][lane + 1];
+  const bool out_lane = k >= 1 && k <= nw - 2 && xw < L.pitch;
+  for (int base = 0; base < OH; base += (NT / 32) * rps) {
+    const int orow = base + warp * rps + sub;
+    const int y = b + orow;
+    const bool active = orow < OH && y < h;
+    const int sr = min(orow, OH - 1) + 1;
+    const uint32_t cw = active ? s_t[sr][k + 1] : 0u;
     uint32_t keep_bytes = 0;
     if (__any_sync(0xffffffffu, cw != 0)) {
-      const uint32_t rowflags = s_rowflags[orow];  // bit 0: row above is in the same cell, bit 1: row below is
+      const uint32_t rowflags = s_rowflags[sr - 1];  // bit 0: row above is in the same cell, bit 1: row below is
       uint32_t Tn[3][3];
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
-        Tn[0][j] = (rowflags & 1u) ? s_t[sr - 1][lane + j] : 0u;
-        Tn[1][j] = s_t[sr][lane + j];
-        Tn[2][j] = (rowflags & 2u) ? s_t[sr + 1][lane + j] : 0u;
+        Tn[0][j] = (rowflags & 1u) ? s_t[sr - 1][k + j] : 0u;
+        Tn[1][j] = s_t[sr][k + j];
+        Tn[2][j] = (rowflags & 2u) ? s_t[sr + 1][k + j] : 0u;
       }
       const uint32_t kept = nms_pair<0>(Tn, lm[0], rm[0]) | (nms_pair<1>(Tn, lm[1], rm[1]) << 2);
       keep_bytes = ((kept * 0x00204081u) & 0x01010101u) * 0xFFu;  // bit q -> byte q
     }
-    if (out_lane) *reinterpret_cast<uint32_t*>(map + (int64_t)y * L.pitch + xw) = cw & keep_bytes;
+    if (active && out_lane) *reinterpret_cast<uint32_t*>(map + (int64_t)y * L.pitch + xw) = cw & keep_bytes;
   }
 }
 
+template <bool NARROW>
+__global__ void __launch_bounds__(NT, 1024 / NT) fast_tiles_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p) {
+  __shared__ __align__(16) uint32_t s_pix[PROWS][PWORDS];
+  __shared__ __align__(16) uint32_t s_t[SROWS][TWORDS];
+  __shared__ uint32_t s_rowflags[OH];
+  __shared__ int s_level;
+  if (threadIdx.x == 0) {
+    int l = 0;
+    while (l + 1 < geom->nlevels && (int)blockIdx.x >= (NARROW ? geom->lv[l + 1].tile_base_fastn : geom->lv[l + 1].tile_base_fast)) ++l;
+    s_level = l;
+  }
+  __syncthreads();
+  const int level = s_level;
+  fast_tile<NARROW>(geom, p, level, geom->lv[level], s_pix, s_t, s_rowflags);
+}
+
 void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s) {
-  if (g.tiles_total_fast == 0) return;
-  fast_all_kernel<<<dim3(g.tiles_total_fast, nframes), NT, 0, s>>>(d_geom, p);
+  if (g.tiles_total_fast > 0) fast_tiles_kernel<false><<<dim3(g.tiles_total_fast, nframes), NT, 0, s>>>(d_geom, p);
+  if (g.tiles_total_fastn > 0) fast_tiles_kernel<true><<<dim3(g.tiles_total_fastn, nframes), NT, 0, s>>>(d_geom, p);
 }
 
 }  // namespace sdorb

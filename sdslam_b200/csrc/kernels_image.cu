@@ -142,24 +142,27 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 }
 
 constexpr int BTW = SDORB_BLUR_TW, BTH = SDORB_BLUR_TH;  // 128 x 32 output pixels per block
-constexpr int B_WORDS = BTW / 4;        // output words per row
-constexpr int B_SRC_WORDS = B_WORDS + 2;  // staged source words per row: x0-4 .. x0+TW+3
-constexpr int B_ROWS = BTH + 6;         // staged rows: y0-3 .. y0+TH+2
-constexpr int B_VROWS = 4;              // output rows per thread in the vertical pass
-static_assert(BTW == 128 && (BTH % B_VROWS) == 0 && (BTH / B_VROWS) * B_WORDS == 256, "blur tiling assumes 256 threads");
+constexpr int B_WORDS = BTW / 4;        // output words per row (= one warp)
+constexpr int B_ROWS = BTH + 6;         // source rows of a tile: y0-3 .. y0+TH+2
+constexpr int B_WARPS = 4;
+constexpr int B_HROWS = (B_ROWS + B_WARPS - 1) / B_WARPS;  // source rows per warp in the horizontal pass
+constexpr int B_VROWS = BTH / B_WARPS;  // output rows per thread in the vertical pass
+static_assert(BTW == 128, "one warp spans a tile row");
 
-__global__ void __launch_bounds__(256) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p) {
-  __shared__ __align__(16) uint32_t s_src[B_ROWS][B_SRC_WORDS];
+// four pixels starting at column gx of a row, BORDER_REFLECT_101 outside [0, w).  Out of line on purpose: only the one
+// or two lanes of a row that straddle the right image edge ever come here.
+__device__ __noinline__ uint32_t blur_edge_word(const uint8_t* __restrict__ row, int gx, int w) {
+  uint32_t v = 0;
+#pragma unroll
+  for (int b = 0; b < 4; ++b) v |= (uint32_t)row[reflect101(gx + b, w)] << (8 * b);
+  return v;
+}
+
+__global__ void __launch_bounds__(B_WARPS * 32) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p) {
   __shared__ __align__(16) uint2 s_h[B_ROWS][B_WORDS];  // horizontal sums, four 16-bit values per entry
-  __shared__ int s_level;
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    int l = 0;
-    while (l + 1 < geom->nlevels && (int)blockIdx.x >= geom->lv[l + 1].tile_base_blur) ++l;
-    s_level = l;
-  }
-  __syncthreads();
-  const int level = s_level;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int level = 0;
+  while (level + 1 < geom->nlevels && (int)blockIdx.x >= geom->lv[level + 1].tile_base_blur) ++level;
   const LevelGeom& L = geom->lv[level];
   const int frame = blockIdx.y;
   const int t = blockIdx.x - L.tile_base_blur;
@@ -168,51 +171,65 @@ __global__ void __launch_bounds__(256) blur_all_kernel(const FrameGeom* __restri
   int spitch;
   const uint8_t* src = level_plane(p, L, level, frame, &spitch);
 
-  // stage rows y0-3 .. y0+TH+2 (reflected), columns x0-4 .. x0+TW+3 as 32-bit words
-  for (int i = tid; i < B_ROWS * B_SRC_WORDS; i += 256) {
-    const int r = i / B_SRC_WORDS, k = i - r * B_SRC_WORDS;
-    const int gy = reflect101(y0 - 3 + r, h);
-    const int gx = x0 - 4 + 4 * k;
-    const uint8_t* row = src + (int64_t)gy * spitch;
-    uint32_t v;
-    if (gx >= 0 && gx + 3 < w) {
-      v = *reinterpret_cast<const uint32_t*>(row + gx);
-    } else {
-      v = 0;
+  // ---- horizontal pass straight from global memory: warp = one source row, lane = one word of it; the neighbour words
+  // come from the neighbour lanes, the two halo words from one extra load on lanes 0 and 31.  All loads of the warp's
+  // rows are issued before the first is used.
+  const int gx = x0 + 4 * lane;
+  const bool interior = gx + 3 < w;                         // this lane's word lies fully inside the row
+  const bool edge = !interior && gx < w + 4;                // straddles the right edge (taps reach 3 px beyond it)
+  const int hx = lane == 0 ? x0 - 4 : x0 + BTW;             // halo word column (lanes 0 and 31 only)
+  const bool h_lane = (lane == 0 && x0 > 0) || lane == 31;  // the left halo of the first tile is mirrored from w1, w2 below
+  const bool h_interior = hx + 3 < w;
+  const bool h_edge = !h_interior && hx < w + 4;
+  uint32_t cw[B_HROWS], ew[B_HROWS];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) v |= (uint32_t)row[reflect101(gx + b, w)] << (8 * b);
+  for (int j = 0; j < B_HROWS; ++j) {
+    const int r = warp + j * B_WARPS;
+    cw[j] = ew[j] = 0;
+    if (r < B_ROWS) {
+      int gy = y0 - 3 + r;
+      gy = gy < 0 ? -gy : gy;
+      gy = gy >= h ? 2 * (h - 1) - gy : gy;
+      if ((unsigned)gy >= (unsigned)h) gy = reflect101(y0 - 3 + r, h);  // images lower than the filter radius
+      const uint8_t* row = src + (int64_t)gy * spitch;
+      if (interior) cw[j] = *reinterpret_cast<const uint32_t*>(row + gx);
+      else if (edge) cw[j] = blur_edge_word(row, gx, w);
+      if (h_lane) {
+        if (h_interior) ew[j] = *reinterpret_cast<const uint32_t*>(row + hx);
+        else if (h_edge) ew[j] = blur_edge_word(row, hx, w);
+      }
     }
-    s_src[r][k] = v;
   }
-  __syncthreads();
-
-  // horizontal pass: H[x] = sum_i K[i] * src[x + i - 3]; the seven taps of a pixel are two byte quadruples
   constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);  // taps -3..0
   constexpr uint32_t KB = 48u | (34u << 8) | (18u << 16);                // taps +1..+3 (+4 unused)
-  for (int i = tid; i < B_ROWS * B_WORDS; i += 256) {
-    const int r = i / B_WORDS, k = i - r * B_WORDS;
-    const uint32_t w0 = s_src[r][k], w1 = s_src[r][k + 1], w2 = s_src[r][k + 2];  // px x-4..x-1 | x..x+3 | x+4..x+7
+#pragma unroll
+  for (int j = 0; j < B_HROWS; ++j) {
+    const int r = warp + j * B_WARPS;
+    if (r >= B_ROWS) break;  // warp-uniform
+    const uint32_t w1 = cw[j];
+    uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
+    if (lane == 0) w0 = x0 > 0 ? ew[j] : __byte_perm(w1, w2, 0x1234);  // px -4..-1 mirror px 4..1
+    if (lane == 31) w2 = ew[j];
+    // H[x] = sum_i K[i] * src[x + i - 3]: the seven taps of a pixel are two byte quadruples of (w0 w1) and (w1 w2)
     const uint32_t h0 = __dp4a(__byte_perm(w0, w1, 0x4321), KA, __dp4a(__byte_perm(w1, w2, 0x4321), KB, 0u));
     const uint32_t h1 = __dp4a(__byte_perm(w0, w1, 0x5432), KA, __dp4a(__byte_perm(w1, w2, 0x5432), KB, 0u));
     const uint32_t h2 = __dp4a(__byte_perm(w0, w1, 0x6543), KA, __dp4a(__byte_perm(w1, w2, 0x6543), KB, 0u));
     const uint32_t h3 = __dp4a(w1, KA, __dp4a(w2, KB, 0u));
-    s_h[r][k] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    s_h[r][lane] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
   }
   __syncthreads();
 
-  // vertical pass: thread = one word column x B_VROWS output rows; V[y] = sum_j K[j] * H[y + j - 3] over row pairs
-  const int k = tid & (B_WORDS - 1), g = tid / B_WORDS;
-  const int gx = x0 + 4 * k;
+  // ---- vertical pass: thread = one word column x B_VROWS output rows; V[y] = sum_j K[j] * H[y + j - 3] over row pairs
   if (gx >= w) return;
   uint2 hv[B_VROWS + 6];
 #pragma unroll
-  for (int j = 0; j < B_VROWS + 6; ++j) hv[j] = s_h[g * B_VROWS + j][k];
+  for (int j = 0; j < B_VROWS + 6; ++j) hv[j] = s_h[warp * B_VROWS + j][lane];
   uint8_t* dst = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
   constexpr uint32_t K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8);
 #pragma unroll
   for (int o = 0; o < B_VROWS; ++o) {
-    const int gy = y0 + g * B_VROWS + o;
-    if (gy >= h) continue;
+    const int gy = y0 + warp * B_VROWS + o;
+    if (gy >= h) break;  // warp-uniform
     uint32_t acc[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -235,7 +252,7 @@ __global__ void __launch_bounds__(256) blur_all_kernel(const FrameGeom* __restri
 
 void launch_blur_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s) {
   if (g.tiles_total_blur == 0) return;
-  blur_all_kernel<<<dim3(g.tiles_total_blur, nframes), 256, 0, s>>>(d_geom, p);
+  blur_all_kernel<<<dim3(g.tiles_total_blur, nframes), B_WARPS * 32, 0, s>>>(d_geom, p);
 }
 
 }  // namespace sdorb

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -28,8 +29,10 @@ struct sdorb_handle {
   sdorb_params prm{};
   Tables tables;
   int device = 0;
-  cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr;
+  cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr, s_aux = nullptr;
   cudaEvent_t ev_in[2]{}, ev_compute[2]{}, ev_out[2]{};
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // the blur runs beside FAST + selection on s_aux
+  bool overlap = false;  // measured: no gain (FAST's CTAs fill every SM first); kept for experiments via SDORB_OVERLAP=1
   // geometry of the current image size
   int gw = 0, gh = 0;
   FrameGeom geom{};
@@ -226,11 +229,21 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
       st.launched();
     }
   }
+  // The blur only needs the pyramid, FAST + selection only the pyramid too: the blur (byte dot products, FMA pipe) runs
+  // on a second stream beside FAST (min / max, ALU pipe) and joins before the descriptors.
+  const bool fork = h->overlap;
+  if (fork) {
+    CU(cudaEventRecord(h->ev_fork, s));
+    CU(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
+    StageScope st(h, h->s_aux, SDORB_STAGE_BLUR);
+    launch_blur_all(h->d_geom, g, planes, n, h->s_aux);
+    st.launched();
+  }
   {
     StageScope st(h, s, SDORB_STAGE_FAST);
-    if (g.tiles_total_fast > 0) {
+    if (g.tiles_total_fast + g.tiles_total_fastn > 0) {
       launch_fast_all(h->d_geom, g, planes, n, s);
-      st.launched();
+      st.launched((g.tiles_total_fast > 0) + (g.tiles_total_fastn > 0));  // full tiles, narrow last-column tiles
     }
   }
   {
@@ -238,7 +251,10 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
     launch_select(h->d_geom, g, planes, sb, n, s);
     st.launched(g.cells_total > 0 ? 2 : 1);  // gather_cells_kernel + select_kernel
   }
-  {
+  if (fork) {
+    CU(cudaEventRecord(h->ev_join, h->s_aux));
+    CU(cudaStreamWaitEvent(s, h->ev_join, 0));
+  } else {
     StageScope st(h, s, SDORB_STAGE_BLUR);
     launch_blur_all(h->d_geom, g, planes, n, s);
     st.launched();
@@ -309,6 +325,10 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   };
   DeviceGuard guard(dev);
   if (cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (const char* e = getenv("SDORB_OVERLAP")) h->overlap = e[0] != '0';
   if (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   for (int i = 0; i < 2; ++i) {
@@ -330,6 +350,7 @@ void sdorb_destroy(sdorb_handle* h) {
   {
     DeviceGuard guard(h->device);
     if (h->s_compute) cudaStreamSynchronize(h->s_compute);
+    if (h->s_aux) cudaStreamSynchronize(h->s_aux);
     if (h->s_in) cudaStreamSynchronize(h->s_in);
     if (h->s_out) cudaStreamSynchronize(h->s_out);
     free_geometry_scratch(h);
@@ -346,6 +367,9 @@ void sdorb_destroy(sdorb_handle* h) {
       if (h->ev_compute[i]) cudaEventDestroy(h->ev_compute[i]);
       if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
     }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->s_aux) cudaStreamDestroy(h->s_aux);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);

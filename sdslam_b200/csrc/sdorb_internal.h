@@ -12,6 +12,7 @@
 // Tile shapes of the all-level launches.  A FAST tile scores 128 x 32 pixels starting at column 12 + 120*tx (a
 // multiple of 4, so every staged row is word aligned) and row 18 + 30*ty, and writes the keypoint map for the inner
 // 120 x 30 pixels (30 whole words per row) starting at (16 + 120*tx, 19 + 30*ty); the first detectable pixel is (19,19).
+// What is left of a level's width after the full tiles goes to one column of narrow tiles (16, 32 or 64 pixels scored).
 #define SDORB_FAST_TW 120
 #define SDORB_FAST_TH 30
 #define SDORB_BLUR_TW 128
@@ -44,7 +45,8 @@ struct LevelGeom {
   int64_t list_base;     // offset (entries) of this level's first cell list in the per-frame list array
   int64_t plane_base;    // offset (bytes) of this level's plane array in the pyramid / blur scratch
   int64_t plane_bytes;   // pitch * h
-  int tile_base_fast, tiles_x_fast, tiles_y_fast;  // flattened tile tables for the all-level launches
+  int tile_base_fast, tiles_x_fast, tiles_y_fast;  // flattened tile tables for the all-level launches (full FAST tiles)
+  int tile_base_fastn, fastn_words;  // narrow FAST tiles of the last tile column: scored words per row (4, 8, 16; 0 = none)
   int tile_base_blur, tiles_x_blur, tiles_y_blur;
   int scaled_patch_size; // (int)(31 * mvScaleFactor[level])
   float scale;           // mvScaleFactor[level]
@@ -59,7 +61,7 @@ struct FrameGeom {
   int th_fast;
   int cells_total;      // per-frame cells over all levels
   int sel_total;        // per-frame selected-entry slots (sum of n_desired)
-  int tiles_total_fast, tiles_total_blur;
+  int tiles_total_fast, tiles_total_fastn, tiles_total_blur;
   int64_t list_total;   // per-frame cell-list entries over all levels
   int64_t plane_total;  // per-frame... unused (planes are level-major); bytes of one frame over all levels
   LevelGeom lv[SDORB_MAX_LEVELS];
