@@ -14,9 +14,18 @@
 
 namespace sdorb {
 
-__device__ const int8_t d_pattern[1024] = {
-#include "orb_pattern.inc"
+// bit_pattern_31_ (src/ORBextractor.cc:146-404) as floats, bit-major: entry [bit * 32 + byte] = (x0, y0, x1, y1) of
+// comparison 8 * byte + bit.  Lane = descriptor byte, so a warp reads 32 consecutive entries (512 B) through L1, which
+// keeps the kernel free of shared memory and lets CTAs be two warps.
+__device__ const float4 d_pattern_f[256] = {
+#define P4(a, b, c, d) {(float)(a), (float)(b), (float)(c), (float)(d)},
+#include "orb_pattern4.inc"
+#undef P4
 };
+
+// cvRound(v) (cvtss2si, round half to even) for |v| < 2^22 without the conversion unit: adding 1.5 * 2^23 rounds to the
+// nearest integer in the float's low mantissa bits with the same tie rule.
+__device__ __forceinline__ int round_even_small(float v) { return __float_as_int(__fadd_rn(v, 12582912.f)) - 0x4B400000; }
 
 // cv::fastAtan2 scalar path (OpenCV core mathfuncs_core: atan_f32), degrees in [0, 360)
 __device__ __forceinline__ float fast_atan2_deg(float y, float x) {
@@ -84,16 +93,14 @@ __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp)
   }
 }
 
-constexpr int DESC_THREADS = 256;
+constexpr int DESC_THREADS = 64;
+constexpr int PATCH_ROWS = 37, PATCH_WORDS = 11;  // +-18 rows; 37 columns starting up to 3 px left of kx - 18
 
 __global__ void __launch_bounds__(DESC_THREADS) describe_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p,
                                                                 SelectBuffers buf, const int* __restrict__ umax_tab,
                                                                 float* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
                                                                 int32_t* __restrict__ counts_out, int capacity) {
-  __shared__ __align__(16) int8_t s_pat[1024];
-  for (int i = threadIdx.x; i < 256; i += DESC_THREADS)
-    reinterpret_cast<uint32_t*>(s_pat)[i] = reinterpret_cast<const uint32_t*>(d_pattern)[i];
-  __syncthreads();
+  __shared__ uint32_t s_patch[DESC_THREADS / 32][PATCH_ROWS * PATCH_WORDS];
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * (DESC_THREADS / 32) + (threadIdx.x >> 5);
   const int frame = blockIdx.y;
@@ -115,6 +122,23 @@ __global__ void __launch_bounds__(DESC_THREADS) describe_kernel(const FrameGeom*
   const LevelGeom& L = geom->lv[level];
   const uint32_t e = buf.sel[(int64_t)frame * geom->sel_total + L.sel_base + idx];
   const int kx = SDORB_ENTRY_X(e), ky = SDORB_ENTRY_Y(e);
+
+  // ---- stage the blurred patch: the 512 descriptor samples lie within +-18 px of the keypoint.  37 rows x 11 aligned
+  // words are fetched as coalesced row segments (74 sectors) instead of 512 scattered byte reads through L1; issued
+  // here so that they complete under the intensity-centroid phase.
+  uint32_t* patch = s_patch[threadIdx.x >> 5];
+  const int xa = (kx - 18) & ~3;  // first staged column (word aligned); the patch row r holds image row ky - 18 + r
+  {
+    const uint8_t* bsrc = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes + (int64_t)(ky - 18) * L.pitch + xa;
+#pragma unroll
+    for (int j = 0; j < (PATCH_ROWS * PATCH_WORDS + 31) / 32; ++j) {
+      const int i = lane + 32 * j;
+      if (i < PATCH_ROWS * PATCH_WORDS) {
+        const int r = i / PATCH_WORDS, c = i - r * PATCH_WORDS;
+        patch[i] = *reinterpret_cast<const uint32_t*>(bsrc + (int64_t)r * L.pitch + 4 * c);
+      }
+    }
+  }
 
   // ---- IC_Angle on the unblurred level
   int pitch;
@@ -149,21 +173,18 @@ __global__ void __launch_bounds__(DESC_THREADS) describe_kernel(const FrameGeom*
   float sn, cs;
   sincosf_glibc(__fmul_rn(angle, 0x1.1df46ap-6f), &sn, &cs);
   const float a = cs, b = sn;
-  const uint8_t* bc = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes + (int64_t)ky * L.pitch + kx;
-  const int bp = L.pitch;
-  const int8_t* pat = s_pat + lane * 32;
+  __syncwarp();
+  const uint8_t* bc = reinterpret_cast<const uint8_t*>(patch) + 18 * (PATCH_WORDS * 4) + (kx - xa);  // the keypoint inside the staged patch
+  constexpr int bp = PATCH_WORDS * 4;
+  const float4* pat = d_pattern_f + lane;
   int val = 0;
 #pragma unroll
   for (int bit = 0; bit < 8; ++bit) {
-    int t[2];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const float px = (float)pat[4 * bit + 2 * q], py = (float)pat[4 * bit + 2 * q + 1];
-      const int dr = __float2int_rn(__fmaf_rn(px, b, __fmul_rn(py, a)));
-      const int dc = __float2int_rn(__fmaf_rn(px, a, -__fmul_rn(py, b)));
-      t[q] = bc[dr * bp + dc];
-    }
-    val |= (t[0] < t[1]) << bit;
+    const float4 pp = __ldg(pat + 32 * bit);
+    const int r0 = round_even_small(__fmaf_rn(pp.x, b, __fmul_rn(pp.y, a))), c0 = round_even_small(__fmaf_rn(pp.x, a, -__fmul_rn(pp.y, b)));
+    const int r1 = round_even_small(__fmaf_rn(pp.z, b, __fmul_rn(pp.w, a))), c1 = round_even_small(__fmaf_rn(pp.z, a, -__fmul_rn(pp.w, b)));
+    const int t0 = bc[r0 * bp + c0], t1 = bc[r1 * bp + c1];
+    val |= (t0 < t1) << bit;
   }
   desc_out[((int64_t)frame * capacity + slot) * 32 + lane] = (uint8_t)val;
   if (lane == 0) {

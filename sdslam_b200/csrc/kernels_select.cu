@@ -139,50 +139,62 @@ __device__ __forceinline__ CellRect cell_rect(const LevelGeom& L, int ci, int cj
 }
 
 // Walks the cell rectangle of the keypoint map in row-major order and writes SDORB_ENTRY(y, x, score) of every keypoint
-// to dst in that order; returns their number.  Item i of the walk is word (i % nwords) of row (i / nwords); a warp
-// takes 32 * U consecutive items per step with all U loads in flight before the first is consumed.
+// to dst in that order; returns their number.  Item i of the walk is the 16-byte segment (i % nseg) of row (i / nseg);
+// a warp takes 32 * U consecutive items per step with all U loads in flight before the first is consumed.
 template <int U>
 __device__ int scan_cell(const uint8_t* __restrict__ map, int pitch, const CellRect& r, int th, int lane, uint32_t* dst, int cap) {
   if (r.x1 <= r.x0) return 0;
-  const int w0 = r.x0 >> 2, nwords = ((r.x1 - 1) >> 2) - w0 + 1;
-  const int items = nwords * (r.y1 - r.y0);
+  const int q0 = r.x0 >> 4, nseg = ((r.x1 - 1) >> 4) - q0 + 1;
+  const int items = nseg * (r.y1 - r.y0);
   const bool small = items < 65536;
-  const uint32_t magic = nwords >= 2 ? 0xFFFFFFFFu / (uint32_t)nwords + 1u : 0u;  // i / nwords == umulhi(i, magic) for i < 65536
+  const uint32_t magic = nseg >= 2 ? 0xFFFFFFFFu / (uint32_t)nseg + 1u : 0u;  // i / nseg == umulhi(i, magic) for i < 65536
   const uint32_t lt = (1u << lane) - 1u;
   int count = 0;
   for (int base = 0; base < items; base += 32 * U) {
-    uint32_t v[U];
+    uint4 v[U];
     int xs[U], ys[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int i = base + 32 * u + lane;
-      v[u] = 0;
+      v[u] = make_uint4(0u, 0u, 0u, 0u);
       xs[u] = ys[u] = 0;
       if (i < items) {
-        const int row = nwords == 1 ? i : (small ? (int)__umulhi((uint32_t)i, magic) : i / nwords);
-        const int xw = (w0 + i - row * nwords) << 2, y = r.y0 + row;
-        uint32_t t = *reinterpret_cast<const uint32_t*>(map + (int64_t)y * pitch + xw);
-        if (xw < r.x0) t &= 0xFFFFFFFFu << (8 * (r.x0 - xw));
-        if (xw + 4 > r.x1) t &= 0xFFFFFFFFu >> (8 * (xw + 4 - r.x1));
-        v[u] = t;
-        xs[u] = xw;
-        ys[u] = y;
+        const int row = nseg == 1 ? i : (small ? (int)__umulhi((uint32_t)i, magic) : i / nseg);
+        xs[u] = (q0 + i - row * nseg) << 4;
+        ys[u] = r.y0 + row;
+        v[u] = *reinterpret_cast<const uint4*>(map + (int64_t)ys[u] * pitch + xs[u]);
       }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (base + 32 * u >= items) break;  // warp-uniform
-      const uint32_t nz = (((v[u] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | v[u]) & 0x80808080u;  // bit 7 of every non-zero byte
-      const int c = __popc(nz);
-      const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2),
-                     b2 = __ballot_sync(0xffffffffu, c & 4);
-      if (b0 | b1 | b2) {
-        int idx = count + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt);
-        for (uint32_t m = nz; m; m &= m - 1, ++idx) {
-          const int q = (__ffs(m) - 1) >> 3;
-          if (idx < cap) dst[idx] = SDORB_ENTRY(ys[u], xs[u] + q, (int)((v[u] >> (8 * q)) & 0xFFu) + th - 1);
+      uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      uint32_t nz[4];
+      int c = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int xw = xs[u] + 4 * j;
+        // bytes outside [x0, x1) belong to the neighbouring cells
+        if (xw + 4 <= r.x0 || xw >= r.x1) wv[j] = 0;
+        else {
+          if (xw < r.x0) wv[j] &= 0xFFFFFFFFu << (8 * (r.x0 - xw));
+          if (xw + 4 > r.x1) wv[j] &= 0xFFFFFFFFu >> (8 * (xw + 4 - r.x1));
         }
-        count += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+        nz[j] = (((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wv[j]) & 0x80808080u;  // bit 7 of every non-zero byte
+        c += (int)(((nz[j] >> 7) * 0x01010101u) >> 24);
+      }
+      // inside one cell strict 3x3 suppression leaves at most 8 keypoints in 16 consecutive pixels: 4 count bits
+      const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2),
+                     b2 = __ballot_sync(0xffffffffu, c & 4), b3 = __ballot_sync(0xffffffffu, c & 8);
+      if (b0 | b1 | b2 | b3) {
+        int idx = count + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          for (uint32_t m = nz[j]; m; m &= m - 1, ++idx) {
+            const int q = (__ffs(m) - 1) >> 3;
+            if (idx < cap) dst[idx] = SDORB_ENTRY(ys[u], xs[u] + 4 * j + q, (int)((wv[j] >> (8 * q)) & 0xFFu) + th - 1);
+          }
+        count += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
       }
     }
   }
@@ -211,7 +223,7 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_cells_kernel(const F
   const uint8_t* map = p.nms + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
   uint32_t* list = buf.cell_list + (int64_t)frame * geom->list_total + L.list_base + (int64_t)c * L.list_cap_cell;
   const CellRect r = cell_rect(L, c / L.cols, c % L.cols);
-  const int n = scan_cell<8>(map, L.pitch, r, geom->th_fast, lane, list, L.list_cap_cell);
+  const int n = scan_cell<4>(map, L.pitch, r, geom->th_fast, lane, list, L.list_cap_cell);
   if (lane == 0) {
     *seen = n;
     if (n > L.list_cap_cell) atomicExch(buf.error_flag, 6);  // cannot happen: the capacity bounds what strict NMS leaves
