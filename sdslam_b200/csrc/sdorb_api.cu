@@ -32,7 +32,7 @@ struct sdorb_handle {
   cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr, s_aux = nullptr;
   cudaEvent_t ev_in[2]{}, ev_compute[2]{}, ev_out[2]{};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // the blur runs beside FAST + selection on s_aux
-  bool overlap = false;  // measured: no gain (FAST's CTAs fill every SM first); kept for experiments via SDORB_OVERLAP=1
+  bool overlap = false;  // measured: +0.5 % at best (every kernel here is issue-bound, so co-residency buys nothing); SDORB_OVERLAP=1 enables it
   // geometry of the current image size
   int gw = 0, gh = 0;
   FrameGeom geom{};
