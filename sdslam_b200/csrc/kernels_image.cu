@@ -145,7 +145,6 @@ constexpr int BTW = SDORB_BLUR_TW, BTH = SDORB_BLUR_TH;  // 128 x 32 output pixe
 constexpr int B_WORDS = BTW / 4;        // output words per row (= one warp)
 constexpr int B_ROWS = BTH + 6;         // source rows of a tile: y0-3 .. y0+TH+2
 constexpr int B_WARPS = 4;
-constexpr int B_HROWS = (B_ROWS + B_WARPS - 1) / B_WARPS;  // source rows per warp in the horizontal pass
 constexpr int B_VROWS = BTH / B_WARPS;  // output rows per thread in the vertical pass
 static_assert(BTW == 128, "one warp spans a tile row");
 
@@ -172,8 +171,7 @@ __global__ void __launch_bounds__(B_WARPS * 32) blur_all_kernel(const FrameGeom*
   const uint8_t* src = level_plane(p, L, level, frame, &spitch);
 
   // ---- horizontal pass straight from global memory: warp = one source row, lane = one word of it; the neighbour words
-  // come from the neighbour lanes, the two halo words from one extra load on lanes 0 and 31.  All loads of the warp's
-  // rows are issued before the first is used.
+  // come from the neighbour lanes, the two halo words from one extra load on lanes 0 and 31.
   const int gx = x0 + 4 * lane;
   const bool interior = gx + 3 < w;                         // this lane's word lies fully inside the row
   const bool edge = !interior && gx < w + 4;                // straddles the right edge (taps reach 3 px beyond it)
@@ -181,16 +179,21 @@ __global__ void __launch_bounds__(B_WARPS * 32) blur_all_kernel(const FrameGeom*
   const bool h_lane = (lane == 0 && x0 > 0) || lane == 31;  // the left halo of the first tile is mirrored from w1, w2 below
   const bool h_interior = hx + 3 < w;
   const bool h_edge = !h_interior && hx < w + 4;
+  constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);  // taps -3..0
+  constexpr uint32_t KB = 48u | (34u << 8) | (18u << 16);                // taps +1..+3 (+4 unused)
+  constexpr int B_HROWS = (B_ROWS + B_WARPS - 1) / B_WARPS;              // source rows per warp
+  const int hlast = 2 * (h - 1);
+  // all loads of the warp's rows are issued before the first is used (the pass is latency-bound otherwise)
   uint32_t cw[B_HROWS], ew[B_HROWS];
 #pragma unroll
   for (int j = 0; j < B_HROWS; ++j) {
     const int r = warp + j * B_WARPS;
     cw[j] = ew[j] = 0;
     if (r < B_ROWS) {
-      int gy = y0 - 3 + r;
-      gy = gy < 0 ? -gy : gy;
-      gy = gy >= h ? 2 * (h - 1) - gy : gy;
-      if ((unsigned)gy >= (unsigned)h) gy = reflect101(y0 - 3 + r, h);  // images lower than the filter radius
+      // BORDER_REFLECT_101 of the row index without branches: one reflection is enough for every level that can hold a
+      // keypoint (h >= 45); the clamp only keeps degenerate levels inside their plane
+      int gy = abs(y0 - 3 + r);
+      gy = max(min(gy, hlast - gy), 0);
       const uint8_t* row = src + (int64_t)gy * spitch;
       if (interior) cw[j] = *reinterpret_cast<const uint32_t*>(row + gx);
       else if (edge) cw[j] = blur_edge_word(row, gx, w);
@@ -200,8 +203,6 @@ __global__ void __launch_bounds__(B_WARPS * 32) blur_all_kernel(const FrameGeom*
       }
     }
   }
-  constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);  // taps -3..0
-  constexpr uint32_t KB = 48u | (34u << 8) | (18u << 16);                // taps +1..+3 (+4 unused)
 #pragma unroll
   for (int j = 0; j < B_HROWS; ++j) {
     const int r = warp + j * B_WARPS;
