@@ -453,12 +453,18 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
     return SDORB_OK;
   }
 
-  // host path: three-stream pipeline over passes of max_batch frames
+  // host path: three-stream pipeline over passes of up to max_batch frames.  Only the first upload and the last
+  // download are exposed, so the passes ramp up from max_batch / 8 and taper off the same way at the end.
   rc = ensure_host_staging(h, capacity);
   if (rc) return rc;
   int pass = 0;
-  for (int f0 = 0; f0 < nframes; f0 += B, ++pass) {
-    const int n = std::min(B, nframes - f0), slot = pass & 1;
+  const int n_min = std::max(B / 8, 1);
+  int ramp = n_min;
+  for (int f0 = 0, n = 0; f0 < nframes; f0 += n, ++pass) {
+    const int left = nframes - f0;
+    n = std::min(std::min(ramp, B), std::max((left + 1) / 2, std::min(left, n_min)));
+    ramp = std::min(ramp * 2, B);
+    const int slot = pass & 1;
     if (pass >= 2) CU(cudaStreamWaitEvent(h->s_in, h->ev_compute[slot], 0));
     if (frame_stride == row_stride * (size_t)height) {
       CU(cudaMemcpy2DAsync(h->d_stage_in[slot], L0.pitch, images + (size_t)f0 * frame_stride, row_stride, width,

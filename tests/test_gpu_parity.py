@@ -97,6 +97,43 @@ def test_stages_match_oracle(label, img, params):
     ex.close()
 
 
+def test_c5_full_size_1080p_matches_oracle():
+    """BASELINE config C5 at its real size: 1920x1080, 4000 keypoints, 12 levels (144-cell grids, lists beyond the
+    shared-memory capacity of the selection kernel, 4-, 8- and 16-word narrow FAST tiles)."""
+    params = (4000, 1.2, 12, 20)
+    img = synth.smooth_noise(300, 1920, 1080)
+    ok, od = orc.Extractor(*params).extract(img)
+    ex = api.ORBextractor(*params, max_width=1920, max_height=1080, max_batch=2)
+    k, d, pyr = ex(img)
+    assert len(ok) == 4000
+    assert_same(ok, od, k, d, "C5 1080p")
+    kk, dd, cc = ex.extract_batch_host(np.stack([img, synth.rects(301, 1920, 1080)]))
+    assert_same(ok, od, kk[0, :cc[0]], dd[0, :cc[0]], "C5 batch frame 0")
+    ok1, od1 = orc.Extractor(*params).extract(synth.rects(301, 1920, 1080))
+    assert_same(ok1, od1, kk[1, :cc[1]], dd[1, :cc[1]], "C5 rects")
+    ex.close()
+
+
+@pytest.mark.parametrize("w,h", [(39 + 64, 39 + 40), (128 + 19, 101), (641, 479), (1241, 376)])
+def test_odd_sizes_and_tile_edges(w, h):
+    """Widths around the 120-column FAST tiles / 128-column blur tiles and heights around the 30-row tiles."""
+    params = (600, 1.2, 5, 15)
+    img = np.random.default_rng(w * 7 + h).integers(0, 256, (h, w), dtype=np.uint8)
+    img = (img // 3 + synth.smooth_noise(w, w, h) // 2).astype(np.uint8)
+    try:
+        ok, od = orc.Extractor(*params).extract(img)
+    except RuntimeError:
+        ex = api.ORBextractor(*params, max_width=w, max_height=h, max_batch=1)
+        with pytest.raises(api.SdorbError):
+            ex(img)
+        ex.close()
+        return
+    ex = api.ORBextractor(*params, max_width=w, max_height=h, max_batch=1)
+    k, d, _ = ex(img)
+    assert_same(ok, od, k, d, "%dx%d" % (w, h))
+    ex.close()
+
+
 # ------------------------------------------------------------------ entry-point equivalence
 def test_batch_host_equals_single_and_oracle(ex_c1):
     imgs = synth.frames(5, 640, 480, start=60)
