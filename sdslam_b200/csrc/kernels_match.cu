@@ -3,8 +3,8 @@
 // Reference: /root/reference/src/ORBmatcher.cc:1459-1473 (256-bit Hamming distance as eight 32-bit SWAR popcounts,
 // == __popc) and the best / second-best scan of SearchByPoints (:1239-1265):
 //     if (d < best1) { best2 = best1; best1 = d; idx = j; } else if (d < best2) best2 = d;
-// with j ascending, so the FIRST minimal index wins ties.  Bound: the integer popc pipe, not memory (64 KB in,
-// 16 KB out per 1000x1000 pair).  One thread owns one query row (8 registers); train rows stream through shared
+// with j ascending, so the FIRST minimal index wins ties.  Bound: the integer popc (XU) pipe, not memory (64 KB in,
+// 16 KB out per 1000x1000 pair); ncu: XU pipe 95 % busy.  One thread owns one query row (8 registers); train rows stream through shared
 // memory and are read as broadcasts.  (distance << 16 | j) packs value and index so a single integer min keeps
 // the first-minimum rule; the runner-up needs only  best2 = min(best2, max(d, best1)).
 #include "kernels.cuh"
@@ -15,12 +15,34 @@ struct MatchOut {
   int32_t best_idx, best_dist, second_dist, accepted;
 };
 
+#ifndef SDORB_MATCH_CSA
+#define SDORB_MATCH_CSA 3  // carry-save adders in front of the popcounts (3 -> 5 POPC per pair, 4 -> 4 POPC)
+#endif
 constexpr int M_THREADS = 128;
 constexpr int M_TILE = 256;  // train rows staged per step (8 KB)
 
+// popcount of a 256-bit XOR.  POPC runs on the quarter-rate XU pipe (16 lanes / clk / SM) and is what bounds the
+// matcher, so three carry-save adders (two LOP3 each, ALU pipe) fold seven of the eight words into one "ones" word and
+// three "twos" words first: 5 POPC per pair instead of 8, same integer result.
+template <int LUT>
+__device__ __forceinline__ uint32_t lop3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(c), "n"(LUT));
+  return d;
+}
 __device__ __forceinline__ int hamming256(const uint32_t q[8], const uint4 lo, const uint4 hi) {
-  return __popc(q[0] ^ lo.x) + __popc(q[1] ^ lo.y) + __popc(q[2] ^ lo.z) + __popc(q[3] ^ lo.w) +
-         __popc(q[4] ^ hi.x) + __popc(q[5] ^ hi.y) + __popc(q[6] ^ hi.z) + __popc(q[7] ^ hi.w);
+  const uint32_t x0 = q[0] ^ lo.x, x1 = q[1] ^ lo.y, x2 = q[2] ^ lo.z, x3 = q[3] ^ lo.w;
+  const uint32_t x4 = q[4] ^ hi.x, x5 = q[5] ^ hi.y, x6 = q[6] ^ hi.z, x7 = q[7] ^ hi.w;
+  // carry-save adder: sum = a ^ b ^ c (LUT 0x96), carry = majority(a, b, c) (LUT 0xE8)
+  const uint32_t s1 = lop3<0x96>(x0, x1, x2), c1 = lop3<0xE8>(x0, x1, x2);
+  const uint32_t s2 = lop3<0x96>(x3, x4, x5), c2 = lop3<0xE8>(x3, x4, x5);
+  const uint32_t s3 = lop3<0x96>(s1, s2, x6), c3 = lop3<0xE8>(s1, s2, x6);
+#if SDORB_MATCH_CSA == 4
+  const uint32_t s4 = lop3<0x96>(c1, c2, c3), c4 = lop3<0xE8>(c1, c2, c3);
+  return __popc(s3) + __popc(x7) + 2 * __popc(s4) + 4 * __popc(c4);
+#else
+  return __popc(s3) + __popc(x7) + 2 * (__popc(c1) + __popc(c2) + __popc(c3));
+#endif
 }
 
 __device__ __forceinline__ int accept_rule(int best1, int best2, float ratio, int th_low) {
@@ -44,8 +66,9 @@ __global__ void __launch_bounds__(M_THREADS) match_kernel(const uint8_t* __restr
     q[0] = lo.x; q[1] = lo.y; q[2] = lo.z; q[3] = lo.w;
     q[4] = hi.x; q[5] = hi.y; q[6] = hi.z; q[7] = hi.w;
   }
-  int best1 = (256 << 16) | 0xFFFF;  // distance << 16 | index
-  int best2 = 256;
+  // (distance << 16 | index) orders candidates by distance, then by index: the smallest packed value is the first
+  // minimum, and the second smallest carries the second smallest distance.  Both are tracked packed (3 min / max, no shift).
+  int best1 = (256 << 16) | 0xFFFF, best2 = (256 << 16) | 0xFFFF;
   const uint4* bsrc = reinterpret_cast<const uint4*>(B + (int64_t)pair * strideB * 32);
   for (int j0 = 0; j0 < nb; j0 += M_TILE) {
     const int cnt = min(M_TILE, nb - j0);
@@ -55,16 +78,17 @@ __global__ void __launch_bounds__(M_THREADS) match_kernel(const uint8_t* __restr
 #pragma unroll 4
     for (int j = 0; j < cnt; ++j) {
       const int d = hamming256(q, s_b[2 * j], s_b[2 * j + 1]);
-      best2 = min(best2, max(d, best1 >> 16));
-      best1 = min(best1, (d << 16) | (j0 + j));
+      const int dp = d * 65536 + (j0 + j);  // IMAD: the ALU pipe is the next bottleneck after POPC
+      best2 = min(best2, max(dp, best1));
+      best1 = min(best1, dp);
     }
   }
   if (active) {
     MatchOut o;
     o.best_dist = best1 >> 16;
     o.best_idx = o.best_dist < 256 ? (best1 & 0xFFFF) : -1;
-    o.second_dist = best2;
-    o.accepted = accept_rule(o.best_dist, best2, ratio, th_low);
+    o.second_dist = best2 >> 16;
+    o.accepted = accept_rule(o.best_dist, o.second_dist, ratio, th_low);
     out[(int64_t)pair * strideA + qi] = o;
   }
 }
