@@ -27,7 +27,7 @@
 
 namespace sdorb {
 
-constexpr int SEL_THREADS = 256;
+constexpr int SEL_THREADS = 128;
 constexpr int SEL_WARPS = SEL_THREADS / 32;
 constexpr int SEL_WORK_CAP = 1024;  // entries of per-warp shared scratch; larger lists fall back to global memory + one lane
 

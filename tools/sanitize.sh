@@ -1,5 +1,6 @@
 #!/bin/bash
-# compute-sanitizer memcheck of the whole extraction + matching path on a small batch (run on the GPU box, one tool per call)
+# compute-sanitizer memcheck of the whole extraction + matching path on a small batch (one tool per call).
+# NOTE: on this pool gpurun answers "compute-sanitizer is closed" (2026-10-18); kept for pools where it is open.
 set -e
 cd "$(dirname "$0")/.."
 compute-sanitizer --tool "${1:-memcheck}" --error-exitcode 3 python - <<'PY'
