@@ -160,6 +160,49 @@ def cpu_match_rate(nthreads, npairs, rng):
     return npairs * 1e6 / (time.perf_counter() - t)
 
 
+def cv2_primitives_rate(params, frames, nthreads):
+    """Frames/s of OpenCV's own SIMD kernels for the three heavy primitives of the reference path (chained cv2.resize +
+    copyMakeBorder, cv2.FAST on every cell ROI, cv2.GaussianBlur per level) -- no culling, orientation or descriptors, so
+    an UPPER bound on what the reference binary (which cannot be built here) could reach on this host.  cv2 releases the
+    GIL, so frames are spread over a thread pool.  Reported next to the oracle port for context only."""
+    try:
+        import cv2
+    except Exception:
+        return None
+    from concurrent.futures import ThreadPoolExecutor
+    from sdslam_b200 import api
+    nf, sf, nl, th = params
+    h, w = frames.shape[1:]
+    geom = api.host_level_geometry(nf, sf, nl, th, w, h)
+    cv2.setNumThreads(1)
+    fast = cv2.FastFeatureDetector_create(threshold=th, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+
+    def one(img):
+        lvl, n = img, 0
+        for l, g in enumerate(geom):
+            if l:
+                lvl = cv2.resize(lvl, (int(g["width"]), int(g["height"])), interpolation=cv2.INTER_LINEAR)
+            cv2.copyMakeBorder(lvl, 19, 19, 19, 19, cv2.BORDER_REFLECT_101)
+            cols, rows, cw, ch = int(g["level_cols"]), int(g["level_rows"]), int(g["cell_w"]), int(g["cell_h"])
+            lh, lw = lvl.shape
+            for i in range(max(rows, 0)):
+                y0 = 16 + i * ch
+                y1 = lh - 16 if i == rows - 1 else y0 + ch + 6
+                for j in range(max(cols, 0)):
+                    x0 = 16 + j * cw
+                    x1 = lw - 16 if j == cols - 1 else x0 + cw + 6
+                    if y1 - y0 >= 7 and x1 - x0 >= 7:
+                        n += len(fast.detect(lvl[y0:y1, x0:x1]))
+            cv2.GaussianBlur(lvl, (7, 7), 2, None, 2, cv2.BORDER_REFLECT_101)
+        return n
+
+    one(frames[0])
+    t = time.perf_counter()
+    with ThreadPoolExecutor(nthreads) as pool:
+        list(pool.map(one, frames))
+    return len(frames) / (time.perf_counter() - t)
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path on the host cores.  The reference binary
     cannot be compiled in this image (no OpenCV C++ / Eigen / Pangolin), so this is the oracle port, frame-parallel
@@ -181,12 +224,16 @@ def run_reference(args):
     dt = time.perf_counter() - t
     fps = args.steps * per_step / dt
     sample = "%d frames per step (2 per host thread), oracle port, %d threads frame-parallel" % (per_step, cores)
+    cv2_n = cv2_primitives_rate((nf, sf, nl, th), frames, cores)
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": args.workload, "width": w, "height": h, "nfeatures": nf, "scale_factor": sf, "nlevels": nl,
                        "th_fast": th, "frames_per_step": per_step},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample,
+                             "cv2_primitives_only": {"value": cv2_n, "unit": "frames/s", "cores": cores,
+                                                     "what": "OpenCV 4.13 SIMD resize + per-cell FAST + GaussianBlur only: upper bound "
+                                                             "for the real reference (not buildable here) on this host"}},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "keypoints_per_frame": total / max(1, args.steps * per_step)}
     print(json.dumps(line))
@@ -378,10 +425,14 @@ def run_ours(args):
             fps_n, _ = cpu_extract_rate(params, host_np[:sample_n], cores)
             fps_1, _ = cpu_extract_rate(params, host_np[:16], 1)
             ham_n = cpu_match_rate(cores, max(cores, 8), np.random.default_rng(0))
+            cv2_n = cv2_primitives_rate(params, host_np[:sample_n], cores)
             line["cpu_baseline"] = {"value": fps_n, "unit": "frames/s", "cores": cores, "kind": "port",
                                     "sample": "first %d frames of the same batch, oracle port, %d threads frame-parallel" % (sample_n, cores),
                                     "value_1core": fps_1, "sample_1core": "first 16 frames, 1 thread (the reference's execution model)",
-                                    "hamming_pairs_per_s": ham_n}
+                                    "hamming_pairs_per_s": ham_n,
+                                    "cv2_primitives_only": {"value": cv2_n, "unit": "frames/s", "cores": cores,
+                                                            "what": "OpenCV 4.13 SIMD resize + per-cell FAST + GaussianBlur only (no culling / "
+                                                                    "orientation / descriptors): upper bound for the real reference on this host"}}
         print(json.dumps(line))
     ex.close()
     if world > 1:
