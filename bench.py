@@ -418,6 +418,21 @@ def run_ours(args):
                         "frame_pairs_per_gpu": npairs, "ms": float(tm.item())},
             "gather_ms": gather_ms,
         }
+        # single-frame synchronous latency of the reference-facing call (sdorb_extract: host image in, results on the host),
+        # the way Frame.cc:195 uses the extractor -- outside every timed region above
+        ex1 = api.ORBextractor(*params, device=local, max_width=w, max_height=h, max_batch=1)
+        lat = {}
+        for want in (False, True):
+            for i in range(5):
+                ex1(host_np[i], want_pyramid=want)
+            ts = []
+            for i in range(30):
+                t0 = time.perf_counter()
+                ex1(host_np[i], want_pyramid=want)
+                ts.append(time.perf_counter() - t0)
+            lat["with_pyramid_ms" if want else "keypoints_only_ms"] = float(np.median(ts) * 1e3)
+        ex1.close()
+        line["single_frame_latency"] = lat
         if world == 1 and not args.no_cpu:
             cores = os.cpu_count() or 1
             native_oracle()

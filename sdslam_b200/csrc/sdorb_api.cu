@@ -53,6 +53,9 @@ struct sdorb_handle {
   // matcher temporaries (host path)
   void* d_match_buf = nullptr;
   size_t match_buf_bytes = 0;
+  // pinned staging for the pyramid read-back of the single-frame entry point
+  uint8_t* h_pyr = nullptr;
+  size_t h_pyr_bytes = 0;
   // bookkeeping
   int64_t launches = 0;
   int64_t stage_launches[SDORB_NUM_STAGES] = {0};
@@ -357,6 +360,7 @@ void sdorb_destroy(sdorb_handle* h) {
     dfree(h->d_umax);
     dfree(h->d_error);
     if (h->d_match_buf) cudaFree(h->d_match_buf);
+    if (h->h_pyr) cudaFreeHost(h->h_pyr);
     for (auto& p : h->pending) {
       cudaEventDestroy(p.a);
       cudaEventDestroy(p.b);
@@ -572,15 +576,47 @@ int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, 
   if (rc) return rc;
   *count = n;
   if (pyramid) {
+    // imagePyramid (src/ORBextractor.cc:684-696).  Level 0 is the caller's own image: host-to-host.  Levels >= 1 come back
+    // through one pinned staging buffer with all copies in flight at once, then are laid into the caller's views.
     DeviceGuard guard(h->device);
-    for (int l = 0; l < h->geom.nlevels; ++l) {
+    const int nl = h->geom.nlevels;
+    size_t need = 0;
+    for (int l = 1; l < nl; ++l) need += (size_t)h->geom.lv[l].w * h->geom.lv[l].h;
+    if (need > h->h_pyr_bytes) {
+      if (h->h_pyr) cudaFreeHost(h->h_pyr);
+      h->h_pyr = nullptr;
+      h->h_pyr_bytes = 0;
+      CU(cudaMallocHost(&h->h_pyr, need));
+      h->h_pyr_bytes = need;
+    }
+    for (int l = 0; l < nl; ++l) {
       const LevelGeom& L = h->geom.lv[l];
       const sdorb_pyr_view& v = pyramid[l];
-      if (!v.data) continue;
-      if (v.width != L.w || v.height != L.h || v.stride < (size_t)L.w) return SDORB_ERR_BAD_ARG;
-      const uint8_t* src = l == 0 ? h->d_stage_in[0] : h->d_pyr + (size_t)L.plane_base * h->prm.max_batch;
-      CU(cudaMemcpy2D(v.data, v.stride, src, L.pitch, L.w, L.h, cudaMemcpyDeviceToHost));
-      if (v.border > 0) sdorb_fill_border_reflect101(v.data, L.w, L.h, v.stride, v.border);
+      if (v.data && (v.width != L.w || v.height != L.h || v.stride < (size_t)L.w)) return SDORB_ERR_BAD_ARG;
+    }
+    size_t off = 0;
+    for (int l = 1; l < nl; ++l) {
+      const LevelGeom& L = h->geom.lv[l];
+      if (pyramid[l].data)
+        CU(cudaMemcpy2DAsync(h->h_pyr + off, L.w, h->d_pyr + (size_t)L.plane_base * h->prm.max_batch, L.pitch, L.w, L.h,
+                             cudaMemcpyDeviceToHost, h->s_compute));
+      off += (size_t)L.w * L.h;
+    }
+    if (pyramid[0].data) {  // overlaps the copies above
+      const sdorb_pyr_view& v = pyramid[0];
+      for (int y = 0; y < height; ++y) memcpy(v.data + (size_t)y * v.stride, image + (size_t)y * stride, (size_t)width);
+      if (v.border > 0) sdorb_fill_border_reflect101(v.data, width, height, v.stride, v.border);
+    }
+    CU(cudaStreamSynchronize(h->s_compute));
+    off = 0;
+    for (int l = 1; l < nl; ++l) {
+      const LevelGeom& L = h->geom.lv[l];
+      const sdorb_pyr_view& v = pyramid[l];
+      if (v.data) {
+        for (int y = 0; y < L.h; ++y) memcpy(v.data + (size_t)y * v.stride, h->h_pyr + off + (size_t)y * L.w, (size_t)L.w);
+        if (v.border > 0) sdorb_fill_border_reflect101(v.data, L.w, L.h, v.stride, v.border);
+      }
+      off += (size_t)L.w * L.h;
     }
   }
   return SDORB_OK;
@@ -606,6 +642,7 @@ static int match_common(sdorb_handle* h, const uint8_t* A, const int32_t* nA, in
     const size_t need = up(bytesA) + up(bytesB) + 2 * up(bytesN) + up(bytesO);
     if (need > h->match_buf_bytes) {
       if (h->d_match_buf) cudaFree(h->d_match_buf);
+    if (h->h_pyr) cudaFreeHost(h->h_pyr);
       h->d_match_buf = nullptr;
       h->match_buf_bytes = 0;
       CU(cudaMalloc(&h->d_match_buf, need));
