@@ -35,6 +35,12 @@ constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in wo
 constexpr int NT = 64;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
+// every byte of x replaced by 0xFF if its bit 7 is set, else 0x00 (PRMT's sign-replicate mode, which __byte_perm masks off)
+__device__ __forceinline__ uint32_t spread_bit7(uint32_t x) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
+  return r;
+}
 
 // per-byte (a > th) in bit 7 of each byte; C prepared by the caller from th
 __device__ __forceinline__ uint32_t gt_th(uint32_t a, uint32_t C, bool th_high) {
@@ -107,7 +113,8 @@ __device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const 
   return __vmaxu2(m, th2) - th2;              // (max(A,B') - th) if positive, else 0;  th2 = (th + 256) per lane
 }
 
-// Strict 3x3 non-max test of the two pixels of pair P on packed score lanes (lane = byte * 257).  T[0..2] are the
+// Strict 3x3 non-max test of the two pixels of pair P on packed score lanes (lane = byte * 257): returns per lane
+// centre - min(centre, max of the eight neighbours), non-zero exactly for a survivor.  T[0..2] are the
 // score words of rows y-1, y, y+1 (previous / own / next word); lm / rm zero the neighbours that lie in another cell.
 template <int P>
 __device__ __forceinline__ uint32_t nms_pair(const uint32_t (&T)[3][3], const uint32_t lm, const uint32_t rm) {
@@ -118,8 +125,7 @@ __device__ __forceinline__ uint32_t nms_pair(const uint32_t (&T)[3][3], const ui
   const uint32_t dl = pair_at<P, -1>(T[2][0], T[2][1], T[2][2]) & lm, dr = pair_at<P, 1>(T[2][0], T[2][1], T[2][2]) & rm;
   const uint32_t m1 = __vimax3_u16x2(l, r, u), m2 = __vimax3_u16x2(ul, ur, d), m3 = __vimax3_u16x2(dl, dr, m1);
   const uint32_t nb = __vmaxu2(m2, m3);
-  const uint32_t diff = c - __vminu2(c, nb);  // lane != 0  <=>  centre strictly greater than all eight neighbours
-  return ((diff & 0xFFFFu) != 0 ? 1u : 0u) | ((diff >> 16) != 0 ? 2u : 0u);
+  return c - __vminu2(c, nb);  // lane != 0  <=>  centre strictly greater than all eight neighbours
 }
 
 __device__ __forceinline__ int div_magic(int n, int d, uint32_t magic) {  // n / d for 0 <= n < 65536 (see geometry.cc)
@@ -273,8 +279,9 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
         Tn[1][j] = s_t[sr][k + j];
         Tn[2][j] = (rowflags & 2u) ? s_t[sr + 1][k + j] : 0u;
       }
-      const uint32_t kept = nms_pair<0>(Tn, lm[0], rm[0]) | (nms_pair<1>(Tn, lm[1], rm[1]) << 2);
-      keep_bytes = ((kept * 0x00204081u) & 0x01010101u) * 0xFFu;  // bit q -> byte q
+      // one byte per pixel of the two difference words, "non-zero" into bit 7 of each byte, bit 7 replicated over the byte
+      const uint32_t d4 = prmt(nms_pair<0>(Tn, lm[0], rm[0]), nms_pair<1>(Tn, lm[1], rm[1]), 0x6420);
+      keep_bytes = spread_bit7(((d4 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d4);
     }
     if (active && out_lane) *reinterpret_cast<uint32_t*>(map + (int64_t)y * L.pitch + xw) = cw & keep_bytes;
   }
