@@ -130,12 +130,19 @@ __global__ void __launch_bounds__(DESC_THREADS) describe_kernel(const FrameGeom*
   const int xa = (kx - 18) & ~3;  // first staged column (word aligned); the patch row r holds image row ky - 18 + r
   {
     const uint8_t* bsrc = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes + (int64_t)(ky - 18) * L.pitch + xa;
+    // word i = lane + 32 j of the patch is (row i / 11, column i % 11); stepping i by 32 = 2 * 11 + 10 is stepped incrementally
+    int c = lane % PATCH_WORDS;
+    int off = (lane / PATCH_WORDS) * L.pitch + 4 * c;
+    const int step = 2 * L.pitch + 4 * 10, wrap = L.pitch - 4 * PATCH_WORDS;
 #pragma unroll
     for (int j = 0; j < (PATCH_ROWS * PATCH_WORDS + 31) / 32; ++j) {
       const int i = lane + 32 * j;
-      if (i < PATCH_ROWS * PATCH_WORDS) {
-        const int r = i / PATCH_WORDS, c = i - r * PATCH_WORDS;
-        patch[i] = *reinterpret_cast<const uint32_t*>(bsrc + (int64_t)r * L.pitch + 4 * c);
+      if (i < PATCH_ROWS * PATCH_WORDS) patch[i] = *reinterpret_cast<const uint32_t*>(bsrc + off);
+      c += 10;
+      off += step;
+      if (c >= PATCH_WORDS) {
+        c -= PATCH_WORDS;
+        off += wrap;
       }
     }
   }
@@ -154,16 +161,25 @@ __global__ void __launch_bounds__(DESC_THREADS) describe_kernel(const FrameGeom*
   const int u = lane - SDORB_HALF_PATCH;
   int m10 = 0, m01 = 0;
   if (lane < 31) {
-    m10 = u * center[u];
+    // lane = column u of the disc; its rows are v = -vmax .. vmax with vmax = max{v : |u| <= umax[v]} (umax is decreasing)
     const int au = u < 0 ? -u : u;
-#pragma unroll 5
+    int vmax = 0;
+#pragma unroll
+    for (int v = 1; v <= SDORB_HALF_PATCH; ++v) vmax = au <= umax_tab[v] ? v : vmax;  // uniform loads
+    const uint8_t* pp = center + u;  // walks down
+    const uint8_t* pm = center + u;  // walks up
+    int colsum = *pp;                // sum of the column (for m10), v-weighted difference (for m01)
+#pragma unroll
     for (int v = 1; v <= SDORB_HALF_PATCH; ++v) {
-      if (au <= umax_tab[v]) {
-        const int plus = center[u + v * pitch], minus = center[u - v * pitch];
+      pp += pitch;
+      pm -= pitch;
+      if (v <= vmax) {
+        const int plus = *pp, minus = *pm;
         m01 += v * (plus - minus);
-        m10 += u * (plus + minus);
+        colsum += plus + minus;
       }
     }
+    m10 = u * colsum;
   }
   m10 = __reduce_add_sync(0xffffffffu, m10);
   m01 = __reduce_add_sync(0xffffffffu, m01);
