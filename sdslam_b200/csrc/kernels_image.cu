@@ -185,21 +185,38 @@ __global__ void __launch_bounds__(B_WARPS * 32) blur_all_kernel(const FrameGeom*
   const int hlast = 2 * (h - 1);
   // all loads of the warp's rows are issued before the first is used (the pass is latency-bound otherwise)
   uint32_t cw[B_HROWS], ew[B_HROWS];
+  if (x0 + BTW + 4 <= w) {
+    // tile (and its right halo word) entirely inside the row: plain loads, no edge tests (block-uniform branch)
+    const bool halo = (lane == 0 && x0 > 0) || lane == 31;
 #pragma unroll
-  for (int j = 0; j < B_HROWS; ++j) {
-    const int r = warp + j * B_WARPS;
-    cw[j] = ew[j] = 0;
-    if (r < B_ROWS) {
-      // BORDER_REFLECT_101 of the row index without branches: one reflection is enough for every level that can hold a
-      // keypoint (h >= 45); the clamp only keeps degenerate levels inside their plane
-      int gy = abs(y0 - 3 + r);
-      gy = max(min(gy, hlast - gy), 0);
-      const uint8_t* row = src + (int64_t)gy * spitch;
-      if (interior) cw[j] = *reinterpret_cast<const uint32_t*>(row + gx);
-      else if (edge) cw[j] = blur_edge_word(row, gx, w);
-      if (h_lane) {
-        if (h_interior) ew[j] = *reinterpret_cast<const uint32_t*>(row + hx);
-        else if (h_edge) ew[j] = blur_edge_word(row, hx, w);
+    for (int j = 0; j < B_HROWS; ++j) {
+      const int r = warp + j * B_WARPS;
+      cw[j] = ew[j] = 0;
+      if (r < B_ROWS) {
+        int gy = abs(y0 - 3 + r);  // BORDER_REFLECT_101 of the row index, see below
+        gy = max(min(gy, hlast - gy), 0);
+        const uint8_t* row = src + (int64_t)gy * spitch;
+        cw[j] = *reinterpret_cast<const uint32_t*>(row + gx);
+        if (halo) ew[j] = *reinterpret_cast<const uint32_t*>(row + hx);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < B_HROWS; ++j) {
+      const int r = warp + j * B_WARPS;
+      cw[j] = ew[j] = 0;
+      if (r < B_ROWS) {
+        // BORDER_REFLECT_101 of the row index without branches: one reflection is enough for every level that can hold
+        // a keypoint (h >= 45); the clamp only keeps degenerate levels inside their plane
+        int gy = abs(y0 - 3 + r);
+        gy = max(min(gy, hlast - gy), 0);
+        const uint8_t* row = src + (int64_t)gy * spitch;
+        if (interior) cw[j] = *reinterpret_cast<const uint32_t*>(row + gx);
+        else if (edge) cw[j] = blur_edge_word(row, gx, w);
+        if (h_lane) {
+          if (h_interior) ew[j] = *reinterpret_cast<const uint32_t*>(row + hx);
+          else if (h_edge) ew[j] = blur_edge_word(row, hx, w);
+        }
       }
     }
   }
