@@ -357,6 +357,21 @@ def run_ours(args):
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
     pairs_per_s = world * pairs / (float(tm.item()) * 1e-3)
 
+    # ---- MapPoint::ComputeDistinctiveDescriptors side figure: groups of 16 consecutive descriptors of this batch as map points
+    nsets = min(frames_per_gpu, 512) * (cap // 16)
+    d_off = torch.arange(0, 16 * nsets + 1, 16, dtype=torch.int32, device=dev)
+    d_idx = torch.zeros(nsets, dtype=torch.int32, device=dev)
+    d_med = torch.zeros(nsets, dtype=torch.int32, device=dev)
+    flat = desc.reshape(-1, 32)
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        ex.distinctive_batch(flat, d_off, d_idx, d_med, device=True, stream=stream.cuda_stream)
+        q0.record(stream)
+        ex.distinctive_batch(flat, d_off, d_idx, d_med, device=True, stream=stream.cuda_stream)
+        q1.record(stream)
+    barrier()
+    distinctive_sets_per_s = world * nsets / (q0.elapsed_time(q1) * 1e-3)
+
     # ---- the one collective of the job: gather the result slabs of (a slice of) the batch on rank 0 over NCCL
     gather_ms = None
     if world > 1:
@@ -415,7 +430,8 @@ def run_ours(args):
             "stages": stages,
             "keypoints_per_frame": mean_kp,
             "hamming": {"value": pairs_per_s, "unit": "pairs/s", "pairs_per_frame_pair": pairs / max(npairs, 1),
-                        "frame_pairs_per_gpu": npairs, "ms": float(tm.item())},
+                        "frame_pairs_per_gpu": npairs, "ms": float(tm.item()),
+                        "distinctive_sets_per_s": distinctive_sets_per_s, "distinctive_set_size": 16},
             "gather_ms": gather_ms,
         }
         # single-frame synchronous latency of the reference-facing call (sdorb_extract: host image in, results on the host),

@@ -196,6 +196,17 @@ class ORBdistance {
     if (A.rows && B.rows)
       Check(sdorb_hamming_matrix(handle_, A.data, A.rows, B.data, B.rows, reinterpret_cast<uint16_t*>(out.data), SDORB_MEM_HOST, NULL));
   }
+  // MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:252-275): row of D (N x 32) with the least median distance
+  // to the other rows, first on ties; -1 for an empty matrix
+  int Distinctive(const cv::Mat& D, int* median = NULL) {
+    RequireRows(D);
+    const int32_t offsets[2] = {0, D.rows};
+    int32_t best = -1, med = 0;
+    const uint8_t dummy[32] = {0};
+    Check(sdorb_distinctive_batch(handle_, D.rows ? D.data : dummy, offsets, 1, &best, &med, SDORB_MEM_HOST, NULL));
+    if (median) *median = med;
+    return best;
+  }
   // per row of A: first index of the smallest distance in B, that distance, the second smallest, and the acceptance
   // best < th_low && best < ratio * second.  greedy = SearchByPoints' vbMatched2 rule (src/ORBmatcher.cc:1228-1270).
   void BestTwo(const cv::Mat& A, const cv::Mat& B, float ratio, int th_low, std::vector<sdorb_match>& out, bool greedy = false) {

@@ -144,6 +144,14 @@ SDORB_API int sdorb_match_greedy_batch(sdorb_handle* h, const uint8_t* descA, co
 SDORB_API int sdorb_hamming_matrix(sdorb_handle* h, const uint8_t* descA, int nA, const uint8_t* descB, int nB,
                          uint16_t* out, int mem, void* stream);
 
+/* ---- MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:225-284), batched over map points ----
+ * Set s holds the descriptors observed for one map point: rows [offsets[s], offsets[s+1]) of desc (32 bytes each, at most
+ * 65535 rows per set).  best_idx[s] = row (relative to the set) with the least median DescriptorDistance to the set,
+ * the first on ties, exactly as the reference picks it (median = element (size_t)(0.5*(N-1)) of the sorted row,
+ * src/MapPoint.cc:266-274); -1 for an empty set.  best_median (may be NULL) receives that median.  mem / stream as above. */
+SDORB_API int sdorb_distinctive_batch(sdorb_handle* h, const uint8_t* desc, const int32_t* offsets, int nsets,
+                            int32_t* best_idx, int32_t* best_median, int mem, void* stream);
+
 /* ---- host helpers (pure CPU table arithmetic, usable without a CUDA device) ---- */
 /* BORDER_REFLECT_101 margin around a level (src/ORBextractor.cc:692-696), used by the C++ shim. */
 SDORB_API void sdorb_fill_border_reflect101(uint8_t* level_origin, int width, int height, size_t stride, int border);

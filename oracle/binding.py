@@ -104,6 +104,9 @@ def lib(path=None):
         L.orc_match_greedy.argtypes = [vp, i, vp, i, f, i, vp]
         L.orc_match_many.argtypes = [vp, vp, vp, vp, i, i, i, f, i, i, vp]
         L.orc_hamming_matrix.argtypes = [vp, i, vp, i, vp]
+        L.orc_distinctive.argtypes = [vp, i, C.POINTER(i)]
+        L.orc_distinctive.restype = i
+        L.orc_distinctive_many.argtypes = [vp, vp, i, i, vp, vp]
     return _lib
 
 
@@ -285,3 +288,13 @@ def hamming_matrix(A, B):
     out = np.zeros((len(A), len(B)), np.uint16)
     lib().orc_hamming_matrix(_p(A), len(A), _p(B), len(B), _p(out))
     return out
+
+
+def distinctive_many(desc, offsets, nthreads=1):
+    """MapPoint::ComputeDistinctiveDescriptors for sets given as rows [offsets[s], offsets[s+1]) of desc."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    offsets = np.ascontiguousarray(offsets, np.int32)
+    n = len(offsets) - 1
+    best, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lib().orc_distinctive_many(_p(desc), _p(offsets), n, nthreads, _p(best), _p(med))
+    return best, med

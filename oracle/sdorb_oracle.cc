@@ -905,6 +905,45 @@ void orc_match_many(const uint8_t* A, const int32_t* nA, const uint8_t* B, const
                 out + (size_t)p * strideA_rows, false);
   });
 }
+// MapPoint::ComputeDistinctiveDescriptors, /root/reference/src/MapPoint.cc:252-275: all pairwise distances of the N
+// observed descriptors (float matrix), per row std::sort and the element at index 0.5*(N-1) as median, the FIRST row
+// with the smallest median wins.
+int orc_distinctive(const uint8_t* desc, int n, int* best_median) {
+  if (n <= 0) {
+    if (best_median) *best_median = INT_MAX;
+    return -1;
+  }
+  std::vector<float> D((size_t)n * n);
+  for (int i = 0; i < n; i++) {
+    D[(size_t)i * n + i] = 0;
+    for (int j = i + 1; j < n; j++) {
+      const int dij = descriptor_distance(desc + (size_t)i * 32, desc + (size_t)j * 32);
+      D[(size_t)i * n + j] = (float)dij;
+      D[(size_t)j * n + i] = (float)dij;
+    }
+  }
+  int BestMedian = INT_MAX, BestIdx = 0;
+  for (int i = 0; i < n; i++) {
+    std::vector<int> vDists(D.begin() + (size_t)i * n, D.begin() + (size_t)(i + 1) * n);
+    std::sort(vDists.begin(), vDists.end());
+    const int median = vDists[(size_t)(0.5 * (n - 1))];
+    if (median < BestMedian) {
+      BestMedian = median;
+      BestIdx = i;
+    }
+  }
+  if (best_median) *best_median = BestMedian;
+  return BestIdx;
+}
+void orc_distinctive_many(const uint8_t* desc, const int32_t* offsets, int nsets, int nthreads, int32_t* best_idx,
+                          int32_t* best_median) {
+  parallel_for(nsets, nthreads, [&](int s) {
+    int med = 0;
+    best_idx[s] = orc_distinctive(desc + (size_t)offsets[s] * 32, offsets[s + 1] - offsets[s], &med);
+    if (best_median) best_median[s] = med;
+  });
+}
+
 void orc_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out) {
   for (int i = 0; i < nA; i++)
     for (int j = 0; j < nB; j++) out[(size_t)i * nB + j] = (uint16_t)descriptor_distance(A + (size_t)i * 32, B + (size_t)j * 32);

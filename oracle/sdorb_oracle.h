@@ -119,6 +119,12 @@ void orc_match_greedy(const uint8_t* descA, int nA, const uint8_t* descB, int nB
 void orc_match_many(const uint8_t* descA, const int32_t* nA, const uint8_t* descB, const int32_t* nB, int npairs,
                     int strideA_rows, int strideB_rows, float ratio, int th_low, int nthreads, orc_match* out);
 void orc_hamming_matrix(const uint8_t* descA, int nA, const uint8_t* descB, int nB, uint16_t* out);
+/* MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:252-275): index of the descriptor with the least median
+ * distance to the others (first on ties), -1 for an empty set; the median itself through *best_median. */
+int orc_distinctive(const uint8_t* desc, int n, int* best_median);
+/* sets are rows [offsets[s], offsets[s+1]) of desc */
+void orc_distinctive_many(const uint8_t* desc, const int32_t* offsets, int nsets, int nthreads, int32_t* best_idx,
+                          int32_t* best_median);
 
 #ifdef __cplusplus
 }

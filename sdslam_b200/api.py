@@ -68,6 +68,7 @@ def lib():
     L.sdorb_match_batch.argtypes = [vp, vp, vp, i, vp, vp, i, i, f, i, vp, i, vp]
     L.sdorb_match_greedy_batch.argtypes = [vp, vp, vp, i, vp, vp, i, i, f, i, vp, i, vp]
     L.sdorb_hamming_matrix.argtypes = [vp, vp, i, vp, i, vp, i, vp]
+    L.sdorb_distinctive_batch.argtypes = [vp, vp, vp, i, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
     L.sdorb_fill_border_reflect101.restype = None
     L.sdorb_host_tables.argtypes = [i, f, i] + [vp] * 6
@@ -259,6 +260,21 @@ class ORBextractor:
         out = np.zeros((len(A), len(B)), np.uint16)
         self._check(lib().sdorb_hamming_matrix(self._h, _ptr(A), len(A), _ptr(B), len(B), _ptr(out), MEM_HOST, None))
         return out
+
+    def distinctive_batch(self, desc, offsets, best_idx=None, best_median=None, device=False, stream=None):
+        """MapPoint::ComputeDistinctiveDescriptors (src/MapPoint.cc:225-284) for many map points at once: set s = rows
+        [offsets[s], offsets[s+1]) of desc.  Returns (best_idx, best_median) per set."""
+        nsets = len(offsets) - 1
+        if not device:
+            desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+            offsets = np.ascontiguousarray(offsets, np.int32)
+            best_idx, best_median = np.zeros(nsets, np.int32), np.zeros(nsets, np.int32)
+        elif stream is None:
+            import torch
+            stream = torch.cuda.current_stream(desc.device).cuda_stream
+        self._check(lib().sdorb_distinctive_batch(self._h, _ptr(desc), _ptr(offsets), nsets, _ptr(best_idx), _ptr(best_median),
+                                                   MEM_DEVICE if device else MEM_HOST, C.c_void_p(stream) if stream else None))
+        return best_idx, best_median
 
     # ---- instrumentation
     def set_profiling(self, on):

@@ -50,6 +50,9 @@ void launch_match(const uint8_t* A, const int32_t* nA, int strideA, const uint8_
 void launch_match_greedy(const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* B, const int32_t* nB,
                          int strideB, int npairs, float ratio, int th_low, void* out, cudaStream_t s);
 void launch_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out, cudaStream_t s);
+// MapPoint::ComputeDistinctiveDescriptors for nsets descriptor sets (rows [offsets[s], offsets[s+1]) of desc).
+void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int nsets, int32_t* best_idx, int32_t* best_median,
+                        cudaStream_t s);
 
 size_t select_smem_bytes(const FrameGeom& g);
 int configure_kernels();  // one-time cudaFuncSetAttribute calls; returns cudaError_t as int

@@ -152,6 +152,62 @@ __global__ void __launch_bounds__(256) hamming_matrix_kernel(const uint8_t* __re
   out[(int64_t)i * nB + j] = (uint16_t)hamming256(q, b[0], b[1]);
 }
 
+// ---- MapPoint::ComputeDistinctiveDescriptors (/root/reference/src/MapPoint.cc:252-275), batched over map points:
+// all pairwise DescriptorDistance values of a set of N observed descriptors, per row the median = element
+// (size_t)(0.5 * (N - 1)) of the sorted row, the FIRST row with the smallest median wins.  One CTA per set, one thread
+// per row: the row's distances go into a 257-bin histogram in shared memory (distances are 0..256), the median is the
+// bin where the running count passes the rank -- a counting sort, no matrix, any N.
+constexpr int D_THREADS = 64;
+
+__global__ void __launch_bounds__(D_THREADS) distinctive_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ offsets,
+                                                                int32_t* __restrict__ best_idx, int32_t* __restrict__ best_median) {
+  __shared__ uint16_t s_hist[D_THREADS][258];  // pitch 258 halfwords = 129 words: threads start in different banks
+  __shared__ int s_best[D_THREADS / 32];
+  const int set = blockIdx.x, tid = threadIdx.x;
+  const int first = offsets[set], n = offsets[set + 1] - first;
+  if (n <= 0) {
+    if (tid == 0) {
+      best_idx[set] = -1;
+      if (best_median) best_median[set] = 0x7fffffff;
+    }
+    return;
+  }
+  const uint4* rows = reinterpret_cast<const uint4*>(desc + (int64_t)first * 32);
+  const int rank = (int)(0.5 * (n - 1));
+  int best = 0x7fffffff;  // median << 16 | row: the smallest packed value is the first row with the smallest median
+  for (int i = tid; i < n; i += D_THREADS) {  // n <= 65535 rows per set
+    uint16_t* hist = s_hist[tid];
+    for (int b = 0; b < 257; ++b) hist[b] = 0;
+    const uint4 lo = __ldg(rows + 2 * i), hi = __ldg(rows + 2 * i + 1);
+    const uint32_t q[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+    for (int j = 0; j < n; ++j) hist[hamming256(q, __ldg(rows + 2 * j), __ldg(rows + 2 * j + 1))] += 1;  // D[i][i] = 0 included
+    int acc = 0, median = 0;
+    for (int b = 0; b < 257; ++b) {
+      acc += hist[b];
+      if (acc > rank) {
+        median = b;
+        break;
+      }
+    }
+    best = min(best, (median << 16) | i);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((tid & 31) == 0) s_best[tid >> 5] = best;
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < D_THREADS / 32; ++w) best = min(best, s_best[w]);
+    best_idx[set] = best & 0xFFFF;
+    if (best_median) best_median[set] = best >> 16;
+  }
+}
+
+void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int nsets, int32_t* best_idx, int32_t* best_median,
+                        cudaStream_t s) {
+  if (nsets <= 0) return;
+  distinctive_kernel<<<nsets, D_THREADS, 0, s>>>(desc, offsets, best_idx, best_median);
+}
+
 void launch_match(const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* B, const int32_t* nB, int strideB,
                   int npairs, float ratio, int th_low, void* out, cudaStream_t s) {
   if (npairs <= 0 || strideA <= 0) return;

@@ -736,6 +736,52 @@ int sdorb_hamming_matrix(sdorb_handle* h, const uint8_t* A, int nA, const uint8_
   return rc;
 }
 
+int sdorb_distinctive_batch(sdorb_handle* h, const uint8_t* desc, const int32_t* offsets, int nsets, int32_t* best_idx,
+                            int32_t* best_median, int mem, void* stream) {
+  if (!h || nsets < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nsets == 0) return SDORB_OK;
+  if (!desc || !offsets || !best_idx) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  if (mem == SDORB_MEM_DEVICE) {
+    if ((uintptr_t)desc % 16) return SDORB_ERR_BAD_ARG;
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_distinctive(desc, offsets, nsets, best_idx, best_median, s);
+    st.launched();
+    CU(cudaGetLastError());
+    return SDORB_OK;
+  }
+  for (int i = 0; i < nsets; ++i)
+    if (offsets[i] < 0 || offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 65535) return SDORB_ERR_BAD_ARG;
+  const size_t rows = (size_t)offsets[nsets], bD = std::max<size_t>(rows * 32, 32), bO = sizeof(int32_t) * ((size_t)nsets + 1),
+               bR = sizeof(int32_t) * (size_t)nsets;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t need = up(bD) + up(bO) + 2 * up(bR);
+  if (need > h->match_buf_bytes) {
+    if (h->d_match_buf) cudaFree(h->d_match_buf);
+    h->d_match_buf = nullptr;
+    h->match_buf_bytes = 0;
+    CU(cudaMalloc(&h->d_match_buf, need));
+    h->match_buf_bytes = need;
+  }
+  uint8_t* pD = (uint8_t*)h->d_match_buf;
+  int32_t* pO = (int32_t*)(pD + up(bD));
+  int32_t* pI = (int32_t*)((uint8_t*)pO + up(bO));
+  int32_t* pM = (int32_t*)((uint8_t*)pI + up(bR));
+  if (rows) CU(cudaMemcpyAsync(pD, desc, rows * 32, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(pO, offsets, bO, cudaMemcpyHostToDevice, s));
+  {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_distinctive(pD, pO, nsets, pI, pM, s);
+    st.launched();
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(best_idx, pI, bR, cudaMemcpyDeviceToHost, s));
+  if (best_median) CU(cudaMemcpyAsync(best_median, pM, bR, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SDORB_OK;
+}
+
 int sdorb_set_profiling(sdorb_handle* h, int enabled) {
   if (!h) return SDORB_ERR_BAD_ARG;
   h->profiling = enabled != 0;

@@ -445,6 +445,37 @@ def test_match_full_size_properties(ex_c1):
     assert np.array_equal(self_m["best_idx"], dself.argmin(axis=1))
 
 
+def test_distinctive_descriptors_equal_oracle(ex_c1):
+    """MapPoint::ComputeDistinctiveDescriptors batched (src/MapPoint.cc:225-284): ragged sets incl. empty, single,
+    duplicates, a set larger than one CTA's threads, and real ORB descriptors."""
+    rng = np.random.default_rng(31)
+    sizes = [1, 2, 3, 0, 7, 16, 64, 65, 130, 300, 5, 0, 33]
+    sets = []
+    for n in sizes:
+        d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        if n >= 5:
+            d[1:n // 2] = d[0] ^ (rng.integers(0, 256, (n // 2 - 1, 32), dtype=np.uint8) & 0x09)
+            d[n - 1] = d[2]
+        sets.append(d)
+    k, dd, c = ex_c1.extract_batch_host(synth.frames(1, 640, 480, start=400))
+    sets.append(dd[0, :200].copy())
+    sizes.append(200)
+    desc = np.concatenate(sets)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    gi, gm = ex_c1.distinctive_batch(desc, offsets)
+    oi, om = orc.distinctive_many(desc, offsets)
+    assert np.array_equal(gi, oi) and np.array_equal(gm, om)
+    assert gi[3] == -1 and gi[0] == 0 and gm[0] == 0
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    td, to = torch.from_numpy(desc).to(dev), torch.from_numpy(offsets).to(dev)
+    ti = torch.zeros(len(sizes), dtype=torch.int32, device=dev)
+    tm = torch.zeros(len(sizes), dtype=torch.int32, device=dev)
+    ex_c1.distinctive_batch(td, to, ti, tm, device=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(ti.cpu().numpy(), oi) and np.array_equal(tm.cpu().numpy(), om)
+
+
 def test_kernel_launch_accounting(ex_c1):
     before = ex_c1.kernel_launches()
     ex_c1(synth.smooth_noise(0), want_pyramid=False)

@@ -229,3 +229,31 @@ def test_match_best2_rule():
     assert np.array_equal(m["accepted"].astype(bool), acc)
     empty = orc.match_best2(A, np.zeros((0, 32), np.uint8))
     assert (empty["best_idx"] == -1).all() and (empty["best_dist"] == 256).all() and (empty["second_dist"] == 256).all()
+
+
+# ------------------------------------------------------------------ MapPoint::ComputeDistinctiveDescriptors
+def _distinctive_numpy(d):
+    """Independent restatement of /root/reference/src/MapPoint.cc:252-275 with numpy bit counting."""
+    n = len(d)
+    if n == 0:
+        return -1, 2 ** 31 - 1
+    dist = np.unpackbits(d[:, None, :] ^ d[None, :, :], axis=2).sum(axis=2)
+    med = np.sort(dist, axis=1)[:, int(0.5 * (n - 1))]
+    return int(np.argmin(med)), int(med.min())
+
+
+def test_distinctive_descriptor_rule():
+    rng = np.random.default_rng(12)
+    sizes = [1, 2, 3, 4, 5, 8, 17, 40, 0, 100, 2]
+    sets = []
+    for n in sizes:
+        d = rng.integers(0, 256, (n, 32), dtype=np.uint8)
+        if n >= 5:  # a cluster of near-duplicates plus outliers, and exact duplicates (first index must win)
+            d[1:n // 2] = d[0] ^ (rng.integers(0, 256, (n // 2 - 1, 32), dtype=np.uint8) & 0x11)
+            d[n - 1] = d[1]
+        sets.append(d)
+    offsets = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    best, med = orc.distinctive_many(np.concatenate(sets), offsets, nthreads=2)
+    for s, d in enumerate(sets):
+        bi, bm = _distinctive_numpy(d)
+        assert (int(best[s]), int(med[s])) == (bi, bm), "set %d (n=%d)" % (s, len(d))
