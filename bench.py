@@ -252,6 +252,19 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = None
+    if world > 1:
+        # keep this rank's threads -- and so its pinned host batch (first touch) -- on the CPUs next to its GPU: with
+        # 8 ranks the end-to-end leg is bound by host memory / PCIe root traffic, not by the GPUs
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hdl = pynvml.nvmlDeviceGetHandleByIndex(local)
+            pynvml.nvmlDeviceSetCpuAffinity(hdl)
+            numa = sorted(os.sched_getaffinity(0))
+            numa = "%d cpus [%d..%d]" % (len(numa), numa[0], numa[-1])
+        except Exception as e:  # not fatal: affinity is an optimisation
+            numa = "unset (%s)" % type(e).__name__
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
@@ -433,6 +446,7 @@ def run_ours(args):
                         "frame_pairs_per_gpu": npairs, "ms": float(tm.item()),
                         "distinctive_sets_per_s": distinctive_sets_per_s, "distinctive_set_size": 16},
             "gather_ms": gather_ms,
+            "host_affinity": numa,
         }
         # single-frame synchronous latency of the reference-facing call (sdorb_extract: host image in, results on the host),
         # the way Frame.cc:195 uses the extractor -- outside every timed region above
