@@ -152,6 +152,29 @@ SDORB_API int sdorb_hamming_matrix(sdorb_handle* h, const uint8_t* descA, int nA
 SDORB_API int sdorb_distinctive_batch(sdorb_handle* h, const uint8_t* desc, const int32_t* offsets, int nsets,
                             int32_t* best_idx, int32_t* best_median, int mem, void* stream);
 
+/* ---- Frame post-processing right after the extractor (src/Frame.cc), batched over frames ----
+ * Keypoints are [nframes][capacity] sdorb_keypoint with counts[nframes], as the extractor leaves them.
+ *
+ * sdorb_assign_grid_batch = Frame::AssignFeaturesToGrid + PosInGrid (src/Frame.cc:179-192, 323-332) on the UNDISTORTED
+ * keypoints (identical to the extractor's when the camera has no distortion, src/Frame.cc:336-339): grid 64 x 48
+ * (FRAME_GRID_COLS / ROWS, src/Frame.h:37-38), cell of a keypoint = (round((x - min_x) * inv_w), round((y - min_y) * inv_h)),
+ * keypoints outside the grid are dropped.  Output in CSR form per frame: cell c = posX * 48 + posY owns
+ * indices[cell_start[c] .. cell_start[c + 1]), ascending (the reference's push_back order); cell_start has 64 * 48 + 1
+ * entries per frame, indices `capacity` entries per frame.  min_x / min_y / inv_w / inv_h are mnMinX, mnMinY,
+ * mfGridElementWidthInv, mfGridElementHeightInv (src/Frame.cc:106-107, 368-397). */
+#define SDORB_GRID_COLS 64
+#define SDORB_GRID_ROWS 48
+SDORB_API int sdorb_assign_grid_batch(sdorb_handle* h, const sdorb_keypoint* keypoints_un, const int32_t* counts, int nframes,
+                            int capacity, float min_x, float min_y, float inv_w, float inv_h, int32_t* cell_start,
+                            int32_t* indices, int mem, void* stream);
+/* sdorb_stereo_from_rgbd_batch = Frame::ComputeStereoFromRGBD (src/Frame.cc:399-417): d = depth(v, u) at the truncated
+ * keypoint position; d > 0: z = d and u_right = x_undistorted - mbf / d, else both -1.  depth: float32 images, row /
+ * frame strides in ELEMENTS; u_right, z: [nframes][capacity] (entries beyond counts[f] are set to -1). */
+SDORB_API int sdorb_stereo_from_rgbd_batch(sdorb_handle* h, const sdorb_keypoint* keypoints, const sdorb_keypoint* keypoints_un,
+                                 const int32_t* counts, int nframes, int capacity, const float* depth, int width, int height,
+                                 size_t depth_row_stride, size_t depth_frame_stride, float mbf, float* u_right, float* z,
+                                 int mem, void* stream);
+
 /* ---- host helpers (pure CPU table arithmetic, usable without a CUDA device) ---- */
 /* BORDER_REFLECT_101 margin around a level (src/ORBextractor.cc:692-696), used by the C++ shim. */
 SDORB_API void sdorb_fill_border_reflect101(uint8_t* level_origin, int width, int height, size_t stride, int border);

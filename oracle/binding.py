@@ -104,6 +104,8 @@ def lib(path=None):
         L.orc_match_greedy.argtypes = [vp, i, vp, i, f, i, vp]
         L.orc_match_many.argtypes = [vp, vp, vp, vp, i, i, i, f, i, i, vp]
         L.orc_hamming_matrix.argtypes = [vp, i, vp, i, vp]
+        L.orc_assign_grid.argtypes = [vp, i, f, f, f, f, vp, vp]
+        L.orc_stereo_from_rgbd.argtypes = [vp, vp, i, vp, i, f, vp, vp]
         L.orc_distinctive.argtypes = [vp, i, C.POINTER(i)]
         L.orc_distinctive.restype = i
         L.orc_distinctive_many.argtypes = [vp, vp, i, i, vp, vp]
@@ -298,3 +300,20 @@ def distinctive_many(desc, offsets, nthreads=1):
     best, med = np.zeros(n, np.int32), np.zeros(n, np.int32)
     lib().orc_distinctive_many(_p(desc), _p(offsets), n, nthreads, _p(best), _p(med))
     return best, med
+
+
+def assign_grid(kps_un, min_x, min_y, inv_w, inv_h):
+    """Frame::AssignFeaturesToGrid: returns (cell_start[64*48+1], indices[n_in_grid])."""
+    k = np.ascontiguousarray(kps_un, KP_DTYPE)
+    cs = np.zeros(64 * 48 + 1, np.int32)
+    idx = np.zeros(max(len(k), 1), np.int32)
+    lib().orc_assign_grid(_p(k), len(k), min_x, min_y, inv_w, inv_h, _p(cs), _p(idx))
+    return cs, idx[:cs[-1]]
+
+
+def stereo_from_rgbd(kps, kps_un, depth, mbf):
+    k, ku = np.ascontiguousarray(kps, KP_DTYPE), np.ascontiguousarray(kps_un, KP_DTYPE)
+    depth = np.ascontiguousarray(depth, np.float32)
+    ur, z = np.zeros(len(k), np.float32), np.zeros(len(k), np.float32)
+    lib().orc_stereo_from_rgbd(_p(k), _p(ku), len(k), _p(depth), depth.shape[1], mbf, _p(ur), _p(z))
+    return ur, z

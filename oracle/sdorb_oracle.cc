@@ -944,6 +944,41 @@ void orc_distinctive_many(const uint8_t* desc, const int32_t* offsets, int nsets
   });
 }
 
+// Frame::AssignFeaturesToGrid + PosInGrid, /root/reference/src/Frame.cc:179-192, 323-332 (FRAME_GRID_COLS 64, FRAME_GRID_ROWS 48,
+// src/Frame.h:37-38).  mGrid[x][y] is returned in CSR form: cell x * 48 + y owns indices[cell_start[c] .. cell_start[c+1]).
+void orc_assign_grid(const orc_keypoint* kps_un, int n, float mnMinX, float mnMinY, float mfGridElementWidthInv,
+                     float mfGridElementHeightInv, int32_t* cell_start, int32_t* indices) {
+  const int COLS = 64, ROWS = 48;
+  std::vector<std::vector<int>> mGrid((size_t)COLS * ROWS);
+  for (int i = 0; i < n; i++) {
+    const orc_keypoint& kp = kps_un[i];
+    const int posX = (int)std::round((kp.x - mnMinX) * mfGridElementWidthInv);
+    const int posY = (int)std::round((kp.y - mnMinY) * mfGridElementHeightInv);
+    if (posX < 0 || posX >= COLS || posY < 0 || posY >= ROWS) continue;
+    mGrid[(size_t)posX * ROWS + posY].push_back(i);
+  }
+  int acc = 0;
+  for (int c = 0; c < COLS * ROWS; c++) {
+    cell_start[c] = acc;
+    for (int i : mGrid[c]) indices[acc++] = i;
+  }
+  cell_start[COLS * ROWS] = acc;
+}
+// Frame::ComputeStereoFromRGBD, src/Frame.cc:399-417
+void orc_stereo_from_rgbd(const orc_keypoint* kps, const orc_keypoint* kps_un, int n, const float* depth, int width, float mbf,
+                          float* u_right, float* z) {
+  for (int i = 0; i < n; i++) {
+    u_right[i] = -1;
+    z[i] = -1;
+    const float v = kps[i].y, u = kps[i].x;
+    const float d = depth[(size_t)(int)v * width + (int)u];  // Mat::at<float>(int, int) with float arguments
+    if (d > 0) {
+      z[i] = d;
+      u_right[i] = kps_un[i].x - mbf / d;
+    }
+  }
+}
+
 void orc_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out) {
   for (int i = 0; i < nA; i++)
     for (int j = 0; j < nB; j++) out[(size_t)i * nB + j] = (uint16_t)descriptor_distance(A + (size_t)i * 32, B + (size_t)j * 32);

@@ -126,6 +126,14 @@ int orc_distinctive(const uint8_t* desc, int n, int* best_median);
 void orc_distinctive_many(const uint8_t* desc, const int32_t* offsets, int nsets, int nthreads, int32_t* best_idx,
                           int32_t* best_median);
 
+/* ---- Frame post-processing restatement (src/Frame.cc) ---- */
+/* AssignFeaturesToGrid + PosInGrid (:179-192, :323-332): cell_start has 64*48+1 entries, indices n entries. */
+void orc_assign_grid(const orc_keypoint* kps_un, int n, float mnMinX, float mnMinY, float mfGridElementWidthInv,
+                     float mfGridElementHeightInv, int32_t* cell_start, int32_t* indices);
+/* ComputeStereoFromRGBD (:399-417): depth is a tightly packed float image of the given width. */
+void orc_stereo_from_rgbd(const orc_keypoint* kps, const orc_keypoint* kps_un, int n, const float* depth, int width, float mbf,
+                          float* u_right, float* z);
+
 #ifdef __cplusplus
 }
 #endif

@@ -69,6 +69,8 @@ def lib():
     L.sdorb_match_greedy_batch.argtypes = [vp, vp, vp, i, vp, vp, i, i, f, i, vp, i, vp]
     L.sdorb_hamming_matrix.argtypes = [vp, vp, i, vp, i, vp, i, vp]
     L.sdorb_distinctive_batch.argtypes = [vp, vp, vp, i, vp, vp, i, vp]
+    L.sdorb_assign_grid_batch.argtypes = [vp, vp, vp, i, i, f, f, f, f, vp, vp, i, vp]
+    L.sdorb_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i, i, vp, i, i, sz, sz, f, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
     L.sdorb_fill_border_reflect101.restype = None
     L.sdorb_host_tables.argtypes = [i, f, i] + [vp] * 6
@@ -275,6 +277,32 @@ class ORBextractor:
         self._check(lib().sdorb_distinctive_batch(self._h, _ptr(desc), _ptr(offsets), nsets, _ptr(best_idx), _ptr(best_median),
                                                    MEM_DEVICE if device else MEM_HOST, C.c_void_p(stream) if stream else None))
         return best_idx, best_median
+
+    # ---- Frame post-processing (src/Frame.cc:179-192, 323-332, 399-417)
+    GRID_COLS, GRID_ROWS = 64, 48
+
+    def assign_grid_batch(self, keypoints_un, counts, min_x, min_y, inv_w, inv_h):
+        """Frame::AssignFeaturesToGrid for a batch (host arrays): returns (cell_start[F, 64*48+1], indices[F, cap])."""
+        kps = np.ascontiguousarray(keypoints_un)
+        nf, cap = kps.shape[0], kps.shape[1]
+        counts = np.ascontiguousarray(counts, np.int32)
+        cs = np.zeros((nf, self.GRID_COLS * self.GRID_ROWS + 1), np.int32)
+        idx = np.zeros((nf, cap), np.int32)
+        self._check(lib().sdorb_assign_grid_batch(self._h, _ptr(kps), _ptr(counts), nf, cap, min_x, min_y, inv_w, inv_h, _ptr(cs),
+                                                   _ptr(idx), MEM_HOST, None))
+        return cs, idx
+
+    def stereo_from_rgbd_batch(self, keypoints, keypoints_un, counts, depth, mbf):
+        """Frame::ComputeStereoFromRGBD for a batch (host arrays, depth float32 [F,H,W]): returns (u_right, z) [F, cap]."""
+        kps, kun = np.ascontiguousarray(keypoints), np.ascontiguousarray(keypoints_un)
+        depth = np.ascontiguousarray(depth, np.float32)
+        nf, cap = kps.shape[0], kps.shape[1]
+        counts = np.ascontiguousarray(counts, np.int32)
+        ur, z = np.zeros((nf, cap), np.float32), np.zeros((nf, cap), np.float32)
+        self._check(lib().sdorb_stereo_from_rgbd_batch(self._h, _ptr(kps), _ptr(kun), _ptr(counts), nf, cap, _ptr(depth), depth.shape[2],
+                                                        depth.shape[1], depth.shape[2], depth.shape[1] * depth.shape[2], mbf,
+                                                        _ptr(ur), _ptr(z), MEM_HOST, None))
+        return ur, z
 
     # ---- instrumentation
     def set_profiling(self, on):

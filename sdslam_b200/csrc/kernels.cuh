@@ -54,6 +54,14 @@ void launch_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, u
 void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int nsets, int32_t* best_idx, int32_t* best_median,
                         cudaStream_t s);
 
+// Frame::AssignFeaturesToGrid / PosInGrid and Frame::ComputeStereoFromRGBD (kernels_frame.cu); device pointers.
+void launch_assign_grid(const void* kps, const int32_t* counts, int nframes, int capacity, float min_x, float min_y, float inv_w,
+                        float inv_h, int32_t* cell_start, int32_t* indices, cudaStream_t s);
+void launch_stereo_rgbd(const void* kps, const void* kps_un, const int32_t* counts, int nframes, int capacity, const float* depth,
+                        int width, int height, int64_t row_stride, int64_t frame_stride, float mbf, float* u_right, float* z,
+                        cudaStream_t s);
+int configure_frame_kernels();
+
 size_t select_smem_bytes(const FrameGeom& g);
 int configure_kernels();  // one-time cudaFuncSetAttribute calls; returns cudaError_t as int
 

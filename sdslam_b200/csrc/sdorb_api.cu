@@ -343,7 +343,7 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (cudaMemcpy(h->d_umax, h->tables.umax, sizeof(int) * 16, cudaMemcpyHostToDevice) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaMalloc(&h->d_error, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
   if (cudaMemset(h->d_error, 0, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_CUDA);
-  if (configure_kernels() != 0) return fail(SDORB_ERR_CUDA);
+  if (configure_kernels() != 0 || configure_frame_kernels() != 0) return fail(SDORB_ERR_CUDA);
   *out = h;
   return SDORB_OK;
 }
@@ -778,6 +778,109 @@ int sdorb_distinctive_batch(sdorb_handle* h, const uint8_t* desc, const int32_t*
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(best_idx, pI, bR, cudaMemcpyDeviceToHost, s));
   if (best_median) CU(cudaMemcpyAsync(best_median, pM, bR, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SDORB_OK;
+}
+
+namespace {
+// scratch for the host-memory forms of the small batched entry points: one growing device buffer, carved by the caller
+int ensure_match_buf(sdorb_handle* h, size_t need) {
+  if (need > h->match_buf_bytes) {
+    if (h->d_match_buf) cudaFree(h->d_match_buf);
+    h->d_match_buf = nullptr;
+    h->match_buf_bytes = 0;
+    CU(cudaMalloc(&h->d_match_buf, need));
+    h->match_buf_bytes = need;
+  }
+  return SDORB_OK;
+}
+size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+}  // namespace
+
+int sdorb_assign_grid_batch(sdorb_handle* h, const sdorb_keypoint* kps, const int32_t* counts, int nframes, int capacity,
+                            float min_x, float min_y, float inv_w, float inv_h, int32_t* cell_start, int32_t* indices, int mem,
+                            void* stream) {
+  if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nframes == 0) return SDORB_OK;
+  if (!kps || !counts || !cell_start || !indices || capacity <= 0 || capacity > 65535) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  const size_t ncs = (size_t)SDORB_GRID_COLS * SDORB_GRID_ROWS + 1;
+  if (mem == SDORB_MEM_DEVICE) {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_assign_grid(kps, counts, nframes, capacity, min_x, min_y, inv_w, inv_h, cell_start, indices, s);
+    st.launched();
+    CU(cudaGetLastError());
+    return SDORB_OK;
+  }
+  const size_t bK = sizeof(sdorb_keypoint) * (size_t)nframes * capacity, bC = sizeof(int32_t) * (size_t)nframes,
+               bS = sizeof(int32_t) * ncs * nframes, bI = sizeof(int32_t) * (size_t)nframes * capacity;
+  int rc = ensure_match_buf(h, up256(bK) + up256(bC) + up256(bS) + up256(bI));
+  if (rc) return rc;
+  uint8_t* base = (uint8_t*)h->d_match_buf;
+  sdorb_keypoint* dK = (sdorb_keypoint*)base;
+  int32_t* dC = (int32_t*)(base + up256(bK));
+  int32_t* dS = (int32_t*)((uint8_t*)dC + up256(bC));
+  int32_t* dI = (int32_t*)((uint8_t*)dS + up256(bS));
+  CU(cudaMemcpyAsync(dK, kps, bK, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(dC, counts, bC, cudaMemcpyHostToDevice, s));
+  CU(cudaMemsetAsync(dI, 0xFF, bI, s));  // unused tail of every frame's index list reads -1
+  {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_assign_grid(dK, dC, nframes, capacity, min_x, min_y, inv_w, inv_h, dS, dI, s);
+    st.launched();
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(cell_start, dS, bS, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(indices, dI, bI, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SDORB_OK;
+}
+
+int sdorb_stereo_from_rgbd_batch(sdorb_handle* h, const sdorb_keypoint* kps, const sdorb_keypoint* kps_un, const int32_t* counts,
+                                 int nframes, int capacity, const float* depth, int width, int height, size_t row_stride,
+                                 size_t frame_stride, float mbf, float* u_right, float* z, int mem, void* stream) {
+  if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nframes == 0) return SDORB_OK;
+  if (!kps || !kps_un || !counts || !depth || !u_right || !z || capacity <= 0 || width <= 0 || height <= 0 ||
+      row_stride < (size_t)width || (nframes > 1 && frame_stride < row_stride * (size_t)(height - 1) + (size_t)width))
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  if (mem == SDORB_MEM_DEVICE) {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_stereo_rgbd(kps, kps_un, counts, nframes, capacity, depth, width, height, (int64_t)row_stride, (int64_t)frame_stride, mbf,
+                       u_right, z, s);
+    st.launched();
+    CU(cudaGetLastError());
+    return SDORB_OK;
+  }
+  const size_t bK = sizeof(sdorb_keypoint) * (size_t)nframes * capacity, bC = sizeof(int32_t) * (size_t)nframes,
+               bD = sizeof(float) * (size_t)nframes * width * height, bO = sizeof(float) * (size_t)nframes * capacity;
+  int rc = ensure_match_buf(h, 2 * up256(bK) + up256(bC) + up256(bD) + 2 * up256(bO));
+  if (rc) return rc;
+  uint8_t* base = (uint8_t*)h->d_match_buf;
+  sdorb_keypoint* dK = (sdorb_keypoint*)base;
+  sdorb_keypoint* dU = (sdorb_keypoint*)(base + up256(bK));
+  int32_t* dC = (int32_t*)((uint8_t*)dU + up256(bK));
+  float* dD = (float*)((uint8_t*)dC + up256(bC));
+  float* dR = (float*)((uint8_t*)dD + up256(bD));
+  float* dZ = (float*)((uint8_t*)dR + up256(bO));
+  CU(cudaMemcpyAsync(dK, kps, bK, cudaMemcpyHostToDevice, s));
+  if (kps_un != kps) CU(cudaMemcpyAsync(dU, kps_un, bK, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(dC, counts, bC, cudaMemcpyHostToDevice, s));
+  for (int f = 0; f < nframes; ++f)  // repack to tight rows
+    CU(cudaMemcpy2DAsync(dD + (size_t)f * width * height, sizeof(float) * (size_t)width, depth + (size_t)f * frame_stride,
+                         sizeof(float) * row_stride, sizeof(float) * (size_t)width, height, cudaMemcpyHostToDevice, s));
+  {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_stereo_rgbd(dK, kps_un != kps ? dU : dK, dC, nframes, capacity, dD, width, height, width, (int64_t)width * height, mbf, dR,
+                       dZ, s);
+    st.launched();
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(u_right, dR, bO, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(z, dZ, bO, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
   return SDORB_OK;
 }

@@ -476,6 +476,32 @@ def test_distinctive_descriptors_equal_oracle(ex_c1):
     assert np.array_equal(ti.cpu().numpy(), oi) and np.array_equal(tm.cpu().numpy(), om)
 
 
+def test_frame_postprocessing_equals_oracle(ex_c1):
+    """Frame::AssignFeaturesToGrid / PosInGrid and ComputeStereoFromRGBD (src/Frame.cc:179-192, 323-332, 399-417) on the
+    extractor's own output (no distortion: mvKeysUn = mvKeys) plus keypoints pushed outside the image bounds."""
+    imgs = synth.frames(3, 640, 480, start=500)
+    imgs[2] = 0  # a frame without keypoints
+    kps, desc, cnt = ex_c1.extract_batch_host(imgs)
+    kun = kps.copy()
+    kun["x"][1] += np.float32(31.3)  # as if undistortion had moved them: some leave the grid on the right
+    kun["y"][1] -= np.float32(27.6)  # ... and at the top
+    inv_w, inv_h = float(np.float32(64) / np.float32(640)), float(np.float32(48) / np.float32(480))
+    cs, idx = ex_c1.assign_grid_batch(kun, cnt, 0.0, 0.0, inv_w, inv_h)
+    for f in range(3):
+        ocs, oidx = orc.assign_grid(kun[f, :cnt[f]], 0.0, 0.0, inv_w, inv_h)
+        assert np.array_equal(cs[f], ocs), "frame %d cell_start" % f
+        assert np.array_equal(idx[f, :ocs[-1]], oidx), "frame %d indices" % f
+    assert cs[2, -1] == 0 and 0 < cs[1, -1] < cnt[1] and cs[0, -1] == cnt[0]
+    rng = np.random.default_rng(7)
+    depth = rng.uniform(-2, 9, (3, 480, 640)).astype(np.float32)
+    depth[depth < 0.3] = 0
+    ur, z = ex_c1.stereo_from_rgbd_batch(kps, kun, cnt, depth, 40.0)
+    for f in range(3):
+        our, oz = orc.stereo_from_rgbd(kps[f, :cnt[f]], kun[f, :cnt[f]], depth[f], 40.0)
+        assert ur[f, :cnt[f]].tobytes() == our.tobytes() and z[f, :cnt[f]].tobytes() == oz.tobytes()
+        assert (ur[f, cnt[f]:] == -1).all() and (z[f, cnt[f]:] == -1).all()
+
+
 def test_kernel_launch_accounting(ex_c1):
     before = ex_c1.kernel_launches()
     ex_c1(synth.smooth_noise(0), want_pyramid=False)

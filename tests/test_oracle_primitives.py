@@ -257,3 +257,45 @@ def test_distinctive_descriptor_rule():
     for s, d in enumerate(sets):
         bi, bm = _distinctive_numpy(d)
         assert (int(best[s]), int(med[s])) == (bi, bm), "set %d (n=%d)" % (s, len(d))
+
+
+# ------------------------------------------------------------------ Frame::AssignFeaturesToGrid / ComputeStereoFromRGBD
+def test_assign_grid_rule():
+    """src/Frame.cc:179-192, 323-332 against a direct Python restatement (round half away from zero, x-major cells)."""
+    import math
+    rng = np.random.default_rng(21)
+    k = np.zeros(700, orc.KP_DTYPE)
+    k["x"] = rng.uniform(-20, 660, 700).astype(np.float32)
+    k["y"] = rng.uniform(-20, 500, 700).astype(np.float32)
+    k["x"][:8] = [0, 5, 15, 634.9, 635, 639.99, 4.99999, 645]   # cell borders: 640 / 64 = 10 px per cell
+    k["y"][:8] = [0, 5, 15, 474.9, 475, 479.99, 4.99999, 100]
+    inv_w, inv_h = np.float32(64) / np.float32(640), np.float32(48) / np.float32(480)
+    cs, idx = orc.assign_grid(k, 0.0, 0.0, float(inv_w), float(inv_h))
+    grid = {}
+    for i in range(len(k)):
+        fx, fy = np.float32(k["x"][i] - np.float32(0)) * inv_w, np.float32(k["y"][i] - np.float32(0)) * inv_h
+        px = int(math.copysign(math.floor(abs(float(fx)) + 0.5), float(fx)))
+        py = int(math.copysign(math.floor(abs(float(fy)) + 0.5), float(fy)))
+        if 0 <= px < 64 and 0 <= py < 48:
+            grid.setdefault(px * 48 + py, []).append(i)
+    assert cs[-1] == sum(len(v) for v in grid.values()) == len(idx)
+    for c in range(64 * 48):
+        assert idx[cs[c]:cs[c + 1]].tolist() == grid.get(c, [])
+
+
+def test_stereo_from_rgbd_rule():
+    rng = np.random.default_rng(22)
+    depth = rng.uniform(-1, 8, (48, 64)).astype(np.float32)
+    depth[depth < 0.5] = 0
+    k = np.zeros(50, orc.KP_DTYPE)
+    k["x"] = rng.uniform(0, 63.9, 50).astype(np.float32)
+    k["y"] = rng.uniform(0, 47.9, 50).astype(np.float32)
+    ku = k.copy()
+    ku["x"] += np.float32(0.25)
+    ur, z = orc.stereo_from_rgbd(k, ku, depth, 40.0)
+    for i in range(50):
+        d = depth[int(k["y"][i]), int(k["x"][i])]
+        if d > 0:
+            assert z[i] == d and ur[i] == np.float32(ku["x"][i] - np.float32(40.0) / d)
+        else:
+            assert z[i] == -1 and ur[i] == -1
