@@ -167,6 +167,15 @@ SDORB_API int sdorb_distinctive_batch(sdorb_handle* h, const uint8_t* desc, cons
 SDORB_API int sdorb_assign_grid_batch(sdorb_handle* h, const sdorb_keypoint* keypoints_un, const int32_t* counts, int nframes,
                             int capacity, float min_x, float min_y, float inv_w, float inv_h, int32_t* cell_start,
                             int32_t* indices, int mem, void* stream);
+/* sdorb_undistort_keypoints_batch = Frame::UndistortKeyPoints (src/Frame.cc:335-366), i.e. cv::undistortPoints(pts, K, dist,
+ * noArray(), K) as OpenCV 4.13 computes it, applied to pt of every keypoint (all other fields copied).  K = {fx, fy, cx, cy}
+ * and dist = {k1, k2, p1, p2[, k3]} are the float values the reference passes (host pointers, 4 and ndist <= 12 entries);
+ * dist[0] == 0 copies the keypoints (src/Frame.cc:336-339).  out may alias keypoints. */
+SDORB_API int sdorb_undistort_keypoints_batch(sdorb_handle* h, const sdorb_keypoint* keypoints, const int32_t* counts, int nframes,
+                                    int capacity, const float* K, const float* dist, int ndist, sdorb_keypoint* out, int mem,
+                                    void* stream);
+/* Frame::ComputeImageBounds (src/Frame.cc:368-397) on the host: bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}; needs no GPU. */
+SDORB_API int sdorb_host_image_bounds(int cols, int rows, const float* K, const float* dist, int ndist, float* bounds);
 /* sdorb_stereo_from_rgbd_batch = Frame::ComputeStereoFromRGBD (src/Frame.cc:399-417): d = depth(v, u) at the truncated
  * keypoint position; d > 0: z = d and u_right = x_undistorted - mbf / d, else both -1.  depth: float32 images, row /
  * frame strides in ELEMENTS; u_right, z: [nframes][capacity] (entries beyond counts[f] are set to -1). */

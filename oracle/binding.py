@@ -106,6 +106,8 @@ def lib(path=None):
         L.orc_hamming_matrix.argtypes = [vp, i, vp, i, vp]
         L.orc_assign_grid.argtypes = [vp, i, f, f, f, f, vp, vp]
         L.orc_stereo_from_rgbd.argtypes = [vp, vp, i, vp, i, f, vp, vp]
+        L.orc_undistort_keypoints.argtypes = [vp, i, vp, vp, i, vp]
+        L.orc_image_bounds.argtypes = [i, i, vp, vp, i, vp]
         L.orc_distinctive.argtypes = [vp, i, C.POINTER(i)]
         L.orc_distinctive.restype = i
         L.orc_distinctive_many.argtypes = [vp, vp, i, i, vp, vp]
@@ -317,3 +319,21 @@ def stereo_from_rgbd(kps, kps_un, depth, mbf):
     ur, z = np.zeros(len(k), np.float32), np.zeros(len(k), np.float32)
     lib().orc_stereo_from_rgbd(_p(k), _p(ku), len(k), _p(depth), depth.shape[1], mbf, _p(ur), _p(z))
     return ur, z
+
+
+def undistort_keypoints(kps, K4, dist):
+    """Frame::UndistortKeyPoints: K4 = (fx, fy, cx, cy), dist = (k1, k2, p1, p2[, k3]) as float32."""
+    k = np.ascontiguousarray(kps, KP_DTYPE)
+    K4 = np.ascontiguousarray(K4, np.float32)
+    dist = np.ascontiguousarray(dist, np.float32)
+    out = np.zeros(len(k), KP_DTYPE)
+    lib().orc_undistort_keypoints(_p(k), len(k), _p(K4), _p(dist), len(dist), _p(out))
+    return out
+
+
+def image_bounds(cols, rows, K4, dist):
+    K4 = np.ascontiguousarray(K4, np.float32)
+    dist = np.ascontiguousarray(dist, np.float32)
+    b = np.zeros(4, np.float32)
+    lib().orc_image_bounds(cols, rows, _p(K4), _p(dist), len(dist), _p(b))
+    return b

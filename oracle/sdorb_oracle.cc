@@ -964,6 +964,59 @@ void orc_assign_grid(const orc_keypoint* kps_un, int n, float mnMinX, float mnMi
   }
   cell_start[COLS * ROWS] = acc;
 }
+// cv::undistortPoints(src, dst, K, dist, noArray(), K) as OpenCV 4.13 computes it (calib3d undistort.dispatch.cpp,
+// cvUndistortPointsInternal: double arithmetic, 5 fixed-point iterations, no tilt, R = identity, P = K), which is what
+// Frame::UndistortKeyPoints (/root/reference/src/Frame.cc:335-366) and ComputeImageBounds (:368-397) call.  K and dist are
+// the CV_32F values the reference passes (Converter::toCvMat, src/Converter.cc:53-60).  k = (k1, k2, p1, p2[, k3]).
+static void undistort_point(float u_in, float v_in, const float K[4], const float* dist, int ndist, float* xo, float* yo) {
+  const double fx = K[0], fy = K[1], cx = K[2], cy = K[3], ifx = 1. / fx, ify = 1. / fy;
+  double k[14] = {0};
+  for (int i = 0; i < ndist && i < 14; i++) k[i] = dist[i];
+  const double u = u_in, v = v_in;
+  double x = (u - cx) * ifx, y = (v - cy) * ify;
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; j++) {
+    const double r2 = x * x + y * y;
+    const double icdist = (1 + ((k[7] * r2 + k[6]) * r2 + k[5]) * r2) / (1 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2);
+    if (icdist < 0) {  // the distortion model folded over: OpenCV falls back to the undistorted guess
+      x = (u - cx) * ifx;
+      y = (v - cy) * ify;
+      break;
+    }
+    const double deltaX = 2 * k[2] * x * y + k[3] * (r2 + 2 * x * x) + k[8] * r2 + k[9] * r2 * r2;
+    const double deltaY = k[2] * (r2 + 2 * y * y) + 2 * k[3] * x * y + k[10] * r2 + k[11] * r2 * r2;
+    x = (x0 - deltaX) * icdist;
+    y = (y0 - deltaY) * icdist;
+  }
+  const double xx = fx * x + 0. * y + cx, yy = 0. * x + fy * y + cy, ww = 1. / (0. * x + 0. * y + 1.);
+  *xo = (float)(xx * ww);
+  *yo = (float)(yy * ww);
+}
+// Frame::UndistortKeyPoints, src/Frame.cc:335-366
+void orc_undistort_keypoints(const orc_keypoint* kps, int n, const float K[4], const float* dist, int ndist, orc_keypoint* out) {
+  for (int i = 0; i < n; i++) {
+    out[i] = kps[i];
+    if (ndist > 0 && dist[0] != 0.0f) undistort_point(kps[i].x, kps[i].y, K, dist, ndist, &out[i].x, &out[i].y);
+  }
+}
+// Frame::ComputeImageBounds, src/Frame.cc:368-397: bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}
+void orc_image_bounds(int cols, int rows, const float K[4], const float* dist, int ndist, float bounds[4]) {
+  if (ndist > 0 && dist[0] != 0.0f) {
+    const float cx[4] = {0.f, (float)cols, 0.f, (float)cols}, cy[4] = {0.f, 0.f, (float)rows, (float)rows};
+    float mx[4], my[4];
+    for (int i = 0; i < 4; i++) undistort_point(cx[i], cy[i], K, dist, ndist, &mx[i], &my[i]);
+    bounds[0] = std::min(mx[0], mx[2]);
+    bounds[1] = std::max(mx[1], mx[3]);
+    bounds[2] = std::min(my[0], my[1]);
+    bounds[3] = std::max(my[2], my[3]);
+  } else {
+    bounds[0] = 0.0f;
+    bounds[1] = (float)cols;
+    bounds[2] = 0.0f;
+    bounds[3] = (float)rows;
+  }
+}
+
 // Frame::ComputeStereoFromRGBD, src/Frame.cc:399-417
 void orc_stereo_from_rgbd(const orc_keypoint* kps, const orc_keypoint* kps_un, int n, const float* depth, int width, float mbf,
                           float* u_right, float* z) {

@@ -130,6 +130,11 @@ void orc_distinctive_many(const uint8_t* desc, const int32_t* offsets, int nsets
 /* AssignFeaturesToGrid + PosInGrid (:179-192, :323-332): cell_start has 64*48+1 entries, indices n entries. */
 void orc_assign_grid(const orc_keypoint* kps_un, int n, float mnMinX, float mnMinY, float mfGridElementWidthInv,
                      float mfGridElementHeightInv, int32_t* cell_start, int32_t* indices);
+/* UndistortKeyPoints (:335-366) = cv::undistortPoints(pts, K, dist, noArray(), K) restated (OpenCV 4.13, double, 5
+ * iterations); K = {fx, fy, cx, cy}, dist = {k1, k2, p1, p2[, k3]}; dist[0] == 0 copies the keypoints (:336-339). */
+void orc_undistort_keypoints(const orc_keypoint* kps, int n, const float K[4], const float* dist, int ndist, orc_keypoint* out);
+/* ComputeImageBounds (:368-397): bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}. */
+void orc_image_bounds(int cols, int rows, const float K[4], const float* dist, int ndist, float bounds[4]);
 /* ComputeStereoFromRGBD (:399-417): depth is a tightly packed float image of the given width. */
 void orc_stereo_from_rgbd(const orc_keypoint* kps, const orc_keypoint* kps_un, int n, const float* depth, int width, float mbf,
                           float* u_right, float* z);

@@ -70,6 +70,8 @@ def lib():
     L.sdorb_hamming_matrix.argtypes = [vp, vp, i, vp, i, vp, i, vp]
     L.sdorb_distinctive_batch.argtypes = [vp, vp, vp, i, vp, vp, i, vp]
     L.sdorb_assign_grid_batch.argtypes = [vp, vp, vp, i, i, f, f, f, f, vp, vp, i, vp]
+    L.sdorb_undistort_keypoints_batch.argtypes = [vp, vp, vp, i, i, vp, vp, i, vp, i, vp]
+    L.sdorb_host_image_bounds.argtypes = [i, i, vp, vp, i, vp]
     L.sdorb_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i, i, vp, i, i, sz, sz, f, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
     L.sdorb_fill_border_reflect101.restype = None
@@ -118,6 +120,16 @@ def host_level_geometry(nfeatures, scaleFactor, nlevels, thFAST, width, height):
     if rc:
         raise SdorbError(rc, lib().sdorb_strerror(rc).decode())
     return g
+
+
+def host_image_bounds(cols, rows, K4, dist):
+    """Frame::ComputeImageBounds (src/Frame.cc:368-397): (mnMinX, mnMaxX, mnMinY, mnMaxY); needs no GPU."""
+    K4, dist = np.ascontiguousarray(K4, np.float32), np.ascontiguousarray(dist, np.float32)
+    b = np.zeros(4, np.float32)
+    rc = lib().sdorb_host_image_bounds(cols, rows, _ptr(K4), _ptr(dist), len(dist), _ptr(b))
+    if rc:
+        raise SdorbError(rc, lib().sdorb_strerror(rc).decode())
+    return b
 
 
 class ORBextractor:
@@ -291,6 +303,16 @@ class ORBextractor:
         self._check(lib().sdorb_assign_grid_batch(self._h, _ptr(kps), _ptr(counts), nf, cap, min_x, min_y, inv_w, inv_h, _ptr(cs),
                                                    _ptr(idx), MEM_HOST, None))
         return cs, idx
+
+    def undistort_keypoints_batch(self, keypoints, counts, K4, dist):
+        """Frame::UndistortKeyPoints for a batch (host arrays); K4 = (fx, fy, cx, cy), dist = (k1, k2, p1, p2[, k3])."""
+        kps = np.ascontiguousarray(keypoints)
+        counts = np.ascontiguousarray(counts, np.int32)
+        K4, dist = np.ascontiguousarray(K4, np.float32), np.ascontiguousarray(dist, np.float32)
+        out = np.zeros_like(kps)
+        self._check(lib().sdorb_undistort_keypoints_batch(self._h, _ptr(kps), _ptr(counts), kps.shape[0], kps.shape[1], _ptr(K4),
+                                                           _ptr(dist), len(dist), _ptr(out), MEM_HOST, None))
+        return out
 
     def stereo_from_rgbd_batch(self, keypoints, keypoints_un, counts, depth, mbf):
         """Frame::ComputeStereoFromRGBD for a batch (host arrays, depth float32 [F,H,W]): returns (u_right, z) [F, cap]."""

@@ -60,6 +60,10 @@ void launch_assign_grid(const void* kps, const int32_t* counts, int nframes, int
 void launch_stereo_rgbd(const void* kps, const void* kps_un, const int32_t* counts, int nframes, int capacity, const float* depth,
                         int width, int height, int64_t row_stride, int64_t frame_stride, float mbf, float* u_right, float* z,
                         cudaStream_t s);
+// Frame::UndistortKeyPoints (device) and Frame::ComputeImageBounds (host); K = {fx, fy, cx, cy}, dist = {k1, k2, p1, p2[, k3]}.
+void launch_undistort(const void* kps, const int32_t* counts, int nframes, int capacity, const float K[4], const float* dist,
+                      int ndist, void* out, cudaStream_t s);
+void host_image_bounds(int cols, int rows, const float K[4], const float* dist, int ndist, float bounds[4]);
 int configure_frame_kernels();
 
 size_t select_smem_bytes(const FrameGeom& g);

@@ -4,6 +4,7 @@
 //   PosInGrid             :323-332  posX = round((x - mnMinX) * mfGridElementWidthInv), same in y; outside the 64 x 48 grid -> dropped
 //   AssignFeaturesToGrid  :179-192  mGrid[posX][posY].push_back(i) for i ascending (FRAME_GRID_COLS 64, FRAME_GRID_ROWS 48, Frame.h:37-38)
 //   ComputeStereoFromRGBD :399-417  d = imDepth.at<float>(v, u) (float indices truncate); d > 0: depth = d, uRight = xUn - mbf / d
+//   UndistortKeyPoints    :335-366  cv::undistortPoints(pts, K, dist, noArray(), K); ComputeImageBounds :368-397 the same on 4 corners
 // The grid comes back in CSR form: cell c = posX * 48 + posY owns indices[cell_start[c] .. cell_start[c+1]), ascending --
 // exactly the order of the reference's push_backs.  One CTA per frame; no atomics decide any order.
 #include "kernels.cuh"
@@ -97,6 +98,113 @@ __global__ void __launch_bounds__(256) stereo_rgbd_kernel(const float* __restric
   }
   u_right[(int64_t)frame * capacity + i] = ur;
   z[(int64_t)frame * capacity + i] = d_out;
+}
+
+// cv::undistortPoints(pts, K, dist, noArray(), K) of OpenCV 4.13 (calib3d undistort.dispatch.cpp): double arithmetic, five
+// fixed-point iterations, operation order kept with round-to-nearest intrinsics (no contraction).  Shared by the host
+// (ComputeImageBounds) and the device (UndistortKeyPoints).
+struct Undistorter {
+  double fx, fy, cx, cy, ifx, ify, k[12];
+};
+
+__host__ __device__ inline void undistort_point(const Undistorter& U, float u_in, float v_in, float* xo, float* yo) {
+#ifdef __CUDA_ARCH__
+#define DMUL(a, b) __dmul_rn(a, b)
+#define DADD(a, b) __dadd_rn(a, b)
+#define DSUB(a, b) __dsub_rn(a, b)
+#define DDIV(a, b) __ddiv_rn(a, b)
+#else
+#define DMUL(a, b) ((a) * (b))
+#define DADD(a, b) ((a) + (b))
+#define DSUB(a, b) ((a) - (b))
+#define DDIV(a, b) ((a) / (b))
+#endif
+  const double* k = U.k;
+  const double u = u_in, v = v_in;
+  double x = DMUL(DSUB(u, U.cx), U.ifx), y = DMUL(DSUB(v, U.cy), U.ify);
+  const double x0 = x, y0 = y;
+  for (int j = 0; j < 5; ++j) {
+    const double r2 = DADD(DMUL(x, x), DMUL(y, y));
+    const double num = DADD(1., DMUL(DADD(DMUL(DADD(DMUL(k[7], r2), k[6]), r2), k[5]), r2));
+    const double den = DADD(1., DMUL(DADD(DMUL(DADD(DMUL(k[4], r2), k[1]), r2), k[0]), r2));
+    const double icdist = DDIV(num, den);
+    if (icdist < 0) {
+      x = DMUL(DSUB(u, U.cx), U.ifx);
+      y = DMUL(DSUB(v, U.cy), U.ify);
+      break;
+    }
+    // deltaX = 2*k2*x*y + k3*(r2 + 2*x*x) + k8*r2 + k9*r2*r2, left to right
+    const double dX = DADD(DADD(DADD(DMUL(DMUL(DMUL(2., k[2]), x), y), DMUL(k[3], DADD(r2, DMUL(DMUL(2., x), x)))), DMUL(k[8], r2)),
+                           DMUL(DMUL(k[9], r2), r2));
+    // deltaY = k2*(r2 + 2*y*y) + 2*k3*x*y + k10*r2 + k11*r2*r2
+    const double dY = DADD(DADD(DADD(DMUL(k[2], DADD(r2, DMUL(DMUL(2., y), y))), DMUL(DMUL(DMUL(2., k[3]), x), y)), DMUL(k[10], r2)),
+                           DMUL(DMUL(k[11], r2), r2));
+    x = DMUL(DSUB(x0, dX), icdist);
+    y = DMUL(DSUB(y0, dY), icdist);
+  }
+  // P = K, R = I:  xx = fx*x + 0*y + cx,  ww = 1 / (0*x + 0*y + 1)
+  const double xx = DADD(DADD(DMUL(U.fx, x), DMUL(0., y)), U.cx), yy = DADD(DADD(DMUL(0., x), DMUL(U.fy, y)), U.cy);
+  const double ww = DDIV(1., DADD(DADD(DMUL(0., x), DMUL(0., y)), 1.));
+  *xo = (float)DMUL(xx, ww);
+  *yo = (float)DMUL(yy, ww);
+#undef DMUL
+#undef DADD
+#undef DSUB
+#undef DDIV
+}
+
+static Undistorter make_undistorter(const float K[4], const float* dist, int ndist) {
+  Undistorter U;
+  U.fx = K[0];
+  U.fy = K[1];
+  U.cx = K[2];
+  U.cy = K[3];
+  U.ifx = 1. / U.fx;
+  U.ify = 1. / U.fy;
+  for (int i = 0; i < 12; ++i) U.k[i] = i < ndist ? (double)dist[i] : 0.;
+  return U;
+}
+
+// Frame::UndistortKeyPoints (src/Frame.cc:335-366): every field but pt is copied
+__global__ void __launch_bounds__(256) undistort_kernel(const float* __restrict__ kps, const int32_t* __restrict__ counts,
+                                                        int capacity, Undistorter U, int identity, float* __restrict__ out) {
+  const int frame = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= min(counts[frame], capacity)) return;
+  const float* a = kps + ((int64_t)frame * capacity + i) * 7;
+  float* b = out + ((int64_t)frame * capacity + i) * 7;
+  float x = a[0], y = a[1];
+  if (!identity) undistort_point(U, x, y, &x, &y);
+  b[0] = x;
+  b[1] = y;
+#pragma unroll
+  for (int f = 2; f < 7; ++f) b[f] = a[f];
+}
+
+void launch_undistort(const void* kps, const int32_t* counts, int nframes, int capacity, const float K[4], const float* dist,
+                      int ndist, void* out, cudaStream_t s) {
+  if (nframes <= 0 || capacity <= 0) return;
+  const int identity = !(ndist > 0 && dist[0] != 0.0f);  // src/Frame.cc:336-339
+  undistort_kernel<<<dim3((capacity + 255) / 256, nframes), 256, 0, s>>>((const float*)kps, counts, capacity,
+                                                                          make_undistorter(K, dist, ndist), identity, (float*)out);
+}
+
+// Frame::ComputeImageBounds (src/Frame.cc:368-397) on the host: bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}
+void host_image_bounds(int cols, int rows, const float K[4], const float* dist, int ndist, float bounds[4]) {
+  if (ndist > 0 && dist[0] != 0.0f) {
+    const Undistorter U = make_undistorter(K, dist, ndist);
+    const float px[4] = {0.f, (float)cols, 0.f, (float)cols}, py[4] = {0.f, 0.f, (float)rows, (float)rows};
+    float mx[4], my[4];
+    for (int i = 0; i < 4; ++i) undistort_point(U, px[i], py[i], &mx[i], &my[i]);
+    bounds[0] = mx[0] < mx[2] ? mx[0] : mx[2];
+    bounds[1] = mx[1] > mx[3] ? mx[1] : mx[3];
+    bounds[2] = my[0] < my[1] ? my[0] : my[1];
+    bounds[3] = my[2] > my[3] ? my[2] : my[3];
+  } else {
+    bounds[0] = 0.f;
+    bounds[1] = (float)cols;
+    bounds[2] = 0.f;
+    bounds[3] = (float)rows;
+  }
 }
 
 void launch_assign_grid(const void* kps, const int32_t* counts, int nframes, int capacity, float min_x, float min_y, float inv_w,

@@ -837,6 +837,47 @@ int sdorb_assign_grid_batch(sdorb_handle* h, const sdorb_keypoint* kps, const in
   return SDORB_OK;
 }
 
+int sdorb_host_image_bounds(int cols, int rows, const float* K, const float* dist, int ndist, float* bounds) {
+  if (!K || !bounds || cols <= 0 || rows <= 0 || ndist < 0 || ndist > 12 || (ndist > 0 && !dist)) return SDORB_ERR_BAD_ARG;
+  host_image_bounds(cols, rows, K, dist, ndist, bounds);
+  return SDORB_OK;
+}
+
+int sdorb_undistort_keypoints_batch(sdorb_handle* h, const sdorb_keypoint* kps, const int32_t* counts, int nframes, int capacity,
+                                    const float* K, const float* dist, int ndist, sdorb_keypoint* out, int mem, void* stream) {
+  if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nframes == 0) return SDORB_OK;
+  if (!kps || !counts || !out || !K || capacity <= 0 || ndist < 0 || ndist > 12 || (ndist > 0 && !dist)) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  if (mem == SDORB_MEM_DEVICE) {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_undistort(kps, counts, nframes, capacity, K, dist, ndist, out, s);
+    st.launched();
+    CU(cudaGetLastError());
+    return SDORB_OK;
+  }
+  const size_t bK = sizeof(sdorb_keypoint) * (size_t)nframes * capacity, bC = sizeof(int32_t) * (size_t)nframes;
+  int rc = ensure_match_buf(h, 2 * up256(bK) + up256(bC));
+  if (rc) return rc;
+  uint8_t* base = (uint8_t*)h->d_match_buf;
+  sdorb_keypoint* dK = (sdorb_keypoint*)base;
+  sdorb_keypoint* dO = (sdorb_keypoint*)(base + up256(bK));
+  int32_t* dC = (int32_t*)((uint8_t*)dO + up256(bK));
+  CU(cudaMemcpyAsync(dK, kps, bK, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(dC, counts, bC, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(dO, dK, bK, cudaMemcpyDeviceToDevice, s));  // entries beyond counts[f] pass through unchanged
+  {
+    StageScope st(h, s, SDORB_STAGE_MATCH);
+    launch_undistort(dK, dC, nframes, capacity, K, dist, ndist, dO, s);
+    st.launched();
+  }
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(out, dO, bK, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return SDORB_OK;
+}
+
 int sdorb_stereo_from_rgbd_batch(sdorb_handle* h, const sdorb_keypoint* kps, const sdorb_keypoint* kps_un, const int32_t* counts,
                                  int nframes, int capacity, const float* depth, int width, int height, size_t row_stride,
                                  size_t frame_stride, float mbf, float* u_right, float* z, int mem, void* stream) {

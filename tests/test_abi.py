@@ -129,3 +129,11 @@ def test_no_cpu_fallback_without_gpu():
     with pytest.raises(api.SdorbError) as e:
         api.ORBextractor(1000, 1.2, 8, 20)
     assert e.value.code in (-3, -5)
+
+
+def test_host_image_bounds_equal_oracle():
+    """Frame::ComputeImageBounds (src/Frame.cc:368-397) runs on the host, no GPU involved."""
+    from test_oracle_primitives import CAMERAS
+    for cam, (K4, dist) in CAMERAS.items():
+        for cols, rows in ((640, 480), (752, 480)):
+            assert api.host_image_bounds(cols, rows, K4, dist).tobytes() == orc.image_bounds(cols, rows, K4, dist).tobytes(), cam

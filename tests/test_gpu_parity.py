@@ -502,6 +502,22 @@ def test_frame_postprocessing_equals_oracle(ex_c1):
         assert (ur[f, cnt[f]:] == -1).all() and (z[f, cnt[f]:] == -1).all()
 
 
+@pytest.mark.parametrize("cam", ["tum1", "euroc", "none"])
+def test_undistort_keypoints_equals_oracle(ex_c1, cam):
+    """Frame::UndistortKeyPoints (src/Frame.cc:335-366) on the extractor's output; the oracle itself is pinned against the
+    real cv2.undistortPoints (tests/test_oracle_primitives.py)."""
+    from test_oracle_primitives import CAMERAS
+    K4, dist = (np.array(v, np.float32) for v in CAMERAS[cam])
+    kps, desc, cnt = ex_c1.extract_batch_host(synth.frames(2, 752, 480, start=600))
+    out = ex_c1.undistort_keypoints_batch(kps, cnt, K4, dist)
+    for f in range(2):
+        ref = orc.undistort_keypoints(kps[f, :cnt[f]], K4, dist)
+        assert out[f, :cnt[f]].tobytes() == ref.tobytes()
+    moved = float(np.abs(out["x"][0, :cnt[0]] - kps["x"][0, :cnt[0]]).max())
+    assert (moved > 0.5) == (cam != "none")
+    assert api.host_image_bounds(752, 480, K4, dist).tobytes() == orc.image_bounds(752, 480, K4, dist).tobytes()
+
+
 def test_kernel_launch_accounting(ex_c1):
     before = ex_c1.kernel_launches()
     ex_c1(synth.smooth_noise(0), want_pyramid=False)

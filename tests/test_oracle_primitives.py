@@ -299,3 +299,41 @@ def test_stereo_from_rgbd_rule():
             assert z[i] == d and ur[i] == np.float32(ku["x"][i] - np.float32(40.0) / d)
         else:
             assert z[i] == -1 and ur[i] == -1
+
+
+# ------------------------------------------------------------------ Frame::UndistortKeyPoints / ComputeImageBounds vs real cv2
+CAMERAS = {  # (fx, fy, cx, cy), distortion: the TUM1 / TUM2 / EuRoC-like models SD-SLAM is run with (README.md:41-105)
+    "tum1": ((517.306408, 516.469215, 318.643040, 255.313989), (0.262383, -0.953104, -0.005358, 0.002628, 1.163314)),
+    "tum2": ((520.908620, 521.007327, 325.141442, 249.701764), (0.231222, -0.784899, -0.003257, -0.000105, 0.917205)),
+    "euroc": ((458.654, 457.296, 367.215, 248.375), (-0.28340811, 0.07395907, 0.00019359, 1.76187114e-05)),
+    "none": ((500.0, 500.0, 320.0, 240.0), (0.0, 0.0, 0.0, 0.0)),
+}
+
+
+@pytest.mark.parametrize("cam", sorted(CAMERAS))
+def test_undistort_keypoints_matches_cv2(cam):
+    K4, dist = CAMERAS[cam]
+    K4, dist = np.array(K4, np.float32), np.array(dist, np.float32)
+    rng = np.random.default_rng(5)
+    k = np.zeros(4000, orc.KP_DTYPE)
+    k["x"] = rng.uniform(0, 752, 4000).astype(np.float32)
+    k["y"] = rng.uniform(0, 480, 4000).astype(np.float32)
+    k["x"][:4], k["y"][:4] = [0, 752, 0, 752], [0, 0, 480, 480]
+    k["octave"] = rng.integers(0, 8, 4000)
+    out = orc.undistort_keypoints(k, K4, dist)
+    Km = np.array([[K4[0], 0, K4[2]], [0, K4[1], K4[3]], [0, 0, 1]], np.float32)
+    if dist[0] != 0:
+        pts = np.stack([k["x"], k["y"]], 1).reshape(-1, 1, 2)
+        ref = cv2.undistortPoints(pts, Km, dist, None, Km).reshape(-1, 2)
+    else:
+        ref = np.stack([k["x"], k["y"]], 1)  # src/Frame.cc:336-339: mvKeysUn = mvKeys
+    assert np.array_equal(out["x"], ref[:, 0]) and np.array_equal(out["y"], ref[:, 1])
+    for name in ("size", "angle", "response", "octave", "class_id"):
+        assert np.array_equal(out[name], k[name])
+    b = orc.image_bounds(752, 480, K4, dist)
+    if dist[0] != 0:
+        c = cv2.undistortPoints(np.array([[[0, 0]], [[752, 0]], [[0, 480]], [[752, 480]]], np.float32), Km, dist, None, Km).reshape(4, 2)
+        exp = [min(c[0, 0], c[2, 0]), max(c[1, 0], c[3, 0]), min(c[0, 1], c[1, 1]), max(c[2, 1], c[3, 1])]
+    else:
+        exp = [0, 752, 0, 480]
+    assert b.tolist() == [float(np.float32(v)) for v in exp]
