@@ -260,6 +260,27 @@ def test_massive_response_ties():
     ex.close()
 
 
+@pytest.mark.parametrize("params", [(0, 1.2, 3, 20), (1, 1.2, 8, 20), (7, 1.2, 2, 20), (50, 1.2, 1, 20), (300, 1.05, 12, 5),
+                                    (1000, 1.9, 4, 20), (20000, 1.2, 8, 7)])
+def test_extreme_parameters(params):
+    """Degenerate but legal Config values (src/Config.cc:108-111): no features, one feature, one level, a very fine and
+    a very coarse pyramid, and far more features requested than the image has corners."""
+    img = synth.smooth_noise(700 + params[0] % 97, 400, 300)
+    try:
+        ok, od = orc.Extractor(*params).extract(img)
+    except RuntimeError:
+        ex = api.ORBextractor(*params, max_width=400, max_height=300, max_batch=1)
+        with pytest.raises(api.SdorbError):
+            ex(img)
+        ex.close()
+        return
+    ex = api.ORBextractor(*params, max_width=400, max_height=300, max_batch=2)
+    k, d, pyr = ex(img)
+    assert_same(ok, od, k, d, str(params))
+    assert len(pyr) == params[2]
+    ex.close()
+
+
 def test_too_small_image_is_geometry_error():
     ex = api.ORBextractor(*C1, max_width=64, max_height=64, max_batch=1)
     with pytest.raises(api.SdorbError) as e:
