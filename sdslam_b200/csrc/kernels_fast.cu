@@ -15,7 +15,7 @@
 //   * one thread owns one 32-bit word = 4 pixels; a warp owns 128 pixels of one row; everything is read from a
 //     shared-memory tile as aligned words and shuffled into place with PRMT;
 //   * min(v - r) over an arc is v - max(r) over the arc, so the arc minima / maxima are taken on the ring bytes
-//     themselves, two pixels at a time in 16-bit lanes (VIMNMX.U16x2, 3-input forms): 80 min/max + 16 PRMT per pixel pair;
+//     themselves, two pixels at a time in 16-bit lanes (VIMNMX.U16x2, 3-input forms): 64 min/max + 16 PRMT per pixel pair;
 //     each lane carries its byte twice (value * 257), so lane order == byte order and no masking is needed;
 //   * scores are kept as t = max(score + 1 - th, 0) in one byte per pixel; the 3x3 strict non-max test runs on the
 //     same packed lanes with per-column / per-row cell-boundary masks;
@@ -85,26 +85,36 @@ __device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const 
   r[13] = pair_at<P, -3>(W[4][0], W[4][1], W[4][2]);
   r[14] = pair_at<P, -2>(W[5][0], W[5][1], W[5][2]);
   r[15] = pair_at<P, -1>(W[6][0], W[6][1], W[6][2]);
-  uint32_t lo3[16], hi3[16];
+  // X = min over the 16 arcs of the arc maximum, Y = max over the arcs of the arc minimum.  The arcs starting at j-1 and
+  // at j (j odd) share the eight pixels j..j+7, so  min(max(arc j-1), max(arc j)) = max(max(r[j..j+7]), min(r[j-1], r[j+8]))
+  // (the grouping of OpenCV's cornerScore loop); the eight-pixel extrema are built from pair extrema (j, j+1), and the six
+  // pixels j+2..j+7 serve both j and j+2.  64 three-input min/max per pixel pair instead of 80.
+  uint32_t lo2[8], hi2[8], pmax[8], pmin[8];  // index q <-> j = 2q+1
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    lo3[k] = __vimin3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
-    hi3[k] = __vimax3_u16x2(r[k], r[(k + 1) & 15], r[(k + 2) & 15]);
+  for (int q = 0; q < 8; ++q) {
+    const int j = 2 * q + 1;
+    lo2[q] = __vminu2(r[j], r[(j + 1) & 15]);
+    hi2[q] = __vmaxu2(r[j], r[(j + 1) & 15]);
+    pmin[q] = __vminu2(r[j - 1], r[(j + 8) & 15]);  // joins the arc maxima
+    pmax[q] = __vmaxu2(r[j - 1], r[(j + 8) & 15]);  // joins the arc minima
   }
-  uint32_t amin[16], amax[16];  // min / max of the ring over the arc k..k+8
+  uint32_t wmax[8], wmin[8];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) {
-    amin[k] = __vimin3_u16x2(lo3[k], lo3[(k + 3) & 15], lo3[(k + 6) & 15]);
-    amax[k] = __vimax3_u16x2(hi3[k], hi3[(k + 3) & 15], hi3[(k + 6) & 15]);
+  for (int q = 0; q < 8; q += 2) {
+    const uint32_t chi = __vimax3_u16x2(hi2[(q + 1) & 7], hi2[(q + 2) & 7], hi2[(q + 3) & 7]);  // pixels j+2 .. j+7
+    const uint32_t clo = __vimin3_u16x2(lo2[(q + 1) & 7], lo2[(q + 2) & 7], lo2[(q + 3) & 7]);
+    wmax[q] = __vimax3_u16x2(chi, hi2[q], pmin[q]);
+    wmin[q] = __vimin3_u16x2(clo, lo2[q], pmax[q]);
+    wmax[q + 1] = __vimax3_u16x2(chi, hi2[(q + 4) & 7], pmin[q + 1]);
+    wmin[q + 1] = __vimin3_u16x2(clo, lo2[(q + 4) & 7], pmax[q + 1]);
   }
-  uint32_t X = amax[15], Y = amin[15];  // X = min over arcs of the arc maximum, Y = max over arcs of the arc minimum
-#pragma unroll
-  for (int k = 0; k < 14; k += 2) {
-    X = __vimin3_u16x2(X, amax[k], amax[k + 1]);
-    Y = __vimax3_u16x2(Y, amin[k], amin[k + 1]);
-  }
-  X = __vminu2(X, amax[14]);
-  Y = __vmaxu2(Y, amin[14]);
+  uint32_t X = __vimin3_u16x2(wmax[0], wmax[1], wmax[2]), Y = __vimax3_u16x2(wmin[0], wmin[1], wmin[2]);
+  X = __vimin3_u16x2(X, wmax[3], wmax[4]);
+  Y = __vimax3_u16x2(Y, wmin[3], wmin[4]);
+  X = __vimin3_u16x2(X, wmax[5], wmax[6]);
+  Y = __vimax3_u16x2(Y, wmin[5], wmin[6]);
+  X = __vminu2(X, wmax[7]);
+  Y = __vmaxu2(Y, wmin[7]);
   // A = v - X, B' = Y - v per lane, biased by 256 so that the lanes never borrow
   const uint32_t Xc = prmt(X, 0u, 0x4341), Yc = prmt(Y, 0u, 0x4341);
   const uint32_t Vc = prmt(W[3][1], 0u, P == 0 ? 0x4140 : 0x4342);
@@ -119,12 +129,13 @@ __device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const 
 template <int P>
 __device__ __forceinline__ uint32_t nms_pair(const uint32_t (&T)[3][3], const uint32_t lm, const uint32_t rm) {
   const uint32_t c = pair_at<P, 0>(T[1][0], T[1][1], T[1][2]);
-  const uint32_t l = pair_at<P, -1>(T[1][0], T[1][1], T[1][2]) & lm, r = pair_at<P, 1>(T[1][0], T[1][1], T[1][2]) & rm;
+  const uint32_t l = pair_at<P, -1>(T[1][0], T[1][1], T[1][2]), r = pair_at<P, 1>(T[1][0], T[1][1], T[1][2]);
   const uint32_t u = pair_at<P, 0>(T[0][0], T[0][1], T[0][2]), d = pair_at<P, 0>(T[2][0], T[2][1], T[2][2]);
-  const uint32_t ul = pair_at<P, -1>(T[0][0], T[0][1], T[0][2]) & lm, ur = pair_at<P, 1>(T[0][0], T[0][1], T[0][2]) & rm;
-  const uint32_t dl = pair_at<P, -1>(T[2][0], T[2][1], T[2][2]) & lm, dr = pair_at<P, 1>(T[2][0], T[2][1], T[2][2]) & rm;
-  const uint32_t m1 = __vimax3_u16x2(l, r, u), m2 = __vimax3_u16x2(ul, ur, d), m3 = __vimax3_u16x2(dl, dr, m1);
-  const uint32_t nb = __vmaxu2(m2, m3);
+  const uint32_t ul = pair_at<P, -1>(T[0][0], T[0][1], T[0][2]), ur = pair_at<P, 1>(T[0][0], T[0][1], T[0][2]);
+  const uint32_t dl = pair_at<P, -1>(T[2][0], T[2][1], T[2][2]), dr = pair_at<P, 1>(T[2][0], T[2][1], T[2][2]);
+  // the lane masks are all-or-nothing per lane, so one AND per column of three neighbours is enough
+  const uint32_t ml = __vimax3_u16x2(ul, l, dl) & lm, mr = __vimax3_u16x2(ur, r, dr) & rm;
+  const uint32_t nb = __vimax3_u16x2(ml, mr, __vmaxu2(u, d));
   return c - __vminu2(c, nb);  // lane != 0  <=>  centre strictly greater than all eight neighbours
 }
 
