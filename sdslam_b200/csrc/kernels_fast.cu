@@ -173,6 +173,30 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
   }
 
   // ---- stage pixels: rows b-4 .. b+OH+3, columns a-4 .. a+4*nw+3 as aligned words, one warp per row; zero outside the image
+  // Rows are at least 4 px inside the image at the top (b >= 19) and every plane has a pitch that is a multiple of 16, so
+  // an aligned word that starts inside a row is readable; bytes beyond the row's last pixel never reach a detectable pixel's ring.
+  if (!NARROW) {
+    static_assert(PROWS % (NT / 32) == 0 && 2 * PROWS <= 2 * NT, "staging loop shape");
+    const int gx = a - 4 + 4 * lane;
+    const uint8_t* colp = src + gx;
+    const bool col_ok = gx < w;
+    uint32_t v[PROWS / (NT / 32)];
+#pragma unroll
+    for (int j = 0; j < PROWS / (NT / 32); ++j) {  // all loads of the thread in flight together
+      const int gy = b - 4 + warp + (NT / 32) * j;
+      v[j] = 0;
+      if (col_ok && gy < h) v[j] = *reinterpret_cast<const uint32_t*>(colp + (int64_t)gy * pitch);
+    }
+#pragma unroll
+    for (int j = 0; j < PROWS / (NT / 32); ++j) s_pix[warp + (NT / 32) * j][lane] = v[j];
+    for (int i = tid; i < 2 * PROWS; i += NT) {  // the two words to the right of the 32 (words 32, 33 of each row)
+      const int r = i >> 1, kk = 32 + (i & 1);
+      const int gy = b - 4 + r, hx = a - 4 + 4 * kk;
+      uint32_t hv = 0;
+      if (gy < h && hx < w) hv = *reinterpret_cast<const uint32_t*>(src + (int64_t)gy * pitch + hx);
+      s_pix[r][kk] = hv;
+    }
+  } else
   for (int r = warp; r < PROWS; r += NT / 32) {
     const int gy = b - 4 + r;
     const uint8_t* row = src + (int64_t)gy * pitch;
