@@ -219,9 +219,22 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
     tile_fast += L.tiles_x_fast * L.tiles_y_fast;
     tile_fastn += L.fastn_words ? L.tiles_y_fast : 0;
     L.tile_base_blur = tile_blur;
-    L.tiles_x_blur = (L.w + SDORB_BLUR_TW - 1) / SDORB_BLUR_TW;
-    L.tiles_y_blur = (L.h + SDORB_BLUR_TH - 1) / SDORB_BLUR_TH;
+    // the reference blurs only levels that hold keypoints (src/ORBextractor.cc:651-660); a level without cells gets no strips
+    L.tiles_x_blur = any_detect ? (L.w + SDORB_BLUR_TW - 1) / SDORB_BLUR_TW : 0;
+    L.tiles_y_blur = any_detect ? (L.h + SDORB_BLUR_TH - 1) / SDORB_BLUR_TH : 0;
     tile_blur += L.tiles_x_blur * L.tiles_y_blur;
+    {
+      // window = the eight bytes at columns lastw-4 .. lastw+3; column x >= w mirrors to 2(w-1) - x
+      const int lastw = (L.w - 1) & ~3;
+      L.blur_sel_last = L.blur_sel_beyond = 0;
+      for (int b = 0; b < 4; ++b) {
+        const int x = lastw + b, xb = lastw + 4 + b;
+        const int i0 = (x < L.w ? x : 2 * (L.w - 1) - x) - (lastw - 4);
+        const int i1 = 2 * (L.w - 1) - xb - (lastw - 4);
+        L.blur_sel_last |= (uint32_t)std::min(std::max(i0, 0), 7) << (4 * b);
+        L.blur_sel_beyond |= (uint32_t)std::min(std::max(i1, 0), 7) << (4 * b);
+      }
+    }
     // resize taps from level l-1 to l
     if (l > 0) {
       const LevelGeom& P = g->lv[l - 1];

@@ -132,145 +132,170 @@ void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level,
 }
 
 // ------------------------------------------------------------------------------------------------ blur
-__device__ __forceinline__ int reflect101(int p, int len) {
-  if ((unsigned)p < (unsigned)len) return p;
-  if (len == 1) return 0;
-  do {
-    p = p < 0 ? -p : 2 * (len - 1) - p;
-  } while ((unsigned)p >= (unsigned)len);
-  return p;
-}
-
-constexpr int BTW = SDORB_BLUR_TW, BTH = SDORB_BLUR_TH;  // 128 x 32 output pixels per block
-constexpr int B_WORDS = BTW / 4;        // output words per row (= one warp)
-constexpr int B_ROWS = BTH + 6;         // source rows of a tile: y0-3 .. y0+TH+2
+// One warp = one strip of 128 columns x SDORB_BLUR_TH output rows; lane = one aligned word (4 pixels) of every row.
+// The warp walks down its strip: per source row three word loads (previous / own / next word), the horizontal 7-tap
+// sums of its four pixels as two IDP.4A each, and -- the vertical filter being symmetric -- the output row whose seventh
+// source row just arrived as  56*H3 + 48*(H2+H4) + 34*(H1+H5) + 18*(H0+H6) + 2^15  over a seven-row register window
+// (the loop is unrolled by seven so that the window slots are fixed registers).  Nothing goes through shared memory and
+// there is no barrier; per row and word: 3 LDG, 9 PRMT, 8 IDP.4A, 12 IADD, 16 IMAD, 1 STG plus addressing.
+// BORDER_REFLECT_101: rows by index arithmetic; columns in registers -- the words that reach beyond the row's ends are
+// rebuilt with PRMT from the two words next to the edge (selectors per level from the host, LevelGeom::blur_sel_*).
+constexpr int BTW = SDORB_BLUR_TW, BTH = SDORB_BLUR_TH;
 constexpr int B_WARPS = 4;
-constexpr int B_VROWS = BTH / B_WARPS;  // output rows per thread in the vertical pass
-static_assert(BTW == 128, "one warp spans a tile row");
+static_assert(BTW == 128, "one warp spans a strip row");
 
-// four pixels starting at column gx of a row, BORDER_REFLECT_101 outside [0, w).  Out of line on purpose: only the one
-// or two lanes of a row that straddle the right image edge ever come here.
-__device__ __noinline__ uint32_t blur_edge_word(const uint8_t* __restrict__ row, int gx, int w) {
-  uint32_t v = 0;
-#pragma unroll
-  for (int b = 0; b < 4; ++b) v |= (uint32_t)row[reflect101(gx + b, w)] << (8 * b);
+struct BlurTileBases {
+  int nlevels;
+  int base[SDORB_MAX_LEVELS + 1];  // first strip tile of each level; base[nlevels] = total
+};
+
+struct BlurLane {
+  const uint8_t* src;  // this lane's own word of row 0
+  int spitch, hlast, y_in0;
+  int ld0, ld1, ld2;         // which of the three words exist inside the row
+  bool edge_warp, is_last, is_pre, is_first;
+  uint32_t sel_last, sel_beyond;
+};
+
+// predicated word load: keeps the three loads of a row straight-line under loop-invariant predicates.  When the
+// predicate is off the result is unspecified -- every such word is either rebuilt by the edge code or belongs to a lane
+// beyond the row, which stores nothing.
+__device__ __forceinline__ uint32_t ldg_word_if(const uint8_t* ptr, int on) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(v) : "l"(ptr), "r"(on));
   return v;
 }
 
-__global__ void __launch_bounds__(B_WARPS * 32) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p) {
-  __shared__ __align__(16) uint2 s_h[B_ROWS][B_WORDS];  // horizontal sums, four 16-bit values per entry
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void blur_load_row(const BlurLane& B, int r, uint32_t (&w)[3]) {
+  int gy = abs(B.y_in0 + r);           // BORDER_REFLECT_101 of the row index: one reflection is enough for every level
+  gy = max(min(gy, B.hlast - gy), 0);  // that can hold a keypoint; the clamp only keeps the address inside the plane
+  const uint8_t* row = B.src + (uint64_t)((uint32_t)gy * (uint32_t)B.spitch);  // a plane is smaller than 2^31 bytes
+  w[1] = ldg_word_if(row, B.ld1);
+  w[0] = ldg_word_if(row - 4, B.ld0);
+  w[2] = ldg_word_if(row + 4, B.ld2);
+}
+
+// horizontal sums of the lane's four pixels of one source row
+template <bool EDGE>
+__device__ __forceinline__ void blur_hrow(const BlurLane& B, const uint32_t (&win)[3], uint32_t (&h)[4]) {
+  constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);  // taps -3..0
+  constexpr uint32_t KB = 48u | (34u << 8) | (18u << 16);                // taps +1..+3
+  uint32_t w0 = win[0], w1 = win[1], w2 = win[2];
+  if (EDGE) {
+    // right end: the last word of the row with its bytes beyond the row mirrored in, and the word after it
+    const uint32_t a = B.is_last ? w0 : w1, b = B.is_last ? w1 : w2;
+    const uint32_t lw = __byte_perm(a, b, B.sel_last), bw = __byte_perm(a, b, B.sel_beyond);
+    if (B.is_last) {
+      w1 = lw;
+      w2 = bw;
+    } else if (B.is_pre) {
+      w2 = lw;
+    }
+    if (B.is_first) w0 = __byte_perm(w1, w1, 0x1233);  // px -3..-1 mirror px 3..1
+  }
+  // every sum carries +128: the vertical weights add up to 256, which makes it the rounding constant 2^15 of the output
+  h[0] = __dp4a(__byte_perm(w0, w1, 0x4321), KA, __dp4a(__byte_perm(w1, w2, 0x4321), KB, 128u));
+  h[1] = __dp4a(__byte_perm(w0, w1, 0x5432), KA, __dp4a(__byte_perm(w1, w2, 0x5432), KB, 128u));
+  h[2] = __dp4a(__byte_perm(w0, w1, 0x6543), KA, __dp4a(__byte_perm(w1, w2, 0x6543), KB, 128u));
+  h[3] = __dp4a(w1, KA, __dp4a(w2, KB, 128u));
+}
+
+// Source row r (slot S = r mod 7) has arrived in H[S]: emit output row r - 6, whose rows r-6 .. r sit in slots S+1 .. S+7.
+template <int S>
+__device__ __forceinline__ uint32_t blur_vrow(const uint32_t (&H)[7][4]) {
+  uint32_t acc[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint32_t s3 = H[(S + 1) % 7][q] + H[S][q], s2 = H[(S + 2) % 7][q] + H[(S + 6) % 7][q];
+    const uint32_t s1 = H[(S + 3) % 7][q] + H[(S + 5) % 7][q];
+    acc[q] = 56u * H[(S + 4) % 7][q] + 48u * s1 + 34u * s2 + 18u * s3;  // includes 256 * 128 = 2^15
+  }
+  // byte 2 of each accumulator is (v + 2^15) >> 16 (v < 2^24)
+  return __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
+}
+
+template <bool EDGE>
+__device__ __forceinline__ void blur_walk(const BlurLane& B, uint8_t* __restrict__ dst, const int dpitch, const int nout) {
+  uint32_t H[7][4];
+  uint32_t cur[3], nxt[3];
+  // source rows 0..5 of the strip fill the window; from row 6 on every source row completes one output row
+  blur_load_row(B, 0, cur);
+#define SDORB_BLUR_FILL(S)          \
+  blur_load_row(B, S + 1, nxt);     \
+  blur_hrow<EDGE>(B, cur, H[S]);          \
+  cur[0] = nxt[0];                  \
+  cur[1] = nxt[1];                  \
+  cur[2] = nxt[2];
+  SDORB_BLUR_FILL(0)
+  SDORB_BLUR_FILL(1)
+  SDORB_BLUR_FILL(2)
+  SDORB_BLUR_FILL(3)
+  SDORB_BLUR_FILL(4)
+  SDORB_BLUR_FILL(5)
+#undef SDORB_BLUR_FILL
+  // output row o + K from source row o + K + 6 (slot (K + 6) mod 7); rows past the strip are read clamped and not stored
+#define SDORB_BLUR_STEP(K)                                                                      \
+  blur_load_row(B, o + K + 7, nxt);                                                             \
+  blur_hrow<EDGE>(B, cur, H[(K + 6) % 7]);                                                            \
+  if (o + K < nout && B.ld1) *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)(o + K) * (uint32_t)dpitch)) = blur_vrow<(K + 6) % 7>(H); \
+  cur[0] = nxt[0];                                                                              \
+  cur[1] = nxt[1];                                                                              \
+  cur[2] = nxt[2];
+  for (int o = 0; o < nout; o += 7) {
+    SDORB_BLUR_STEP(0)
+    SDORB_BLUR_STEP(1)
+    SDORB_BLUR_STEP(2)
+    SDORB_BLUR_STEP(3)
+    SDORB_BLUR_STEP(4)
+    SDORB_BLUR_STEP(5)
+    SDORB_BLUR_STEP(6)
+  }
+#undef SDORB_BLUR_STEP
+}
+
+__global__ void __launch_bounds__(B_WARPS * 32, 7) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, BlurTileBases tb) {
+  const int lane = threadIdx.x & 31;
+  const int tile = blockIdx.x * B_WARPS + (threadIdx.x >> 5);
+  if (tile >= tb.base[tb.nlevels]) return;
   int level = 0;
-  while (level + 1 < geom->nlevels && (int)blockIdx.x >= geom->lv[level + 1].tile_base_blur) ++level;
+  while (tile >= tb.base[level + 1]) ++level;
   const LevelGeom& L = geom->lv[level];
   const int frame = blockIdx.y;
-  const int t = blockIdx.x - L.tile_base_blur;
-  const int x0 = (t % L.tiles_x_blur) * BTW, y0 = (t / L.tiles_x_blur) * BTH;
+  const int t = tile - tb.base[level];
+  const int tx = t % L.tiles_x_blur, ty = t / L.tiles_x_blur;
+  const int x0 = tx * BTW, y0 = ty * BTH;
   const int w = L.w, h = L.h;
-  int spitch;
-  const uint8_t* src = level_plane(p, L, level, frame, &spitch);
-
-  // ---- horizontal pass straight from global memory: warp = one source row, lane = one word of it; the neighbour words
-  // come from the neighbour lanes, the two halo words from one extra load on lanes 0 and 31.
   const int gx = x0 + 4 * lane;
-  const bool interior = gx + 3 < w;                         // this lane's word lies fully inside the row
-  const bool edge = !interior && gx < w + 4;                // straddles the right edge (taps reach 3 px beyond it)
-  const int hx = lane == 0 ? x0 - 4 : x0 + BTW;             // halo word column (lanes 0 and 31 only)
-  const bool h_lane = (lane == 0 && x0 > 0) || lane == 31;  // the left halo of the first tile is mirrored from w1, w2 below
-  const bool h_interior = hx + 3 < w;
-  const bool h_edge = !h_interior && hx < w + 4;
-  constexpr uint32_t KA = 18u | (34u << 8) | (48u << 16) | (56u << 24);  // taps -3..0
-  constexpr uint32_t KB = 48u | (34u << 8) | (18u << 16);                // taps +1..+3 (+4 unused)
-  constexpr int B_HROWS = (B_ROWS + B_WARPS - 1) / B_WARPS;              // source rows per warp
-  const int hlast = 2 * (h - 1);
-  // all loads of the warp's rows are issued before the first is used (the pass is latency-bound otherwise)
-  uint32_t cw[B_HROWS], ew[B_HROWS];
-  if (x0 + BTW + 4 <= w) {
-    // tile (and its right halo word) entirely inside the row: plain loads, no edge tests (block-uniform branch)
-    const bool halo = (lane == 0 && x0 > 0) || lane == 31;
-#pragma unroll
-    for (int j = 0; j < B_HROWS; ++j) {
-      const int r = warp + j * B_WARPS;
-      cw[j] = ew[j] = 0;
-      if (r < B_ROWS) {
-        int gy = abs(y0 - 3 + r);  // BORDER_REFLECT_101 of the row index, see below
-        gy = max(min(gy, hlast - gy), 0);
-        const uint8_t* row = src + (int64_t)gy * spitch;
-        cw[j] = *reinterpret_cast<const uint32_t*>(row + gx);
-        if (halo) ew[j] = *reinterpret_cast<const uint32_t*>(row + hx);
-      }
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < B_HROWS; ++j) {
-      const int r = warp + j * B_WARPS;
-      cw[j] = ew[j] = 0;
-      if (r < B_ROWS) {
-        // BORDER_REFLECT_101 of the row index without branches: one reflection is enough for every level that can hold
-        // a keypoint (h >= 45); the clamp only keeps degenerate levels inside their plane
-        int gy = abs(y0 - 3 + r);
-        gy = max(min(gy, hlast - gy), 0);
-        const uint8_t* row = src + (int64_t)gy * spitch;
-        if (interior) cw[j] = *reinterpret_cast<const uint32_t*>(row + gx);
-        else if (edge) cw[j] = blur_edge_word(row, gx, w);
-        if (h_lane) {
-          if (h_interior) ew[j] = *reinterpret_cast<const uint32_t*>(row + hx);
-          else if (h_edge) ew[j] = blur_edge_word(row, hx, w);
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < B_HROWS; ++j) {
-    const int r = warp + j * B_WARPS;
-    if (r >= B_ROWS) break;  // warp-uniform
-    const uint32_t w1 = cw[j];
-    uint32_t w0 = __shfl_up_sync(0xffffffffu, w1, 1), w2 = __shfl_down_sync(0xffffffffu, w1, 1);
-    if (lane == 0) w0 = x0 > 0 ? ew[j] : __byte_perm(w1, w2, 0x1234);  // px -4..-1 mirror px 4..1
-    if (lane == 31) w2 = ew[j];
-    // H[x] = sum_i K[i] * src[x + i - 3]: the seven taps of a pixel are two byte quadruples of (w0 w1) and (w1 w2)
-    const uint32_t h0 = __dp4a(__byte_perm(w0, w1, 0x4321), KA, __dp4a(__byte_perm(w1, w2, 0x4321), KB, 0u));
-    const uint32_t h1 = __dp4a(__byte_perm(w0, w1, 0x5432), KA, __dp4a(__byte_perm(w1, w2, 0x5432), KB, 0u));
-    const uint32_t h2 = __dp4a(__byte_perm(w0, w1, 0x6543), KA, __dp4a(__byte_perm(w1, w2, 0x6543), KB, 0u));
-    const uint32_t h3 = __dp4a(w1, KA, __dp4a(w2, KB, 0u));
-    s_h[r][lane] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
-  }
-  __syncthreads();
+  const int lastw = (w - 1) & ~3;
+  BlurLane B;
+  const uint8_t* plane = level_plane(p, L, level, frame, &B.spitch);
+  B.src = plane + gx;
+  B.hlast = 2 * (h - 1);
+  B.y_in0 = y0 - 3;
+  B.ld1 = gx <= lastw;
+  B.ld0 = B.ld1 && gx > 0;
+  B.ld2 = gx + 4 <= lastw;
+  B.is_last = gx == lastw;
+  B.is_pre = gx + 4 == lastw;
+  B.is_first = gx == 0;
+  B.edge_warp = x0 == 0 || x0 + BTW + 4 > lastw;
+  B.sel_last = L.blur_sel_last;
+  B.sel_beyond = L.blur_sel_beyond;
+  const int nout = min(BTH, h - y0);
+  uint8_t* dst = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes + (int64_t)y0 * L.pitch + gx;
+  const int dpitch = L.pitch;
 
-  // ---- vertical pass: thread = one word column x B_VROWS output rows; V[y] = sum_j K[j] * H[y + j - 3] over row pairs
-  if (gx >= w) return;
-  uint2 hv[B_VROWS + 6];
-#pragma unroll
-  for (int j = 0; j < B_VROWS + 6; ++j) hv[j] = s_h[warp * B_VROWS + j][lane];
-  uint8_t* dst = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
-  constexpr uint32_t K01 = 18u | (34u << 8), K23 = 48u | (56u << 8), K45 = 48u | (34u << 8);
-#pragma unroll
-  for (int o = 0; o < B_VROWS; ++o) {
-    const int gy = y0 + warp * B_VROWS + o;
-    if (gy >= h) break;  // warp-uniform
-    uint32_t acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const uint32_t sel = (q & 1) ? 0x7632u : 0x5410u;
-      const uint32_t a0 = q < 2 ? hv[o].x : hv[o].y, a1 = q < 2 ? hv[o + 1].x : hv[o + 1].y;
-      const uint32_t a2 = q < 2 ? hv[o + 2].x : hv[o + 2].y, a3 = q < 2 ? hv[o + 3].x : hv[o + 3].y;
-      const uint32_t a4 = q < 2 ? hv[o + 4].x : hv[o + 4].y, a5 = q < 2 ? hv[o + 5].x : hv[o + 5].y;
-      const uint32_t a6 = q < 2 ? hv[o + 6].x : hv[o + 6].y;
-      uint32_t v = __dp2a_lo(__byte_perm(a0, a1, sel), K01, 32768u);
-      v = __dp2a_lo(__byte_perm(a2, a3, sel), K23, v);
-      v = __dp2a_lo(__byte_perm(a4, a5, sel), K45, v);
-      v = __dp2a_lo(a6, (q & 1) ? (18u << 8) : 18u, v);
-      acc[q] = v;
-    }
-    // byte 2 of each accumulator is (v + 2^15) >> 16 (v < 2^24)
-    const uint32_t out = __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
-    *reinterpret_cast<uint32_t*>(dst + (int64_t)gy * L.pitch + gx) = out;
-  }
+  if (B.edge_warp) blur_walk<true>(B, dst, dpitch, nout);  // warp-uniform
+  else blur_walk<false>(B, dst, dpitch, nout);
 }
 
 void launch_blur_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s) {
   if (g.tiles_total_blur == 0) return;
-  blur_all_kernel<<<dim3(g.tiles_total_blur, nframes), B_WARPS * 32, 0, s>>>(d_geom, p);
+  BlurTileBases tb;
+  tb.nlevels = g.nlevels;
+  for (int l = 0; l < g.nlevels; ++l) tb.base[l] = g.lv[l].tile_base_blur;
+  for (int l = g.nlevels; l <= SDORB_MAX_LEVELS; ++l) tb.base[l] = g.tiles_total_blur;
+  blur_all_kernel<<<dim3((g.tiles_total_blur + B_WARPS - 1) / B_WARPS, nframes), B_WARPS * 32, 0, s>>>(d_geom, p, tb);
 }
 
 }  // namespace sdorb

@@ -16,7 +16,7 @@
 #define SDORB_FAST_TW 120
 #define SDORB_FAST_TH 30
 #define SDORB_BLUR_TW 128
-#define SDORB_BLUR_TH 32
+#define SDORB_BLUR_TH 64
 
 // Packed keypoint entry used between the FAST, selection and describe kernels.
 // Ascending order of the packed word == row-major (y, then x) order, the order cv::FAST emits in.
@@ -47,7 +47,9 @@ struct LevelGeom {
   int64_t plane_bytes;   // pitch * h
   int tile_base_fast, tiles_x_fast, tiles_y_fast;  // flattened tile tables for the all-level launches (full FAST tiles)
   int tile_base_fastn, fastn_words;  // narrow FAST tiles of the last tile column: scored words per row (4, 8, 16; 0 = none)
-  int tile_base_blur, tiles_x_blur, tiles_y_blur;
+  int tile_base_blur, tiles_x_blur, tiles_y_blur;  // blur strips: 128 columns x SDORB_BLUR_TH rows, one warp each (none for levels without cells)
+  uint32_t blur_sel_last, blur_sel_beyond;  // PRMT selectors that rebuild, from the row's last two words, the last word with its
+                                            // out-of-row bytes mirrored in (BORDER_REFLECT_101) and the word after it
   int scaled_patch_size; // (int)(31 * mvScaleFactor[level])
   float scale;           // mvScaleFactor[level]
   int coef_x_base, coef_y_base;  // offsets into the resize coefficient tables (entries), levels >= 1
