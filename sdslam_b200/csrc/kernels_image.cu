@@ -217,15 +217,19 @@ __device__ __forceinline__ uint32_t blur_vrow(const uint32_t (&H)[7][4]) {
 template <bool EDGE>
 __device__ __forceinline__ void blur_walk(const BlurLane& B, uint8_t* __restrict__ dst, const int dpitch, const int nout) {
   uint32_t H[7][4];
-  uint32_t cur[3], nxt[3];
+  uint32_t cur[3], nx1[3], nxt[3];  // loads run two rows ahead of the arithmetic
   // source rows 0..5 of the strip fill the window; from row 6 on every source row completes one output row
   blur_load_row(B, 0, cur);
+  blur_load_row(B, 1, nx1);
 #define SDORB_BLUR_FILL(S)          \
-  blur_load_row(B, S + 1, nxt);     \
+  blur_load_row(B, S + 2, nxt);     \
   blur_hrow<EDGE>(B, cur, H[S]);          \
-  cur[0] = nxt[0];                  \
-  cur[1] = nxt[1];                  \
-  cur[2] = nxt[2];
+  cur[0] = nx1[0];                  \
+  cur[1] = nx1[1];                  \
+  cur[2] = nx1[2];                  \
+  nx1[0] = nxt[0];                  \
+  nx1[1] = nxt[1];                  \
+  nx1[2] = nxt[2];
   SDORB_BLUR_FILL(0)
   SDORB_BLUR_FILL(1)
   SDORB_BLUR_FILL(2)
@@ -235,12 +239,15 @@ __device__ __forceinline__ void blur_walk(const BlurLane& B, uint8_t* __restrict
 #undef SDORB_BLUR_FILL
   // output row o + K from source row o + K + 6 (slot (K + 6) mod 7); rows past the strip are read clamped and not stored
 #define SDORB_BLUR_STEP(K)                                                                      \
-  blur_load_row(B, o + K + 7, nxt);                                                             \
+  blur_load_row(B, o + K + 8, nxt);                                                             \
   blur_hrow<EDGE>(B, cur, H[(K + 6) % 7]);                                                            \
   if (o + K < nout && B.ld1) *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)(o + K) * (uint32_t)dpitch)) = blur_vrow<(K + 6) % 7>(H); \
-  cur[0] = nxt[0];                                                                              \
-  cur[1] = nxt[1];                                                                              \
-  cur[2] = nxt[2];
+  cur[0] = nx1[0];                                                                              \
+  cur[1] = nx1[1];                                                                              \
+  cur[2] = nx1[2];                                                                              \
+  nx1[0] = nxt[0];                                                                              \
+  nx1[1] = nxt[1];                                                                              \
+  nx1[2] = nxt[2];
   for (int o = 0; o < nout; o += 7) {
     SDORB_BLUR_STEP(0)
     SDORB_BLUR_STEP(1)
@@ -253,7 +260,7 @@ __device__ __forceinline__ void blur_walk(const BlurLane& B, uint8_t* __restrict
 #undef SDORB_BLUR_STEP
 }
 
-__global__ void __launch_bounds__(B_WARPS * 32, 7) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, BlurTileBases tb) {
+__global__ void __launch_bounds__(B_WARPS * 32, 5) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, BlurTileBases tb) {
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x * B_WARPS + (threadIdx.x >> 5);
   if (tile >= tb.base[tb.nlevels]) return;
