@@ -251,6 +251,10 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
         const int ngroups = (L.w + 3) / 4;
         std::vector<ResizeGroup> gs(ngroups);
         bool fits = true;
+        for (int y = 0; y < L.h; ++y) {  // the kernel multiplies the vertical coefficients as unsigned 16-bit values
+          const ResizeTap& tp = taps->data()[L.coef_y_base + y];
+          if (tp.c0 < 0 || tp.c1 < 0) fits = false;
+        }
         for (int gi = 0; gi < ngroups && fits; ++gi) {
           ResizeGroup& G = gs[gi];
           G.pad_ = 0;

@@ -26,23 +26,33 @@ __device__ __forceinline__ const uint8_t* level_plane(const BatchPlanes& p, cons
 }
 
 // ------------------------------------------------------------------------------------------------ resize
-constexpr int RZ_ROWS = 8;  // consecutive destination rows per thread (a source row feeds two destination rows)
+constexpr int RZ_ROWS = 16;  // consecutive destination rows per thread (a source row feeds up to two destination rows)
 
-// horizontal pass of one source row for four destination pixels
-__device__ __forceinline__ void resize_hrow(const uint8_t* __restrict__ row, int base, int last_word, int shift,
-                                            const ResizeGroup& G, int (&hv)[4]) {
-  const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row + min(base, last_word));
-  const uint32_t w1 = *reinterpret_cast<const uint32_t*>(row + min(base + 4, last_word));
-  const uint32_t w2 = *reinterpret_cast<const uint32_t*>(row + min(base + 8, last_word));
-  const uint32_t lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
-  const uint32_t p01 = __byte_perm(lo, hi, G.sel01), p23 = __byte_perm(lo, hi, G.sel23);
-  hv[0] = (int)__dp2a_lo(G.coef[0], p01, 0u);
-  hv[1] = (int)__dp2a_hi(G.coef[1], p01, 0u);
-  hv[2] = (int)__dp2a_lo(G.coef[2], p23, 0u);
-  hv[3] = (int)__dp2a_hi(G.coef[3], p23, 0u);
+// predicated word load: keeps the loads of a row straight-line under loop-invariant predicates.  When the predicate is
+// off the result is unspecified -- the callers only switch off words none of whose bytes can reach a result.
+__device__ __forceinline__ uint32_t ldg_word_if(const uint8_t* ptr, int on) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(v) : "l"(ptr), "r"(on));
+  return v;
 }
 
-// One thread = 4 consecutive destination pixels x RZ_ROWS consecutive rows.  Block (32, 4): 128 x 32 pixels.
+// horizontal pass of one source row for four destination pixels, already shifted: a[i] = (c0*s0 + c1*s1) >> 4
+__device__ __forceinline__ void resize_hrow(const uint8_t* __restrict__ row, int ld1, int ld2, int shift, const ResizeGroup& G,
+                                            uint32_t (&a)[4]) {
+  const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row);
+  const uint32_t w1 = ldg_word_if(row + 4, ld1), w2 = ldg_word_if(row + 8, ld2);
+  const uint32_t lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+  const uint32_t p01 = __byte_perm(lo, hi, G.sel01), p23 = __byte_perm(lo, hi, G.sel23);
+  a[0] = __dp2a_lo(G.coef[0], p01, 0u) >> 4;
+  a[1] = __dp2a_hi(G.coef[1], p01, 0u) >> 4;
+  a[2] = __dp2a_lo(G.coef[2], p23, 0u) >> 4;
+  a[3] = __dp2a_hi(G.coef[3], p23, 0u) >> 4;
+}
+
+// One thread = 4 consecutive destination pixels x RZ_ROWS consecutive rows.  Block (32, 4): 128 x 64 pixels.
+// Coefficients are non-negative on this path (checked when the groups are built), so every intermediate fits an
+// unsigned lane and the result needs no clamp: the two products of a pixel are cut to their upper halves two pixels at
+// a time (PRMT), summed with the rounding constant in 16-bit lanes and shifted as one word.
 __global__ void __launch_bounds__(128) resize_level_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
                                                            const ResizeTap* __restrict__ taps,
                                                            const ResizeGroup* __restrict__ groups) {
@@ -52,39 +62,43 @@ __global__ void __launch_bounds__(128) resize_level_kernel(const FrameGeom* __re
   const int x4 = gi * 4;
   const int y0 = (blockIdx.y * 4 + threadIdx.y) * RZ_ROWS;
   const int frame = blockIdx.z;
-  if (x4 >= D.w || y0 >= D.h) return;
+  const int dh = D.h;
+  if (x4 >= D.w || y0 >= dh) return;
   int spitch;
   const uint8_t* src = level_plane(p, S, level - 1, frame, &spitch);
-  uint8_t* dst = p.pyr + D.plane_base * p.batch_cap + (int64_t)frame * D.plane_bytes;
+  const int dpitch = D.pitch;
+  uint8_t* dst = p.pyr + D.plane_base * p.batch_cap + (int64_t)frame * D.plane_bytes + (int64_t)y0 * dpitch + x4;
   const ResizeGroup G = groups[D.group_base + gi];
   const int base = G.src_x & ~3, shift = (G.src_x & 3) * 8, last_word = (S.w - 1) & ~3;
-  const ResizeTap* ty = taps + D.coef_y_base;
-  int h1[4] = {0, 0, 0, 0};
-  int have = -1;  // source row currently held in h1
-  const int y1 = min(y0 + RZ_ROWS, D.h);
-  for (int y = y0; y < y1; ++y) {
-    const ResizeTap t = ty[y];
-    int h0[4];
-    if ((int)t.s0 == have) {
+  // the eight bytes from src_x on hold every tap; words past the row's last word hold none
+  const int ld1 = base + 4 <= last_word, ld2 = shift != 0 && base + 8 <= last_word;
+  src += base;
+  const uint2* ty = reinterpret_cast<const uint2*>(taps + D.coef_y_base + y0);
+  uint32_t a0[4], a1[4] = {0, 0, 0, 0};
+  uint32_t have = 0xFFFFFFFFu;  // source row held in a1
 #pragma unroll
-      for (int i = 0; i < 4; ++i) h0[i] = h1[i];
+  for (int j = 0; j < RZ_ROWS; ++j) {
+    if (y0 + j >= dh) break;
+    const uint2 t = ty[j];  // {s0 | s1 << 16, c0 | c1 << 16}
+    const uint32_t s0 = t.x & 0xFFFFu, s1 = t.x >> 16, c0 = t.y & 0xFFFFu, c1 = t.y >> 16;
+    if (s0 == have) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a0[i] = a1[i];
     } else {
-      resize_hrow(src + (int64_t)t.s0 * spitch, base, last_word, shift, G, h0);
+      resize_hrow(src + (uint64_t)(s0 * (uint32_t)spitch), ld1, ld2, shift, G, a0);
     }
-    if (t.s1 != t.s0) resize_hrow(src + (int64_t)t.s1 * spitch, base, last_word, shift, G, h1);
-    else {
+    if (s1 != s0) {
+      resize_hrow(src + (uint64_t)(s1 * (uint32_t)spitch), ld1, ld2, shift, G, a1);
+    } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) h1[i] = h0[i];
+      for (int i = 0; i < 4; ++i) a1[i] = a0[i];
     }
-    have = t.s1;
-    uint32_t out = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int v = (((t.c0 * (h0[i] >> 4)) >> 16) + ((t.c1 * (h1[i] >> 4)) >> 16) + 2) >> 2;
-      v = min(max(v, 0), 255);
-      out |= (uint32_t)v << (8 * i);
-    }
-    *reinterpret_cast<uint32_t*>(dst + (int64_t)y * D.pitch + x4) = out;  // pitch is a multiple of 128: padding absorbs the tail
+    have = s1;
+    // v = (((c0 * a0) >> 16) + ((c1 * a1) >> 16) + 2) >> 2
+    const uint32_t u01 = __byte_perm(c0 * a0[0], c0 * a0[1], 0x7632), u23 = __byte_perm(c0 * a0[2], c0 * a0[3], 0x7632);
+    const uint32_t l01 = __byte_perm(c1 * a1[0], c1 * a1[1], 0x7632), l23 = __byte_perm(c1 * a1[2], c1 * a1[3], 0x7632);
+    const uint32_t v01 = (u01 + l01 + 0x00020002u) >> 2, v23 = (u23 + l23 + 0x00020002u) >> 2;  // lanes <= 1022: no carry
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)j * (uint32_t)dpitch)) = __byte_perm(v01, v23, 0x6420);  // the pitch absorbs the tail
   }
 }
 
@@ -156,15 +170,6 @@ struct BlurLane {
   bool edge_warp, is_last, is_pre, is_first;
   uint32_t sel_last, sel_beyond;
 };
-
-// predicated word load: keeps the three loads of a row straight-line under loop-invariant predicates.  When the
-// predicate is off the result is unspecified -- every such word is either rebuilt by the edge code or belongs to a lane
-// beyond the row, which stores nothing.
-__device__ __forceinline__ uint32_t ldg_word_if(const uint8_t* ptr, int on) {
-  uint32_t v;
-  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(v) : "l"(ptr), "r"(on));
-  return v;
-}
 
 __device__ __forceinline__ void blur_load_row(const BlurLane& B, int r, uint32_t (&w)[3]) {
   int gy = abs(B.y_in0 + r);           // BORDER_REFLECT_101 of the row index: one reflection is enough for every level
