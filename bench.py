@@ -385,6 +385,36 @@ def run_ours(args):
     barrier()
     distinctive_sets_per_s = world * nsets / (q0.elapsed_time(q1) * 1e-3)
 
+    # ---- guided-matcher side figure: ORBmatcher::SearchForInitialization (windowSize 100, nnratio 0.9, orientation check) on the
+    # frame pairs (2k, 2k+1) of this batch, device-resident: Frame::AssignFeaturesToGrid of frame 2k+1, then the search
+    kA, kB = kps[0::2].contiguous(), kps[1::2].contiguous()
+    inv_w, inv_h = float(np.float32(64) / np.float32(w)), float(np.float32(48) / np.float32(h))
+    g_cs = torch.zeros((npairs, 64 * 48 + 1), dtype=torch.int32, device=dev)
+    g_ix = torch.zeros((npairs, cap), dtype=torch.int32, device=dev)
+    s_prev0 = kA[:, :, 0:2].contiguous()
+    s_prev = s_prev0.clone()
+    s_m12 = torch.zeros((npairs, cap), dtype=torch.int32, device=dev)
+    s_nm = torch.zeros(npairs, dtype=torch.int32, device=dev)
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def search_once():
+        ex.assign_grid_batch(kB, nB, 0.0, 0.0, inv_w, inv_h, cell_start=g_cs, indices=g_ix, device=True, stream=stream.cuda_stream)
+        ex.search_for_initialization_batch(kA, dA, nA, kB, dB, nB, (g_cs, g_ix, 0.0, 0.0, inv_w, inv_h), s_prev, 100, 0.9, True,
+                                           matches12=s_m12, nmatches=s_nm, device=True, stream=stream.cuda_stream)
+
+    with torch.cuda.stream(stream):
+        search_once()
+        s_prev.copy_(s_prev0)
+        s0.record(stream)
+        search_once()
+        s1.record(stream)
+    barrier()
+    ts = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    search_pairs_per_s = world * npairs / (float(ts.item()) * 1e-3)
+    search_matches = float(s_nm.double().mean().item())
+
     # ---- the one collective of the job: gather the result slabs of (a slice of) the batch on rank 0 over NCCL
     gather_ms = None
     if world > 1:
@@ -444,7 +474,9 @@ def run_ours(args):
             "keypoints_per_frame": mean_kp,
             "hamming": {"value": pairs_per_s, "unit": "pairs/s", "pairs_per_frame_pair": pairs / max(npairs, 1),
                         "frame_pairs_per_gpu": npairs, "ms": float(tm.item()),
-                        "distinctive_sets_per_s": distinctive_sets_per_s, "distinctive_set_size": 16},
+                        "distinctive_sets_per_s": distinctive_sets_per_s, "distinctive_set_size": 16,
+                        "search_for_initialization_frame_pairs_per_s": search_pairs_per_s,
+                        "search_for_initialization_matches_per_pair": search_matches},
             "gather_ms": gather_ms,
             "host_affinity": numa,
         }

@@ -184,6 +184,60 @@ SDORB_API int sdorb_stereo_from_rgbd_batch(sdorb_handle* h, const sdorb_keypoint
                                  size_t depth_row_stride, size_t depth_frame_stride, float mbf, float* u_right, float* z,
                                  int mem, void* stream);
 
+/* ---- guided matchers: the callers either side of DescriptorDistance (src/ORBmatcher.cc), batched over frame pairs ----
+ * All arrays are slabs [npairs][capacity] (keypoints: sdorb_keypoint, descriptors: 32 bytes per row) with per-pair counts;
+ * the grid of the searched frame is what sdorb_assign_grid_batch produced for it (cell_start [npairs][64*48+1], indices
+ * [npairs][capacity]) together with the four Frame members of the window query Frame::GetFeaturesInArea
+ * (src/Frame.cc:271-321): mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv.  Queries are visited in index
+ * order and every accepted match changes what later queries may take, exactly as in the reference; the results are
+ * identical to running the reference function pair by pair.  capacity <= 16384.  mem / stream as above. */
+typedef struct {
+  const int32_t* cell_start;
+  const int32_t* indices;
+  float min_x, min_y, inv_w, inv_h;
+} sdorb_frame_grid;
+
+/* ORBmatcher::SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize) (src/ORBmatcher.cc:256-357), the
+ * matcher constructed as ORBmatcher(nnratio, check_orientation) (:40).  prev_matched [npairs][capacity][2] (x, y) is
+ * updated in place (:349-352); matches12 [npairs][capacity] receives vnMatches12 (-1 = none; entries >= n1 are -1);
+ * nmatches [npairs] the return value. */
+SDORB_API int sdorb_search_for_initialization_batch(sdorb_handle* h, const sdorb_keypoint* kps1_un, const uint8_t* desc1,
+                                                    const int32_t* n1, const sdorb_keypoint* kps2_un, const uint8_t* desc2,
+                                                    const int32_t* n2, const sdorb_frame_grid* grid2, int npairs, int capacity,
+                                                    float* prev_matched, int window_size, float nnratio, int check_orientation,
+                                                    int32_t* matches12, int32_t* nmatches, int mem, void* stream);
+
+/* ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) (src/ORBmatcher.cc:946-1075) from the projection
+ * on.  The pose algebra of :955-987 stays with the caller (Eigen, double): per last-frame keypoint i it passes
+ * proj[i] = (u, v, invzc) as the floats of :983-987, flags_last[i] (bit 0: mvpMapPoints[i] is set and not an outlier,
+ * :966-971; bit 1: that map point has Observations() > 0) and desc_mp[i] = pMP->GetDescriptor(); mode = 1 for bForward,
+ * 2 for bBackward, 0 for neither (:962-963).  Current frame: undistorted keypoints, descriptors, u_right (mvuRight),
+ * occupied[i2] != 0 where mvpMapPoints[i2] is set with Observations() > 0 on entry (:1018-1020), its grid, bounds =
+ * {mnMinX, mnMaxX, mnMinY, mnMaxY}; scale_factors = mvScaleFactors (nlevels <= 32 host floats).
+ * assigned [npairs][capacity]: for every current-frame keypoint the last-frame index whose map point the call leaves in
+ * CurrentFrame.mvpMapPoints, -1 where the call sets none (or clears it in the rotation check); nmatches [npairs]. */
+typedef struct {
+  const sdorb_keypoint* kps_last;     /* LastFrame.mvKeys (octave) */
+  const sdorb_keypoint* kps_last_un;  /* LastFrame.mvKeysUn (angle) */
+  const float* proj;                  /* [npairs][capacity][3] */
+  const uint8_t* flags_last;          /* [npairs][capacity] */
+  const uint8_t* desc_mp;             /* [npairs][capacity][32] */
+  const int32_t* n_last;
+  const sdorb_keypoint* kps_cur_un;
+  const uint8_t* desc_cur;
+  const float* u_right_cur;           /* [npairs][capacity] */
+  const uint8_t* occupied_cur;        /* [npairs][capacity] */
+  const int32_t* n_cur;
+  sdorb_frame_grid grid_cur;
+  const float* scale_factors;         /* host pointer, nlevels entries */
+  int nlevels;
+  float bounds[4];
+  float th, mbf;
+  int mode, check_orientation;
+} sdorb_projection_search;
+SDORB_API int sdorb_search_by_projection_batch(sdorb_handle* h, const sdorb_projection_search* q, int npairs, int capacity,
+                                               int32_t* assigned, int32_t* nmatches, int mem, void* stream);
+
 /* ---- host helpers (pure CPU table arithmetic, usable without a CUDA device) ---- */
 /* BORDER_REFLECT_101 margin around a level (src/ORBextractor.cc:692-696), used by the C++ shim. */
 SDORB_API void sdorb_fill_border_reflect101(uint8_t* level_origin, int width, int height, size_t stride, int border);

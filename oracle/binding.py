@@ -64,6 +64,11 @@ def use_native():
     return True
 
 
+class FrameGrid(C.Structure):
+    _fields_ = [("cell_start", C.c_void_p), ("indices", C.c_void_p), ("mnMinX", C.c_float), ("mnMinY", C.c_float),
+                ("mfGridElementWidthInv", C.c_float), ("mfGridElementHeightInv", C.c_float)]
+
+
 _lib = None
 
 
@@ -111,6 +116,13 @@ def lib(path=None):
         L.orc_distinctive.argtypes = [vp, i, C.POINTER(i)]
         L.orc_distinctive.restype = i
         L.orc_distinctive_many.argtypes = [vp, vp, i, i, vp, vp]
+        L.orc_features_in_area.argtypes = [vp, C.POINTER(FrameGrid), f, f, f, i, i, vp]
+        L.orc_features_in_area.restype = i
+        L.orc_three_maxima.argtypes = [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+        L.orc_search_for_initialization.argtypes = [vp, vp, i, vp, vp, i, C.POINTER(FrameGrid), vp, i, f, i, vp]
+        L.orc_search_for_initialization.restype = i
+        L.orc_search_by_projection.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, C.POINTER(FrameGrid), vp, vp, f, f, i, i, vp]
+        L.orc_search_by_projection.restype = i
     return _lib
 
 
@@ -337,3 +349,57 @@ def image_bounds(cols, rows, K4, dist):
     b = np.zeros(4, np.float32)
     lib().orc_image_bounds(cols, rows, _p(K4), _p(dist), len(dist), _p(b))
     return b
+
+
+def _grid(cell_start, indices, min_x, min_y, inv_w, inv_h):
+    cs = np.ascontiguousarray(cell_start, np.int32)
+    ix = np.ascontiguousarray(indices, np.int32)
+    if len(ix) == 0:
+        ix = np.zeros(1, np.int32)
+    return FrameGrid(_p(cs), _p(ix), min_x, min_y, inv_w, inv_h), (cs, ix)
+
+
+def features_in_area(kps_un, grid, x, y, r, min_level, max_level=-1):
+    """Frame::GetFeaturesInArea; grid = (cell_start, indices, min_x, min_y, inv_w, inv_h)."""
+    k = np.ascontiguousarray(kps_un, KP_DTYPE)
+    g, keep = _grid(*grid)
+    out = np.zeros(max(len(k), 1), np.int32)
+    n = lib().orc_features_in_area(_p(k), C.byref(g), x, y, r, min_level, max_level, _p(out))
+    return out[:n]
+
+
+def three_maxima(sizes):
+    s = np.ascontiguousarray(sizes, np.int32)
+    a, b, c = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+    lib().orc_three_maxima(_p(s), len(s), C.byref(a), C.byref(b), C.byref(c))
+    return a.value, b.value, c.value
+
+
+def search_for_initialization(kps1_un, desc1, kps2_un, desc2, grid2, prev_matched, window_size=100, nnratio=0.9,
+                              check_orientation=True):
+    """ORBmatcher::SearchForInitialization: returns (nmatches, matches12, prev_matched_updated)."""
+    k1, k2 = np.ascontiguousarray(kps1_un, KP_DTYPE), np.ascontiguousarray(kps2_un, KP_DTYPE)
+    d1, d2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    g, keep = _grid(*grid2)
+    prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = lib().orc_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), C.byref(g), _p(prev), window_size,
+                                            nnratio, int(check_orientation), _p(m12))
+    return n, m12[:len(k1)], prev
+
+
+def search_by_projection(kps_last, kps_last_un, proj, flags_last, desc_mp, kps_cur_un, desc_cur, u_right_cur, occupied_cur,
+                         grid_cur, scale_factors, bounds, th, mbf, mode, check_orientation=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) from the projection on: (nmatches, assigned)."""
+    kl, klu = np.ascontiguousarray(kps_last, KP_DTYPE), np.ascontiguousarray(kps_last_un, KP_DTYPE)
+    kc = np.ascontiguousarray(kps_cur_un, KP_DTYPE)
+    pr = np.ascontiguousarray(proj, np.float32).reshape(-1, 3)
+    fl, oc = np.ascontiguousarray(flags_last, np.uint8), np.ascontiguousarray(occupied_cur, np.uint8)
+    dm, dc = np.ascontiguousarray(desc_mp, np.uint8), np.ascontiguousarray(desc_cur, np.uint8)
+    ur = np.ascontiguousarray(u_right_cur, np.float32)
+    sf, bd = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(bounds, np.float32)
+    g, keep = _grid(*grid_cur)
+    asg = np.full(max(len(kc), 1), -1, np.int32)
+    n = lib().orc_search_by_projection(_p(kl), _p(klu), _p(pr), _p(fl), _p(dm), len(kl), _p(kc), _p(dc), _p(ur), _p(oc), len(kc),
+                                       C.byref(g), _p(sf), _p(bd), th, mbf, mode, int(check_orientation), _p(asg))
+    return n, asg[:len(kc)]

@@ -905,6 +905,211 @@ void orc_match_many(const uint8_t* A, const int32_t* nA, const uint8_t* B, const
                 out + (size_t)p * strideA_rows, false);
   });
 }
+// ---------------------------------------------------------------------------------------------- guided matchers
+// Frame::GetFeaturesInArea, /root/reference/src/Frame.cc:271-321.
+static std::vector<int> features_in_area(const orc_keypoint* kps, const orc_frame_grid& G, float x, float y, float r, int minLevel,
+                                         int maxLevel) {
+  const int COLS = 64, ROWS = 48;
+  std::vector<int> vIndices;
+  const int nMinCellX = std::max(0, (int)std::floor((x - G.mnMinX - r) * G.mfGridElementWidthInv));
+  if (nMinCellX >= COLS) return vIndices;
+  const int nMaxCellX = std::min(COLS - 1, (int)std::ceil((x - G.mnMinX + r) * G.mfGridElementWidthInv));
+  if (nMaxCellX < 0) return vIndices;
+  const int nMinCellY = std::max(0, (int)std::floor((y - G.mnMinY - r) * G.mfGridElementHeightInv));
+  if (nMinCellY >= ROWS) return vIndices;
+  const int nMaxCellY = std::min(ROWS - 1, (int)std::ceil((y - G.mnMinY + r) * G.mfGridElementHeightInv));
+  if (nMaxCellY < 0) return vIndices;
+  const bool bCheckLevels = (minLevel > 0) || (maxLevel >= 0);
+  for (int ix = nMinCellX; ix <= nMaxCellX; ix++) {
+    for (int iy = nMinCellY; iy <= nMaxCellY; iy++) {
+      const int c = ix * ROWS + iy;
+      for (int j = G.cell_start[c]; j < G.cell_start[c + 1]; j++) {
+        const orc_keypoint& kpUn = kps[G.indices[j]];
+        if (bCheckLevels) {
+          if (kpUn.octave < minLevel) continue;
+          if (maxLevel >= 0)
+            if (kpUn.octave > maxLevel) continue;
+        }
+        const float distx = kpUn.x - x;
+        const float disty = kpUn.y - y;
+        if (std::fabs(distx) < r && std::fabs(disty) < r) vIndices.push_back(G.indices[j]);
+      }
+    }
+  }
+  return vIndices;
+}
+int orc_features_in_area(const orc_keypoint* kps_un, const orc_frame_grid* grid, float x, float y, float r, int minLevel,
+                         int maxLevel, int32_t* out) {
+  const std::vector<int> v = features_in_area(kps_un, *grid, x, y, r, minLevel, maxLevel);
+  std::copy(v.begin(), v.end(), out);
+  return (int)v.size();
+}
+// ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:1423-1454.
+void orc_three_maxima(const int32_t* sizes, int L, int* ind1, int* ind2, int* ind3) {
+  int max1 = 0, max2 = 0, max3 = 0;
+  for (int i = 0; i < L; i++) {
+    const int s = sizes[i];
+    if (s > max1) {
+      max3 = max2;
+      max2 = max1;
+      max1 = s;
+      *ind3 = *ind2;
+      *ind2 = *ind1;
+      *ind1 = i;
+    } else if (s > max2) {
+      max3 = max2;
+      max2 = s;
+      *ind3 = *ind2;
+      *ind2 = i;
+    } else if (s > max3) {
+      max3 = s;
+      *ind3 = i;
+    }
+  }
+  if (max2 < 0.1f * (float)max1) {
+    *ind2 = -1;
+    *ind3 = -1;
+  } else if (max3 < 0.1f * (float)max1) {
+    *ind3 = -1;
+  }
+}
+static const int kHistoLength = 30, kThHigh = 100, kThLow = 50;  // src/ORBmatcher.cc:36-38
+static int rotation_bin(float a1, float a2) {  // src/ORBmatcher.cc:316-322, 1042-1048
+  const float factor = 1.0f / kHistoLength;
+  float rot = a1 - a2;
+  if (rot < 0.0) rot += 360.0f;
+  int bin = (int)std::round(rot * factor);
+  if (bin == kHistoLength) bin = 0;
+  return bin;
+}
+// ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:256-357.
+int orc_search_for_initialization(const orc_keypoint* k1, const uint8_t* d1s, int n1, const orc_keypoint* k2, const uint8_t* d2s,
+                                  int n2, const orc_frame_grid* grid2, float* prev, int windowSize, float mfNNratio,
+                                  int mbCheckOrientation, int32_t* vnMatches12) {
+  int nmatches = 0;
+  std::fill(vnMatches12, vnMatches12 + n1, -1);
+  std::vector<std::vector<int>> rotHist(kHistoLength);
+  std::vector<int> vMatchedDistance((size_t)n2, INT_MAX), vnMatches21((size_t)n2, -1);
+  for (int i1 = 0; i1 < n1; i1++) {
+    const int level1 = k1[i1].octave;
+    if (level1 > 0) continue;
+    const std::vector<int> vIndices2 = features_in_area(k2, *grid2, prev[2 * i1], prev[2 * i1 + 1], (float)windowSize, level1, level1);
+    if (vIndices2.empty()) continue;
+    const uint8_t* d1 = d1s + (size_t)i1 * 32;
+    int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+    for (int i2 : vIndices2) {
+      const int dist = descriptor_distance(d1, d2s + (size_t)i2 * 32);
+      if (vMatchedDistance[i2] <= dist) continue;
+      if (dist < bestDist) {
+        bestDist2 = bestDist;
+        bestDist = dist;
+        bestIdx2 = i2;
+      } else if (dist < bestDist2) {
+        bestDist2 = dist;
+      }
+    }
+    if (bestDist <= kThLow) {
+      if (bestDist < (float)bestDist2 * mfNNratio) {
+        if (vnMatches21[bestIdx2] >= 0) {
+          vnMatches12[vnMatches21[bestIdx2]] = -1;
+          nmatches--;
+        }
+        vnMatches12[i1] = bestIdx2;
+        vnMatches21[bestIdx2] = i1;
+        vMatchedDistance[bestIdx2] = bestDist;
+        nmatches++;
+        if (mbCheckOrientation) rotHist[rotation_bin(k1[i1].angle, k2[bestIdx2].angle)].push_back(i1);
+      }
+    }
+  }
+  if (mbCheckOrientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    int32_t sizes[kHistoLength];
+    for (int i = 0; i < kHistoLength; i++) sizes[i] = (int)rotHist[i].size();
+    orc_three_maxima(sizes, kHistoLength, &ind1, &ind2, &ind3);
+    for (int i = 0; i < kHistoLength; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i]) {
+        if (vnMatches12[idx1] >= 0) {
+          vnMatches12[idx1] = -1;
+          nmatches--;
+        }
+      }
+    }
+  }
+  for (int i1 = 0; i1 < n1; i1++)
+    if (vnMatches12[i1] >= 0) {
+      prev[2 * i1] = k2[vnMatches12[i1]].x;
+      prev[2 * i1 + 1] = k2[vnMatches12[i1]].y;
+    }
+  return nmatches;
+}
+// ORBmatcher::SearchByProjection(Frame &CurrentFrame, const Frame &LastFrame, th, bMono), src/ORBmatcher.cc:946-1075, from
+// the projection (u, v, invzc) on.  `ur = u - mbf*invzc` (:1024) is a multiply feeding a subtraction: GCC contracts it
+// into one fused multiply-add under the reference's -O3 -march=native (CMakeLists.txt:39-40), frozen here with fmaf.
+int orc_search_by_projection(const orc_keypoint* kL, const orc_keypoint* kLun, const float* proj, const uint8_t* flagsL,
+                             const uint8_t* descMP, int nL, const orc_keypoint* kC, const uint8_t* descC, const float* uRightC,
+                             const uint8_t* occupied_in, int nC, const orc_frame_grid* gridC, const float* mvScaleFactors,
+                             const float bounds[4], float th, float mbf, int mode, int mbCheckOrientation, int32_t* assigned) {
+  int nmatches = 0;
+  std::fill(assigned, assigned + nC, -1);
+  std::vector<uint8_t> occupiedC(occupied_in, occupied_in + nC);
+  std::vector<std::vector<int>> rotHist(kHistoLength);
+  const bool bForward = mode == 1, bBackward = mode == 2;
+  for (int i = 0; i < nL; i++) {
+    if (!(flagsL[i] & 1)) continue;  // pMP && !mvbOutlier[i]
+    const float u = proj[3 * i], v = proj[3 * i + 1], invzc = proj[3 * i + 2];
+    if (invzc < 0) continue;
+    if (u < bounds[0] || u > bounds[1]) continue;
+    if (v < bounds[2] || v > bounds[3]) continue;
+    const int nLastOctave = kL[i].octave;
+    const float radius = th * mvScaleFactors[nLastOctave];
+    std::vector<int> vIndices2;
+    if (bForward)
+      vIndices2 = features_in_area(kC, *gridC, u, v, radius, nLastOctave, -1);
+    else if (bBackward)
+      vIndices2 = features_in_area(kC, *gridC, u, v, radius, 0, nLastOctave);
+    else
+      vIndices2 = features_in_area(kC, *gridC, u, v, radius, nLastOctave - 1, nLastOctave + 1);
+    if (vIndices2.empty()) continue;
+    const uint8_t* dMP = descMP + (size_t)i * 32;
+    int bestDist = 256, bestIdx2 = -1;
+    for (int i2 : vIndices2) {
+      if (occupiedC[i2]) continue;  // mvpMapPoints[i2] && Observations() > 0
+      if (uRightC[i2] > 0) {
+        const float ur = fmaf(-mbf, invzc, u);
+        const float er = std::fabs(ur - uRightC[i2]);
+        if (er > radius) continue;
+      }
+      const int dist = descriptor_distance(dMP, descC + (size_t)i2 * 32);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx2 = i2;
+      }
+    }
+    if (bestDist <= kThHigh) {
+      assigned[bestIdx2] = i;                        // CurrentFrame.mvpMapPoints[bestIdx2] = pMP
+      occupiedC[bestIdx2] = (flagsL[i] & 2) ? 1 : 0;  // what a later candidate test (:1018-1020) sees for it
+      nmatches++;
+      if (mbCheckOrientation) rotHist[rotation_bin(kLun[i].angle, kC[bestIdx2].angle)].push_back(bestIdx2);
+    }
+  }
+  if (mbCheckOrientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    int32_t sizes[kHistoLength];
+    for (int i = 0; i < kHistoLength; i++) sizes[i] = (int)rotHist[i].size();
+    orc_three_maxima(sizes, kHistoLength, &ind1, &ind2, &ind3);
+    for (int i = 0; i < kHistoLength; i++) {
+      if (i != ind1 && i != ind2 && i != ind3) {
+        for (int idx : rotHist[i]) {
+          assigned[idx] = -1;  // mvpMapPoints[idx] = NULL
+          nmatches--;
+        }
+      }
+    }
+  }
+  return nmatches;
+}
 // MapPoint::ComputeDistinctiveDescriptors, /root/reference/src/MapPoint.cc:252-275: all pairwise distances of the N
 // observed descriptors (float matrix), per row std::sort and the element at index 0.5*(N-1) as median, the FIRST row
 // with the smallest median wins.

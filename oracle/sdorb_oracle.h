@@ -139,6 +139,37 @@ void orc_image_bounds(int cols, int rows, const float K[4], const float* dist, i
 void orc_stereo_from_rgbd(const orc_keypoint* kps, const orc_keypoint* kps_un, int n, const float* depth, int width, float mbf,
                           float* u_right, float* z);
 
+
+/* ---- guided matchers (src/ORBmatcher.cc) on Frame::GetFeaturesInArea (src/Frame.cc:271-321) ---- */
+/* the Frame grid as orc_assign_grid leaves it, with the four Frame members the window query reads */
+typedef struct {
+  const int32_t* cell_start; /* 64*48+1 */
+  const int32_t* indices;
+  float mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv;
+} orc_frame_grid;
+/* Frame::GetFeaturesInArea (:271-321): indices of the keypoints inside the window, in the reference's order (cell
+ * columns outer, rows inner, push order inside a cell); returns the count (at most n written to out). */
+int orc_features_in_area(const orc_keypoint* kps_un, const orc_frame_grid* grid, float x, float y, float r, int minLevel,
+                         int maxLevel, int32_t* out);
+/* ORBmatcher::ComputeThreeMaxima (:1423-1454) on the bin sizes. */
+void orc_three_maxima(const int32_t* sizes, int L, int* ind1, int* ind2, int* ind3);
+/* ORBmatcher::SearchForInitialization (:256-357).  prev_matched: n1 (x, y) pairs, updated in place (:349-352);
+ * matches12: n1 entries; returns nmatches. */
+int orc_search_for_initialization(const orc_keypoint* kps1_un, const uint8_t* desc1, int n1, const orc_keypoint* kps2_un,
+                                  const uint8_t* desc2, int n2, const orc_frame_grid* grid2, float* prev_matched,
+                                  int window_size, float nnratio, int check_orientation, int32_t* matches12);
+/* ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (:946-1075) from the projection on: the caller supplies
+ * per keypoint i of the last frame the float triple (u, v, invzc) of :979-987 and flags (bit 0: the keypoint has a map
+ * point that is not an outlier, :968-971; bit 1: that map point has Observations() > 0), its map point's descriptor, and
+ * for the current frame mvuRight and `occupied` (mvpMapPoints[i2] && Observations() > 0 on entry, :1018-1020; the
+ * restatement tracks it as map points are assigned).  mode: 0 neither, 1 bForward, 2 bBackward (:962-963).  bounds = {mnMinX, mnMaxX, mnMinY, mnMaxY}.
+ * assigned[i2] = last-frame index whose map point ends up in mvpMapPoints[i2] through this call, else -1. */
+int orc_search_by_projection(const orc_keypoint* kps_last, const orc_keypoint* kps_last_un, const float* proj /* n x 3 */,
+                             const uint8_t* flags_last, const uint8_t* desc_mp, int n_last, const orc_keypoint* kps_cur_un,
+                             const uint8_t* desc_cur, const float* u_right_cur, const uint8_t* occupied_cur, int n_cur,
+                             const orc_frame_grid* grid_cur, const float* scale_factors, const float bounds[4], float th,
+                             float mbf, int mode, int check_orientation, int32_t* assigned);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,6 +41,19 @@ class _PyrView(C.Structure):
                 ("border", C.c_int)]
 
 
+class _FrameGrid(C.Structure):
+    _fields_ = [("cell_start", C.c_void_p), ("indices", C.c_void_p), ("min_x", C.c_float), ("min_y", C.c_float),
+                ("inv_w", C.c_float), ("inv_h", C.c_float)]
+
+
+class _ProjectionSearch(C.Structure):
+    _fields_ = [("kps_last", C.c_void_p), ("kps_last_un", C.c_void_p), ("proj", C.c_void_p), ("flags_last", C.c_void_p),
+                ("desc_mp", C.c_void_p), ("n_last", C.c_void_p), ("kps_cur_un", C.c_void_p), ("desc_cur", C.c_void_p),
+                ("u_right_cur", C.c_void_p), ("occupied_cur", C.c_void_p), ("n_cur", C.c_void_p), ("grid_cur", _FrameGrid),
+                ("scale_factors", C.c_void_p), ("nlevels", C.c_int), ("bounds", C.c_float * 4), ("th", C.c_float),
+                ("mbf", C.c_float), ("mode", C.c_int), ("check_orientation", C.c_int)]
+
+
 _lib = None
 
 
@@ -72,6 +85,9 @@ def lib():
     L.sdorb_assign_grid_batch.argtypes = [vp, vp, vp, i, i, f, f, f, f, vp, vp, i, vp]
     L.sdorb_undistort_keypoints_batch.argtypes = [vp, vp, vp, i, i, vp, vp, i, vp, i, vp]
     L.sdorb_host_image_bounds.argtypes = [i, i, vp, vp, i, vp]
+    L.sdorb_search_for_initialization_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(_FrameGrid), i, i, vp, i, f, i, vp, vp,
+                                                        i, vp]
+    L.sdorb_search_by_projection_batch.argtypes = [vp, C.POINTER(_ProjectionSearch), i, i, vp, vp, i, vp]
     L.sdorb_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i, i, vp, i, i, sz, sz, f, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
     L.sdorb_fill_border_reflect101.restype = None
@@ -293,16 +309,20 @@ class ORBextractor:
     # ---- Frame post-processing (src/Frame.cc:179-192, 323-332, 399-417)
     GRID_COLS, GRID_ROWS = 64, 48
 
-    def assign_grid_batch(self, keypoints_un, counts, min_x, min_y, inv_w, inv_h):
-        """Frame::AssignFeaturesToGrid for a batch (host arrays): returns (cell_start[F, 64*48+1], indices[F, cap])."""
-        kps = np.ascontiguousarray(keypoints_un)
-        nf, cap = kps.shape[0], kps.shape[1]
-        counts = np.ascontiguousarray(counts, np.int32)
-        cs = np.zeros((nf, self.GRID_COLS * self.GRID_ROWS + 1), np.int32)
-        idx = np.zeros((nf, cap), np.int32)
-        self._check(lib().sdorb_assign_grid_batch(self._h, _ptr(kps), _ptr(counts), nf, cap, min_x, min_y, inv_w, inv_h, _ptr(cs),
-                                                   _ptr(idx), MEM_HOST, None))
-        return cs, idx
+    def assign_grid_batch(self, keypoints_un, counts, min_x, min_y, inv_w, inv_h, cell_start=None, indices=None, device=False,
+                          stream=None):
+        """Frame::AssignFeaturesToGrid for a batch: returns (cell_start[F, 64*48+1], indices[F, cap]).  Host arrays, or with
+        device=True torch tensors on the handle's GPU (keypoints [F, cap, 7] float32, outputs int32, caller-allocated)."""
+        if not device:
+            keypoints_un = np.ascontiguousarray(keypoints_un)
+            counts = np.ascontiguousarray(counts, np.int32)
+            cell_start = np.zeros((keypoints_un.shape[0], self.GRID_COLS * self.GRID_ROWS + 1), np.int32)
+            indices = np.zeros(keypoints_un.shape[:2], np.int32)
+        nf, cap = keypoints_un.shape[0], keypoints_un.shape[1]
+        self._check(lib().sdorb_assign_grid_batch(self._h, _ptr(keypoints_un), _ptr(counts), nf, cap, min_x, min_y, inv_w, inv_h,
+                                                   _ptr(cell_start), _ptr(indices), MEM_DEVICE if device else MEM_HOST,
+                                                   C.c_void_p(stream) if stream else None))
+        return cell_start, indices
 
     def undistort_keypoints_batch(self, keypoints, counts, K4, dist):
         """Frame::UndistortKeyPoints for a batch (host arrays); K4 = (fx, fy, cx, cy), dist = (k1, k2, p1, p2[, k3])."""
@@ -325,6 +345,57 @@ class ORBextractor:
                                                         depth.shape[1], depth.shape[2], depth.shape[1] * depth.shape[2], mbf,
                                                         _ptr(ur), _ptr(z), MEM_HOST, None))
         return ur, z
+
+    # ---- guided matchers (ORBmatcher::SearchForInitialization / SearchByProjection(Frame, Frame)), host arrays
+    def search_for_initialization_batch(self, kps1_un, desc1, n1, kps2_un, desc2, n2, grid2, prev_matched, window_size=100,
+                                        nnratio=0.9, check_orientation=True, matches12=None, nmatches=None, device=False,
+                                        stream=None):
+        """grid2 = (cell_start[P, 3073], indices[P, cap], min_x, min_y, inv_w, inv_h) of the second frames (assign_grid_batch).
+        Returns (nmatches[P], matches12[P, cap], prev_matched[P, cap, 2] updated).  Host arrays (prev_matched is copied), or
+        with device=True torch tensors on the handle's GPU: prev_matched is updated in place, matches12 / nmatches are the
+        caller's int32 tensors."""
+        if not device:
+            kps1_un, kps2_un = np.ascontiguousarray(kps1_un), np.ascontiguousarray(kps2_un)
+            desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+            n1, n2 = np.ascontiguousarray(n1, np.int32), np.ascontiguousarray(n2, np.int32)
+            cs, ix = np.ascontiguousarray(grid2[0], np.int32), np.ascontiguousarray(grid2[1], np.int32)
+            prev_matched = np.array(prev_matched, np.float32).reshape(kps1_un.shape[0], kps1_un.shape[1], 2).copy()
+            matches12 = np.zeros(kps1_un.shape[:2], np.int32)
+            nmatches = np.zeros(kps1_un.shape[0], np.int32)
+        else:
+            cs, ix = grid2[0], grid2[1]
+        P, cap = kps1_un.shape[0], kps1_un.shape[1]
+        g = _FrameGrid(_ptr(cs), _ptr(ix), *[float(v) for v in grid2[2:6]])
+        self._check(lib().sdorb_search_for_initialization_batch(
+            self._h, _ptr(kps1_un), _ptr(desc1), _ptr(n1), _ptr(kps2_un), _ptr(desc2), _ptr(n2), C.byref(g), P, cap,
+            _ptr(prev_matched), int(window_size), float(nnratio), int(check_orientation), _ptr(matches12), _ptr(nmatches),
+            MEM_DEVICE if device else MEM_HOST, C.c_void_p(stream) if stream else None))
+        return nmatches, matches12, prev_matched
+
+    def search_by_projection_batch(self, kps_last, kps_last_un, proj, flags_last, desc_mp, n_last, kps_cur_un, desc_cur,
+                                   u_right_cur, occupied_cur, n_cur, grid_cur, scale_factors, bounds, th, mbf, mode,
+                                   check_orientation=True):
+        """Returns (nmatches[P], assigned[P, cap]); see sdorb_search_by_projection_batch in include/sdorb.h."""
+        kl, klu, kc = np.ascontiguousarray(kps_last), np.ascontiguousarray(kps_last_un), np.ascontiguousarray(kps_cur_un)
+        P, cap = kl.shape[0], kl.shape[1]
+        keep = [np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(flags_last, np.uint8),
+                np.ascontiguousarray(desc_mp, np.uint8), np.ascontiguousarray(n_last, np.int32),
+                np.ascontiguousarray(desc_cur, np.uint8), np.ascontiguousarray(u_right_cur, np.float32),
+                np.ascontiguousarray(occupied_cur, np.uint8), np.ascontiguousarray(n_cur, np.int32),
+                np.ascontiguousarray(grid_cur[0], np.int32), np.ascontiguousarray(grid_cur[1], np.int32),
+                np.ascontiguousarray(scale_factors, np.float32)]
+        q = _ProjectionSearch()
+        q.kps_last, q.kps_last_un, q.kps_cur_un = _ptr(kl), _ptr(klu), _ptr(kc)
+        q.proj, q.flags_last, q.desc_mp, q.n_last = _ptr(keep[0]), _ptr(keep[1]), _ptr(keep[2]), _ptr(keep[3])
+        q.desc_cur, q.u_right_cur, q.occupied_cur, q.n_cur = _ptr(keep[4]), _ptr(keep[5]), _ptr(keep[6]), _ptr(keep[7])
+        q.grid_cur = _FrameGrid(_ptr(keep[8]), _ptr(keep[9]), *[float(v) for v in grid_cur[2:6]])
+        q.scale_factors, q.nlevels = _ptr(keep[10]), len(keep[10])
+        q.bounds = (C.c_float * 4)(*[float(v) for v in bounds])
+        q.th, q.mbf, q.mode, q.check_orientation = float(th), float(mbf), int(mode), int(check_orientation)
+        asg = np.zeros((P, cap), np.int32)
+        nm = np.zeros(P, np.int32)
+        self._check(lib().sdorb_search_by_projection_batch(self._h, C.byref(q), P, cap, _ptr(asg), _ptr(nm), MEM_HOST, None))
+        return nm, asg
 
     # ---- instrumentation
     def set_profiling(self, on):

@@ -66,6 +66,39 @@ void launch_undistort(const void* kps, const int32_t* counts, int nframes, int c
 void host_image_bounds(int cols, int rows, const float K[4], const float* dist, int ndist, float bounds[4]);
 int configure_frame_kernels();
 
+// Guided matchers (kernels_search.cu); all pointers are device pointers, arrays are [npairs][capacity] slabs.
+struct SearchGrid {
+  const int32_t* cell_start;  // [npairs][64*48+1]  CSR grid of the searched frame (launch_assign_grid)
+  const int32_t* indices;     // [npairs][capacity]
+  float min_x, min_y, inv_w, inv_h;  // mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv
+};
+struct SearchInitArgs {  // ORBmatcher::SearchForInitialization
+  const void* kps1;  const uint8_t* desc1;  const int32_t* n1;   // F1: mvKeysUn, mDescriptors, N
+  const void* kps2;  const uint8_t* desc2;  const int32_t* n2;   // F2
+  SearchGrid grid;       // of F2
+  float* prev_matched;   // [npairs][capacity][2], in / out
+  int32_t* matches12;    // [npairs][capacity]
+  int32_t* nmatches;     // [npairs]
+  int capacity, window_size, th_low, check_orientation;
+  float nnratio;
+};
+struct SearchProjArgs {  // ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) from the projection on
+  const void* kps_last;  const void* kps_last_un;  const float* proj;  const uint8_t* flags_last;  const uint8_t* desc_mp;
+  const int32_t* n_last;
+  const void* kps_cur_un;  const uint8_t* desc_cur;  const float* u_right_cur;  const uint8_t* occupied_cur;  const int32_t* n_cur;
+  SearchGrid grid;      // of the current frame
+  int32_t* assigned;    // [npairs][capacity]
+  int32_t* nmatches;    // [npairs]
+  int capacity, mode, th_high, check_orientation;
+  float th, mbf, min_x, max_x, min_y, max_y;
+  float scale_factors[SDORB_MAX_LEVELS];
+};
+void launch_search_init(const SearchInitArgs& a, int npairs, cudaStream_t s);
+void launch_search_projection(const SearchProjArgs& a, int npairs, cudaStream_t s);
+size_t search_init_smem(int capacity);
+size_t search_projection_smem(int capacity);
+int configure_search_kernels();
+
 size_t select_smem_bytes(const FrameGeom& g);
 int configure_kernels();  // one-time cudaFuncSetAttribute calls; returns cudaError_t as int
 

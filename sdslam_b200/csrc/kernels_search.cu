@@ -1,0 +1,387 @@
+// kernels_search.cu -- the guided matchers either side of DescriptorDistance, for sm_100a.
+//
+// Reference: /root/reference/src/ORBmatcher.cc
+//   SearchForInitialization              :256-357
+//   SearchByProjection(Frame&, Frame&)   :946-1075   (from the projection (u, v, invzc) on; the pose algebra stays with the caller)
+//   ComputeThreeMaxima                   :1423-1454
+// and the window query both of them run per keypoint, Frame::GetFeaturesInArea, src/Frame.cc:271-321, over the CSR grid
+// that sdorb_assign_grid_batch leaves on the device.
+//
+// Both matchers are greedy over the query keypoints IN ORDER: an accepted match changes what later queries may take
+// (vMatchedDistance / vnMatches21, mvpMapPoints of the current frame).  That order is the result, so one warp owns one
+// frame pair and walks its queries sequentially; the parallelism is the batch (thousands of pairs in flight) and, inside
+// a query, the candidates of the window: the grid columns of the window are contiguous index spans of the CSR grid, the
+// lanes flatten them with a prefix sum and take candidates k, k+32, ... ; (distance << 16 | k) min-reduced over the warp
+// keeps the reference's "first minimum in candidate order" rule, the runner-up is merged alongside.
+#include "kernels.cuh"
+#include "match_common.cuh"
+
+namespace sdorb {
+
+constexpr int GRID_COLS = 64, GRID_ROWS = 48;
+constexpr int HISTO_LENGTH = 30;  // src/ORBmatcher.cc:38
+constexpr int DIST_NONE = 0x7FFF;  // stands for INT_MAX in the packed (distance << 16 | candidate) words
+
+struct KP {  // cv::KeyPoint, 28 bytes
+  float x, y, size, angle, response;
+  int32_t octave, class_id;
+};
+
+// Frame::GetFeaturesInArea's cell window (src/Frame.cc:275-291); false = the reference returns an empty vector
+__device__ __forceinline__ bool area_cells(float x, float y, float r, const SearchGrid& g, int& x0, int& x1, int& y0, int& y1) {
+  x0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(x, g.min_x), r), g.inv_w)));
+  if (x0 >= GRID_COLS) return false;
+  x1 = min(GRID_COLS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(x, g.min_x), r), g.inv_w)));
+  if (x1 < 0) return false;
+  y0 = max(0, (int)floorf(__fmul_rn(__fsub_rn(__fsub_rn(y, g.min_y), r), g.inv_h)));
+  if (y0 >= GRID_ROWS) return false;
+  y1 = min(GRID_ROWS - 1, (int)ceilf(__fmul_rn(__fadd_rn(__fsub_rn(y, g.min_y), r), g.inv_h)));
+  if (y1 < 0) return false;
+  return true;
+}
+
+// The window's candidates in the reference's order are, per grid column ix, the contiguous span
+// indices[cell_start[ix*48 + y0] .. cell_start[ix*48 + y1 + 1]).  Fills s_begin[c] / s_prefix[c] for the columns and returns the total.
+__device__ __forceinline__ int window_spans(const int32_t* __restrict__ cs, int x0, int x1, int y0, int y1, int lane, int* s_begin,
+                                            int* s_prefix) {
+  const int ncols = x1 - x0 + 1;
+  int total = 0;
+  for (int c0 = 0; c0 < ncols; c0 += 32) {
+    const int c = c0 + lane;
+    int b = 0, len = 0;
+    if (c < ncols) {
+      b = cs[(x0 + c) * GRID_ROWS + y0];
+      len = cs[(x0 + c) * GRID_ROWS + y1 + 1] - b;
+    }
+    int incl = len;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (c < ncols) {
+      s_begin[c] = b;
+      s_prefix[c] = total + incl - len;
+    }
+    total += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  if (lane == 0) s_prefix[ncols] = total;
+  __syncwarp();
+  return total;
+}
+
+// position in `indices` of candidate k
+__device__ __forceinline__ int candidate_slot(int k, int ncols, const int* s_begin, const int* s_prefix) {
+  int lo = 0, hi = ncols - 1;  // largest c with s_prefix[c] <= k
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (s_prefix[mid] <= k) lo = mid;
+    else hi = mid - 1;
+  }
+  return s_begin[lo] + (k - s_prefix[lo]);
+}
+
+// the two smallest distances of the warp's candidates; first candidate on ties
+__device__ __forceinline__ void warp_best2(int& best1, int& best2) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const int ob1 = __shfl_xor_sync(0xffffffffu, best1, o), ob2 = __shfl_xor_sync(0xffffffffu, best2, o);
+    const int lo1 = min(best1, ob1), hi1 = max(best1, ob1);
+    best2 = min(min(best2, ob2), hi1 >> 16);
+    best1 = lo1;
+  }
+}
+
+__device__ __forceinline__ int rotation_bin(float a1, float a2) {  // src/ORBmatcher.cc:316-322
+  const float factor = 1.0f / HISTO_LENGTH;
+  float rot = __fsub_rn(a1, a2);
+  if (rot < 0.0f) rot = __fadd_rn(rot, 360.0f);
+  int bin = (int)roundf(__fmul_rn(rot, factor));
+  if (bin == HISTO_LENGTH) bin = 0;
+  return bin;
+}
+
+// ComputeThreeMaxima, src/ORBmatcher.cc:1423-1454; returns a 30-bit mask of the bins that survive
+__device__ __forceinline__ uint32_t three_maxima_mask(const int* histo) {
+  int max1 = 0, max2 = 0, max3 = 0, ind1 = -1, ind2 = -1, ind3 = -1;
+  for (int i = 0; i < HISTO_LENGTH; i++) {
+    const int s = histo[i];
+    if (s > max1) {
+      max3 = max2;
+      max2 = max1;
+      max1 = s;
+      ind3 = ind2;
+      ind2 = ind1;
+      ind1 = i;
+    } else if (s > max2) {
+      max3 = max2;
+      max2 = s;
+      ind3 = ind2;
+      ind2 = i;
+    } else if (s > max3) {
+      max3 = s;
+      ind3 = i;
+    }
+  }
+  if ((float)max2 < __fmul_rn(0.1f, (float)max1)) {
+    ind2 = -1;
+    ind3 = -1;
+  } else if ((float)max3 < __fmul_rn(0.1f, (float)max1)) {
+    ind3 = -1;
+  }
+  uint32_t m = 0;
+  if (ind1 >= 0) m |= 1u << ind1;
+  if (ind2 >= 0) m |= 1u << ind2;
+  if (ind3 >= 0) m |= 1u << ind3;
+  return m;
+}
+
+__device__ __forceinline__ void load_desc(const uint8_t* d, uint32_t (&q)[8]) {
+  const uint4 lo = reinterpret_cast<const uint4*>(d)[0], hi = reinterpret_cast<const uint4*>(d)[1];
+  q[0] = lo.x; q[1] = lo.y; q[2] = lo.z; q[3] = lo.w;
+  q[4] = hi.x; q[5] = hi.y; q[6] = hi.z; q[7] = hi.w;
+}
+
+// ---------------------------------------------------------------------------------------- SearchForInitialization
+// shared memory per pair: vMatchedDistance[cap] (int), vnMatches21[cap] (int), rotation bin of every query (int8), spans
+__global__ void __launch_bounds__(32) search_init_kernel(SearchInitArgs a) {
+  extern __shared__ int s_mem[];
+  const int pair = blockIdx.x, lane = threadIdx.x, cap = a.capacity;
+  int* s_dist = s_mem;              // vMatchedDistance
+  int* s_m21 = s_mem + cap;         // vnMatches21
+  int* s_begin = s_m21 + cap;       // [64]
+  int* s_prefix = s_begin + GRID_COLS;  // [65]
+  int* s_histo = s_prefix + GRID_COLS + 1;  // [30] (+2 pad)
+  int8_t* s_bin = reinterpret_cast<int8_t*>(s_histo + 32);  // [cap]
+  const int n1 = min(a.n1[pair], cap), n2 = min(a.n2[pair], cap);
+  const KP* k1 = reinterpret_cast<const KP*>(a.kps1) + (int64_t)pair * cap;
+  const KP* k2 = reinterpret_cast<const KP*>(a.kps2) + (int64_t)pair * cap;
+  const uint8_t* d1 = a.desc1 + (int64_t)pair * cap * 32;
+  const uint8_t* d2 = a.desc2 + (int64_t)pair * cap * 32;
+  const int32_t* cs = a.grid.cell_start + (int64_t)pair * (GRID_COLS * GRID_ROWS + 1);
+  const int32_t* idx = a.grid.indices + (int64_t)pair * cap;
+  float* prev = a.prev_matched + (int64_t)pair * cap * 2;
+  int32_t* m12 = a.matches12 + (int64_t)pair * cap;
+  for (int i = lane; i < n2; i += 32) {
+    s_dist[i] = INT_MAX;
+    s_m21[i] = -1;
+  }
+  for (int i = lane; i < cap; i += 32) {
+    m12[i] = -1;
+    if (i < n1) s_bin[i] = -1;
+  }
+  if (lane < 32) s_histo[lane] = 0;
+  __syncwarp();
+  int nmatches = 0;  // lane 0's copy counts
+  const float r = (float)a.window_size;
+  for (int i1 = 0; i1 < n1; ++i1) {
+    const int level1 = k1[i1].octave;
+    if (level1 > 0) continue;
+    const float x = prev[2 * i1], y = prev[2 * i1 + 1];
+    int x0, x1, y0, y1;
+    if (!area_cells(x, y, r, a.grid, x0, x1, y0, y1)) continue;
+    const int total = window_spans(cs, x0, x1, y0, y1, lane, s_begin, s_prefix);
+    uint32_t q[8];
+    load_desc(d1 + (int64_t)i1 * 32, q);
+    int best1 = (DIST_NONE << 16) | 0xFFFF, best2 = DIST_NONE;
+    for (int k = lane; k < total; k += 32) {
+      const int i2 = idx[candidate_slot(k, x1 - x0 + 1, s_begin, s_prefix)];
+      const KP kp = k2[i2];
+      // bCheckLevels is true (maxLevel = level1 >= 0): octave < level1 or > level1 is skipped (level1 <= 0 here)
+      if (kp.octave < level1 || kp.octave > level1) continue;
+      if (!(fabsf(__fsub_rn(kp.x, x)) < r && fabsf(__fsub_rn(kp.y, y)) < r)) continue;
+      uint32_t t[8];
+      load_desc(d2 + (int64_t)i2 * 32, t);
+      const uint4 lo = make_uint4(t[0], t[1], t[2], t[3]), hi = make_uint4(t[4], t[5], t[6], t[7]);
+      const int d = hamming256(q, lo, hi);
+      if (s_dist[i2] <= d) continue;
+      best2 = min(best2, max(d, best1 >> 16));
+      best1 = min(best1, (d << 16) | k);
+    }
+    warp_best2(best1, best2);
+    const int bestDist = best1 >> 16;
+    if (bestDist <= a.th_low) {  // also false when nothing was found (DIST_NONE)
+      const float second = best2 == DIST_NONE ? (float)INT_MAX : (float)best2;
+      if ((float)bestDist < __fmul_rn(second, a.nnratio)) {
+        if (lane == 0) {
+          const int bestIdx2 = idx[candidate_slot(best1 & 0xFFFF, x1 - x0 + 1, s_begin, s_prefix)];
+          const int old = s_m21[bestIdx2];
+          if (old >= 0) {
+            m12[old] = -1;
+            nmatches--;
+          }
+          m12[i1] = bestIdx2;
+          s_m21[bestIdx2] = i1;
+          s_dist[bestIdx2] = bestDist;
+          nmatches++;
+          if (a.check_orientation) {
+            const int bin = rotation_bin(k1[i1].angle, k2[bestIdx2].angle);
+            s_bin[i1] = (int8_t)bin;
+            s_histo[bin]++;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (a.check_orientation) {
+    const uint32_t keep = three_maxima_mask(s_histo);
+    int removed = 0;
+    for (int i = lane; i < n1; i += 32) {
+      const int bin = s_bin[i];
+      if (bin >= 0 && !((keep >> bin) & 1u) && m12[i] >= 0) {
+        m12[i] = -1;
+        removed++;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    nmatches -= removed;
+    __syncwarp();
+  }
+  for (int i = lane; i < n1; i += 32) {  // :349-352
+    const int m = m12[i];
+    if (m >= 0) {
+      prev[2 * i] = k2[m].x;
+      prev[2 * i + 1] = k2[m].y;
+    }
+  }
+  if (lane == 0) a.nmatches[pair] = nmatches;
+}
+
+size_t search_init_smem(int capacity) {
+  return sizeof(int) * ((size_t)2 * capacity + GRID_COLS + GRID_COLS + 1 + 32) + (size_t)capacity + 16;
+}
+
+// ---------------------------------------------------------------------------------------- SearchByProjection (Frame, Frame)
+// shared memory per pair: occupied[cap] (uint8), push bin / push index of every last-frame keypoint, spans
+__global__ void __launch_bounds__(32) search_projection_kernel(SearchProjArgs a) {
+  extern __shared__ int s_mem[];
+  const int pair = blockIdx.x, lane = threadIdx.x, cap = a.capacity;
+  int* s_push_idx = s_mem;               // [cap] bestIdx2 pushed into rotHist by last-frame keypoint i
+  int* s_begin = s_mem + cap;            // [64]
+  int* s_prefix = s_begin + GRID_COLS;   // [65]
+  int* s_histo = s_prefix + GRID_COLS + 1;   // [32]
+  int8_t* s_bin = reinterpret_cast<int8_t*>(s_histo + 32);  // [cap]
+  uint8_t* s_occ = reinterpret_cast<uint8_t*>(s_bin + cap);  // [cap]
+  const int nL = min(a.n_last[pair], cap), nC = min(a.n_cur[pair], cap);
+  const KP* kL = reinterpret_cast<const KP*>(a.kps_last) + (int64_t)pair * cap;
+  const KP* kLun = reinterpret_cast<const KP*>(a.kps_last_un) + (int64_t)pair * cap;
+  const KP* kC = reinterpret_cast<const KP*>(a.kps_cur_un) + (int64_t)pair * cap;
+  const float* proj = a.proj + (int64_t)pair * cap * 3;
+  const uint8_t* fl = a.flags_last + (int64_t)pair * cap;
+  const uint8_t* dMP = a.desc_mp + (int64_t)pair * cap * 32;
+  const uint8_t* dC = a.desc_cur + (int64_t)pair * cap * 32;
+  const float* uR = a.u_right_cur + (int64_t)pair * cap;
+  const int32_t* cs = a.grid.cell_start + (int64_t)pair * (GRID_COLS * GRID_ROWS + 1);
+  const int32_t* idx = a.grid.indices + (int64_t)pair * cap;
+  int32_t* assigned = a.assigned + (int64_t)pair * cap;
+  for (int i = lane; i < cap; i += 32) {
+    assigned[i] = -1;
+    s_bin[i] = -1;
+    s_occ[i] = i < nC ? a.occupied_cur[(int64_t)pair * cap + i] : 0;
+  }
+  s_histo[lane] = 0;
+  __syncwarp();
+  int nmatches = 0;
+  for (int i = 0; i < nL; ++i) {
+    const int flags = fl[i];
+    if (!(flags & 1)) continue;
+    const float u = proj[3 * i], v = proj[3 * i + 1], invzc = proj[3 * i + 2];
+    if (invzc < 0.f) continue;
+    if (u < a.min_x || u > a.max_x) continue;
+    if (v < a.min_y || v > a.max_y) continue;
+    const int oct = kL[i].octave;
+    const float radius = __fmul_rn(a.th, a.scale_factors[min(max(oct, 0), SDORB_MAX_LEVELS - 1)]);
+    int minLevel, maxLevel;
+    if (a.mode == 1) {
+      minLevel = oct;
+      maxLevel = -1;
+    } else if (a.mode == 2) {
+      minLevel = 0;
+      maxLevel = oct;
+    } else {
+      minLevel = oct - 1;
+      maxLevel = oct + 1;
+    }
+    int x0, x1, y0, y1;
+    if (!area_cells(u, v, radius, a.grid, x0, x1, y0, y1)) continue;
+    const int total = window_spans(cs, x0, x1, y0, y1, lane, s_begin, s_prefix);
+    const bool check_levels = minLevel > 0 || maxLevel >= 0;
+    uint32_t q[8];
+    load_desc(dMP + (int64_t)i * 32, q);
+    const float ur = __fmaf_rn(-a.mbf, invzc, u);  // u - mbf*invzc, contracted by the reference build (see the oracle)
+    int best1 = (256 << 16) | 0xFFFF;
+    for (int k = lane; k < total; k += 32) {
+      const int i2 = idx[candidate_slot(k, x1 - x0 + 1, s_begin, s_prefix)];
+      const KP kp = kC[i2];
+      if (check_levels) {
+        if (kp.octave < minLevel) continue;
+        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+      }
+      if (!(fabsf(__fsub_rn(kp.x, u)) < radius && fabsf(__fsub_rn(kp.y, v)) < radius)) continue;
+      if (s_occ[i2]) continue;
+      const float r2 = uR[i2];
+      if (r2 > 0.f) {
+        if (fabsf(__fsub_rn(ur, r2)) > radius) continue;
+      }
+      uint32_t t[8];
+      load_desc(dC + (int64_t)i2 * 32, t);
+      const uint4 lo = make_uint4(t[0], t[1], t[2], t[3]), hi = make_uint4(t[4], t[5], t[6], t[7]);
+      best1 = min(best1, (hamming256(q, lo, hi) << 16) | k);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) best1 = min(best1, __shfl_xor_sync(0xffffffffu, best1, o));
+    const int bestDist = best1 >> 16;
+    if (bestDist <= a.th_high && bestDist < 256) {
+      if (lane == 0) {
+        const int bestIdx2 = idx[candidate_slot(best1 & 0xFFFF, x1 - x0 + 1, s_begin, s_prefix)];
+        assigned[bestIdx2] = i;
+        s_occ[bestIdx2] = (flags & 2) ? 1 : 0;
+        nmatches++;
+        if (a.check_orientation) {
+          const int bin = rotation_bin(kLun[i].angle, kC[bestIdx2].angle);
+          s_bin[i] = (int8_t)bin;
+          s_push_idx[i] = bestIdx2;
+          s_histo[bin]++;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (a.check_orientation) {
+    const uint32_t keep = three_maxima_mask(s_histo);
+    int removed = 0;
+    for (int i = lane; i < nL; i += 32) {
+      const int bin = s_bin[i];
+      if (bin >= 0 && !((keep >> bin) & 1u)) {
+        assigned[s_push_idx[i]] = -1;  // every push of a removed bin clears its slot and is counted (:1064-1067)
+        removed++;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    nmatches -= removed;
+  }
+  if (lane == 0) a.nmatches[pair] = nmatches;
+}
+
+size_t search_projection_smem(int capacity) {
+  return sizeof(int) * ((size_t)capacity + GRID_COLS + GRID_COLS + 1 + 32) + (size_t)2 * capacity + 16;
+}
+
+int configure_search_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(search_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(search_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return (int)e;
+}
+
+void launch_search_init(const SearchInitArgs& a, int npairs, cudaStream_t s) {
+  search_init_kernel<<<npairs, 32, search_init_smem(a.capacity), s>>>(a);
+}
+void launch_search_projection(const SearchProjArgs& a, int npairs, cudaStream_t s) {
+  search_projection_kernel<<<npairs, 32, search_projection_smem(a.capacity), s>>>(a);
+}
+
+}  // namespace sdorb

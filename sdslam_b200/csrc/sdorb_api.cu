@@ -343,7 +343,7 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (cudaMemcpy(h->d_umax, h->tables.umax, sizeof(int) * 16, cudaMemcpyHostToDevice) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaMalloc(&h->d_error, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
   if (cudaMemset(h->d_error, 0, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_CUDA);
-  if (configure_kernels() != 0 || configure_frame_kernels() != 0) return fail(SDORB_ERR_CUDA);
+  if (configure_kernels() != 0 || configure_frame_kernels() != 0 || configure_search_kernels() != 0) return fail(SDORB_ERR_CUDA);
   *out = h;
   return SDORB_OK;
 }
@@ -834,6 +834,149 @@ int sdorb_assign_grid_batch(sdorb_handle* h, const sdorb_keypoint* kps, const in
   CU(cudaMemcpyAsync(cell_start, dS, bS, cudaMemcpyDeviceToHost, s));
   CU(cudaMemcpyAsync(indices, dI, bI, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  return SDORB_OK;
+}
+
+// ---- guided matchers -------------------------------------------------------------------------------------------------
+namespace {
+// Lays the host arrays of one call out in the handle's scratch buffer: sizes first, then copies.
+struct Stager {
+  struct Item { const void* host_in; void* host_out; size_t bytes, off; };
+  std::vector<Item> items;
+  size_t total = 0;
+  size_t add(const void* in, void* out, size_t bytes) {
+    items.push_back({in, out, bytes, total});
+    total += up256(bytes);
+    return items.size() - 1;
+  }
+  uint8_t* dev(sdorb_handle* h, size_t i) const { return (uint8_t*)h->d_match_buf + items[i].off; }
+  int upload(sdorb_handle* h, cudaStream_t s) {
+    int rc = ensure_match_buf(h, total);
+    if (rc) return rc;
+    for (auto& it : items)
+      if (it.host_in) CU(cudaMemcpyAsync((uint8_t*)h->d_match_buf + it.off, it.host_in, it.bytes, cudaMemcpyHostToDevice, s));
+    return SDORB_OK;
+  }
+  int download(sdorb_handle* h, cudaStream_t s) {
+    for (auto& it : items)
+      if (it.host_out) CU(cudaMemcpyAsync(it.host_out, (uint8_t*)h->d_match_buf + it.off, it.bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return SDORB_OK;
+  }
+};
+const int kSearchMaxCapacity = 16384;
+}  // namespace
+
+int sdorb_search_for_initialization_batch(sdorb_handle* h, const sdorb_keypoint* kps1, const uint8_t* desc1, const int32_t* n1,
+                                          const sdorb_keypoint* kps2, const uint8_t* desc2, const int32_t* n2,
+                                          const sdorb_frame_grid* grid2, int npairs, int capacity, float* prev_matched,
+                                          int window_size, float nnratio, int check_orientation, int32_t* matches12,
+                                          int32_t* nmatches, int mem, void* stream) {
+  if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (npairs == 0) return SDORB_OK;
+  if (!kps1 || !desc1 || !n1 || !kps2 || !desc2 || !n2 || !grid2 || !grid2->cell_start || !grid2->indices || !prev_matched ||
+      !matches12 || !nmatches || capacity <= 0 || capacity > kSearchMaxCapacity)
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  SearchInitArgs a;
+  a.capacity = capacity;
+  a.window_size = window_size;
+  a.th_low = 50;  // ORBmatcher::TH_LOW, src/ORBmatcher.cc:37
+  a.check_orientation = check_orientation ? 1 : 0;
+  a.nnratio = nnratio;
+  a.grid.min_x = grid2->min_x;
+  a.grid.min_y = grid2->min_y;
+  a.grid.inv_w = grid2->inv_w;
+  a.grid.inv_h = grid2->inv_h;
+  const size_t P = (size_t)npairs, C = (size_t)capacity, ncs = (size_t)SDORB_GRID_COLS * SDORB_GRID_ROWS + 1;
+  Stager st;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (((uintptr_t)desc1 | (uintptr_t)desc2) % 16) return SDORB_ERR_BAD_ARG;
+    a.kps1 = kps1; a.desc1 = desc1; a.n1 = n1; a.kps2 = kps2; a.desc2 = desc2; a.n2 = n2;
+    a.grid.cell_start = grid2->cell_start; a.grid.indices = grid2->indices;
+    a.prev_matched = prev_matched; a.matches12 = matches12; a.nmatches = nmatches;
+  } else {
+    const size_t iK1 = st.add(kps1, nullptr, sizeof(sdorb_keypoint) * P * C), iD1 = st.add(desc1, nullptr, 32 * P * C),
+                 iN1 = st.add(n1, nullptr, 4 * P), iK2 = st.add(kps2, nullptr, sizeof(sdorb_keypoint) * P * C),
+                 iD2 = st.add(desc2, nullptr, 32 * P * C), iN2 = st.add(n2, nullptr, 4 * P),
+                 iCS = st.add(grid2->cell_start, nullptr, 4 * ncs * P), iIX = st.add(grid2->indices, nullptr, 4 * P * C),
+                 iPM = st.add(prev_matched, prev_matched, 8 * P * C), iM = st.add(nullptr, matches12, 4 * P * C),
+                 iNM = st.add(nullptr, nmatches, 4 * P);
+    int rc = st.upload(h, s);
+    if (rc) return rc;
+    a.kps1 = (void*)st.dev(h, iK1); a.desc1 = (uint8_t*)st.dev(h, iD1); a.n1 = (int32_t*)st.dev(h, iN1);
+    a.kps2 = (void*)st.dev(h, iK2); a.desc2 = (uint8_t*)st.dev(h, iD2); a.n2 = (int32_t*)st.dev(h, iN2);
+    a.grid.cell_start = (int32_t*)st.dev(h, iCS); a.grid.indices = (int32_t*)st.dev(h, iIX);
+    a.prev_matched = (float*)st.dev(h, iPM); a.matches12 = (int32_t*)st.dev(h, iM); a.nmatches = (int32_t*)st.dev(h, iNM);
+  }
+  {
+    StageScope sc(h, s, SDORB_STAGE_MATCH);
+    launch_search_init(a, npairs, s);
+    sc.launched();
+  }
+  CU(cudaGetLastError());
+  if (mem == SDORB_MEM_HOST) return st.download(h, s);
+  return SDORB_OK;
+}
+
+int sdorb_search_by_projection_batch(sdorb_handle* h, const sdorb_projection_search* q, int npairs, int capacity, int32_t* assigned,
+                                     int32_t* nmatches, int mem, void* stream) {
+  if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (npairs == 0) return SDORB_OK;
+  if (!q || !q->kps_last || !q->kps_last_un || !q->proj || !q->flags_last || !q->desc_mp || !q->n_last || !q->kps_cur_un ||
+      !q->desc_cur || !q->u_right_cur || !q->occupied_cur || !q->n_cur || !q->grid_cur.cell_start || !q->grid_cur.indices ||
+      !q->scale_factors || q->nlevels <= 0 || q->nlevels > SDORB_MAX_LEVELS || q->mode < 0 || q->mode > 2 || !assigned ||
+      !nmatches || capacity <= 0 || capacity > kSearchMaxCapacity)
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  SearchProjArgs a;
+  a.capacity = capacity;
+  a.mode = q->mode;
+  a.th_high = 100;  // ORBmatcher::TH_HIGH, src/ORBmatcher.cc:36
+  a.check_orientation = q->check_orientation ? 1 : 0;
+  a.th = q->th;
+  a.mbf = q->mbf;
+  a.min_x = q->bounds[0]; a.max_x = q->bounds[1]; a.min_y = q->bounds[2]; a.max_y = q->bounds[3];
+  for (int l = 0; l < SDORB_MAX_LEVELS; ++l) a.scale_factors[l] = q->scale_factors[std::min(l, q->nlevels - 1)];
+  a.grid.min_x = q->grid_cur.min_x; a.grid.min_y = q->grid_cur.min_y;
+  a.grid.inv_w = q->grid_cur.inv_w; a.grid.inv_h = q->grid_cur.inv_h;
+  const size_t P = (size_t)npairs, C = (size_t)capacity, ncs = (size_t)SDORB_GRID_COLS * SDORB_GRID_ROWS + 1;
+  Stager st;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (((uintptr_t)q->desc_mp | (uintptr_t)q->desc_cur) % 16) return SDORB_ERR_BAD_ARG;
+    a.kps_last = q->kps_last; a.kps_last_un = q->kps_last_un; a.proj = q->proj; a.flags_last = q->flags_last;
+    a.desc_mp = q->desc_mp; a.n_last = q->n_last; a.kps_cur_un = q->kps_cur_un; a.desc_cur = q->desc_cur;
+    a.u_right_cur = q->u_right_cur; a.occupied_cur = q->occupied_cur; a.n_cur = q->n_cur;
+    a.grid.cell_start = q->grid_cur.cell_start; a.grid.indices = q->grid_cur.indices;
+    a.assigned = assigned; a.nmatches = nmatches;
+  } else {
+    const size_t bK = sizeof(sdorb_keypoint) * P * C;
+    const size_t iKL = st.add(q->kps_last, nullptr, bK), iKU = st.add(q->kps_last_un, nullptr, bK),
+                 iPR = st.add(q->proj, nullptr, 12 * P * C), iFL = st.add(q->flags_last, nullptr, P * C),
+                 iDM = st.add(q->desc_mp, nullptr, 32 * P * C), iNL = st.add(q->n_last, nullptr, 4 * P),
+                 iKC = st.add(q->kps_cur_un, nullptr, bK), iDC = st.add(q->desc_cur, nullptr, 32 * P * C),
+                 iUR = st.add(q->u_right_cur, nullptr, 4 * P * C), iOC = st.add(q->occupied_cur, nullptr, P * C),
+                 iNC = st.add(q->n_cur, nullptr, 4 * P), iCS = st.add(q->grid_cur.cell_start, nullptr, 4 * ncs * P),
+                 iIX = st.add(q->grid_cur.indices, nullptr, 4 * P * C), iAS = st.add(nullptr, assigned, 4 * P * C),
+                 iNM = st.add(nullptr, nmatches, 4 * P);
+    int rc = st.upload(h, s);
+    if (rc) return rc;
+    a.kps_last = (void*)st.dev(h, iKL); a.kps_last_un = (void*)st.dev(h, iKU); a.proj = (float*)st.dev(h, iPR);
+    a.flags_last = (uint8_t*)st.dev(h, iFL); a.desc_mp = (uint8_t*)st.dev(h, iDM); a.n_last = (int32_t*)st.dev(h, iNL);
+    a.kps_cur_un = (void*)st.dev(h, iKC); a.desc_cur = (uint8_t*)st.dev(h, iDC); a.u_right_cur = (float*)st.dev(h, iUR);
+    a.occupied_cur = (uint8_t*)st.dev(h, iOC); a.n_cur = (int32_t*)st.dev(h, iNC);
+    a.grid.cell_start = (int32_t*)st.dev(h, iCS); a.grid.indices = (int32_t*)st.dev(h, iIX);
+    a.assigned = (int32_t*)st.dev(h, iAS); a.nmatches = (int32_t*)st.dev(h, iNM);
+  }
+  {
+    StageScope sc(h, s, SDORB_STAGE_MATCH);
+    launch_search_projection(a, npairs, s);
+    sc.launched();
+  }
+  CU(cudaGetLastError());
+  if (mem == SDORB_MEM_HOST) return st.download(h, s);
   return SDORB_OK;
 }
 

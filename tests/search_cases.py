@@ -1,0 +1,267 @@
+"""Synthetic frame pairs for the guided matchers (ORBmatcher::SearchForInitialization / SearchByProjection(Frame, Frame),
+/root/reference/src/ORBmatcher.cc:256-357, 946-1075) and a direct Python restatement of both, written from the reference
+text on Python lists and a dict-of-lists grid (Frame::mGrid) -- deliberately sharing nothing with oracle/sdorb_oracle.cc.
+Used by tests/test_oracle_search.py (pins the oracle) and tests/test_gpu_search.py (kernels against the oracle)."""
+import math
+
+import numpy as np
+
+from oracle import binding as orc
+
+F32 = np.float32
+COLS, ROWS = 64, 48
+TH_HIGH, TH_LOW, HISTO_LENGTH = 100, 50, 30  # src/ORBmatcher.cc:36-38
+INT_MAX = 2 ** 31 - 1
+
+
+def frame_pair(seed, n1=600, n2=640, width=640, height=480, nlevels=8, jitter=6.0, flips=12, dup=0.0, level0=0.6):
+    """Frame 1: random keypoints; frame 2: the same points moved by up to `jitter` px with `flips` descriptor bits
+    flipped, shuffled, padded with unrelated ones.  `dup` = fraction of frame-2 descriptors that are exact copies of
+    another one (distance ties and contested matches)."""
+    rng = np.random.default_rng(seed)
+    k1 = np.zeros(n1, orc.KP_DTYPE)
+    k1["x"] = rng.uniform(-5, width + 5, n1).astype(F32)
+    k1["y"] = rng.uniform(-5, height + 5, n1).astype(F32)
+    k1["octave"] = np.where(rng.random(n1) < level0, 0, rng.integers(0, nlevels, n1))
+    k1["angle"] = rng.uniform(0, 360, n1).astype(F32)
+    k1["size"], k1["class_id"] = 31, -1
+    d1 = rng.integers(0, 256, (n1, 32), dtype=np.uint8)
+    k2 = np.zeros(n2, orc.KP_DTYPE)
+    d2 = rng.integers(0, 256, (n2, 32), dtype=np.uint8)
+    k2["x"] = rng.uniform(-5, width + 5, n2).astype(F32)
+    k2["y"] = rng.uniform(-5, height + 5, n2).astype(F32)
+    k2["octave"] = np.where(rng.random(n2) < level0, 0, rng.integers(0, nlevels, n2))
+    k2["angle"] = rng.uniform(0, 360, n2).astype(F32)
+    k2["size"], k2["class_id"] = 31, -1
+    m = min(n1, n2)
+    src = rng.permutation(n1)[:m]
+    dst = rng.permutation(n2)[:m]
+    k2["x"][dst] = k1["x"][src] + rng.uniform(-jitter, jitter, m).astype(F32)
+    k2["y"][dst] = k1["y"][src] + rng.uniform(-jitter, jitter, m).astype(F32)
+    lvl = k1["octave"][src] + np.where(rng.random(m) < 0.15, rng.integers(-1, 2, m), 0)
+    k2["octave"][dst] = np.clip(lvl, 0, nlevels - 1)
+    rot = F32(rng.uniform(0, 360))  # one dominant rotation plus outliers: the histogram check has something to cut
+    noise = np.where(rng.random(m) < 0.2, rng.uniform(0, 360, m), rng.normal(0, 4, m))
+    k2["angle"][dst] = np.mod(k1["angle"][src] - rot + noise, 360).astype(F32)
+    dd = d1[src].copy()
+    for r in range(m):
+        bits = rng.choice(256, int(rng.integers(0, flips + 1)), replace=False)
+        for b in bits:
+            dd[r, b >> 3] ^= 1 << (b & 7)
+    d2[dst] = dd
+    ndup = int(dup * n2)
+    if ndup:
+        a, b = rng.integers(0, n2, ndup), rng.integers(0, n2, ndup)
+        d2[a] = d2[b]
+        k2["x"][a] = k2["x"][b] + rng.integers(-2, 3, ndup).astype(F32)
+        k2["y"][a] = k2["y"][b] + rng.integers(-2, 3, ndup).astype(F32)
+        k2["octave"][a] = k2["octave"][b]
+    return k1, d1, k2, d2
+
+
+def grid_params(width=640, height=480, min_x=0.0, min_y=0.0):
+    """mnMinX, mnMinY, mfGridElementWidthInv, mfGridElementHeightInv as Frame's constructor computes them
+    (src/Frame.cc:106-107, 161-162) for bounds [min, min + size]."""
+    inv_w = F32(COLS) / F32(F32(min_x + width) - F32(min_x))
+    inv_h = F32(ROWS) / F32(F32(min_y + height) - F32(min_y))
+    return float(F32(min_x)), float(F32(min_y)), float(inv_w), float(inv_h)
+
+
+def _round_away(v):
+    v = float(v)
+    return int(math.copysign(math.floor(abs(v) + 0.5), v))
+
+
+def py_grid(kps, gp):
+    """Frame::AssignFeaturesToGrid with PosInGrid (src/Frame.cc:179-192, 323-332): {(ix, iy): [i, ...]}."""
+    min_x, min_y, inv_w, inv_h = (F32(v) for v in gp)
+    grid = {}
+    for i in range(len(kps)):
+        px = _round_away(F32(F32(kps["x"][i]) - min_x) * inv_w)
+        py = _round_away(F32(F32(kps["y"][i]) - min_y) * inv_h)
+        if 0 <= px < COLS and 0 <= py < ROWS:
+            grid.setdefault((px, py), []).append(i)
+    return grid
+
+
+def py_features_in_area(kps, grid, gp, x, y, r, min_level, max_level):
+    """Frame::GetFeaturesInArea, src/Frame.cc:271-321."""
+    min_x, min_y, inv_w, inv_h = (F32(v) for v in gp)
+    x, y, r = F32(x), F32(y), F32(r)
+    out = []
+    c0 = max(0, int(math.floor(F32(F32(F32(x - min_x) - r) * inv_w))))
+    if c0 >= COLS:
+        return out
+    c1 = min(COLS - 1, int(math.ceil(F32(F32(F32(x - min_x) + r) * inv_w))))
+    if c1 < 0:
+        return out
+    r0 = max(0, int(math.floor(F32(F32(F32(y - min_y) - r) * inv_h))))
+    if r0 >= ROWS:
+        return out
+    r1 = min(ROWS - 1, int(math.ceil(F32(F32(F32(y - min_y) + r) * inv_h))))
+    if r1 < 0:
+        return out
+    check = min_level > 0 or max_level >= 0
+    for ix in range(c0, c1 + 1):
+        for iy in range(r0, r1 + 1):
+            for i in grid.get((ix, iy), ()):
+                o = int(kps["octave"][i])
+                if check:
+                    if o < min_level:
+                        continue
+                    if max_level >= 0 and o > max_level:
+                        continue
+                if abs(F32(kps["x"][i]) - x) < r and abs(F32(kps["y"][i]) - y) < r:
+                    out.append(i)
+    return out
+
+
+def py_distance(a, b):
+    return int(np.unpackbits(np.bitwise_xor(a, b)).sum())
+
+
+def py_three_maxima(sizes):
+    """ORBmatcher::ComputeThreeMaxima, src/ORBmatcher.cc:1423-1454."""
+    m1 = m2 = m3 = 0
+    i1 = i2 = i3 = -1
+    for i, s in enumerate(sizes):
+        if s > m1:
+            m3, m2, m1 = m2, m1, s
+            i3, i2, i1 = i2, i1, i
+        elif s > m2:
+            m3, m2 = m2, s
+            i3, i2 = i2, i
+        elif s > m3:
+            m3, i3 = s, i
+    if F32(m2) < F32(0.1) * F32(m1):
+        i2 = i3 = -1
+    elif F32(m3) < F32(0.1) * F32(m1):
+        i3 = -1
+    return i1, i2, i3
+
+
+def _bin(a1, a2):
+    rot = F32(a1) - F32(a2)
+    if rot < 0:
+        rot = F32(rot + F32(360))
+    b = _round_away(F32(rot * F32(F32(1) / F32(HISTO_LENGTH))))
+    return 0 if b == HISTO_LENGTH else b
+
+
+def py_search_for_initialization(k1, d1, k2, d2, gp, prev, window, nnratio, check_orientation):
+    """ORBmatcher::SearchForInitialization, src/ORBmatcher.cc:256-357: (nmatches, vnMatches12, vbPrevMatched)."""
+    grid = py_grid(k2, gp)
+    prev = np.array(prev, F32).reshape(-1, 2).copy()
+    n = 0
+    m12 = [-1] * len(k1)
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    mdist = [INT_MAX] * len(k2)
+    m21 = [-1] * len(k2)
+    for i1 in range(len(k1)):
+        lvl = int(k1["octave"][i1])
+        if lvl > 0:
+            continue
+        cand = py_features_in_area(k2, grid, gp, prev[i1, 0], prev[i1, 1], window, lvl, lvl)
+        if not cand:
+            continue
+        best, best2, bidx = INT_MAX, INT_MAX, -1
+        for i2 in cand:
+            d = py_distance(d1[i1], d2[i2])
+            if mdist[i2] <= d:
+                continue
+            if d < best:
+                best2, best, bidx = best, d, i2
+            elif d < best2:
+                best2 = d
+        if best <= TH_LOW and F32(best) < F32(F32(best2) * F32(nnratio)):
+            if m21[bidx] >= 0:
+                m12[m21[bidx]] = -1
+                n -= 1
+            m12[i1], m21[bidx], mdist[bidx] = bidx, i1, best
+            n += 1
+            if check_orientation:
+                hist[_bin(k1["angle"][i1], k2["angle"][bidx])].append(i1)
+    if check_orientation:
+        keep = py_three_maxima([len(h) for h in hist])
+        for b in range(HISTO_LENGTH):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                if m12[i1] >= 0:
+                    m12[i1] = -1
+                    n -= 1
+    for i1 in range(len(k1)):
+        if m12[i1] >= 0:
+            prev[i1] = (k2["x"][m12[i1]], k2["y"][m12[i1]])
+    return n, np.array(m12, np.int32), prev
+
+
+def projection_inputs(seed, k1, d1, nlevels=8, width=640, height=480):
+    """What the caller of SearchByProjection supplies for the last frame: the projected (u, v, invzc), the flags and
+    the map points' descriptors -- here frame 1's keypoints moved a little, some without map point, some behind the camera,
+    some outside the bounds."""
+    rng = np.random.default_rng(seed + 77)
+    n = len(k1)
+    proj = np.zeros((n, 3), F32)
+    proj[:, 0] = k1["x"] + rng.uniform(-3, 3, n).astype(F32)
+    proj[:, 1] = k1["y"] + rng.uniform(-3, 3, n).astype(F32)
+    proj[:, 2] = (1.0 / rng.uniform(0.5, 12, n)).astype(F32)
+    proj[rng.random(n) < 0.05, 2] *= -1
+    flags = (rng.random(n) < 0.8).astype(np.uint8) | ((rng.random(n) < 0.7).astype(np.uint8) << 1)
+    desc_mp = d1.copy()
+    return proj, flags, desc_mp
+
+
+def py_search_by_projection(kl, klu, proj, flags, desc_mp, kc, dc, ur_c, occ_c, gp, scale_factors, bounds, th, mbf, mode,
+                            check_orientation):
+    """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono), src/ORBmatcher.cc:946-1075, from :983 on:
+    (nmatches, assigned)."""
+    grid = py_grid(kc, gp)
+    n = 0
+    assigned = [-1] * len(kc)
+    occ = [bool(v) for v in occ_c]
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    for i in range(len(kl)):
+        if not flags[i] & 1:
+            continue
+        u, v, invzc = (F32(t) for t in proj[i])
+        if invzc < 0:
+            continue
+        if u < F32(bounds[0]) or u > F32(bounds[1]) or v < F32(bounds[2]) or v > F32(bounds[3]):
+            continue
+        o = int(kl["octave"][i])
+        radius = F32(F32(th) * F32(scale_factors[o]))
+        if mode == 1:
+            cand = py_features_in_area(kc, grid, gp, u, v, radius, o, -1)
+        elif mode == 2:
+            cand = py_features_in_area(kc, grid, gp, u, v, radius, 0, o)
+        else:
+            cand = py_features_in_area(kc, grid, gp, u, v, radius, o - 1, o + 1)
+        if not cand:
+            continue
+        best, bidx = 256, -1
+        for i2 in cand:
+            if occ[i2]:
+                continue
+            if ur_c[i2] > 0:
+                # u - mbf*invzc, fused under the reference's -O3 -march=native: one rounding of the exact value
+                ur = F32(np.float64(u) - np.float64(F32(mbf)) * np.float64(invzc))
+                if abs(F32(ur - F32(ur_c[i2]))) > radius:
+                    continue
+            d = py_distance(desc_mp[i], dc[i2])
+            if d < best:
+                best, bidx = d, i2
+        if best <= TH_HIGH:
+            assigned[bidx] = i
+            occ[bidx] = bool(flags[i] & 2)
+            n += 1
+            if check_orientation:
+                hist[_bin(klu["angle"][i], kc["angle"][bidx])].append(bidx)
+    if check_orientation:
+        keep = py_three_maxima([len(h) for h in hist])
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for i2 in hist[b]:
+                    assigned[i2] = -1
+                    n -= 1
+    return n, np.array(assigned, np.int32)

@@ -1,0 +1,187 @@
+"""The guided matchers on the GPU (sdorb_search_for_initialization_batch / sdorb_search_by_projection_batch, through the
+C ABI) against the CPU oracle: ORBmatcher::SearchForInitialization (/root/reference/src/ORBmatcher.cc:256-357) and
+ORBmatcher::SearchByProjection(Frame&, const Frame&, th, bMono) (:946-1075) over Frame::GetFeaturesInArea
+(src/Frame.cc:271-321).  Bit-exact: vnMatches12, vbPrevMatched, the map-point assignment and the return values.
+Needs a B200: run with  pytest -m gpu."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import search_cases as sc
+from oracle import binding as orc
+from sdslam_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ex():
+    e = api.ORBextractor(1000, 1.2, 8, 20, max_width=640, max_height=480, max_batch=8)
+    yield e
+    e.close()
+
+
+def _slab(arrs, cap, dtype, tail=()):
+    out = np.zeros((len(arrs), cap) + tuple(tail), dtype)
+    for p, a in enumerate(arrs):
+        out[p, :len(a)] = a
+    return out
+
+
+def _init_batch(ex, pairs, gp, window, ratio, orient, cap):
+    P = len(pairs)
+    k1 = _slab([p[0] for p in pairs], cap, api.KP_DTYPE)
+    d1 = _slab([p[1] for p in pairs], cap, np.uint8, (32,))
+    k2 = _slab([p[2] for p in pairs], cap, api.KP_DTYPE)
+    d2 = _slab([p[3] for p in pairs], cap, np.uint8, (32,))
+    n1 = np.array([len(p[0]) for p in pairs], np.int32)
+    n2 = np.array([len(p[2]) for p in pairs], np.int32)
+    cs, idx = ex.assign_grid_batch(k2, n2, *gp)
+    prev = np.stack([k1["x"], k1["y"]], 2)
+    return (k1, d1, n1, k2, d2, n2, (cs, idx) + tuple(gp), prev), ex.search_for_initialization_batch(
+        k1, d1, n1, k2, d2, n2, (cs, idx) + tuple(gp), prev, window, ratio, orient)
+
+
+@pytest.mark.parametrize("window,ratio,orient", [(100, 0.9, True), (30, 0.9, True), (100, 0.6, False), (400, 1.0, True)])
+def test_search_for_initialization_equals_oracle(ex, window, ratio, orient):
+    sizes = [(600, 640, 0.0), (400, 380, 0.3), (500, 500, 0.5), (64, 700, 0.0), (300, 1, 0.0), (0, 50, 0.0), (50, 0, 0.0),
+             (700, 700, 0.8), (33, 31, 0.0), (1, 1, 0.0)]
+    pairs = [sc.frame_pair(40 + s, a, b, dup=d, flips=20) for s, (a, b, d) in enumerate(sizes)]
+    gp = sc.grid_params()
+    cap = 704
+    (k1, d1, n1, k2, d2, n2, grid, prev), (nm, m12, pm) = _init_batch(ex, pairs, gp, window, ratio, orient, cap)
+    total = 0
+    for p, (a1, b1, a2, b2) in enumerate(pairs):
+        ocs, oidx = orc.assign_grid(a2, *gp)
+        on, om12, opm = orc.search_for_initialization(a1, b1, a2, b2, (ocs, oidx) + tuple(gp), prev[p, :len(a1)], window, ratio, orient)
+        assert nm[p] == on, "pair %d: nmatches %d vs oracle %d" % (p, nm[p], on)
+        assert np.array_equal(m12[p, :len(a1)], om12), "pair %d: vnMatches12" % p
+        assert (m12[p, len(a1):] == -1).all()
+        assert pm[p, :len(a1)].tobytes() == opm.tobytes(), "pair %d: vbPrevMatched" % p
+        assert pm[p, len(a1):].tobytes() == prev[p, len(a1):].tobytes()
+        total += on
+    assert total > 300
+    # second round from the updated vbPrevMatched (Tracking::MonocularInitialization keeps calling it)
+    nm2, m12b, pm2 = ex.search_for_initialization_batch(k1, d1, n1, k2, d2, n2, grid, pm, window, ratio, orient)
+    for p, (a1, b1, a2, b2) in enumerate(pairs):
+        on, om12, opm = orc.search_for_initialization(a1, b1, a2, b2, (grid[0][p], grid[1][p]) + tuple(gp), pm[p, :len(a1)], window,
+                                                      ratio, orient)
+        assert nm2[p] == on and np.array_equal(m12b[p, :len(a1)], om12) and pm2[p, :len(a1)].tobytes() == opm.tobytes()
+
+
+def _projection_case(seed, nl, nc, stereo, dup=0.0):
+    kl, dl, kc, dc = sc.frame_pair(seed + 20, nl, nc, jitter=4.0, dup=dup, level0=0.3)
+    proj, flags, dmp = sc.projection_inputs(seed, kl, dl)
+    rng = np.random.default_rng(seed)
+    ur = (np.where(rng.random(nc) < 0.6, kc["x"] - rng.uniform(0, 30, nc), -1) if stereo else np.full(nc, -1)).astype(np.float32)
+    occ = (rng.random(nc) < 0.1).astype(np.uint8)
+    klu = kl.copy()
+    klu["angle"] = np.mod(kl["angle"] + np.float32(0.5), 360)  # mvKeysUn carries the angle, mvKeys the octave
+    return kl, klu, proj, flags, dmp, kc, dc, ur, occ
+
+
+@pytest.mark.parametrize("th,mode,orient,stereo", [(15.0, 0, True, False), (7.0, 0, True, True), (15.0, 1, True, True),
+                                                   (15.0, 2, False, True), (30.0, 0, True, True)])
+def test_search_by_projection_equals_oracle(ex, th, mode, orient, stereo):
+    sizes = [(600, 640), (500, 450), (400, 500), (300, 0), (0, 300), (700, 700), (1, 1), (65, 33)]
+    cases = [_projection_case(s, a, b, stereo, dup=0.2 if s == 5 else 0.0) for s, (a, b) in enumerate(sizes)]
+    cap = 704
+    gp = sc.grid_params()
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    col = lambda j, dt, tail=(): _slab([c[j] for c in cases], cap, dt, tail)
+    kl, klu, proj, flags, dmp = col(0, api.KP_DTYPE), col(1, api.KP_DTYPE), col(2, np.float32, (3,)), col(3, np.uint8), col(4, np.uint8, (32,))
+    kc, dc, ur, occ = col(5, api.KP_DTYPE), col(6, np.uint8, (32,)), col(7, np.float32), col(8, np.uint8)
+    nl = np.array([len(c[0]) for c in cases], np.int32)
+    nc = np.array([len(c[5]) for c in cases], np.int32)
+    cs, idx = ex.assign_grid_batch(kc, nc, *gp)
+    nm, asg = ex.search_by_projection_batch(kl, klu, proj, flags, dmp, nl, kc, dc, ur, occ, nc, (cs, idx) + tuple(gp), sf, bounds, th,
+                                            40.0, mode, orient)
+    total = 0
+    for p, c in enumerate(cases):
+        ocs, oidx = orc.assign_grid(c[5], *gp)
+        on, oasg = orc.search_by_projection(c[0], c[1], c[2], c[3], c[4], c[5], c[6], c[7], c[8], (ocs, oidx) + tuple(gp), sf, bounds,
+                                            th, 40.0, mode, orient)
+        assert nm[p] == on, "pair %d: nmatches %d vs oracle %d" % (p, nm[p], on)
+        assert np.array_equal(asg[p, :len(c[5])], oasg), "pair %d: assignment" % p
+        assert (asg[p, len(c[5]):] == -1).all()
+        total += on
+    assert total > 300
+
+
+def test_search_golden_fixture(ex):
+    """The committed vectors made by the independent Python restatement (tests/golden/make_search_golden.py)."""
+    z = np.load(os.path.join(GOLD, "matcher", "search_pairs.npz"))
+    gp = tuple(float(v) for v in z["gp"])
+    k1, k2 = z["k1"].view(api.KP_DTYPE).reshape(1, -1), z["k2"].view(api.KP_DTYPE).reshape(1, -1)
+    cap = max(k1.shape[1], k2.shape[1])
+    pad = lambda a, tail=(): _slab([a.reshape((-1,) + tuple(tail))], cap, a.dtype, tail)
+    K1, K2, D1, D2 = pad(k1[0]), pad(k2[0]), pad(z["d1"], (32,)), pad(z["d2"], (32,))
+    n1, n2 = np.array([k1.shape[1]], np.int32), np.array([k2.shape[1]], np.int32)
+    cs, idx = ex.assign_grid_batch(K2, n2, *gp)
+    grid = (cs, idx) + gp
+    nm, m12, pm = ex.search_for_initialization_batch(K1, D1, n1, K2, D2, n2, grid, pad(z["prev"], (2,)), 100, 0.9, True)
+    assert nm[0] == int(z["init_n"]) and np.array_equal(m12[0, :n1[0]], z["init_m12"])
+    assert pm[0, :n1[0]].tobytes() == z["init_prev"].tobytes()
+    nm, asg = ex.search_by_projection_batch(K1, K1, pad(z["proj"], (3,)), pad(z["flags"]), D1, n1, K2, D2, pad(z["ur"]), pad(z["occ"]),
+                                            n2, grid, z["sf"], z["bounds"], 15.0, 40.0, 0, True)
+    assert nm[0] == int(z["proj_n"]) and np.array_equal(asg[0, :n2[0]], z["proj_assigned"])
+
+
+def test_extract_to_initialization_search_on_device_memory(ex):
+    """The monocular-initialisation chain on real ORB output with everything resident on the device: extract two shifted
+    views of one scene, grid the second, SearchForInitialization (windowSize 100, nnratio 0.9) -- device pointers in, device
+    pointers out -- equals the oracle run on the extractor's host output, and finds the shift."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    big = synth.smooth_noise(3, 700, 520)
+    imgs = np.stack([big[20:500, 30:670], big[14:494, 19:659]])  # second view shifted by (+11, +6) px
+    kps, desc, cnt = ex.extract_batch_host(np.ascontiguousarray(imgs))
+    gp = sc.grid_params()
+    cap = kps.shape[1]
+    prev = np.stack([kps["x"][0], kps["y"][0]], 1)[None].astype(np.float32)
+    def t(a):  # keypoint slabs travel as [P, cap, 7] float32 (28-byte cv::KeyPoint rows)
+        a = np.ascontiguousarray(a)
+        return torch.from_numpy(a.view(np.float32).reshape(a.shape + (7,)) if a.dtype == api.KP_DTYPE else a).to(dev)
+
+    tk1, tk2, td1, td2 = t(kps[0:1]), t(kps[1:2]), t(desc[0:1]), t(desc[1:2])
+    tn1, tn2 = t(cnt[0:1].astype(np.int32)), t(cnt[1:2].astype(np.int32))
+    tprev = t(prev)
+    tcs = torch.zeros((1, 64 * 48 + 1), dtype=torch.int32, device=dev)
+    tidx = torch.zeros((1, cap), dtype=torch.int32, device=dev)
+    ex.assign_grid_batch(tk2, tn2, *gp, cell_start=tcs, indices=tidx, device=True,
+                         stream=torch.cuda.current_stream().cuda_stream)
+    tm12 = torch.zeros((1, cap), dtype=torch.int32, device=dev)
+    tnm = torch.zeros(1, dtype=torch.int32, device=dev)
+    ex.search_for_initialization_batch(tk1, td1, tn1, tk2, td2, tn2, (tcs, tidx) + gp, tprev, 100, 0.9, True, matches12=tm12,
+                                       nmatches=tnm, device=True, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    n1, n2 = int(cnt[0]), int(cnt[1])
+    ocs, oidx = orc.assign_grid(kps[1, :n2], *gp)
+    on, om12, opm = orc.search_for_initialization(kps[0, :n1], desc[0, :n1], kps[1, :n2], desc[1, :n2], (ocs, oidx) + gp, prev[0, :n1],
+                                                  100, 0.9, True)
+    assert int(tnm.cpu()[0]) == on and np.array_equal(tm12.cpu().numpy()[0, :n1], om12)
+    assert tprev.cpu().numpy()[0, :n1].tobytes() == opm.tobytes()
+    m = np.flatnonzero(om12 >= 0)
+    assert len(m) > 40
+    dx = kps["x"][1][om12[m]] - kps["x"][0][m]
+    dy = kps["y"][1][om12[m]] - kps["y"][0][m]
+    assert abs(float(np.median(dx)) - 11) <= 1.5 and abs(float(np.median(dy)) - 6) <= 1.5
+
+
+def test_search_argument_errors(ex):
+    k = np.zeros((1, 8), api.KP_DTYPE)
+    d = np.zeros((1, 8, 32), np.uint8)
+    n = np.zeros(1, np.int32)
+    cs, idx = np.zeros((1, 64 * 48 + 1), np.int32), np.zeros((1, 8), np.int32)
+    g = api._FrameGrid(api._ptr(cs), api._ptr(idx), 0.0, 0.0, 0.1, 0.1)
+    prev, m12, nm = np.zeros((1, 8, 2), np.float32), np.zeros((1, 8), np.int32), np.zeros(1, np.int32)
+    L = api.lib()
+    call = lambda cap, mem, kp1=k: L.sdorb_search_for_initialization_batch(
+        ex._h, api._ptr(kp1), api._ptr(d), api._ptr(n), api._ptr(k), api._ptr(d), api._ptr(n), C.byref(g), 1, cap, api._ptr(prev), 100,
+        0.9, 1, api._ptr(m12), api._ptr(nm), mem, None)
+    assert call(8, api.MEM_HOST) == 0 and nm[0] == 0
+    assert call(0, api.MEM_HOST) < 0 and call(16385, api.MEM_HOST) < 0 and call(8, 7) < 0 and call(8, api.MEM_HOST, None) < 0

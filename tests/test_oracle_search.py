@@ -1,0 +1,96 @@
+"""Pins the oracle's guided matchers (oracle/sdorb_oracle.cc: orc_features_in_area, orc_three_maxima,
+orc_search_for_initialization, orc_search_by_projection) against a second, independent restatement of
+/root/reference/src/ORBmatcher.cc:256-357, 946-1075, 1423-1454 and src/Frame.cc:271-321 (tests/search_cases.py).
+The reference has no tests or fixtures for these functions and cannot be compiled here (Eigen / OpenCV C++ headers are
+absent), so two independently written restatements agreeing is the pin; a committed fixture (tests/golden/matcher/search_pairs.npz,
+made by tests/golden/make_search_golden.py from the Python restatement) freezes it.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+import search_cases as sc
+from oracle import binding as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _orc_grid(k, gp):
+    cs, idx = orc.assign_grid(k, *gp)
+    return (cs, idx) + tuple(gp)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_features_in_area_equals_restatement(seed):
+    k1, d1, k2, d2 = sc.frame_pair(seed, 300, 500)
+    gp = sc.grid_params(640, 480, -3.5 if seed & 1 else 0.0, 2.25 if seed & 1 else 0.0)
+    g = _orc_grid(k2, gp)
+    pg = sc.py_grid(k2, gp)
+    rng = np.random.default_rng(seed)
+    for q in range(300):
+        x, y = rng.uniform(-80, 720), rng.uniform(-80, 560)
+        r = float(rng.choice([0.5, 3, 15, 40, 100, 900]))
+        lo, hi = [(-1, -1), (0, -1), (2, -1), (0, 0), (1, 3), (0, 5), (3, 2)][q % 7]
+        assert orc.features_in_area(k2, g, x, y, r, lo, hi).tolist() == sc.py_features_in_area(k2, pg, gp, x, y, r, lo, hi)
+
+
+def test_three_maxima_equals_restatement():
+    rng = np.random.default_rng(5)
+    cases = [rng.integers(0, 40, 30) for _ in range(200)] + [np.zeros(30, int), np.full(30, 7), np.arange(30), np.arange(30)[::-1]]
+    cases += [np.array([100] + [9] * 29), np.array([100, 10] + [9] * 28), np.array([100, 10, 10] + [0] * 27), np.array([0] * 29 + [1])]
+    for s in cases:
+        assert orc.three_maxima(s) == sc.py_three_maxima([int(v) for v in s])
+
+
+@pytest.mark.parametrize("seed,n1,n2,window,ratio,orient,dup", [
+    (0, 600, 640, 100, 0.9, True, 0.0), (1, 400, 380, 30, 0.9, True, 0.3), (2, 500, 500, 100, 0.6, False, 0.5),
+    (3, 64, 700, 15, 1.0, True, 0.0), (4, 300, 1, 100, 0.9, True, 0.0), (5, 0, 50, 100, 0.9, True, 0.0),
+    (6, 50, 0, 100, 0.9, True, 0.0), (7, 700, 700, 400, 0.9, True, 0.8)])
+def test_search_for_initialization_equals_restatement(seed, n1, n2, window, ratio, orient, dup):
+    k1, d1, k2, d2 = sc.frame_pair(seed, n1, n2, dup=dup, flips=20)
+    gp = sc.grid_params()
+    prev = np.stack([k1["x"], k1["y"]], 1) if n1 else np.zeros((0, 2), np.float32)  # Initializer: vbPrevMatched = F1 keypoints
+    n, m12, pm = orc.search_for_initialization(k1, d1, k2, d2, _orc_grid(k2, gp), prev, window, ratio, orient)
+    pn, pm12, ppm = sc.py_search_for_initialization(k1, d1, k2, d2, gp, prev, window, ratio, orient)
+    assert n == pn and np.array_equal(m12, pm12) and pm.tobytes() == ppm.tobytes()
+    assert n == int((m12 >= 0).sum())
+    if seed == 0:
+        assert n > 100  # the case exercises real matches
+    if n:  # a second call continues from the updated vbPrevMatched, as Tracking::MonocularInitialization does
+        n2_, m12b, _ = orc.search_for_initialization(k1, d1, k2, d2, _orc_grid(k2, gp), pm, window, ratio, orient)
+        pn2, pm12b, _ = sc.py_search_for_initialization(k1, d1, k2, d2, gp, ppm, window, ratio, orient)
+        assert n2_ == pn2 and np.array_equal(m12b, pm12b)
+
+
+@pytest.mark.parametrize("seed,nl,nc,th,mode,orient,stereo", [
+    (0, 600, 640, 15.0, 0, True, False), (1, 500, 450, 7.0, 0, True, True), (2, 400, 500, 15.0, 1, True, True),
+    (3, 400, 500, 15.0, 2, False, True), (4, 300, 0, 15.0, 0, True, False), (5, 0, 300, 15.0, 0, True, False),
+    (6, 700, 700, 30.0, 0, True, True)])
+def test_search_by_projection_equals_restatement(seed, nl, nc, th, mode, orient, stereo):
+    kl, dl, kc, dc = sc.frame_pair(seed + 20, nl, nc, jitter=4.0, dup=0.2 if seed == 6 else 0.0, level0=0.3)
+    proj, flags, dmp = sc.projection_inputs(seed, kl, dl)
+    rng = np.random.default_rng(seed)
+    ur = np.where(rng.random(nc) < 0.6, kc["x"] - rng.uniform(0, 30, nc), -1).astype(np.float32) if stereo else np.full(nc, -1, np.float32)
+    occ = (rng.random(nc) < 0.1).astype(np.uint8)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    gp = sc.grid_params()
+    bounds = (0.0, 640.0, 0.0, 480.0)
+    klu = kl.copy()
+    klu["angle"] = kl["angle"]
+    n, asg = orc.search_by_projection(kl, klu, proj, flags, dmp, kc, dc, ur, occ, _orc_grid(kc, gp), sf, bounds, th, 40.0, mode, orient)
+    pn, pasg = sc.py_search_by_projection(kl, klu, proj, flags, dmp, kc, dc, ur, occ, gp, sf, bounds, th, 40.0, mode, orient)
+    assert n == pn and np.array_equal(asg, pasg)
+    if seed == 0:
+        assert n > 100
+
+
+def test_search_golden_fixture():
+    """The committed vectors (inputs + results of the Python restatement) against the oracle."""
+    z = np.load(os.path.join(GOLD, "matcher", "search_pairs.npz"))
+    gp = tuple(float(v) for v in z["gp"])
+    k1, k2 = z["k1"].view(orc.KP_DTYPE).reshape(-1), z["k2"].view(orc.KP_DTYPE).reshape(-1)
+    n, m12, pm = orc.search_for_initialization(k1, z["d1"], k2, z["d2"], _orc_grid(k2, gp), z["prev"], 100, 0.9, True)
+    assert n == int(z["init_n"]) and np.array_equal(m12, z["init_m12"]) and pm.tobytes() == z["init_prev"].tobytes()
+    n, asg = orc.search_by_projection(k1, k1, z["proj"], z["flags"], z["d1"], k2, z["d2"], z["ur"], z["occ"], _orc_grid(k2, gp),
+                                      z["sf"], z["bounds"], 15.0, 40.0, 0, True)
+    assert n == int(z["proj_n"]) and np.array_equal(asg, z["proj_assigned"])
