@@ -415,6 +415,35 @@ def run_ours(args):
     search_pairs_per_s = world * npairs / (float(ts.item()) * 1e-3)
     search_matches = float(s_nm.double().mean().item())
 
+    # ---- ORB-SLAM2-style mode side figure (row f1: iniThFAST 20 / minThFAST 7 on 30-pixel cells + DistributeOctTree), the first
+    # frames of the same batch, resident
+    o2_n = min(frames_per_gpu, 2 * args.pass_frames)
+    ex2 = api.ORBextractor(nf, sf, nl, th, minThFAST=7, device=local, max_width=w, max_height=h, max_batch=args.pass_frames)
+    cap2 = ex2.max_keypoints
+    kps2 = torch.zeros((o2_n, cap2, 7), dtype=torch.float32, device=dev)
+    desc2 = torch.zeros((o2_n, cap2, 32), dtype=torch.uint8, device=dev)
+    cnt2 = torch.zeros(o2_n, dtype=torch.int32, device=dev)
+    o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(stream):
+        for _ in range(2):
+            ex2.extract_batch_device(dimgs[:o2_n], kps2, desc2, cnt2, stream=stream.cuda_stream)
+        ex2.set_profiling(True)
+        ex2.stage_times(reset=True)
+        o0.record(stream)
+        for _ in range(3):
+            ex2.extract_batch_device(dimgs[:o2_n], kps2, desc2, cnt2, stream=stream.cuda_stream)
+        o1.record(stream)
+    barrier()
+    o2_ms, _ = ex2.stage_times()
+    to = torch.tensor([o0.elapsed_time(o1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(to, op=dist.ReduceOp.MAX)
+    orbslam2 = {"frames_per_s": world * o2_n * 3 / (float(to.item()) * 1e-3), "frames_per_gpu_per_step": o2_n, "ini_th_fast": th,
+                "min_th_fast": 7, "keypoints_per_frame": float(cnt2.double().mean().item()),
+                "select_ms_per_step": o2_ms["select"] / 3, "fast_ms_per_step": o2_ms["fast"] / 3}
+    ex2.close()
+    del kps2, desc2, cnt2
+
     # ---- the one collective of the job: gather the result slabs of (a slice of) the batch on rank 0 over NCCL
     gather_ms = None
     if world > 1:
@@ -477,6 +506,7 @@ def run_ours(args):
                         "distinctive_sets_per_s": distinctive_sets_per_s, "distinctive_set_size": 16,
                         "search_for_initialization_frame_pairs_per_s": search_pairs_per_s,
                         "search_for_initialization_matches_per_pair": search_matches},
+            "orbslam2_mode": orbslam2,
             "gather_ms": gather_ms,
             "host_affinity": numa,
         }

@@ -13,8 +13,11 @@
  *   - image sizes for which the reference itself throws cv::Exception (a cell ROI outside the level image) throw
  *     std::runtime_error("... geometry ...") instead.
  * The north-star surface ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) / operator()(image, mask,
- * keypoints, descriptors) is provided as overloads: SD-SLAM has a single FAST threshold (src/ORBextractor.cc:536), so
- * iniThFAST is used as thFAST and minThFAST is ignored.
+ * keypoints, descriptors) is provided as overloads.  SD-SLAM itself has a single FAST threshold and no quadtree
+ * (src/ORBextractor.cc:536): the 5-argument constructor selects the ORB-SLAM2-style mode of the
+ * library (30-pixel cells with the iniThFAST / minThFAST fallback, DistributeOctTree), whose
+ * results follow the public ORB-SLAM2 algorithm, not anything in /root/reference; operator() may then return a few
+ * keypoints more than nfeatures, as ORB-SLAM2 does.
  */
 #ifndef SD_SLAM_ORBEXTRACTOR_H
 #define SD_SLAM_ORBEXTRACTOR_H
@@ -45,13 +48,25 @@ class ORBextractor {
   // src/ORBextractor.h:38, src/ORBextractor.cc:406-457
   ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int _thFAST, const Options& opt = Options())
       : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), thFAST(_thFAST), handle_(NULL) {
+    Init(-1, opt);
+  }
+  // north-star form: (nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST) -- the ORB-SLAM2-style mode
+  ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int iniThFAST, int minThFAST, const Options& opt = Options())
+      : nfeatures(_nfeatures), scaleFactor(_scaleFactor), nlevels(_nlevels), thFAST(iniThFAST), handle_(NULL) {
+    Init(minThFAST < 0 ? 0 : minThFAST, opt);
+  }
+
+ protected:
+  void Init(int min_th_fast, const Options& opt) {
+    const int _nfeatures = nfeatures, _nlevels = nlevels, _thFAST = thFAST;
+    const float _scaleFactor = scaleFactor;
     const int max_width = opt.max_width, max_height = opt.max_height, device = opt.device;
     sdorb_params p;
     p.nfeatures = _nfeatures;
     p.scale_factor = _scaleFactor;
     p.nlevels = _nlevels;
     p.th_fast = _thFAST;
-    p.min_th_fast = -1;
+    p.min_th_fast = min_th_fast;
     p.device = device;
     p.max_width = max_width;
     p.max_height = max_height;
@@ -70,10 +85,8 @@ class ORBextractor {
     kps_.resize(capacity_);
     desc_.resize((size_t)capacity_ * 32);
   }
-  // north-star form: (nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)
-  ORBextractor(int _nfeatures, float _scaleFactor, int _nlevels, int iniThFAST, int /*minThFAST*/, const Options& opt = Options())
-      : ORBextractor(_nfeatures, _scaleFactor, _nlevels, iniThFAST, opt) {}
 
+ public:
   ~ORBextractor() { sdorb_destroy(handle_); }
   ORBextractor(const ORBextractor&) = delete;
   ORBextractor& operator=(const ORBextractor&) = delete;

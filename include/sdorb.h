@@ -55,8 +55,12 @@ typedef struct {
   float scale_factor;
   int nlevels;
   int th_fast;      /* the reference's single FAST threshold (thFAST / north-star iniThFAST) */
-  int min_th_fast;  /* -1 = reference behaviour (no fallback threshold exists in SD-SLAM).  >= 0 is the
-                       ORB-SLAM2-style mode, which this reference does not contain: SDORB_ERR_UNSUPPORTED */
+  int min_th_fast;  /* -1 = reference behaviour (SD-SLAM has one FAST threshold and no quadtree).  >= 0 selects the
+                       ORB-SLAM2-style mode (the north star's iniThFAST / minThFAST /
+                       DistributeOctTree): th_fast is iniThFAST, cells of about 30 pixels fall back to min_th_fast when
+                       iniThFAST finds nothing in them, DistributeOctTree culls every level.  That algorithm is NOT in
+                       /root/reference; it follows the public ORB-SLAM2 source, and a frame may then yield up to
+                       sdorb_max_keypoints() > nfeatures keypoints. */
   int device;       /* CUDA device ordinal; -1 = the calling thread's current device */
   int max_width, max_height; /* largest image the handle will be given (<= 4095 each) */
   int max_batch;    /* frames processed per internal pass; device scratch is sized for this many */

@@ -116,6 +116,10 @@ def lib(path=None):
         L.orc_distinctive.argtypes = [vp, i, C.POINTER(i)]
         L.orc_distinctive.restype = i
         L.orc_distinctive_many.argtypes = [vp, vp, i, i, vp, vp]
+        L.orc_set_orbslam2_mode.argtypes = [vp, i, i]
+        L.orc_set_orbslam2_mode.restype = None
+        L.orc_distribute_oct_tree.argtypes = [vp, i, i, i, i, i, i, vp, i]
+        L.orc_distribute_oct_tree.restype = i
         L.orc_features_in_area.argtypes = [vp, C.POINTER(FrameGrid), f, f, f, i, i, vp]
         L.orc_features_in_area.restype = i
         L.orc_three_maxima.argtypes = [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
@@ -206,12 +210,20 @@ def pattern_rotate(px, py, a, b):
 class Extractor:
     """Oracle twin of SD_SLAM::ORBextractor(nfeatures, scaleFactor, nlevels, thFAST)."""
 
-    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, th_fast=20):
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, th_fast=20, min_th_fast=None):
+        """min_th_fast given: the ORB-SLAM2-style mode (th_fast = iniThFAST; 30-pixel cells, DistributeOctTree)."""
         self.params = Params(nfeatures, scale_factor, nlevels, th_fast)
         self.nfeatures, self.nlevels = nfeatures, nlevels
         self._h = lib().orc_create(C.byref(self.params))
         if not self._h:
             raise ValueError("bad oracle parameters")
+        self.octree = min_th_fast is not None and min_th_fast >= 0
+        if self.octree:
+            lib().orc_set_orbslam2_mode(self._h, th_fast, min_th_fast)
+
+    def _cap(self):
+        # DistributeOctTree stops at >= N nodes per level: up to N + 2 (or the 4 children of each initial node) keypoints
+        return max(self.nfeatures, 1) + (8 * self.nlevels if self.octree else 0)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -234,7 +246,7 @@ class Extractor:
         """Returns (kps, desc) or, with dump=True, (kps, desc, stages dict)."""
         img = _u8(img)
         h, w = img.shape
-        cap = max(self.nfeatures, 1)
+        cap = self._cap()
         kps = np.zeros(cap, KP_DTYPE)
         desc = np.zeros((cap, 32), np.uint8)
         d = None
@@ -263,12 +275,21 @@ class Extractor:
     def extract_many(self, imgs, nthreads=1, want_outputs=True):
         imgs = np.ascontiguousarray(imgs, np.uint8)
         nf, h, w = imgs.shape
-        cap = max(self.nfeatures, 1)
+        cap = self._cap()
         kps = np.zeros((nf, cap), KP_DTYPE) if want_outputs else None
         desc = np.zeros((nf, cap, 32), np.uint8) if want_outputs else None
         counts = np.zeros(nf, np.int32)
         lib().orc_extract_many(self._h, _p(imgs), nf, w, h, nthreads, _p(kps), _p(desc), _p(counts), cap)
         return kps, desc, counts
+
+
+def distribute_oct_tree(keys, min_x, max_x, min_y, max_y, n):
+    """ORB-SLAM2's ORBextractor::DistributeOctTree (row f1); keys relative to (min_x, min_y)."""
+    k = np.ascontiguousarray(keys, KP_DTYPE)
+    out = np.zeros(len(k) + 1, KP_DTYPE)  # one keypoint per node, every node holds at least one
+    m = lib().orc_distribute_oct_tree(_p(k), len(k), min_x, max_x, min_y, max_y, n, _p(out), len(out))
+    assert m <= len(out)
+    return out[:m]
 
 
 # ---------------------------------------------------------------- matcher

@@ -395,6 +395,7 @@ struct orc_extractor {
   double scaleFactor; /* the member is a double initialised from a float (src/ORBextractor.h:78) */
   int nlevels;
   int thFAST;
+  int iniThFAST = -1, minThFAST = -1; /* >= 0: the ORB-SLAM2-style mode (row f1), see compute_keypoints_octree */
   std::vector<float> mvScaleFactor, mvInvScaleFactor, mvLevelSigma2, mvInvLevelSigma2;
   std::vector<int> mnFeaturesPerLevel, umax;
 };
@@ -674,6 +675,210 @@ bool compute_keypoints(const orc_extractor& e, const std::vector<Image>& pyr, in
   return true;
 }
 
+/* ------------------------------------------------------------------ ORB-SLAM2-style mode
+ * iniThFAST / minThFAST fallback on 30-pixel cells + DistributeOctTree.  NOT part of /root/reference:
+ * this restates the public ORB-SLAM2 algorithm (raulmur/ORB_SLAM2, src/ORBextractor.cc: ExtractorNode::DivideNode,
+ * ORBextractor::DistributeOctTree, ORBextractor::ComputeKeyPointsOctTree) from its published form; the source is not in
+ * this image and there is no network, so this mode is PARITY UNPINNED against ORB-SLAM2 itself (the FAST / blur /
+ * descriptor primitives it shares with the reference mode are pinned as above, and a second, independently written Python
+ * restatement in tests/cv2_pipeline.py must agree).
+ * One point of ORB-SLAM2 is not a function of its inputs: DistributeOctTree sorts (size, ExtractorNode*) pairs, so nodes of
+ * equal size are ordered by the heap addresses of std::list nodes.  Frozen here as the bump-allocator model: a node created
+ * later has the higher address. */
+struct ExtractorNode {
+  int ULx, ULy, URx, BRy; /* UL = (ULx, ULy), UR = (URx, ULy), BL = (ULx, BRy), BR = (URx, BRy) */
+  std::vector<orc_keypoint> vKeys;
+  bool bNoMore = false;
+  int serial = 0; /* creation order; stands in for the node's address in the (size, pointer) sort */
+  void DivideNode(ExtractorNode& n1, ExtractorNode& n2, ExtractorNode& n3, ExtractorNode& n4) const {
+    const int halfX = (int)std::ceil((float)(URx - ULx) / 2);
+    const int halfY = (int)std::ceil((float)(BRy - ULy) / 2);
+    n1.ULx = ULx, n1.ULy = ULy, n1.URx = ULx + halfX, n1.BRy = ULy + halfY;
+    n2.ULx = n1.URx, n2.ULy = ULy, n2.URx = URx, n2.BRy = ULy + halfY;
+    n3.ULx = ULx, n3.ULy = n1.BRy, n3.URx = n1.URx, n3.BRy = BRy;
+    n4.ULx = n3.URx, n4.ULy = n3.ULy, n4.URx = URx, n4.BRy = BRy;
+    for (const orc_keypoint& kp : vKeys) {
+      if (kp.x < n1.URx) {
+        if (kp.y < n1.BRy)
+          n1.vKeys.push_back(kp);
+        else
+          n3.vKeys.push_back(kp);
+      } else if (kp.y < n1.BRy)
+        n2.vKeys.push_back(kp);
+      else
+        n4.vKeys.push_back(kp);
+    }
+    n1.bNoMore = n1.vKeys.size() == 1;
+    n2.bNoMore = n2.vKeys.size() == 1;
+    n3.bNoMore = n3.vKeys.size() == 1;
+    n4.bNoMore = n4.vKeys.size() == 1;
+  }
+};
+}  // namespace
+#include <list>
+namespace {
+typedef std::list<ExtractorNode> NodeList;
+
+std::vector<orc_keypoint> distribute_oct_tree(const std::vector<orc_keypoint>& vToDistributeKeys, int minX, int maxX, int minY,
+                                              int maxY, int N) {
+  const int nIni = (int)std::round((float)(maxX - minX) / (maxY - minY));
+  const float hX = (float)(maxX - minX) / nIni;
+  NodeList lNodes;
+  std::vector<ExtractorNode*> vpIniNodes((size_t)nIni);
+  int serial = 0;
+  for (int i = 0; i < nIni; i++) {
+    ExtractorNode ni;
+    ni.ULx = (int)(hX * (float)i);
+    ni.URx = (int)(hX * (float)(i + 1));
+    ni.ULy = 0;
+    ni.BRy = maxY - minY;
+    ni.serial = serial++;
+    lNodes.push_back(ni);
+    vpIniNodes[i] = &lNodes.back();
+  }
+  for (const orc_keypoint& kp : vToDistributeKeys) vpIniNodes[(size_t)(kp.x / hX)]->vKeys.push_back(kp);
+  for (NodeList::iterator lit = lNodes.begin(); lit != lNodes.end();) {
+    if (lit->vKeys.size() == 1) {
+      lit->bNoMore = true;
+      ++lit;
+    } else if (lit->vKeys.empty())
+      lit = lNodes.erase(lit);
+    else
+      ++lit;
+  }
+  bool bFinish = false;
+  typedef std::pair<int, std::pair<int, NodeList::iterator>> SizeAndNode; /* (size, (serial, node)) */
+  std::vector<SizeAndNode> vSizeAndPointerToNode;
+  auto add_child = [&](ExtractorNode& n, int* nToExpand) {
+    if (n.vKeys.size() > 0) {
+      n.serial = serial++;
+      lNodes.push_front(n);
+      if (n.vKeys.size() > 1) {
+        if (nToExpand) ++*nToExpand;
+        vSizeAndPointerToNode.push_back(std::make_pair((int)n.vKeys.size(), std::make_pair(n.serial, lNodes.begin())));
+      }
+    }
+  };
+  while (!bFinish) {
+    int prevSize = (int)lNodes.size();
+    NodeList::iterator lit = lNodes.begin();
+    int nToExpand = 0;
+    vSizeAndPointerToNode.clear();
+    while (lit != lNodes.end()) {
+      if (lit->bNoMore) {
+        ++lit;
+        continue;
+      }
+      ExtractorNode n1, n2, n3, n4;
+      lit->DivideNode(n1, n2, n3, n4);
+      add_child(n1, &nToExpand);
+      add_child(n2, &nToExpand);
+      add_child(n3, &nToExpand);
+      add_child(n4, &nToExpand);
+      lit = lNodes.erase(lit);
+    }
+    if ((int)lNodes.size() >= N || (int)lNodes.size() == prevSize) {
+      bFinish = true;
+    } else if ((int)lNodes.size() + nToExpand * 3 > N) {
+      while (!bFinish) {
+        prevSize = (int)lNodes.size();
+        std::vector<SizeAndNode> vPrev = vSizeAndPointerToNode;
+        vSizeAndPointerToNode.clear();
+        std::sort(vPrev.begin(), vPrev.end(), [](const SizeAndNode& a, const SizeAndNode& b) {
+          return a.first < b.first || (a.first == b.first && a.second.first < b.second.first);
+        });
+        for (int j = (int)vPrev.size() - 1; j >= 0; j--) {
+          ExtractorNode n1, n2, n3, n4;
+          vPrev[j].second.second->DivideNode(n1, n2, n3, n4);
+          add_child(n1, nullptr);
+          add_child(n2, nullptr);
+          add_child(n3, nullptr);
+          add_child(n4, nullptr);
+          lNodes.erase(vPrev[j].second.second);
+          if ((int)lNodes.size() >= N) break;
+        }
+        if ((int)lNodes.size() >= N || (int)lNodes.size() == prevSize) bFinish = true;
+      }
+    }
+  }
+  std::vector<orc_keypoint> vResultKeys;
+  for (const ExtractorNode& n : lNodes) {
+    const orc_keypoint* pKP = &n.vKeys[0];
+    float maxResponse = pKP->response;
+    for (size_t k = 1; k < n.vKeys.size(); k++)
+      if (n.vKeys[k].response > maxResponse) {
+        pKP = &n.vKeys[k];
+        maxResponse = n.vKeys[k].response;
+      }
+    vResultKeys.push_back(*pKP);
+  }
+  return vResultKeys;
+}
+
+/* ORBextractor::ComputeKeyPointsOctTree.  Returns false where ORB-SLAM2 itself is undefined (a level too small for one
+ * 30-pixel cell, or nIni == 0: divisions by zero). */
+bool compute_keypoints_octree(const orc_extractor& e, const std::vector<Image>& pyr, std::vector<std::vector<orc_keypoint>>& all,
+                              orc_dump* dump, int* raw_kp_pos) {
+  all.assign(e.nlevels, {});
+  const float W = 30;
+  for (int level = 0; level < e.nlevels; ++level) {
+    const Image& L = pyr[level];
+    const int minBorderX = EDGE_THRESHOLD - 3, minBorderY = minBorderX;
+    const int maxBorderX = L.w - EDGE_THRESHOLD + 3, maxBorderY = L.h - EDGE_THRESHOLD + 3;
+    const float width = (float)(maxBorderX - minBorderX), height = (float)(maxBorderY - minBorderY);
+    const int nCols = (int)(width / W), nRows = (int)(height / W);
+    if (nCols <= 0 || nRows <= 0) return false;
+    const int wCell = (int)std::ceil(width / nCols), hCell = (int)std::ceil(height / nRows);
+    if ((int)std::round((float)(maxBorderX - minBorderX) / (maxBorderY - minBorderY)) < 1) return false;
+    std::vector<orc_keypoint> vToDistributeKeys;
+    for (int i = 0; i < nRows; i++) {
+      const float iniY = (float)(minBorderY + i * hCell);
+      float maxY = iniY + hCell + 6;
+      if (iniY >= maxBorderY - 3) continue;
+      if (maxY > maxBorderY) maxY = (float)maxBorderY;
+      for (int j = 0; j < nCols; j++) {
+        const float iniX = (float)(minBorderX + j * wCell);
+        float maxX = iniX + wCell + 6;
+        if (iniX >= maxBorderX - 6) continue;
+        if (maxX > maxBorderX) maxX = (float)maxBorderX;
+        const int y0 = (int)iniY, y1 = (int)maxY, x0 = (int)iniX, x1 = (int)maxX;
+        std::vector<orc_keypoint> vKeysCell;
+        fast_detect(L.inner() + (size_t)y0 * L.step + x0, x1 - x0, y1 - y0, L.step, e.iniThFAST, true, vKeysCell);
+        if (vKeysCell.empty())
+          fast_detect(L.inner() + (size_t)y0 * L.step + x0, x1 - x0, y1 - y0, L.step, e.minThFAST, true, vKeysCell);
+        for (orc_keypoint& k : vKeysCell) {
+          k.x += j * wCell;
+          k.y += i * hCell;
+          vToDistributeKeys.push_back(k);
+        }
+      }
+    }
+    if (dump)
+      for (const orc_keypoint& k : vToDistributeKeys) {
+        if (dump->raw_kps && *raw_kp_pos < dump->raw_kps_cap) {
+          dump->raw_kps[*raw_kp_pos] = k;
+          dump->raw_kps[*raw_kp_pos].octave = level;
+        }
+        ++*raw_kp_pos;
+      }
+    std::vector<orc_keypoint>& keypoints = all[level];
+    keypoints = distribute_oct_tree(vToDistributeKeys, minBorderX, maxBorderX, minBorderY, maxBorderY, e.mnFeaturesPerLevel[level]);
+    const int scaledPatchSize = (int)(PATCH_SIZE * e.mvScaleFactor[level]);
+    for (orc_keypoint& k : keypoints) {
+      k.x += minBorderX;
+      k.y += minBorderY;
+      k.octave = level;
+      k.size = (float)scaledPatchSize;
+    }
+  }
+  for (int level = 0; level < e.nlevels; ++level) {
+    const Image& L = pyr[level];
+    for (orc_keypoint& k : all[level])
+      k.angle = ic_angle(L.inner() + (ptrdiff_t)cv_round(k.y) * L.step + cv_round(k.x), (int)L.step, e.umax);
+  }
+  return true;
+}
+
 /* src/ORBextractor.cc:620-678 */
 int extract(const orc_extractor& e, const uint8_t* img, int w, int h, size_t step, orc_keypoint* kps, uint8_t* desc,
             int cap, orc_dump* dump) {
@@ -687,7 +892,10 @@ int extract(const orc_extractor& e, const uint8_t* img, int w, int h, size_t ste
   }
   std::vector<std::vector<orc_keypoint>> all;
   int raw_cell_pos = 0, raw_kp_pos = 0;
-  if (!compute_keypoints(e, pyr, w, h, all, dump, &raw_cell_pos, &raw_kp_pos)) return -1;
+  if (e.minThFAST >= 0) {
+    if (!compute_keypoints_octree(e, pyr, all, dump, &raw_kp_pos)) return -1;
+  } else if (!compute_keypoints(e, pyr, w, h, all, dump, &raw_cell_pos, &raw_kp_pos))
+    return -1;
   if (dump) dump->raw_kps_total = raw_kp_pos;
 
   int n = 0;
@@ -851,6 +1059,15 @@ orc_extractor* orc_create(const orc_params* p) {
   return e;
 }
 void orc_destroy(orc_extractor* e) { delete e; }
+void orc_set_orbslam2_mode(orc_extractor* e, int ini_th_fast, int min_th_fast) {
+  e->iniThFAST = ini_th_fast;
+  e->minThFAST = min_th_fast;
+}
+int orc_distribute_oct_tree(const orc_keypoint* keys, int n, int minX, int maxX, int minY, int maxY, int N, orc_keypoint* out, int cap) {
+  const std::vector<orc_keypoint> r = distribute_oct_tree(std::vector<orc_keypoint>(keys, keys + n), minX, maxX, minY, maxY, N);
+  for (size_t i = 0; i < r.size() && (int)i < cap; i++) out[i] = r[i];
+  return (int)r.size();
+}
 void orc_get_tables(const orc_extractor* e, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
                     int* n_per_level, int* umax) {
   for (int i = 0; i < e->nlevels; i++) {

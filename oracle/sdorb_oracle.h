@@ -62,6 +62,15 @@ void orc_pattern_rotate(int px, int py, float a, float b, int* drow, int* dcol);
 typedef struct orc_extractor orc_extractor;
 orc_extractor* orc_create(const orc_params* p);
 void orc_destroy(orc_extractor* e);
+/* Row f1: switches the extractor to the ORB-SLAM2-style mode -- per 30-pixel cell cv::FAST with
+ * iniThFAST, minThFAST where that finds nothing, then DistributeOctTree per level.  Not in /root/reference: restated from the
+ * public ORB-SLAM2 algorithm, PARITY UNPINNED against ORB-SLAM2 itself (see the comment in sdorb_oracle.cc).  min_th_fast < 0
+ * switches back to the reference's ComputeKeyPoints. */
+void orc_set_orbslam2_mode(orc_extractor* e, int ini_th_fast, int min_th_fast);
+/* ORBextractor::DistributeOctTree of ORB-SLAM2 on keypoints whose coordinates are relative to (minX, minY); returns the
+ * number of result keypoints (at most cap written). */
+int orc_distribute_oct_tree(const orc_keypoint* keys, int n, int minX, int maxX, int minY, int maxY, int N, orc_keypoint* out,
+                            int cap);
 /* tables: each array has nlevels entries; umax has 16. Any pointer may be NULL. */
 void orc_get_tables(const orc_extractor* e, float* scale, float* inv_scale, float* sigma2, float* inv_sigma2,
                     int* n_per_level, int* umax);

@@ -155,12 +155,15 @@ class ORBextractor:
 
     def __init__(self, nfeatures, scaleFactor, nlevels, thFAST, minThFAST=None, device=-1, max_width=1920,
                  max_height=1088, max_batch=64):
-        # The north-star 5-argument form (iniThFAST, minThFAST) maps iniThFAST -> thFAST; SD-SLAM has no
-        # fallback threshold, so minThFAST is accepted and ignored.
+        # minThFAST given (the north-star 5-argument form, thFAST = iniThFAST): the ORB-SLAM2-style mode -- 30-pixel cells
+        # with the ini / min threshold fallback and DistributeOctTree (not in SD-SLAM itself,
+        # SURVEY.md section 0).  None: the reference's ComputeKeyPoints.
         self._h = C.c_void_p()
         self.nfeatures, self.scaleFactor, self.nlevels, self.thFAST = nfeatures, scaleFactor, nlevels, thFAST
         self.max_batch = max_batch
-        p = _Params(nfeatures, scaleFactor, nlevels, thFAST, -1, device, max_width, max_height, max_batch)
+        self.minThFAST = minThFAST
+        p = _Params(nfeatures, scaleFactor, nlevels, thFAST, -1 if minThFAST is None else int(minThFAST), device, max_width,
+                    max_height, max_batch)
         self._check(lib().sdorb_create(C.byref(p), C.byref(self._h)))
         self.max_keypoints = lib().sdorb_max_keypoints(self._h)
         n = nlevels

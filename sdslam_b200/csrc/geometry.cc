@@ -107,8 +107,10 @@ static void resize_axis(int src, int dst, bool horizontal, ResizeTap* out) {
   }
 }
 
+int octree_level_slots(int n_desired, int n_ini) { return std::max(std::max(n_desired, 0) + 3, 4 * n_ini); }
+
 int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int height, FrameGeom* g,
-                     std::vector<ResizeTap>* taps, std::vector<ResizeGroup>* groups) {
+                     std::vector<ResizeTap>* taps, std::vector<ResizeGroup>* groups, int min_th_fast) {
   if (width <= 0 || height <= 0 || width > SDORB_MAX_DIM || height > SDORB_MAX_DIM) return -1;
   *g = FrameGeom{};
   g->nlevels = t.nlevels;
@@ -116,6 +118,13 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
   g->height = height;
   g->nfeatures = nfeatures;
   g->th_fast = std::min(std::max(th_fast, 0), 255);  // cv::FAST clamps the threshold
+  if (min_th_fast >= 0) {
+    // ORB-SLAM2-style mode: FAST runs once with the smaller threshold -- a keypoint for
+    // iniThFAST is exactly a keypoint for minThFAST whose score reaches iniThFAST -- and the cells choose afterwards
+    g->octree = 1;
+    g->ini_th = g->th_fast;
+    g->th_fast = std::min(g->th_fast, std::min(min_th_fast, 255));
+  }
   taps->clear();
   if (groups) groups->clear();
   const float ratio = (float)width / height;
@@ -134,14 +143,52 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
     L.scaled_patch_size = (int)(31 * t.scale[l]);
     L.max_bx = L.w - SDORB_EDGE;
     L.max_by = L.h - SDORB_EDGE;
-    L.cols = (int)std::sqrt((float)L.n_desired / (5 * ratio));
-    L.rows = (int)(ratio * L.cols);
+    L.cols = g->octree ? 0 : (int)std::sqrt((float)L.n_desired / (5 * ratio));
+    L.rows = g->octree ? 0 : (int)(ratio * L.cols);
     L.cell_base = cell_base;
     L.sel_base = sel_base;
     L.list_base = list_base;
     sel_base += std::max(L.n_desired, 0);
     bool any_detect = false;
-    if (L.cols > 0 && L.rows > 0) {
+    if (g->octree) {
+      // ComputeKeyPointsOctTree of ORB-SLAM2: cells of about 30 pixels over [16, w-16) x [16, h-16); cell (i, j) is the ROI
+      // [16 + j*wCell, +wCell+6) clipped at w-16, skipped from iniX >= maxBorderX-6 / iniY >= maxBorderY-3 on; its
+      // detectable rectangle starts at 19 + j*wCell like the reference's cells, so the same kernels serve both grids.
+      const int min_b = SDORB_EDGE - 3, bx1 = L.w - SDORB_EDGE + 3, by1 = L.h - SDORB_EDGE + 3;
+      const float wf = (float)(bx1 - min_b), hf = (float)(by1 - min_b);
+      const int ncols = (int)(wf / 30.f), nrows = (int)(hf / 30.f);
+      if (ncols <= 0 || nrows <= 0) return -4;  // ORB-SLAM2 divides by zero here
+      L.cell_w = (int)std::ceil(wf / ncols);
+      L.cell_h = (int)std::ceil(hf / nrows);
+      L.n_ini = (int)std::round((float)(bx1 - min_b) / (by1 - min_b));
+      if (L.n_ini < 1) return -4;  // ... and here (portrait levels)
+      if (L.n_ini > 8) return -7;
+      L.h_x = (float)(bx1 - min_b) / L.n_ini;
+      // rows / columns whose ROI is at least 7 pixels, i.e. that can hold a keypoint: iniX <= maxBorderX - 7
+      L.cols = L.rows = 0;
+      for (int j = 0; j < ncols; ++j)
+        if (min_b + j * L.cell_w <= bx1 - 7) L.cols = j + 1;
+      for (int i = 0; i < nrows; ++i)
+        if (min_b + i * L.cell_h <= by1 - 7) L.rows = i + 1;
+      L.cell_w_magic = L.cell_w >= 2 ? (uint32_t)(0x100000000ull / (uint64_t)L.cell_w) + 1u : 0u;
+      L.cell_h_magic = L.cell_h >= 2 ? (uint32_t)(0x100000000ull / (uint64_t)L.cell_h) + 1u : 0u;
+      L.n_features_cell = 0;
+      sel_base += octree_level_slots(L.n_desired, L.n_ini) - std::max(L.n_desired, 0);  // DistributeOctTree may return more than N
+      if (L.cols > 0 && L.rows > 0) {
+        if ((int64_t)L.cols * L.rows > SDORB_MAX_CELLS_PER_LEVEL) return -7;
+        any_detect = true;
+        L.det_x1 = L.max_bx;
+        L.det_y1 = L.max_by;
+        L.last_x0 = SDORB_EDGE + (L.cols - 1) * L.cell_w;
+        L.last_y0 = SDORB_EDGE + (L.rows - 1) * L.cell_h;
+        const int cw = std::min(L.cell_w, L.max_bx - SDORB_EDGE), ch = std::min(L.cell_h, L.max_by - SDORB_EDGE);
+        L.list_cap_cell = ((cw + 1) / 2) * ((ch + 1) / 2);
+        cell_base += L.rows * L.cols;
+        list_base += (int64_t)L.list_cap_cell * L.rows * L.cols;
+      } else {
+        L.cols = L.rows = 0;
+      }
+    } else if (L.cols > 0 && L.rows > 0) {
       if ((int64_t)L.cols * L.rows > SDORB_MAX_CELLS_PER_LEVEL) return -7;
       const int W = L.max_bx - SDORB_EDGE, H = L.max_by - SDORB_EDGE;
       L.cell_w = (int)std::ceil((float)W / L.cols);

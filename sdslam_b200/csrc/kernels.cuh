@@ -3,6 +3,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
+
 #include "sdorb_internal.h"
 
 namespace sdorb {
@@ -25,6 +27,8 @@ struct SelectBuffers {
   uint32_t* sel;        // [batch][sel_total]  selected entries, level-major, in output order
   int32_t* sel_count;   // [batch][nlevels]
   int32_t* error_flag;  // device int: set to SDORB_ERR_OVERFLOW magnitude when a fixed-capacity list overflows
+  uint32_t* okeys;      // [batch][list_total]   ORB-SLAM2-style mode: vToDistributeKeys of every level, contiguous
+  uint16_t* onode;      // [batch][list_total]   ... and the list position of each keypoint's quadtree node
 };
 
 // ComputePyramid: level l from level l-1 for every frame (cv::resize INTER_LINEAR fixed point).
@@ -38,6 +42,10 @@ void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPla
 // Quota redistribution + retainBest per cell + retainBest per level.
 void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b, int nframes,
                    cudaStream_t s);
+// ORB-SLAM2-style mode (FrameGeom::octree): gather_cells_kernel with the ini / min threshold choice per cell, then
+// DistributeOctTree per (level, frame) (kernels_octree.cu).
+void launch_octree(const FrameGeom* d_geom, const FrameGeom& g, const SelectBuffers& b, int nframes, cudaStream_t s);
+int configure_octree_kernel();
 // Test hook: std::nth_element(a, a + nth, a + n, response >) as the selection kernel performs it (one warp).
 void launch_debug_nth_element(uint32_t* d_entries, int n, int nth, cudaStream_t s);
 // IC_Angle + rBRIEF descriptor + output assembly (coordinate scaling, cv::KeyPoint layout).

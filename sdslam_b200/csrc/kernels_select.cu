@@ -223,7 +223,23 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_cells_kernel(const F
   const uint8_t* map = p.nms + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
   uint32_t* list = buf.cell_list + (int64_t)frame * geom->list_total + L.list_base + (int64_t)c * L.list_cap_cell;
   const CellRect r = cell_rect(L, c / L.cols, c % L.cols);
-  const int n = scan_cell<4>(map, L.pitch, r, geom->th_fast, lane, list, L.list_cap_cell);
+  int n = scan_cell<4>(map, L.pitch, r, geom->th_fast, lane, list, L.list_cap_cell);
+  if (geom->octree && n > 0 && n <= L.list_cap_cell) {
+    // ORB-SLAM2-style mode: the cell keeps its iniThFAST keypoints, all of them (minThFAST) only when it has none of those.
+    // In-place compaction in order: a step's reads precede its writes and a write never passes its own read index.
+    const uint32_t lt = (1u << lane) - 1u;
+    int hi = 0;
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const uint32_t e = i < n ? list[i] : 0u;
+      const bool keep = i < n && SDORB_ENTRY_SCORE(e) >= geom->ini_th;
+      const uint32_t b = __ballot_sync(0xffffffffu, keep);
+      if (keep) list[hi + __popc(b & lt)] = e;
+      hi += __popc(b);
+    }
+    if (hi > 0) n = hi;
+  }
   if (lane == 0) {
     *seen = n;
     if (n > L.list_cap_cell) atomicExch(buf.error_flag, 6);  // cannot happen: the capacity bounds what strict NMS leaves
@@ -383,6 +399,10 @@ void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlane
   select_caps(g, &mc, &lc);
   if (g.cells_total > 0)
     gather_cells_kernel<<<dim3((g.cells_total + GATHER_WARPS - 1) / GATHER_WARPS, nframes), GATHER_WARPS * 32, 0, s>>>(d_geom, p, b);
+  if (g.octree) {
+    launch_octree(d_geom, g, b, nframes, s);
+    return;
+  }
   select_kernel<<<dim3(g.nlevels, nframes), SEL_THREADS, select_smem_bytes(g), s>>>(d_geom, b, mc, lc);
 }
 

@@ -45,6 +45,8 @@ struct sdorb_handle {
   uint8_t* d_stage_in[2] = {nullptr, nullptr};
   int32_t *d_cell_seen = nullptr, *d_sel_count = nullptr, *d_error = nullptr;
   uint32_t *d_cell_list = nullptr, *d_sel = nullptr;
+  uint32_t* d_okeys = nullptr;  // ORB-SLAM2-style mode only
+  uint16_t* d_onode = nullptr;
   // output staging for the host path (2 slots)
   sdorb_keypoint* d_kps[2] = {nullptr, nullptr};
   uint8_t* d_desc[2] = {nullptr, nullptr};
@@ -108,6 +110,8 @@ void free_geometry_scratch(sdorb_handle* h) {
   dfree(h->d_stage_in[1]);
   dfree(h->d_cell_seen);
   dfree(h->d_cell_list);
+  dfree(h->d_okeys);
+  dfree(h->d_onode);
   dfree(h->d_sel);
   dfree(h->d_sel_count);
   for (int i = 0; i < 2; ++i) {
@@ -135,7 +139,7 @@ int ensure_geometry(sdorb_handle* h, int width, int height) {
   FrameGeom g;
   std::vector<ResizeTap> taps;
   std::vector<ResizeGroup> groups;
-  const int ge = build_frame_geom(h->tables, h->prm.nfeatures, h->prm.th_fast, width, height, &g, &taps, &groups);
+  const int ge = build_frame_geom(h->tables, h->prm.nfeatures, h->prm.th_fast, width, height, &g, &taps, &groups, h->prm.min_th_fast);
   if (ge) return geom_err(ge);
   CU(cudaStreamSynchronize(h->s_compute));
   free_geometry_scratch(h);
@@ -154,6 +158,10 @@ int ensure_geometry(sdorb_handle* h, int width, int height) {
   CU(cudaMalloc(&h->d_cell_seen, cells_bytes));
   CU(cudaMemset(h->d_cell_seen, 0, cells_bytes));
   CU(cudaMalloc(&h->d_cell_list, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
+  if (g.octree) {
+    CU(cudaMalloc(&h->d_okeys, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
+    CU(cudaMalloc(&h->d_onode, sizeof(uint16_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
+  }
   CU(cudaMalloc(&h->d_sel, sizeof(uint32_t) * std::max<size_t>((size_t)g.sel_total * B, 1)));
   CU(cudaMalloc(&h->d_sel_count, sizeof(int32_t) * (size_t)g.nlevels * B));
   h->geom = g;
@@ -224,7 +232,7 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
   planes.blur = h->d_blur;
   planes.nms = h->d_nms;
   planes.batch_cap = h->prm.max_batch;
-  SelectBuffers sb{h->d_cell_seen, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error};
+  SelectBuffers sb{h->d_cell_seen, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error, h->d_okeys, h->d_onode};
   {
     StageScope st(h, s, SDORB_STAGE_PYRAMID);
     for (int l = 1; l < g.nlevels; ++l) {
@@ -311,7 +319,6 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
       params->max_batch > 65535 || params->max_width <= 0 || params->max_height <= 0 ||
       params->max_width > SDORB_MAX_DIM || params->max_height > SDORB_MAX_DIM || !(params->scale_factor > 0.f))
     return SDORB_ERR_BAD_ARG;
-  if (params->min_th_fast >= 0) return SDORB_ERR_UNSUPPORTED;  // ORB-SLAM2 ini/min mode is not part of this reference
   sdorb_handle* h = new (std::nothrow) sdorb_handle;
   if (!h) return SDORB_ERR_NOMEM;
   h->prm = *params;
@@ -343,7 +350,8 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (cudaMemcpy(h->d_umax, h->tables.umax, sizeof(int) * 16, cudaMemcpyHostToDevice) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaMalloc(&h->d_error, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
   if (cudaMemset(h->d_error, 0, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_CUDA);
-  if (configure_kernels() != 0 || configure_frame_kernels() != 0 || configure_search_kernels() != 0) return fail(SDORB_ERR_CUDA);
+  if (configure_kernels() != 0 || configure_frame_kernels() != 0 || configure_search_kernels() != 0 || configure_octree_kernel() != 0)
+    return fail(SDORB_ERR_CUDA);
   *out = h;
   return SDORB_OK;
 }
@@ -396,7 +404,9 @@ int sdorb_get_tables(const sdorb_handle* h, float* sf, float* isf, float* s2, fl
 int sdorb_max_keypoints(const sdorb_handle* h) {
   if (!h) return SDORB_ERR_BAD_ARG;
   int s = 0;
-  for (int v : h->tables.n_per_level) s += std::max(v, 0);
+  // ORB-SLAM2-style mode: DistributeOctTree returns up to N + 2 keypoints per level, or the 4 children of each of its
+  // (at most 8) initial nodes
+  for (int v : h->tables.n_per_level) s += h->prm.min_th_fast >= 0 ? octree_level_slots(v, 8) : std::max(v, 0);
   return s;
 }
 

@@ -54,13 +54,17 @@ struct LevelGeom {
   float scale;           // mvScaleFactor[level]
   int coef_x_base, coef_y_base;  // offsets into the resize coefficient tables (entries), levels >= 1
   int group_base;        // first ResizeGroup of this level (levels >= 1), -1 when the 8-byte window does not fit (scale > ~2)
+  int n_ini;             // ORB-SLAM2-style mode: initial quadtree nodes, round(width / height) of the bordered level
+  float h_x;             // ... and their width hX
 };
 
 struct FrameGeom {
   int nlevels;
   int width, height;
   int nfeatures;
-  int th_fast;
+  int th_fast;           // threshold the FAST kernel runs with (ORB-SLAM2-style mode: min(iniThFAST, minThFAST))
+  int octree;            // 1 = ORB-SLAM2-style mode: 30-pixel cells, ini / min threshold, DistributeOctTree
+  int ini_th;            // iniThFAST of that mode
   int cells_total;      // per-frame cells over all levels
   int sel_total;        // per-frame selected-entry slots (sum of n_desired)
   int tiles_total_fast, tiles_total_fastn, tiles_total_blur;

@@ -59,7 +59,91 @@ def tables(nfeatures, scale_factor, nlevels):
     return sf, inv, npl, umax
 
 
-def extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, th_fast=20):
+def octree_cells(level, ini_th, min_th):
+    """ORB-SLAM2 ComputeKeyPointsOctTree, the cell loop: real cv2 FAST on every 30-pixel cell ROI with iniThFAST, with
+    minThFAST where that finds nothing.  Returns vToDistributeKeys as (x, y, response) relative to (minBorderX, minBorderY)."""
+    lh, lw = level.shape
+    det = [cv2.FastFeatureDetector_create(threshold=t, nonmaxSuppression=True, type=cv2.FAST_FEATURE_DETECTOR_TYPE_9_16)
+           for t in (ini_th, min_th)]
+    min_bx = min_by = EDGE - 3
+    max_bx, max_by = lw - EDGE + 3, lh - EDGE + 3
+    width, height = f32(max_bx - min_bx), f32(max_by - min_by)
+    ncols, nrows = int(width / f32(30)), int(height / f32(30))
+    wcell, hcell = int(np.ceil(width / f32(ncols))), int(np.ceil(height / f32(nrows)))
+    keys = []
+    for i in range(nrows):
+        ini_y = min_by + i * hcell
+        if ini_y >= max_by - 3:
+            continue
+        max_y = min(ini_y + hcell + 6, max_by)
+        for j in range(ncols):
+            ini_x = min_bx + j * wcell
+            if ini_x >= max_bx - 6:
+                continue
+            max_x = min(ini_x + wcell + 6, max_bx)
+            roi = level[ini_y:max_y, ini_x:max_x]
+            found = det[0].detect(roi)
+            if not found:
+                found = det[1].detect(roi)
+            keys += [(k.pt[0] + j * wcell, k.pt[1] + i * hcell, k.response) for k in found]
+    return keys, (min_bx, max_bx, min_by, max_by)
+
+
+def distribute_oct_tree(keys, min_x, max_x, min_y, max_y, n_wanted):
+    """ORB-SLAM2 DistributeOctTree written as whole-list passes over arrays instead of std::list surgery (the form the CUDA
+    kernel uses): the list is always in descending creation order because every node enters at the front; a node is
+    (x0, x1, y0, y1, [key indices in input order]).  Equal sizes in the (size, pointer) sort: later-created node first."""
+    if not keys:
+        return []
+    n_ini = int(math.floor(float(f32(max_x - min_x) / f32(max_y - min_y)) + 0.5))
+    hx = f32(max_x - min_x) / f32(n_ini)
+    ini = [[int(hx * f32(i)), int(hx * f32(i + 1)), 0, max_y - min_y, []] for i in range(n_ini)]
+    for k, (x, y, r) in enumerate(keys):
+        ini[int(f32(x) / hx)][4].append(k)
+    nodes = [nd for nd in ini if nd[4]]  # front .. back
+
+    def divide(nd):
+        x0, x1, y0, y1, ks = nd
+        sx = x0 + int(math.ceil(float(f32(x1 - x0) / f32(2))))
+        sy = y0 + int(math.ceil(float(f32(y1 - y0) / f32(2))))
+        ch = [[x0, sx, y0, sy, []], [sx, x1, y0, sy, []], [x0, sx, sy, y1, []], [sx, x1, sy, y1, []]]
+        for k in ks:
+            x, y, _ = keys[k]
+            ch[(0 if x < sx else 1) + (0 if y < sy else 2)][4].append(k)
+        return [c for c in ch if c[4]]
+
+    sorted_mode = False
+    while True:
+        prev = len(nodes)
+        cand = [i for i, nd in enumerate(nodes) if len(nd[4]) > 1]  # list order = newest first
+        if sorted_mode:
+            cand.sort(key=lambda i: (-len(nodes[i][4]), i))  # biggest first; equal sizes: newest (= smallest position) first
+        created, done, size = [], set(), len(nodes)
+        for i in cand:
+            ch = divide(nodes[i])
+            created += ch
+            done.add(i)
+            size += len(ch) - 1
+            if sorted_mode and size >= n_wanted:
+                break
+        n_expand = sum(1 for c in created if len(c[4]) > 1)
+        nodes = created[::-1] + [nd for i, nd in enumerate(nodes) if i not in done]
+        if len(nodes) >= n_wanted or len(nodes) == prev:
+            break
+        if not sorted_mode and len(nodes) + 3 * n_expand > n_wanted:
+            sorted_mode = True
+    out = []
+    for nd in nodes:
+        best = nd[4][0]
+        for k in nd[4][1:]:
+            if keys[k][2] > keys[best][2]:
+                best = k
+        out.append(keys[best])
+    return out
+
+
+def extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, th_fast=20, min_th_fast=None):
+    """min_th_fast given: the ORB-SLAM2-style mode (th_fast = iniThFAST), SURVEY.md section 8 row f1."""
     assert img.dtype == np.uint8 and img.ndim == 2
     h0, w0 = img.shape
     sf, inv, npl, umax = tables(nfeatures, scale_factor, nlevels)
@@ -82,7 +166,10 @@ def extract(img, nfeatures=1000, scale_factor=1.2, nlevels=8, th_fast=20):
         cols = int(np.sqrt(f32(ndes) / (f32(5) * ratio)))
         rows = int(ratio * f32(cols))
         kps = []  # (x, y, response)
-        if cols > 0 and rows > 0:
+        if min_th_fast is not None:
+            keys, (bx0, bx1, by0, by1) = octree_cells(level, th_fast, min_th_fast)
+            kps = [(x + bx0, y + by0, r) for x, y, r in distribute_oct_tree(keys, bx0, bx1, by0, by1, ndes)]
+        elif cols > 0 and rows > 0:
             max_bx, max_by = lw - EDGE, lh - EDGE
             W, H = max_bx - EDGE, max_by - EDGE
             cw, ch = int(np.ceil(f32(W) / f32(cols))), int(np.ceil(f32(H) / f32(rows)))

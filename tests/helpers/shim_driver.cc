@@ -1,6 +1,7 @@
 // Exercises include/ORBextractor.h (the C++ drop-in for SD_SLAM::ORBextractor) the way Frame / Tracking do
 // (/root/reference/src/Tracking.cc:98, src/Frame.cc:78-84,195) and dumps the results for tests/test_cpp_shim.py.
-//   shim_driver <in.raw> <w> <h> <nfeatures> <scale> <nlevels> <thFAST> <out.bin>
+//   shim_driver <in.raw> <w> <h> <nfeatures> <scale> <nlevels> <thFAST> <out.bin> [minThFAST]
+// With minThFAST the north-star 5-argument constructor (iniThFAST, minThFAST: the ORB-SLAM2-style mode) is used.
 // out.bin: int32 n | n*28 B keypoints | n*32 B descriptors | int32 nlevels | per level: int32 w, h, step-padded (w+38)*(h+38) bytes
 //          | nlevels*4 floats of the getters | int32 distance(d0,d1) | 4*int32 best-two of row 0 against all rows
 #include <cstdio>
@@ -10,14 +11,16 @@
 #include "ORBextractor.h"
 
 int main(int argc, char** argv) {
-  if (argc != 9) return 2;
+  if (argc != 9 && argc != 10) return 2;
   const int w = atoi(argv[2]), h = atoi(argv[3]);
   std::vector<unsigned char> raw((size_t)w * h);
   FILE* f = fopen(argv[1], "rb");
   if (!f || fread(raw.data(), 1, raw.size(), f) != raw.size()) return 3;
   fclose(f);
   try {
-    SD_SLAM::ORBextractor* mpORBextractorLeft = new SD_SLAM::ORBextractor(atoi(argv[4]), (float)atof(argv[5]), atoi(argv[6]), atoi(argv[7]));
+    SD_SLAM::ORBextractor* mpORBextractorLeft =
+        argc == 10 ? new SD_SLAM::ORBextractor(atoi(argv[4]), (float)atof(argv[5]), atoi(argv[6]), atoi(argv[7]), atoi(argv[9]))
+                   : new SD_SLAM::ORBextractor(atoi(argv[4]), (float)atof(argv[5]), atoi(argv[6]), atoi(argv[7]));
     cv::Mat im(h, w, CV_8UC1, raw.data(), (size_t)w);
     std::vector<cv::KeyPoint> mvKeys;
     cv::Mat mDescriptors;

@@ -117,8 +117,8 @@ def test_bad_arguments_rejected_without_touching_cuda():
     assert L.sdorb_create(None, C.byref(h)) == -1
     p = api._Params(1000, 1.2, 0, 20, -1, 0, 640, 480, 4)  # nlevels 0
     assert L.sdorb_create(C.byref(p), C.byref(h)) == -1 and not h.value
-    p = api._Params(1000, 1.2, 8, 20, 7, 0, 640, 480, 4)   # ORB-SLAM2 ini/min mode: not in this reference
-    assert L.sdorb_create(C.byref(p), C.byref(h)) == -7 and not h.value
+    p = api._Params(1000, 1.2, 8, 20, 7, 0, 640, 480, 0)   # max_batch 0 (the ORB-SLAM2-style mode itself is accepted: row f1)
+    assert L.sdorb_create(C.byref(p), C.byref(h)) == -1 and not h.value
     assert L.sdorb_extract(None, None, 0, 0, 0, None, None, 0, None, None) == -1
     assert L.sdorb_kernel_launches(None) == 0
 

@@ -37,12 +37,14 @@ def test_shim_compiles_and_keeps_the_reference_surface(driver):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("w,h,params", [(640, 480, (1000, 1.2, 8, 20)), (320, 240, (500, 2.0, 3, 20))])
+@pytest.mark.parametrize("w,h,params", [(640, 480, (1000, 1.2, 8, 20)), (320, 240, (500, 2.0, 3, 20)),
+                                        (640, 480, (1000, 1.2, 8, 20, 7))])
 def test_shim_driver_equals_oracle(driver, tmp_path, w, h, params):
+    """Four constructor arguments: the reference; five (iniThFAST, minThFAST): the ORB-SLAM2-style mode (row f1)."""
     img = synth.smooth_noise(77, w, h)
     raw, out = str(tmp_path / "in.raw"), str(tmp_path / "out.bin")
     img.tofile(raw)
-    subprocess.check_call([driver, raw, str(w), str(h)] + [str(p) for p in params] + [out])
+    subprocess.check_call([driver, raw, str(w), str(h)] + [str(p) for p in params[:4]] + [out] + [str(p) for p in params[4:]])
     buf = open(out, "rb").read()
     off = 0
     (n,) = struct.unpack_from("<i", buf, off)
@@ -51,7 +53,7 @@ def test_shim_driver_equals_oracle(driver, tmp_path, w, h, params):
     off += 28 * n
     d = np.frombuffer(buf, np.uint8, 32 * n, off).reshape(n, 32)
     off += 32 * n
-    o = orc.Extractor(*params)
+    o = orc.Extractor(*params[:4], min_th_fast=params[4] if len(params) > 4 else None)
     ok, od, st = o.extract(img, dump=True)
     assert n == len(ok) and k.tobytes() == ok.tobytes() and np.array_equal(d, od)
     (nl,) = struct.unpack_from("<i", buf, off)
