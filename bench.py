@@ -266,9 +266,19 @@ def run_ours(args):
         except Exception as e:  # not fatal: affinity is an optimisation
             numa = "unset (%s)" % type(e).__name__
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL writes its version banner to stdout when the first communicator comes up; rank 0 must print exactly one JSON
+        # line, so file descriptor 1 points at stderr until the communicator exists
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     w, h, nf, sf, nl, th, frames_per_gpu = WORKLOADS[args.workload]
     if args.frames:
         frames_per_gpu = args.frames

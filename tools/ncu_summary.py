@@ -24,7 +24,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 def main():
     rep = sys.argv[1]
-    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv"], text=True)
+    raw = subprocess.check_output(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], text=True)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
