@@ -291,6 +291,22 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
       L.coef_y_base = (int)taps->size();
       taps->resize(taps->size() + L.h);
       resize_axis(P.h, L.h, false, taps->data() + L.coef_y_base);
+      {
+        // source rows touched by every group of 8 destination rows: one contiguous, ascending range for the prefetching kernel
+        const ResizeTap* tyv = taps->data() + L.coef_y_base;
+        int span = 0;
+        bool ok = true;
+        for (int y = 0; y < L.h && ok; ++y) {
+          const ResizeTap& tp = tyv[y];
+          if (tp.s1 != tp.s0 && tp.s1 != tp.s0 + 1) ok = false;
+          if (y > 0 && (tp.s1 < tyv[y - 1].s1 || tp.s0 < tyv[y - 1].s0)) ok = false;
+        }
+        for (int y = 0; y < L.h && ok; y += 8) {
+          const int yl = std::min(y + 8, L.h) - 1;
+          span = std::max(span, (int)tyv[yl].s1 - (int)tyv[y].s0 + 1);
+        }
+        L.rz_span = ok ? span : 0;
+      }
       // four destination pixels per group, all taps inside one 8-byte source window
       L.group_base = -1;
       if (groups) {

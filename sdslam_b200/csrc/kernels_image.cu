@@ -36,12 +36,18 @@ __device__ __forceinline__ uint32_t ldg_word_if(const uint8_t* ptr, int on) {
   return v;
 }
 
+// The three source words that hold every tap of four destination pixels in one source row.
+struct ResizeRaw {
+  uint32_t w0, w1, w2;
+};
+__device__ __forceinline__ void resize_fetch(const uint8_t* __restrict__ row, int on, int ld1, int ld2, ResizeRaw& r) {
+  r.w0 = ldg_word_if(row, on);
+  r.w1 = ldg_word_if(row + 4, on & ld1);
+  r.w2 = ldg_word_if(row + 8, on & ld2);
+}
 // horizontal pass of one source row for four destination pixels, already shifted: a[i] = (c0*s0 + c1*s1) >> 4
-__device__ __forceinline__ void resize_hrow(const uint8_t* __restrict__ row, int ld1, int ld2, int shift, const ResizeGroup& G,
-                                            uint32_t (&a)[4]) {
-  const uint32_t w0 = *reinterpret_cast<const uint32_t*>(row);
-  const uint32_t w1 = ldg_word_if(row + 4, ld1), w2 = ldg_word_if(row + 8, ld2);
-  const uint32_t lo = __funnelshift_r(w0, w1, shift), hi = __funnelshift_r(w1, w2, shift);
+__device__ __forceinline__ void resize_hrow(const ResizeRaw& r, int shift, const ResizeGroup& G, uint32_t (&a)[4]) {
+  const uint32_t lo = __funnelshift_r(r.w0, r.w1, shift), hi = __funnelshift_r(r.w1, r.w2, shift);
   const uint32_t p01 = __byte_perm(lo, hi, G.sel01), p23 = __byte_perm(lo, hi, G.sel23);
   a[0] = __dp2a_lo(G.coef[0], p01, 0u) >> 4;
   a[1] = __dp2a_hi(G.coef[1], p01, 0u) >> 4;
@@ -50,6 +56,9 @@ __device__ __forceinline__ void resize_hrow(const uint8_t* __restrict__ row, int
 }
 
 // One thread = 4 consecutive destination pixels x RZ_ROWS consecutive rows.  Block (32, 4): 128 x 64 pixels.
+// The kernel waits on memory, not on issue slots (ncu: long-scoreboard stalls): a thread walks down its source rows and
+// a row's words are needed as soon as they are asked for.  So the walk is software-pipelined: the source words of
+// destination row j+1 (and the vertical taps of row j+2) are requested before row j is computed.
 // Coefficients are non-negative on this path (checked when the groups are built), so every intermediate fits an
 // unsigned lane and the result needs no clamp: the two products of a pixel are cut to their upper halves two pixels at
 // a time (PRMT), summed with the rounding constant in 16-bit lanes and shifted as one word.
@@ -73,32 +82,117 @@ __global__ void __launch_bounds__(128) resize_level_kernel(const FrameGeom* __re
   // the eight bytes from src_x on hold every tap; words past the row's last word hold none
   const int ld1 = base + 4 <= last_word, ld2 = shift != 0 && base + 8 <= last_word;
   src += base;
-  const uint2* ty = reinterpret_cast<const uint2*>(taps + D.coef_y_base + y0);
+  const uint2* ty = reinterpret_cast<const uint2*>(taps + D.coef_y_base + y0);  // {s0 | s1 << 16, c0 | c1 << 16}
+  const int jlast = min(RZ_ROWS, dh - y0) - 1;  // rows past it repeat its taps: their requests are harmless re-reads
+  uint2 t = ty[0], t1 = ty[min(1, jlast)];
+  uint32_t s0 = t.x & 0xFFFFu, s1 = t.x >> 16;
+  int need0 = 1, need1 = s1 != s0;
+  ResizeRaw r0, r1;
+  resize_fetch(src + (uint64_t)(s0 * (uint32_t)spitch), need0, ld1, ld2, r0);
+  resize_fetch(src + (uint64_t)(s1 * (uint32_t)spitch), need1, ld1, ld2, r1);
   uint32_t a0[4], a1[4] = {0, 0, 0, 0};
-  uint32_t have = 0xFFFFFFFFu;  // source row held in a1
 #pragma unroll
   for (int j = 0; j < RZ_ROWS; ++j) {
-    if (y0 + j >= dh) break;
-    const uint2 t = ty[j];  // {s0 | s1 << 16, c0 | c1 << 16}
-    const uint32_t s0 = t.x & 0xFFFFu, s1 = t.x >> 16, c0 = t.y & 0xFFFFu, c1 = t.y >> 16;
-    if (s0 == have) {
+    if (j > jlast) break;
+    // requests of row j+1: a source row is new unless it is the one row j leaves behind (s1) / equals its partner
+    const uint2 tn = t1;
+    t1 = ty[min(j + 2, jlast)];
+    const uint32_t n0 = tn.x & 0xFFFFu, n1 = tn.x >> 16;
+    const int nneed0 = n0 != s1, nneed1 = n1 != n0;
+    ResizeRaw q0, q1;
+    resize_fetch(src + (uint64_t)(n0 * (uint32_t)spitch), nneed0, ld1, ld2, q0);
+    resize_fetch(src + (uint64_t)(n1 * (uint32_t)spitch), nneed1, ld1, ld2, q1);
+    // row j
+    const uint32_t c0 = t.y & 0xFFFFu, c1 = t.y >> 16;
+    if (need0) {
+      resize_hrow(r0, shift, G, a0);
+    } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) a0[i] = a1[i];
-    } else {
-      resize_hrow(src + (uint64_t)(s0 * (uint32_t)spitch), ld1, ld2, shift, G, a0);
     }
-    if (s1 != s0) {
-      resize_hrow(src + (uint64_t)(s1 * (uint32_t)spitch), ld1, ld2, shift, G, a1);
+    if (need1) {
+      resize_hrow(r1, shift, G, a1);
     } else {
 #pragma unroll
       for (int i = 0; i < 4; ++i) a1[i] = a0[i];
     }
-    have = s1;
     // v = (((c0 * a0) >> 16) + ((c1 * a1) >> 16) + 2) >> 2
     const uint32_t u01 = __byte_perm(c0 * a0[0], c0 * a0[1], 0x7632), u23 = __byte_perm(c0 * a0[2], c0 * a0[3], 0x7632);
     const uint32_t l01 = __byte_perm(c1 * a1[0], c1 * a1[1], 0x7632), l23 = __byte_perm(c1 * a1[2], c1 * a1[3], 0x7632);
     const uint32_t v01 = (u01 + l01 + 0x00020002u) >> 2, v23 = (u23 + l23 + 0x00020002u) >> 2;  // lanes <= 1022: no carry
     *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)j * (uint32_t)dpitch)) = __byte_perm(v01, v23, 0x6420);  // the pitch absorbs the tail
+    t = tn;
+    s0 = n0;
+    s1 = n1;
+    need0 = nneed0;
+    need1 = nneed1;
+    r0 = q0;
+    r1 = q1;
+  }
+}
+
+// The same arithmetic with every source word of the thread requested up front.  The row-walk kernel above waits for
+// memory once per destination row (ncu source page: all its stall samples sit on the first use of a row's words, and one row
+// of look-ahead does not cover the latency with the warps an SM holds).  The source rows of RZP_ROWS consecutive destination
+// rows are one contiguous range of at most KMAX rows (checked on the host per level), so this variant issues all of them
+// -- 3 * KMAX independent loads per thread -- before it touches any, then walks the rows in registers: H of source row k
+// is computed once and the destination row whose lower tap is row k (at most one per source row when shrinking, a second
+// one only where the last row is clamped) is emitted from H(k-1) / H(k).
+constexpr int RZP_ROWS = 8;
+template <int KMAX>
+__global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
+                                                               const ResizeTap* __restrict__ taps,
+                                                               const ResizeGroup* __restrict__ groups) {
+  const LevelGeom& D = geom->lv[level];
+  const LevelGeom& S = geom->lv[level - 1];
+  const int gi = blockIdx.x * 32 + threadIdx.x;
+  const int x4 = gi * 4;
+  const int y0 = (blockIdx.y * 4 + threadIdx.y) * RZP_ROWS;  // warp-uniform
+  const int frame = blockIdx.z;
+  const int dh = D.h;
+  if (y0 >= dh) return;
+  const int jn = min(RZP_ROWS, dh - y0);
+  // the vertical taps of the warp's rows live in its lanes: {s0 | s1 << 16, c0 | c1 << 16} of row y0 + lane
+  const uint2* ty = reinterpret_cast<const uint2*>(taps + D.coef_y_base + y0);
+  const uint2 tl = ty[min((int)threadIdx.x, jn - 1)];
+  const int live = x4 < D.w;  // lanes beyond the row stay for the shuffles; they load and store nothing
+  int spitch;
+  const uint8_t* src = level_plane(p, S, level - 1, frame, &spitch);
+  const int dpitch = D.pitch;
+  uint8_t* dst = p.pyr + D.plane_base * p.batch_cap + (int64_t)frame * D.plane_bytes + (int64_t)y0 * dpitch + x4;
+  const ResizeGroup G = groups[D.group_base + min(gi, ((D.w + 3) >> 2) - 1)];
+  const int base = G.src_x & ~3, shift = (G.src_x & 3) * 8, last_word = (S.w - 1) & ~3;
+  const int ld1 = base + 4 <= last_word, ld2 = shift != 0 && base + 8 <= last_word;
+  const unsigned act = 0xffffffffu;
+  const uint32_t row0 = __shfl_sync(act, tl.x, 0) & 0xFFFFu, rowl = __shfl_sync(act, tl.x, jn - 1) >> 16;  // first / last source row
+  src += base + (uint64_t)(row0 * (uint32_t)spitch);
+  ResizeRaw raw[KMAX];
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k)
+    resize_fetch(src + (uint64_t)((uint32_t)k * (uint32_t)spitch), live & (int)(row0 + k <= rowl), ld1, ld2, raw[k]);
+  uint32_t ap[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
+  int jd = 0;
+  uint32_t tx = __shfl_sync(act, tl.x, 0), tc = __shfl_sync(act, tl.y, 0);
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) {
+    if (row0 + k > rowl) break;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) ap[i] = ac[i];
+    resize_hrow(raw[k], shift, G, ac);
+    while (jd < jn && (tx >> 16) == row0 + k) {
+      const bool same = (tx & 0xFFFFu) == (tx >> 16);  // s0 == s1: both taps on this row (clamped ends)
+      const uint32_t c0 = tc & 0xFFFFu, c1 = tc >> 16;
+      const uint32_t u0 = same ? ac[0] : ap[0], u1 = same ? ac[1] : ap[1], u2 = same ? ac[2] : ap[2], u3 = same ? ac[3] : ap[3];
+      // v = (((c0 * a0) >> 16) + ((c1 * a1) >> 16) + 2) >> 2
+      const uint32_t u01 = __byte_perm(c0 * u0, c0 * u1, 0x7632), u23 = __byte_perm(c0 * u2, c0 * u3, 0x7632);
+      const uint32_t l01 = __byte_perm(c1 * ac[0], c1 * ac[1], 0x7632), l23 = __byte_perm(c1 * ac[2], c1 * ac[3], 0x7632);
+      const uint32_t v01 = (u01 + l01 + 0x00020002u) >> 2, v23 = (u23 + l23 + 0x00020002u) >> 2;  // lanes <= 1022: no carry
+      if (live) *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)jd * (uint32_t)dpitch)) = __byte_perm(v01, v23, 0x6420);  // the pitch absorbs the tail
+      ++jd;
+      const int jq = min(jd, jn - 1);
+      tx = __shfl_sync(act, tl.x, jq);
+      tc = __shfl_sync(act, tl.y, jq);
+    }
   }
 }
 
@@ -134,7 +228,11 @@ __global__ void __launch_bounds__(256) resize_level_generic_kernel(const FrameGe
 void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level, const BatchPlanes& p,
                          const ResizeTap* d_taps, const ResizeGroup* d_groups, int nframes, cudaStream_t s) {
   const LevelGeom& D = g.lv[level];
-  if (D.group_base >= 0) {
+  if (D.group_base >= 0 && D.rz_span > 0 && D.rz_span <= 11) {
+    dim3 block(32, 4);
+    dim3 grid((D.w + 127) / 128, (D.h + 4 * RZP_ROWS - 1) / (4 * RZP_ROWS), nframes);
+    resize_level_pre_kernel<11><<<grid, block, 0, s>>>(d_geom, level, p, d_taps, d_groups);
+  } else if (D.group_base >= 0) {
     dim3 block(32, 4);
     dim3 grid((D.w + 127) / 128, (D.h + 4 * RZ_ROWS - 1) / (4 * RZ_ROWS), nframes);
     resize_level_kernel<<<grid, block, 0, s>>>(d_geom, level, p, d_taps, d_groups);
