@@ -18,6 +18,10 @@ CONFIGS = [  # label, generator, width, height, params, frames
     ("C0 defaults", "smooth_noise", 640, 480, (1000, 2.0, 5, 20), 512),
     ("ini 2000", "smooth_noise", 640, 480, (2000, 1.2, 8, 20), 256),
     ("C5 1080p", "smooth_noise", 1920, 1080, (4000, 1.2, 12, 20), 64),
+    # ORB-SLAM2-style mode (row f1): the fifth parameter is minThFAST
+    ("f1 smooth_noise", "smooth_noise", 640, 480, (1000, 1.2, 8, 20, 7), 1024),
+    ("f1 rects", "rects", 640, 480, (1000, 1.2, 8, 20, 7), 512),
+    ("f1 euroc 2000", "smooth_noise", 752, 480, (2000, 1.2, 8, 20, 7), 256),
 ]
 
 
@@ -30,13 +34,14 @@ def main():
         t = time.time()
         imgs = synth.frames(n, w, h, kind, start=10_000)
         t_gen = time.time() - t
-        ex = api.ORBextractor(*params, max_width=w, max_height=h, max_batch=min(n, 256))
+        min_th = params[4] if len(params) > 4 else None
+        ex = api.ORBextractor(*params[:4], minThFAST=min_th, max_width=w, max_height=h, max_batch=min(n, 256))
         t = time.time()
         gk, gd, gc = ex.extract_batch_host(imgs)
         t_gpu = time.time() - t
         ex.close()
         t = time.time()
-        ok, od, oc = orc.Extractor(*params).extract_many(imgs, nthreads=threads)
+        ok, od, oc = orc.Extractor(*params[:4], min_th_fast=min_th).extract_many(imgs, nthreads=threads)
         t_cpu = time.time() - t
         cap = min(gk.shape[1], ok.shape[1])
         bad = 0
