@@ -299,7 +299,7 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
         for (int y = 0; y < L.h && ok; ++y) {
           const ResizeTap& tp = tyv[y];
           if (tp.s1 != tp.s0 && tp.s1 != tp.s0 + 1) ok = false;
-          if (y > 0 && (tp.s1 < tyv[y - 1].s1 || tp.s0 < tyv[y - 1].s0)) ok = false;
+          if (y > 0 && (tp.s1 <= tyv[y - 1].s1 || tp.s0 < tyv[y - 1].s0)) ok = false;  // a source row ends at most one destination row
         }
         for (int y = 0; y < L.h && ok; y += 8) {
           const int yl = std::min(y + 8, L.h) - 1;

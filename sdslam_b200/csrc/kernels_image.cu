@@ -134,64 +134,69 @@ __global__ void __launch_bounds__(128) resize_level_kernel(const FrameGeom* __re
 // The same arithmetic with every source word of the thread requested up front.  The row-walk kernel above waits for
 // memory once per destination row (ncu source page: all its stall samples sit on the first use of a row's words, and one row
 // of look-ahead does not cover the latency with the warps an SM holds).  The source rows of RZP_ROWS consecutive destination
-// rows are one contiguous range of at most KMAX rows (checked on the host per level), so this variant issues all of them
-// -- 3 * KMAX independent loads per thread -- before it touches any, then walks the rows in registers: H of source row k
-// is computed once and the destination row whose lower tap is row k (at most one per source row when shrinking, a second
-// one only where the last row is clamped) is emitted from H(k-1) / H(k).
+// rows are one contiguous range of at most KMAX rows, and when the image shrinks every source row is the lower tap of at
+// most one destination row (both checked on the host per level, LevelGeom::rz_span).  So this variant issues all
+// 3 * KMAX independent loads of a thread before it touches any, then walks the source rows in registers: H of source row
+// k is computed once, and the destination row that ends on row k -- looked up in a per-warp table in shared memory, filled
+// from the vertical taps by the lanes that hold them -- is emitted from H(k-1) / H(k).
 constexpr int RZP_ROWS = 8;
 template <int KMAX>
 __global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
                                                                const ResizeTap* __restrict__ taps,
                                                                const ResizeGroup* __restrict__ groups) {
+  __shared__ int2 s_emit[4][KMAX];  // per warp and source row k: {destination row | same-row flag << 8, c0 | c1 << 16} or {-1, 0}
   const LevelGeom& D = geom->lv[level];
   const LevelGeom& S = geom->lv[level - 1];
-  const int gi = blockIdx.x * 32 + threadIdx.x;
-  const int x4 = gi * 4;
+  const int lane = threadIdx.x;
+  // lanes beyond the row redo the row's last group: same loads, same bytes stored to the same place
+  const int gi = min(blockIdx.x * 32 + lane, ((D.w + 3) >> 2) - 1);
   const int y0 = (blockIdx.y * 4 + threadIdx.y) * RZP_ROWS;  // warp-uniform
   const int frame = blockIdx.z;
   const int dh = D.h;
   if (y0 >= dh) return;
   const int jn = min(RZP_ROWS, dh - y0);
-  // the vertical taps of the warp's rows live in its lanes: {s0 | s1 << 16, c0 | c1 << 16} of row y0 + lane
-  const uint2* ty = reinterpret_cast<const uint2*>(taps + D.coef_y_base + y0);
-  const uint2 tl = ty[min((int)threadIdx.x, jn - 1)];
-  const int live = x4 < D.w;  // lanes beyond the row stay for the shuffles; they load and store nothing
+  // vertical taps {s0 | s1 << 16, c0 | c1 << 16} of row y0 + lane, for the lanes < jn
+  const uint2 tl = reinterpret_cast<const uint2*>(taps + D.coef_y_base + y0)[min(lane, jn - 1)];
+  const uint32_t row0 = __shfl_sync(0xffffffffu, tl.x, 0) & 0xFFFFu, rowl = __shfl_sync(0xffffffffu, tl.x, jn - 1) >> 16;
+  int2* emit = s_emit[threadIdx.y];
+  if (lane < KMAX) emit[lane] = make_int2(-1, 0);
+  __syncwarp();
+  if (lane < jn) {
+    const uint32_t s0 = tl.x & 0xFFFFu, s1 = tl.x >> 16;
+    emit[s1 - row0] = make_int2(lane | (s0 == s1 ? 0x100 : 0), (int)tl.y);
+  }
+  __syncwarp();
   int spitch;
   const uint8_t* src = level_plane(p, S, level - 1, frame, &spitch);
   const int dpitch = D.pitch;
-  uint8_t* dst = p.pyr + D.plane_base * p.batch_cap + (int64_t)frame * D.plane_bytes + (int64_t)y0 * dpitch + x4;
-  const ResizeGroup G = groups[D.group_base + min(gi, ((D.w + 3) >> 2) - 1)];
+  uint8_t* dst = p.pyr + D.plane_base * p.batch_cap + (int64_t)frame * D.plane_bytes + (int64_t)y0 * dpitch + gi * 4;
+  const ResizeGroup G = groups[D.group_base + gi];
   const int base = G.src_x & ~3, shift = (G.src_x & 3) * 8, last_word = (S.w - 1) & ~3;
   const int ld1 = base + 4 <= last_word, ld2 = shift != 0 && base + 8 <= last_word;
-  const unsigned act = 0xffffffffu;
-  const uint32_t row0 = __shfl_sync(act, tl.x, 0) & 0xFFFFu, rowl = __shfl_sync(act, tl.x, jn - 1) >> 16;  // first / last source row
   src += base + (uint64_t)(row0 * (uint32_t)spitch);
   ResizeRaw raw[KMAX];
+  {
+    const uint8_t* rp = src;
 #pragma unroll
-  for (int k = 0; k < KMAX; ++k)
-    resize_fetch(src + (uint64_t)((uint32_t)k * (uint32_t)spitch), live & (int)(row0 + k <= rowl), ld1, ld2, raw[k]);
+    for (int k = 0; k < KMAX; ++k, rp += spitch) resize_fetch(rp, row0 + k <= rowl, ld1, ld2, raw[k]);
+  }
   uint32_t ap[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
-  int jd = 0;
-  uint32_t tx = __shfl_sync(act, tl.x, 0), tc = __shfl_sync(act, tl.y, 0);
 #pragma unroll
   for (int k = 0; k < KMAX; ++k) {
     if (row0 + k > rowl) break;
 #pragma unroll
     for (int i = 0; i < 4; ++i) ap[i] = ac[i];
     resize_hrow(raw[k], shift, G, ac);
-    while (jd < jn && (tx >> 16) == row0 + k) {
-      const bool same = (tx & 0xFFFFu) == (tx >> 16);  // s0 == s1: both taps on this row (clamped ends)
-      const uint32_t c0 = tc & 0xFFFFu, c1 = tc >> 16;
+    const int2 e = emit[k];
+    if (e.x >= 0) {
+      const bool same = e.x & 0x100;  // s0 == s1: both taps on this row (clamped ends)
+      const uint32_t c0 = (uint32_t)e.y & 0xFFFFu, c1 = (uint32_t)e.y >> 16;
       const uint32_t u0 = same ? ac[0] : ap[0], u1 = same ? ac[1] : ap[1], u2 = same ? ac[2] : ap[2], u3 = same ? ac[3] : ap[3];
       // v = (((c0 * a0) >> 16) + ((c1 * a1) >> 16) + 2) >> 2
       const uint32_t u01 = __byte_perm(c0 * u0, c0 * u1, 0x7632), u23 = __byte_perm(c0 * u2, c0 * u3, 0x7632);
       const uint32_t l01 = __byte_perm(c1 * ac[0], c1 * ac[1], 0x7632), l23 = __byte_perm(c1 * ac[2], c1 * ac[3], 0x7632);
       const uint32_t v01 = (u01 + l01 + 0x00020002u) >> 2, v23 = (u23 + l23 + 0x00020002u) >> 2;  // lanes <= 1022: no carry
-      if (live) *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)jd * (uint32_t)dpitch)) = __byte_perm(v01, v23, 0x6420);  // the pitch absorbs the tail
-      ++jd;
-      const int jq = min(jd, jn - 1);
-      tx = __shfl_sync(act, tl.x, jq);
-      tc = __shfl_sync(act, tl.y, jq);
+      *reinterpret_cast<uint32_t*>(dst + (uint32_t)(e.x & 0xFF) * (uint32_t)dpitch) = __byte_perm(v01, v23, 0x6420);  // the pitch absorbs the tail
     }
   }
 }

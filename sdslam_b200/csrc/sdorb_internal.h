@@ -55,7 +55,7 @@ struct LevelGeom {
   int coef_x_base, coef_y_base;  // offsets into the resize coefficient tables (entries), levels >= 1
   int group_base;        // first ResizeGroup of this level (levels >= 1), -1 when the 8-byte window does not fit (scale > ~2)
   int rz_span;           // largest number of source rows that 8 consecutive destination rows (groups starting at multiples of 8) touch;
-                         // 0 when a row's taps are not (s, s+1) / (s, s) or step backwards -- selects the resize kernel
+                         // 0 when a row's taps are not (s, s+1) / (s, s) or two rows end on one source row -- selects the resize kernel
   int n_ini;             // ORB-SLAM2-style mode: initial quadtree nodes, round(width / height) of the bordered level
   float h_x;             // ... and their width hX
 };
