@@ -168,32 +168,29 @@ __device__ int scan_cell(const uint8_t* __restrict__ map, int pitch, const CellR
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       if (base + 32 * u >= items) break;  // warp-uniform
-      uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-      uint32_t nz[4];
-      int c = 0;
+      const uint32_t wv[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      // one bit per pixel of the segment: byte != 0 into bit 7 of each byte, the four bits 7 of a word gathered by a multiply
+      uint32_t m16 = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int xw = xs[u] + 4 * j;
-        // bytes outside [x0, x1) belong to the neighbouring cells
-        if (xw + 4 <= r.x0 || xw >= r.x1) wv[j] = 0;
-        else {
-          if (xw < r.x0) wv[j] &= 0xFFFFFFFFu << (8 * (r.x0 - xw));
-          if (xw + 4 > r.x1) wv[j] &= 0xFFFFFFFFu >> (8 * (xw + 4 - r.x1));
-        }
-        nz[j] = (((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wv[j]) & 0x80808080u;  // bit 7 of every non-zero byte
-        c += (int)(((nz[j] >> 7) * 0x01010101u) >> 24);
+        const uint32_t nz = ((((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wv[j]) >> 7) & 0x01010101u;
+        m16 |= ((nz * 0x10204080u) >> 28) << (4 * j);
       }
+      // pixels outside [x0, x1) belong to the neighbouring cells
+      const int lo = min(max(r.x0 - xs[u], 0), 16), hi = min(max(r.x1 - xs[u], 0), 16);
+      m16 &= (0xFFFFu << lo) & ((1u << hi) - 1u);
+      const int c = __popc(m16);
       // inside one cell strict 3x3 suppression leaves at most 8 keypoints in 16 consecutive pixels: 4 count bits
       const uint32_t b0 = __ballot_sync(0xffffffffu, c & 1), b1 = __ballot_sync(0xffffffffu, c & 2),
                      b2 = __ballot_sync(0xffffffffu, c & 4), b3 = __ballot_sync(0xffffffffu, c & 8);
       if (b0 | b1 | b2 | b3) {
         int idx = count + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          for (uint32_t m = nz[j]; m; m &= m - 1, ++idx) {
-            const int q = (__ffs(m) - 1) >> 3;
-            if (idx < cap) dst[idx] = SDORB_ENTRY(ys[u], xs[u] + 4 * j + q, (int)((wv[j] >> (8 * q)) & 0xFFu) + th - 1);
-          }
+        for (uint32_t m = m16; m; m &= m - 1, ++idx) {
+          const int q = __ffs(m) - 1;
+          const uint32_t lo8 = __byte_perm(wv[0], wv[1], q & 7), hi8 = __byte_perm(wv[2], wv[3], q & 7);
+          const uint32_t t = ((q & 8) ? hi8 : lo8) & 0xFFu;
+          if (idx < cap) dst[idx] = SDORB_ENTRY(ys[u], xs[u] + q, (int)t + th - 1);
+        }
         count += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
       }
     }
