@@ -263,6 +263,8 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
   const uint32_t th2 = (uint32_t)(th + 256) * 0x00010001u;
 
   // ---- phase S: dense scores.  Scored row sr is image row b-1+sr and staged row sr+3; scored word k is staged word k+1.
+  bool use_compass = true;  // warp-uniform
+  int dense_rows = 0;
   for (int base = 0; base < SROWS; base += (NT / 32) * rps) {
     const int sr = base + warp * rps + sub;
     const int gy = b - 1 + sr;
@@ -279,16 +281,24 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
         W[dy][2] = s_pix[srl + dy][k + 2];
       }
       // compass pre-test on 4 pixels (a 9-arc contains one of ring {0,8} and one of ring {4,12}): lets the warp skip the
-      // pixel pairs that no lane needs (flat image regions)
+      // pixel pairs that no lane needs (flat image regions).  On corner-dense tiles it never skips anything, so a warp that
+      // needed both pairs in two consecutive rows stops testing for the rest of the tile (scoring a pair is always correct).
       const uint32_t live = active ? valid_cols : 0u;
-      const uint32_t c = W[3][1];
-      const uint32_t lf = prmt(W[3][0], c, 0x4321), rt = prmt(c, W[3][2], 0x6543);
-      const uint32_t fv = gt_th(__vabsdiffu4(W[0][1], c), C, th_high) | gt_th(__vabsdiffu4(W[6][1], c), C, th_high);
-      const uint32_t fh = gt_th(__vabsdiffu4(lf, c), C, th_high) | gt_th(__vabsdiffu4(rt, c), C, th_high);
-      const uint32_t cand = fv & fh & 0x80808080u & live;
+      bool need0 = true, need1 = true;
+      if (use_compass) {
+        const uint32_t c = W[3][1];
+        const uint32_t lf = prmt(W[3][0], c, 0x4321), rt = prmt(c, W[3][2], 0x6543);
+        const uint32_t fv = gt_th(__vabsdiffu4(W[0][1], c), C, th_high) | gt_th(__vabsdiffu4(W[6][1], c), C, th_high);
+        const uint32_t fh = gt_th(__vabsdiffu4(lf, c), C, th_high) | gt_th(__vabsdiffu4(rt, c), C, th_high);
+        const uint32_t cand = fv & fh & 0x80808080u & live;
+        need0 = __any_sync(0xffffffffu, cand & 0x00008080u);
+        need1 = __any_sync(0xffffffffu, cand & 0x80800000u);
+        dense_rows = (need0 && need1) ? dense_rows + 1 : 0;
+        use_compass = dense_rows < 2;
+      }
       uint32_t t0 = 0, t1 = 0;
-      if (__any_sync(0xffffffffu, cand & 0x00008080u)) t0 = score_pair<0>(W, th2);
-      if (__any_sync(0xffffffffu, cand & 0x80800000u)) t1 = score_pair<1>(W, th2);
+      if (need0) t0 = score_pair<0>(W, th2);
+      if (need1) t1 = score_pair<1>(W, th2);
       T = prmt(t0, t1, 0x6420) & live;
     }
     if (in_tile) s_t[sr][k + 1] = T;
