@@ -15,8 +15,10 @@
 //   * one thread owns one 32-bit word = 4 pixels; a warp owns 128 pixels of one row; everything is read from a
 //     shared-memory tile as aligned words and shuffled into place with PRMT;
 //   * min(v - r) over an arc is v - max(r) over the arc, so the arc minima / maxima are taken on the ring bytes
-//     themselves, two pixels at a time in 16-bit lanes (VIMNMX.U16x2, 3-input forms): 64 min/max + 16 PRMT per pixel pair;
-//     each lane carries its byte twice (value * 257), so lane order == byte order and no masking is needed;
+//     themselves, two pixels at a time in 16-bit lanes (VIMNMX.U16x2, 3-input forms): 64 min/max per pixel pair;
+//     the two pixels of a pair lie two apart, each in the high byte of its lane with its left neighbour as the low byte,
+//     so a ring sample is a plain unaligned window of the row (23 PRMT per word for its 32 samples, see ring_at) and
+//     needs no masking: u16 order is byte order up to ties, and ties do not change the high byte of a min / max;
 //   * scores are kept as t = max(score + 1 - th, 0) in one byte per pixel; the 3x3 strict non-max test runs on the
 //     same packed lanes with per-column / per-row cell-boundary masks;
 //   * survivors are written back as map words (coalesced 120-byte row segments).
@@ -63,28 +65,50 @@ __device__ __forceinline__ uint32_t pair_at(const uint32_t w0, const uint32_t w1
   }
 }
 
-// t = max(cornerScore + 1 - th, 0) for the two pixels of pair P, as two 16-bit lanes.  W[dy+3][0..2] are the staged
+// Ring sample of the pixel pair P of a word -- P = 0: pixels (0, 2), P = 1: pixels (1, 3) -- at horizontal offset DX, from
+// the row's three words: the pixel byte sits in the HIGH byte of its 16-bit lane, the low byte is whatever lies to its left.
+// u16 min / max order such lanes by the pixel byte first, and taking the high byte commutes with min / max (it is
+// monotone), so the arc extrema come out right in the high bytes.  Pixels two apart make the sample a plain unaligned
+// 4-byte window of the row starting at byte 3 + P + DX of the 12-byte window: free when that is word aligned, and the
+// window of (P = 0, DX) is the window of (P = 1, DX - 1) -- 23 PRMT per word for its 32 ring samples instead of 32.
+template <int P, int DX>
+__device__ __forceinline__ uint32_t ring_at(const uint32_t w0, const uint32_t w1, const uint32_t w2) {
+  constexpr int s = 3 + P + DX;
+  static_assert(s >= 0 && s <= 8, "offset out of window");
+  if (s == 0) return w0;
+  if (s == 4) return w1;
+  if (s == 8) return w2;
+  if (s < 4) {
+    constexpr uint32_t sel = s | ((s + 1) << 4) | ((s + 2) << 8) | ((s + 3) << 12);
+    return prmt(w0, w1, sel);
+  } else {
+    constexpr uint32_t t = s - 4, sel = t | ((t + 1) << 4) | ((t + 2) << 8) | ((t + 3) << 12);
+    return prmt(w1, w2, sel);
+  }
+}
+
+// t = max(cornerScore + 1 - th, 0) for the two pixels of pair P (pixels (0, 2) or (1, 3) of the word), as two 16-bit lanes.  W[dy+3][0..2] are the staged
 // words of rows y-3..y+3 (previous / own / next word).
 template <int P>
 __device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const uint32_t th2) {
   uint32_t r[16];
   // ring in OpenCV order: (0,3)(1,3)(2,2)(3,1)(3,0)(3,-1)(2,-2)(1,-3)(0,-3)(-1,-3)(-2,-2)(-3,-1)(-3,0)(-3,1)(-2,2)(-1,3)
-  r[0] = pair_at<P, 0>(W[6][0], W[6][1], W[6][2]);
-  r[1] = pair_at<P, 1>(W[6][0], W[6][1], W[6][2]);
-  r[2] = pair_at<P, 2>(W[5][0], W[5][1], W[5][2]);
-  r[3] = pair_at<P, 3>(W[4][0], W[4][1], W[4][2]);
-  r[4] = pair_at<P, 3>(W[3][0], W[3][1], W[3][2]);
-  r[5] = pair_at<P, 3>(W[2][0], W[2][1], W[2][2]);
-  r[6] = pair_at<P, 2>(W[1][0], W[1][1], W[1][2]);
-  r[7] = pair_at<P, 1>(W[0][0], W[0][1], W[0][2]);
-  r[8] = pair_at<P, 0>(W[0][0], W[0][1], W[0][2]);
-  r[9] = pair_at<P, -1>(W[0][0], W[0][1], W[0][2]);
-  r[10] = pair_at<P, -2>(W[1][0], W[1][1], W[1][2]);
-  r[11] = pair_at<P, -3>(W[2][0], W[2][1], W[2][2]);
-  r[12] = pair_at<P, -3>(W[3][0], W[3][1], W[3][2]);
-  r[13] = pair_at<P, -3>(W[4][0], W[4][1], W[4][2]);
-  r[14] = pair_at<P, -2>(W[5][0], W[5][1], W[5][2]);
-  r[15] = pair_at<P, -1>(W[6][0], W[6][1], W[6][2]);
+  r[0] = ring_at<P, 0>(W[6][0], W[6][1], W[6][2]);
+  r[1] = ring_at<P, 1>(W[6][0], W[6][1], W[6][2]);
+  r[2] = ring_at<P, 2>(W[5][0], W[5][1], W[5][2]);
+  r[3] = ring_at<P, 3>(W[4][0], W[4][1], W[4][2]);
+  r[4] = ring_at<P, 3>(W[3][0], W[3][1], W[3][2]);
+  r[5] = ring_at<P, 3>(W[2][0], W[2][1], W[2][2]);
+  r[6] = ring_at<P, 2>(W[1][0], W[1][1], W[1][2]);
+  r[7] = ring_at<P, 1>(W[0][0], W[0][1], W[0][2]);
+  r[8] = ring_at<P, 0>(W[0][0], W[0][1], W[0][2]);
+  r[9] = ring_at<P, -1>(W[0][0], W[0][1], W[0][2]);
+  r[10] = ring_at<P, -2>(W[1][0], W[1][1], W[1][2]);
+  r[11] = ring_at<P, -3>(W[2][0], W[2][1], W[2][2]);
+  r[12] = ring_at<P, -3>(W[3][0], W[3][1], W[3][2]);
+  r[13] = ring_at<P, -3>(W[4][0], W[4][1], W[4][2]);
+  r[14] = ring_at<P, -2>(W[5][0], W[5][1], W[5][2]);
+  r[15] = ring_at<P, -1>(W[6][0], W[6][1], W[6][2]);
   // X = min over the 16 arcs of the arc maximum, Y = max over the arcs of the arc minimum.  The arcs starting at j-1 and
   // at j (j odd) share the eight pixels j..j+7, so  min(max(arc j-1), max(arc j)) = max(max(r[j..j+7]), min(r[j-1], r[j+8]))
   // (the grouping of OpenCV's cornerScore loop); the eight-pixel extrema are built from pair extrema (j, j+1), and the six
@@ -117,7 +141,7 @@ __device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const 
   Y = __vmaxu2(Y, wmin[7]);
   // A = v - X, B' = Y - v per lane, biased by 256 so that the lanes never borrow
   const uint32_t Xc = prmt(X, 0u, 0x4341), Yc = prmt(Y, 0u, 0x4341);
-  const uint32_t Vc = prmt(W[3][1], 0u, P == 0 ? 0x4140 : 0x4342);
+  const uint32_t Vc = prmt(W[3][1], 0u, P == 0 ? 0x4240 : 0x4341);  // pixels (0, 2) / (1, 3) of the own word
   const uint32_t A = Vc + 0x01000100u - Xc, B = Yc + 0x01000100u - Vc;
   const uint32_t m = __vmaxu2(A, B);          // max(A, B') + 256
   return __vmaxu2(m, th2) - th2;              // (max(A,B') - th) if positive, else 0;  th2 = (th + 256) per lane
@@ -291,15 +315,20 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
         const uint32_t fv = gt_th(__vabsdiffu4(W[0][1], c), C, th_high) | gt_th(__vabsdiffu4(W[6][1], c), C, th_high);
         const uint32_t fh = gt_th(__vabsdiffu4(lf, c), C, th_high) | gt_th(__vabsdiffu4(rt, c), C, th_high);
         const uint32_t cand = fv & fh & 0x80808080u & live;
-        need0 = __any_sync(0xffffffffu, cand & 0x00008080u);
-        need1 = __any_sync(0xffffffffu, cand & 0x80800000u);
+        need0 = __any_sync(0xffffffffu, cand & 0x00800080u);  // pixels 0, 2
+        need1 = __any_sync(0xffffffffu, cand & 0x80008000u);  // pixels 1, 3
         dense_rows = (need0 && need1) ? dense_rows + 1 : 0;
         use_compass = dense_rows < 2;
       }
       uint32_t t0 = 0, t1 = 0;
-      if (need0) t0 = score_pair<0>(W, th2);
-      if (need1) t1 = score_pair<1>(W, th2);
-      T = prmt(t0, t1, 0x6420) & live;
+      if (need0 && need1) {  // one block: the two pairs share nine of their ring windows
+        t0 = score_pair<0>(W, th2);
+        t1 = score_pair<1>(W, th2);
+      } else {
+        if (need0) t0 = score_pair<0>(W, th2);
+        if (need1) t1 = score_pair<1>(W, th2);
+      }
+      T = prmt(t0, t1, 0x6240) & live;  // bytes t(0), t(1), t(2), t(3)
     }
     if (in_tile) s_t[sr][k + 1] = T;
   }
