@@ -20,7 +20,8 @@
 //     so a ring sample is a plain unaligned window of the row (23 PRMT per word for its 32 samples, see ring_at) and
 //     needs no masking: u16 order is byte order up to ties, and ties do not change the high byte of a min / max;
 //   * scores are kept as t = max(score + 1 - th, 0) in one byte per pixel; the 3x3 strict non-max test runs on the
-//     same packed lanes with per-column / per-row cell-boundary masks;
+//     same kind of lanes (neighbour windows with junk low bytes against a centre with a zero low byte, see nms_pair)
+//     with per-column / per-row cell-boundary masks;
 //   * survivors are written back as map words (coalesced 120-byte row segments).
 // A cheap 4-pixel SWAR compass test (VABSDIFF4) is kept only to skip pixel pairs no lane of the warp needs (flat image
 // regions).  The kernel is bound by the integer ALU pipe (min/max, PRMT), not by HBM: see DESIGN.md.
@@ -37,32 +38,10 @@ constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in wo
 constexpr int NT = 64;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
-// every byte of x replaced by 0xFF if its bit 7 is set, else 0x00 (PRMT's sign-replicate mode, which __byte_perm masks off)
-__device__ __forceinline__ uint32_t spread_bit7(uint32_t x) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %1, 0xba98;" : "=r"(r) : "r"(x));
-  return r;
-}
-
 // per-byte (a > th) in bit 7 of each byte; C prepared by the caller from th
 __device__ __forceinline__ uint32_t gt_th(uint32_t a, uint32_t C, bool th_high) {
   const uint32_t t = (a & 0x7f7f7f7fu) + C;
   return th_high ? (t & a) : (t | a);
-}
-
-// Packed pair (pixels 2p, 2p+1 of the word) of the bytes at horizontal offset dx in a row given as three words
-// (previous, own, next word): lane = byte * 257.
-template <int P, int DX>
-__device__ __forceinline__ uint32_t pair_at(const uint32_t w0, const uint32_t w1, const uint32_t w2) {
-  constexpr int i = 4 + 2 * P + DX;  // byte index in the 12-byte window
-  static_assert(i >= 1 && i <= 9, "offset out of window");
-  if (i <= 6) {
-    constexpr uint32_t s = i, sel = s | (s << 4) | ((s + 1) << 8) | ((s + 1) << 12);
-    return prmt(w0, w1, sel);
-  } else {
-    constexpr uint32_t s = i - 4, sel = s | (s << 4) | ((s + 1) << 8) | ((s + 1) << 12);
-    return prmt(w1, w2, sel);
-  }
 }
 
 // Ring sample of the pixel pair P of a word -- P = 0: pixels (0, 2), P = 1: pixels (1, 3) -- at horizontal offset DX, from
@@ -147,20 +126,23 @@ __device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const 
   return __vmaxu2(m, th2) - th2;              // (max(A,B') - th) if positive, else 0;  th2 = (th + 256) per lane
 }
 
-// Strict 3x3 non-max test of the two pixels of pair P on packed score lanes (lane = byte * 257): returns per lane
-// centre - min(centre, max of the eight neighbours), non-zero exactly for a survivor.  T[0..2] are the
-// score words of rows y-1, y, y+1 (previous / own / next word); lm / rm zero the neighbours that lie in another cell.
+// Strict 3x3 non-max test of the two pixels of pair P (pixels (0, 2) or (1, 3) of the word) on the score tile: returns per
+// 16-bit lane a word whose LOW byte is non-zero exactly for a survivor.  T[0..2] are the score words of rows y-1, y, y+1
+// (previous / own / next word); lm / rm zero the neighbours that lie in another cell.  Same lane format as the ring
+// samples (ring_at): the neighbours' scores sit in the high bytes with junk below them, the centre's with a zero low byte.
+// With the junk of the neighbour maximum forced to 0xFF,  centre > neighbours  <=>  centre lane > neighbour lane, and then
+// centre - neighbours = (difference - 1) << 8 | 1.  The nine windows of the two pairs cost nine PRMT (three per row).
 template <int P>
 __device__ __forceinline__ uint32_t nms_pair(const uint32_t (&T)[3][3], const uint32_t lm, const uint32_t rm) {
-  const uint32_t c = pair_at<P, 0>(T[1][0], T[1][1], T[1][2]);
-  const uint32_t l = pair_at<P, -1>(T[1][0], T[1][1], T[1][2]), r = pair_at<P, 1>(T[1][0], T[1][1], T[1][2]);
-  const uint32_t u = pair_at<P, 0>(T[0][0], T[0][1], T[0][2]), d = pair_at<P, 0>(T[2][0], T[2][1], T[2][2]);
-  const uint32_t ul = pair_at<P, -1>(T[0][0], T[0][1], T[0][2]), ur = pair_at<P, 1>(T[0][0], T[0][1], T[0][2]);
-  const uint32_t dl = pair_at<P, -1>(T[2][0], T[2][1], T[2][2]), dr = pair_at<P, 1>(T[2][0], T[2][1], T[2][2]);
+  const uint32_t c = prmt(T[1][1], 0u, P == 0 ? 0x2404 : 0x3414);  // score << 8 of pixels (0, 2) / (1, 3)
+  const uint32_t l = ring_at<P, -1>(T[1][0], T[1][1], T[1][2]), r = ring_at<P, 1>(T[1][0], T[1][1], T[1][2]);
+  const uint32_t u = ring_at<P, 0>(T[0][0], T[0][1], T[0][2]), d = ring_at<P, 0>(T[2][0], T[2][1], T[2][2]);
+  const uint32_t ul = ring_at<P, -1>(T[0][0], T[0][1], T[0][2]), ur = ring_at<P, 1>(T[0][0], T[0][1], T[0][2]);
+  const uint32_t dl = ring_at<P, -1>(T[2][0], T[2][1], T[2][2]), dr = ring_at<P, 1>(T[2][0], T[2][1], T[2][2]);
   // the lane masks are all-or-nothing per lane, so one AND per column of three neighbours is enough
   const uint32_t ml = __vimax3_u16x2(ul, l, dl) & lm, mr = __vimax3_u16x2(ur, r, dr) & rm;
-  const uint32_t nb = __vimax3_u16x2(ml, mr, __vmaxu2(u, d));
-  return c - __vminu2(c, nb);  // lane != 0  <=>  centre strictly greater than all eight neighbours
+  const uint32_t nb = __vimax3_u16x2(ml, mr, __vmaxu2(u, d)) | 0x00FF00FFu;
+  return c - __vminu2(c, nb);
 }
 
 __device__ __forceinline__ int div_magic(int n, int d, uint32_t magic) {  // n / d for 0 <= n < 65536 (see geometry.cc)
@@ -277,8 +259,8 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
           cx1 = (cj == L.cols - 1) ? L.max_bx : cx0 + L.cell_w;
         }
         valid_cols |= 0xFFu << (8 * q);
-        if (x - 1 >= cx0) lm[q >> 1] |= 0xFFFFu << (16 * (q & 1));
-        if (x + 1 < cx1) rm[q >> 1] |= 0xFFFFu << (16 * (q & 1));
+        if (x - 1 >= cx0) lm[q & 1] |= 0xFFFFu << (16 * (q >> 1));  // pixel q is lane q >> 1 of pair q & 1
+        if (x + 1 < cx1) rm[q & 1] |= 0xFFFFu << (16 * (q >> 1));
       }
     }
   }
@@ -353,9 +335,9 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
         Tn[1][j] = s_t[sr][k + j];
         Tn[2][j] = (rowflags & 2u) ? s_t[sr + 1][k + j] : 0u;
       }
-      // one byte per pixel of the two difference words, "non-zero" into bit 7 of each byte, bit 7 replicated over the byte
-      const uint32_t d4 = prmt(nms_pair<0>(Tn, lm[0], rm[0]), nms_pair<1>(Tn, lm[1], rm[1]), 0x6420);
-      keep_bytes = spread_bit7(((d4 & 0x7f7f7f7fu) + 0x7f7f7f7fu) | d4);
+      // the low bytes of the four difference lanes in pixel order: 1 for a survivor, else 0; times 255 = a byte mask
+      const uint32_t d4 = prmt(nms_pair<0>(Tn, lm[0], rm[0]), nms_pair<1>(Tn, lm[1], rm[1]), 0x6240);
+      keep_bytes = d4 * 0xFFu;
     }
     if (active && out_lane) *reinterpret_cast<uint32_t*>(map + (int64_t)y * L.pitch + xw) = cw & keep_bytes;
   }
