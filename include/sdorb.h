@@ -242,6 +242,33 @@ typedef struct {
 SDORB_API int sdorb_search_by_projection_batch(sdorb_handle* h, const sdorb_projection_search* q, int npairs, int capacity,
                                                int32_t* assigned, int32_t* nmatches, int mem, void* stream);
 
+/* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs) (src/ORBmatcher.cc:359-462, with CheckDistEpipolarLine
+ * :128-144) from the epipole on: the pose algebra of :361-368 stays with the caller, which passes per pair F12 (row-major
+ * doubles, F12(i, j) = F12[3 * i + j]) and the epipole (ex, ey) as the floats of :367-368.  has_mp1 / has_mp2 [npairs][capacity]:
+ * the keypoint already has a map point (GetMapPointMatches()[idx] != NULL); u_right: mvuRight; scale_factors / level_sigma2:
+ * pKF2's mvScaleFactors / mvLevelSigma2 (host pointers, nlevels <= 32 entries).  matches12 [npairs][capacity] receives vMatches12
+ * (-1 = none; vMatchedPairs is the list of (i, matches12[i]) with matches12[i] >= 0), nmatches [npairs] the return value. */
+typedef struct {
+  const sdorb_keypoint* kps1_un;
+  const uint8_t* desc1;
+  const uint8_t* has_mp1;
+  const float* u_right1;
+  const int32_t* n1;
+  const sdorb_keypoint* kps2_un;
+  const uint8_t* desc2;
+  const uint8_t* has_mp2;
+  const float* u_right2;
+  const int32_t* n2;
+  const double* F12;     /* [npairs][9] */
+  const float* epipole;  /* [npairs][2] */
+  const float* scale_factors;
+  const float* level_sigma2;
+  int nlevels;
+  int check_orientation;
+} sdorb_triangulation_search;
+SDORB_API int sdorb_search_for_triangulation_batch(sdorb_handle* h, const sdorb_triangulation_search* q, int npairs, int capacity,
+                                                   int32_t* matches12, int32_t* nmatches, int mem, void* stream);
+
 /* ---- host helpers (pure CPU table arithmetic, usable without a CUDA device) ---- */
 /* BORDER_REFLECT_101 margin around a level (src/ORBextractor.cc:692-696), used by the C++ shim. */
 SDORB_API void sdorb_fill_border_reflect101(uint8_t* level_origin, int width, int height, size_t stride, int border);

@@ -127,6 +127,10 @@ def lib(path=None):
         L.orc_search_for_initialization.restype = i
         L.orc_search_by_projection.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, C.POINTER(FrameGrid), vp, vp, f, f, i, i, vp]
         L.orc_search_by_projection.restype = i
+        L.orc_check_dist_epipolar_line.argtypes = [f, f, f, f, vp, f]
+        L.orc_check_dist_epipolar_line.restype = i
+        L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, f, f, vp, vp, i, vp]
+        L.orc_search_for_triangulation.restype = i
     return _lib
 
 
@@ -424,3 +428,23 @@ def search_by_projection(kps_last, kps_last_un, proj, flags_last, desc_mp, kps_c
     n = lib().orc_search_by_projection(_p(kl), _p(klu), _p(pr), _p(fl), _p(dm), len(kl), _p(kc), _p(dc), _p(ur), _p(oc), len(kc),
                                        C.byref(g), _p(sf), _p(bd), th, mbf, mode, int(check_orientation), _p(asg))
     return n, asg[:len(kc)]
+
+
+def check_dist_epipolar_line(x1, y1, x2, y2, F12, sigma2):
+    F = np.ascontiguousarray(F12, np.float64).reshape(9)
+    return bool(lib().orc_check_dist_epipolar_line(x1, y1, x2, y2, _p(F), sigma2))
+
+
+def search_for_triangulation(kps1_un, desc1, has_mp1, u_right1, kps2_un, desc2, has_mp2, u_right2, F12, ex, ey, scale_factors,
+                             level_sigma2, check_orientation=True):
+    """ORBmatcher::SearchForTriangulation from the epipole on: (nmatches, vMatches12)."""
+    k1, k2 = np.ascontiguousarray(kps1_un, KP_DTYPE), np.ascontiguousarray(kps2_un, KP_DTYPE)
+    d1, d2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    m1, m2 = np.ascontiguousarray(has_mp1, np.uint8), np.ascontiguousarray(has_mp2, np.uint8)
+    r1, r2 = np.ascontiguousarray(u_right1, np.float32), np.ascontiguousarray(u_right2, np.float32)
+    F = np.ascontiguousarray(F12, np.float64).reshape(9)
+    sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = lib().orc_search_for_triangulation(_p(k1), _p(d1), _p(m1), _p(r1), len(k1), _p(k2), _p(d2), _p(m2), _p(r2), len(k2), _p(F),
+                                           ex, ey, _p(sf), _p(s2), int(check_orientation), _p(m12))
+    return n, m12[:len(k1)]

@@ -1327,6 +1327,75 @@ int orc_search_by_projection(const orc_keypoint* kL, const orc_keypoint* kLun, c
   }
   return nmatches;
 }
+// ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:128-144.  F12 is an Eigen::Matrix3d, so a, b, c are evaluated in double
+// and rounded to float; the reference's -O3 -march=native contracts  p*q + r*s  into  fma(p, q, r*s)  (first product fused,
+// checked against the compiled verbatim expression in tests/test_oracle_search.py), frozen here with explicit fma / fmaf.
+static bool check_dist_epipolar_line(float x1, float y1, float x2, float y2, const double* F12 /* row-major */, float sigma2) {
+  const float a = (float)(fma((double)x1, F12[0 * 3 + 0], (double)y1 * F12[1 * 3 + 0]) + F12[2 * 3 + 0]);
+  const float b = (float)(fma((double)x1, F12[0 * 3 + 1], (double)y1 * F12[1 * 3 + 1]) + F12[2 * 3 + 1]);
+  const float c = (float)(fma((double)x1, F12[0 * 3 + 2], (double)y1 * F12[1 * 3 + 2]) + F12[2 * 3 + 2]);
+  const float num = fmaf(a, x2, b * y2) + c;
+  const float den = fmaf(a, a, b * b);
+  if (den == 0) return false;
+  const float dsqr = num * num / den;
+  return dsqr < 3.84 * sigma2;
+}
+int orc_check_dist_epipolar_line(float x1, float y1, float x2, float y2, const double* F12, float sigma2) {
+  return check_dist_epipolar_line(x1, y1, x2, y2, F12, sigma2) ? 1 : 0;
+}
+// ORBmatcher::SearchForTriangulation, src/ORBmatcher.cc:359-462, from the epipole (ex, ey) on (:361-368 is pose algebra that stays
+// with the caller).  has_mp1 / has_mp2: vpMapPoints[idx] != NULL; u_right: mvuRight.  Note that this reference never sets
+// vbMatched2 (:373, :405): several keypoints of KF1 may take the same keypoint of KF2, exactly as restated.
+int orc_search_for_triangulation(const orc_keypoint* k1, const uint8_t* d1s, const uint8_t* has_mp1, const float* u_right1, int n1,
+                                 const orc_keypoint* k2, const uint8_t* d2s, const uint8_t* has_mp2, const float* u_right2, int n2,
+                                 const double* F12, float ex, float ey, const float* mvScaleFactors, const float* mvLevelSigma2,
+                                 int mbCheckOrientation, int32_t* vMatches12) {
+  int nmatches = 0;
+  std::vector<char> vbMatched2((size_t)n2, 0);
+  std::fill(vMatches12, vMatches12 + n1, -1);
+  std::vector<std::vector<int>> rotHist(kHistoLength);
+  for (int idx1 = 0; idx1 < n1; idx1++) {
+    if (has_mp1[idx1]) continue;
+    const bool bStereo1 = u_right1[idx1] >= 0;
+    const orc_keypoint& kp1 = k1[idx1];
+    const uint8_t* d1 = d1s + (size_t)idx1 * 32;
+    int bestDist = kThLow, bestIdx2 = -1;
+    for (int idx2 = 0; idx2 < n2; idx2++) {
+      if (vbMatched2[idx2] || has_mp2[idx2]) continue;
+      const bool bStereo2 = u_right2[idx2] >= 0;
+      const orc_keypoint& kp2 = k2[idx2];
+      if (!check_dist_epipolar_line(kp1.x, kp1.y, kp2.x, kp2.y, F12, mvLevelSigma2[kp2.octave])) continue;
+      const int dist = descriptor_distance(d1, d2s + (size_t)idx2 * 32);
+      if (dist > kThLow || dist > bestDist) continue;
+      if (!bStereo1 && !bStereo2) {
+        const float distex = ex - kp2.x;
+        const float distey = ey - kp2.y;
+        if (fmaf(distex, distex, distey * distey) < 100 * mvScaleFactors[kp2.octave]) continue;
+      }
+      bestIdx2 = idx2;
+      bestDist = dist;
+    }
+    if (bestIdx2 >= 0) {
+      vMatches12[idx1] = bestIdx2;
+      nmatches++;
+      if (mbCheckOrientation) rotHist[rotation_bin(kp1.angle, k2[bestIdx2].angle)].push_back(idx1);
+    }
+  }
+  if (mbCheckOrientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    int32_t sizes[kHistoLength];
+    for (int i = 0; i < kHistoLength; i++) sizes[i] = (int)rotHist[i].size();
+    orc_three_maxima(sizes, kHistoLength, &ind1, &ind2, &ind3);
+    for (int i = 0; i < kHistoLength; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i]) {
+        vMatches12[idx1] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
 // MapPoint::ComputeDistinctiveDescriptors, /root/reference/src/MapPoint.cc:252-275: all pairwise distances of the N
 // observed descriptors (float matrix), per row std::sort and the element at index 0.5*(N-1) as median, the FIRST row
 // with the smallest median wins.

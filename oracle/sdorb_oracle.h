@@ -179,6 +179,17 @@ int orc_search_by_projection(const orc_keypoint* kps_last, const orc_keypoint* k
                              const orc_frame_grid* grid_cur, const float* scale_factors, const float bounds[4], float th,
                              float mbf, int mode, int check_orientation, int32_t* assigned);
 
+/* ORBmatcher::CheckDistEpipolarLine (src/ORBmatcher.cc:128-144); F12 row-major (F12(i, j) = F12[3 * i + j]), sigma2 =
+ * pKF2->mvLevelSigma2[kp2.octave]. */
+int orc_check_dist_epipolar_line(float x1, float y1, float x2, float y2, const double* F12, float sigma2);
+/* ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:359-462) from the epipole (ex, ey) of :366-368 on.  has_mp: the keypoint
+ * already has a map point; u_right: mvuRight.  matches12 receives vMatches12 (n1 entries, -1 = none; vMatchedPairs is the
+ * list of (i, matches12[i]) with matches12[i] >= 0); returns nmatches. */
+int orc_search_for_triangulation(const orc_keypoint* kps1_un, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1,
+                                 int n1, const orc_keypoint* kps2_un, const uint8_t* desc2, const uint8_t* has_mp2,
+                                 const float* u_right2, int n2, const double* F12, float ex, float ey, const float* scale_factors,
+                                 const float* level_sigma2, int check_orientation, int32_t* matches12);
+
 #ifdef __cplusplus
 }
 #endif

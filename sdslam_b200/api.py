@@ -54,6 +54,13 @@ class _ProjectionSearch(C.Structure):
                 ("mbf", C.c_float), ("mode", C.c_int), ("check_orientation", C.c_int)]
 
 
+class _TriangulationSearch(C.Structure):
+    _fields_ = [("kps1_un", C.c_void_p), ("desc1", C.c_void_p), ("has_mp1", C.c_void_p), ("u_right1", C.c_void_p), ("n1", C.c_void_p),
+                ("kps2_un", C.c_void_p), ("desc2", C.c_void_p), ("has_mp2", C.c_void_p), ("u_right2", C.c_void_p), ("n2", C.c_void_p),
+                ("F12", C.c_void_p), ("epipole", C.c_void_p), ("scale_factors", C.c_void_p), ("level_sigma2", C.c_void_p),
+                ("nlevels", C.c_int), ("check_orientation", C.c_int)]
+
+
 _lib = None
 
 
@@ -88,6 +95,7 @@ def lib():
     L.sdorb_search_for_initialization_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(_FrameGrid), i, i, vp, i, f, i, vp, vp,
                                                         i, vp]
     L.sdorb_search_by_projection_batch.argtypes = [vp, C.POINTER(_ProjectionSearch), i, i, vp, vp, i, vp]
+    L.sdorb_search_for_triangulation_batch.argtypes = [vp, C.POINTER(_TriangulationSearch), i, i, vp, vp, i, vp]
     L.sdorb_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i, i, vp, i, i, sz, sz, f, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
     L.sdorb_fill_border_reflect101.restype = None
@@ -399,6 +407,31 @@ class ORBextractor:
         nm = np.zeros(P, np.int32)
         self._check(lib().sdorb_search_by_projection_batch(self._h, C.byref(q), P, cap, _ptr(asg), _ptr(nm), MEM_HOST, None))
         return nm, asg
+
+    def search_for_triangulation_batch(self, kps1_un, desc1, has_mp1, u_right1, n1, kps2_un, desc2, has_mp2, u_right2, n2, F12, epipole,
+                                       scale_factors, level_sigma2, check_orientation=True, matches12=None, nmatches=None,
+                                       device=False, stream=None):
+        """ORBmatcher::SearchForTriangulation for many keyframe pairs (see include/sdorb.h): returns (nmatches[P],
+        matches12[P, cap]).  Host arrays, or with device=True torch tensors on the handle's GPU (scale_factors / level_sigma2
+        stay host arrays; matches12 / nmatches are the caller's int32 tensors)."""
+        sf, s2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(level_sigma2, np.float32)
+        if not device:
+            kps1_un, kps2_un = np.ascontiguousarray(kps1_un), np.ascontiguousarray(kps2_un)
+            desc1, desc2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+            has_mp1, has_mp2 = np.ascontiguousarray(has_mp1, np.uint8), np.ascontiguousarray(has_mp2, np.uint8)
+            u_right1, u_right2 = np.ascontiguousarray(u_right1, np.float32), np.ascontiguousarray(u_right2, np.float32)
+            n1, n2 = np.ascontiguousarray(n1, np.int32), np.ascontiguousarray(n2, np.int32)
+            F12, epipole = np.ascontiguousarray(F12, np.float64), np.ascontiguousarray(epipole, np.float32)
+            matches12 = np.zeros(kps1_un.shape[:2], np.int32)
+            nmatches = np.zeros(kps1_un.shape[0], np.int32)
+        P, cap = kps1_un.shape[0], kps1_un.shape[1]
+        q = _TriangulationSearch(_ptr(kps1_un), _ptr(desc1), _ptr(has_mp1), _ptr(u_right1), _ptr(n1), _ptr(kps2_un), _ptr(desc2),
+                                 _ptr(has_mp2), _ptr(u_right2), _ptr(n2), _ptr(F12), _ptr(epipole), _ptr(sf), _ptr(s2), len(sf),
+                                 int(check_orientation))
+        self._check(lib().sdorb_search_for_triangulation_batch(self._h, C.byref(q), P, cap, _ptr(matches12), _ptr(nmatches),
+                                                                MEM_DEVICE if device else MEM_HOST,
+                                                                C.c_void_p(stream) if stream else None))
+        return nmatches, matches12
 
     # ---- instrumentation
     def set_profiling(self, on):

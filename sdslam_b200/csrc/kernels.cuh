@@ -101,6 +101,18 @@ struct SearchProjArgs {  // ORBmatcher::SearchByProjection(Frame&, const Frame&,
   float th, mbf, min_x, max_x, min_y, max_y;
   float scale_factors[SDORB_MAX_LEVELS];
 };
+struct SearchTriArgs {  // ORBmatcher::SearchForTriangulation from the epipole on
+  const void* kps1;  const uint8_t* desc1;  const uint8_t* has_mp1;  const float* u_right1;  const int32_t* n1;  // KF1
+  const void* kps2;  const uint8_t* desc2;  const uint8_t* has_mp2;  const float* u_right2;  const int32_t* n2;  // KF2
+  const double* F12;     // [npairs][9] row-major
+  const float* epipole;  // [npairs][2]  (ex, ey)
+  int32_t* matches12;    // [npairs][capacity]  vMatches12
+  int32_t* nmatches;     // [npairs]
+  int capacity, th_low, check_orientation;
+  float gate[SDORB_MAX_LEVELS];   // smallest float >= 3.84 * mvLevelSigma2[level]
+  float eplim[SDORB_MAX_LEVELS];  // 100 * mvScaleFactors[level]
+};
+void launch_search_triangulation(const SearchTriArgs& a, int npairs, cudaStream_t s);
 void launch_search_init(const SearchInitArgs& a, int npairs, cudaStream_t s);
 void launch_search_projection(const SearchProjArgs& a, int npairs, cudaStream_t s);
 size_t search_init_smem(int capacity);

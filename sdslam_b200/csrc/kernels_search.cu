@@ -370,6 +370,135 @@ size_t search_projection_smem(int capacity) {
   return sizeof(int) * ((size_t)capacity + GRID_COLS + GRID_COLS + 1 + 32) + (size_t)2 * capacity + 16;
 }
 
+// ---------------------------------------------------------------------------------------- SearchForTriangulation
+// src/ORBmatcher.cc:359-462 with CheckDistEpipolarLine :128-144.  This reference never sets vbMatched2, so every keypoint of
+// KF1 is independent: among the keypoints of KF2 that have no map point, pass the epipolar gate, lie within TH_LOW and (for a
+// mono / mono pair) away from the epipole, the LAST one with the smallest distance wins (`dist > bestDist` keeps ties
+// moving on).  Thread = keypoint of KF1, CTA = frame pair; KF2 is staged through shared memory in tiles; the rotation
+// histogram of the pair is finished by the same CTA.  Arithmetic as the reference build evaluates it: a, b, c in double
+// with one FMA each, num / den / the epipole distance in float with one FMA each (see the oracle).
+constexpr int TRI_THREADS = 256;
+constexpr int TRI_TILE = 256;
+
+struct TriTrain {
+  float x, y;
+  float gate;   // smallest float >= 3.84 * mvLevelSigma2[octave]  (dsqr < gate  <=>  the double comparison of :143); -1 = has a map point
+  float eplim;  // 100 * mvScaleFactors[octave] for a mono keypoint, -1 for a stereo one (the epipole test does not apply)
+};
+
+__global__ void __launch_bounds__(TRI_THREADS) search_triangulation_kernel(SearchTriArgs a) {
+  __shared__ uint4 s_desc[TRI_TILE][2];
+  __shared__ TriTrain s_tr[TRI_TILE];
+  __shared__ int s_histo[32];
+  __shared__ int s_removed;
+  extern __shared__ int8_t s_bin[];  // [capacity]
+  const int pair = blockIdx.x, tid = threadIdx.x, cap = a.capacity;
+  const int n1 = min(a.n1[pair], cap), n2 = min(a.n2[pair], cap);
+  const KP* k1 = reinterpret_cast<const KP*>(a.kps1) + (int64_t)pair * cap;
+  const KP* k2 = reinterpret_cast<const KP*>(a.kps2) + (int64_t)pair * cap;
+  const uint8_t* d1 = a.desc1 + (int64_t)pair * cap * 32;
+  const uint8_t* d2 = a.desc2 + (int64_t)pair * cap * 32;
+  const uint8_t* mp1 = a.has_mp1 + (int64_t)pair * cap;
+  const uint8_t* mp2 = a.has_mp2 + (int64_t)pair * cap;
+  const float* ur1 = a.u_right1 + (int64_t)pair * cap;
+  const float* ur2 = a.u_right2 + (int64_t)pair * cap;
+  const double* F = a.F12 + (int64_t)pair * 9;
+  const float ex = a.epipole[2 * pair], ey = a.epipole[2 * pair + 1];
+  int32_t* m12 = a.matches12 + (int64_t)pair * cap;
+  if (tid < 32) s_histo[tid] = 0;
+  if (tid == 0) s_removed = 0;
+  int matched = 0;
+  for (int q0 = 0; q0 < n1; q0 += TRI_THREADS) {
+    const int i1 = q0 + tid;
+    const bool live = i1 < n1 && !mp1[i1];
+    uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    float la = 0.f, lb = 0.f, lc = 0.f, den = 0.f;
+    bool stereo1 = true;
+    if (live) {
+      load_desc(d1 + (int64_t)i1 * 32, q);
+      const double x1 = (double)k1[i1].x, y1 = (double)k1[i1].y;
+      la = (float)__dadd_rn(__fma_rn(x1, F[0], __dmul_rn(y1, F[3])), F[6]);
+      lb = (float)__dadd_rn(__fma_rn(x1, F[1], __dmul_rn(y1, F[4])), F[7]);
+      lc = (float)__dadd_rn(__fma_rn(x1, F[2], __dmul_rn(y1, F[5])), F[8]);
+      den = __fmaf_rn(la, la, __fmul_rn(lb, lb));
+      stereo1 = ur1[i1] >= 0.f;
+    }
+    const bool query_ok = live && den != 0.f;
+    // packed (distance << 16 | 0xFFFF - idx2): the minimum is the smallest distance, the largest index among equals
+    uint32_t best = ((uint32_t)(a.th_low + 1) << 16);
+    for (int t0 = 0; t0 < n2; t0 += TRI_TILE) {
+      __syncthreads();
+      const int i2 = t0 + tid;
+      if (tid < TRI_TILE && i2 < n2) {
+        s_desc[tid][0] = reinterpret_cast<const uint4*>(d2 + (int64_t)i2 * 32)[0];
+        s_desc[tid][1] = reinterpret_cast<const uint4*>(d2 + (int64_t)i2 * 32)[1];
+        const KP kp = k2[i2];
+        const int oct = min(max(kp.octave, 0), SDORB_MAX_LEVELS - 1);
+        TriTrain tr;
+        tr.x = kp.x;
+        tr.y = kp.y;
+        tr.gate = mp2[i2] ? -1.f : a.gate[oct];
+        tr.eplim = ur2[i2] >= 0.f ? -1.f : a.eplim[oct];
+        s_tr[tid] = tr;
+      }
+      __syncthreads();
+      if (query_ok) {
+        const int m = min(TRI_TILE, n2 - t0);
+        for (int j = 0; j < m; ++j) {
+          const TriTrain tr = s_tr[j];
+          const float num = __fadd_rn(__fmaf_rn(la, tr.x, __fmul_rn(lb, tr.y)), lc);
+          const float dsqr = __fdiv_rn(__fmul_rn(num, num), den);
+          if (!(dsqr < tr.gate)) continue;
+          const int dist = hamming256(q, s_desc[j][0], s_desc[j][1]);
+          if (!stereo1) {
+            const float dx = __fsub_rn(ex, tr.x), dy = __fsub_rn(ey, tr.y);
+            if (__fmaf_rn(dx, dx, __fmul_rn(dy, dy)) < tr.eplim) continue;
+          }
+          best = min(best, ((uint32_t)dist << 16) | (uint32_t)(0xFFFF - (t0 + j)));
+        }
+      }
+    }
+    int bin = -1;
+    if (i1 < n1) {
+      int m = -1;
+      if (query_ok && (int)(best >> 16) <= a.th_low) {
+        m = 0xFFFF - (int)(best & 0xFFFFu);
+        ++matched;
+        if (a.check_orientation) {
+          bin = rotation_bin(k1[i1].angle, k2[m].angle);
+          atomicAdd(&s_histo[bin], 1);
+        }
+      }
+      m12[i1] = m;
+      s_bin[i1] = (int8_t)bin;
+    }
+  }
+  for (int i = n1 + tid; i < cap; i += TRI_THREADS) m12[i] = -1;
+  __syncthreads();
+  int removed = 0;
+  if (a.check_orientation) {
+    const uint32_t keep = three_maxima_mask(s_histo);
+    for (int i = tid; i < n1; i += TRI_THREADS) {
+      const int bin = s_bin[i];
+      if (bin >= 0 && !((keep >> bin) & 1u)) {
+        m12[i] = -1;
+        ++removed;
+      }
+    }
+  }
+  // nmatches = matches found - matches removed, summed over the CTA
+  int net = matched - removed;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) net += __shfl_xor_sync(0xffffffffu, net, o);
+  if ((tid & 31) == 0) atomicAdd(&s_removed, net);
+  __syncthreads();
+  if (tid == 0) a.nmatches[pair] = s_removed;
+}
+
+void launch_search_triangulation(const SearchTriArgs& a, int npairs, cudaStream_t s) {
+  search_triangulation_kernel<<<npairs, TRI_THREADS, (size_t)a.capacity + 16, s>>>(a);
+}
+
 int configure_search_kernels() {
   cudaError_t e = cudaFuncSetAttribute(search_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -983,6 +984,62 @@ int sdorb_search_by_projection_batch(sdorb_handle* h, const sdorb_projection_sea
   {
     StageScope sc(h, s, SDORB_STAGE_MATCH);
     launch_search_projection(a, npairs, s);
+    sc.launched();
+  }
+  CU(cudaGetLastError());
+  if (mem == SDORB_MEM_HOST) return st.download(h, s);
+  return SDORB_OK;
+}
+
+int sdorb_search_for_triangulation_batch(sdorb_handle* h, const sdorb_triangulation_search* q, int npairs, int capacity,
+                                         int32_t* matches12, int32_t* nmatches, int mem, void* stream) {
+  if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (npairs == 0) return SDORB_OK;
+  if (!q || !q->kps1_un || !q->desc1 || !q->has_mp1 || !q->u_right1 || !q->n1 || !q->kps2_un || !q->desc2 || !q->has_mp2 ||
+      !q->u_right2 || !q->n2 || !q->F12 || !q->epipole || !q->scale_factors || !q->level_sigma2 || q->nlevels <= 0 ||
+      q->nlevels > SDORB_MAX_LEVELS || !matches12 || !nmatches || capacity <= 0 || capacity > kSearchMaxCapacity)
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  SearchTriArgs a;
+  a.capacity = capacity;
+  a.th_low = 50;  // ORBmatcher::TH_LOW, src/ORBmatcher.cc:37
+  a.check_orientation = q->check_orientation ? 1 : 0;
+  for (int l = 0; l < SDORB_MAX_LEVELS; ++l) {
+    const int ll = std::min(l, q->nlevels - 1);
+    // dsqr < 3.84 * sigma2 is a double comparison of a float (src/ORBmatcher.cc:143): the same as dsqr < the smallest float >= the product
+    const double thr = 3.84 * (double)q->level_sigma2[ll];
+    float g = (float)thr;
+    if ((double)g < thr) g = std::nextafter(g, INFINITY);
+    a.gate[l] = g;
+    a.eplim[l] = 100 * q->scale_factors[ll];
+  }
+  const size_t P = (size_t)npairs, C = (size_t)capacity;
+  Stager st;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (((uintptr_t)q->desc1 | (uintptr_t)q->desc2) % 16 || (uintptr_t)q->F12 % 8) return SDORB_ERR_BAD_ARG;
+    a.kps1 = q->kps1_un; a.desc1 = q->desc1; a.has_mp1 = q->has_mp1; a.u_right1 = q->u_right1; a.n1 = q->n1;
+    a.kps2 = q->kps2_un; a.desc2 = q->desc2; a.has_mp2 = q->has_mp2; a.u_right2 = q->u_right2; a.n2 = q->n2;
+    a.F12 = q->F12; a.epipole = q->epipole; a.matches12 = matches12; a.nmatches = nmatches;
+  } else {
+    const size_t bK = sizeof(sdorb_keypoint) * P * C;
+    const size_t iK1 = st.add(q->kps1_un, nullptr, bK), iD1 = st.add(q->desc1, nullptr, 32 * P * C), iM1 = st.add(q->has_mp1, nullptr, P * C),
+                 iR1 = st.add(q->u_right1, nullptr, 4 * P * C), iN1 = st.add(q->n1, nullptr, 4 * P), iK2 = st.add(q->kps2_un, nullptr, bK),
+                 iD2 = st.add(q->desc2, nullptr, 32 * P * C), iM2 = st.add(q->has_mp2, nullptr, P * C),
+                 iR2 = st.add(q->u_right2, nullptr, 4 * P * C), iN2 = st.add(q->n2, nullptr, 4 * P), iF = st.add(q->F12, nullptr, 72 * P),
+                 iE = st.add(q->epipole, nullptr, 8 * P), iM = st.add(nullptr, matches12, 4 * P * C), iNM = st.add(nullptr, nmatches, 4 * P);
+    int rc = st.upload(h, s);
+    if (rc) return rc;
+    a.kps1 = (void*)st.dev(h, iK1); a.desc1 = (uint8_t*)st.dev(h, iD1); a.has_mp1 = (uint8_t*)st.dev(h, iM1);
+    a.u_right1 = (float*)st.dev(h, iR1); a.n1 = (int32_t*)st.dev(h, iN1);
+    a.kps2 = (void*)st.dev(h, iK2); a.desc2 = (uint8_t*)st.dev(h, iD2); a.has_mp2 = (uint8_t*)st.dev(h, iM2);
+    a.u_right2 = (float*)st.dev(h, iR2); a.n2 = (int32_t*)st.dev(h, iN2);
+    a.F12 = (double*)st.dev(h, iF); a.epipole = (float*)st.dev(h, iE);
+    a.matches12 = (int32_t*)st.dev(h, iM); a.nmatches = (int32_t*)st.dev(h, iNM);
+  }
+  {
+    StageScope sc(h, s, SDORB_STAGE_MATCH);
+    launch_search_triangulation(a, npairs, s);
     sc.launched();
   }
   CU(cudaGetLastError());

@@ -265,3 +265,116 @@ def py_search_by_projection(kl, klu, proj, flags, desc_mp, kc, dc, ur_c, occ_c, 
                     assigned[i2] = -1
                     n -= 1
     return n, np.array(assigned, np.int32)
+
+
+# ------------------------------------------------------------------ SearchForTriangulation (src/ORBmatcher.cc:359-462, 128-144)
+def _round_f32(fr):
+    """Fraction -> nearest float32 (ties to even), without the double rounding of float32(float(fr))."""
+    from fractions import Fraction
+    f = F32(float(fr))
+    best = None
+    for c in (np.nextafter(f, F32(-np.inf)), f, np.nextafter(f, F32(np.inf))):
+        err = abs(Fraction(float(c)) - fr)
+        even = (int(np.float32(c).view(np.uint32)) & 1) == 0
+        key = (err, 0 if even else 1)
+        if best is None or key < best[0]:
+            best = (key, c)
+    return F32(best[1])
+
+
+def _fmaf(a, b, c):
+    from fractions import Fraction
+    return _round_f32(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))
+
+
+def _fma(a, b, c):
+    from fractions import Fraction
+    return float(Fraction(float(a)) * Fraction(float(b)) + Fraction(float(c)))  # Fraction -> float rounds to nearest even
+
+
+def py_check_dist_epipolar_line(x1, y1, x2, y2, F12, sigma2):
+    """ORBmatcher::CheckDistEpipolarLine as the reference build evaluates it: a, b, c in double with the first product fused
+    (fma(x1, F(0,j), y1 * F(1,j)) + F(2,j)), num / den in float with the first product fused."""
+    F12 = np.asarray(F12, np.float64).reshape(3, 3)
+    x1, y1, x2, y2 = F32(x1), F32(y1), F32(x2), F32(y2)
+    abc = [F32(_fma(float(x1), F12[0, j], float(y1) * F12[1, j]) + F12[2, j]) for j in range(3)]
+    a, b, c = abc
+    num = F32(_fmaf(a, x2, F32(b * y2)) + c)
+    den = _fmaf(a, a, F32(b * b))
+    if den == 0:
+        return False
+    dsqr = F32(F32(num * num) / den)
+    return float(dsqr) < 3.84 * float(F32(sigma2))
+
+
+def py_search_for_triangulation(k1, d1, mp1, ur1, k2, d2, mp2, ur2, F12, ex, ey, sf, sigma2, check_orientation):
+    """ORBmatcher::SearchForTriangulation from the epipole on: (nmatches, vMatches12)."""
+    n = 0
+    m12 = [-1] * len(k1)
+    matched2 = [False] * len(k2)  # never set by this reference
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    ex, ey = F32(ex), F32(ey)
+    for i1 in range(len(k1)):
+        if mp1[i1]:
+            continue
+        stereo1 = ur1[i1] >= 0
+        best, bidx = TH_LOW, -1
+        for i2 in range(len(k2)):
+            if matched2[i2] or mp2[i2]:
+                continue
+            stereo2 = ur2[i2] >= 0
+            if not py_check_dist_epipolar_line(k1["x"][i1], k1["y"][i1], k2["x"][i2], k2["y"][i2], F12, sigma2[int(k2["octave"][i2])]):
+                continue
+            d = py_distance(d1[i1], d2[i2])
+            if d > TH_LOW or d > best:
+                continue
+            if not stereo1 and not stereo2:
+                dx, dy = F32(ex - F32(k2["x"][i2])), F32(ey - F32(k2["y"][i2]))
+                if _fmaf(dx, dx, F32(dy * dy)) < F32(F32(100) * F32(sf[int(k2["octave"][i2])])):
+                    continue
+            bidx, best = i2, d
+        if bidx >= 0:
+            m12[i1] = bidx
+            n += 1
+            if check_orientation:
+                hist[_bin(k1["angle"][i1], k2["angle"][bidx])].append(i1)
+    if check_orientation:
+        keep = py_three_maxima([len(h) for h in hist])
+        for b in range(HISTO_LENGTH):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                m12[i1] = -1
+                n -= 1
+    return n, np.array(m12, np.int32)
+
+
+def triangulation_case(seed, n1=300, n2=320, width=640, height=480, nlevels=8, dup=0.1):
+    """Two keyframes related by an epipolar geometry F12: the second frame's copies of frame-1 keypoints are put on (or a
+    pixel or two off) their epipolar lines; some keypoints already have map points, some are stereo; the epipole lies inside
+    the image so that the mono / mono epipole test bites."""
+    rng = np.random.default_rng(seed + 500)
+    k1, d1, k2, d2 = frame_pair(seed + 300, n1, n2, width, height, nlevels, dup=dup, level0=0.4)
+    F12 = np.array([[1.1e-6, 2.3e-5, -0.011], [-2.1e-5, 0.9e-6, 0.023], [0.0093, -0.031, 1.0]], np.float64)
+    F12 = F12 * rng.uniform(0.5, 2.0) + rng.normal(0, 1e-7, (3, 3))
+    m = min(n1, n2)
+    src = rng.permutation(n1)[:m]
+    dst = rng.permutation(n2)[:m]
+    for s_, t_ in zip(src, dst):
+        x1, y1 = float(k1["x"][s_]), float(k1["y"][s_])
+        a, b, c = (x1 * F12[0, j] + y1 * F12[1, j] + F12[2, j] for j in range(3))
+        x2 = rng.uniform(0, width)
+        y2 = -(a * x2 + c) / b if abs(b) > 1e-12 else rng.uniform(0, height)
+        off = rng.choice([0.0, 0.0, 0.7, 1.5, 2.5, 6.0]) * rng.choice([-1, 1]) * (1.2 ** int(k2["octave"][t_]))
+        k2["x"][t_], k2["y"][t_] = F32(x2), F32(y2 + off)
+        dd = d1[s_].copy()
+        for bit in rng.choice(256, int(rng.integers(0, 30)), replace=False):
+            dd[bit >> 3] ^= 1 << (bit & 7)
+        d2[t_] = dd
+    mp1 = (rng.random(n1) < 0.3).astype(np.uint8)
+    mp2 = (rng.random(n2) < 0.3).astype(np.uint8)
+    ur1 = np.where(rng.random(n1) < 0.3, k1["x"] - 5, -1).astype(F32)
+    ur2 = np.where(rng.random(n2) < 0.3, k2["x"] - 5, -1).astype(F32)
+    ex, ey = F32(rng.uniform(100, width - 100)), F32(rng.uniform(100, height - 100))
+    sf = (F32(1.2) ** np.arange(nlevels)).astype(F32)
+    return k1, d1, mp1, ur1, k2, d2, mp2, ur2, F12, ex, ey, sf, (sf * sf).astype(F32)

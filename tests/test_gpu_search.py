@@ -185,3 +185,52 @@ def test_search_argument_errors(ex):
         0.9, 1, api._ptr(m12), api._ptr(nm), mem, None)
     assert call(8, api.MEM_HOST) == 0 and nm[0] == 0
     assert call(0, api.MEM_HOST) < 0 and call(16385, api.MEM_HOST) < 0 and call(8, 7) < 0 and call(8, api.MEM_HOST, None) < 0
+
+
+# ------------------------------------------------------------------ SearchForTriangulation (row f4, second half)
+@pytest.mark.parametrize("orient", [True, False])
+def test_search_for_triangulation_equals_oracle(ex, orient):
+    """sdorb_search_for_triangulation_batch = ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:359-462) from the epipole
+    on: a ragged batch of keyframe pairs (more keypoints than one CTA's threads, empty frames, duplicate descriptors), each with
+    its own F12 and epipole."""
+    sizes = [(600, 640, 0.1), (300, 280, 0.3), (1000, 900, 0.0), (0, 50, 0.0), (50, 0, 0.0), (257, 513, 0.5), (1, 1, 0.0)]
+    cases = [sc.triangulation_case(s, a, b, dup=d) for s, (a, b, d) in enumerate(sizes)]
+    cap = 1024
+    col = lambda j, dt, tail=(): _slab([c[j] for c in cases], cap, dt, tail)
+    k1, d1, mp1, ur1 = col(0, api.KP_DTYPE), col(1, np.uint8, (32,)), col(2, np.uint8), col(3, np.float32)
+    k2, d2, mp2, ur2 = col(4, api.KP_DTYPE), col(5, np.uint8, (32,)), col(6, np.uint8), col(7, np.float32)
+    n1 = np.array([len(c[0]) for c in cases], np.int32)
+    n2 = np.array([len(c[4]) for c in cases], np.int32)
+    F = np.stack([c[8].reshape(9) for c in cases])
+    ep = np.array([[c[9], c[10]] for c in cases], np.float32)
+    sf, s2 = cases[0][11], cases[0][12]
+    nm, m12 = ex.search_for_triangulation_batch(k1, d1, mp1, ur1, n1, k2, d2, mp2, ur2, n2, F, ep, sf, s2, orient)
+    total = 0
+    for p, c in enumerate(cases):
+        on, om12 = orc.search_for_triangulation(*c, orient)
+        assert nm[p] == on, "pair %d: nmatches %d vs oracle %d" % (p, nm[p], on)
+        assert np.array_equal(m12[p, :len(c[0])], om12), "pair %d: vMatches12" % p
+        assert (m12[p, len(c[0]):] == -1).all()
+        total += on
+    assert total > 150
+    # device memory in, device memory out
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a.view(np.float32).reshape(a.shape + (7,)) if a.dtype == api.KP_DTYPE else a).to(dev)
+    tm12 = torch.zeros((len(cases), cap), dtype=torch.int32, device=dev)
+    tnm = torch.zeros(len(cases), dtype=torch.int32, device=dev)
+    ex.search_for_triangulation_batch(t(k1), t(d1), t(mp1), t(ur1), t(n1), t(k2), t(d2), t(mp2), t(ur2), t(n2), t(F), t(ep), sf, s2, orient,
+                                      matches12=tm12, nmatches=tnm, device=True, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(tm12.cpu().numpy(), m12) and np.array_equal(tnm.cpu().numpy(), nm)
+
+
+def test_triangulation_golden_fixture(ex):
+    from test_oracle_search import _load_triangulation_fixture
+    c, n, m12 = _load_triangulation_fixture()
+    cap = max(len(c[0]), len(c[4]))
+    one = lambda a, tail=(): _slab([a], cap, a.dtype, tail)
+    nm, gm = ex.search_for_triangulation_batch(one(c[0]), one(c[1], (32,)), one(c[2]), one(c[3]), [len(c[0])], one(c[4]), one(c[5], (32,)),
+                                               one(c[6]), one(c[7]), [len(c[4])], c[8].reshape(1, 9), np.array([[c[9], c[10]]], np.float32),
+                                               c[11], c[12], True)
+    assert nm[0] == n and np.array_equal(gm[0, :len(c[0])], m12)

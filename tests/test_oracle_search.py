@@ -94,3 +94,78 @@ def test_search_golden_fixture():
     n, asg = orc.search_by_projection(k1, k1, z["proj"], z["flags"], z["d1"], k2, z["d2"], z["ur"], z["occ"], _orc_grid(k2, gp),
                                       z["sf"], z["bounds"], 15.0, 40.0, 0, True)
     assert n == int(z["proj_n"]) and np.array_equal(asg, z["proj_assigned"])
+
+
+# ------------------------------------------------------------------ SearchForTriangulation (row f4, second half)
+_VERBATIM_EPIPOLAR = r"""
+// the arithmetic of ORBmatcher::CheckDistEpipolarLine (src/ORBmatcher.cc:128-144), F12(i, j) as F[3 * i + j]
+extern "C" int check(float x1, float y1, float x2, float y2, const double* F, float sigma2) {
+  const float a = x1*F[0*3+0]+y1*F[1*3+0]+F[2*3+0];
+  const float b = x1*F[0*3+1]+y1*F[1*3+1]+F[2*3+1];
+  const float c = x1*F[0*3+2]+y1*F[1*3+2]+F[2*3+2];
+  const float num = a*x2+b*y2+c;
+  const float den = a*a+b*b;
+  if (den == 0)
+    return 0;
+  const float dsqr = num*num/den;
+  return dsqr<3.84*sigma2;
+}
+"""
+
+
+def test_epipolar_gate_matches_reference_flags():
+    """g++ -O3 -march=native (the reference's flags, CMakeLists.txt:40) contracts p*q + r*s into fma(p, q, r*s); the oracle
+    freezes that.  Compile the verbatim expression with those flags and compare on points near and far from the line."""
+    import ctypes
+    import subprocess
+    import tempfile
+    if " fma" not in open("/proc/cpuinfo").read():
+        pytest.skip("host CPU has no FMA: the reference build would not contract here")
+    with tempfile.TemporaryDirectory() as d:
+        src, so = os.path.join(d, "v.cc"), os.path.join(d, "v.so")
+        open(src, "w").write(_VERBATIM_EPIPOLAR)
+        subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++11", "-shared", "-fPIC", "-o", so, src])
+        lib = ctypes.CDLL(so)
+        lib.check.argtypes = [ctypes.c_float] * 4 + [ctypes.c_void_p, ctypes.c_float]
+        case = sc.triangulation_case(1, 400, 400)
+        k1, k2, F12, sigma2 = case[0], case[4], case[8], case[12]
+        F = np.ascontiguousarray(F12, np.float64).reshape(9)
+        rng = np.random.default_rng(8)
+        n_true = 0
+        for _ in range(20000):
+            i1, i2 = int(rng.integers(0, len(k1))), int(rng.integers(0, len(k2)))
+            s2 = float(sigma2[int(k2["octave"][i2])])
+            args = (float(k1["x"][i1]), float(k1["y"][i1]), float(k2["x"][i2]), float(k2["y"][i2]))
+            ref = bool(lib.check(*args, F.ctypes.data, s2))
+            assert orc.check_dist_epipolar_line(*args, F12, s2) == ref
+            n_true += ref
+        assert 50 < n_true < 19000
+        Z = np.zeros(9)
+        assert not orc.check_dist_epipolar_line(1.0, 2.0, 3.0, 4.0, Z, 1.0) and not lib.check(1.0, 2.0, 3.0, 4.0, Z.ctypes.data, 1.0)
+
+
+@pytest.mark.parametrize("seed,n1,n2,orient", [(0, 140, 150, True), (1, 120, 90, False), (2, 60, 200, True), (3, 0, 40, True),
+                                               (4, 40, 0, True), (5, 150, 150, True)])
+def test_search_for_triangulation_equals_restatement(seed, n1, n2, orient):
+    case = sc.triangulation_case(seed, n1, n2, dup=0.3 if seed == 5 else 0.1)
+    n, m12 = orc.search_for_triangulation(*case, orient)
+    pn, pm12 = sc.py_search_for_triangulation(*case, orient)
+    assert n == pn and np.array_equal(m12, pm12)
+    assert n <= int((m12 >= 0).sum())  # every removal of the orientation check is counted, also none twice here
+    if seed == 0:
+        assert n > 10
+
+
+def _load_triangulation_fixture():
+    z = np.load(os.path.join(GOLD, "matcher", "triangulation_pair.npz"))
+    k1, k2 = z["k1"].view(orc.KP_DTYPE).reshape(-1), z["k2"].view(orc.KP_DTYPE).reshape(-1)
+    case = (k1, z["d1"], z["mp1"], z["ur1"], k2, z["d2"], z["mp2"], z["ur2"], z["F12"], float(z["epipole"][0]), float(z["epipole"][1]),
+            z["sf"], z["sigma2"])
+    return case, int(z["n"]), z["m12"]
+
+
+def test_triangulation_golden_fixture():
+    """The committed vectors made by the Python restatement (tests/golden/make_search_golden.py) against the oracle."""
+    case, n, m12 = _load_triangulation_fixture()
+    on, om12 = orc.search_for_triangulation(*case, True)
+    assert on == n and np.array_equal(om12, m12) and n > 10
