@@ -41,14 +41,14 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const FrameGeom* __
                                                              int max_nodes) {
   extern __shared__ __align__(16) uint32_t smem[];
   int* offs = reinterpret_cast<int*>(smem);                              // [max_cells + 1]
-  OctNode* nodes[2];
-  nodes[0] = reinterpret_cast<OctNode*>(offs + ((max_cells + 2) & ~1));  // [max_nodes] x 2
-  nodes[1] = nodes[0] + max_nodes;
-  int* ccnt = reinterpret_cast<int*>(nodes[1] + max_nodes);              // [max_nodes][4] child sizes of the round
-  int* cpos = ccnt + 4 * max_nodes;                                      // [max_nodes][4] new list positions of the children
+  OctNode* const nodes_a = reinterpret_cast<OctNode*>(offs + ((max_cells + 2) & ~1));  // [max_nodes] x 2
+  OctNode* const nodes_b = nodes_a + max_nodes;
+  int* ccnt = reinterpret_cast<int*>(nodes_b + max_nodes);               // [max_nodes][4] child sizes of the round
+  int* ccnt_b = ccnt + 4 * max_nodes;                                    // [max_nodes][4] child sizes of the next table (filled on the way)
+  int* cpos = ccnt_b + 4 * max_nodes;                                    // [max_nodes][4] new list positions of the children
   int* keep_pos = cpos + 4 * max_nodes;                                  // [max_nodes] new position of a node that stays; -1 = divided
   int* order = keep_pos + max_nodes;                                     // [max_nodes] nodes to divide, in processing order
-  unsigned long long* best = reinterpret_cast<unsigned long long*>(order + ((max_nodes + 1) & ~1));  // [max_nodes]
+  unsigned long long* best = reinterpret_cast<unsigned long long*>(order + max_nodes);  // [max_nodes]  (max_nodes is even)
   __shared__ int s_warp_sums[OCT_THREADS / 32];
   __shared__ int s_nalive, s_ncand, s_finish, s_sorted, s_total;
 
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const FrameGeom* __
         nd.y1 = (int16_t)(L.h - 2 * OCT_BORDER);  // maxY - minY
         nd.size = ccnt[i];
         keep_pos[i] = n;
-        nodes[0][n++] = nd;
+        nodes_a[n++] = nd;
       }
     }
     s_nalive = n;
@@ -137,36 +137,41 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const FrameGeom* __
   for (int k = tid; k < K; k += OCT_THREADS) knode[k] = (uint16_t)keep_pos[knode[k]];
   __syncthreads();
 
-  // ---- the rounds
-  int cur = 0;
+  // ---- the rounds.  ccnt[cb] holds the child sizes of the current table's nodes; the sweep that moves the keypoints to the
+  // next table counts the children of that table into ccnt[cb ^ 1] on the way (one pass over the keypoints per round).
+  uint32_t* ckey = reinterpret_cast<uint32_t*>(best);  // sort keys of the candidates of a sorted round (best is not used before the end)
+  for (int i = tid; i < 4 * s_nalive; i += OCT_THREADS) ccnt[i] = 0;
+  __syncthreads();
+  for (int k = tid; k < K; k += OCT_THREADS) {
+    const int i = knode[k];
+    if (nodes_a[i].size > 1) atomicAdd(&ccnt[4 * i + oct_child(keys[k], nodes_a[i])], 1);
+  }
+  int cur = 0, cb = 0;
   while (true) {
-    const OctNode* nd = nodes[cur];
-    OctNode* nn = nodes[cur ^ 1];
+    const OctNode* nd = cur ? nodes_b : nodes_a;
+    OctNode* nn = cur ? nodes_a : nodes_b;
+    const int* cc = cb ? ccnt_b : ccnt;
+    int* cnext = cb ? ccnt : ccnt_b;
     const int n_alive = s_nalive;
-    for (int i = tid; i < 4 * n_alive; i += OCT_THREADS) ccnt[i] = 0;
-    __syncthreads();
-    for (int k = tid; k < K; k += OCT_THREADS) {
-      const int i = knode[k];
-      if (nd[i].size > 1) atomicAdd(&ccnt[4 * i + oct_child(keys[k], nd[i])], 1);
-    }
+    for (int i = tid; i < 4 * max_nodes; i += OCT_THREADS) cnext[i] = 0;
     // candidates in list order
     if (tid == 0) {
       int m = 0;
       for (int i = 0; i < n_alive; ++i)
-        if (nd[i].size > 1) keep_pos[m++] = i;  // keep_pos doubles as the candidate list until the order is fixed
+        if (nd[i].size > 1) {
+          ckey[m] = ((uint32_t)nd[i].size << 16) | (uint32_t)(0xFFFF - m);
+          keep_pos[m++] = i;  // keep_pos doubles as the candidate list until the order is fixed
+        }
       s_ncand = m;
     }
-    __syncthreads();
+    __syncthreads();  // also: the child counts of this round are complete
     const int m = s_ncand;
     if (s_sorted) {
       // descending (size, address): rank every candidate; equal sizes -> the later-created node = the smaller position first
       for (int j = tid; j < m; j += OCT_THREADS) {
-        const int sj = nd[keep_pos[j]].size;
+        const uint32_t kj = ckey[j];
         int r = 0;
-        for (int q = 0; q < m; ++q) {
-          const int sq = nd[keep_pos[q]].size;
-          r += (sq > sj || (sq == sj && q < j)) ? 1 : 0;
-        }
+        for (int q = 0; q < m; ++q) r += ckey[q] > kj ? 1 : 0;
         order[r] = keep_pos[j];
       }
     } else {
@@ -179,7 +184,7 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const FrameGeom* __
       for (int j = 0; j < m; ++j) {
         const int i = order[j];
         int nz = 0;
-        for (int c = 0; c < 4; ++c) nz += ccnt[4 * i + c] > 0 ? 1 : 0;
+        for (int c = 0; c < 4; ++c) nz += cc[4 * i + c] > 0 ? 1 : 0;
         created += nz;
         size += nz - 1;
         if (s_sorted && size >= N) {
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const FrameGeom* __
         const OctNode p = nd[i];
         const int16_t sx = (int16_t)(p.x0 + ((p.x1 - p.x0 + 1) >> 1)), sy = (int16_t)(p.y0 + ((p.y1 - p.y0 + 1) >> 1));
         for (int c = 0; c < 4; ++c) {
-          const int cnt = ccnt[4 * i + c];
+          const int cnt = cc[4 * i + c];
           if (cnt == 0) continue;
           const int pos = created - 1 - t;  // pushed to the front in creation order
           ++t;
@@ -229,12 +234,17 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const FrameGeom* __
     }
     __syncthreads();
     if (s_finish == 2) break;  // keeps the previous table
+    const bool more = s_finish == 0;
     for (int k = tid; k < K; k += OCT_THREADS) {
       const int i = knode[k];
+      const uint32_t e = keys[k];
       const int kp = keep_pos[i];
-      knode[k] = (uint16_t)(kp >= 0 ? kp : cpos[4 * i + oct_child(keys[k], nd[i])]);
+      const int np = kp >= 0 ? kp : cpos[4 * i + oct_child(e, nd[i])];
+      knode[k] = (uint16_t)np;
+      if (more && nn[np].size > 1) atomicAdd(&cnext[4 * np + oct_child(e, nn[np])], 1);
     }
     cur ^= 1;
+    cb ^= 1;
     __syncthreads();
     if (s_finish) break;
   }
@@ -266,8 +276,8 @@ static void octree_caps(const FrameGeom& g, int* max_cells, int* max_nodes) {
 }
 
 static size_t octree_smem_bytes(int mc, int mn) {
-  return sizeof(int) * (size_t)((mc + 2) & ~1) + sizeof(OctNode) * 2 * (size_t)mn + sizeof(int) * (size_t)(4 + 4 + 1) * mn +
-         sizeof(int) * (size_t)((mn + 1) & ~1) + sizeof(unsigned long long) * (size_t)mn + 16;
+  return sizeof(int) * (size_t)((mc + 2) & ~1) + sizeof(OctNode) * 2 * (size_t)mn + sizeof(int) * (size_t)(4 + 4 + 4 + 1 + 1) * mn +
+         sizeof(unsigned long long) * (size_t)mn + 16;
 }
 
 void launch_octree(const FrameGeom* d_geom, const FrameGeom& g, const SelectBuffers& b, int nframes, cudaStream_t s) {
