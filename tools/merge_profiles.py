@@ -43,6 +43,11 @@ for r in out:
     t["dram_bytes_per_launch"] += float(r[ix["dram__bytes_read.sum"]]) + float(r[ix["dram__bytes_write.sum"]])
     t["kernels_per_pass"] += 1
     t["us_per_pass_under_ncu"] += float(r[ix["gpu__time_duration.sum"]]) / 1e3
+    # busiest launch of the stage: what actually bounds it (none of these kernels waits on HBM)
+    for key, col in (("alu_pipe_pct", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                     ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                     ("dram_throughput_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")):
+        t[key] = max(t.get(key, 0.0), float(r[ix[col]]))
 for k, v in traffic.items():
     v["frames_per_pass"] = 256 if k.startswith("search") else 512
     v["source"] = "profiles/%s_ncu_full_summary.csv (ncu --set full --clock-control none, one pass of 512 frames 640x480; tools/profile_r1d.sh)" % tag
