@@ -1,7 +1,7 @@
 #!/bin/bash
 # ncu captures behind profiles/r1d_* (run on the GPU box through gpurun; every ncu run follows a plain run that exited 0)
 set -x
-CMD="python bench.py --steps 2 --warmup 3 --frames 512 --pass-frames 512 --no-cpu --e2e-steps 1"
+CMD="python bench.py --steps 2 --warmup 3 --frames 512 --pass-frames 512 --e2e-pass-frames 512 --no-cpu --e2e-steps 1"
 timeout 300 $CMD > gpurun_out/ncu_plain_r1d.json 2> gpurun_out/ncu_plain_r1d.err || exit 1
 if [ "$1" != "rest" ]; then
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_r1d.csv $CMD > gpurun_out/ncu_r1d_a.log 2>&1
