@@ -579,7 +579,7 @@ def main():
     ap.add_argument("--pass-frames", type=int, default=2048,
                     help="frames per internal pass of the library (max_batch) in the resident leg: longer launches lose less to "
                          "launch gaps and partial last waves (512 -> 2048: +5 %%)")
-    ap.add_argument("--e2e-pass-frames", type=int, default=512,
+    ap.add_argument("--e2e-pass-frames", type=int, default=768,
                     help="max_batch of the handle of the end-to-end leg: the host pipeline overlaps copies and kernels pass by pass")
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -33,6 +33,8 @@ struct sdorb_handle {
   cudaStream_t s_compute = nullptr, s_in = nullptr, s_out = nullptr, s_aux = nullptr;
   cudaEvent_t ev_in[2]{}, ev_compute[2]{}, ev_out[2]{};
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // the blur runs beside FAST + selection on s_aux
+  bool pipe_taper = false;   // host pipeline: shrink the last passes (SDORB_PIPE_TAPER=1; measured: -1.5 %)
+  int pipe_growth_pct = 125; // ... and grow the first ones by this factor (SDORB_PIPE_GROWTH, percent)
   bool overlap = false;  // measured: +0.5 % at best (every kernel here is issue-bound, so co-residency buys nothing); SDORB_OVERLAP=1 enables it
   // geometry of the current image size
   int gw = 0, gh = 0;
@@ -340,6 +342,8 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (const char* e = getenv("SDORB_OVERLAP")) h->overlap = e[0] != '0';
+  if (const char* e = getenv("SDORB_PIPE_TAPER")) h->pipe_taper = e[0] != '0';
+  if (const char* e = getenv("SDORB_PIPE_GROWTH")) h->pipe_growth_pct = std::min(std::max(atoi(e), 101), 1000);
   if (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   for (int i = 0; i < 2; ++i) {
@@ -469,7 +473,10 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
   }
 
   // host path: three-stream pipeline over passes of up to max_batch frames.  Only the first upload and the last
-  // download are exposed, so the passes ramp up from max_batch / 8 and taper off the same way at the end.
+  // download are exposed, so the passes start at max_batch / 8.  A pass can only start once it is uploaded completely, and
+  // PCIe delivers frames only a little faster than the kernels consume them (5.6 vs 7 us per 640x480 frame), so the passes
+  // grow by that ratio (1.25): the upload of pass p+1 then ends when pass p does.  Doubling stalled the kernels for 2 ms per
+  // 4096-frame call; tapering the last passes costs more in small-pass efficiency than the shorter last download saves.
   rc = ensure_host_staging(h, capacity);
   if (rc) return rc;
   int pass = 0;
@@ -477,11 +484,15 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
   int ramp = n_min;
   for (int f0 = 0, n = 0; f0 < nframes; f0 += n, ++pass) {
     const int left = nframes - f0;
-    n = std::min(std::min(ramp, B), std::max((left + 1) / 2, std::min(left, n_min)));
-    ramp = std::min(ramp * 2, B);
+    n = h->pipe_taper ? std::min(std::min(ramp, B), std::max((left + 1) / 2, std::min(left, n_min))) : std::min(std::min(ramp, B), left);
+    ramp = std::min(std::max(ramp + 1, (int)((int64_t)ramp * h->pipe_growth_pct / 100)), B);
     const int slot = pass & 1;
     if (pass >= 2) CU(cudaStreamWaitEvent(h->s_in, h->ev_compute[slot], 0));
-    if (frame_stride == row_stride * (size_t)height) {
+    if (frame_stride == row_stride * (size_t)height && row_stride == (size_t)width && (size_t)L0.pitch == row_stride) {
+      // contiguous on both sides: one linear copy (a 2D copy of 640-byte rows is issued row by row)
+      CU(cudaMemcpyAsync(h->d_stage_in[slot], images + (size_t)f0 * frame_stride, frame_stride * (size_t)n, cudaMemcpyHostToDevice,
+                         h->s_in));
+    } else if (frame_stride == row_stride * (size_t)height) {
       CU(cudaMemcpy2DAsync(h->d_stage_in[slot], L0.pitch, images + (size_t)f0 * frame_stride, row_stride, width,
                            (size_t)height * n, cudaMemcpyHostToDevice, h->s_in));
     } else {
