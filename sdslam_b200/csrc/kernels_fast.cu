@@ -153,10 +153,11 @@ __device__ __forceinline__ int div_magic(int n, int d, uint32_t magic) {  // n /
 // NARROW = true: the last tile column of a level, fast_last_words (4, 8 or 16) words per row, 32 / nw rows per warp step.
 template <bool NARROW>
 __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, const BatchPlanes& p, const int level, const LevelGeom& L,
-                                          uint32_t (&s_pix)[PROWS][PWORDS], uint32_t (&s_t)[SROWS][TWORDS], uint32_t (&s_rowflags)[OH]) {
+                                          const int tile, uint32_t (&s_pix)[PROWS][PWORDS], uint32_t (&s_t)[SROWS][TWORDS],
+                                          uint32_t (&s_rowflags)[OH]) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.y;
-  const int t = (int)blockIdx.x - (NARROW ? L.tile_base_fastn : L.tile_base_fast);
+  const int t = tile - (NARROW ? L.tile_base_fastn : L.tile_base_fast);
   const int tx = NARROW ? L.tiles_x_fast : t % L.tiles_x_fast;  // the narrow tile follows the level's full tiles
   const int ty = NARROW ? t : t / L.tiles_x_fast;
   // A tile scores nw words per row: 32 (one warp per row), or fewer in the last tile column, where a warp then takes
@@ -343,25 +344,32 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
   }
 }
 
-template <bool NARROW>
-__global__ void __launch_bounds__(NT, 1024 / NT) fast_tiles_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p) {
+// One launch for all tiles of all levels: blocks [0, tiles_total_fast) are the full tiles, the rest the narrow tiles of the
+// last tile columns (their own launch ran at 57 % ALU utilisation against 89 % for the full tiles: short, few CTAs, a tail of
+// its own; behind the full tiles in the same grid they fill the SMs the last full tiles leave free).
+__global__ void __launch_bounds__(NT, 1024 / NT) fast_tiles_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, int n_full) {
   __shared__ __align__(16) uint32_t s_pix[PROWS][PWORDS];
   __shared__ __align__(16) uint32_t s_t[SROWS][TWORDS];
   __shared__ uint32_t s_rowflags[OH];
   __shared__ int s_level;
+  const bool narrow = (int)blockIdx.x >= n_full;  // CTA-uniform
+  const int t = narrow ? (int)blockIdx.x - n_full : (int)blockIdx.x;
   if (threadIdx.x == 0) {
     int l = 0;
-    while (l + 1 < geom->nlevels && (int)blockIdx.x >= (NARROW ? geom->lv[l + 1].tile_base_fastn : geom->lv[l + 1].tile_base_fast)) ++l;
+    while (l + 1 < geom->nlevels && t >= (narrow ? geom->lv[l + 1].tile_base_fastn : geom->lv[l + 1].tile_base_fast)) ++l;
     s_level = l;
   }
   __syncthreads();
   const int level = s_level;
-  fast_tile<NARROW>(geom, p, level, geom->lv[level], s_pix, s_t, s_rowflags);
+  if (narrow)
+    fast_tile<true>(geom, p, level, geom->lv[level], t, s_pix, s_t, s_rowflags);
+  else
+    fast_tile<false>(geom, p, level, geom->lv[level], t, s_pix, s_t, s_rowflags);
 }
 
 void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s) {
-  if (g.tiles_total_fast > 0) fast_tiles_kernel<false><<<dim3(g.tiles_total_fast, nframes), NT, 0, s>>>(d_geom, p);
-  if (g.tiles_total_fastn > 0) fast_tiles_kernel<true><<<dim3(g.tiles_total_fastn, nframes), NT, 0, s>>>(d_geom, p);
+  const int total = g.tiles_total_fast + g.tiles_total_fastn;
+  if (total > 0) fast_tiles_kernel<<<dim3(total, nframes), NT, 0, s>>>(d_geom, p, g.tiles_total_fast);
 }
 
 }  // namespace sdorb

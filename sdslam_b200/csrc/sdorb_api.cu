@@ -257,7 +257,7 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
     StageScope st(h, s, SDORB_STAGE_FAST);
     if (g.tiles_total_fast + g.tiles_total_fastn > 0) {
       launch_fast_all(h->d_geom, g, planes, n, s);
-      st.launched((g.tiles_total_fast > 0) + (g.tiles_total_fastn > 0));  // full tiles, narrow last-column tiles
+      st.launched();  // full tiles and the narrow last-column tiles in one grid
     }
   }
   {
