@@ -300,6 +300,7 @@ int build_frame_geom(const Tables& t, int nfeatures, int th_fast, int width, int
           const ResizeTap& tp = tyv[y];
           if (tp.s1 != tp.s0 && tp.s1 != tp.s0 + 1) ok = false;
           if (y > 0 && (tp.s1 <= tyv[y - 1].s1 || tp.s0 < tyv[y - 1].s0)) ok = false;  // a source row ends at most one destination row
+          if (tp.s1 == tp.s0 && y % 8 != 0) ok = false;  // both taps on one row: only as the first row of a group of eight
         }
         for (int y = 0; y < L.h && ok; y += 8) {
           const int yl = std::min(y + 8, L.h) - 1;

@@ -144,7 +144,7 @@ template <int KMAX>
 __global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
                                                                const ResizeTap* __restrict__ taps,
                                                                const ResizeGroup* __restrict__ groups) {
-  __shared__ int2 s_emit[4][KMAX];  // per warp and source row k: {destination row | same-row flag << 8, c0 | c1 << 16} or {-1, 0}
+  __shared__ int4 s_emit[4][KMAX];  // per warp and source row k: {destination row or -1, c0, c1, -}
   const LevelGeom& D = geom->lv[level];
   const LevelGeom& S = geom->lv[level - 1];
   const int lane = threadIdx.x;
@@ -158,13 +158,12 @@ __global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* 
   // vertical taps {s0 | s1 << 16, c0 | c1 << 16} of row y0 + lane, for the lanes < jn
   const uint2 tl = reinterpret_cast<const uint2*>(taps + D.coef_y_base + y0)[min(lane, jn - 1)];
   const uint32_t row0 = __shfl_sync(0xffffffffu, tl.x, 0) & 0xFFFFu, rowl = __shfl_sync(0xffffffffu, tl.x, jn - 1) >> 16;
-  int2* emit = s_emit[threadIdx.y];
-  if (lane < KMAX) emit[lane] = make_int2(-1, 0);
+  int4* emit = s_emit[threadIdx.y];
+  if (lane < KMAX) emit[lane] = make_int4(-1, 0, 0, 0);
   __syncwarp();
-  if (lane < jn) {
-    const uint32_t s0 = tl.x & 0xFFFFu, s1 = tl.x >> 16;
-    emit[s1 - row0] = make_int2(lane | (s0 == s1 ? 0x100 : 0), (int)tl.y);
-  }
+  // a row with both taps on one source row (s0 == s1, the clamped first row of a level) is always the first of its group of
+  // eight (checked on the host), i.e. ends on source row k = 0, where "the row before" does not exist anyway
+  if (lane < jn) emit[(tl.x >> 16) - row0] = make_int4(lane, (int)(tl.y & 0xFFFFu), (int)(tl.y >> 16), 0);
   __syncwarp();
   int spitch;
   const uint8_t* src = level_plane(p, S, level - 1, frame, &spitch);
@@ -187,16 +186,15 @@ __global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* 
 #pragma unroll
     for (int i = 0; i < 4; ++i) ap[i] = ac[i];
     resize_hrow(raw[k], shift, G, ac);
-    const int2 e = emit[k];
+    const int4 e = emit[k];
     if (e.x >= 0) {
-      const bool same = e.x & 0x100;  // s0 == s1: both taps on this row (clamped ends)
-      const uint32_t c0 = (uint32_t)e.y & 0xFFFFu, c1 = (uint32_t)e.y >> 16;
-      const uint32_t u0 = same ? ac[0] : ap[0], u1 = same ? ac[1] : ap[1], u2 = same ? ac[2] : ap[2], u3 = same ? ac[3] : ap[3];
+      const uint32_t c0 = (uint32_t)e.y, c1 = (uint32_t)e.z;
+      const uint32_t(&au)[4] = k == 0 ? ac : ap;  // the upper tap's row: H(k-1), or H(0) itself for the clamped first row
       // v = (((c0 * a0) >> 16) + ((c1 * a1) >> 16) + 2) >> 2
-      const uint32_t u01 = __byte_perm(c0 * u0, c0 * u1, 0x7632), u23 = __byte_perm(c0 * u2, c0 * u3, 0x7632);
+      const uint32_t u01 = __byte_perm(c0 * au[0], c0 * au[1], 0x7632), u23 = __byte_perm(c0 * au[2], c0 * au[3], 0x7632);
       const uint32_t l01 = __byte_perm(c1 * ac[0], c1 * ac[1], 0x7632), l23 = __byte_perm(c1 * ac[2], c1 * ac[3], 0x7632);
       const uint32_t v01 = (u01 + l01 + 0x00020002u) >> 2, v23 = (u23 + l23 + 0x00020002u) >> 2;  // lanes <= 1022: no carry
-      *reinterpret_cast<uint32_t*>(dst + (uint32_t)(e.x & 0xFF) * (uint32_t)dpitch) = __byte_perm(v01, v23, 0x6420);  // the pitch absorbs the tail
+      *reinterpret_cast<uint32_t*>(dst + (uint32_t)e.x * (uint32_t)dpitch) = __byte_perm(v01, v23, 0x6420);  // the pitch absorbs the tail
     }
   }
 }
