@@ -485,8 +485,8 @@ def run_ours(args):
         hbm_stages = ("pyramid", "fast", "blur")
         dom = max(hbm_stages, key=lambda s: stage_ms[s])
         kernel_name = {"pyramid": "resize_level_kernel", "fast": "fast_tiles_kernel", "blur": "blur_all_kernel"}[dom]
-        # one "launch" of the stage = one pass of the library over frames_per_pass frames (the FAST stage is two kernels per
-        # pass -- full tiles and the narrow last tile column -- timed together; the pyramid is one kernel per level)
+        # one "launch" of the stage = one pass of the library over frames_per_pass frames (the FAST stage is one kernel per
+        # pass; the pyramid is one kernel per level)
         n_launch = max(1, -(-frames_per_gpu // args.pass_frames) * args.steps)
         avg_launch_s = stage_ms[dom] * 1e-3 / n_launch
         bytes_per_launch = sbytes[dom] * nframes_total / n_launch
