@@ -161,11 +161,11 @@ __global__ void __launch_bounds__(DESC_THREADS) describe_kernel(const FrameGeom*
   const int u = lane - SDORB_HALF_PATCH;
   int m10 = 0, m01 = 0;
   if (lane < 31) {
-    // lane = column u of the disc; its rows are v = -vmax .. vmax with vmax = max{v : |u| <= umax[v]} (umax is decreasing)
+    // lane = column u of the disc; its rows are v = -vmax .. vmax with vmax = max{v : |u| <= umax[v]}
+    // the disc is symmetric under u <-> v (the constructor's second loop makes umax so, src/ORBextractor.cc:449-456), hence
+    // max{v : |u| <= umax[v]} = umax[|u|]
     const int au = u < 0 ? -u : u;
-    int vmax = 0;
-#pragma unroll
-    for (int v = 1; v <= SDORB_HALF_PATCH; ++v) vmax = au <= umax_tab[v] ? v : vmax;  // uniform loads
+    const int vmax = umax_tab[au];
     const uint8_t* pp = center + u;  // walks down
     const uint8_t* pm = center + u;  // walks up
     int colsum = *pp;                // sum of the column (for m10), v-weighted difference (for m01)

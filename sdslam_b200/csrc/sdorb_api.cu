@@ -332,6 +332,16 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   }
   h->device = dev;
   build_tables(params->nfeatures, params->scale_factor, params->nlevels, &h->tables);
+  // the describe kernel takes the height of disc column u as umax[|u|]: the table must be symmetric (it is, by construction)
+  for (int au = 0; au <= SDORB_HALF_PATCH; ++au) {
+    int vmax = 0;
+    for (int v = 1; v <= SDORB_HALF_PATCH; ++v)
+      if (au <= h->tables.umax[v]) vmax = v;
+    if (vmax != h->tables.umax[au]) {
+      delete h;
+      return SDORB_ERR_UNSUPPORTED;
+    }
+  }
   auto fail = [&](int code) {
     sdorb_destroy(h);
     return code;
