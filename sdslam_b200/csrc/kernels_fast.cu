@@ -29,13 +29,13 @@
 
 namespace sdorb {
 
-constexpr int OW = SDORB_FAST_TW, OH = SDORB_FAST_TH;  // output pixels per tile: 120 x 30 (30 whole words per row)
+constexpr int OW = SDORB_FAST_TW, OH = SDORB_FAST_TH;  // output pixels per tile: 120 x 60 (30 whole words per row)
 constexpr int SWORDS = 32;                             // scored words per row (128 px: outputs + one word on each side)
 constexpr int SROWS = OH + 2;                          // scored rows (outputs + 1 on each side)
 constexpr int PWORDS = SWORDS + 2;                     // staged pixel words per row (scored +- 4 px)
 constexpr int PROWS = SROWS + 6;                       // staged pixel rows (scored +- 3)
 constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in words (one zero word on each side)
-constexpr int NT = 64;
+constexpr int NT = 128;
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 // per-byte (a > th) in bit 7 of each byte; C prepared by the caller from th

@@ -9,12 +9,13 @@
 #define SDORB_MAX_DIM 4095   // keypoint entries pack y:12 | x:12 | score:8
 #define SDORB_MAX_CELLS_PER_LEVEL 4096
 
-// Tile shapes of the all-level launches.  A FAST tile scores 128 x 32 pixels starting at column 12 + 120*tx (a
-// multiple of 4, so every staged row is word aligned) and row 18 + 30*ty, and writes the keypoint map for the inner
-// 120 x 30 pixels (30 whole words per row) starting at (16 + 120*tx, 19 + 30*ty); the first detectable pixel is (19,19).
+// Tile shapes of the all-level launches.  A FAST tile scores 128 x 62 pixels starting at column 12 + 120*tx (a
+// multiple of 4, so every staged row is word aligned) and row 18 + 60*ty, and writes the keypoint map for the inner
+// 120 x 60 pixels (30 whole words per row) starting at (16 + 120*tx, 19 + 60*ty); the first detectable pixel is (19,19).
+// (60 rows and four warps per tile instead of 30 and two: 3 % fewer halo rows at the same 32 warps per SM.)
 // What is left of a level's width after the full tiles goes to one column of narrow tiles (16, 32 or 64 pixels scored).
 #define SDORB_FAST_TW 120
-#define SDORB_FAST_TH 30
+#define SDORB_FAST_TH 60
 #define SDORB_BLUR_TW 128
 #define SDORB_BLUR_TH 64
 
