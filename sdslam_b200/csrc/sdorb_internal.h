@@ -17,7 +17,7 @@
 #define SDORB_FAST_TW 120
 #define SDORB_FAST_TH 60
 #define SDORB_BLUR_TW 128
-#define SDORB_BLUR_TH 64
+#define SDORB_BLUR_TH 128
 
 // Packed keypoint entry used between the FAST, selection and describe kernels.
 // Ascending order of the packed word == row-major (y, then x) order, the order cv::FAST emits in.
