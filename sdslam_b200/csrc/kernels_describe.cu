@@ -93,7 +93,7 @@ __device__ __forceinline__ void sincosf_glibc(float y, float* sinp, float* cosp)
   }
 }
 
-constexpr int DESC_THREADS = 64;
+constexpr int DESC_THREADS = 128;
 constexpr int PATCH_ROWS = 37, PATCH_WORDS = 11;  // +-18 rows; 37 columns starting up to 3 px left of kx - 18
 
 __global__ void __launch_bounds__(DESC_THREADS) describe_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p,
