@@ -122,8 +122,7 @@ __device__ __forceinline__ uint32_t score_pair(const uint32_t (&W)[7][3], const 
   const uint32_t Xc = prmt(X, 0u, 0x4341), Yc = prmt(Y, 0u, 0x4341);
   const uint32_t Vc = prmt(W[3][1], 0u, P == 0 ? 0x4240 : 0x4341);  // pixels (0, 2) / (1, 3) of the own word
   const uint32_t A = Vc + 0x01000100u - Xc, B = Yc + 0x01000100u - Vc;
-  const uint32_t m = __vmaxu2(A, B);          // max(A, B') + 256
-  return __vmaxu2(m, th2) - th2;              // (max(A,B') - th) if positive, else 0;  th2 = (th + 256) per lane
+  return __vimax3_u16x2(A, B, th2) - th2;     // (max(A, B') - th) if positive, else 0;  th2 = (th + 256) per lane
 }
 
 // Strict 3x3 non-max test of the two pixels of pair P (pixels (0, 2) or (1, 3) of the word) on the score tile: returns per
