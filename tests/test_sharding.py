@@ -83,3 +83,55 @@ def test_gather_single_process_passthrough():
     assert out[0] is a
     with pytest.raises(ValueError):
         sharding.gather_slabs([a], 5)
+
+
+# ------------------------------------------------------------------ frame PAIRS (matching / guided search) shard the same way
+NPAIRS, NDESC = 5, 40
+
+
+def _pair_inputs():
+    rng = np.random.default_rng(12)
+    A = rng.integers(0, 256, (NPAIRS, NDESC, 32), dtype=np.uint8)
+    B = rng.integers(0, 256, (NPAIRS, NDESC, 32), dtype=np.uint8)
+    B[:, ::3] = A[:, ::3] ^ 1  # every third row one bit away from its partner
+    return A, B
+
+
+def _match(A, B):
+    from oracle import binding as orc
+    out = np.zeros((len(A), NDESC, 4), np.int32)
+    for p in range(len(A)):
+        out[p] = orc.match_best2(A[p], B[p]).view(np.int32).reshape(NDESC, 4)
+    return torch.from_numpy(out)
+
+
+def _pair_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        A, B = _pair_inputs()
+        lo, hi = sharding.frame_range(rank, world, NPAIRS)
+        got = sharding.gather_slabs([_match(A[lo:hi], B[lo:hi])], NPAIRS)
+        if rank == 0:
+            q.put(got[0].numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_pair_sharding_equals_single_rank():
+    """Frame pairs (ORBmatcher::DescriptorDistance best / second-best per pair) over two ranks with an odd pair count: rank 0
+    ends up with the single-rank result."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_pair_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    ref = _match(*_pair_inputs()).numpy()
+    assert got.shape == ref.shape and got.tobytes() == ref.tobytes()
+    assert int(ref[..., 3].sum()) > 0  # some matches accepted
