@@ -242,6 +242,34 @@ typedef struct {
 SDORB_API int sdorb_search_by_projection_batch(sdorb_handle* h, const sdorb_projection_search* q, int npairs, int capacity,
                                                int32_t* assigned, int32_t* nmatches, int mem, void* stream);
 
+/* ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th) (src/ORBmatcher.cc:43-119, with
+ * RadiusByViewingCos :121-126): the local-map search of Tracking::SearchLocalPoints, batched over frames.  Map-point slabs are
+ * [nframes][capacity_mp]: proj = (mTrackProjX, mTrackProjY, mTrackProjXR), view_cos = mTrackViewCos, level = mnTrackScaleLevel,
+ * flags (bit 0: mbTrackInView && !isBad(); bit 1: Observations() > 0), desc_mp = GetDescriptor().  Frame slabs are
+ * [nframes][capacity]: undistorted keypoints, descriptors, mvuRight, occupied (mvpMapPoints[idx] set with Observations() > 0 on
+ * entry), and the frame's grid.  The map points are visited in order and every accepted match occupies its keypoint for the
+ * later ones, exactly as in the reference.  assigned [nframes][capacity]: index of the map point the call leaves in
+ * F.mvpMapPoints[idx], -1 where it sets none; nmatches [nframes].  The matcher is the one constructed as ORBmatcher(nnratio). */
+typedef struct {
+  const float* proj;        /* [nframes][capacity_mp][3] */
+  const float* view_cos;    /* [nframes][capacity_mp] */
+  const int32_t* level;     /* [nframes][capacity_mp] */
+  const uint8_t* flags;     /* [nframes][capacity_mp] */
+  const uint8_t* desc_mp;   /* [nframes][capacity_mp][32] */
+  const int32_t* n_mp;      /* [nframes] */
+  const sdorb_keypoint* kps_un;
+  const uint8_t* desc;
+  const float* u_right;
+  const uint8_t* occupied;
+  const int32_t* n_frame;
+  sdorb_frame_grid grid;
+  const float* scale_factors; /* host pointer, nlevels entries */
+  int nlevels;
+  float th, nnratio;
+} sdorb_map_point_search;
+SDORB_API int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search* q, int nframes, int capacity_mp, int capacity,
+                                            int32_t* assigned, int32_t* nmatches, int mem, void* stream);
+
 /* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs) (src/ORBmatcher.cc:359-462, with CheckDistEpipolarLine
  * :128-144) from the epipole on: the pose algebra of :361-368 stays with the caller, which passes per pair F12 (row-major
  * doubles, F12(i, j) = F12[3 * i + j]) and the epipole (ex, ey) as the floats of :367-368.  has_mp1 / has_mp2 [npairs][capacity]:

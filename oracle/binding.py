@@ -127,6 +127,8 @@ def lib(path=None):
         L.orc_search_for_initialization.restype = i
         L.orc_search_by_projection.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, C.POINTER(FrameGrid), vp, vp, f, f, i, i, vp]
         L.orc_search_by_projection.restype = i
+        L.orc_search_map_points.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, C.POINTER(FrameGrid), vp, f, f, vp]
+        L.orc_search_map_points.restype = i
         L.orc_check_dist_epipolar_line.argtypes = [f, f, f, f, vp, f]
         L.orc_check_dist_epipolar_line.restype = i
         L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, f, f, vp, vp, i, vp]
@@ -448,3 +450,18 @@ def search_for_triangulation(kps1_un, desc1, has_mp1, u_right1, kps2_un, desc2, 
     n = lib().orc_search_for_triangulation(_p(k1), _p(d1), _p(m1), _p(r1), len(k1), _p(k2), _p(d2), _p(m2), _p(r2), len(k2), _p(F),
                                            ex, ey, _p(sf), _p(s2), int(check_orientation), _p(m12))
     return n, m12[:len(k1)]
+
+
+def search_map_points(proj, view_cos, level, flags, desc_mp, kps_un, desc, u_right, occupied, grid, scale_factors, th, nnratio=0.8):
+    """ORBmatcher::SearchByProjection(Frame, vpMapPoints, th): (nmatches, assigned)."""
+    pr = np.ascontiguousarray(proj, np.float32).reshape(-1, 3)
+    vc, lv = np.ascontiguousarray(view_cos, np.float32), np.ascontiguousarray(level, np.int32)
+    fl, dm = np.ascontiguousarray(flags, np.uint8), np.ascontiguousarray(desc_mp, np.uint8)
+    k, d = np.ascontiguousarray(kps_un, KP_DTYPE), np.ascontiguousarray(desc, np.uint8)
+    ur, oc = np.ascontiguousarray(u_right, np.float32), np.ascontiguousarray(occupied, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    g, keep = _grid(*grid)
+    asg = np.full(max(len(k), 1), -1, np.int32)
+    n = lib().orc_search_map_points(_p(pr), _p(vc), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(ur), _p(oc), len(k), C.byref(g),
+                                    _p(sf), th, nnratio, _p(asg))
+    return n, asg[:len(k)]

@@ -1327,6 +1327,56 @@ int orc_search_by_projection(const orc_keypoint* kL, const orc_keypoint* kLun, c
   }
   return nmatches;
 }
+// ORBmatcher::SearchByProjection(Frame &F, const vector<MapPoint*> &vpMapPoints, const float th), src/ORBmatcher.cc:43-119 (the
+// local-map search of Tracking::SearchLocalPoints), with RadiusByViewingCos :121-126.  Per map point the caller supplies
+// (mTrackProjX, mTrackProjY, mTrackProjXR), mTrackViewCos, mnTrackScaleLevel, flags (bit 0: mbTrackInView && !isBad(), bit 1:
+// Observations() > 0) and GetDescriptor(); for the frame mvuRight and `occupied` (mvpMapPoints[idx] && Observations() > 0 on
+// entry; tracked as map points are assigned).  assigned[idx] = index of the map point the call leaves in F.mvpMapPoints[idx], else -1.
+int orc_search_map_points(const float* proj /* n x 3 */, const float* view_cos, const int32_t* level, const uint8_t* flags,
+                          const uint8_t* descMP, int nMP, const orc_keypoint* kF, const uint8_t* descF, const float* uRight,
+                          const uint8_t* occupied_in, int nF, const orc_frame_grid* grid, const float* mvScaleFactors, float th,
+                          float mfNNratio, int32_t* assigned) {
+  int nmatches = 0;
+  std::fill(assigned, assigned + nF, -1);
+  std::vector<uint8_t> occupied(occupied_in, occupied_in + nF);
+  const bool bFactor = th != 1.0;
+  for (int iMP = 0; iMP < nMP; iMP++) {
+    if (!(flags[iMP] & 1)) continue;
+    const int nPredictedLevel = level[iMP];
+    float r = view_cos[iMP] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos
+    if (bFactor) r *= th;
+    const std::vector<int> vIndices = features_in_area(kF, *grid, proj[3 * iMP], proj[3 * iMP + 1],
+                                                       r * mvScaleFactors[nPredictedLevel], nPredictedLevel - 1, nPredictedLevel);
+    if (vIndices.empty()) continue;
+    const uint8_t* MPdescriptor = descMP + (size_t)iMP * 32;
+    int bestDist = 256, bestLevel = -1, bestDist2 = 256, bestLevel2 = -1, bestIdx = -1;
+    for (int idx : vIndices) {
+      if (occupied[idx]) continue;
+      if (uRight[idx] > 0) {
+        const float er = std::fabs(proj[3 * iMP + 2] - uRight[idx]);
+        if (er > r * mvScaleFactors[nPredictedLevel]) continue;
+      }
+      const int dist = descriptor_distance(MPdescriptor, descF + (size_t)idx * 32);
+      if (dist < bestDist) {
+        bestDist2 = bestDist;
+        bestDist = dist;
+        bestLevel2 = bestLevel;
+        bestLevel = kF[idx].octave;
+        bestIdx = idx;
+      } else if (dist < bestDist2) {
+        bestLevel2 = kF[idx].octave;
+        bestDist2 = dist;
+      }
+    }
+    if (bestDist <= kThHigh) {
+      if (bestLevel == bestLevel2 && bestDist > mfNNratio * bestDist2) continue;
+      assigned[bestIdx] = iMP;
+      occupied[bestIdx] = (flags[iMP] & 2) ? 1 : 0;
+      nmatches++;
+    }
+  }
+  return nmatches;
+}
 // ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:128-144.  F12 is an Eigen::Matrix3d, so a, b, c are evaluated in double
 // and rounded to float; the reference's -O3 -march=native contracts  p*q + r*s  into  fma(p, q, r*s)  (first product fused,
 // checked against the compiled verbatim expression in tests/test_oracle_search.py), frozen here with explicit fma / fmaf.

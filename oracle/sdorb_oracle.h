@@ -179,6 +179,12 @@ int orc_search_by_projection(const orc_keypoint* kps_last, const orc_keypoint* k
                              const orc_frame_grid* grid_cur, const float* scale_factors, const float bounds[4], float th,
                              float mbf, int mode, int check_orientation, int32_t* assigned);
 
+/* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:43-119): see sdorb_oracle.cc for the
+ * argument conventions; returns nmatches, assigned has n_frame entries. */
+int orc_search_map_points(const float* proj, const float* view_cos, const int32_t* level, const uint8_t* flags, const uint8_t* desc_mp,
+                          int n_mp, const orc_keypoint* kps_un, const uint8_t* desc, const float* u_right, const uint8_t* occupied,
+                          int n_frame, const orc_frame_grid* grid, const float* scale_factors, float th, float nnratio,
+                          int32_t* assigned);
 /* ORBmatcher::CheckDistEpipolarLine (src/ORBmatcher.cc:128-144); F12 row-major (F12(i, j) = F12[3 * i + j]), sigma2 =
  * pKF2->mvLevelSigma2[kp2.octave]. */
 int orc_check_dist_epipolar_line(float x1, float y1, float x2, float y2, const double* F12, float sigma2);

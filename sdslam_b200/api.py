@@ -54,6 +54,13 @@ class _ProjectionSearch(C.Structure):
                 ("mbf", C.c_float), ("mode", C.c_int), ("check_orientation", C.c_int)]
 
 
+class _MapPointSearch(C.Structure):
+    _fields_ = [("proj", C.c_void_p), ("view_cos", C.c_void_p), ("level", C.c_void_p), ("flags", C.c_void_p), ("desc_mp", C.c_void_p),
+                ("n_mp", C.c_void_p), ("kps_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("occupied", C.c_void_p),
+                ("n_frame", C.c_void_p), ("grid", _FrameGrid), ("scale_factors", C.c_void_p), ("nlevels", C.c_int), ("th", C.c_float),
+                ("nnratio", C.c_float)]
+
+
 class _TriangulationSearch(C.Structure):
     _fields_ = [("kps1_un", C.c_void_p), ("desc1", C.c_void_p), ("has_mp1", C.c_void_p), ("u_right1", C.c_void_p), ("n1", C.c_void_p),
                 ("kps2_un", C.c_void_p), ("desc2", C.c_void_p), ("has_mp2", C.c_void_p), ("u_right2", C.c_void_p), ("n2", C.c_void_p),
@@ -95,6 +102,7 @@ def lib():
     L.sdorb_search_for_initialization_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, C.POINTER(_FrameGrid), i, i, vp, i, f, i, vp, vp,
                                                         i, vp]
     L.sdorb_search_by_projection_batch.argtypes = [vp, C.POINTER(_ProjectionSearch), i, i, vp, vp, i, vp]
+    L.sdorb_search_map_points_batch.argtypes = [vp, C.POINTER(_MapPointSearch), i, i, i, vp, vp, i, vp]
     L.sdorb_search_for_triangulation_batch.argtypes = [vp, C.POINTER(_TriangulationSearch), i, i, vp, vp, i, vp]
     L.sdorb_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i, i, vp, i, i, sz, sz, f, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
@@ -406,6 +414,24 @@ class ORBextractor:
         asg = np.zeros((P, cap), np.int32)
         nm = np.zeros(P, np.int32)
         self._check(lib().sdorb_search_by_projection_batch(self._h, C.byref(q), P, cap, _ptr(asg), _ptr(nm), MEM_HOST, None))
+        return nm, asg
+
+    def search_map_points_batch(self, proj, view_cos, level, flags, desc_mp, n_mp, kps_un, desc, u_right, occupied, n_frame, grid,
+                                scale_factors, th, nnratio=0.8):
+        """ORBmatcher::SearchByProjection(Frame, vpMapPoints, th) for a batch of frames (host arrays; see include/sdorb.h):
+        returns (nmatches[F], assigned[F, cap])."""
+        keep = [np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(view_cos, np.float32), np.ascontiguousarray(level, np.int32),
+                np.ascontiguousarray(flags, np.uint8), np.ascontiguousarray(desc_mp, np.uint8), np.ascontiguousarray(n_mp, np.int32),
+                np.ascontiguousarray(kps_un), np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(u_right, np.float32),
+                np.ascontiguousarray(occupied, np.uint8), np.ascontiguousarray(n_frame, np.int32),
+                np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32),
+                np.ascontiguousarray(scale_factors, np.float32)]
+        F, capmp, cap = keep[1].shape[0], keep[1].shape[1], keep[6].shape[1]
+        q = _MapPointSearch(*[_ptr(k) for k in keep[:11]], _FrameGrid(_ptr(keep[11]), _ptr(keep[12]), *[float(v) for v in grid[2:6]]),
+                            _ptr(keep[13]), len(keep[13]), float(th), float(nnratio))
+        asg = np.zeros((F, cap), np.int32)
+        nm = np.zeros(F, np.int32)
+        self._check(lib().sdorb_search_map_points_batch(self._h, C.byref(q), F, capmp, cap, _ptr(asg), _ptr(nm), MEM_HOST, None))
         return nm, asg
 
     def search_for_triangulation_batch(self, kps1_un, desc1, has_mp1, u_right1, n1, kps2_un, desc2, has_mp2, u_right2, n2, F12, epipole,

@@ -112,6 +112,17 @@ struct SearchTriArgs {  // ORBmatcher::SearchForTriangulation from the epipole o
   float gate[SDORB_MAX_LEVELS];   // smallest float >= 3.84 * mvLevelSigma2[level]
   float eplim[SDORB_MAX_LEVELS];  // 100 * mvScaleFactors[level]
 };
+struct SearchPointsArgs {  // ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)
+  const float* proj;  const float* view_cos;  const int32_t* level;  const uint8_t* flags;  const uint8_t* desc_mp;  const int32_t* n_mp;
+  const void* kps;  const uint8_t* desc;  const float* u_right;  const uint8_t* occupied;  const int32_t* n_frame;
+  SearchGrid grid;
+  int32_t* assigned;  // [nframes][capacity]
+  int32_t* nmatches;  // [nframes]
+  int capacity, capacity_mp, th_high;
+  float th, nnratio;
+  float scale_factors[SDORB_MAX_LEVELS];
+};
+void launch_search_points(const SearchPointsArgs& a, int nframes, cudaStream_t s);
 void launch_search_triangulation(const SearchTriArgs& a, int npairs, cudaStream_t s);
 void launch_search_init(const SearchInitArgs& a, int npairs, cudaStream_t s);
 void launch_search_projection(const SearchProjArgs& a, int npairs, cudaStream_t s);

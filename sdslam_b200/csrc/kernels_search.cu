@@ -370,6 +370,107 @@ size_t search_projection_smem(int capacity) {
   return sizeof(int) * ((size_t)capacity + GRID_COLS + GRID_COLS + 1 + 32) + (size_t)2 * capacity + 16;
 }
 
+// ---------------------------------------------------------------------------------------- SearchByProjection (Frame, map points)
+// src/ORBmatcher.cc:43-119, the local-map search of Tracking::SearchLocalPoints: the map points are visited in order and an
+// accepted match occupies its keypoint for the later ones, so one warp owns a frame; per map point the window's candidates
+// are taken 32 at a time.  Best and second-best (with their pyramid levels) are the two smallest packed words
+// (distance << 16 | candidate): the sequential update rule of :87-97 is exactly that order.
+__device__ __forceinline__ void warp_min2(uint32_t& m1, uint32_t& m2) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const uint32_t a1 = __shfl_xor_sync(0xffffffffu, m1, o), a2 = __shfl_xor_sync(0xffffffffu, m2, o);
+    const uint32_t lo = min(m1, a1), hi = max(m1, a1);
+    m2 = min(hi, min(m2, a2));
+    m1 = lo;
+  }
+}
+
+__global__ void __launch_bounds__(32) search_points_kernel(SearchPointsArgs a) {
+  extern __shared__ int s_mem[];
+  const int frame = blockIdx.x, lane = threadIdx.x, cap = a.capacity, capmp = a.capacity_mp;
+  int* s_begin = s_mem;                   // [64]
+  int* s_prefix = s_begin + GRID_COLS;    // [65]
+  uint8_t* s_occ = reinterpret_cast<uint8_t*>(s_prefix + GRID_COLS + 1 + 1);  // [cap]
+  const int nMP = min(a.n_mp[frame], capmp), nF = min(a.n_frame[frame], cap);
+  const float* proj = a.proj + (int64_t)frame * capmp * 3;
+  const float* vcos = a.view_cos + (int64_t)frame * capmp;
+  const int32_t* lvl = a.level + (int64_t)frame * capmp;
+  const uint8_t* fl = a.flags + (int64_t)frame * capmp;
+  const uint8_t* dMP = a.desc_mp + (int64_t)frame * capmp * 32;
+  const KP* kF = reinterpret_cast<const KP*>(a.kps) + (int64_t)frame * cap;
+  const uint8_t* dF = a.desc + (int64_t)frame * cap * 32;
+  const float* uR = a.u_right + (int64_t)frame * cap;
+  const int32_t* cs = a.grid.cell_start + (int64_t)frame * (GRID_COLS * GRID_ROWS + 1);
+  const int32_t* idx = a.grid.indices + (int64_t)frame * cap;
+  int32_t* assigned = a.assigned + (int64_t)frame * cap;
+  for (int i = lane; i < cap; i += 32) {
+    assigned[i] = -1;
+    s_occ[i] = i < nF ? a.occupied[(int64_t)frame * cap + i] : 0;
+  }
+  __syncwarp();
+  int nmatches = 0;
+  const bool factor = (double)a.th != 1.0;
+  for (int i = 0; i < nMP; ++i) {
+    const int flags = fl[i];
+    if (!(flags & 1)) continue;
+    const int level = lvl[i];
+    float r = (double)vcos[i] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos, :121-126
+    if (factor) r = __fmul_rn(r, a.th);
+    const float radius = __fmul_rn(r, a.scale_factors[min(max(level, 0), SDORB_MAX_LEVELS - 1)]);
+    const float x = proj[3 * i], y = proj[3 * i + 1], xr = proj[3 * i + 2];
+    int x0, x1, y0, y1;
+    if (!area_cells(x, y, radius, a.grid, x0, x1, y0, y1)) continue;
+    const int total = window_spans(cs, x0, x1, y0, y1, lane, s_begin, s_prefix);
+    const int minLevel = level - 1, maxLevel = level;
+    const bool check_levels = minLevel > 0 || maxLevel >= 0;
+    uint32_t q[8];
+    load_desc(dMP + (int64_t)i * 32, q);
+    uint32_t m1 = (256u << 16) | 0xFFFFu, m2 = (256u << 16) | 0xFFFFu;
+    for (int k = lane; k < total; k += 32) {
+      const int i2 = idx[candidate_slot(k, x1 - x0 + 1, s_begin, s_prefix)];
+      const KP kp = kF[i2];
+      if (check_levels) {
+        if (kp.octave < minLevel) continue;
+        if (maxLevel >= 0 && kp.octave > maxLevel) continue;
+      }
+      if (!(fabsf(__fsub_rn(kp.x, x)) < radius && fabsf(__fsub_rn(kp.y, y)) < radius)) continue;
+      if (s_occ[i2]) continue;
+      const float r2 = uR[i2];
+      if (r2 > 0.f && fabsf(__fsub_rn(xr, r2)) > radius) continue;
+      uint32_t t[8];
+      load_desc(dF + (int64_t)i2 * 32, t);
+      const uint4 lo = make_uint4(t[0], t[1], t[2], t[3]), hi = make_uint4(t[4], t[5], t[6], t[7]);
+      const uint32_t v = ((uint32_t)hamming256(q, lo, hi) << 16) | (uint32_t)k;
+      m2 = min(m2, max(m1, v));
+      m1 = min(m1, v);
+    }
+    warp_min2(m1, m2);
+    const int bestDist = (int)(m1 >> 16), bestDist2 = (int)(m2 >> 16);
+    if (bestDist <= a.th_high && bestDist < 256) {
+      if (lane == 0) {
+        const int bestIdx = idx[candidate_slot((int)(m1 & 0xFFFFu), x1 - x0 + 1, s_begin, s_prefix)];
+        const int bestLevel = kF[bestIdx].octave;
+        int bestLevel2 = -1;
+        if (bestDist2 < 256) bestLevel2 = kF[idx[candidate_slot((int)(m2 & 0xFFFFu), x1 - x0 + 1, s_begin, s_prefix)]].octave;
+        const bool reject = bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nnratio, (float)bestDist2);
+        if (!reject) {
+          assigned[bestIdx] = i;
+          s_occ[bestIdx] = (flags & 2) ? 1 : 0;
+          nmatches++;
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) a.nmatches[frame] = nmatches;
+}
+
+size_t search_points_smem(int capacity) { return sizeof(int) * (size_t)(GRID_COLS + GRID_COLS + 2) + (size_t)capacity + 16; }
+
+void launch_search_points(const SearchPointsArgs& a, int nframes, cudaStream_t s) {
+  search_points_kernel<<<nframes, 32, search_points_smem(a.capacity), s>>>(a);
+}
+
 // ---------------------------------------------------------------------------------------- SearchForTriangulation
 // src/ORBmatcher.cc:359-462 with CheckDistEpipolarLine :128-144.  This reference never sets vbMatched2, so every keypoint of
 // KF1 is independent: among the keypoints of KF2 that have no map point, pass the epipolar gate, lie within TH_LOW and (for a
@@ -503,6 +604,8 @@ int configure_search_kernels() {
   cudaError_t e = cudaFuncSetAttribute(search_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e != cudaSuccess) return (int)e;
   e = cudaFuncSetAttribute(search_projection_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return (int)e;
+  e = cudaFuncSetAttribute(search_points_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   return (int)e;
 }
 

@@ -1012,6 +1012,61 @@ int sdorb_search_by_projection_batch(sdorb_handle* h, const sdorb_projection_sea
   return SDORB_OK;
 }
 
+int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search* q, int nframes, int capacity_mp, int capacity,
+                                  int32_t* assigned, int32_t* nmatches, int mem, void* stream) {
+  if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nframes == 0) return SDORB_OK;
+  if (!q || !q->proj || !q->view_cos || !q->level || !q->flags || !q->desc_mp || !q->n_mp || !q->kps_un || !q->desc || !q->u_right ||
+      !q->occupied || !q->n_frame || !q->grid.cell_start || !q->grid.indices || !q->scale_factors || q->nlevels <= 0 ||
+      q->nlevels > SDORB_MAX_LEVELS || !assigned || !nmatches || capacity <= 0 || capacity > kSearchMaxCapacity || capacity_mp <= 0)
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  SearchPointsArgs a;
+  a.capacity = capacity;
+  a.capacity_mp = capacity_mp;
+  a.th_high = 100;  // ORBmatcher::TH_HIGH, src/ORBmatcher.cc:36
+  a.th = q->th;
+  a.nnratio = q->nnratio;
+  for (int l = 0; l < SDORB_MAX_LEVELS; ++l) a.scale_factors[l] = q->scale_factors[std::min(l, q->nlevels - 1)];
+  a.grid.min_x = q->grid.min_x; a.grid.min_y = q->grid.min_y;
+  a.grid.inv_w = q->grid.inv_w; a.grid.inv_h = q->grid.inv_h;
+  const size_t P = (size_t)nframes, C = (size_t)capacity, M = (size_t)capacity_mp, ncs = (size_t)SDORB_GRID_COLS * SDORB_GRID_ROWS + 1;
+  Stager st;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (((uintptr_t)q->desc_mp | (uintptr_t)q->desc) % 16) return SDORB_ERR_BAD_ARG;
+    a.proj = q->proj; a.view_cos = q->view_cos; a.level = q->level; a.flags = q->flags; a.desc_mp = q->desc_mp; a.n_mp = q->n_mp;
+    a.kps = q->kps_un; a.desc = q->desc; a.u_right = q->u_right; a.occupied = q->occupied; a.n_frame = q->n_frame;
+    a.grid.cell_start = q->grid.cell_start; a.grid.indices = q->grid.indices;
+    a.assigned = assigned; a.nmatches = nmatches;
+  } else {
+    const size_t iPR = st.add(q->proj, nullptr, 12 * P * M), iVC = st.add(q->view_cos, nullptr, 4 * P * M),
+                 iLV = st.add(q->level, nullptr, 4 * P * M), iFL = st.add(q->flags, nullptr, P * M),
+                 iDM = st.add(q->desc_mp, nullptr, 32 * P * M), iNM = st.add(q->n_mp, nullptr, 4 * P),
+                 iK = st.add(q->kps_un, nullptr, sizeof(sdorb_keypoint) * P * C), iD = st.add(q->desc, nullptr, 32 * P * C),
+                 iUR = st.add(q->u_right, nullptr, 4 * P * C), iOC = st.add(q->occupied, nullptr, P * C),
+                 iNF = st.add(q->n_frame, nullptr, 4 * P), iCS = st.add(q->grid.cell_start, nullptr, 4 * ncs * P),
+                 iIX = st.add(q->grid.indices, nullptr, 4 * P * C), iAS = st.add(nullptr, assigned, 4 * P * C),
+                 iNO = st.add(nullptr, nmatches, 4 * P);
+    int rc = st.upload(h, s);
+    if (rc) return rc;
+    a.proj = (float*)st.dev(h, iPR); a.view_cos = (float*)st.dev(h, iVC); a.level = (int32_t*)st.dev(h, iLV);
+    a.flags = (uint8_t*)st.dev(h, iFL); a.desc_mp = (uint8_t*)st.dev(h, iDM); a.n_mp = (int32_t*)st.dev(h, iNM);
+    a.kps = (void*)st.dev(h, iK); a.desc = (uint8_t*)st.dev(h, iD); a.u_right = (float*)st.dev(h, iUR);
+    a.occupied = (uint8_t*)st.dev(h, iOC); a.n_frame = (int32_t*)st.dev(h, iNF);
+    a.grid.cell_start = (int32_t*)st.dev(h, iCS); a.grid.indices = (int32_t*)st.dev(h, iIX);
+    a.assigned = (int32_t*)st.dev(h, iAS); a.nmatches = (int32_t*)st.dev(h, iNO);
+  }
+  {
+    StageScope sc(h, s, SDORB_STAGE_MATCH);
+    launch_search_points(a, nframes, s);
+    sc.launched();
+  }
+  CU(cudaGetLastError());
+  if (mem == SDORB_MEM_HOST) return st.download(h, s);
+  return SDORB_OK;
+}
+
 int sdorb_search_for_triangulation_batch(sdorb_handle* h, const sdorb_triangulation_search* q, int npairs, int capacity,
                                          int32_t* matches12, int32_t* nmatches, int mem, void* stream) {
   if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;

@@ -378,3 +378,72 @@ def triangulation_case(seed, n1=300, n2=320, width=640, height=480, nlevels=8, d
     ex, ey = F32(rng.uniform(100, width - 100)), F32(rng.uniform(100, height - 100))
     sf = (F32(1.2) ** np.arange(nlevels)).astype(F32)
     return k1, d1, mp1, ur1, k2, d2, mp2, ur2, F12, ex, ey, sf, (sf * sf).astype(F32)
+
+
+# ------------------------------------------------------------------ SearchByProjection(Frame, map points) (src/ORBmatcher.cc:43-126)
+def map_point_inputs(seed, kf, df, n_mp=400, nlevels=8):
+    """Map points of the local map as Tracking::SearchLocalPoints hands them over: most project near a keypoint of the frame
+    (descriptor a few bits away, predicted level the keypoint's or one above), some are not in view, some have no observations."""
+    rng = np.random.default_rng(seed + 900)
+    nF = len(kf)
+    proj = np.zeros((n_mp, 3), F32)
+    level = np.zeros(n_mp, np.int32)
+    desc_mp = rng.integers(0, 256, (n_mp, 32), dtype=np.uint8)
+    if nF:
+        src = rng.integers(0, nF, n_mp)
+        proj[:, 0] = kf["x"][src] + rng.uniform(-3, 3, n_mp).astype(F32)
+        proj[:, 1] = kf["y"][src] + rng.uniform(-3, 3, n_mp).astype(F32)
+        proj[:, 2] = proj[:, 0] - rng.uniform(0, 30, n_mp).astype(F32)
+        level[:] = np.clip(kf["octave"][src] + rng.integers(0, 2, n_mp), 0, nlevels - 1)
+        dd = df[src].copy()
+        for r in range(n_mp):
+            for b in rng.choice(256, int(rng.integers(0, 40)), replace=False):
+                dd[r, b >> 3] ^= 1 << (b & 7)
+        desc_mp = dd
+    else:
+        proj[:, 0], proj[:, 1] = rng.uniform(0, 640, n_mp), rng.uniform(0, 480, n_mp)
+        level[:] = rng.integers(0, nlevels, n_mp)
+    view_cos = np.where(rng.random(n_mp) < 0.5, rng.uniform(0.9981, 1.0, n_mp), rng.uniform(0.5, 0.998, n_mp)).astype(F32)
+    view_cos[:4] = [0.998, np.nextafter(F32(0.998), F32(1)), np.nextafter(F32(0.998), F32(0)), 1.0][:min(4, n_mp)] if n_mp >= 4 else view_cos[:4]
+    flags = (rng.random(n_mp) < 0.85).astype(np.uint8) | ((rng.random(n_mp) < 0.7).astype(np.uint8) << 1)
+    return proj, view_cos, level, flags, desc_mp
+
+
+def py_search_map_points(proj, view_cos, level, flags, desc_mp, kf, df, ur, occ_in, gp, sf, th, nnratio):
+    """ORBmatcher::SearchByProjection(Frame, vpMapPoints, th): (nmatches, assigned)."""
+    grid = py_grid(kf, gp)
+    n = 0
+    assigned = [-1] * len(kf)
+    occ = [bool(v) for v in occ_in]
+    factor = float(F32(th)) != 1.0
+    for i in range(len(proj)):
+        if not flags[i] & 1:
+            continue
+        lvl = int(level[i])
+        r = F32(2.5) if float(view_cos[i]) > 0.998 else F32(4.0)
+        if factor:
+            r = F32(r * F32(th))
+        radius = F32(r * F32(sf[lvl]))
+        x, y, xr = (F32(v) for v in proj[i])
+        cand = py_features_in_area(kf, grid, gp, x, y, radius, lvl - 1, lvl)
+        if not cand:
+            continue
+        best = best2 = 256
+        blevel = blevel2 = bidx = -1
+        for idx in cand:
+            if occ[idx]:
+                continue
+            if ur[idx] > 0 and abs(F32(xr - F32(ur[idx]))) > radius:
+                continue
+            d = py_distance(desc_mp[i], df[idx])
+            if d < best:
+                best2, best, blevel2, blevel, bidx = best, d, blevel, int(kf["octave"][idx]), idx
+            elif d < best2:
+                blevel2, best2 = int(kf["octave"][idx]), d
+        if best <= TH_HIGH:
+            if blevel == blevel2 and F32(best) > F32(F32(nnratio) * F32(best2)):
+                continue
+            assigned[bidx] = i
+            occ[bidx] = bool(flags[i] & 2)
+            n += 1
+    return n, np.array(assigned, np.int32)

@@ -234,3 +234,39 @@ def test_triangulation_golden_fixture(ex):
                                                one(c[6]), one(c[7]), [len(c[4])], c[8].reshape(1, 9), np.array([[c[9], c[10]]], np.float32),
                                                c[11], c[12], True)
     assert nm[0] == n and np.array_equal(gm[0, :len(c[0])], m12)
+
+
+# ------------------------------------------------------------------ SearchByProjection(Frame, map points): Tracking::SearchLocalPoints
+@pytest.mark.parametrize("th,ratio,stereo", [(1.0, 0.8, False), (3.0, 0.8, True), (5.0, 0.6, True)])
+def test_search_map_points_equals_oracle(ex, th, ratio, stereo):
+    """sdorb_search_map_points_batch = ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th)
+    (src/ORBmatcher.cc:43-119): ragged batch incl. empty frames / no map points, duplicate descriptors, view cosines around the
+    0.998 switch of RadiusByViewingCos."""
+    sizes = [(600, 500, 0.0), (500, 700, 0.0), (300, 200, 0.0), (0, 50, 0.0), (200, 0, 0.0), (700, 900, 0.3), (1, 1, 0.0)]
+    frames = []
+    for s, (nf, nmp, dup) in enumerate(sizes):
+        _, _, kf, df = sc.frame_pair(s + 60, 10, nf, dup=dup, level0=0.3)
+        proj, vc, lvl, fl, dmp = sc.map_point_inputs(s, kf, df, nmp)
+        rng = np.random.default_rng(s)
+        ur = (np.where(rng.random(nf) < 0.6, kf["x"] - rng.uniform(0, 30, nf), -1) if stereo else np.full(nf, -1)).astype(np.float32)
+        occ = (rng.random(nf) < 0.1).astype(np.uint8)
+        frames.append((proj, vc, lvl, fl, dmp, kf, df, ur, occ))
+    cap, capmp = 704, 912
+    gp = sc.grid_params()
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    col = lambda j, c, dt, tail=(): _slab([f[j] for f in frames], c, dt, tail)
+    proj, vc, lvl, fl, dmp = col(0, capmp, np.float32, (3,)), col(1, capmp, np.float32), col(2, capmp, np.int32), col(3, capmp, np.uint8), col(4, capmp, np.uint8, (32,))
+    kf, df, ur, occ = col(5, cap, api.KP_DTYPE), col(6, cap, np.uint8, (32,)), col(7, cap, np.float32), col(8, cap, np.uint8)
+    nmp = np.array([len(f[0]) for f in frames], np.int32)
+    nf = np.array([len(f[5]) for f in frames], np.int32)
+    cs, idx = ex.assign_grid_batch(kf, nf, *gp)
+    nm, asg = ex.search_map_points_batch(proj, vc, lvl, fl, dmp, nmp, kf, df, ur, occ, nf, (cs, idx) + tuple(gp), sf, th, ratio)
+    total = 0
+    for p, f in enumerate(frames):
+        ocs, oidx = orc.assign_grid(f[5], *gp)
+        on, oasg = orc.search_map_points(f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7], f[8], (ocs, oidx) + tuple(gp), sf, th, ratio)
+        assert nm[p] == on, "frame %d: nmatches %d vs oracle %d" % (p, nm[p], on)
+        assert np.array_equal(asg[p, :len(f[5])], oasg), "frame %d: assignment" % p
+        assert (asg[p, len(f[5]):] == -1).all()
+        total += on
+    assert total > 300

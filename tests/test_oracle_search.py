@@ -169,3 +169,22 @@ def test_triangulation_golden_fixture():
     case, n, m12 = _load_triangulation_fixture()
     on, om12 = orc.search_for_triangulation(*case, True)
     assert on == n and np.array_equal(om12, m12) and n > 10
+
+
+# ------------------------------------------------------------------ SearchByProjection(Frame, map points): Tracking::SearchLocalPoints
+@pytest.mark.parametrize("seed,nf,nmp,th,ratio,stereo", [(0, 600, 500, 1.0, 0.8, False), (1, 500, 700, 3.0, 0.8, True),
+                                                         (2, 300, 200, 5.0, 0.6, True), (3, 0, 50, 1.0, 0.8, False),
+                                                         (4, 200, 0, 1.0, 0.8, False), (5, 700, 900, 1.0, 1.0, True)])
+def test_search_map_points_equals_restatement(seed, nf, nmp, th, ratio, stereo):
+    _, _, kf, df = sc.frame_pair(seed + 60, 10, nf, dup=0.3 if seed == 5 else 0.0, level0=0.3)
+    proj, vc, lvl, fl, dmp = sc.map_point_inputs(seed, kf, df, nmp)
+    rng = np.random.default_rng(seed)
+    ur = (np.where(rng.random(nf) < 0.6, kf["x"] - rng.uniform(0, 30, nf), -1) if stereo else np.full(nf, -1)).astype(np.float32)
+    occ = (rng.random(nf) < 0.1).astype(np.uint8)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    gp = sc.grid_params()
+    n, asg = orc.search_map_points(proj, vc, lvl, fl, dmp, kf, df, ur, occ, _orc_grid(kf, gp), sf, th, ratio)
+    pn, pasg = sc.py_search_map_points(proj, vc, lvl, fl, dmp, kf, df, ur, occ, gp, sf, th, ratio)
+    assert n == pn and np.array_equal(asg, pasg)
+    if seed == 0:
+        assert n > 100
