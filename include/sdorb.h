@@ -270,6 +270,15 @@ typedef struct {
 SDORB_API int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search* q, int nframes, int capacity_mp, int capacity,
                                             int32_t* assigned, int32_t* nmatches, int mem, void* stream);
 
+/* ORBmatcher::SearchByPoints(currentKF, pKF, matches) (src/ORBmatcher.cc:1207-1296; loop detection, src/LoopClosing.cc:255), batched
+ * over keyframe pairs.  valid1 / valid2 [npairs][capacity]: the keypoint has a map point that is not bad (:1231-1236, :1246-1251).
+ * matches12 [npairs][capacity]: index into the second keyframe whose map point the call puts into matches[idx1], -1 = NULL;
+ * nmatches [npairs].  The matcher is the one constructed as ORBmatcher(nnratio, check_orientation). */
+SDORB_API int sdorb_search_by_points_batch(sdorb_handle* h, const sdorb_keypoint* kps1_un, const uint8_t* desc1, const uint8_t* valid1,
+                                           const int32_t* n1, const sdorb_keypoint* kps2_un, const uint8_t* desc2,
+                                           const uint8_t* valid2, const int32_t* n2, int npairs, int capacity, float nnratio,
+                                           int check_orientation, int32_t* matches12, int32_t* nmatches, int mem, void* stream);
+
 /* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs) (src/ORBmatcher.cc:359-462, with CheckDistEpipolarLine
  * :128-144) from the epipole on: the pose algebra of :361-368 stays with the caller, which passes per pair F12 (row-major
  * doubles, F12(i, j) = F12[3 * i + j]) and the epipole (ex, ey) as the floats of :367-368.  has_mp1 / has_mp2 [npairs][capacity]:

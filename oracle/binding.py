@@ -129,6 +129,8 @@ def lib(path=None):
         L.orc_search_by_projection.restype = i
         L.orc_search_map_points.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, C.POINTER(FrameGrid), vp, f, f, vp]
         L.orc_search_map_points.restype = i
+        L.orc_search_by_points.argtypes = [vp, vp, vp, i, vp, vp, vp, i, f, i, vp]
+        L.orc_search_by_points.restype = i
         L.orc_check_dist_epipolar_line.argtypes = [f, f, f, f, vp, f]
         L.orc_check_dist_epipolar_line.restype = i
         L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, f, f, vp, vp, i, vp]
@@ -465,3 +467,13 @@ def search_map_points(proj, view_cos, level, flags, desc_mp, kps_un, desc, u_rig
     n = lib().orc_search_map_points(_p(pr), _p(vc), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(ur), _p(oc), len(k), C.byref(g),
                                     _p(sf), th, nnratio, _p(asg))
     return n, asg[:len(k)]
+
+
+def search_by_points(kps1_un, desc1, valid1, kps2_un, desc2, valid2, nnratio=0.75, check_orientation=True):
+    """ORBmatcher::SearchByPoints: (nmatches, matches12)."""
+    k1, k2 = np.ascontiguousarray(kps1_un, KP_DTYPE), np.ascontiguousarray(kps2_un, KP_DTYPE)
+    d1, d2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+    v1, v2 = np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(valid2, np.uint8)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = lib().orc_search_by_points(_p(k1), _p(d1), _p(v1), len(k1), _p(k2), _p(d2), _p(v2), len(k2), nnratio, int(check_orientation), _p(m12))
+    return n, m12[:len(k1)]

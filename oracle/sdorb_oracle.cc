@@ -1377,6 +1377,53 @@ int orc_search_map_points(const float* proj /* n x 3 */, const float* view_cos, 
   }
   return nmatches;
 }
+// ORBmatcher::SearchByPoints(currentKF, pKF, matches), src/ORBmatcher.cc:1207-1296 (loop detection, LoopClosing.cc:255).
+// valid1 / valid2: the keypoint has a map point that is not bad.  matches12[idx1] = idx2 whose map point ends up in matches[idx1].
+int orc_search_by_points(const orc_keypoint* k1, const uint8_t* d1s, const uint8_t* valid1, int n1, const orc_keypoint* k2,
+                         const uint8_t* d2s, const uint8_t* valid2, int n2, float mfNNratio, int mbCheckOrientation, int32_t* matches12) {
+  int nmatches = 0;
+  std::vector<std::vector<int>> rotHist(kHistoLength);
+  std::fill(matches12, matches12 + n1, -1);
+  std::vector<char> vbMatched2((size_t)n2, 0);
+  for (int idx1 = 0; idx1 < n1; idx1++) {
+    if (!valid1[idx1]) continue;
+    const uint8_t* d1 = d1s + (size_t)idx1 * 32;
+    int bestDist1 = 256, bestIdx2 = -1, bestDist2 = 256;
+    for (int idx2 = 0; idx2 < n2; idx2++) {
+      if (!valid2[idx2] || vbMatched2[idx2]) continue;
+      const int dist = descriptor_distance(d1, d2s + (size_t)idx2 * 32);
+      if (dist < bestDist1) {
+        bestDist2 = bestDist1;
+        bestDist1 = dist;
+        bestIdx2 = idx2;
+      } else if (dist < bestDist2) {
+        bestDist2 = dist;
+      }
+    }
+    if (bestDist1 < kThLow) {
+      if ((float)bestDist1 < mfNNratio * (float)bestDist2) {
+        matches12[idx1] = bestIdx2;
+        vbMatched2[bestIdx2] = 1;
+        if (mbCheckOrientation) rotHist[rotation_bin(k1[idx1].angle, k2[bestIdx2].angle)].push_back(idx1);
+        nmatches++;
+      }
+    }
+  }
+  if (mbCheckOrientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    int32_t sizes[kHistoLength];
+    for (int i = 0; i < kHistoLength; i++) sizes[i] = (int)rotHist[i].size();
+    orc_three_maxima(sizes, kHistoLength, &ind1, &ind2, &ind3);
+    for (int i = 0; i < kHistoLength; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i]) {
+        matches12[idx1] = -1;
+        nmatches--;
+      }
+    }
+  }
+  return nmatches;
+}
 // ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:128-144.  F12 is an Eigen::Matrix3d, so a, b, c are evaluated in double
 // and rounded to float; the reference's -O3 -march=native contracts  p*q + r*s  into  fma(p, q, r*s)  (first product fused,
 // checked against the compiled verbatim expression in tests/test_oracle_search.py), frozen here with explicit fma / fmaf.

@@ -103,6 +103,7 @@ def lib():
                                                         i, vp]
     L.sdorb_search_by_projection_batch.argtypes = [vp, C.POINTER(_ProjectionSearch), i, i, vp, vp, i, vp]
     L.sdorb_search_map_points_batch.argtypes = [vp, C.POINTER(_MapPointSearch), i, i, i, vp, vp, i, vp]
+    L.sdorb_search_by_points_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, f, i, vp, vp, i, vp]
     L.sdorb_search_for_triangulation_batch.argtypes = [vp, C.POINTER(_TriangulationSearch), i, i, vp, vp, i, vp]
     L.sdorb_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i, i, vp, i, i, sz, sz, f, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
@@ -433,6 +434,20 @@ class ORBextractor:
         nm = np.zeros(F, np.int32)
         self._check(lib().sdorb_search_map_points_batch(self._h, C.byref(q), F, capmp, cap, _ptr(asg), _ptr(nm), MEM_HOST, None))
         return nm, asg
+
+    def search_by_points_batch(self, kps1_un, desc1, valid1, n1, kps2_un, desc2, valid2, n2, nnratio=0.75, check_orientation=True):
+        """ORBmatcher::SearchByPoints for a batch of keyframe pairs (host arrays): returns (nmatches[P], matches12[P, cap])."""
+        k1, k2 = np.ascontiguousarray(kps1_un), np.ascontiguousarray(kps2_un)
+        d1, d2 = np.ascontiguousarray(desc1, np.uint8), np.ascontiguousarray(desc2, np.uint8)
+        v1, v2 = np.ascontiguousarray(valid1, np.uint8), np.ascontiguousarray(valid2, np.uint8)
+        n1, n2 = np.ascontiguousarray(n1, np.int32), np.ascontiguousarray(n2, np.int32)
+        P, cap = k1.shape[0], k1.shape[1]
+        m12 = np.zeros((P, cap), np.int32)
+        nm = np.zeros(P, np.int32)
+        self._check(lib().sdorb_search_by_points_batch(self._h, _ptr(k1), _ptr(d1), _ptr(v1), _ptr(n1), _ptr(k2), _ptr(d2), _ptr(v2),
+                                                        _ptr(n2), P, cap, float(nnratio), int(check_orientation), _ptr(m12), _ptr(nm),
+                                                        MEM_HOST, None))
+        return nm, m12
 
     def search_for_triangulation_batch(self, kps1_un, desc1, has_mp1, u_right1, n1, kps2_un, desc2, has_mp2, u_right2, n2, F12, epipole,
                                        scale_factors, level_sigma2, check_orientation=True, matches12=None, nmatches=None,

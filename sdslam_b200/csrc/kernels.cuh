@@ -123,6 +123,15 @@ struct SearchPointsArgs {  // ORBmatcher::SearchByProjection(Frame&, const vecto
   float scale_factors[SDORB_MAX_LEVELS];
 };
 void launch_search_points(const SearchPointsArgs& a, int nframes, cudaStream_t s);
+struct SearchByPointsArgs {  // ORBmatcher::SearchByPoints
+  const void* kps1;  const uint8_t* desc1;  const uint8_t* valid1;  const int32_t* n1;
+  const void* kps2;  const uint8_t* desc2;  const uint8_t* valid2;  const int32_t* n2;
+  int32_t* matches12;  // [npairs][capacity]
+  int32_t* nmatches;   // [npairs]
+  int capacity, th_low, check_orientation;
+  float nnratio;
+};
+void launch_search_by_points(const SearchByPointsArgs& a, int npairs, cudaStream_t s);
 void launch_search_triangulation(const SearchTriArgs& a, int npairs, cudaStream_t s);
 void launch_search_init(const SearchInitArgs& a, int npairs, cudaStream_t s);
 void launch_search_projection(const SearchProjArgs& a, int npairs, cudaStream_t s);

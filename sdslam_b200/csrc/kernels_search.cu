@@ -471,6 +471,89 @@ void launch_search_points(const SearchPointsArgs& a, int nframes, cudaStream_t s
   search_points_kernel<<<nframes, 32, search_points_smem(a.capacity), s>>>(a);
 }
 
+// ---------------------------------------------------------------------------------------- SearchByPoints
+// src/ORBmatcher.cc:1207-1296 (loop detection): brute force over the keypoints of the other keyframe that have a good map point and
+// are not taken yet (vbMatched2), best / second-best, TH_LOW and the ratio test, rotation histogram.  Queries in order; one
+// warp per keyframe pair, the lanes split the rows of the second keyframe.
+__global__ void __launch_bounds__(32) search_by_points_kernel(SearchByPointsArgs a) {
+  extern __shared__ int s_mem[];
+  const int pair = blockIdx.x, lane = threadIdx.x, cap = a.capacity;
+  uint32_t* s_taken = reinterpret_cast<uint32_t*>(s_mem);       // bitset over the rows of KF2: no good map point, or matched
+  int* s_histo = s_mem + (cap + 31) / 32;                        // [32]
+  int8_t* s_bin = reinterpret_cast<int8_t*>(s_histo + 32);       // [cap]
+  const int n1 = min(a.n1[pair], cap), n2 = min(a.n2[pair], cap);
+  const KP* k1 = reinterpret_cast<const KP*>(a.kps1) + (int64_t)pair * cap;
+  const KP* k2 = reinterpret_cast<const KP*>(a.kps2) + (int64_t)pair * cap;
+  const uint8_t* d1 = a.desc1 + (int64_t)pair * cap * 32;
+  const uint4* d2 = reinterpret_cast<const uint4*>(a.desc2 + (int64_t)pair * cap * 32);
+  const uint8_t* v1 = a.valid1 + (int64_t)pair * cap;
+  const uint8_t* v2 = a.valid2 + (int64_t)pair * cap;
+  int32_t* m12 = a.matches12 + (int64_t)pair * cap;
+  for (int w = lane; w < (n2 + 31) / 32; w += 32) {
+    uint32_t bits = 0;
+    for (int b = 0; b < 32; ++b) {
+      const int j = 32 * w + b;
+      if (j >= n2 || !v2[j]) bits |= 1u << b;
+    }
+    s_taken[w] = bits;
+  }
+  for (int i = lane; i < cap; i += 32) {
+    m12[i] = -1;
+    s_bin[i] = -1;
+  }
+  s_histo[lane] = 0;
+  __syncwarp();
+  int nmatches = 0;
+  for (int i1 = 0; i1 < n1; ++i1) {
+    if (!v1[i1]) continue;
+    uint32_t q[8];
+    load_desc(d1 + (int64_t)i1 * 32, q);
+    int best1 = (256 << 16) | 0xFFFF, best2 = 256;
+    for (int j = lane; j < n2; j += 32) {
+      if ((s_taken[j >> 5] >> (j & 31)) & 1u) continue;
+      const int d = hamming256(q, d2[2 * j], d2[2 * j + 1]);
+      best2 = min(best2, max(d, best1 >> 16));
+      best1 = min(best1, (d << 16) | j);
+    }
+    warp_best2(best1, best2);
+    const int bd = best1 >> 16;
+    if (bd < a.th_low && (float)bd < __fmul_rn(a.nnratio, (float)best2)) {
+      if (lane == 0) {
+        const int j = best1 & 0xFFFF;
+        m12[i1] = j;
+        s_taken[j >> 5] |= 1u << (j & 31);
+        if (a.check_orientation) {
+          const int bin = rotation_bin(k1[i1].angle, k2[j].angle);
+          s_bin[i1] = (int8_t)bin;
+          s_histo[bin]++;
+        }
+        nmatches++;
+      }
+    }
+    __syncwarp();
+  }
+  if (a.check_orientation) {
+    const uint32_t keep = three_maxima_mask(s_histo);
+    int removed = 0;
+    for (int i = lane; i < n1; i += 32) {
+      const int bin = s_bin[i];
+      if (bin >= 0 && !((keep >> bin) & 1u)) {
+        m12[i] = -1;
+        removed++;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) removed += __shfl_xor_sync(0xffffffffu, removed, o);
+    nmatches -= removed;
+  }
+  if (lane == 0) a.nmatches[pair] = nmatches;
+}
+
+void launch_search_by_points(const SearchByPointsArgs& a, int npairs, cudaStream_t s) {
+  const size_t smem = sizeof(int) * (size_t)((a.capacity + 31) / 32 + 32) + (size_t)a.capacity + 16;
+  search_by_points_kernel<<<npairs, 32, smem, s>>>(a);
+}
+
 // ---------------------------------------------------------------------------------------- SearchForTriangulation
 // src/ORBmatcher.cc:359-462 with CheckDistEpipolarLine :128-144.  This reference never sets vbMatched2, so every keypoint of
 // KF1 is independent: among the keypoints of KF2 that have no map point, pass the epipolar gate, lie within TH_LOW and (for a

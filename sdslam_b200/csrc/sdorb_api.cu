@@ -1067,6 +1067,50 @@ int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search*
   return SDORB_OK;
 }
 
+int sdorb_search_by_points_batch(sdorb_handle* h, const sdorb_keypoint* kps1, const uint8_t* desc1, const uint8_t* valid1,
+                                 const int32_t* n1, const sdorb_keypoint* kps2, const uint8_t* desc2, const uint8_t* valid2,
+                                 const int32_t* n2, int npairs, int capacity, float nnratio, int check_orientation, int32_t* matches12,
+                                 int32_t* nmatches, int mem, void* stream) {
+  if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (npairs == 0) return SDORB_OK;
+  if (!kps1 || !desc1 || !valid1 || !n1 || !kps2 || !desc2 || !valid2 || !n2 || !matches12 || !nmatches || capacity <= 0 ||
+      capacity > kSearchMaxCapacity)
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  SearchByPointsArgs a;
+  a.capacity = capacity;
+  a.th_low = 50;  // ORBmatcher::TH_LOW, src/ORBmatcher.cc:37
+  a.check_orientation = check_orientation ? 1 : 0;
+  a.nnratio = nnratio;
+  const size_t P = (size_t)npairs, C = (size_t)capacity;
+  Stager st;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (((uintptr_t)desc1 | (uintptr_t)desc2) % 16) return SDORB_ERR_BAD_ARG;
+    a.kps1 = kps1; a.desc1 = desc1; a.valid1 = valid1; a.n1 = n1; a.kps2 = kps2; a.desc2 = desc2; a.valid2 = valid2; a.n2 = n2;
+    a.matches12 = matches12; a.nmatches = nmatches;
+  } else {
+    const size_t bK = sizeof(sdorb_keypoint) * P * C;
+    const size_t iK1 = st.add(kps1, nullptr, bK), iD1 = st.add(desc1, nullptr, 32 * P * C), iV1 = st.add(valid1, nullptr, P * C),
+                 iN1 = st.add(n1, nullptr, 4 * P), iK2 = st.add(kps2, nullptr, bK), iD2 = st.add(desc2, nullptr, 32 * P * C),
+                 iV2 = st.add(valid2, nullptr, P * C), iN2 = st.add(n2, nullptr, 4 * P), iM = st.add(nullptr, matches12, 4 * P * C),
+                 iNM = st.add(nullptr, nmatches, 4 * P);
+    int rc = st.upload(h, s);
+    if (rc) return rc;
+    a.kps1 = (void*)st.dev(h, iK1); a.desc1 = (uint8_t*)st.dev(h, iD1); a.valid1 = (uint8_t*)st.dev(h, iV1); a.n1 = (int32_t*)st.dev(h, iN1);
+    a.kps2 = (void*)st.dev(h, iK2); a.desc2 = (uint8_t*)st.dev(h, iD2); a.valid2 = (uint8_t*)st.dev(h, iV2); a.n2 = (int32_t*)st.dev(h, iN2);
+    a.matches12 = (int32_t*)st.dev(h, iM); a.nmatches = (int32_t*)st.dev(h, iNM);
+  }
+  {
+    StageScope sc(h, s, SDORB_STAGE_MATCH);
+    launch_search_by_points(a, npairs, s);
+    sc.launched();
+  }
+  CU(cudaGetLastError());
+  if (mem == SDORB_MEM_HOST) return st.download(h, s);
+  return SDORB_OK;
+}
+
 int sdorb_search_for_triangulation_batch(sdorb_handle* h, const sdorb_triangulation_search* q, int npairs, int capacity,
                                          int32_t* matches12, int32_t* nmatches, int mem, void* stream) {
   if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;

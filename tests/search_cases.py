@@ -447,3 +447,40 @@ def py_search_map_points(proj, view_cos, level, flags, desc_mp, kf, df, ur, occ_
             occ[bidx] = bool(flags[i] & 2)
             n += 1
     return n, np.array(assigned, np.int32)
+
+
+# ------------------------------------------------------------------ SearchByPoints (src/ORBmatcher.cc:1207-1296)
+def py_search_by_points(k1, d1, v1, k2, d2, v2, nnratio, check_orientation):
+    """ORBmatcher::SearchByPoints: (nmatches, matches12)."""
+    n = 0
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    m12 = [-1] * len(k1)
+    matched2 = [False] * len(k2)
+    for i1 in range(len(k1)):
+        if not v1[i1]:
+            continue
+        best1 = best2 = 256
+        bidx = -1
+        for i2 in range(len(k2)):
+            if not v2[i2] or matched2[i2]:
+                continue
+            d = py_distance(d1[i1], d2[i2])
+            if d < best1:
+                best2, best1, bidx = best1, d, i2
+            elif d < best2:
+                best2 = d
+        if best1 < TH_LOW and F32(best1) < F32(F32(nnratio) * F32(best2)):
+            m12[i1] = bidx
+            matched2[bidx] = True
+            if check_orientation:
+                hist[_bin(k1["angle"][i1], k2["angle"][bidx])].append(i1)
+            n += 1
+    if check_orientation:
+        keep = py_three_maxima([len(h) for h in hist])
+        for b in range(HISTO_LENGTH):
+            if b in keep:
+                continue
+            for i1 in hist[b]:
+                m12[i1] = -1
+                n -= 1
+    return n, np.array(m12, np.int32)

@@ -270,3 +270,28 @@ def test_search_map_points_equals_oracle(ex, th, ratio, stereo):
         assert (asg[p, len(f[5]):] == -1).all()
         total += on
     assert total > 300
+
+
+@pytest.mark.parametrize("ratio,orient", [(0.75, True), (0.9, False)])
+def test_search_by_points_equals_oracle(ex, ratio, orient):
+    """sdorb_search_by_points_batch = ORBmatcher::SearchByPoints (src/ORBmatcher.cc:1207-1296): ragged batch of keyframe pairs,
+    keypoints without (good) map points on both sides, duplicate descriptors (contested rows of the second keyframe)."""
+    sizes = [(600, 640, 0.0), (400, 380, 0.4), (1000, 1000, 0.1), (0, 50, 0.0), (50, 0, 0.0), (33, 65, 0.6), (1, 1, 0.0)]
+    pairs = [sc.frame_pair(80 + s, a, b, dup=d, flips=25) for s, (a, b, d) in enumerate(sizes)]
+    rng = np.random.default_rng(3)
+    valid = [((rng.random(len(p[0])) < 0.8).astype(np.uint8), (rng.random(len(p[2])) < 0.8).astype(np.uint8)) for p in pairs]
+    cap = 1024
+    k1, d1 = _slab([p[0] for p in pairs], cap, api.KP_DTYPE), _slab([p[1] for p in pairs], cap, np.uint8, (32,))
+    k2, d2 = _slab([p[2] for p in pairs], cap, api.KP_DTYPE), _slab([p[3] for p in pairs], cap, np.uint8, (32,))
+    v1, v2 = _slab([v[0] for v in valid], cap, np.uint8), _slab([v[1] for v in valid], cap, np.uint8)
+    n1 = np.array([len(p[0]) for p in pairs], np.int32)
+    n2 = np.array([len(p[2]) for p in pairs], np.int32)
+    nm, m12 = ex.search_by_points_batch(k1, d1, v1, n1, k2, d2, v2, n2, ratio, orient)
+    total = 0
+    for p, (a1, b1, a2, b2) in enumerate(pairs):
+        on, om12 = orc.search_by_points(a1, b1, valid[p][0], a2, b2, valid[p][1], ratio, orient)
+        assert nm[p] == on, "pair %d: nmatches %d vs oracle %d" % (p, nm[p], on)
+        assert np.array_equal(m12[p, :len(a1)], om12), "pair %d: matches" % p
+        assert (m12[p, len(a1):] == -1).all()
+        total += on
+    assert total > 300

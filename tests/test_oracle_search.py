@@ -188,3 +188,17 @@ def test_search_map_points_equals_restatement(seed, nf, nmp, th, ratio, stereo):
     assert n == pn and np.array_equal(asg, pasg)
     if seed == 0:
         assert n > 100
+
+
+# ------------------------------------------------------------------ SearchByPoints (loop detection)
+@pytest.mark.parametrize("seed,n1,n2,ratio,orient,dup", [(0, 300, 320, 0.75, True, 0.0), (1, 200, 150, 0.9, False, 0.4),
+                                                         (2, 0, 40, 0.75, True, 0.0), (3, 40, 0, 0.75, True, 0.0), (4, 250, 250, 0.75, True, 0.6)])
+def test_search_by_points_equals_restatement(seed, n1, n2, ratio, orient, dup):
+    k1, d1, k2, d2 = sc.frame_pair(seed + 80, n1, n2, dup=dup, flips=25)
+    rng = np.random.default_rng(seed)
+    v1, v2 = (rng.random(n1) < 0.8).astype(np.uint8), (rng.random(n2) < 0.8).astype(np.uint8)
+    n, m12 = orc.search_by_points(k1, d1, v1, k2, d2, v2, ratio, orient)
+    pn, pm12 = sc.py_search_by_points(k1, d1, v1, k2, d2, v2, ratio, orient)
+    assert n == pn and np.array_equal(m12, pm12)
+    if seed == 0:
+        assert n > 50
