@@ -238,6 +238,10 @@ typedef struct {
   float bounds[4];
   float th, mbf;
   int mode, check_orientation;
+  int orb_dist;                       /* distance threshold; 0 = TH_HIGH (100).  With it the same entry point serves
+                                         SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1298-1420):
+                                         kps_last.octave = nPredictedLevel, mode 0, flags bit 1 set, u_right_cur = -1,
+                                         occupied_cur = (mvpMapPoints[i2] != NULL), proj[2] = any value >= 0 */
 } sdorb_projection_search;
 SDORB_API int sdorb_search_by_projection_batch(sdorb_handle* h, const sdorb_projection_search* q, int npairs, int capacity,
                                                int32_t* assigned, int32_t* nmatches, int mem, void* stream);

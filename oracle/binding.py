@@ -125,7 +125,7 @@ def lib(path=None):
         L.orc_three_maxima.argtypes = [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
         L.orc_search_for_initialization.argtypes = [vp, vp, i, vp, vp, i, C.POINTER(FrameGrid), vp, i, f, i, vp]
         L.orc_search_for_initialization.restype = i
-        L.orc_search_by_projection.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, C.POINTER(FrameGrid), vp, vp, f, f, i, i, vp]
+        L.orc_search_by_projection.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, C.POINTER(FrameGrid), vp, vp, f, f, i, i, vp, i]
         L.orc_search_by_projection.restype = i
         L.orc_search_map_points.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, C.POINTER(FrameGrid), vp, f, f, vp]
         L.orc_search_map_points.restype = i
@@ -418,7 +418,7 @@ def search_for_initialization(kps1_un, desc1, kps2_un, desc2, grid2, prev_matche
 
 
 def search_by_projection(kps_last, kps_last_un, proj, flags_last, desc_mp, kps_cur_un, desc_cur, u_right_cur, occupied_cur,
-                         grid_cur, scale_factors, bounds, th, mbf, mode, check_orientation=True):
+                         grid_cur, scale_factors, bounds, th, mbf, mode, check_orientation=True, orb_dist=0):
     """ORBmatcher::SearchByProjection(CurrentFrame, LastFrame, th, bMono) from the projection on: (nmatches, assigned)."""
     kl, klu = np.ascontiguousarray(kps_last, KP_DTYPE), np.ascontiguousarray(kps_last_un, KP_DTYPE)
     kc = np.ascontiguousarray(kps_cur_un, KP_DTYPE)
@@ -430,7 +430,7 @@ def search_by_projection(kps_last, kps_last_un, proj, flags_last, desc_mp, kps_c
     g, keep = _grid(*grid_cur)
     asg = np.full(max(len(kc), 1), -1, np.int32)
     n = lib().orc_search_by_projection(_p(kl), _p(klu), _p(pr), _p(fl), _p(dm), len(kl), _p(kc), _p(dc), _p(ur), _p(oc), len(kc),
-                                       C.byref(g), _p(sf), _p(bd), th, mbf, mode, int(check_orientation), _p(asg))
+                                       C.byref(g), _p(sf), _p(bd), th, mbf, mode, int(check_orientation), _p(asg), int(orb_dist))
     return n, asg[:len(kc)]
 
 

@@ -1267,7 +1267,9 @@ int orc_search_for_initialization(const orc_keypoint* k1, const uint8_t* d1s, in
 int orc_search_by_projection(const orc_keypoint* kL, const orc_keypoint* kLun, const float* proj, const uint8_t* flagsL,
                              const uint8_t* descMP, int nL, const orc_keypoint* kC, const uint8_t* descC, const float* uRightC,
                              const uint8_t* occupied_in, int nC, const orc_frame_grid* gridC, const float* mvScaleFactors,
-                             const float bounds[4], float th, float mbf, int mode, int mbCheckOrientation, int32_t* assigned) {
+                             const float bounds[4], float th, float mbf, int mode, int mbCheckOrientation, int32_t* assigned,
+                             int orb_dist) {
+  const int thHigh = orb_dist > 0 ? orb_dist : kThHigh; /* the KeyFrame overload (:1298-1420) passes its own ORBdist */
   int nmatches = 0;
   std::fill(assigned, assigned + nC, -1);
   std::vector<uint8_t> occupiedC(occupied_in, occupied_in + nC);
@@ -1304,7 +1306,7 @@ int orc_search_by_projection(const orc_keypoint* kL, const orc_keypoint* kLun, c
         bestIdx2 = i2;
       }
     }
-    if (bestDist <= kThHigh) {
+    if (bestDist <= thHigh) {
       assigned[bestIdx2] = i;                        // CurrentFrame.mvpMapPoints[bestIdx2] = pMP
       occupiedC[bestIdx2] = (flagsL[i] & 2) ? 1 : 0;  // what a later candidate test (:1018-1020) sees for it
       nmatches++;

@@ -177,7 +177,7 @@ int orc_search_by_projection(const orc_keypoint* kps_last, const orc_keypoint* k
                              const uint8_t* flags_last, const uint8_t* desc_mp, int n_last, const orc_keypoint* kps_cur_un,
                              const uint8_t* desc_cur, const float* u_right_cur, const uint8_t* occupied_cur, int n_cur,
                              const orc_frame_grid* grid_cur, const float* scale_factors, const float bounds[4], float th,
-                             float mbf, int mode, int check_orientation, int32_t* assigned);
+                             float mbf, int mode, int check_orientation, int32_t* assigned, int orb_dist /* 0 = TH_HIGH */);
 
 /* ORBmatcher::SearchByProjection(Frame&, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:43-119): see sdorb_oracle.cc for the
  * argument conventions; returns nmatches, assigned has n_frame entries. */

@@ -51,7 +51,7 @@ class _ProjectionSearch(C.Structure):
                 ("desc_mp", C.c_void_p), ("n_last", C.c_void_p), ("kps_cur_un", C.c_void_p), ("desc_cur", C.c_void_p),
                 ("u_right_cur", C.c_void_p), ("occupied_cur", C.c_void_p), ("n_cur", C.c_void_p), ("grid_cur", _FrameGrid),
                 ("scale_factors", C.c_void_p), ("nlevels", C.c_int), ("bounds", C.c_float * 4), ("th", C.c_float),
-                ("mbf", C.c_float), ("mode", C.c_int), ("check_orientation", C.c_int)]
+                ("mbf", C.c_float), ("mode", C.c_int), ("check_orientation", C.c_int), ("orb_dist", C.c_int)]
 
 
 class _MapPointSearch(C.Structure):
@@ -394,7 +394,7 @@ class ORBextractor:
 
     def search_by_projection_batch(self, kps_last, kps_last_un, proj, flags_last, desc_mp, n_last, kps_cur_un, desc_cur,
                                    u_right_cur, occupied_cur, n_cur, grid_cur, scale_factors, bounds, th, mbf, mode,
-                                   check_orientation=True):
+                                   check_orientation=True, orb_dist=0):
         """Returns (nmatches[P], assigned[P, cap]); see sdorb_search_by_projection_batch in include/sdorb.h."""
         kl, klu, kc = np.ascontiguousarray(kps_last), np.ascontiguousarray(kps_last_un), np.ascontiguousarray(kps_cur_un)
         P, cap = kl.shape[0], kl.shape[1]
@@ -412,6 +412,7 @@ class ORBextractor:
         q.scale_factors, q.nlevels = _ptr(keep[10]), len(keep[10])
         q.bounds = (C.c_float * 4)(*[float(v) for v in bounds])
         q.th, q.mbf, q.mode, q.check_orientation = float(th), float(mbf), int(mode), int(check_orientation)
+        q.orb_dist = int(orb_dist)
         asg = np.zeros((P, cap), np.int32)
         nm = np.zeros(P, np.int32)
         self._check(lib().sdorb_search_by_projection_batch(self._h, C.byref(q), P, cap, _ptr(asg), _ptr(nm), MEM_HOST, None))

@@ -966,7 +966,7 @@ int sdorb_search_by_projection_batch(sdorb_handle* h, const sdorb_projection_sea
   SearchProjArgs a;
   a.capacity = capacity;
   a.mode = q->mode;
-  a.th_high = 100;  // ORBmatcher::TH_HIGH, src/ORBmatcher.cc:36
+  a.th_high = q->orb_dist > 0 ? q->orb_dist : 100;  // ORBmatcher::TH_HIGH, src/ORBmatcher.cc:36, or the KeyFrame overload's ORBdist
   a.check_orientation = q->check_orientation ? 1 : 0;
   a.th = q->th;
   a.mbf = q->mbf;

@@ -484,3 +484,65 @@ def py_search_by_points(k1, d1, v1, k2, d2, v2, nnratio, check_orientation):
                 m12[i1] = -1
                 n -= 1
     return n, np.array(m12, np.int32)
+
+
+# ------------------------------------------------------------------ SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist)
+def py_search_by_projection_kf(kkf_un, proj_uv, valid, pred_level, desc_mp, kc, dc, has_mp_cur, gp, sf, bounds, th, orb_dist,
+                               check_orientation):
+    """src/ORBmatcher.cc:1298-1420 from the projection on: valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP) && the depth test
+    of :1345-1350; pred_level = pMP->PredictScale(dist3D, &CurrentFrame).  (nmatches, assigned)."""
+    grid = py_grid(kc, gp)
+    n = 0
+    assigned = [-1] * len(kc)
+    has_mp = [bool(v) for v in has_mp_cur]
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    for i in range(len(kkf_un)):
+        if not valid[i]:
+            continue
+        u, v = F32(proj_uv[i][0]), F32(proj_uv[i][1])
+        if u < F32(bounds[0]) or u > F32(bounds[1]) or v < F32(bounds[2]) or v > F32(bounds[3]):
+            continue
+        lvl = int(pred_level[i])
+        radius = F32(F32(th) * F32(sf[lvl]))
+        cand = py_features_in_area(kc, grid, gp, u, v, radius, lvl - 1, lvl + 1)
+        if not cand:
+            continue
+        best, bidx = 256, -1
+        for i2 in cand:
+            if has_mp[i2]:
+                continue
+            d = py_distance(desc_mp[i], dc[i2])
+            if d < best:
+                best, bidx = d, i2
+        if best <= orb_dist:
+            assigned[bidx] = i
+            has_mp[bidx] = True
+            n += 1
+            if check_orientation:
+                hist[_bin(kkf_un["angle"][i], kc["angle"][bidx])].append(bidx)
+    if check_orientation:
+        keep = py_three_maxima([len(h) for h in hist])
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for i2 in hist[b]:
+                    assigned[i2] = -1
+                    n -= 1
+    return n, np.array(assigned, np.int32)
+
+
+def kf_projection_args(seed, nk, nc):
+    """Inputs of the KeyFrame overload and their mapping onto the Frame / Frame entry point (include/sdorb.h,
+    sdorb_projection_search::orb_dist): octave of kps_last = predicted level, flags = valid | 2, proj[2] = 1, mvuRight = -1."""
+    kk, dk, kc, dc = frame_pair(seed + 120, nk, nc, jitter=4.0, level0=0.3, flips=30)
+    rng = np.random.default_rng(seed + 7)
+    proj = np.zeros((nk, 3), F32)
+    proj[:, 0] = kk["x"] + rng.uniform(-3, 3, nk).astype(F32)
+    proj[:, 1] = kk["y"] + rng.uniform(-3, 3, nk).astype(F32)
+    proj[:, 2] = 1
+    valid = (rng.random(nk) < 0.8).astype(np.uint8)
+    pred = np.clip(kk["octave"] + rng.integers(-1, 2, nk), 0, 7).astype(np.int32)
+    has_mp = (rng.random(nc) < 0.15).astype(np.uint8)
+    k_level = kk.copy()
+    k_level["octave"] = pred
+    return dict(kk=kk, proj=proj, valid=valid, pred=pred, dmp=dk, kc=kc, dc=dc, has_mp=has_mp, k_level=k_level,
+                flags=(valid | 2).astype(np.uint8), ur=np.full(nc, -1, F32))

@@ -295,3 +295,26 @@ def test_search_by_points_equals_oracle(ex, ratio, orient):
         assert (m12[p, len(a1):] == -1).all()
         total += on
     assert total > 300
+
+
+def test_keyframe_projection_overload_on_gpu(ex):
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1298-1420) through
+    sdorb_search_by_projection_batch with orb_dist = 64, against the direct Python restatement of that overload."""
+    cases = [sc.kf_projection_args(s, nk, nc) for s, (nk, nc) in enumerate([(500, 520), (400, 300), (0, 100), (300, 0)])]
+    cap = 544
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    gp, bounds = sc.grid_params(), (0.0, 640.0, 0.0, 480.0)
+    col = lambda key, dt, tail=(): _slab([c[key] for c in cases], cap, dt, tail)
+    kc = col("kc", api.KP_DTYPE)
+    nk = np.array([len(c["kk"]) for c in cases], np.int32)
+    nc = np.array([len(c["kc"]) for c in cases], np.int32)
+    cs, idx = ex.assign_grid_batch(kc, nc, *gp)
+    nm, asg = ex.search_by_projection_batch(col("k_level", api.KP_DTYPE), col("kk", api.KP_DTYPE), col("proj", np.float32, (3,)),
+                                            col("flags", np.uint8), col("dmp", np.uint8, (32,)), nk, kc, col("dc", np.uint8, (32,)),
+                                            col("ur", np.float32), col("has_mp", np.uint8), nc, (cs, idx) + tuple(gp), sf, bounds, 10.0,
+                                            0.0, 0, True, orb_dist=64)
+    for p, a in enumerate(cases):
+        pn, pasg = sc.py_search_by_projection_kf(a["kk"], a["proj"], a["valid"], a["pred"], a["dmp"], a["kc"], a["dc"], a["has_mp"], gp,
+                                                 sf, bounds, 10.0, 64, True)
+        assert nm[p] == pn and np.array_equal(asg[p, :len(a["kc"])], pasg), "case %d" % p
+    assert int(nm.sum()) > 100

@@ -202,3 +202,21 @@ def test_search_by_points_equals_restatement(seed, n1, n2, ratio, orient, dup):
     assert n == pn and np.array_equal(m12, pm12)
     if seed == 0:
         assert n > 50
+
+
+# ------------------------------------------------------------------ SearchByProjection(Frame, KeyFrame, ...) through the Frame / Frame form
+@pytest.mark.parametrize("seed,nk,nc,th,orb_dist,orient", [(0, 500, 520, 10.0, 100, True), (1, 400, 300, 3.0, 64, True),
+                                                           (2, 300, 400, 10.0, 64, False), (3, 0, 100, 10.0, 100, True)])
+def test_keyframe_projection_overload_maps_onto_frame_frame_form(seed, nk, nc, th, orb_dist, orient):
+    """The relocalisation overload (src/ORBmatcher.cc:1298-1420) restated directly in Python equals the oracle's Frame / Frame
+    function driven with the mapping documented at sdorb_projection_search::orb_dist."""
+    a = sc.kf_projection_args(seed, nk, nc)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    gp, bounds = sc.grid_params(), (0.0, 640.0, 0.0, 480.0)
+    pn, pasg = sc.py_search_by_projection_kf(a["kk"], a["proj"], a["valid"], a["pred"], a["dmp"], a["kc"], a["dc"], a["has_mp"], gp, sf,
+                                             bounds, th, orb_dist, orient)
+    n, asg = orc.search_by_projection(a["k_level"], a["kk"], a["proj"], a["flags"], a["dmp"], a["kc"], a["dc"], a["ur"], a["has_mp"],
+                                      _orc_grid(a["kc"], gp), sf, bounds, th, 0.0, 0, orient, orb_dist=orb_dist)
+    assert n == pn and np.array_equal(asg, pasg)
+    if seed == 0:
+        assert n > 100
