@@ -283,6 +283,30 @@ SDORB_API int sdorb_search_by_points_batch(sdorb_handle* h, const sdorb_keypoint
                                            const uint8_t* valid2, const int32_t* n2, int npairs, int capacity, float nnratio,
                                            int check_orientation, int32_t* matches12, int32_t* nmatches, int mem, void* stream);
 
+/* The keypoint search of ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th) (src/ORBmatcher.cc:535-586), batched over
+ * keyframes: for every map point that passed the checks of :489-531 (flags bit 0; the caller does the pose algebra) the most
+ * similar keypoint inside the radius th * mvScaleFactors[level] whose level is level-1 or level and whose reprojection error
+ * passes the chi-square test (:560-580); proj = (u, v, ur), level = PredictScale(...).  best_idx [nframes][capacity_mp] = that
+ * keypoint if its distance is <= TH_LOW, else -1; best_dist the distance (256 = no candidate).  Replacing / adding the
+ * observation (:588-606) stays with the caller.  scale_factors / inv_level_sigma2: host pointers, nlevels entries. */
+typedef struct {
+  const float* proj;       /* [nframes][capacity_mp][3] */
+  const int32_t* level;    /* [nframes][capacity_mp] */
+  const uint8_t* flags;    /* [nframes][capacity_mp] */
+  const uint8_t* desc_mp;  /* [nframes][capacity_mp][32] */
+  const int32_t* n_mp;     /* [nframes] */
+  const sdorb_keypoint* kps_un; /* [nframes][capacity] */
+  const uint8_t* desc;
+  const float* u_right;
+  sdorb_frame_grid grid;
+  const float* scale_factors;
+  const float* inv_level_sigma2;
+  int nlevels;
+  float th;
+} sdorb_fuse_search;
+SDORB_API int sdorb_fuse_search_batch(sdorb_handle* h, const sdorb_fuse_search* q, int nframes, int capacity_mp, int capacity,
+                                      int32_t* best_idx, int32_t* best_dist, int mem, void* stream);
+
 /* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs) (src/ORBmatcher.cc:359-462, with CheckDistEpipolarLine
  * :128-144) from the epipole on: the pose algebra of :361-368 stays with the caller, which passes per pair F12 (row-major
  * doubles, F12(i, j) = F12[3 * i + j]) and the epipole (ex, ey) as the floats of :367-368.  has_mp1 / has_mp2 [npairs][capacity]:

@@ -131,6 +131,8 @@ def lib(path=None):
         L.orc_search_map_points.restype = i
         L.orc_search_by_points.argtypes = [vp, vp, vp, i, vp, vp, vp, i, f, i, vp]
         L.orc_search_by_points.restype = i
+        L.orc_fuse_search.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, C.POINTER(FrameGrid), vp, vp, f, vp, vp]
+        L.orc_fuse_search.restype = None
         L.orc_check_dist_epipolar_line.argtypes = [f, f, f, f, vp, f]
         L.orc_check_dist_epipolar_line.restype = i
         L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, f, f, vp, vp, i, vp]
@@ -477,3 +479,15 @@ def search_by_points(kps1_un, desc1, valid1, kps2_un, desc2, valid2, nnratio=0.7
     m12 = np.full(max(len(k1), 1), -1, np.int32)
     n = lib().orc_search_by_points(_p(k1), _p(d1), _p(v1), len(k1), _p(k2), _p(d2), _p(v2), len(k2), nnratio, int(check_orientation), _p(m12))
     return n, m12[:len(k1)]
+
+
+def fuse_search(proj, level, flags, desc_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th):
+    """The keypoint search of ORBmatcher::Fuse: (best_idx, best_dist) per map point."""
+    pr = np.ascontiguousarray(proj, np.float32).reshape(-1, 3)
+    lv, fl, dm = np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.uint8), np.ascontiguousarray(desc_mp, np.uint8)
+    k, d, ur = np.ascontiguousarray(kps_un, KP_DTYPE), np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(u_right, np.float32)
+    sf, is2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(inv_level_sigma2, np.float32)
+    g, keep = _grid(*grid)
+    bi, bd = np.full(max(len(pr), 1), -1, np.int32), np.full(max(len(pr), 1), 256, np.int32)
+    lib().orc_fuse_search(_p(pr), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(ur), C.byref(g), _p(sf), _p(is2), th, _p(bi), _p(bd))
+    return bi[:len(pr)], bd[:len(pr)]

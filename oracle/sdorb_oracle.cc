@@ -1426,6 +1426,45 @@ int orc_search_by_points(const orc_keypoint* k1, const uint8_t* d1s, const uint8
   }
   return nmatches;
 }
+// The keypoint search inside ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th), src/ORBmatcher.cc:535-586: per map point
+// that passed the checks of :489-531 (flags bit 0) the most similar keypoint within the radius, subject to the level window and
+// the chi-square test of the reprojection error; best_idx = -1 where none reaches TH_LOW.  The map surgery of :588-606 stays with the
+// caller.  e2 as the reference build contracts it: fma(er, er, fma(ex, ex, ey*ey)) (checked against the compiled expression).
+void orc_fuse_search(const float* proj /* n x 3: u, v, ur */, const int32_t* level, const uint8_t* flags, const uint8_t* descMP, int nMP,
+                     const orc_keypoint* kKF, const uint8_t* descKF, const float* uRight, const orc_frame_grid* grid,
+                     const float* mvScaleFactors, const float* mvInvLevelSigma2, float th, int32_t* best_idx, int32_t* best_dist) {
+  for (int i = 0; i < nMP; i++) {
+    best_idx[i] = -1;
+    best_dist[i] = 256;
+    if (!(flags[i] & 1)) continue;
+    const float u = proj[3 * i], v = proj[3 * i + 1], ur = proj[3 * i + 2];
+    const int nPredictedLevel = level[i];
+    const float radius = th * mvScaleFactors[nPredictedLevel];
+    const std::vector<int> vIndices = features_in_area(kKF, *grid, u, v, radius, -1, -1);  // KeyFrame::GetFeaturesInArea: no level filter
+    int bestDist = 256, bestIdx = -1;
+    for (int idx : vIndices) {
+      const orc_keypoint& kp = kKF[idx];
+      const int kpLevel = kp.octave;
+      if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+      if (uRight[idx] >= 0) {
+        const float ex = u - kp.x, ey = v - kp.y, er = ur - uRight[idx];
+        const float e2 = fmaf(er, er, fmaf(ex, ex, ey * ey));
+        if (e2 * mvInvLevelSigma2[kpLevel] > 7.8) continue;
+      } else {
+        const float ex = u - kp.x, ey = v - kp.y;
+        const float e2 = fmaf(ex, ex, ey * ey);
+        if (e2 * mvInvLevelSigma2[kpLevel] > 5.99) continue;
+      }
+      const int dist = descriptor_distance(descMP + (size_t)i * 32, descKF + (size_t)idx * 32);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx = idx;
+      }
+    }
+    best_dist[i] = bestDist;
+    if (bestDist <= kThLow) best_idx[i] = bestIdx;
+  }
+}
 // ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:128-144.  F12 is an Eigen::Matrix3d, so a, b, c are evaluated in double
 // and rounded to float; the reference's -O3 -march=native contracts  p*q + r*s  into  fma(p, q, r*s)  (first product fused,
 // checked against the compiled verbatim expression in tests/test_oracle_search.py), frozen here with explicit fma / fmaf.

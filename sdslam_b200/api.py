@@ -61,6 +61,12 @@ class _MapPointSearch(C.Structure):
                 ("nnratio", C.c_float)]
 
 
+class _FuseSearch(C.Structure):
+    _fields_ = [("proj", C.c_void_p), ("level", C.c_void_p), ("flags", C.c_void_p), ("desc_mp", C.c_void_p), ("n_mp", C.c_void_p),
+                ("kps_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("grid", _FrameGrid),
+                ("scale_factors", C.c_void_p), ("inv_level_sigma2", C.c_void_p), ("nlevels", C.c_int), ("th", C.c_float)]
+
+
 class _TriangulationSearch(C.Structure):
     _fields_ = [("kps1_un", C.c_void_p), ("desc1", C.c_void_p), ("has_mp1", C.c_void_p), ("u_right1", C.c_void_p), ("n1", C.c_void_p),
                 ("kps2_un", C.c_void_p), ("desc2", C.c_void_p), ("has_mp2", C.c_void_p), ("u_right2", C.c_void_p), ("n2", C.c_void_p),
@@ -104,6 +110,7 @@ def lib():
     L.sdorb_search_by_projection_batch.argtypes = [vp, C.POINTER(_ProjectionSearch), i, i, vp, vp, i, vp]
     L.sdorb_search_map_points_batch.argtypes = [vp, C.POINTER(_MapPointSearch), i, i, i, vp, vp, i, vp]
     L.sdorb_search_by_points_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, f, i, vp, vp, i, vp]
+    L.sdorb_fuse_search_batch.argtypes = [vp, C.POINTER(_FuseSearch), i, i, i, vp, vp, i, vp]
     L.sdorb_search_for_triangulation_batch.argtypes = [vp, C.POINTER(_TriangulationSearch), i, i, vp, vp, i, vp]
     L.sdorb_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i, i, vp, i, i, sz, sz, f, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
@@ -449,6 +456,20 @@ class ORBextractor:
                                                         _ptr(n2), P, cap, float(nnratio), int(check_orientation), _ptr(m12), _ptr(nm),
                                                         MEM_HOST, None))
         return nm, m12
+
+    def fuse_search_batch(self, proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th):
+        """The keypoint search of ORBmatcher::Fuse for a batch of keyframes (host arrays): (best_idx[F, cap_mp], best_dist[F, cap_mp])."""
+        keep = [np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.uint8),
+                np.ascontiguousarray(desc_mp, np.uint8), np.ascontiguousarray(n_mp, np.int32), np.ascontiguousarray(kps_un),
+                np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(u_right, np.float32),
+                np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32),
+                np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(inv_level_sigma2, np.float32)]
+        F, capmp, cap = keep[1].shape[0], keep[1].shape[1], keep[5].shape[1]
+        q = _FuseSearch(*[_ptr(k) for k in keep[:8]], _FrameGrid(_ptr(keep[8]), _ptr(keep[9]), *[float(v) for v in grid[2:6]]),
+                        _ptr(keep[10]), _ptr(keep[11]), len(keep[10]), float(th))
+        bi, bd = np.zeros((F, capmp), np.int32), np.zeros((F, capmp), np.int32)
+        self._check(lib().sdorb_fuse_search_batch(self._h, C.byref(q), F, capmp, cap, _ptr(bi), _ptr(bd), MEM_HOST, None))
+        return bi, bd
 
     def search_for_triangulation_batch(self, kps1_un, desc1, has_mp1, u_right1, n1, kps2_un, desc2, has_mp2, u_right2, n2, F12, epipole,
                                        scale_factors, level_sigma2, check_orientation=True, matches12=None, nmatches=None,

@@ -132,6 +132,17 @@ struct SearchByPointsArgs {  // ORBmatcher::SearchByPoints
   float nnratio;
 };
 void launch_search_by_points(const SearchByPointsArgs& a, int npairs, cudaStream_t s);
+struct FuseSearchArgs {  // the keypoint search of ORBmatcher::Fuse
+  const float* proj;  const int32_t* level;  const uint8_t* flags;  const uint8_t* desc_mp;  const int32_t* n_mp;
+  const void* kps;  const uint8_t* desc;  const float* u_right;
+  SearchGrid grid;
+  int32_t* best_idx;   // [nframes][capacity_mp]
+  int32_t* best_dist;  // [nframes][capacity_mp]
+  int capacity, capacity_mp, th_low;
+  float th;
+  float scale_factors[SDORB_MAX_LEVELS], inv_sigma2[SDORB_MAX_LEVELS];
+};
+void launch_fuse_search(const FuseSearchArgs& a, int nframes, cudaStream_t s);
 void launch_search_triangulation(const SearchTriArgs& a, int npairs, cudaStream_t s);
 void launch_search_init(const SearchInitArgs& a, int npairs, cudaStream_t s);
 void launch_search_projection(const SearchProjArgs& a, int npairs, cudaStream_t s);

@@ -554,6 +554,67 @@ void launch_search_by_points(const SearchByPointsArgs& a, int npairs, cudaStream
   search_by_points_kernel<<<npairs, 32, smem, s>>>(a);
 }
 
+// ---------------------------------------------------------------------------------------- Fuse (the keypoint search)
+// src/ORBmatcher.cc:535-586: every map point is independent here (the map surgery that follows stays with the caller), so a
+// thread takes a map point and walks the window's grid cells in the reference's order; strict < keeps the first minimum.
+__global__ void __launch_bounds__(128) fuse_search_kernel(FuseSearchArgs a) {
+  const int frame = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x, cap = a.capacity, capmp = a.capacity_mp;
+  if (i >= capmp) return;
+  int32_t* out_idx = a.best_idx + (int64_t)frame * capmp;
+  int32_t* out_dist = a.best_dist + (int64_t)frame * capmp;
+  int bestDist = 256, bestIdx = -1;
+  const int nMP = min(a.n_mp[frame], capmp);
+  if (i < nMP && (a.flags[(int64_t)frame * capmp + i] & 1)) {
+    const float* pr = a.proj + ((int64_t)frame * capmp + i) * 3;
+    const float u = pr[0], v = pr[1], ur = pr[2];
+    const int level = a.level[(int64_t)frame * capmp + i];
+    const float radius = __fmul_rn(a.th, a.scale_factors[min(max(level, 0), SDORB_MAX_LEVELS - 1)]);
+    int x0, x1, y0, y1;
+    if (area_cells(u, v, radius, a.grid, x0, x1, y0, y1)) {
+      const KP* kF = reinterpret_cast<const KP*>(a.kps) + (int64_t)frame * cap;
+      const uint8_t* dF = a.desc + (int64_t)frame * cap * 32;
+      const float* uR = a.u_right + (int64_t)frame * cap;
+      const int32_t* cs = a.grid.cell_start + (int64_t)frame * (GRID_COLS * GRID_ROWS + 1);
+      const int32_t* idx = a.grid.indices + (int64_t)frame * cap;
+      uint32_t q[8];
+      load_desc(a.desc_mp + ((int64_t)frame * capmp + i) * 32, q);
+      for (int ix = x0; ix <= x1; ++ix) {
+        const int e = cs[ix * GRID_ROWS + y1 + 1];
+        for (int s = cs[ix * GRID_ROWS + y0]; s < e; ++s) {  // the cells (ix, y0..y1) are one contiguous span
+          const int i2 = idx[s];
+          const KP kp = kF[i2];
+          if (!(fabsf(__fsub_rn(kp.x, u)) < radius && fabsf(__fsub_rn(kp.y, v)) < radius)) continue;
+          if (kp.octave < level - 1 || kp.octave > level) continue;
+          const float inv = a.inv_sigma2[min(max(kp.octave, 0), SDORB_MAX_LEVELS - 1)];
+          const float ex = __fsub_rn(u, kp.x), ey = __fsub_rn(v, kp.y);
+          float e2 = __fmaf_rn(ex, ex, __fmul_rn(ey, ey));
+          const float r2 = uR[i2];
+          double lim = 5.99;
+          if (r2 >= 0.f) {
+            const float er = __fsub_rn(ur, r2);
+            e2 = __fmaf_rn(er, er, e2);
+            lim = 7.8;
+          }
+          if ((double)__fmul_rn(e2, inv) > lim) continue;
+          uint32_t t[8];
+          load_desc(dF + (int64_t)i2 * 32, t);
+          const int d = hamming256(q, make_uint4(t[0], t[1], t[2], t[3]), make_uint4(t[4], t[5], t[6], t[7]));
+          if (d < bestDist) {
+            bestDist = d;
+            bestIdx = i2;
+          }
+        }
+      }
+    }
+  }
+  out_dist[i] = bestDist;
+  out_idx[i] = bestDist <= a.th_low ? bestIdx : -1;
+}
+
+void launch_fuse_search(const FuseSearchArgs& a, int nframes, cudaStream_t s) {
+  fuse_search_kernel<<<dim3((a.capacity_mp + 127) / 128, nframes), 128, 0, s>>>(a);
+}
+
 // ---------------------------------------------------------------------------------------- SearchForTriangulation
 // src/ORBmatcher.cc:359-462 with CheckDistEpipolarLine :128-144.  This reference never sets vbMatched2, so every keypoint of
 // KF1 is independent: among the keypoints of KF2 that have no map point, pass the epipolar gate, lie within TH_LOW and (for a

@@ -1111,6 +1111,60 @@ int sdorb_search_by_points_batch(sdorb_handle* h, const sdorb_keypoint* kps1, co
   return SDORB_OK;
 }
 
+int sdorb_fuse_search_batch(sdorb_handle* h, const sdorb_fuse_search* q, int nframes, int capacity_mp, int capacity, int32_t* best_idx,
+                            int32_t* best_dist, int mem, void* stream) {
+  if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nframes == 0) return SDORB_OK;
+  if (!q || !q->proj || !q->level || !q->flags || !q->desc_mp || !q->n_mp || !q->kps_un || !q->desc || !q->u_right ||
+      !q->grid.cell_start || !q->grid.indices || !q->scale_factors || !q->inv_level_sigma2 || q->nlevels <= 0 ||
+      q->nlevels > SDORB_MAX_LEVELS || !best_idx || !best_dist || capacity <= 0 || capacity > kSearchMaxCapacity || capacity_mp <= 0)
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  FuseSearchArgs a;
+  a.capacity = capacity;
+  a.capacity_mp = capacity_mp;
+  a.th_low = 50;  // ORBmatcher::TH_LOW, src/ORBmatcher.cc:37
+  a.th = q->th;
+  for (int l = 0; l < SDORB_MAX_LEVELS; ++l) {
+    a.scale_factors[l] = q->scale_factors[std::min(l, q->nlevels - 1)];
+    a.inv_sigma2[l] = q->inv_level_sigma2[std::min(l, q->nlevels - 1)];
+  }
+  a.grid.min_x = q->grid.min_x; a.grid.min_y = q->grid.min_y;
+  a.grid.inv_w = q->grid.inv_w; a.grid.inv_h = q->grid.inv_h;
+  const size_t P = (size_t)nframes, C = (size_t)capacity, M = (size_t)capacity_mp, ncs = (size_t)SDORB_GRID_COLS * SDORB_GRID_ROWS + 1;
+  Stager st;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (((uintptr_t)q->desc_mp | (uintptr_t)q->desc) % 16) return SDORB_ERR_BAD_ARG;
+    a.proj = q->proj; a.level = q->level; a.flags = q->flags; a.desc_mp = q->desc_mp; a.n_mp = q->n_mp;
+    a.kps = q->kps_un; a.desc = q->desc; a.u_right = q->u_right;
+    a.grid.cell_start = q->grid.cell_start; a.grid.indices = q->grid.indices;
+    a.best_idx = best_idx; a.best_dist = best_dist;
+  } else {
+    const size_t iPR = st.add(q->proj, nullptr, 12 * P * M), iLV = st.add(q->level, nullptr, 4 * P * M), iFL = st.add(q->flags, nullptr, P * M),
+                 iDM = st.add(q->desc_mp, nullptr, 32 * P * M), iNM = st.add(q->n_mp, nullptr, 4 * P),
+                 iK = st.add(q->kps_un, nullptr, sizeof(sdorb_keypoint) * P * C), iD = st.add(q->desc, nullptr, 32 * P * C),
+                 iUR = st.add(q->u_right, nullptr, 4 * P * C), iCS = st.add(q->grid.cell_start, nullptr, 4 * ncs * P),
+                 iIX = st.add(q->grid.indices, nullptr, 4 * P * C), iBI = st.add(nullptr, best_idx, 4 * P * M),
+                 iBD = st.add(nullptr, best_dist, 4 * P * M);
+    int rc = st.upload(h, s);
+    if (rc) return rc;
+    a.proj = (float*)st.dev(h, iPR); a.level = (int32_t*)st.dev(h, iLV); a.flags = (uint8_t*)st.dev(h, iFL);
+    a.desc_mp = (uint8_t*)st.dev(h, iDM); a.n_mp = (int32_t*)st.dev(h, iNM);
+    a.kps = (void*)st.dev(h, iK); a.desc = (uint8_t*)st.dev(h, iD); a.u_right = (float*)st.dev(h, iUR);
+    a.grid.cell_start = (int32_t*)st.dev(h, iCS); a.grid.indices = (int32_t*)st.dev(h, iIX);
+    a.best_idx = (int32_t*)st.dev(h, iBI); a.best_dist = (int32_t*)st.dev(h, iBD);
+  }
+  {
+    StageScope sc(h, s, SDORB_STAGE_MATCH);
+    launch_fuse_search(a, nframes, s);
+    sc.launched();
+  }
+  CU(cudaGetLastError());
+  if (mem == SDORB_MEM_HOST) return st.download(h, s);
+  return SDORB_OK;
+}
+
 int sdorb_search_for_triangulation_batch(sdorb_handle* h, const sdorb_triangulation_search* q, int npairs, int capacity,
                                          int32_t* matches12, int32_t* nmatches, int mem, void* stream) {
   if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;

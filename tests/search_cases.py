@@ -546,3 +546,78 @@ def kf_projection_args(seed, nk, nc):
     k_level["octave"] = pred
     return dict(kk=kk, proj=proj, valid=valid, pred=pred, dmp=dk, kc=kc, dc=dc, has_mp=has_mp, k_level=k_level,
                 flags=(valid | 2).astype(np.uint8), ur=np.full(nc, -1, F32))
+
+
+# ------------------------------------------------------------------ Fuse: the keypoint search (src/ORBmatcher.cc:535-586)
+def fuse_inputs(seed, kf, n_mp=400, nlevels=8, stereo=True):
+    """Map points as ORBmatcher::Fuse sees them after its visibility checks: most project close to a keypoint of the keyframe
+    (some right on the chi-square limit), predicted level the keypoint's or one above / below, some fail the checks (flag 0)."""
+    rng = np.random.default_rng(seed + 1300)
+    nF = len(kf)
+    proj = np.zeros((n_mp, 3), F32)
+    level = rng.integers(0, nlevels, n_mp).astype(np.int32)
+    ur = np.full(nF, -1, F32)
+    if nF:
+        ur_all = np.where(rng.random(nF) < 0.6, kf["x"] - rng.uniform(0, 30, nF), -1).astype(F32)
+        if stereo:
+            ur = ur_all
+        src = rng.integers(0, nF, n_mp)
+        spread = rng.choice([0.3, 1.5, 4.0], n_mp)
+        proj[:, 0] = kf["x"][src] + (rng.uniform(-1, 1, n_mp) * spread).astype(F32)
+        proj[:, 1] = kf["y"][src] + (rng.uniform(-1, 1, n_mp) * spread).astype(F32)
+        proj[:, 2] = np.where(ur[src] >= 0, ur[src] + rng.uniform(-1.5, 1.5, n_mp), proj[:, 0] - 10).astype(F32)
+        level[:] = np.clip(kf["octave"][src] + rng.integers(-1, 2, n_mp), 0, nlevels - 1)
+    else:
+        proj[:, 0], proj[:, 1] = rng.uniform(0, 640, n_mp), rng.uniform(0, 480, n_mp)
+    flags = (rng.random(n_mp) < 0.85).astype(np.uint8)
+    return proj, level, flags, ur
+
+
+def fuse_descriptors(seed, df, kf_src_n, n_mp):
+    """Map-point descriptors: the descriptor of the keypoint the point was projected next to (same draw of src as fuse_inputs)
+    with 0..70 bits flipped, so distances straddle TH_LOW = 50."""
+    rng = np.random.default_rng(seed + 1400)
+    if kf_src_n == 0:
+        return rng.integers(0, 256, (n_mp, 32), dtype=np.uint8)
+    r0 = np.random.default_rng(seed + 1300)
+    r0.integers(0, 8, n_mp)
+    r0.random(kf_src_n), r0.uniform(0, 30, kf_src_n)
+    dd = df[r0.integers(0, kf_src_n, n_mp)].copy()
+    for r in range(n_mp):
+        for b in rng.choice(256, int(rng.integers(0, 71)), replace=False):
+            dd[r, b >> 3] ^= 1 << (b & 7)
+    return dd
+
+
+def py_fuse_search(proj, level, flags, desc_mp, kf, df, ur, gp, sf, inv_sigma2, th):
+    """(best_idx, best_dist) per map point; e2 in the contracted form of the reference build (see
+    test_fuse_e2_matches_reference_flags): fma(er, er, fma(ex, ex, ey * ey))."""
+    grid = py_grid(kf, gp)
+    bi, bd = [-1] * len(proj), [256] * len(proj)
+    for i in range(len(proj)):
+        if not flags[i] & 1:
+            continue
+        lvl = int(level[i])
+        u, v, r = (F32(x) for x in proj[i])
+        radius = F32(F32(th) * F32(sf[lvl]))
+        best, bidx = 256, -1
+        for idx in py_features_in_area(kf, grid, gp, u, v, radius, -1, -1):
+            kl = int(kf["octave"][idx])
+            if kl < lvl - 1 or kl > lvl:
+                continue
+            ex, ey = F32(u - F32(kf["x"][idx])), F32(v - F32(kf["y"][idx]))
+            e2 = _fmaf(ex, ex, F32(ey * ey))
+            lim = 5.99
+            if ur[idx] >= 0:
+                er = F32(r - F32(ur[idx]))
+                e2 = _fmaf(er, er, e2)
+                lim = 7.8
+            if float(F32(e2 * F32(inv_sigma2[kl]))) > lim:
+                continue
+            d = py_distance(desc_mp[i], df[idx])
+            if d < best:
+                best, bidx = d, idx
+        bd[i] = best
+        if best <= TH_LOW:
+            bi[i] = bidx
+    return np.array(bi, np.int32), np.array(bd, np.int32)

@@ -318,3 +318,39 @@ def test_keyframe_projection_overload_on_gpu(ex):
                                                  sf, bounds, 10.0, 64, True)
         assert nm[p] == pn and np.array_equal(asg[p, :len(a["kc"])], pasg), "case %d" % p
     assert int(nm.sum()) > 100
+
+
+@pytest.mark.parametrize("th,stereo", [(3.0, True), (2.5, False), (4.0, True)])
+def test_fuse_search_equals_oracle(ex, th, stereo):
+    """sdorb_fuse_search_batch = the keypoint search of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:535-586):
+    ragged batch of keyframes incl. empty ones / no map points, duplicate descriptors, reprojection errors on the chi-square
+    limits, descriptor distances on both sides of TH_LOW."""
+    sizes = [(600, 500, 0.0), (500, 700, 0.0), (300, 200, 0.0), (0, 50, 0.0), (200, 0, 0.0), (700, 900, 0.3), (1, 1, 0.0)]
+    frames = []
+    for s, (nf, nmp, dup) in enumerate(sizes):
+        _, _, kf, df = sc.frame_pair(s + 140, 10, nf, dup=dup, level0=0.3)
+        proj, lvl, fl, ur = sc.fuse_inputs(s, kf, nmp, stereo=stereo)
+        frames.append((proj, lvl, fl, sc.fuse_descriptors(s, df, nf, nmp), kf, df, ur))
+    cap, capmp = 704, 912
+    gp = sc.grid_params()
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    inv = (np.float32(1) / (sf * sf)).astype(np.float32)
+    col = lambda j, c, dt, tail=(): _slab([f[j] for f in frames], c, dt, tail)
+    kf = col(4, cap, api.KP_DTYPE)
+    nmp = np.array([len(f[0]) for f in frames], np.int32)
+    nf = np.array([len(f[4]) for f in frames], np.int32)
+    cs, idx = ex.assign_grid_batch(kf, nf, *gp)
+    bi, bd = ex.fuse_search_batch(col(0, capmp, np.float32, (3,)), col(1, capmp, np.int32), col(2, capmp, np.uint8),
+                                  col(3, capmp, np.uint8, (32,)), nmp, kf, col(5, cap, np.uint8, (32,)), col(6, cap, np.float32),
+                                  (cs, idx) + tuple(gp), sf, inv, th)
+    fused = rejected = 0
+    for p, f in enumerate(frames):
+        ocs, oidx = orc.assign_grid(f[4], *gp)
+        obi, obd = orc.fuse_search(f[0], f[1], f[2], f[3], f[4], f[5], f[6], (ocs, oidx) + tuple(gp), sf, inv, th)
+        n = len(f[0])
+        assert np.array_equal(bi[p, :n], obi), "keyframe %d: best_idx" % p
+        assert np.array_equal(bd[p, :n], obd), "keyframe %d: best_dist" % p
+        assert (bi[p, n:] == -1).all() and (bd[p, n:] == 256).all()
+        fused += int((obi >= 0).sum())
+        rejected += int(((obd > 50) & (obd < 256)).sum())
+    assert fused > 500 and rejected > 50

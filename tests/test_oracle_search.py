@@ -220,3 +220,78 @@ def test_keyframe_projection_overload_maps_onto_frame_frame_form(seed, nk, nc, t
     assert n == pn and np.array_equal(asg, pasg)
     if seed == 0:
         assert n > 100
+
+
+# ------------------------------------------------------------------ Fuse: the keypoint search (src/ORBmatcher.cc:535-586)
+_VERBATIM_FUSE_E2 = r"""
+extern "C" int gate(float u, float v, float ur, float kpx, float kpy, float kpr, float inv, int stereo) {
+  if (stereo) {
+    const float ex = u-kpx;
+    const float ey = v-kpy;
+    const float er = ur-kpr;
+    const float e2 = ex*ex+ey*ey+er*er;
+    if (e2*inv>7.8) return 0;
+  } else {
+    const float ex = u-kpx;
+    const float ey = v-kpy;
+    const float e2 = ex*ex+ey*ey;
+    if (e2*inv>5.99) return 0;
+  }
+  return 1;
+}
+"""
+
+
+def test_fuse_e2_matches_reference_flags():
+    """The chi-square gate of Fuse (src/ORBmatcher.cc:560-580) compiled verbatim with the reference's flags (-O3 -march=native,
+    CMakeLists.txt:40) against the oracle's frozen contraction, on single-keypoint frames with errors around both limits."""
+    import ctypes
+    import subprocess
+    import tempfile
+    if " fma" not in open("/proc/cpuinfo").read():
+        pytest.skip("host CPU has no FMA: the reference build would not contract here")
+    with tempfile.TemporaryDirectory() as d:
+        src, so = os.path.join(d, "v.cc"), os.path.join(d, "v.so")
+        open(src, "w").write(_VERBATIM_FUSE_E2)
+        subprocess.check_call(["g++", "-O3", "-march=native", "-std=c++11", "-shared", "-fPIC", "-o", so, src])
+        lib = ctypes.CDLL(so)
+        lib.gate.argtypes = [ctypes.c_float] * 7 + [ctypes.c_int]
+        rng = np.random.default_rng(21)
+        sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+        inv = (np.float32(1) / (sf * sf)).astype(np.float32)
+        gp = sc.grid_params()
+        kf = np.zeros(1, orc.KP_DTYPE)
+        desc = np.zeros((1, 32), np.uint8)
+        n_pass = 0
+        for t in range(4000):
+            lvl = int(rng.integers(0, 8))
+            stereo = bool(t & 1)
+            lim = (7.8 if stereo else 5.99) / float(inv[lvl])
+            rad = np.sqrt(lim * rng.uniform(0.9, 1.1))  # |e| around the limit
+            dirn = rng.normal(size=3 if stereo else 2)
+            e = dirn / np.linalg.norm(dirn) * rad
+            kf["x"], kf["y"], kf["octave"] = np.float32(rng.uniform(100, 500)), np.float32(rng.uniform(100, 400)), lvl
+            kpr = np.float32(kf["x"][0] - 12.5) if stereo else np.float32(-1)
+            u, v = np.float32(kf["x"][0] + e[0]), np.float32(kf["y"][0] + e[1])
+            ur = np.float32(kpr + e[2]) if stereo else np.float32(0)
+            ref = lib.gate(float(u), float(v), float(ur), float(kf["x"][0]), float(kf["y"][0]), float(kpr), float(inv[lvl]), int(stereo))
+            bi, bd = orc.fuse_search(np.array([[u, v, ur]], np.float32), [lvl], [1], desc, kf, desc, [kpr], _orc_grid(kf, gp), sf, inv, 30.0)
+            assert (bd[0] == 0) == bool(ref) and (bi[0] == 0) == bool(ref)
+            n_pass += ref
+        assert 1000 < n_pass < 3000
+
+
+@pytest.mark.parametrize("seed,nf,nmp,th,stereo,dup", [(0, 600, 500, 3.0, True, 0.0), (1, 500, 700, 2.5, False, 0.0), (2, 0, 50, 3.0, True, 0.0),
+                                                       (3, 200, 0, 3.0, True, 0.0), (4, 700, 900, 4.0, True, 0.3), (5, 1, 1, 3.0, False, 0.0)])
+def test_fuse_search_equals_restatement(seed, nf, nmp, th, stereo, dup):
+    _, _, kf, df = sc.frame_pair(seed + 140, 10, nf, dup=dup, level0=0.3)
+    proj, lvl, fl, ur = sc.fuse_inputs(seed, kf, nmp, stereo=stereo)
+    dmp = sc.fuse_descriptors(seed, df, nf, nmp)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    inv = (np.float32(1) / (sf * sf)).astype(np.float32)
+    gp = sc.grid_params()
+    bi, bd = orc.fuse_search(proj, lvl, fl, dmp, kf, df, ur, _orc_grid(kf, gp), sf, inv, th)
+    pbi, pbd = sc.py_fuse_search(proj, lvl, fl, dmp, kf, df, ur, gp, sf, inv, th)
+    assert np.array_equal(bi, pbi) and np.array_equal(bd, pbd)
+    if seed == 0:
+        assert (bi >= 0).sum() > 100 and ((bd > 50) & (bd < 256)).sum() > 20
