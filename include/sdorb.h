@@ -270,6 +270,13 @@ typedef struct {
   const float* scale_factors; /* host pointer, nlevels entries */
   int nlevels;
   float th, nnratio;
+  /* 1: the loop-closing overload ORBmatcher::SearchByProjection(KeyFrame* pKF, Scw, vpPoints, vpMatched, th)
+   * (src/ORBmatcher.cc:146-254) from the projection on (the Sim3 algebra :153-209 stays with the caller): radius
+   * th * mvScaleFactors[level] (th = the int of :146 as a float), candidates from KeyFrame::GetFeaturesInArea (src/KeyFrame.cc:529-565)
+   * with the level window :233-236, single best <= TH_LOW, no ratio test, no mvuRight test; occupied = vpMatched[idx] != NULL on
+   * entry and every match occupies its keypoint (:246); flags bit 0 = !isBad() && not in spAlreadyFound && passed :179-209.
+   * assigned[idx] = index of the point written to vpMatched[idx].  view_cos, u_right and nnratio are not read (may be NULL). */
+  int sim3_form;
 } sdorb_map_point_search;
 SDORB_API int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search* q, int nframes, int capacity_mp, int capacity,
                                             int32_t* assigned, int32_t* nmatches, int mem, void* stream);
@@ -287,8 +294,10 @@ SDORB_API int sdorb_search_by_points_batch(sdorb_handle* h, const sdorb_keypoint
  * keyframes: for every map point that passed the checks of :489-531 (flags bit 0; the caller does the pose algebra) the most
  * similar keypoint inside the radius th * mvScaleFactors[level] whose level is level-1 or level and whose reprojection error
  * passes the chi-square test (:560-580); proj = (u, v, ur), level = PredictScale(...).  best_idx [nframes][capacity_mp] = that
- * keypoint if its distance is <= TH_LOW, else -1; best_dist the distance (256 = no candidate).  Replacing / adding the
- * observation (:588-606) stays with the caller.  scale_factors / inv_level_sigma2: host pointers, nlevels entries. */
+ * keypoint if its distance is <= th_dist (TH_LOW = 50 in the reference), else -1; best_dist the distance (256 = no candidate).
+ * Replacing / adding the observation (:588-606) stays with the caller.  scale_factors / inv_level_sigma2: host pointers, nlevels
+ * entries.  check_reprojection = 0 is the search of the Sim3 overload Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (:682-708, also
+ * TH_LOW): no chi-square test; u_right, inv_level_sigma2 and proj[2] are then not read (the pointers may be NULL). */
 typedef struct {
   const float* proj;       /* [nframes][capacity_mp][3] */
   const int32_t* level;    /* [nframes][capacity_mp] */
@@ -303,9 +312,22 @@ typedef struct {
   const float* inv_level_sigma2;
   int nlevels;
   float th;
+  int check_reprojection;
+  int th_dist;
 } sdorb_fuse_search;
 SDORB_API int sdorb_fuse_search_batch(sdorb_handle* h, const sdorb_fuse_search* q, int nframes, int capacity_mp, int capacity,
                                       int32_t* best_idx, int32_t* best_dist, int mem, void* stream);
+
+/* ORBmatcher::SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th) (src/ORBmatcher.cc:734-944) from the projections on, batched
+ * over keyframe pairs.  q12: the map points of KF1 (entry i1 belongs to keypoint i1: capacity_mp == capacity, n_mp = N1; flags bit
+ * 0 = pMP && !vbAlreadyMatched1[i1] && !isBad() && passed :786-808; desc_mp = pMP->GetDescriptor()) projected into KF2, whose
+ * keypoints / descriptors / grid / scale factors the struct carries; q21 the reverse direction (:848-925).  Both searches run without
+ * the reprojection gate (check_reprojection must be 0) against TH_HIGH (th_dist is ignored).  match1 / match2 [npairs][capacity] =
+ * vnMatch1 / vnMatch2; matches12[i1] = idx2 whose map point the agreement check (:927-941) puts into vpMatches12[i1], else -1;
+ * nfound [npairs] the return values. */
+SDORB_API int sdorb_search_by_sim3_batch(sdorb_handle* h, const sdorb_fuse_search* q12, const sdorb_fuse_search* q21, int npairs,
+                                         int capacity, int32_t* match1, int32_t* match2, int32_t* matches12, int32_t* nfound, int mem,
+                                         void* stream);
 
 /* ORBmatcher::SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs) (src/ORBmatcher.cc:359-462, with CheckDistEpipolarLine
  * :128-144) from the epipole on: the pose algebra of :361-368 stays with the caller, which passes per pair F12 (row-major

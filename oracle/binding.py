@@ -131,8 +131,13 @@ def lib(path=None):
         L.orc_search_map_points.restype = i
         L.orc_search_by_points.argtypes = [vp, vp, vp, i, vp, vp, vp, i, f, i, vp]
         L.orc_search_by_points.restype = i
-        L.orc_fuse_search.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, C.POINTER(FrameGrid), vp, vp, f, vp, vp]
+        L.orc_fuse_search.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, C.POINTER(FrameGrid), vp, vp, f, i, i, vp, vp]
         L.orc_fuse_search.restype = None
+        L.orc_search_by_sim3.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, C.POINTER(FrameGrid), vp, vp, C.POINTER(FrameGrid),
+                                         vp, vp, f, vp, vp, vp]
+        L.orc_search_by_sim3.restype = i
+        L.orc_search_by_projection_sim3.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, i, C.POINTER(FrameGrid), vp, i, vp]
+        L.orc_search_by_projection_sim3.restype = i
         L.orc_check_dist_epipolar_line.argtypes = [f, f, f, f, vp, f]
         L.orc_check_dist_epipolar_line.restype = i
         L.orc_search_for_triangulation.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, f, f, vp, vp, i, vp]
@@ -481,13 +486,50 @@ def search_by_points(kps1_un, desc1, valid1, kps2_un, desc2, valid2, nnratio=0.7
     return n, m12[:len(k1)]
 
 
-def fuse_search(proj, level, flags, desc_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th):
-    """The keypoint search of ORBmatcher::Fuse: (best_idx, best_dist) per map point."""
+def fuse_search(proj, level, flags, desc_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th, check_reprojection=True,
+                th_dist=50):
+    """The keypoint search of ORBmatcher::Fuse (check_reprojection=False: its Sim3 overload; with th_dist=100 one direction of
+    SearchBySim3): (best_idx, best_dist) per map point."""
     pr = np.ascontiguousarray(proj, np.float32).reshape(-1, 3)
     lv, fl, dm = np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.uint8), np.ascontiguousarray(desc_mp, np.uint8)
-    k, d, ur = np.ascontiguousarray(kps_un, KP_DTYPE), np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(u_right, np.float32)
-    sf, is2 = np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(inv_level_sigma2, np.float32)
+    k, d = np.ascontiguousarray(kps_un, KP_DTYPE), np.ascontiguousarray(desc, np.uint8)
+    ur = np.ascontiguousarray(u_right, np.float32) if u_right is not None else None
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    is2 = np.ascontiguousarray(inv_level_sigma2, np.float32) if inv_level_sigma2 is not None else None
+    assert not check_reprojection or (ur is not None and is2 is not None)
     g, keep = _grid(*grid)
     bi, bd = np.full(max(len(pr), 1), -1, np.int32), np.full(max(len(pr), 1), 256, np.int32)
-    lib().orc_fuse_search(_p(pr), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(ur), C.byref(g), _p(sf), _p(is2), th, _p(bi), _p(bd))
+    lib().orc_fuse_search(_p(pr), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(ur) if ur is not None else None, C.byref(g), _p(sf),
+                          _p(is2) if is2 is not None else None, th, int(check_reprojection), int(th_dist), _p(bi), _p(bd))
     return bi[:len(pr)], bd[:len(pr)]
+
+
+def search_by_sim3(side1, side2, scale_factors, th):
+    """ORBmatcher::SearchBySim3 from the projections on.  side = (proj, level, flags, desc_mp, kps_un, desc, grid): the map points of
+    that keyframe (entry i belongs to keypoint i) projected into the other one, and the keyframe's own keypoints / descriptors /
+    grid.  Returns (nFound, matches12, vnMatch1, vnMatch2)."""
+    def prep(side):
+        pr, lv, fl, dm, k, d, grid = side
+        g, keep = _grid(*grid)
+        return [np.ascontiguousarray(pr, np.float32).reshape(-1, 3), np.ascontiguousarray(lv, np.int32), np.ascontiguousarray(fl, np.uint8),
+                np.ascontiguousarray(dm, np.uint8), np.ascontiguousarray(k, KP_DTYPE), np.ascontiguousarray(d, np.uint8), g, keep]
+    a, b = prep(side1), prep(side2)
+    n1, n2 = len(a[4]), len(b[4])
+    assert len(a[0]) == n1 and len(b[0]) == n2
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    m1, m2, m12 = np.full(max(n1, 1), -1, np.int32), np.full(max(n2, 1), -1, np.int32), np.full(max(n1, 1), -1, np.int32)
+    n = lib().orc_search_by_sim3(_p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]), n1, _p(b[0]), _p(b[1]), _p(b[2]), _p(b[3]), n2,
+                                 _p(a[4]), _p(a[5]), C.byref(a[6]), _p(b[4]), _p(b[5]), C.byref(b[6]), _p(sf), _p(sf), th, _p(m1), _p(m2), _p(m12))
+    return n, m12[:n1], m1[:n1], m2[:n2]
+
+
+def search_by_projection_sim3(proj, level, flags, desc_mp, kps_un, desc, matched, grid, scale_factors, th):
+    """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) from the projection on: (nmatches, assigned)."""
+    pr = np.ascontiguousarray(proj, np.float32).reshape(-1, 3)
+    lv, fl, dm = np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.uint8), np.ascontiguousarray(desc_mp, np.uint8)
+    k, d, mt = np.ascontiguousarray(kps_un, KP_DTYPE), np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(matched, np.uint8)
+    sf = np.ascontiguousarray(scale_factors, np.float32)
+    g, keep = _grid(*grid)
+    asg = np.full(max(len(k), 1), -1, np.int32)
+    n = lib().orc_search_by_projection_sim3(_p(pr), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(mt), len(k), C.byref(g), _p(sf), int(th), _p(asg))
+    return n, asg[:len(k)]

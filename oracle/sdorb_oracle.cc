@@ -1428,11 +1428,15 @@ int orc_search_by_points(const orc_keypoint* k1, const uint8_t* d1s, const uint8
 }
 // The keypoint search inside ORBmatcher::Fuse(KeyFrame*, const vector<MapPoint*>&, th), src/ORBmatcher.cc:535-586: per map point
 // that passed the checks of :489-531 (flags bit 0) the most similar keypoint within the radius, subject to the level window and
-// the chi-square test of the reprojection error; best_idx = -1 where none reaches TH_LOW.  The map surgery of :588-606 stays with the
+// the chi-square test of the reprojection error; best_idx = -1 where none reaches thDist.  The map surgery of :588-606 stays with the
 // caller.  e2 as the reference build contracts it: fma(er, er, fma(ex, ex, ey*ey)) (checked against the compiled expression).
+// bCheckReprojection = 0, thDist = TH_LOW is the search of the Sim3 overload Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)
+// (:682-708; its bestDist starts at INT_MAX, which only differs for "no candidate": reported as 256 here too);
+// bCheckReprojection = 0, thDist = TH_HIGH is either direction of SearchBySim3 (:812-845, :890-923).
 void orc_fuse_search(const float* proj /* n x 3: u, v, ur */, const int32_t* level, const uint8_t* flags, const uint8_t* descMP, int nMP,
                      const orc_keypoint* kKF, const uint8_t* descKF, const float* uRight, const orc_frame_grid* grid,
-                     const float* mvScaleFactors, const float* mvInvLevelSigma2, float th, int32_t* best_idx, int32_t* best_dist) {
+                     const float* mvScaleFactors, const float* mvInvLevelSigma2, float th, int bCheckReprojection, int thDist,
+                     int32_t* best_idx, int32_t* best_dist) {
   for (int i = 0; i < nMP; i++) {
     best_idx[i] = -1;
     best_dist[i] = 256;
@@ -1441,19 +1445,21 @@ void orc_fuse_search(const float* proj /* n x 3: u, v, ur */, const int32_t* lev
     const int nPredictedLevel = level[i];
     const float radius = th * mvScaleFactors[nPredictedLevel];
     const std::vector<int> vIndices = features_in_area(kKF, *grid, u, v, radius, -1, -1);  // KeyFrame::GetFeaturesInArea: no level filter
-    int bestDist = 256, bestIdx = -1;
+    int bestDist = INT_MAX, bestIdx = -1;
     for (int idx : vIndices) {
       const orc_keypoint& kp = kKF[idx];
       const int kpLevel = kp.octave;
       if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
-      if (uRight[idx] >= 0) {
-        const float ex = u - kp.x, ey = v - kp.y, er = ur - uRight[idx];
-        const float e2 = fmaf(er, er, fmaf(ex, ex, ey * ey));
-        if (e2 * mvInvLevelSigma2[kpLevel] > 7.8) continue;
-      } else {
-        const float ex = u - kp.x, ey = v - kp.y;
-        const float e2 = fmaf(ex, ex, ey * ey);
-        if (e2 * mvInvLevelSigma2[kpLevel] > 5.99) continue;
+      if (bCheckReprojection) {
+        if (uRight[idx] >= 0) {
+          const float ex = u - kp.x, ey = v - kp.y, er = ur - uRight[idx];
+          const float e2 = fmaf(er, er, fmaf(ex, ex, ey * ey));
+          if (e2 * mvInvLevelSigma2[kpLevel] > 7.8) continue;
+        } else {
+          const float ex = u - kp.x, ey = v - kp.y;
+          const float e2 = fmaf(ex, ex, ey * ey);
+          if (e2 * mvInvLevelSigma2[kpLevel] > 5.99) continue;
+        }
       }
       const int dist = descriptor_distance(descMP + (size_t)i * 32, descKF + (size_t)idx * 32);
       if (dist < bestDist) {
@@ -1461,9 +1467,70 @@ void orc_fuse_search(const float* proj /* n x 3: u, v, ur */, const int32_t* lev
         bestIdx = idx;
       }
     }
-    best_dist[i] = bestDist;
-    if (bestDist <= kThLow) best_idx[i] = bestIdx;
+    if (bestIdx >= 0) best_dist[i] = bestDist;
+    if (bestDist <= thDist) best_idx[i] = bestIdx;
   }
+}
+// ORBmatcher::SearchBySim3, src/ORBmatcher.cc:734-944, from the projections on: map point i1 of KF1 (flags1 bit 0: it exists, is
+// not bad, is not already matched and passed :786-808) is searched among the keypoints of KF2 and vice versa (both TH_HIGH, no
+// reprojection gate), then the agreement check :927-941.  vnMatch1 / vnMatch2 as in the reference; matches12[i1] = idx2 of the
+// map point the call puts into vpMatches12[i1], else -1; returns nFound.
+int orc_search_by_sim3(const float* proj1, const int32_t* level1, const uint8_t* flags1, const uint8_t* descMP1, int N1,
+                       const float* proj2, const int32_t* level2, const uint8_t* flags2, const uint8_t* descMP2, int N2,
+                       const orc_keypoint* k1, const uint8_t* d1, const orc_frame_grid* grid1, const orc_keypoint* k2, const uint8_t* d2,
+                       const orc_frame_grid* grid2, const float* mvScaleFactors1, const float* mvScaleFactors2, float th,
+                       int32_t* vnMatch1, int32_t* vnMatch2, int32_t* matches12) {
+  std::vector<int32_t> dist((size_t)std::max(N1, N2) + 1);
+  orc_fuse_search(proj1, level1, flags1, descMP1, N1, k2, d2, nullptr, grid2, mvScaleFactors2, nullptr, th, 0, kThHigh, vnMatch1, dist.data());
+  orc_fuse_search(proj2, level2, flags2, descMP2, N2, k1, d1, nullptr, grid1, mvScaleFactors1, nullptr, th, 0, kThHigh, vnMatch2, dist.data());
+  int nFound = 0;
+  for (int i1 = 0; i1 < N1; i1++) {
+    matches12[i1] = -1;
+    const int idx2 = vnMatch1[i1];
+    if (idx2 >= 0) {
+      const int idx1 = vnMatch2[idx2];
+      if (idx1 == i1) {
+        matches12[i1] = idx2;
+        nFound++;
+      }
+    }
+  }
+  return nFound;
+}
+// ORBmatcher::SearchByProjection(KeyFrame* pKF, Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:146-254 (loop closing), from the
+// projection on: flags bit 0 = the point is not bad, not in spAlreadyFound and passed :179-209.  vpMatched_in[idx] != 0: the
+// keypoint holds a map point on entry; every match made occupies its keypoint for the later points (:246).  assigned[idx] = index
+// of the point the call writes into vpMatched[idx], else -1; returns nmatches.
+int orc_search_by_projection_sim3(const float* proj /* n x 3, [2] unused */, const int32_t* level, const uint8_t* flags, const uint8_t* descMP,
+                                  int nMP, const orc_keypoint* kKF, const uint8_t* descKF, const uint8_t* vpMatched_in, int nKF,
+                                  const orc_frame_grid* grid, const float* mvScaleFactors, int th, int32_t* assigned) {
+  int nmatches = 0;
+  std::fill(assigned, assigned + nKF, -1);
+  std::vector<uint8_t> vpMatched(vpMatched_in, vpMatched_in + nKF);
+  for (int iMP = 0; iMP < nMP; iMP++) {
+    if (!(flags[iMP] & 1)) continue;
+    const int nPredictedLevel = level[iMP];
+    const float radius = th * mvScaleFactors[nPredictedLevel];
+    const std::vector<int> vIndices = features_in_area(kKF, *grid, proj[3 * iMP], proj[3 * iMP + 1], radius, -1, -1);
+    if (vIndices.empty()) continue;
+    int bestDist = 256, bestIdx = -1;
+    for (int idx : vIndices) {
+      if (vpMatched[idx]) continue;
+      const int kpLevel = kKF[idx].octave;
+      if (kpLevel < nPredictedLevel - 1 || kpLevel > nPredictedLevel) continue;
+      const int dist = descriptor_distance(descMP + (size_t)iMP * 32, descKF + (size_t)idx * 32);
+      if (dist < bestDist) {
+        bestDist = dist;
+        bestIdx = idx;
+      }
+    }
+    if (bestDist <= kThLow) {
+      vpMatched[bestIdx] = 1;
+      assigned[bestIdx] = iMP;
+      nmatches++;
+    }
+  }
+  return nmatches;
 }
 // ORBmatcher::CheckDistEpipolarLine, src/ORBmatcher.cc:128-144.  F12 is an Eigen::Matrix3d, so a, b, c are evaluated in double
 // and rounded to float; the reference's -O3 -march=native contracts  p*q + r*s  into  fma(p, q, r*s)  (first product fused,

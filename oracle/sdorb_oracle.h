@@ -189,10 +189,22 @@ int orc_search_map_points(const float* proj, const float* view_cos, const int32_
  * entries (index into the second keyframe or -1); returns nmatches. */
 int orc_search_by_points(const orc_keypoint* kps1_un, const uint8_t* desc1, const uint8_t* valid1, int n1, const orc_keypoint* kps2_un,
                          const uint8_t* desc2, const uint8_t* valid2, int n2, float nnratio, int check_orientation, int32_t* matches12);
-/* The keypoint search of ORBmatcher::Fuse (src/ORBmatcher.cc:535-586); see sdorb_oracle.cc. */
+/* The keypoint search of ORBmatcher::Fuse (src/ORBmatcher.cc:535-586; without the reprojection gate: the Sim3 overload :682-708 and
+ * either direction of SearchBySim3); see sdorb_oracle.cc. */
 void orc_fuse_search(const float* proj, const int32_t* level, const uint8_t* flags, const uint8_t* desc_mp, int n_mp,
                      const orc_keypoint* kps_un, const uint8_t* desc, const float* u_right, const orc_frame_grid* grid,
-                     const float* scale_factors, const float* inv_level_sigma2, float th, int32_t* best_idx, int32_t* best_dist);
+                     const float* scale_factors, const float* inv_level_sigma2, float th, int check_reprojection, int th_dist,
+                     int32_t* best_idx, int32_t* best_dist);
+/* ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:734-944) from the projections on; returns nFound. */
+int orc_search_by_sim3(const float* proj1, const int32_t* level1, const uint8_t* flags1, const uint8_t* desc_mp1, int n1,
+                       const float* proj2, const int32_t* level2, const uint8_t* flags2, const uint8_t* desc_mp2, int n2,
+                       const orc_keypoint* kps1_un, const uint8_t* desc1, const orc_frame_grid* grid1, const orc_keypoint* kps2_un,
+                       const uint8_t* desc2, const orc_frame_grid* grid2, const float* scale_factors1, const float* scale_factors2,
+                       float th, int32_t* match1, int32_t* match2, int32_t* matches12);
+/* ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:146-254) from the projection on. */
+int orc_search_by_projection_sim3(const float* proj, const int32_t* level, const uint8_t* flags, const uint8_t* desc_mp, int n_mp,
+                                  const orc_keypoint* kps_un, const uint8_t* desc, const uint8_t* matched_in, int n_kf,
+                                  const orc_frame_grid* grid, const float* scale_factors, int th, int32_t* assigned);
 /* ORBmatcher::CheckDistEpipolarLine (src/ORBmatcher.cc:128-144); F12 row-major (F12(i, j) = F12[3 * i + j]), sigma2 =
  * pKF2->mvLevelSigma2[kp2.octave]. */
 int orc_check_dist_epipolar_line(float x1, float y1, float x2, float y2, const double* F12, float sigma2);

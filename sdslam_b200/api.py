@@ -58,13 +58,14 @@ class _MapPointSearch(C.Structure):
     _fields_ = [("proj", C.c_void_p), ("view_cos", C.c_void_p), ("level", C.c_void_p), ("flags", C.c_void_p), ("desc_mp", C.c_void_p),
                 ("n_mp", C.c_void_p), ("kps_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("occupied", C.c_void_p),
                 ("n_frame", C.c_void_p), ("grid", _FrameGrid), ("scale_factors", C.c_void_p), ("nlevels", C.c_int), ("th", C.c_float),
-                ("nnratio", C.c_float)]
+                ("nnratio", C.c_float), ("sim3_form", C.c_int)]
 
 
 class _FuseSearch(C.Structure):
     _fields_ = [("proj", C.c_void_p), ("level", C.c_void_p), ("flags", C.c_void_p), ("desc_mp", C.c_void_p), ("n_mp", C.c_void_p),
                 ("kps_un", C.c_void_p), ("desc", C.c_void_p), ("u_right", C.c_void_p), ("grid", _FrameGrid),
-                ("scale_factors", C.c_void_p), ("inv_level_sigma2", C.c_void_p), ("nlevels", C.c_int), ("th", C.c_float)]
+                ("scale_factors", C.c_void_p), ("inv_level_sigma2", C.c_void_p), ("nlevels", C.c_int), ("th", C.c_float),
+                ("check_reprojection", C.c_int), ("th_dist", C.c_int)]
 
 
 class _TriangulationSearch(C.Structure):
@@ -111,6 +112,7 @@ def lib():
     L.sdorb_search_map_points_batch.argtypes = [vp, C.POINTER(_MapPointSearch), i, i, i, vp, vp, i, vp]
     L.sdorb_search_by_points_batch.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, i, i, f, i, vp, vp, i, vp]
     L.sdorb_fuse_search_batch.argtypes = [vp, C.POINTER(_FuseSearch), i, i, i, vp, vp, i, vp]
+    L.sdorb_search_by_sim3_batch.argtypes = [vp, C.POINTER(_FuseSearch), C.POINTER(_FuseSearch), i, i, vp, vp, vp, vp, i, vp]
     L.sdorb_search_for_triangulation_batch.argtypes = [vp, C.POINTER(_TriangulationSearch), i, i, vp, vp, i, vp]
     L.sdorb_stereo_from_rgbd_batch.argtypes = [vp, vp, vp, vp, i, i, vp, i, i, sz, sz, f, vp, vp, i, vp]
     L.sdorb_fill_border_reflect101.argtypes = [vp, i, i, sz, i]
@@ -437,7 +439,25 @@ class ORBextractor:
                 np.ascontiguousarray(scale_factors, np.float32)]
         F, capmp, cap = keep[1].shape[0], keep[1].shape[1], keep[6].shape[1]
         q = _MapPointSearch(*[_ptr(k) for k in keep[:11]], _FrameGrid(_ptr(keep[11]), _ptr(keep[12]), *[float(v) for v in grid[2:6]]),
-                            _ptr(keep[13]), len(keep[13]), float(th), float(nnratio))
+                            _ptr(keep[13]), len(keep[13]), float(th), float(nnratio), 0)
+        asg = np.zeros((F, cap), np.int32)
+        nm = np.zeros(F, np.int32)
+        self._check(lib().sdorb_search_map_points_batch(self._h, C.byref(q), F, capmp, cap, _ptr(asg), _ptr(nm), MEM_HOST, None))
+        return nm, asg
+
+    def search_by_projection_sim3_batch(self, proj, level, flags, desc_mp, n_mp, kps_un, desc, matched, n_kf, grid, scale_factors, th):
+        """ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (loop closing) for a batch of keyframes (host
+        arrays; sdorb_map_point_search::sim3_form): returns (nmatches[F], assigned[F, cap])."""
+        keep = [np.ascontiguousarray(proj, np.float32), None, np.ascontiguousarray(level, np.int32),
+                np.ascontiguousarray(flags, np.uint8), np.ascontiguousarray(desc_mp, np.uint8), np.ascontiguousarray(n_mp, np.int32),
+                np.ascontiguousarray(kps_un), np.ascontiguousarray(desc, np.uint8), None,
+                np.ascontiguousarray(matched, np.uint8), np.ascontiguousarray(n_kf, np.int32),
+                np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32),
+                np.ascontiguousarray(scale_factors, np.float32)]
+        F, capmp, cap = keep[2].shape[0], keep[2].shape[1], keep[6].shape[1]
+        q = _MapPointSearch(*[_ptr(k) if k is not None else None for k in keep[:11]],
+                            _FrameGrid(_ptr(keep[11]), _ptr(keep[12]), *[float(v) for v in grid[2:6]]),
+                            _ptr(keep[13]), len(keep[13]), float(int(th)), 0.0, 1)
         asg = np.zeros((F, cap), np.int32)
         nm = np.zeros(F, np.int32)
         self._check(lib().sdorb_search_map_points_batch(self._h, C.byref(q), F, capmp, cap, _ptr(asg), _ptr(nm), MEM_HOST, None))
@@ -457,19 +477,44 @@ class ORBextractor:
                                                         MEM_HOST, None))
         return nm, m12
 
-    def fuse_search_batch(self, proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th):
-        """The keypoint search of ORBmatcher::Fuse for a batch of keyframes (host arrays): (best_idx[F, cap_mp], best_dist[F, cap_mp])."""
+    @staticmethod
+    def _fuse_query(proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th, check, th_dist):
+        opt = lambda a: np.ascontiguousarray(a, np.float32) if a is not None else None
         keep = [np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.uint8),
                 np.ascontiguousarray(desc_mp, np.uint8), np.ascontiguousarray(n_mp, np.int32), np.ascontiguousarray(kps_un),
-                np.ascontiguousarray(desc, np.uint8), np.ascontiguousarray(u_right, np.float32),
+                np.ascontiguousarray(desc, np.uint8), opt(u_right),
                 np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32),
-                np.ascontiguousarray(scale_factors, np.float32), np.ascontiguousarray(inv_level_sigma2, np.float32)]
+                np.ascontiguousarray(scale_factors, np.float32), opt(inv_level_sigma2)]
+        ptr = lambda a: _ptr(a) if a is not None else None
+        q = _FuseSearch(*[ptr(k) for k in keep[:8]], _FrameGrid(_ptr(keep[8]), _ptr(keep[9]), *[float(v) for v in grid[2:6]]),
+                        _ptr(keep[10]), ptr(keep[11]), len(keep[10]), float(th), int(check), int(th_dist))
+        return q, keep
+
+    def fuse_search_batch(self, proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th,
+                          check_reprojection=True, th_dist=50):
+        """The keypoint search of ORBmatcher::Fuse for a batch of keyframes (host arrays): (best_idx[F, cap_mp], best_dist[F, cap_mp]).
+        check_reprojection=False: the search of the Sim3 overload (u_right / inv_level_sigma2 may be None)."""
+        q, keep = self._fuse_query(proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th,
+                                   check_reprojection, th_dist)
         F, capmp, cap = keep[1].shape[0], keep[1].shape[1], keep[5].shape[1]
-        q = _FuseSearch(*[_ptr(k) for k in keep[:8]], _FrameGrid(_ptr(keep[8]), _ptr(keep[9]), *[float(v) for v in grid[2:6]]),
-                        _ptr(keep[10]), _ptr(keep[11]), len(keep[10]), float(th))
         bi, bd = np.zeros((F, capmp), np.int32), np.zeros((F, capmp), np.int32)
         self._check(lib().sdorb_fuse_search_batch(self._h, C.byref(q), F, capmp, cap, _ptr(bi), _ptr(bd), MEM_HOST, None))
         return bi, bd
+
+    def search_by_sim3_batch(self, side1, side2, scale_factors, th):
+        """ORBmatcher::SearchBySim3 for a batch of keyframe pairs (host arrays).  side = (proj[P, cap, 3], level[P, cap], flags[P, cap],
+        desc_mp[P, cap, 32], n[P], kps_un[P, cap], desc[P, cap, 32], grid) of that keyframe: its map points projected into the other
+        keyframe, and its own keypoints / descriptors / grid.  Returns (nfound[P], matches12[P, cap], match1, match2)."""
+        p1, l1, f1, m1, n1, k1, d1, g1 = side1
+        p2, l2, f2, m2, n2, k2, d2, g2 = side2
+        q12, keep12 = self._fuse_query(p1, l1, f1, m1, n1, k2, d2, None, g2, scale_factors, None, th, 0, 100)
+        q21, keep21 = self._fuse_query(p2, l2, f2, m2, n2, k1, d1, None, g1, scale_factors, None, th, 0, 100)
+        P, cap = keep12[1].shape
+        assert keep21[1].shape == (P, cap) and keep12[5].shape[:2] == (P, cap) and keep21[5].shape[:2] == (P, cap)
+        o1, o2, o12, nf = np.zeros((P, cap), np.int32), np.zeros((P, cap), np.int32), np.zeros((P, cap), np.int32), np.zeros(P, np.int32)
+        self._check(lib().sdorb_search_by_sim3_batch(self._h, C.byref(q12), C.byref(q21), P, cap, _ptr(o1), _ptr(o2), _ptr(o12), _ptr(nf),
+                                                     MEM_HOST, None))
+        return nf, o12, o1, o2
 
     def search_for_triangulation_batch(self, kps1_un, desc1, has_mp1, u_right1, n1, kps2_un, desc2, has_mp2, u_right2, n2, F12, epipole,
                                        scale_factors, level_sigma2, check_orientation=True, matches12=None, nmatches=None,

@@ -119,6 +119,7 @@ struct SearchPointsArgs {  // ORBmatcher::SearchByProjection(Frame&, const vecto
   int32_t* assigned;  // [nframes][capacity]
   int32_t* nmatches;  // [nframes]
   int capacity, capacity_mp, th_high;
+  int sim3_form;  // 1: SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th), src/ORBmatcher.cc:146-254
   float th, nnratio;
   float scale_factors[SDORB_MAX_LEVELS];
 };
@@ -137,12 +138,14 @@ struct FuseSearchArgs {  // the keypoint search of ORBmatcher::Fuse
   const void* kps;  const uint8_t* desc;  const float* u_right;
   SearchGrid grid;
   int32_t* best_idx;   // [nframes][capacity_mp]
-  int32_t* best_dist;  // [nframes][capacity_mp]
-  int capacity, capacity_mp, th_low;
+  int32_t* best_dist;  // [nframes][capacity_mp], may be null
+  int capacity, capacity_mp, th_dist, check_reprojection;
   float th;
   float scale_factors[SDORB_MAX_LEVELS], inv_sigma2[SDORB_MAX_LEVELS];
 };
 void launch_fuse_search(const FuseSearchArgs& a, int nframes, cudaStream_t s);
+void launch_sim3_agreement(const int32_t* match1, const int32_t* match2, const int32_t* n1, int capacity, int32_t* matches12,
+                           int32_t* nfound, int npairs, cudaStream_t s);
 void launch_search_triangulation(const SearchTriArgs& a, int npairs, cudaStream_t s);
 void launch_search_init(const SearchInitArgs& a, int npairs, cudaStream_t s);
 void launch_search_projection(const SearchProjArgs& a, int npairs, cudaStream_t s);

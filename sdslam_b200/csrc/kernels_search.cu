@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(32) search_points_kernel(SearchPointsArgs a) {
   uint8_t* s_occ = reinterpret_cast<uint8_t*>(s_prefix + GRID_COLS + 1 + 1);  // [cap]
   const int nMP = min(a.n_mp[frame], capmp), nF = min(a.n_frame[frame], cap);
   const float* proj = a.proj + (int64_t)frame * capmp * 3;
-  const float* vcos = a.view_cos + (int64_t)frame * capmp;
+  const float* vcos = a.view_cos + (int64_t)frame * capmp;  // not read in the Sim3 form (may be null)
   const int32_t* lvl = a.level + (int64_t)frame * capmp;
   const uint8_t* fl = a.flags + (int64_t)frame * capmp;
   const uint8_t* dMP = a.desc_mp + (int64_t)frame * capmp * 32;
@@ -414,8 +414,11 @@ __global__ void __launch_bounds__(32) search_points_kernel(SearchPointsArgs a) {
     const int flags = fl[i];
     if (!(flags & 1)) continue;
     const int level = lvl[i];
-    float r = (double)vcos[i] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos, :121-126
-    if (factor) r = __fmul_rn(r, a.th);
+    float r = a.th;  // the Sim3 form, :213: th * mvScaleFactors[nPredictedLevel]
+    if (!a.sim3_form) {
+      r = (double)vcos[i] > 0.998 ? 2.5f : 4.0f;  // RadiusByViewingCos, :121-126
+      if (factor) r = __fmul_rn(r, a.th);
+    }
     const float radius = __fmul_rn(r, a.scale_factors[min(max(level, 0), SDORB_MAX_LEVELS - 1)]);
     const float x = proj[3 * i], y = proj[3 * i + 1], xr = proj[3 * i + 2];
     int x0, x1, y0, y1;
@@ -435,8 +438,10 @@ __global__ void __launch_bounds__(32) search_points_kernel(SearchPointsArgs a) {
       }
       if (!(fabsf(__fsub_rn(kp.x, x)) < radius && fabsf(__fsub_rn(kp.y, y)) < radius)) continue;
       if (s_occ[i2]) continue;
-      const float r2 = uR[i2];
-      if (r2 > 0.f && fabsf(__fsub_rn(xr, r2)) > radius) continue;
+      if (!a.sim3_form) {
+        const float r2 = uR[i2];
+        if (r2 > 0.f && fabsf(__fsub_rn(xr, r2)) > radius) continue;
+      }
       uint32_t t[8];
       load_desc(dF + (int64_t)i2 * 32, t);
       const uint4 lo = make_uint4(t[0], t[1], t[2], t[3]), hi = make_uint4(t[4], t[5], t[6], t[7]);
@@ -452,10 +457,10 @@ __global__ void __launch_bounds__(32) search_points_kernel(SearchPointsArgs a) {
         const int bestLevel = kF[bestIdx].octave;
         int bestLevel2 = -1;
         if (bestDist2 < 256) bestLevel2 = kF[idx[candidate_slot((int)(m2 & 0xFFFFu), x1 - x0 + 1, s_begin, s_prefix)]].octave;
-        const bool reject = bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nnratio, (float)bestDist2);
+        const bool reject = !a.sim3_form && bestLevel == bestLevel2 && (float)bestDist > __fmul_rn(a.nnratio, (float)bestDist2);
         if (!reject) {
           assigned[bestIdx] = i;
-          s_occ[bestIdx] = (flags & 2) ? 1 : 0;
+          s_occ[bestIdx] = (a.sim3_form || (flags & 2)) ? 1 : 0;  // :246: vpMatched[bestIdx] = pMP
           nmatches++;
         }
       }
@@ -557,11 +562,12 @@ void launch_search_by_points(const SearchByPointsArgs& a, int npairs, cudaStream
 // ---------------------------------------------------------------------------------------- Fuse (the keypoint search)
 // src/ORBmatcher.cc:535-586: every map point is independent here (the map surgery that follows stays with the caller), so a
 // thread takes a map point and walks the window's grid cells in the reference's order; strict < keeps the first minimum.
+// Without the reprojection gate it is the search of the Sim3 overload of Fuse (:682-708) and of both directions of SearchBySim3
+// (:812-845, :890-923; th_dist = TH_HIGH).
 __global__ void __launch_bounds__(128) fuse_search_kernel(FuseSearchArgs a) {
   const int frame = blockIdx.y, i = blockIdx.x * 128 + threadIdx.x, cap = a.capacity, capmp = a.capacity_mp;
   if (i >= capmp) return;
   int32_t* out_idx = a.best_idx + (int64_t)frame * capmp;
-  int32_t* out_dist = a.best_dist + (int64_t)frame * capmp;
   int bestDist = 256, bestIdx = -1;
   const int nMP = min(a.n_mp[frame], capmp);
   if (i < nMP && (a.flags[(int64_t)frame * capmp + i] & 1)) {
@@ -585,17 +591,19 @@ __global__ void __launch_bounds__(128) fuse_search_kernel(FuseSearchArgs a) {
           const KP kp = kF[i2];
           if (!(fabsf(__fsub_rn(kp.x, u)) < radius && fabsf(__fsub_rn(kp.y, v)) < radius)) continue;
           if (kp.octave < level - 1 || kp.octave > level) continue;
-          const float inv = a.inv_sigma2[min(max(kp.octave, 0), SDORB_MAX_LEVELS - 1)];
-          const float ex = __fsub_rn(u, kp.x), ey = __fsub_rn(v, kp.y);
-          float e2 = __fmaf_rn(ex, ex, __fmul_rn(ey, ey));
-          const float r2 = uR[i2];
-          double lim = 5.99;
-          if (r2 >= 0.f) {
-            const float er = __fsub_rn(ur, r2);
-            e2 = __fmaf_rn(er, er, e2);
-            lim = 7.8;
+          if (a.check_reprojection) {
+            const float inv = a.inv_sigma2[min(max(kp.octave, 0), SDORB_MAX_LEVELS - 1)];
+            const float ex = __fsub_rn(u, kp.x), ey = __fsub_rn(v, kp.y);
+            float e2 = __fmaf_rn(ex, ex, __fmul_rn(ey, ey));
+            const float r2 = uR[i2];
+            double lim = 5.99;
+            if (r2 >= 0.f) {
+              const float er = __fsub_rn(ur, r2);
+              e2 = __fmaf_rn(er, er, e2);
+              lim = 7.8;
+            }
+            if ((double)__fmul_rn(e2, inv) > lim) continue;
           }
-          if ((double)__fmul_rn(e2, inv) > lim) continue;
           uint32_t t[8];
           load_desc(dF + (int64_t)i2 * 32, t);
           const int d = hamming256(q, make_uint4(t[0], t[1], t[2], t[3]), make_uint4(t[4], t[5], t[6], t[7]));
@@ -607,12 +615,48 @@ __global__ void __launch_bounds__(128) fuse_search_kernel(FuseSearchArgs a) {
       }
     }
   }
-  out_dist[i] = bestDist;
-  out_idx[i] = bestDist <= a.th_low ? bestIdx : -1;
+  if (a.best_dist) a.best_dist[(int64_t)frame * capmp + i] = bestDist;
+  out_idx[i] = bestDist <= a.th_dist ? bestIdx : -1;
 }
 
 void launch_fuse_search(const FuseSearchArgs& a, int nframes, cudaStream_t s) {
   fuse_search_kernel<<<dim3((a.capacity_mp + 127) / 128, nframes), 128, 0, s>>>(a);
+}
+
+// The agreement check of ORBmatcher::SearchBySim3, src/ORBmatcher.cc:927-941: vpMatches12[i1] takes the map point of idx2 =
+// vnMatch1[i1] when vnMatch2[idx2] == i1.  One CTA per keyframe pair; the count is an integer sum (order-independent).
+__global__ void __launch_bounds__(256) sim3_agreement_kernel(const int32_t* __restrict__ match1, const int32_t* __restrict__ match2,
+                                                             const int32_t* __restrict__ n1, int capacity, int32_t* __restrict__ matches12,
+                                                             int32_t* __restrict__ nfound) {
+  __shared__ int s_found;
+  const int pair = blockIdx.x, N1 = min(n1[pair], capacity);
+  const int32_t* m1 = match1 + (int64_t)pair * capacity;
+  const int32_t* m2 = match2 + (int64_t)pair * capacity;
+  int32_t* m12 = matches12 + (int64_t)pair * capacity;
+  if (threadIdx.x == 0) s_found = 0;
+  __syncthreads();
+  int found = 0;
+  for (int i1 = threadIdx.x; i1 < capacity; i1 += 256) {
+    int out = -1;
+    if (i1 < N1) {
+      const int idx2 = m1[i1];
+      if (idx2 >= 0 && idx2 < capacity && m2[idx2] == i1) {
+        out = idx2;
+        ++found;
+      }
+    }
+    m12[i1] = out;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) found += __shfl_xor_sync(0xffffffffu, found, o);
+  if ((threadIdx.x & 31) == 0 && found) atomicAdd(&s_found, found);
+  __syncthreads();
+  if (threadIdx.x == 0) nfound[pair] = s_found;
+}
+
+void launch_sim3_agreement(const int32_t* match1, const int32_t* match2, const int32_t* n1, int capacity, int32_t* matches12,
+                           int32_t* nfound, int npairs, cudaStream_t s) {
+  sim3_agreement_kernel<<<npairs, 256, 0, s>>>(match1, match2, n1, capacity, matches12, nfound);
 }
 
 // ---------------------------------------------------------------------------------------- SearchForTriangulation

@@ -1016,8 +1016,9 @@ int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search*
                                   int32_t* assigned, int32_t* nmatches, int mem, void* stream) {
   if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
   if (nframes == 0) return SDORB_OK;
-  if (!q || !q->proj || !q->view_cos || !q->level || !q->flags || !q->desc_mp || !q->n_mp || !q->kps_un || !q->desc || !q->u_right ||
-      !q->occupied || !q->n_frame || !q->grid.cell_start || !q->grid.indices || !q->scale_factors || q->nlevels <= 0 ||
+  const bool sim3 = q && q->sim3_form != 0;
+  if (!q || !q->proj || (!sim3 && !q->view_cos) || !q->level || !q->flags || !q->desc_mp || !q->n_mp || !q->kps_un || !q->desc ||
+      (!sim3 && !q->u_right) || !q->occupied || !q->n_frame || !q->grid.cell_start || !q->grid.indices || !q->scale_factors || q->nlevels <= 0 ||
       q->nlevels > SDORB_MAX_LEVELS || !assigned || !nmatches || capacity <= 0 || capacity > kSearchMaxCapacity || capacity_mp <= 0)
     return SDORB_ERR_BAD_ARG;
   DeviceGuard guard(h->device);
@@ -1025,7 +1026,8 @@ int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search*
   SearchPointsArgs a;
   a.capacity = capacity;
   a.capacity_mp = capacity_mp;
-  a.th_high = 100;  // ORBmatcher::TH_HIGH, src/ORBmatcher.cc:36
+  a.th_high = sim3 ? 50 : 100;  // ORBmatcher::TH_LOW (:243) / TH_HIGH (:100), src/ORBmatcher.cc:36-37
+  a.sim3_form = sim3 ? 1 : 0;
   a.th = q->th;
   a.nnratio = q->nnratio;
   for (int l = 0; l < SDORB_MAX_LEVELS; ++l) a.scale_factors[l] = q->scale_factors[std::min(l, q->nlevels - 1)];
@@ -1040,11 +1042,12 @@ int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search*
     a.grid.cell_start = q->grid.cell_start; a.grid.indices = q->grid.indices;
     a.assigned = assigned; a.nmatches = nmatches;
   } else {
-    const size_t iPR = st.add(q->proj, nullptr, 12 * P * M), iVC = st.add(q->view_cos, nullptr, 4 * P * M),
+    // view_cos / u_right are not read in the Sim3 form: nothing is uploaded for them (their slots stay unread)
+    const size_t iPR = st.add(q->proj, nullptr, 12 * P * M), iVC = st.add(sim3 ? nullptr : q->view_cos, nullptr, sim3 ? 4 : 4 * P * M),
                  iLV = st.add(q->level, nullptr, 4 * P * M), iFL = st.add(q->flags, nullptr, P * M),
                  iDM = st.add(q->desc_mp, nullptr, 32 * P * M), iNM = st.add(q->n_mp, nullptr, 4 * P),
                  iK = st.add(q->kps_un, nullptr, sizeof(sdorb_keypoint) * P * C), iD = st.add(q->desc, nullptr, 32 * P * C),
-                 iUR = st.add(q->u_right, nullptr, 4 * P * C), iOC = st.add(q->occupied, nullptr, P * C),
+                 iUR = st.add(sim3 ? nullptr : q->u_right, nullptr, sim3 ? 4 : 4 * P * C), iOC = st.add(q->occupied, nullptr, P * C),
                  iNF = st.add(q->n_frame, nullptr, 4 * P), iCS = st.add(q->grid.cell_start, nullptr, 4 * ncs * P),
                  iIX = st.add(q->grid.indices, nullptr, 4 * P * C), iAS = st.add(nullptr, assigned, 4 * P * C),
                  iNO = st.add(nullptr, nmatches, 4 * P);
@@ -1111,53 +1114,127 @@ int sdorb_search_by_points_batch(sdorb_handle* h, const sdorb_keypoint* kps1, co
   return SDORB_OK;
 }
 
-int sdorb_fuse_search_batch(sdorb_handle* h, const sdorb_fuse_search* q, int nframes, int capacity_mp, int capacity, int32_t* best_idx,
-                            int32_t* best_dist, int mem, void* stream) {
-  if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
-  if (nframes == 0) return SDORB_OK;
-  if (!q || !q->proj || !q->level || !q->flags || !q->desc_mp || !q->n_mp || !q->kps_un || !q->desc || !q->u_right ||
-      !q->grid.cell_start || !q->grid.indices || !q->scale_factors || !q->inv_level_sigma2 || q->nlevels <= 0 ||
-      q->nlevels > SDORB_MAX_LEVELS || !best_idx || !best_dist || capacity <= 0 || capacity > kSearchMaxCapacity || capacity_mp <= 0)
-    return SDORB_ERR_BAD_ARG;
-  DeviceGuard guard(h->device);
-  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
-  FuseSearchArgs a;
-  a.capacity = capacity;
-  a.capacity_mp = capacity_mp;
-  a.th_low = 50;  // ORBmatcher::TH_LOW, src/ORBmatcher.cc:37
-  a.th = q->th;
-  for (int l = 0; l < SDORB_MAX_LEVELS; ++l) {
-    a.scale_factors[l] = q->scale_factors[std::min(l, q->nlevels - 1)];
-    a.inv_sigma2[l] = q->inv_level_sigma2[std::min(l, q->nlevels - 1)];
+namespace {
+// Staging of one sdorb_fuse_search (host memory) / pointer pass-through (device memory), shared by the Fuse and SearchBySim3 entries.
+struct FuseStage {
+  size_t iPR, iLV, iFL, iDM, iNM, iK, iD, iUR, iCS, iIX;
+  static bool valid(const sdorb_fuse_search* q, int capacity_mp, int capacity) {
+    return q && q->proj && q->level && q->flags && q->desc_mp && q->n_mp && q->kps_un && q->desc && q->grid.cell_start && q->grid.indices &&
+           q->scale_factors && q->nlevels > 0 && q->nlevels <= SDORB_MAX_LEVELS && capacity > 0 && capacity <= kSearchMaxCapacity &&
+           capacity_mp > 0 && (!q->check_reprojection || (q->u_right && q->inv_level_sigma2));
   }
-  a.grid.min_x = q->grid.min_x; a.grid.min_y = q->grid.min_y;
-  a.grid.inv_w = q->grid.inv_w; a.grid.inv_h = q->grid.inv_h;
-  const size_t P = (size_t)nframes, C = (size_t)capacity, M = (size_t)capacity_mp, ncs = (size_t)SDORB_GRID_COLS * SDORB_GRID_ROWS + 1;
-  Stager st;
-  if (mem == SDORB_MEM_DEVICE) {
-    if (((uintptr_t)q->desc_mp | (uintptr_t)q->desc) % 16) return SDORB_ERR_BAD_ARG;
+  static void scalars(const sdorb_fuse_search* q, int capacity_mp, int capacity, int th_dist, FuseSearchArgs& a) {
+    a.capacity = capacity;
+    a.capacity_mp = capacity_mp;
+    a.th_dist = th_dist;
+    a.check_reprojection = q->check_reprojection ? 1 : 0;
+    a.th = q->th;
+    for (int l = 0; l < SDORB_MAX_LEVELS; ++l) {
+      a.scale_factors[l] = q->scale_factors[std::min(l, q->nlevels - 1)];
+      a.inv_sigma2[l] = q->check_reprojection ? q->inv_level_sigma2[std::min(l, q->nlevels - 1)] : 0.f;
+    }
+    a.grid.min_x = q->grid.min_x; a.grid.min_y = q->grid.min_y;
+    a.grid.inv_w = q->grid.inv_w; a.grid.inv_h = q->grid.inv_h;
+  }
+  static bool device_ok(const sdorb_fuse_search* q) { return (((uintptr_t)q->desc_mp | (uintptr_t)q->desc) % 16) == 0; }
+  static void device(const sdorb_fuse_search* q, FuseSearchArgs& a) {
     a.proj = q->proj; a.level = q->level; a.flags = q->flags; a.desc_mp = q->desc_mp; a.n_mp = q->n_mp;
     a.kps = q->kps_un; a.desc = q->desc; a.u_right = q->u_right;
     a.grid.cell_start = q->grid.cell_start; a.grid.indices = q->grid.indices;
-    a.best_idx = best_idx; a.best_dist = best_dist;
-  } else {
-    const size_t iPR = st.add(q->proj, nullptr, 12 * P * M), iLV = st.add(q->level, nullptr, 4 * P * M), iFL = st.add(q->flags, nullptr, P * M),
-                 iDM = st.add(q->desc_mp, nullptr, 32 * P * M), iNM = st.add(q->n_mp, nullptr, 4 * P),
-                 iK = st.add(q->kps_un, nullptr, sizeof(sdorb_keypoint) * P * C), iD = st.add(q->desc, nullptr, 32 * P * C),
-                 iUR = st.add(q->u_right, nullptr, 4 * P * C), iCS = st.add(q->grid.cell_start, nullptr, 4 * ncs * P),
-                 iIX = st.add(q->grid.indices, nullptr, 4 * P * C), iBI = st.add(nullptr, best_idx, 4 * P * M),
-                 iBD = st.add(nullptr, best_dist, 4 * P * M);
-    int rc = st.upload(h, s);
-    if (rc) return rc;
+  }
+  void add(Stager& st, const sdorb_fuse_search* q, size_t P, size_t M, size_t C) {
+    const size_t ncs = (size_t)SDORB_GRID_COLS * SDORB_GRID_ROWS + 1;
+    const bool ur = q->check_reprojection != 0;  // mvuRight is only read by the reprojection gate
+    iPR = st.add(q->proj, nullptr, 12 * P * M); iLV = st.add(q->level, nullptr, 4 * P * M); iFL = st.add(q->flags, nullptr, P * M);
+    iDM = st.add(q->desc_mp, nullptr, 32 * P * M); iNM = st.add(q->n_mp, nullptr, 4 * P);
+    iK = st.add(q->kps_un, nullptr, sizeof(sdorb_keypoint) * P * C); iD = st.add(q->desc, nullptr, 32 * P * C);
+    iUR = st.add(ur ? q->u_right : nullptr, nullptr, ur ? 4 * P * C : 4); iCS = st.add(q->grid.cell_start, nullptr, 4 * ncs * P);
+    iIX = st.add(q->grid.indices, nullptr, 4 * P * C);
+  }
+  void resolve(sdorb_handle* h, const Stager& st, FuseSearchArgs& a) const {
     a.proj = (float*)st.dev(h, iPR); a.level = (int32_t*)st.dev(h, iLV); a.flags = (uint8_t*)st.dev(h, iFL);
     a.desc_mp = (uint8_t*)st.dev(h, iDM); a.n_mp = (int32_t*)st.dev(h, iNM);
     a.kps = (void*)st.dev(h, iK); a.desc = (uint8_t*)st.dev(h, iD); a.u_right = (float*)st.dev(h, iUR);
     a.grid.cell_start = (int32_t*)st.dev(h, iCS); a.grid.indices = (int32_t*)st.dev(h, iIX);
+  }
+};
+}  // namespace
+
+int sdorb_fuse_search_batch(sdorb_handle* h, const sdorb_fuse_search* q, int nframes, int capacity_mp, int capacity, int32_t* best_idx,
+                            int32_t* best_dist, int mem, void* stream) {
+  if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (nframes == 0) return SDORB_OK;
+  if (!FuseStage::valid(q, capacity_mp, capacity) || !best_idx || !best_dist || q->th_dist < 0 || q->th_dist > 256) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  FuseSearchArgs a;
+  FuseStage::scalars(q, capacity_mp, capacity, q->th_dist, a);
+  const size_t P = (size_t)nframes, C = (size_t)capacity, M = (size_t)capacity_mp;
+  Stager st;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (!FuseStage::device_ok(q)) return SDORB_ERR_BAD_ARG;
+    FuseStage::device(q, a);
+    a.best_idx = best_idx; a.best_dist = best_dist;
+  } else {
+    FuseStage fs;
+    fs.add(st, q, P, M, C);
+    const size_t iBI = st.add(nullptr, best_idx, 4 * P * M), iBD = st.add(nullptr, best_dist, 4 * P * M);
+    int rc = st.upload(h, s);
+    if (rc) return rc;
+    fs.resolve(h, st, a);
     a.best_idx = (int32_t*)st.dev(h, iBI); a.best_dist = (int32_t*)st.dev(h, iBD);
   }
   {
     StageScope sc(h, s, SDORB_STAGE_MATCH);
     launch_fuse_search(a, nframes, s);
+    sc.launched();
+  }
+  CU(cudaGetLastError());
+  if (mem == SDORB_MEM_HOST) return st.download(h, s);
+  return SDORB_OK;
+}
+
+int sdorb_search_by_sim3_batch(sdorb_handle* h, const sdorb_fuse_search* q12, const sdorb_fuse_search* q21, int npairs, int capacity,
+                               int32_t* match1, int32_t* match2, int32_t* matches12, int32_t* nfound, int mem, void* stream) {
+  if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (npairs == 0) return SDORB_OK;
+  if (!FuseStage::valid(q12, capacity, capacity) || !FuseStage::valid(q21, capacity, capacity) || q12->check_reprojection ||
+      q21->check_reprojection || !match1 || !match2 || !matches12 || !nfound)
+    return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
+  FuseSearchArgs a12, a21;
+  FuseStage::scalars(q12, capacity, capacity, 100, a12);  // ORBmatcher::TH_HIGH, src/ORBmatcher.cc:36 (:843, :921)
+  FuseStage::scalars(q21, capacity, capacity, 100, a21);
+  a12.best_dist = a21.best_dist = nullptr;
+  const size_t P = (size_t)npairs, C = (size_t)capacity;
+  int32_t *d_m12 = matches12, *d_nf = nfound;
+  Stager st;
+  if (mem == SDORB_MEM_DEVICE) {
+    if (!FuseStage::device_ok(q12) || !FuseStage::device_ok(q21)) return SDORB_ERR_BAD_ARG;
+    FuseStage::device(q12, a12);
+    FuseStage::device(q21, a21);
+    a12.best_idx = match1; a21.best_idx = match2;
+  } else {
+    FuseStage f12, f21;
+    f12.add(st, q12, P, C, C);
+    f21.add(st, q21, P, C, C);
+    const size_t iM1 = st.add(nullptr, match1, 4 * P * C), iM2 = st.add(nullptr, match2, 4 * P * C),
+                 iM12 = st.add(nullptr, matches12, 4 * P * C), iNF = st.add(nullptr, nfound, 4 * P);
+    int rc = st.upload(h, s);
+    if (rc) return rc;
+    f12.resolve(h, st, a12);
+    f21.resolve(h, st, a21);
+    a12.best_idx = (int32_t*)st.dev(h, iM1); a21.best_idx = (int32_t*)st.dev(h, iM2);
+    d_m12 = (int32_t*)st.dev(h, iM12); d_nf = (int32_t*)st.dev(h, iNF);
+  }
+  {
+    StageScope sc(h, s, SDORB_STAGE_MATCH);
+    launch_fuse_search(a12, npairs, s);
+    sc.launched();
+    launch_fuse_search(a21, npairs, s);
+    sc.launched();
+    launch_sim3_agreement(a12.best_idx, a21.best_idx, a12.n_mp, capacity, d_m12, d_nf, npairs, s);
     sc.launched();
   }
   CU(cudaGetLastError());

@@ -589,9 +589,10 @@ def fuse_descriptors(seed, df, kf_src_n, n_mp):
     return dd
 
 
-def py_fuse_search(proj, level, flags, desc_mp, kf, df, ur, gp, sf, inv_sigma2, th):
+def py_fuse_search(proj, level, flags, desc_mp, kf, df, ur, gp, sf, inv_sigma2, th, check_reprojection=True, th_dist=TH_LOW):
     """(best_idx, best_dist) per map point; e2 in the contracted form of the reference build (see
-    test_fuse_e2_matches_reference_flags): fma(er, er, fma(ex, ex, ey * ey))."""
+    test_fuse_e2_matches_reference_flags): fma(er, er, fma(ex, ex, ey * ey)).  check_reprojection=False: the search of the Sim3
+    overload (src/ORBmatcher.cc:682-708) and, with th_dist = TH_HIGH, of either direction of SearchBySim3 (:812-845, :890-923)."""
     grid = py_grid(kf, gp)
     bi, bd = [-1] * len(proj), [256] * len(proj)
     for i in range(len(proj)):
@@ -605,19 +606,107 @@ def py_fuse_search(proj, level, flags, desc_mp, kf, df, ur, gp, sf, inv_sigma2, 
             kl = int(kf["octave"][idx])
             if kl < lvl - 1 or kl > lvl:
                 continue
-            ex, ey = F32(u - F32(kf["x"][idx])), F32(v - F32(kf["y"][idx]))
-            e2 = _fmaf(ex, ex, F32(ey * ey))
-            lim = 5.99
-            if ur[idx] >= 0:
-                er = F32(r - F32(ur[idx]))
-                e2 = _fmaf(er, er, e2)
-                lim = 7.8
-            if float(F32(e2 * F32(inv_sigma2[kl]))) > lim:
-                continue
+            if check_reprojection:
+                ex, ey = F32(u - F32(kf["x"][idx])), F32(v - F32(kf["y"][idx]))
+                e2 = _fmaf(ex, ex, F32(ey * ey))
+                lim = 5.99
+                if ur[idx] >= 0:
+                    er = F32(r - F32(ur[idx]))
+                    e2 = _fmaf(er, er, e2)
+                    lim = 7.8
+                if float(F32(e2 * F32(inv_sigma2[kl]))) > lim:
+                    continue
             d = py_distance(desc_mp[i], df[idx])
             if d < best:
                 best, bidx = d, idx
         bd[i] = best
-        if best <= TH_LOW:
+        if best <= th_dist:
             bi[i] = bidx
     return np.array(bi, np.int32), np.array(bd, np.int32)
+
+
+# ------------------------------------------------------------------ SearchBySim3 (src/ORBmatcher.cc:734-944)
+def sim3_case(seed, n1, n2, nlevels=8, dup=0.0):
+    """Two keyframes seeing the same scene: keypoint i of either keyframe may carry a map point (flag), which projects into the
+    other keyframe next to its true partner (or somewhere else), with the map point's own descriptor a few bits off."""
+    k1, d1, k2, d2 = frame_pair(seed + 160, n1, n2, jitter=5.0, level0=0.3, flips=30, dup=dup)
+    rng = np.random.default_rng(seed + 1600)
+
+    def side(ka, da, kb, db):
+        na, nb = len(ka), len(kb)
+        proj = np.zeros((na, 3), F32)
+        level = rng.integers(0, nlevels, na).astype(np.int32)
+        dmp = da.copy()
+        if na and nb:
+            src = np.where(rng.random(na) < 0.8, np.arange(na) % nb, rng.integers(0, nb, na))
+            proj[:, 0] = kb["x"][src] + rng.uniform(-4, 4, na).astype(F32)
+            proj[:, 1] = kb["y"][src] + rng.uniform(-4, 4, na).astype(F32)
+            level[:] = np.clip(kb["octave"][src] + rng.integers(0, 2, na), 0, nlevels - 1)
+            dmp = db[src].copy()
+            for r in range(na):
+                for b in rng.choice(256, int(rng.integers(0, 60)), replace=False):
+                    dmp[r, b >> 3] ^= 1 << (b & 7)
+        elif na:
+            proj[:, 0], proj[:, 1] = rng.uniform(0, 640, na), rng.uniform(0, 480, na)
+        flags = (rng.random(na) < 0.8).astype(np.uint8)
+        return proj, level, flags, dmp
+    return (side(k1, d1, k2, d2) + (k1, d1)), (side(k2, d2, k1, d1) + (k2, d2))
+
+
+def py_search_by_sim3(s1, s2, gp, sf, th):
+    """(nFound, matches12, vnMatch1, vnMatch2); s = (proj, level, flags, desc_mp, kps, desc) of a keyframe."""
+    def one_way(s, kb, db):
+        proj, level, flags, dmp = s[:4]
+        grid = py_grid(kb, gp)
+        out = [-1] * len(proj)
+        for i in range(len(proj)):
+            if not flags[i] & 1:
+                continue
+            lvl = int(level[i])
+            radius = F32(F32(th) * F32(sf[lvl]))
+            best, bidx = INT_MAX, -1
+            for idx in py_features_in_area(kb, grid, gp, F32(proj[i][0]), F32(proj[i][1]), radius, -1, -1):
+                if kb["octave"][idx] < lvl - 1 or kb["octave"][idx] > lvl:
+                    continue
+                d = py_distance(dmp[i], db[idx])
+                if d < best:
+                    best, bidx = d, idx
+            if best <= TH_HIGH:
+                out[i] = bidx
+        return out
+    m1, m2 = one_way(s1, s2[4], s2[5]), one_way(s2, s1[4], s1[5])
+    m12 = [-1] * len(m1)
+    n = 0
+    for i1, idx2 in enumerate(m1):
+        if idx2 >= 0 and m2[idx2] == i1:
+            m12[i1] = idx2
+            n += 1
+    return n, np.array(m12, np.int32), np.array(m1, np.int32), np.array(m2, np.int32)
+
+
+# ------------------------------------------------------------------ SearchByProjection(KeyFrame, Scw, vpPoints, vpMatched, th) (:146-254)
+def py_search_by_projection_sim3(proj, level, flags, desc_mp, kf, df, matched_in, gp, sf, th):
+    """(nmatches, assigned): assigned[idx] = index of the point written to vpMatched[idx]."""
+    grid = py_grid(kf, gp)
+    matched = [bool(m) for m in matched_in]
+    assigned = [-1] * len(kf)
+    n = 0
+    for i in range(len(proj)):
+        if not flags[i] & 1:
+            continue
+        lvl = int(level[i])
+        radius = F32(F32(int(th)) * F32(sf[lvl]))
+        best, bidx = 256, -1
+        for idx in py_features_in_area(kf, grid, gp, F32(proj[i][0]), F32(proj[i][1]), radius, -1, -1):
+            if matched[idx]:
+                continue
+            if kf["octave"][idx] < lvl - 1 or kf["octave"][idx] > lvl:
+                continue
+            d = py_distance(desc_mp[i], df[idx])
+            if d < best:
+                best, bidx = d, idx
+        if best <= TH_LOW:
+            matched[bidx] = True
+            assigned[bidx] = i
+            n += 1
+    return n, np.array(assigned, np.int32)

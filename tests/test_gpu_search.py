@@ -354,3 +354,98 @@ def test_fuse_search_equals_oracle(ex, th, stereo):
         fused += int((obi >= 0).sum())
         rejected += int(((obd > 50) & (obd < 256)).sum())
     assert fused > 500 and rejected > 50
+
+
+@pytest.mark.parametrize("th,th_dist", [(3.0, 50), (4.0, 100)])
+def test_fuse_search_sim3_form_equals_oracle(ex, th, th_dist):
+    """check_reprojection = 0: the search of Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:682-708); u_right and
+    inv_level_sigma2 are NULL."""
+    sizes = [(600, 500, 0.0), (0, 50, 0.0), (200, 0, 0.0), (700, 900, 0.3), (1, 1, 0.0)]
+    frames = []
+    for s, (nf, nmp, dup) in enumerate(sizes):
+        _, _, kf, df = sc.frame_pair(s + 140, 10, nf, dup=dup, level0=0.3)
+        proj, lvl, fl, _ = sc.fuse_inputs(s, kf, nmp, stereo=False)
+        frames.append((proj, lvl, fl, sc.fuse_descriptors(s, df, nf, nmp), kf, df))
+    cap, capmp = 704, 912
+    gp = sc.grid_params()
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    col = lambda j, c, dt, tail=(): _slab([f[j] for f in frames], c, dt, tail)
+    kf = col(4, cap, api.KP_DTYPE)
+    nmp = np.array([len(f[0]) for f in frames], np.int32)
+    nf = np.array([len(f[4]) for f in frames], np.int32)
+    cs, idx = ex.assign_grid_batch(kf, nf, *gp)
+    bi, bd = ex.fuse_search_batch(col(0, capmp, np.float32, (3,)), col(1, capmp, np.int32), col(2, capmp, np.uint8),
+                                  col(3, capmp, np.uint8, (32,)), nmp, kf, col(5, cap, np.uint8, (32,)), None,
+                                  (cs, idx) + tuple(gp), sf, None, th, check_reprojection=False, th_dist=th_dist)
+    found = 0
+    for p, f in enumerate(frames):
+        ocs, oidx = orc.assign_grid(f[4], *gp)
+        obi, obd = orc.fuse_search(f[0], f[1], f[2], f[3], f[4], f[5], None, (ocs, oidx) + tuple(gp), sf, None, th, False, th_dist)
+        n = len(f[0])
+        assert np.array_equal(bi[p, :n], obi) and np.array_equal(bd[p, :n], obd), "keyframe %d" % p
+        assert (bi[p, n:] == -1).all() and (bd[p, n:] == 256).all()
+        found += int((obi >= 0).sum())
+    assert found > 300
+
+
+def test_search_by_sim3_equals_oracle(ex):
+    """sdorb_search_by_sim3_batch = ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:734-944) from the projections on: vnMatch1, vnMatch2,
+    the agreement check and nFound, on a ragged batch incl. empty keyframes and duplicate descriptors."""
+    sizes = [(500, 520, 0.0), (300, 400, 0.3), (0, 100, 0.0), (100, 0, 0.0), (640, 600, 0.1), (1, 1, 0.0)]
+    cases = [sc.sim3_case(s, a, b, dup=d) for s, (a, b, d) in enumerate(sizes)]
+    cap = 640
+    gp = sc.grid_params()
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    th = 7.5
+
+    def side(j):
+        ks = _slab([c[j][4] for c in cases], cap, api.KP_DTYPE)
+        n = np.array([len(c[j][4]) for c in cases], np.int32)
+        cs, idx = ex.assign_grid_batch(ks, n, *gp)
+        return (_slab([c[j][0] for c in cases], cap, np.float32, (3,)), _slab([c[j][1] for c in cases], cap, np.int32),
+                _slab([c[j][2] for c in cases], cap, np.uint8), _slab([c[j][3] for c in cases], cap, np.uint8, (32,)), n, ks,
+                _slab([c[j][5] for c in cases], cap, np.uint8, (32,)), (cs, idx) + tuple(gp))
+    nf, m12, m1, m2 = ex.search_by_sim3_batch(side(0), side(1), sf, th)
+    total = 0
+    for p, (s1, s2) in enumerate(cases):
+        g1, g2 = orc.assign_grid(s1[4], *gp) + tuple(gp), orc.assign_grid(s2[4], *gp) + tuple(gp)
+        on, om12, om1, om2 = orc.search_by_sim3(s1 + (g1,), s2 + (g2,), sf, th)
+        n1, n2 = len(s1[4]), len(s2[4])
+        assert nf[p] == on, "pair %d: nFound %d vs oracle %d" % (p, nf[p], on)
+        assert np.array_equal(m12[p, :n1], om12) and np.array_equal(m1[p, :n1], om1) and np.array_equal(m2[p, :n2], om2), "pair %d" % p
+        assert (m12[p, n1:] == -1).all() and (m1[p, n1:] == -1).all() and (m2[p, n2:] == -1).all()
+        total += on
+    assert total > 300
+
+
+@pytest.mark.parametrize("th", [10, 4])
+def test_search_by_projection_sim3_equals_oracle(ex, th):
+    """sdorb_search_map_points_batch with sim3_form = 1 = ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th)
+    (src/ORBmatcher.cc:146-254): keypoints already matched on entry, matches occupying their keypoint for the later points."""
+    sizes = [(600, 500, 0.0), (500, 700, 0.0), (0, 50, 0.0), (200, 0, 0.0), (700, 900, 0.3), (1, 1, 0.0)]
+    frames = []
+    for s, (nf, nmp, dup) in enumerate(sizes):
+        _, _, kf, df = sc.frame_pair(s + 140, 10, nf, dup=dup, level0=0.3)
+        proj, lvl, fl, _ = sc.fuse_inputs(s, kf, nmp, stereo=False)
+        matched = (np.random.default_rng(s).random(nf) < 0.15).astype(np.uint8)
+        frames.append((proj, lvl, fl, sc.fuse_descriptors(s, df, nf, nmp), kf, df, matched))
+    cap, capmp = 704, 912
+    gp = sc.grid_params()
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    col = lambda j, c, dt, tail=(): _slab([f[j] for f in frames], c, dt, tail)
+    kf = col(4, cap, api.KP_DTYPE)
+    nmp = np.array([len(f[0]) for f in frames], np.int32)
+    nf = np.array([len(f[4]) for f in frames], np.int32)
+    cs, idx = ex.assign_grid_batch(kf, nf, *gp)
+    nm, asg = ex.search_by_projection_sim3_batch(col(0, capmp, np.float32, (3,)), col(1, capmp, np.int32), col(2, capmp, np.uint8),
+                                                 col(3, capmp, np.uint8, (32,)), nmp, kf, col(5, cap, np.uint8, (32,)),
+                                                 col(6, cap, np.uint8), nf, (cs, idx) + tuple(gp), sf, th)
+    total = 0
+    for p, f in enumerate(frames):
+        ocs, oidx = orc.assign_grid(f[4], *gp)
+        on, oasg = orc.search_by_projection_sim3(f[0], f[1], f[2], f[3], f[4], f[5], f[6], (ocs, oidx) + tuple(gp), sf, th)
+        assert nm[p] == on, "keyframe %d: nmatches %d vs oracle %d" % (p, nm[p], on)
+        assert np.array_equal(asg[p, :len(f[4])], oasg), "keyframe %d: assignment" % p
+        assert (asg[p, len(f[4]):] == -1).all()
+        total += on
+    assert total > 300

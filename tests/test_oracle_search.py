@@ -295,3 +295,49 @@ def test_fuse_search_equals_restatement(seed, nf, nmp, th, stereo, dup):
     assert np.array_equal(bi, pbi) and np.array_equal(bd, pbd)
     if seed == 0:
         assert (bi >= 0).sum() > 100 and ((bd > 50) & (bd < 256)).sum() > 20
+
+
+@pytest.mark.parametrize("seed,nf,nmp,th,th_dist", [(0, 600, 500, 3.0, 50), (1, 500, 700, 4.0, 100), (2, 0, 50, 3.0, 50), (4, 700, 900, 4.0, 50)])
+def test_fuse_search_sim3_form_equals_restatement(seed, nf, nmp, th, th_dist):
+    """Without the reprojection gate: Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:682-708; TH_LOW) and one
+    direction of SearchBySim3 (TH_HIGH)."""
+    _, _, kf, df = sc.frame_pair(seed + 140, 10, nf, dup=0.3 if seed == 4 else 0.0, level0=0.3)
+    proj, lvl, fl, _ = sc.fuse_inputs(seed, kf, nmp, stereo=False)
+    dmp = sc.fuse_descriptors(seed, df, nf, nmp)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    gp = sc.grid_params()
+    bi, bd = orc.fuse_search(proj, lvl, fl, dmp, kf, df, None, _orc_grid(kf, gp), sf, None, th, False, th_dist)
+    pbi, pbd = sc.py_fuse_search(proj, lvl, fl, dmp, kf, df, None, gp, sf, None, th, False, th_dist)
+    assert np.array_equal(bi, pbi) and np.array_equal(bd, pbd)
+    if seed < 2:
+        assert (bi >= 0).sum() > 100
+
+
+@pytest.mark.parametrize("seed,n1,n2,th,dup", [(0, 500, 520, 7.5, 0.0), (1, 300, 400, 7.5, 0.3), (2, 0, 100, 7.5, 0.0), (3, 100, 0, 7.5, 0.0),
+                                               (4, 640, 600, 3.0, 0.1)])
+def test_search_by_sim3_equals_restatement(seed, n1, n2, th, dup):
+    s1, s2 = sc.sim3_case(seed, n1, n2, dup=dup)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    gp = sc.grid_params()
+    n, m12, m1, m2 = orc.search_by_sim3(s1 + (_orc_grid(s1[4], gp),), s2 + (_orc_grid(s2[4], gp),), sf, th)
+    pn, pm12, pm1, pm2 = sc.py_search_by_sim3(s1, s2, gp, sf, th)
+    assert n == pn and np.array_equal(m12, pm12) and np.array_equal(m1, pm1) and np.array_equal(m2, pm2)
+    if seed == 0:
+        assert n > 100 and (m1 >= 0).sum() > n  # some one-way matches fail the agreement check
+
+
+@pytest.mark.parametrize("seed,nf,nmp,th,dup", [(0, 600, 500, 10, 0.0), (1, 500, 700, 4, 0.0), (2, 0, 50, 10, 0.0), (3, 200, 0, 10, 0.0),
+                                                (4, 700, 900, 10, 0.3)])
+def test_search_by_projection_sim3_equals_restatement(seed, nf, nmp, th, dup):
+    _, _, kf, df = sc.frame_pair(seed + 140, 10, nf, dup=dup, level0=0.3)
+    proj, lvl, fl, _ = sc.fuse_inputs(seed, kf, nmp, stereo=False)
+    dmp = sc.fuse_descriptors(seed, df, nf, nmp)
+    matched = (np.random.default_rng(seed).random(nf) < 0.15).astype(np.uint8)
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    gp = sc.grid_params()
+    n, asg = orc.search_by_projection_sim3(proj, lvl, fl, dmp, kf, df, matched, _orc_grid(kf, gp), sf, th)
+    pn, pasg = sc.py_search_by_projection_sim3(proj, lvl, fl, dmp, kf, df, matched, gp, sf, th)
+    assert n == pn and np.array_equal(asg, pasg)
+    assert not (asg[matched.astype(bool)] >= 0).any()
+    if seed == 0:
+        assert n > 100
