@@ -219,7 +219,10 @@ SDORB_API int sdorb_search_for_initialization_batch(sdorb_handle* h, const sdorb
  * occupied[i2] != 0 where mvpMapPoints[i2] is set with Observations() > 0 on entry (:1018-1020), its grid, bounds =
  * {mnMinX, mnMaxX, mnMinY, mnMaxY}; scale_factors = mvScaleFactors (nlevels <= 32 host floats).
  * assigned [npairs][capacity]: for every current-frame keypoint the last-frame index whose map point the call leaves in
- * CurrentFrame.mvpMapPoints, -1 where the call sets none (or clears it in the rotation check); nmatches [npairs]. */
+ * CurrentFrame.mvpMapPoints, -1 where the call sets none (or clears it in the rotation check); nmatches [npairs].
+ * The overload SearchByProjection(CurrentFrame, KeyFrame* pKF, th, bMono) (src/ORBmatcher.cc:1077-1207) is the same text from the
+ * projection on with pKF in the place of LastFrame (kps_last = pKF->mvKeys, kps_last_un = pKF->mvKeysUn, flags bit 0 = the map
+ * point exists and !isBad(), :1101-1103): it is served by this entry unchanged. */
 typedef struct {
   const sdorb_keypoint* kps_last;     /* LastFrame.mvKeys (octave) */
   const sdorb_keypoint* kps_last_un;  /* LastFrame.mvKeysUn (angle) */
@@ -239,7 +242,7 @@ typedef struct {
   float th, mbf;
   int mode, check_orientation;
   int orb_dist;                       /* distance threshold; 0 = TH_HIGH (100).  With it the same entry point serves
-                                         SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1298-1420):
+                                         SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1306-1421):
                                          kps_last.octave = nPredictedLevel, mode 0, flags bit 1 set, u_right_cur = -1,
                                          occupied_cur = (mvpMapPoints[i2] != NULL), proj[2] = any value >= 0 */
 } sdorb_projection_search;
@@ -281,7 +284,7 @@ typedef struct {
 SDORB_API int sdorb_search_map_points_batch(sdorb_handle* h, const sdorb_map_point_search* q, int nframes, int capacity_mp, int capacity,
                                             int32_t* assigned, int32_t* nmatches, int mem, void* stream);
 
-/* ORBmatcher::SearchByPoints(currentKF, pKF, matches) (src/ORBmatcher.cc:1207-1296; loop detection, src/LoopClosing.cc:255), batched
+/* ORBmatcher::SearchByPoints(currentKF, pKF, matches) (src/ORBmatcher.cc:1209-1304; loop detection, src/LoopClosing.cc:255), batched
  * over keyframe pairs.  valid1 / valid2 [npairs][capacity]: the keypoint has a map point that is not bad (:1231-1236, :1246-1251).
  * matches12 [npairs][capacity]: index into the second keyframe whose map point the call puts into matches[idx1], -1 = NULL;
  * nmatches [npairs].  The matcher is the one constructed as ORBmatcher(nnratio, check_orientation). */

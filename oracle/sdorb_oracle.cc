@@ -1269,7 +1269,7 @@ int orc_search_by_projection(const orc_keypoint* kL, const orc_keypoint* kLun, c
                              const uint8_t* occupied_in, int nC, const orc_frame_grid* gridC, const float* mvScaleFactors,
                              const float bounds[4], float th, float mbf, int mode, int mbCheckOrientation, int32_t* assigned,
                              int orb_dist) {
-  const int thHigh = orb_dist > 0 ? orb_dist : kThHigh; /* the KeyFrame overload (:1298-1420) passes its own ORBdist */
+  const int thHigh = orb_dist > 0 ? orb_dist : kThHigh; /* the KeyFrame overload (:1306-1421) passes its own ORBdist */
   int nmatches = 0;
   std::fill(assigned, assigned + nC, -1);
   std::vector<uint8_t> occupiedC(occupied_in, occupied_in + nC);
@@ -1379,7 +1379,7 @@ int orc_search_map_points(const float* proj /* n x 3 */, const float* view_cos, 
   }
   return nmatches;
 }
-// ORBmatcher::SearchByPoints(currentKF, pKF, matches), src/ORBmatcher.cc:1207-1296 (loop detection, LoopClosing.cc:255).
+// ORBmatcher::SearchByPoints(currentKF, pKF, matches), src/ORBmatcher.cc:1209-1304 (loop detection, LoopClosing.cc:255).
 // valid1 / valid2: the keypoint has a map point that is not bad.  matches12[idx1] = idx2 whose map point ends up in matches[idx1].
 int orc_search_by_points(const orc_keypoint* k1, const uint8_t* d1s, const uint8_t* valid1, int n1, const orc_keypoint* k2,
                          const uint8_t* d2s, const uint8_t* valid2, int n2, float mfNNratio, int mbCheckOrientation, int32_t* matches12) {

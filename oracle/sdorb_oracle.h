@@ -185,7 +185,7 @@ int orc_search_map_points(const float* proj, const float* view_cos, const int32_
                           int n_mp, const orc_keypoint* kps_un, const uint8_t* desc, const float* u_right, const uint8_t* occupied,
                           int n_frame, const orc_frame_grid* grid, const float* scale_factors, float th, float nnratio,
                           int32_t* assigned);
-/* ORBmatcher::SearchByPoints (src/ORBmatcher.cc:1207-1296): valid = the keypoint has a map point that is not bad; matches12 has n1
+/* ORBmatcher::SearchByPoints (src/ORBmatcher.cc:1209-1304): valid = the keypoint has a map point that is not bad; matches12 has n1
  * entries (index into the second keyframe or -1); returns nmatches. */
 int orc_search_by_points(const orc_keypoint* kps1_un, const uint8_t* desc1, const uint8_t* valid1, int n1, const orc_keypoint* kps2_un,
                          const uint8_t* desc2, const uint8_t* valid2, int n2, float nnratio, int check_orientation, int32_t* matches12);

@@ -477,7 +477,7 @@ void launch_search_points(const SearchPointsArgs& a, int nframes, cudaStream_t s
 }
 
 // ---------------------------------------------------------------------------------------- SearchByPoints
-// src/ORBmatcher.cc:1207-1296 (loop detection): brute force over the keypoints of the other keyframe that have a good map point and
+// src/ORBmatcher.cc:1209-1304 (loop detection): brute force over the keypoints of the other keyframe that have a good map point and
 // are not taken yet (vbMatched2), best / second-best, TH_LOW and the ratio test, rotation histogram.  Queries in order; one
 // warp per keyframe pair, the lanes split the rows of the second keyframe.
 __global__ void __launch_bounds__(32) search_by_points_kernel(SearchByPointsArgs a) {

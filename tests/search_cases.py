@@ -449,7 +449,7 @@ def py_search_map_points(proj, view_cos, level, flags, desc_mp, kf, df, ur, occ_
     return n, np.array(assigned, np.int32)
 
 
-# ------------------------------------------------------------------ SearchByPoints (src/ORBmatcher.cc:1207-1296)
+# ------------------------------------------------------------------ SearchByPoints (src/ORBmatcher.cc:1209-1304)
 def py_search_by_points(k1, d1, v1, k2, d2, v2, nnratio, check_orientation):
     """ORBmatcher::SearchByPoints: (nmatches, matches12)."""
     n = 0
@@ -489,7 +489,7 @@ def py_search_by_points(k1, d1, v1, k2, d2, v2, nnratio, check_orientation):
 # ------------------------------------------------------------------ SearchByProjection(Frame, KeyFrame, sAlreadyFound, th, ORBdist)
 def py_search_by_projection_kf(kkf_un, proj_uv, valid, pred_level, desc_mp, kc, dc, has_mp_cur, gp, sf, bounds, th, orb_dist,
                                check_orientation):
-    """src/ORBmatcher.cc:1298-1420 from the projection on: valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP) && the depth test
+    """src/ORBmatcher.cc:1306-1421 from the projection on: valid[i] = pMP && !isBad() && !sAlreadyFound.count(pMP) && the depth test
     of :1345-1350; pred_level = pMP->PredictScale(dist3D, &CurrentFrame).  (nmatches, assigned)."""
     grid = py_grid(kc, gp)
     n = 0

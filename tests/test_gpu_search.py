@@ -274,7 +274,7 @@ def test_search_map_points_equals_oracle(ex, th, ratio, stereo):
 
 @pytest.mark.parametrize("ratio,orient", [(0.75, True), (0.9, False)])
 def test_search_by_points_equals_oracle(ex, ratio, orient):
-    """sdorb_search_by_points_batch = ORBmatcher::SearchByPoints (src/ORBmatcher.cc:1207-1296): ragged batch of keyframe pairs,
+    """sdorb_search_by_points_batch = ORBmatcher::SearchByPoints (src/ORBmatcher.cc:1209-1304): ragged batch of keyframe pairs,
     keypoints without (good) map points on both sides, duplicate descriptors (contested rows of the second keyframe)."""
     sizes = [(600, 640, 0.0), (400, 380, 0.4), (1000, 1000, 0.1), (0, 50, 0.0), (50, 0, 0.0), (33, 65, 0.6), (1, 1, 0.0)]
     pairs = [sc.frame_pair(80 + s, a, b, dup=d, flips=25) for s, (a, b, d) in enumerate(sizes)]
@@ -298,7 +298,7 @@ def test_search_by_points_equals_oracle(ex, ratio, orient):
 
 
 def test_keyframe_projection_overload_on_gpu(ex):
-    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1298-1420) through
+    """SearchByProjection(Frame&, KeyFrame*, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1306-1421) through
     sdorb_search_by_projection_batch with orb_dist = 64, against the direct Python restatement of that overload."""
     cases = [sc.kf_projection_args(s, nk, nc) for s, (nk, nc) in enumerate([(500, 520), (400, 300), (0, 100), (300, 0)])]
     cap = 544

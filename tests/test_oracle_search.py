@@ -208,7 +208,7 @@ def test_search_by_points_equals_restatement(seed, n1, n2, ratio, orient, dup):
 @pytest.mark.parametrize("seed,nk,nc,th,orb_dist,orient", [(0, 500, 520, 10.0, 100, True), (1, 400, 300, 3.0, 64, True),
                                                            (2, 300, 400, 10.0, 64, False), (3, 0, 100, 10.0, 100, True)])
 def test_keyframe_projection_overload_maps_onto_frame_frame_form(seed, nk, nc, th, orb_dist, orient):
-    """The relocalisation overload (src/ORBmatcher.cc:1298-1420) restated directly in Python equals the oracle's Frame / Frame
+    """The relocalisation overload (src/ORBmatcher.cc:1306-1421) restated directly in Python equals the oracle's Frame / Frame
     function driven with the mapping documented at sdorb_projection_search::orb_dist."""
     a = sc.kf_projection_args(seed, nk, nc)
     sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
