@@ -449,3 +449,41 @@ def test_search_by_projection_sim3_equals_oracle(ex, th):
         assert (asg[p, len(f[4]):] == -1).all()
         total += on
     assert total > 300
+
+
+def test_local_map_loop_golden_fixture(ex):
+    """tests/golden/matcher/local_map_loop.npz (made by the Python restatements, tests/golden/make_loop_golden.py) through the C ABI:
+    local-map search, SearchByPoints, both Fuse searches, SearchBySim3, the Sim3 SearchByProjection."""
+    z = np.load(os.path.join(GOLD, "matcher", "local_map_loop.npz"))
+    gp = tuple(float(v) for v in z["gp"])
+    sf, inv = z["sf"], z["inv_sigma2"]
+    one = lambda a, dt=None: np.ascontiguousarray(a if dt is None else a.view(dt).reshape(-1))[None]
+    kf = one(z["kf"], api.KP_DTYPE)
+    nf, nmp = np.array([kf.shape[1]], np.int32), np.array([len(z["proj"])], np.int32)
+    grid = ex.assign_grid_batch(kf, nf, *gp) + gp
+    args = (one(z["proj"]), one(z["level"]), one(z["flags"]), one(z["dmp"]), nmp, kf, one(z["df"]))
+    bi, bd = ex.fuse_search_batch(*args, one(z["ur"]), grid, sf, inv, 3.0)
+    assert np.array_equal(bi[0], z["fuse_idx"]) and np.array_equal(bd[0], z["fuse_dist"])
+    bi, bd = ex.fuse_search_batch(*args, None, grid, sf, None, 4.0, check_reprojection=False)
+    assert np.array_equal(bi[0], z["fuse_sim3_idx"]) and np.array_equal(bd[0], z["fuse_sim3_dist"])
+    nm, asg = ex.search_by_projection_sim3_batch(*args, one(z["occ"]), nf, grid, sf, 10)
+    assert nm[0] == int(z["proj_sim3_n"]) and np.array_equal(asg[0], z["proj_sim3_assigned"])
+    nm, asg = ex.search_map_points_batch(one(z["lm_proj"]), one(z["lm_view_cos"]), one(z["lm_level"]), one(z["lm_flags"]), one(z["lm_dmp"]),
+                                         nmp, kf, one(z["df"]), one(z["ur"]), one(z["occ"]), nf, grid, sf, 3.0, 0.8)
+    assert nm[0] == int(z["lm_n"]) and np.array_equal(asg[0], z["lm_assigned"])
+    ka, kb = z["sim3_k_a"].view(api.KP_DTYPE).reshape(-1), z["sim3_k_b"].view(api.KP_DTYPE).reshape(-1)
+    cap = max(len(ka), len(kb))
+    pad = lambda a, tail=(): _slab([a], cap, a.dtype, tail)
+
+    def side(t, k):
+        ks, n = pad(k), np.array([len(k)], np.int32)
+        return (pad(z["sim3_proj_" + t], (3,)), pad(z["sim3_level_" + t]), pad(z["sim3_flags_" + t]), pad(z["sim3_dmp_" + t], (32,)), n, ks,
+                pad(z["sim3_d_" + t], (32,)), ex.assign_grid_batch(ks, n, *gp) + gp)
+    nfound, m12, m1, m2 = ex.search_by_sim3_batch(side("a", ka), side("b", kb), sf, 7.5)
+    assert nfound[0] == int(z["sim3_n"]) and np.array_equal(m12[0, :len(ka)], z["sim3_m12"])
+    assert np.array_equal(m1[0, :len(ka)], z["sim3_m1"]) and np.array_equal(m2[0, :len(kb)], z["sim3_m2"])
+    k1, k2 = z["bp_k1"].view(api.KP_DTYPE).reshape(-1), z["bp_k2"].view(api.KP_DTYPE).reshape(-1)
+    cap = max(len(k1), len(k2))
+    nm, m12 = ex.search_by_points_batch(pad(k1), pad(z["bp_d1"], (32,)), pad(z["bp_v1"]), [len(k1)], pad(k2), pad(z["bp_d2"], (32,)),
+                                        pad(z["bp_v2"]), [len(k2)], 0.75, True)
+    assert nm[0] == int(z["bp_n"]) and np.array_equal(m12[0, :len(k1)], z["bp_m12"])

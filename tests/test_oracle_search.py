@@ -341,3 +341,29 @@ def test_search_by_projection_sim3_equals_restatement(seed, nf, nmp, th, dup):
     assert not (asg[matched.astype(bool)] >= 0).any()
     if seed == 0:
         assert n > 100
+
+
+def test_local_map_loop_golden_fixture():
+    """tests/golden/matcher/local_map_loop.npz (inputs + results of the Python restatements, tests/golden/make_loop_golden.py) against
+    the oracle: local-map search, SearchByPoints, both Fuse searches, SearchBySim3, the Sim3 SearchByProjection."""
+    z = np.load(os.path.join(GOLD, "matcher", "local_map_loop.npz"))
+    gp = tuple(float(v) for v in z["gp"])
+    sf, inv = z["sf"], z["inv_sigma2"]
+    kf = z["kf"].view(orc.KP_DTYPE).reshape(-1)
+    g = _orc_grid(kf, gp)
+    bi, bd = orc.fuse_search(z["proj"], z["level"], z["flags"], z["dmp"], kf, z["df"], z["ur"], g, sf, inv, 3.0)
+    assert np.array_equal(bi, z["fuse_idx"]) and np.array_equal(bd, z["fuse_dist"])
+    bi, bd = orc.fuse_search(z["proj"], z["level"], z["flags"], z["dmp"], kf, z["df"], None, g, sf, None, 4.0, False, 50)
+    assert np.array_equal(bi, z["fuse_sim3_idx"]) and np.array_equal(bd, z["fuse_sim3_dist"])
+    n, asg = orc.search_by_projection_sim3(z["proj"], z["level"], z["flags"], z["dmp"], kf, z["df"], z["occ"], g, sf, 10)
+    assert n == int(z["proj_sim3_n"]) and np.array_equal(asg, z["proj_sim3_assigned"])
+    n, asg = orc.search_map_points(z["lm_proj"], z["lm_view_cos"], z["lm_level"], z["lm_flags"], z["lm_dmp"], kf, z["df"], z["ur"], z["occ"],
+                                   g, sf, 3.0, 0.8)
+    assert n == int(z["lm_n"]) and np.array_equal(asg, z["lm_assigned"])
+    ka, kb = z["sim3_k_a"].view(orc.KP_DTYPE).reshape(-1), z["sim3_k_b"].view(orc.KP_DTYPE).reshape(-1)
+    side = lambda t, k: (z["sim3_proj_" + t], z["sim3_level_" + t], z["sim3_flags_" + t], z["sim3_dmp_" + t], k, z["sim3_d_" + t], _orc_grid(k, gp))
+    n, m12, m1, m2 = orc.search_by_sim3(side("a", ka), side("b", kb), sf, 7.5)
+    assert n == int(z["sim3_n"]) and np.array_equal(m12, z["sim3_m12"]) and np.array_equal(m1, z["sim3_m1"]) and np.array_equal(m2, z["sim3_m2"])
+    k1, k2 = z["bp_k1"].view(orc.KP_DTYPE).reshape(-1), z["bp_k2"].view(orc.KP_DTYPE).reshape(-1)
+    n, m12 = orc.search_by_points(k1, z["bp_d1"], z["bp_v1"], k2, z["bp_d2"], z["bp_v2"], 0.75, True)
+    assert n == int(z["bp_n"]) and np.array_equal(m12, z["bp_m12"])
