@@ -17,6 +17,13 @@
  * the published OpenCV 4.13 algorithms (imgproc resize.cpp fixed-point INTER_LINEAR, features2d
  * fast.cpp / fast_score.cpp, smooth fixed-point Gaussian, core mathfuncs fastAtan2,
  * keypoint.cpp retainBest) and are pinned bit-for-bit against Python cv2 4.13.0 in tests/.
+ * Also restated (the callers either side of the path, SURVEY.md section 8 f): every search routine of src/ORBmatcher.cc
+ * (:43-119, :146-254, :256-357, :359-462, :535-586, :682-708, :734-944, :946-1207, :1209-1304, :1306-1421, :1423-1454),
+ * Frame::GetFeaturesInArea / AssignFeaturesToGrid / UndistortKeyPoints / ComputeStereoFromRGBD (src/Frame.cc), MapPoint::
+ * ComputeDistinctiveDescriptors (src/MapPoint.cc:225-284) and the ORB-SLAM2-style extractor mode.  The reference holds no tests
+ * or vectors for any of them and cannot be built here: the matcher functions are pinned against separately written Python
+ * restatements (tests/search_cases.py) and committed fixtures made from those; the ORB-SLAM2-style mode is PARITY UNPINNED
+ * against ORB-SLAM2 itself (its source is not in this image).
  *
  * Build: g++ -O2 -std=c++17 -ffp-contract=off (see Makefile).  -ffp-contract=off matters: every
  * fused multiply-add the reference's build performs is written as an explicit fmaf() here.
