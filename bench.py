@@ -68,7 +68,20 @@ def stage_bytes_per_frame(geom, nkp):
         # latency-bound stages, listed for completeness (no roofline claim): packed entries in / out
         "select": 8 * nkp,
         "describe": nkp * (749 + 512 + 60),
+        # what a single fused pass could not avoid: the frame in, the pyramid levels 1.. out (imagePyramid is an
+        # output of operator()), keypoints + descriptors out
+        "fused_lower_bound": px[0] + (P - px[0]) + 60 * nkp,
     }
+
+
+def popc_pipe(pairs_per_s_per_gpu, clocks, sms=148, lanes_per_clk_sm=16, popc_per_pair=5):
+    mhz = (clocks or {}).get("sm_mhz") or (clocks or {}).get("sm_max_mhz")
+    if not mhz:
+        return None
+    peak = sms * lanes_per_clk_sm * mhz * 1e6  # popcounts / s
+    return {"popc_per_pair": popc_per_pair, "peak_popc_per_s": peak, "achieved_popc_per_s": pairs_per_s_per_gpu * popc_per_pair,
+            "frac": pairs_per_s_per_gpu * popc_per_pair / peak, "frac_if_8_popc_per_pair": pairs_per_s_per_gpu * 8 / peak,
+            "peak_source": "nominal 16 POPC / clk / SM x 148 SMs x the SM clock sampled in this run"}
 
 
 class ClockSampler:
@@ -519,11 +532,18 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "bytes_per_launch": bytes_per_launch, "avg_launch_ms": avg_launch_s * 1e3,
-                         "frac_of_nominal_8000": achieved / 8000.0, "ncu_profile": ncu_pipes},
+                         "frac_of_nominal_8000": achieved / 8000.0, "ncu_profile": ncu_pipes,
+                         # the whole pipeline against the bytes a single fused pass could not avoid, per GPU
+                         "fused_lower_bound": {"bytes_per_frame": sbytes["fused_lower_bound"],
+                                               "gbs": frames_per_gpu * args.steps / (ms_total_max * 1e-3) * sbytes["fused_lower_bound"] / 1e9,
+                                               "frac": frames_per_gpu * args.steps / (ms_total_max * 1e-3) * sbytes["fused_lower_bound"] / 1e9 / peak}},
             "stages": stages,
             "keypoints_per_frame": mean_kp,
             "hamming": {"value": pairs_per_s, "unit": "pairs/s", "pairs_per_frame_pair": pairs / max(npairs, 1),
                         "frame_pairs_per_gpu": npairs, "ms": float(tm.item()),
+                        # bound: the POPC (XU) pipe, nominally 16 lanes / clk / SM; match_kernel folds the 8 XOR words of a pair
+                        # into 5 popcounts with carry-save adders, the reference's loop needs 8
+                        "popc_pipe": popc_pipe(pairs_per_s / world, clocks),
                         "distinctive_sets_per_s": distinctive_sets_per_s, "distinctive_set_size": 16,
                         "search_for_initialization_frame_pairs_per_s": search_pairs_per_s,
                         "search_for_initialization_matches_per_pair": search_matches},
