@@ -298,7 +298,8 @@ SDORB_API int sdorb_search_by_points_batch(sdorb_handle* h, const sdorb_keypoint
  * similar keypoint inside the radius th * mvScaleFactors[level] whose level is level-1 or level and whose reprojection error
  * passes the chi-square test (:560-580); proj = (u, v, ur), level = PredictScale(...).  best_idx [nframes][capacity_mp] = that
  * keypoint if its distance is <= th_dist (TH_LOW = 50 in the reference), else -1; best_dist the distance (256 = no candidate).
- * Replacing / adding the observation (:588-606) stays with the caller.  scale_factors / inv_level_sigma2: host pointers, nlevels
+ * Replacing / adding the observation (:588-606) stays with the caller, which applies the results in map-point order and evaluates
+ * isBad() / IsInKeyFrame(pKF) (:497) again there: those two are the only checks an earlier iteration's surgery can change.  scale_factors / inv_level_sigma2: host pointers, nlevels
  * entries.  check_reprojection = 0 is the search of the Sim3 overload Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (:682-708, also
  * TH_LOW): no chi-square test; u_right, inv_level_sigma2 and proj[2] are then not read (the pointers may be NULL). */
 typedef struct {

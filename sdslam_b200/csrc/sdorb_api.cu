@@ -35,6 +35,12 @@ struct sdorb_handle {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // the blur runs beside FAST + selection on s_aux
   bool pipe_taper = false;   // host pipeline: shrink the last passes (SDORB_PIPE_TAPER=1; measured: -1.5 %)
   int pipe_growth_pct = 125; // ... and grow the first ones by this factor (SDORB_PIPE_GROWTH, percent)
+  // host pipeline, two compute lanes: odd passes run on a twin handle (own scratch arena, own stream) so that the tail of pass p
+  // (partial last waves of its 13 launches, the small upper pyramid levels) is filled by the start of pass p+1.  SDORB_PIPE_DUAL
+  bool pipe_dual = false;
+  int pipe_const = 0;        // > 0: passes of this many frames after the first (SDORB_PIPE_CONST) instead of the geometric ramp
+  sdorb_handle* twin = nullptr;
+  bool is_twin = false;
   bool overlap = false;  // measured: +0.5 % at best (every kernel here is issue-bound, so co-residency buys nothing); SDORB_OVERLAP=1 enables it
   // geometry of the current image size
   int gw = 0, gh = 0;
@@ -354,6 +360,8 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (const char* e = getenv("SDORB_OVERLAP")) h->overlap = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_TAPER")) h->pipe_taper = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_GROWTH")) h->pipe_growth_pct = std::min(std::max(atoi(e), 101), 1000);
+  if (const char* e = getenv("SDORB_PIPE_DUAL")) h->pipe_dual = e[0] != '0';
+  if (const char* e = getenv("SDORB_PIPE_CONST")) h->pipe_const = std::max(atoi(e), 0);
   if (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   for (int i = 0; i < 2; ++i) {
@@ -373,6 +381,8 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
 
 void sdorb_destroy(sdorb_handle* h) {
   if (!h) return;
+  if (h->twin) sdorb_destroy(h->twin);
+  h->twin = nullptr;
   {
     DeviceGuard guard(h->device);
     if (h->s_compute) cudaStreamSynchronize(h->s_compute);
@@ -492,11 +502,28 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
   int pass = 0;
   const int n_min = std::max(B / 8, 1);
   int ramp = n_min;
+  // two compute lanes (see pipe_dual): staging slot 1 belongs to the twin's scratch arena and stream
+  const bool dual = h->pipe_dual && !h->is_twin && nframes > n_min;
+  if (dual) {
+    if (!h->twin) {
+      sdorb_params p2 = h->prm;
+      p2.device = h->device;
+      rc = sdorb_create(&p2, &h->twin);
+      if (rc) return rc;
+      h->twin->is_twin = true;
+    }
+    h->twin->profiling = h->profiling;
+    rc = ensure_geometry(h->twin, width, height);
+    if (rc) return rc;
+  }
   for (int f0 = 0, n = 0; f0 < nframes; f0 += n, ++pass) {
     const int left = nframes - f0;
     n = h->pipe_taper ? std::min(std::min(ramp, B), std::max((left + 1) / 2, std::min(left, n_min))) : std::min(std::min(ramp, B), left);
     ramp = std::min(std::max(ramp + 1, (int)((int64_t)ramp * h->pipe_growth_pct / 100)), B);
+    if (h->pipe_const > 0) ramp = std::min(h->pipe_const, B);
     const int slot = pass & 1;
+    sdorb_handle* hc = (dual && slot) ? h->twin : h;  // the lane: scratch arena + compute stream
+    cudaStream_t cs = hc->s_compute;
     if (pass >= 2) CU(cudaStreamWaitEvent(h->s_in, h->ev_compute[slot], 0));
     if (frame_stride == row_stride * (size_t)height && row_stride == (size_t)width && (size_t)L0.pitch == row_stride) {
       // contiguous on both sides: one linear copy (a 2D copy of 640-byte rows is issued row by row)
@@ -512,15 +539,18 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
                              h->s_in));
     }
     CU(cudaEventRecord(h->ev_in[slot], h->s_in));
-    CU(cudaStreamWaitEvent(h->s_compute, h->ev_in[slot], 0));
-    if (pass >= 2) CU(cudaStreamWaitEvent(h->s_compute, h->ev_out[slot], 0));
+    CU(cudaStreamWaitEvent(cs, h->ev_in[slot], 0));
+    if (pass >= 2) CU(cudaStreamWaitEvent(cs, h->ev_out[slot], 0));
     BatchPlanes pl{};
     pl.img0 = h->d_stage_in[slot];
     pl.img0_frame_stride = L0.plane_bytes;
     pl.img0_pitch = L0.pitch;
-    rc = enqueue_pass(h, pl, n, h->d_kps[slot], h->d_desc[slot], h->d_counts[slot], capacity, h->s_compute);
-    if (rc) return rc;
-    CU(cudaEventRecord(h->ev_compute[slot], h->s_compute));
+    rc = enqueue_pass(hc, pl, n, h->d_kps[slot], h->d_desc[slot], h->d_counts[slot], capacity, cs);
+    if (rc) {
+      if (hc != h) h->cuda_error = hc->cuda_error;
+      return rc;
+    }
+    CU(cudaEventRecord(h->ev_compute[slot], cs));
     CU(cudaStreamWaitEvent(h->s_out, h->ev_compute[slot], 0));
     CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, h->d_kps[slot], sizeof(sdorb_keypoint) * (size_t)capacity * n,
                        cudaMemcpyDeviceToHost, h->s_out));
@@ -531,6 +561,18 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
   }
   CU(cudaStreamSynchronize(h->s_out));
   CU(cudaStreamSynchronize(h->s_compute));
+  if (dual) {
+    CU(cudaStreamSynchronize(h->twin->s_compute));
+    h->launches += h->twin->launches;
+    for (int i = 0; i < SDORB_NUM_STAGES; ++i) h->stage_launches[i] += h->twin->stage_launches[i], h->twin->stage_launches[i] = 0;
+    h->twin->launches = 0;
+    h->pending.insert(h->pending.end(), h->twin->pending.begin(), h->twin->pending.end());  // stage events of the second lane
+    h->twin->pending.clear();
+    rc = check_deferred(h->twin);
+    if (rc) return rc;
+    if (h->twin->deferred_error && !h->deferred_error) h->deferred_error = h->twin->deferred_error;
+    h->twin->deferred_error = 0;
+  }
   rc = check_deferred(h);
   if (rc) return rc;
   if (h->deferred_error) {

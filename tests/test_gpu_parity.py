@@ -159,6 +159,49 @@ def test_batch_larger_than_max_batch_and_ragged_tail(ex_c1):
     assert_same(ok, od, kps[18, :cnt[18]], desc[18, :cnt[18]])
 
 
+@pytest.mark.parametrize("const", [0, 3])
+def test_two_compute_lanes_equal_one(ex_c1, const, monkeypatch):
+    """Host pipeline with two compute lanes (SDORB_PIPE_DUAL: odd passes on a twin scratch arena and stream): 23 frames through
+    passes of at most 4 frames, geometric and constant pass schedules, byte-identical to the one-lane result, the oracle and the
+    stage accounting of one lane (launch counts, stage events of both lanes)."""
+    base = synth.frames(5, 640, 480, start=90)
+    base[3] = synth.rects(4)
+    imgs = np.concatenate([base] * 5)[:23]
+    monkeypatch.setenv("SDORB_PIPE_DUAL", "0")  # the schedule switches are read when the handle is created
+    monkeypatch.setenv("SDORB_PIPE_CONST", "0")
+    ex1 = api.ORBextractor(*C1, max_width=640, max_height=480, max_batch=4)
+    try:
+        kps, desc, cnt = ex1.extract_batch_host(imgs)
+    finally:
+        ex1.close()
+    monkeypatch.setenv("SDORB_PIPE_DUAL", "1")
+    monkeypatch.setenv("SDORB_PIPE_CONST", str(const))
+    ex2 = api.ORBextractor(*C1, max_width=640, max_height=480, max_batch=4)
+    try:
+        for rep in range(2):  # the second call reuses the twin
+            k2, d2, c2 = ex2.extract_batch_host(imgs)
+            assert np.array_equal(c2, cnt), "call %d" % rep
+            for f in range(len(imgs)):
+                assert k2[f, :cnt[f]].tobytes() == kps[f, :cnt[f]].tobytes() and d2[f, :cnt[f]].tobytes() == desc[f, :cnt[f]].tobytes(), \
+                    "call %d frame %d" % (rep, f)
+        o = orc.Extractor(*C1)
+        for f in (3, 22):
+            ok, od = o.extract(imgs[f])
+            assert_same(ok, od, k2[f, :c2[f]], d2[f, :c2[f]], "frame %d" % f)
+        before = ex2.kernel_launches()
+        ex2.set_profiling(True)
+        ex2.stage_times(reset=True)
+        ex2.extract_batch_host(imgs)
+        ms, launches = ex2.stage_times()
+        ex2.set_profiling(False)
+        npass = launches["fast"]
+        assert npass >= 6 and launches["pyramid"] == 7 * npass and ex2.kernel_launches() - before == 12 * npass
+        assert all(ms[s] > 0 for s in ("pyramid", "fast", "select", "blur", "describe"))
+        ex2(imgs[0], want_pyramid=False)  # the single-frame entry on the same handle afterwards
+    finally:
+        ex2.close()
+
+
 def test_device_entry_point_equals_host_entry_point(ex_c1):
     torch = pytest.importorskip("torch")
     imgs = synth.frames(6, 640, 480, start=80)
