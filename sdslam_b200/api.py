@@ -478,42 +478,53 @@ class ORBextractor:
         return nm, m12
 
     @staticmethod
-    def _fuse_query(proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th, check, th_dist):
-        opt = lambda a: np.ascontiguousarray(a, np.float32) if a is not None else None
-        keep = [np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.uint8),
-                np.ascontiguousarray(desc_mp, np.uint8), np.ascontiguousarray(n_mp, np.int32), np.ascontiguousarray(kps_un),
-                np.ascontiguousarray(desc, np.uint8), opt(u_right),
-                np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32),
-                np.ascontiguousarray(scale_factors, np.float32), opt(inv_level_sigma2)]
+    def _fuse_query(proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th, check, th_dist,
+                    device=False):
+        hostf = lambda a: np.ascontiguousarray(a, np.float32) if a is not None else None
+        if device:  # torch tensors on the handle's GPU, taken as they are; the level tables stay host arrays
+            keep = [proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid[0], grid[1]]
+        else:
+            keep = [np.ascontiguousarray(proj, np.float32), np.ascontiguousarray(level, np.int32), np.ascontiguousarray(flags, np.uint8),
+                    np.ascontiguousarray(desc_mp, np.uint8), np.ascontiguousarray(n_mp, np.int32), np.ascontiguousarray(kps_un),
+                    np.ascontiguousarray(desc, np.uint8), hostf(u_right),
+                    np.ascontiguousarray(grid[0], np.int32), np.ascontiguousarray(grid[1], np.int32)]
+        keep += [hostf(scale_factors), hostf(inv_level_sigma2)]
         ptr = lambda a: _ptr(a) if a is not None else None
         q = _FuseSearch(*[ptr(k) for k in keep[:8]], _FrameGrid(_ptr(keep[8]), _ptr(keep[9]), *[float(v) for v in grid[2:6]]),
                         _ptr(keep[10]), ptr(keep[11]), len(keep[10]), float(th), int(check), int(th_dist))
         return q, keep
 
     def fuse_search_batch(self, proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th,
-                          check_reprojection=True, th_dist=50):
-        """The keypoint search of ORBmatcher::Fuse for a batch of keyframes (host arrays): (best_idx[F, cap_mp], best_dist[F, cap_mp]).
-        check_reprojection=False: the search of the Sim3 overload (u_right / inv_level_sigma2 may be None)."""
+                          check_reprojection=True, th_dist=50, best_idx=None, best_dist=None, device=False, stream=None):
+        """The keypoint search of ORBmatcher::Fuse for a batch of keyframes: (best_idx[F, cap_mp], best_dist[F, cap_mp]).
+        check_reprojection=False: the search of the Sim3 overload (u_right / inv_level_sigma2 may be None).  Host arrays, or with
+        device=True torch tensors on the handle's GPU (best_idx / best_dist are then the caller's int32 tensors)."""
         q, keep = self._fuse_query(proj, level, flags, desc_mp, n_mp, kps_un, desc, u_right, grid, scale_factors, inv_level_sigma2, th,
-                                   check_reprojection, th_dist)
+                                   check_reprojection, th_dist, device)
         F, capmp, cap = keep[1].shape[0], keep[1].shape[1], keep[5].shape[1]
-        bi, bd = np.zeros((F, capmp), np.int32), np.zeros((F, capmp), np.int32)
-        self._check(lib().sdorb_fuse_search_batch(self._h, C.byref(q), F, capmp, cap, _ptr(bi), _ptr(bd), MEM_HOST, None))
-        return bi, bd
+        if not device:
+            best_idx, best_dist = np.zeros((F, capmp), np.int32), np.zeros((F, capmp), np.int32)
+        self._check(lib().sdorb_fuse_search_batch(self._h, C.byref(q), F, capmp, cap, _ptr(best_idx), _ptr(best_dist),
+                                                   MEM_DEVICE if device else MEM_HOST, C.c_void_p(stream) if stream else None))
+        return best_idx, best_dist
 
-    def search_by_sim3_batch(self, side1, side2, scale_factors, th):
-        """ORBmatcher::SearchBySim3 for a batch of keyframe pairs (host arrays).  side = (proj[P, cap, 3], level[P, cap], flags[P, cap],
+    def search_by_sim3_batch(self, side1, side2, scale_factors, th, out=None, device=False, stream=None):
+        """ORBmatcher::SearchBySim3 for a batch of keyframe pairs.  side = (proj[P, cap, 3], level[P, cap], flags[P, cap],
         desc_mp[P, cap, 32], n[P], kps_un[P, cap], desc[P, cap, 32], grid) of that keyframe: its map points projected into the other
-        keyframe, and its own keypoints / descriptors / grid.  Returns (nfound[P], matches12[P, cap], match1, match2)."""
+        keyframe, and its own keypoints / descriptors / grid.  Returns (nfound[P], matches12[P, cap], match1, match2).  Host arrays,
+        or with device=True torch tensors and out = (nfound, matches12, match1, match2) int32 tensors of the caller."""
         p1, l1, f1, m1, n1, k1, d1, g1 = side1
         p2, l2, f2, m2, n2, k2, d2, g2 = side2
-        q12, keep12 = self._fuse_query(p1, l1, f1, m1, n1, k2, d2, None, g2, scale_factors, None, th, 0, 100)
-        q21, keep21 = self._fuse_query(p2, l2, f2, m2, n2, k1, d1, None, g1, scale_factors, None, th, 0, 100)
+        q12, keep12 = self._fuse_query(p1, l1, f1, m1, n1, k2, d2, None, g2, scale_factors, None, th, 0, 100, device)
+        q21, keep21 = self._fuse_query(p2, l2, f2, m2, n2, k1, d1, None, g1, scale_factors, None, th, 0, 100, device)
         P, cap = keep12[1].shape
-        assert keep21[1].shape == (P, cap) and keep12[5].shape[:2] == (P, cap) and keep21[5].shape[:2] == (P, cap)
-        o1, o2, o12, nf = np.zeros((P, cap), np.int32), np.zeros((P, cap), np.int32), np.zeros((P, cap), np.int32), np.zeros(P, np.int32)
+        assert tuple(keep21[1].shape) == (P, cap) and tuple(keep12[5].shape[:2]) == (P, cap) and tuple(keep21[5].shape[:2]) == (P, cap)
+        if device:
+            nf, o12, o1, o2 = out
+        else:
+            o1, o2, o12, nf = np.zeros((P, cap), np.int32), np.zeros((P, cap), np.int32), np.zeros((P, cap), np.int32), np.zeros(P, np.int32)
         self._check(lib().sdorb_search_by_sim3_batch(self._h, C.byref(q12), C.byref(q21), P, cap, _ptr(o1), _ptr(o2), _ptr(o12), _ptr(nf),
-                                                     MEM_HOST, None))
+                                                     MEM_DEVICE if device else MEM_HOST, C.c_void_p(stream) if stream else None))
         return nf, o12, o1, o2
 
     def search_for_triangulation_batch(self, kps1_un, desc1, has_mp1, u_right1, n1, kps2_un, desc2, has_mp2, u_right2, n2, F12, epipole,

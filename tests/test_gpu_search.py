@@ -487,3 +487,56 @@ def test_local_map_loop_golden_fixture(ex):
     nm, m12 = ex.search_by_points_batch(pad(k1), pad(z["bp_d1"], (32,)), pad(z["bp_v1"]), [len(k1)], pad(k2), pad(z["bp_d2"], (32,)),
                                         pad(z["bp_v2"]), [len(k2)], 0.75, True)
     assert nm[0] == int(z["bp_n"]) and np.array_equal(m12[0, :len(k1)], z["bp_m12"])
+
+
+def test_fuse_and_sim3_on_device_memory(ex):
+    """sdorb_fuse_search_batch / sdorb_search_by_sim3_batch with SDORB_MEM_DEVICE (device pointers in and out, caller's stream)
+    equal the host-memory calls."""
+    torch = pytest.importorskip("torch")
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a.view(np.float32).reshape(a.shape + (7,)) if a.dtype == api.KP_DTYPE else a)).to(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    gp = sc.grid_params()
+    sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
+    inv = (np.float32(1) / (sf * sf)).astype(np.float32)
+    frames = []
+    for s, (nf, nmp) in enumerate([(600, 500), (0, 50), (300, 400)]):
+        _, _, kf, df = sc.frame_pair(s + 140, 10, nf, level0=0.3)
+        proj, lvl, fl, ur = sc.fuse_inputs(s, kf, nmp, stereo=True)
+        frames.append((proj, lvl, fl, sc.fuse_descriptors(s, df, nf, nmp), kf, df, ur))
+    cap, capmp = 608, 512
+    col = lambda j, c, dt, tail=(): _slab([f[j] for f in frames], c, dt, tail)
+    kf = col(4, cap, api.KP_DTYPE)
+    nmp = np.array([len(f[0]) for f in frames], np.int32)
+    nf = np.array([len(f[4]) for f in frames], np.int32)
+    cs, idx = ex.assign_grid_batch(kf, nf, *gp)
+    host_args = (col(0, capmp, np.float32, (3,)), col(1, capmp, np.int32), col(2, capmp, np.uint8), col(3, capmp, np.uint8, (32,)), nmp, kf,
+                 col(5, cap, np.uint8, (32,)), col(6, cap, np.float32))
+    bi, bd = ex.fuse_search_batch(*host_args, (cs, idx) + tuple(gp), sf, inv, 3.0)
+    tbi = torch.full((len(frames), capmp), -7, dtype=torch.int32, device=dev)
+    tbd = torch.full((len(frames), capmp), -7, dtype=torch.int32, device=dev)
+    ex.fuse_search_batch(*[t(a) for a in host_args], (t(cs), t(idx)) + tuple(gp), sf, inv, 3.0, best_idx=tbi, best_dist=tbd, device=True,
+                         stream=stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(tbi.cpu().numpy(), bi) and np.array_equal(tbd.cpu().numpy(), bd) and (bi >= 0).sum() > 100
+
+    cases = [sc.sim3_case(s, a, b) for s, (a, b) in enumerate([(500, 520), (0, 100), (300, 200)])]
+    cap = 544
+
+    def side(j, dev_side):
+        ks = _slab([c[j][4] for c in cases], cap, api.KP_DTYPE)
+        n = np.array([len(c[j][4]) for c in cases], np.int32)
+        cs, idx = ex.assign_grid_batch(ks, n, *gp)
+        arrs = [_slab([c[j][0] for c in cases], cap, np.float32, (3,)), _slab([c[j][1] for c in cases], cap, np.int32),
+                _slab([c[j][2] for c in cases], cap, np.uint8), _slab([c[j][3] for c in cases], cap, np.uint8, (32,)), n, ks,
+                _slab([c[j][5] for c in cases], cap, np.uint8, (32,))]
+        if dev_side:
+            return tuple(t(a) for a in arrs) + ((t(cs), t(idx)) + tuple(gp),)
+        return tuple(arrs) + ((cs, idx) + tuple(gp),)
+    nfound, m12, m1, m2 = ex.search_by_sim3_batch(side(0, False), side(1, False), sf, 7.5)
+    out = (torch.zeros(len(cases), dtype=torch.int32, device=dev),) + tuple(
+        torch.full((len(cases), cap), -7, dtype=torch.int32, device=dev) for _ in range(3))
+    ex.search_by_sim3_batch(side(0, True), side(1, True), sf, 7.5, out=out, device=True, stream=stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(out[0].cpu().numpy(), nfound) and np.array_equal(out[1].cpu().numpy(), m12)
+    assert np.array_equal(out[2].cpu().numpy(), m1) and np.array_equal(out[3].cpu().numpy(), m2) and int(nfound.sum()) > 100
