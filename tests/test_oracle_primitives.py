@@ -337,3 +337,20 @@ def test_undistort_keypoints_matches_cv2(cam):
     else:
         exp = [0, 752, 0, 480]
     assert b.tolist() == [float(np.float32(v)) for v in exp]
+
+
+def test_oracle_under_asan_ubsan(tmp_path):
+    """SURVEY.md section 4, row "Sanitizers": the oracle compiled with -fsanitize=address,undefined runs both extractor modes
+    (incl. the reference defaults with their negative cell height, a cornerless and a tiny image), the primitives, every matcher
+    (incl. empty sides) and the Frame post-processing without a report (tests/helpers/oracle_sanitize_driver.cc)."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "orc_san")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-ffp-contract=off", "-pthread", "-fsanitize=address,undefined", "-fno-sanitize-recover=all",
+           "-o", exe, os.path.join(root, "tests", "helpers", "oracle_sanitize_driver.cc"), os.path.join(root, "oracle", "sdorb_oracle.cc"), "-lm"]
+    try:
+        subprocess.check_call(cmd)
+    except (OSError, subprocess.CalledProcessError):
+        pytest.skip("no sanitizer runtime for g++ on this host")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "oracle sanitize run ok" in r.stdout, r.stderr[-4000:]
