@@ -320,11 +320,11 @@ def test_keyframe_projection_overload_on_gpu(ex):
     assert int(nm.sum()) > 100
 
 
-@pytest.mark.parametrize("th,stereo", [(3.0, True), (2.5, False), (4.0, True)])
-def test_fuse_search_equals_oracle(ex, th, stereo):
+@pytest.mark.parametrize("th,stereo,origin", [(3.0, True, None), (2.5, False, None), (4.0, True, (-12.25, -7.5))])
+def test_fuse_search_equals_oracle(ex, th, stereo, origin):
     """sdorb_fuse_search_batch = the keypoint search of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:535-586):
     ragged batch of keyframes incl. empty ones / no map points, duplicate descriptors, reprojection errors on the chi-square
-    limits, descriptor distances on both sides of TH_LOW."""
+    limits, descriptor distances on both sides of TH_LOW; origin: image bounds of a distorted camera (mnMinX, mnMinY < 0)."""
     sizes = [(600, 500, 0.0), (500, 700, 0.0), (300, 200, 0.0), (0, 50, 0.0), (200, 0, 0.0), (700, 900, 0.3), (1, 1, 0.0)]
     frames = []
     for s, (nf, nmp, dup) in enumerate(sizes):
@@ -332,7 +332,7 @@ def test_fuse_search_equals_oracle(ex, th, stereo):
         proj, lvl, fl, ur = sc.fuse_inputs(s, kf, nmp, stereo=stereo)
         frames.append((proj, lvl, fl, sc.fuse_descriptors(s, df, nf, nmp), kf, df, ur))
     cap, capmp = 704, 912
-    gp = sc.grid_params()
+    gp = sc.grid_params() if origin is None else sc.grid_params(667.75, 497.0, *origin)
     sf = (np.float32(1.2) ** np.arange(8)).astype(np.float32)
     inv = (np.float32(1) / (sf * sf)).astype(np.float32)
     col = lambda j, c, dt, tail=(): _slab([f[j] for f in frames], c, dt, tail)
