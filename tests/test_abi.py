@@ -137,3 +137,38 @@ def test_host_image_bounds_equal_oracle():
     for cam, (K4, dist) in CAMERAS.items():
         for cols, rows in ((640, 480), (752, 480)):
             assert api.host_image_bounds(cols, rows, K4, dist).tobytes() == orc.image_bounds(cols, rows, K4, dist).tobytes(), cam
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """Every struct of include/sdorb.h against its ctypes / numpy mirror in sdslam_b200/api.py: sizeof and the offset of every
+    field, taken from a C program compiled against the header (gcc, the C ABI of this platform)."""
+    import ctypes as C
+    import subprocess
+    import numpy as np
+    from sdslam_b200 import api
+    pairs = {"sdorb_params": api._Params, "sdorb_pyr_view": api._PyrView, "sdorb_frame_grid": api._FrameGrid,
+             "sdorb_projection_search": api._ProjectionSearch, "sdorb_map_point_search": api._MapPointSearch,
+             "sdorb_fuse_search": api._FuseSearch, "sdorb_triangulation_search": api._TriangulationSearch}
+    dtypes = {"sdorb_keypoint": api.KP_DTYPE, "sdorb_match": api.MATCH_DTYPE, "sdorb_level_geom": api.GEOM_DTYPE}
+    lines = []
+    for cname, cls in pairs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    for cname, dt in dtypes.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for fname in dt.names:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, fname, cname, fname))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "sdorb.h"\nint main(void) {\n%s\nreturn 0; }\n' % "\n".join(lines))
+    exe = str(tmp_path / "layout")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", exe, str(src)])
+    got = dict(l.split() for l in subprocess.check_output([exe], text=True).splitlines())
+    for cname, cls in pairs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, fname)]) == getattr(cls, fname).offset, "%s.%s" % (cname, fname)
+    for cname, dt in dtypes.items():
+        assert int(got[cname]) == dt.itemsize, cname
+        for fname in dt.names:
+            assert int(got["%s.%s" % (cname, fname)]) == dt.fields[fname][1], "%s.%s" % (cname, fname)
