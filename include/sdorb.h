@@ -42,6 +42,10 @@ extern "C" {
 #define SDORB_ERR_OVERFLOW (-6)  /* an internal fixed-capacity list overflowed (results invalid) */
 #define SDORB_ERR_UNSUPPORTED (-7)
 
+/* largest batch (frames / frame pairs per call) of the entry points that say so below; larger requests return
+ * SDORB_ERR_BAD_ARG -- split them into several calls */
+#define SDORB_MAX_GRID_BATCH 65535
+
 /* where the image / result buffers of a batch call live */
 #define SDORB_MEM_HOST 0   /* host memory: the call copies in and out and returns when results are on the host */
 #define SDORB_MEM_DEVICE 1 /* device memory of the handle's GPU: the call only enqueues work on `stream` */
@@ -174,7 +178,7 @@ SDORB_API int sdorb_assign_grid_batch(sdorb_handle* h, const sdorb_keypoint* key
 /* sdorb_undistort_keypoints_batch = Frame::UndistortKeyPoints (src/Frame.cc:335-366), i.e. cv::undistortPoints(pts, K, dist,
  * noArray(), K) as OpenCV 4.13 computes it, applied to pt of every keypoint (all other fields copied).  K = {fx, fy, cx, cy}
  * and dist = {k1, k2, p1, p2[, k3]} are the float values the reference passes (host pointers, 4 and ndist <= 12 entries);
- * dist[0] == 0 copies the keypoints (src/Frame.cc:336-339).  out may alias keypoints. */
+ * dist[0] == 0 copies the keypoints (src/Frame.cc:336-339).  out may alias keypoints.  nframes <= SDORB_MAX_GRID_BATCH. */
 SDORB_API int sdorb_undistort_keypoints_batch(sdorb_handle* h, const sdorb_keypoint* keypoints, const int32_t* counts, int nframes,
                                     int capacity, const float* K, const float* dist, int ndist, sdorb_keypoint* out, int mem,
                                     void* stream);
@@ -182,7 +186,7 @@ SDORB_API int sdorb_undistort_keypoints_batch(sdorb_handle* h, const sdorb_keypo
 SDORB_API int sdorb_host_image_bounds(int cols, int rows, const float* K, const float* dist, int ndist, float* bounds);
 /* sdorb_stereo_from_rgbd_batch = Frame::ComputeStereoFromRGBD (src/Frame.cc:399-417): d = depth(v, u) at the truncated
  * keypoint position; d > 0: z = d and u_right = x_undistorted - mbf / d, else both -1.  depth: float32 images, row /
- * frame strides in ELEMENTS; u_right, z: [nframes][capacity] (entries beyond counts[f] are set to -1). */
+ * frame strides in ELEMENTS; u_right, z: [nframes][capacity] (entries beyond counts[f] are set to -1).  nframes <= SDORB_MAX_GRID_BATCH. */
 SDORB_API int sdorb_stereo_from_rgbd_batch(sdorb_handle* h, const sdorb_keypoint* keypoints, const sdorb_keypoint* keypoints_un,
                                  const int32_t* counts, int nframes, int capacity, const float* depth, int width, int height,
                                  size_t depth_row_stride, size_t depth_frame_stride, float mbf, float* u_right, float* z,
@@ -308,7 +312,7 @@ typedef struct {
   const uint8_t* flags;    /* [nframes][capacity_mp] */
   const uint8_t* desc_mp;  /* [nframes][capacity_mp][32] */
   const int32_t* n_mp;     /* [nframes] */
-  const sdorb_keypoint* kps_un; /* [nframes][capacity] */
+  const sdorb_keypoint* kps_un; /* [nframes][capacity]  nframes <= SDORB_MAX_GRID_BATCH. */
   const uint8_t* desc;
   const float* u_right;
   sdorb_frame_grid grid;
@@ -328,7 +332,7 @@ SDORB_API int sdorb_fuse_search_batch(sdorb_handle* h, const sdorb_fuse_search* 
  * keypoints / descriptors / grid / scale factors the struct carries; q21 the reverse direction (:848-925).  Both searches run without
  * the reprojection gate (check_reprojection must be 0) against TH_HIGH (th_dist is ignored).  match1 / match2 [npairs][capacity] =
  * vnMatch1 / vnMatch2; matches12[i1] = idx2 whose map point the agreement check (:927-941) puts into vpMatches12[i1], else -1;
- * nfound [npairs] the return values. */
+ * nfound [npairs] the return values.  npairs <= SDORB_MAX_GRID_BATCH. */
 SDORB_API int sdorb_search_by_sim3_batch(sdorb_handle* h, const sdorb_fuse_search* q12, const sdorb_fuse_search* q21, int npairs,
                                          int capacity, int32_t* match1, int32_t* match2, int32_t* matches12, int32_t* nfound, int mem,
                                          void* stream);

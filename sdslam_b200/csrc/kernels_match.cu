@@ -28,10 +28,11 @@ __global__ void __launch_bounds__(M_THREADS) match_kernel(const uint8_t* __restr
                                                           const int32_t* __restrict__ nB, int strideB, float ratio,
                                                           int th_low, MatchOut* __restrict__ out) {
   __shared__ uint4 s_b[M_TILE * 2];
-  const int pair = blockIdx.y;
-  const int na = nA[pair], nb = nB[pair];
-  const int qi = blockIdx.x * M_THREADS + threadIdx.x;
-  if (blockIdx.x * M_THREADS >= na) return;
+  const int pair = blockIdx.x;  // the batch index lives on gridDim.x (2^31 - 1), the query block on gridDim.y
+  // device-resident counts are clamped to the slab like the guided-search kernels do (the host form validates them)
+  const int na = min(max(nA[pair], 0), strideA), nb = min(max(nB[pair], 0), strideB);
+  const int qi = blockIdx.y * M_THREADS + threadIdx.x;
+  if (blockIdx.y * M_THREADS >= na) return;
   const bool active = qi < na;
   uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (active) {
@@ -76,7 +77,7 @@ __global__ void __launch_bounds__(32) match_greedy_kernel(const uint8_t* __restr
                                                           int th_low, MatchOut* __restrict__ out) {
   extern __shared__ uint32_t s_matched[];  // bitset over train rows
   const int pair = blockIdx.x, lane = threadIdx.x;
-  const int na = nA[pair], nb = nB[pair];
+  const int na = min(max(nA[pair], 0), strideA), nb = min(max(nB[pair], 0), strideB);  // s_matched is sized from strideB
   for (int i = lane; i < (nb + 31) / 32; i += 32) s_matched[i] = 0;
   __syncwarp();
   const uint4* bsrc = reinterpret_cast<const uint4*>(B + (int64_t)pair * strideB * 32);
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(32) match_greedy_kernel(const uint8_t* __restr
 __global__ void __launch_bounds__(256) hamming_matrix_kernel(const uint8_t* __restrict__ A, int nA,
                                                              const uint8_t* __restrict__ B, int nB,
                                                              uint16_t* __restrict__ out) {
-  const int j = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+  const int j = blockIdx.y * 256 + threadIdx.x, i = blockIdx.x;  // rows of A on gridDim.x: no 65535 limit
   if (j >= nB) return;
   const uint4* qa = reinterpret_cast<const uint4*>(A + (int64_t)i * 32);
   const uint4 lo = qa[0], hi = qa[1];
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(D_THREADS) distinctive_kernel(const uint8_t* _
   __shared__ uint16_t s_hist[D_THREADS][258];  // pitch 258 halfwords = 129 words: threads start in different banks
   __shared__ int s_best[D_THREADS / 32];
   const int set = blockIdx.x, tid = threadIdx.x;
-  const int first = offsets[set], n = offsets[set + 1] - first;
+  const int first = offsets[set], n = min(offsets[set + 1] - first, 65535);  // uint16 bins and (median << 16 | row) hold 65535 rows
   if (n <= 0) {
     if (tid == 0) {
       best_idx[set] = -1;
@@ -185,7 +186,7 @@ void launch_distinctive(const uint8_t* desc, const int32_t* offsets, int nsets, 
 void launch_match(const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* B, const int32_t* nB, int strideB,
                   int npairs, float ratio, int th_low, void* out, cudaStream_t s) {
   if (npairs <= 0 || strideA <= 0) return;
-  dim3 grid((strideA + M_THREADS - 1) / M_THREADS, npairs);
+  dim3 grid(npairs, (strideA + M_THREADS - 1) / M_THREADS);
   match_kernel<<<grid, M_THREADS, 0, s>>>(A, nA, strideA, B, nB, strideB, ratio, th_low, (MatchOut*)out);
 }
 
@@ -198,7 +199,7 @@ void launch_match_greedy(const uint8_t* A, const int32_t* nA, int strideA, const
 
 void launch_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out, cudaStream_t s) {
   if (nA <= 0 || nB <= 0) return;
-  hamming_matrix_kernel<<<dim3((nB + 255) / 256, nA), 256, 0, s>>>(A, nA, B, nB, out);
+  hamming_matrix_kernel<<<dim3(nA, (nB + 255) / 256), 256, 0, s>>>(A, nA, B, nB, out);
 }
 
 }  // namespace sdorb

@@ -301,6 +301,9 @@ int check_deferred(sdorb_handle* h) {
 
 bool aligned16(const void* p, size_t a, size_t b) { return ((uintptr_t)p % 16 == 0) && (a % 16 == 0) && (b % 16 == 0); }
 
+int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height, size_t row_stride,
+                  size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int capacity);
+
 }  // namespace
 
 extern "C" {
@@ -499,6 +502,27 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
   // 4096-frame call; tapering the last passes costs more in small-pass efficiency than the shorter last download saves.
   rc = ensure_host_staging(h, capacity);
   if (rc) return rc;
+  // Any failure after the first enqueue leaves copies into / out of the caller's buffers in flight on three (four) streams:
+  // drain them before the error is returned, so that the caller may free or reuse its buffers right away.
+  rc = host_pipeline(h, images, nframes, width, height, row_stride, frame_stride, keypoints, descriptors, counts, capacity);
+  if (rc) {
+    cudaStreamSynchronize(h->s_in);
+    cudaStreamSynchronize(h->s_compute);
+    cudaStreamSynchronize(h->s_out);
+    if (h->twin) cudaStreamSynchronize(h->twin->s_compute);
+    cudaGetLastError();
+  }
+  return rc;
+}
+
+}  // extern "C"
+
+namespace {
+int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height, size_t row_stride,
+                  size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int capacity) {
+  const int B = h->prm.max_batch;
+  const LevelGeom& L0 = h->geom.lv[0];
+  int rc = SDORB_OK;
   int pass = 0;
   const int n_min = std::max(B / 8, 1);
   int ramp = n_min;
@@ -582,6 +606,10 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
   }
   return SDORB_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 void sdorb_fill_border_reflect101(uint8_t* origin, int width, int height, size_t stride, int border) {
   if (!origin || width <= 0 || height <= 0 || border <= 0) return;
@@ -696,6 +724,46 @@ int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, 
   return SDORB_OK;
 }
 
+namespace {
+// scratch for the host-memory forms of the small batched entry points: one growing device buffer, carved by the caller
+int ensure_match_buf(sdorb_handle* h, size_t need) {
+  if (need > h->match_buf_bytes) {
+    if (h->d_match_buf) cudaFree(h->d_match_buf);
+    h->d_match_buf = nullptr;
+    h->match_buf_bytes = 0;
+    CU(cudaMalloc(&h->d_match_buf, need));
+    h->match_buf_bytes = need;
+  }
+  return SDORB_OK;
+}
+size_t up256(size_t v) { return (v + 255) / 256 * 256; }
+// Lays the host arrays of one call out in the handle's scratch buffer: sizes first, then copies.
+struct Stager {
+  struct Item { const void* host_in; void* host_out; size_t bytes, off; };
+  std::vector<Item> items;
+  size_t total = 0;
+  size_t add(const void* in, void* out, size_t bytes) {
+    items.push_back({in, out, bytes, total});
+    total += up256(bytes);
+    return items.size() - 1;
+  }
+  uint8_t* dev(sdorb_handle* h, size_t i) const { return (uint8_t*)h->d_match_buf + items[i].off; }
+  int upload(sdorb_handle* h, cudaStream_t s) {
+    int rc = ensure_match_buf(h, total);
+    if (rc) return rc;
+    for (auto& it : items)
+      if (it.host_in) CU(cudaMemcpyAsync((uint8_t*)h->d_match_buf + it.off, it.host_in, it.bytes, cudaMemcpyHostToDevice, s));
+    return SDORB_OK;
+  }
+  int download(sdorb_handle* h, cudaStream_t s) {
+    for (auto& it : items)
+      if (it.host_out) CU(cudaMemcpyAsync(it.host_out, (uint8_t*)h->d_match_buf + it.off, it.bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return SDORB_OK;
+  }
+};
+}  // namespace
+
 static int match_common(sdorb_handle* h, const uint8_t* A, const int32_t* nA, int strideA, const uint8_t* Bm,
                         const int32_t* nB, int strideB, int npairs, float ratio, int th_low, sdorb_match* out, int mem,
                         void* stream, bool greedy) {
@@ -712,16 +780,9 @@ static int match_common(sdorb_handle* h, const uint8_t* A, const int32_t* nA, in
   if (mem == SDORB_MEM_HOST) {
     for (int p = 0; p < npairs; ++p)
       if (nA[p] < 0 || nA[p] > strideA || nB[p] < 0 || nB[p] > strideB) return SDORB_ERR_BAD_ARG;
-    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-    const size_t need = up(bytesA) + up(bytesB) + 2 * up(bytesN) + up(bytesO);
-    if (need > h->match_buf_bytes) {
-      if (h->d_match_buf) cudaFree(h->d_match_buf);
-    if (h->h_pyr) cudaFreeHost(h->h_pyr);
-      h->d_match_buf = nullptr;
-      h->match_buf_bytes = 0;
-      CU(cudaMalloc(&h->d_match_buf, need));
-      h->match_buf_bytes = need;
-    }
+    auto up = up256;
+    const int rcb = ensure_match_buf(h, up(bytesA) + up(bytesB) + 2 * up(bytesN) + up(bytesO));
+    if (rcb) return rcb;
     uint8_t* base = (uint8_t*)h->d_match_buf;
     uint8_t* pA = base;
     uint8_t* pB = pA + up(bytesA);
@@ -782,32 +843,19 @@ int sdorb_hamming_matrix(sdorb_handle* h, const uint8_t* A, int nA, const uint8_
     CU(cudaGetLastError());
     return SDORB_OK;
   }
-  uint8_t *dA = nullptr, *dB = nullptr;
-  uint16_t* dO = nullptr;
-  CU(cudaMalloc(&dA, (size_t)nA * 32));
-  CU(cudaMalloc(&dB, (size_t)nB * 32));
-  CU(cudaMalloc(&dO, sizeof(uint16_t) * (size_t)nA * nB));
-  int rc = SDORB_OK;
-  auto step = [&](cudaError_t e) {
-    if (e != cudaSuccess && rc == SDORB_OK) {
-      h->cuda_error = cudaGetErrorString(e);
-      rc = SDORB_ERR_CUDA;
-    }
-  };
-  step(cudaMemcpyAsync(dA, A, (size_t)nA * 32, cudaMemcpyHostToDevice, s));
-  step(cudaMemcpyAsync(dB, Bm, (size_t)nB * 32, cudaMemcpyHostToDevice, s));
+  // host form: staged through the handle's scratch buffer (no allocation per call; DescriptorDistance calls this per pair)
+  Stager st;
+  const size_t iA = st.add(A, nullptr, (size_t)nA * 32), iB = st.add(Bm, nullptr, (size_t)nB * 32);
+  const size_t iO = st.add(nullptr, out, sizeof(uint16_t) * (size_t)nA * nB);
+  int rc = st.upload(h, s);
+  if (rc) return rc;
   {
-    StageScope st(h, s, SDORB_STAGE_MATCH);
-    launch_hamming_matrix(dA, nA, dB, nB, dO, s);
-    st.launched();
+    StageScope sc(h, s, SDORB_STAGE_MATCH);
+    launch_hamming_matrix(st.dev(h, iA), nA, st.dev(h, iB), nB, (uint16_t*)st.dev(h, iO), s);
+    sc.launched();
   }
-  step(cudaGetLastError());
-  step(cudaMemcpyAsync(out, dO, sizeof(uint16_t) * (size_t)nA * nB, cudaMemcpyDeviceToHost, s));
-  step(cudaStreamSynchronize(s));
-  cudaFree(dA);
-  cudaFree(dB);
-  cudaFree(dO);
-  return rc;
+  CU(cudaGetLastError());
+  return st.download(h, s);
 }
 
 int sdorb_distinctive_batch(sdorb_handle* h, const uint8_t* desc, const int32_t* offsets, int nsets, int32_t* best_idx,
@@ -829,15 +877,9 @@ int sdorb_distinctive_batch(sdorb_handle* h, const uint8_t* desc, const int32_t*
     if (offsets[i] < 0 || offsets[i + 1] < offsets[i] || offsets[i + 1] - offsets[i] > 65535) return SDORB_ERR_BAD_ARG;
   const size_t rows = (size_t)offsets[nsets], bD = std::max<size_t>(rows * 32, 32), bO = sizeof(int32_t) * ((size_t)nsets + 1),
                bR = sizeof(int32_t) * (size_t)nsets;
-  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-  const size_t need = up(bD) + up(bO) + 2 * up(bR);
-  if (need > h->match_buf_bytes) {
-    if (h->d_match_buf) cudaFree(h->d_match_buf);
-    h->d_match_buf = nullptr;
-    h->match_buf_bytes = 0;
-    CU(cudaMalloc(&h->d_match_buf, need));
-    h->match_buf_bytes = need;
-  }
+  auto up = up256;
+  const int rcb = ensure_match_buf(h, up(bD) + up(bO) + 2 * up(bR));
+  if (rcb) return rcb;
   uint8_t* pD = (uint8_t*)h->d_match_buf;
   int32_t* pO = (int32_t*)(pD + up(bD));
   int32_t* pI = (int32_t*)((uint8_t*)pO + up(bO));
@@ -855,21 +897,6 @@ int sdorb_distinctive_batch(sdorb_handle* h, const uint8_t* desc, const int32_t*
   CU(cudaStreamSynchronize(s));
   return SDORB_OK;
 }
-
-namespace {
-// scratch for the host-memory forms of the small batched entry points: one growing device buffer, carved by the caller
-int ensure_match_buf(sdorb_handle* h, size_t need) {
-  if (need > h->match_buf_bytes) {
-    if (h->d_match_buf) cudaFree(h->d_match_buf);
-    h->d_match_buf = nullptr;
-    h->match_buf_bytes = 0;
-    CU(cudaMalloc(&h->d_match_buf, need));
-    h->match_buf_bytes = need;
-  }
-  return SDORB_OK;
-}
-size_t up256(size_t v) { return (v + 255) / 256 * 256; }
-}  // namespace
 
 int sdorb_assign_grid_batch(sdorb_handle* h, const sdorb_keypoint* kps, const int32_t* counts, int nframes, int capacity,
                             float min_x, float min_y, float inv_w, float inv_h, int32_t* cell_start, int32_t* indices, int mem,
@@ -913,31 +940,6 @@ int sdorb_assign_grid_batch(sdorb_handle* h, const sdorb_keypoint* kps, const in
 
 // ---- guided matchers -------------------------------------------------------------------------------------------------
 namespace {
-// Lays the host arrays of one call out in the handle's scratch buffer: sizes first, then copies.
-struct Stager {
-  struct Item { const void* host_in; void* host_out; size_t bytes, off; };
-  std::vector<Item> items;
-  size_t total = 0;
-  size_t add(const void* in, void* out, size_t bytes) {
-    items.push_back({in, out, bytes, total});
-    total += up256(bytes);
-    return items.size() - 1;
-  }
-  uint8_t* dev(sdorb_handle* h, size_t i) const { return (uint8_t*)h->d_match_buf + items[i].off; }
-  int upload(sdorb_handle* h, cudaStream_t s) {
-    int rc = ensure_match_buf(h, total);
-    if (rc) return rc;
-    for (auto& it : items)
-      if (it.host_in) CU(cudaMemcpyAsync((uint8_t*)h->d_match_buf + it.off, it.host_in, it.bytes, cudaMemcpyHostToDevice, s));
-    return SDORB_OK;
-  }
-  int download(sdorb_handle* h, cudaStream_t s) {
-    for (auto& it : items)
-      if (it.host_out) CU(cudaMemcpyAsync(it.host_out, (uint8_t*)h->d_match_buf + it.off, it.bytes, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
-    return SDORB_OK;
-  }
-};
 const int kSearchMaxCapacity = 16384;
 }  // namespace
 
@@ -1206,7 +1208,9 @@ int sdorb_fuse_search_batch(sdorb_handle* h, const sdorb_fuse_search* q, int nfr
                             int32_t* best_dist, int mem, void* stream) {
   if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
   if (nframes == 0) return SDORB_OK;
-  if (!FuseStage::valid(q, capacity_mp, capacity) || !best_idx || !best_dist || q->th_dist < 0 || q->th_dist > 256) return SDORB_ERR_BAD_ARG;
+  if (!FuseStage::valid(q, capacity_mp, capacity) || !best_idx || !best_dist || q->th_dist < 0 || q->th_dist > 256 ||
+      nframes > SDORB_MAX_GRID_BATCH)
+    return SDORB_ERR_BAD_ARG;
   DeviceGuard guard(h->device);
   cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
   FuseSearchArgs a;
@@ -1241,7 +1245,7 @@ int sdorb_search_by_sim3_batch(sdorb_handle* h, const sdorb_fuse_search* q12, co
   if (!h || npairs < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
   if (npairs == 0) return SDORB_OK;
   if (!FuseStage::valid(q12, capacity, capacity) || !FuseStage::valid(q21, capacity, capacity) || q12->check_reprojection ||
-      q21->check_reprojection || !match1 || !match2 || !matches12 || !nfound)
+      q21->check_reprojection || !match1 || !match2 || !matches12 || !nfound || npairs > SDORB_MAX_GRID_BATCH)
     return SDORB_ERR_BAD_ARG;
   DeviceGuard guard(h->device);
   cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
@@ -1350,7 +1354,8 @@ int sdorb_undistort_keypoints_batch(sdorb_handle* h, const sdorb_keypoint* kps, 
                                     const float* K, const float* dist, int ndist, sdorb_keypoint* out, int mem, void* stream) {
   if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
   if (nframes == 0) return SDORB_OK;
-  if (!kps || !counts || !out || !K || capacity <= 0 || ndist < 0 || ndist > 12 || (ndist > 0 && !dist)) return SDORB_ERR_BAD_ARG;
+  if (!kps || !counts || !out || !K || capacity <= 0 || ndist < 0 || ndist > 12 || (ndist > 0 && !dist) || nframes > SDORB_MAX_GRID_BATCH)
+    return SDORB_ERR_BAD_ARG;
   DeviceGuard guard(h->device);
   cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;
   if (mem == SDORB_MEM_DEVICE) {
@@ -1387,7 +1392,8 @@ int sdorb_stereo_from_rgbd_batch(sdorb_handle* h, const sdorb_keypoint* kps, con
   if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
   if (nframes == 0) return SDORB_OK;
   if (!kps || !kps_un || !counts || !depth || !u_right || !z || capacity <= 0 || width <= 0 || height <= 0 ||
-      row_stride < (size_t)width || (nframes > 1 && frame_stride < row_stride * (size_t)(height - 1) + (size_t)width))
+      row_stride < (size_t)width || (nframes > 1 && frame_stride < row_stride * (size_t)(height - 1) + (size_t)width) ||
+      nframes > SDORB_MAX_GRID_BATCH)
     return SDORB_ERR_BAD_ARG;
   DeviceGuard guard(h->device);
   cudaStream_t s = (mem == SDORB_MEM_DEVICE && stream) ? (cudaStream_t)stream : h->s_compute;

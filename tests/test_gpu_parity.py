@@ -371,6 +371,56 @@ def test_pyramid_output_has_reflect101_border(ex_c1):
     assert np.array_equal(pyr[0], img)
 
 
+def test_pyramid_then_match_then_pyramid_on_one_handle():
+    """The reference's sequence on ONE handle (ORBdistance shares the extractor's): operator() with imagePyramid, a host-memory
+    match that has to grow the matcher scratch, operator() with imagePyramid again.  The pinned pyramid staging buffer must
+    survive the matcher's reallocation (round-1 advisor finding: it was freed there and then used and freed again)."""
+    ex = api.ORBextractor(*C1, max_width=640, max_height=480, max_batch=2)
+    o = orc.Extractor(*C1)
+    imgs = [synth.smooth_noise(120), synth.rects(121)]
+    k0, d0, pyr0 = ex(imgs[0])
+    k1, d1, _ = ex(imgs[1])
+    for grow in (1, 3, 9):  # each call needs a larger scratch buffer than the one before
+        A = np.repeat(d0[None], grow, axis=0)
+        Bm = np.repeat(d1[None], grow, axis=0)
+        nA = np.full(grow, len(d0), np.int32)
+        nB = np.full(grow, len(d1), np.int32)
+        m = ex.match_batch(A, nA, Bm, nB)
+        assert m[0, :len(d0)].tobytes() == orc.match_best2(d0, d1).tobytes()
+        assert ex.hamming_matrix(d0[:50 * grow], d1[:40 * grow]).tobytes() == orc.hamming_matrix(d0[:50 * grow], d1[:40 * grow]).tobytes()
+        for img in imgs:
+            k, d, pyr = ex(img)
+            ok, od, st = o.extract(img, dump=True)
+            assert_same(ok, od, k, d, "after match (grow %d)" % grow)
+            off = 0
+            for l, g in enumerate(st["geometry"]):
+                w, h = int(g["width"]), int(g["height"])
+                assert np.array_equal(pyr[l], st["pyramid"][off:off + w * h].reshape(h, w)), "pyramid level %d after match" % l
+                assert np.array_equal(pyr[l].base, orc.border_reflect101(np.ascontiguousarray(pyr[l]), 19))
+                off += w * h
+    ex.close()
+
+
+def test_oversized_batches_are_rejected(ex_c1):
+    """Entry points whose batch index rides on gridDim.y refuse more than SDORB_MAX_GRID_BATCH frames up front."""
+    n = 65536
+    kps = np.zeros((n, 1), api.KP_DTYPE)
+    cnt = np.zeros(n, np.int32)
+    with pytest.raises(api.SdorbError) as e:
+        ex_c1.undistort_keypoints_batch(kps, cnt, (500., 500., 320., 240.), (0.1, 0., 0., 0.))
+    assert e.value.code == -1  # SDORB_ERR_BAD_ARG
+    # the matcher's batch index is on gridDim.x: 70000 tiny pairs in one call
+    npairs = 70000
+    rng = np.random.default_rng(3)
+    A = rng.integers(0, 256, (npairs, 2, 32), dtype=np.uint8)
+    Bm = rng.integers(0, 256, (npairs, 3, 32), dtype=np.uint8)
+    nA = np.full(npairs, 2, np.int32)
+    nB = np.full(npairs, 3, np.int32)
+    got = ex_c1.match_batch(A, nA, Bm, nB)
+    exp = orc.match_many(A, nA, Bm, nB)
+    assert got.tobytes() == exp.tobytes()
+
+
 # ------------------------------------------------------------------ the selection order: device nth_element vs libstdc++
 def _std_nth_element(entries, nth):
     """Ground truth from the real std::nth_element (oracle retainBest with n = nth + 1 keeps the arrangement of the
