@@ -1,0 +1,166 @@
+"""ctypes binding of oracle/_ref/libsdorb_ref.so: the reference's OWN sources (/root/reference/src/ORBextractor.cc, unmodified,
+and ORBmatcher::DescriptorDistance) compiled against oracle/ref_compat by oracle/ref_build/Makefile.
+
+TEST INFRASTRUCTURE ONLY: loaded by tests/ (to pin the oracle restatement and to generate tests/golden/), by
+__graft_entry__.build() (building the checker is not using it) and by bench.py's CPU legs (cpu_baseline kind "reference").
+/root/reference exists only in the build container: on the GPU box the prebuilt .so that travelled with the snapshot is used.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle.binding import KP_DTYPE
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_DIR = os.path.join(_HERE, "_ref")
+SO = os.path.join(_DIR, "libsdorb_ref.so")
+SO_NATIVE = os.path.join(_DIR, "libsdorb_ref_native.so")
+REFERENCE = os.environ.get("SDORB_REFERENCE", "/root/reference")
+
+
+def reference_present():
+    return os.path.exists(os.path.join(REFERENCE, "src", "ORBextractor.cc"))
+
+
+def build(force=False):
+    """(Re)build oracle/_ref when the reference sources are present; otherwise the prebuilt library must already be there."""
+    if reference_present():
+        cmd = ["make", "-C", os.path.join(_HERE, "ref_build"), "-s", "REF=" + REFERENCE]
+        if force:
+            subprocess.check_call(cmd + ["clean"])
+        subprocess.check_call(cmd)
+    return SO if os.path.exists(SO) else None
+
+
+def available():
+    return os.path.exists(SO) or (reference_present() and build() is not None)
+
+
+def _native_runs_here():
+    """libsdorb_ref_native.so was compiled with -march=native on the build machine: only load it where every CPU flag of that
+    machine is present."""
+    f = os.path.join(_DIR, "native_cpu_flags.txt")
+    if not (os.path.exists(SO_NATIVE) and os.path.exists(f)):
+        return False
+    try:
+        built = set(open(f).read().split())
+        with open("/proc/cpuinfo") as c:
+            here = set(next(l for l in c if l.startswith("flags")).split(":", 1)[1].split())
+    except Exception:
+        return False
+    return built <= here
+
+
+_libs = {}
+
+
+def lib(native=False):
+    path = SO_NATIVE if native else SO
+    if path not in _libs:
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        vp, i, f, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+        L.ref_create.restype = vp
+        L.ref_create.argtypes = [i, f, i, i]
+        L.ref_destroy.argtypes = [vp]
+        L.ref_get_tables.argtypes = [vp] * 10
+        L.ref_extract.restype = i
+        L.ref_extract.argtypes = [vp, vp, i, i, sz, vp, vp, i, vp, vp]
+        L.ref_extract_many.restype = C.c_long
+        L.ref_extract_many.argtypes = [vp, vp, i, i, i, i, vp, vp, vp, i]
+        L.ref_descriptor_distance.restype = i
+        L.ref_descriptor_distance.argtypes = [vp, vp]
+        L.ref_hamming_matrix.argtypes = [vp, i, vp, i, vp]
+        _libs[path] = L
+    return _libs[path]
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class Extractor:
+    """SD_SLAM::ORBextractor(nfeatures, scaleFactor, nlevels, thFAST) of the reference itself."""
+
+    def __init__(self, nfeatures=1000, scale_factor=1.2, nlevels=8, th_fast=20, native=False):
+        self._lib = lib(native)
+        self.nfeatures, self.nlevels = nfeatures, nlevels
+        self._h = self._lib.ref_create(nfeatures, scale_factor, nlevels, th_fast)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.ref_destroy(self._h)
+            self._h = None
+
+    def tables(self):
+        n = self.nlevels
+        nl, sf = C.c_int(), C.c_float()
+        a, b, c, d = (np.empty(n, np.float32) for _ in range(4))
+        npl, umax, pat = np.empty(n, np.int32), np.empty(16, np.int32), np.empty(1024, np.int32)
+        self._lib.ref_get_tables(self._h, C.addressof(nl), C.addressof(sf), _p(a), _p(b), _p(c), _p(d), _p(npl), _p(umax), _p(pat))
+        return dict(nlevels=nl.value, scale_factor=sf.value, scale=a, inv_scale=b, sigma2=c, inv_sigma2=d, n_per_level=npl,
+                    umax=umax, pattern=pat.reshape(512, 2))
+
+    def level_sizes(self, w, h):
+        inv = self.tables()["inv_scale"]
+        # src/ORBextractor.cc:683: cvRound((float)cols * scale); np.rint is round-half-even like cvRound
+        return [(int(np.rint(np.float32(w) * s)), int(np.rint(np.float32(h) * s))) for s in inv]
+
+    def _cap(self):
+        return max(int(self.tables()["n_per_level"].sum()), self.nfeatures, 1)
+
+    def extract(self, img, pyramid=False):
+        """(kps, desc) or (kps, desc, [level arrays], [padded level arrays]); raises where the reference throws cv::Exception."""
+        img = np.asarray(img)
+        assert img.dtype == np.uint8 and img.ndim == 2 and (img.size == 0 or img.strides[1] == 1)
+        h, w = img.shape
+        cap = self._cap()
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        tight = padded = None
+        if pyramid:
+            sizes = self.level_sizes(w, h)
+            tight = np.zeros(sum(a * b for a, b in sizes), np.uint8)
+            padded = np.zeros(sum((a + 38) * (b + 38) for a, b in sizes), np.uint8)
+        n = self._lib.ref_extract(self._h, _p(img), w, h, img.strides[0], _p(kps), _p(desc), cap, _p(tight), _p(padded))
+        if n == -4:
+            raise RuntimeError("reference: cv::Exception (cell ROI outside the level image)")
+        if n < 0:
+            raise RuntimeError("reference shim error %d" % n)
+        assert n <= cap
+        if not pyramid:
+            return kps[:n], desc[:n]
+        lv, pd, o, q = [], [], 0, 0
+        for a, b in sizes:
+            lv.append(tight[o:o + a * b].reshape(b, a))
+            pd.append(padded[q:q + (a + 38) * (b + 38)].reshape(b + 38, a + 38))
+            o += a * b
+            q += (a + 38) * (b + 38)
+        return kps[:n], desc[:n], lv, pd
+
+    def extract_many(self, imgs, nthreads=1, want_outputs=True):
+        imgs = np.ascontiguousarray(imgs, np.uint8)
+        nf, h, w = imgs.shape
+        cap = self._cap()
+        kps = np.zeros((nf, cap), KP_DTYPE) if want_outputs else None
+        desc = np.zeros((nf, cap, 32), np.uint8) if want_outputs else None
+        counts = np.zeros(nf, np.int32)
+        self._lib.ref_extract_many(self._h, _p(imgs), nf, w, h, nthreads, _p(kps), _p(desc), _p(counts), cap)
+        return kps, desc, counts
+
+
+def descriptor_distance(a, b, native=False):
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib(native).ref_descriptor_distance(_p(a), _p(b))
+
+
+def hamming_matrix(A, B, native=False):
+    A = np.ascontiguousarray(A, np.uint8).reshape(-1, 32)
+    B = np.ascontiguousarray(B, np.uint8).reshape(-1, 32)
+    out = np.zeros((len(A), len(B)), np.uint16)
+    lib(native).ref_hamming_matrix(_p(A), len(A), _p(B), len(B), _p(out))
+    return out

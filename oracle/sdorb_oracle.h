@@ -6,12 +6,15 @@
  * primitives it calls.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it; the product (libsdorb.so) never links, loads or calls it.
  *
- * Parity pin: the reference has no tests or golden vectors and cannot be
- * compiled here (no OpenCV C++ headers).  Every primitive below is therefore pinned against the
- * only importable implementation of the arithmetic of record, Python cv2 4.13.0
- * (tests/test_oracle_primitives.py), and the whole operator() against an independent Python
- * assembly of cv2 calls (tests/test_oracle_e2e.py) whose outputs are committed under
- * tests/golden/.
+ * Parity pin (round 2: PINNED to the reference itself).  The reference has no tests or golden vectors,
+ * but its own ORBextractor.cc compiles unmodified against oracle/ref_compat (a cv:: surface whose pixel primitives are the
+ * ones below) into oracle/_ref/libsdorb_ref.so (oracle/ref_build/Makefile).  tests/test_ref_parity.py and tools/ref_sweep.py
+ * assert  restatement == reference  byte for byte (keypoints incl. order, angles, descriptors, pyramid and its borders,
+ * constructor tables, where it throws) on every fixture, the staged configurations, random sizes / parameters and 6560 bench
+ * frames; the fixtures under tests/golden/ are generated from the reference (tests/golden/make_golden.py).  The OpenCV / glibc /
+ * libstdc++ primitives are pinned against the only importable implementation of that arithmetic, Python cv2 4.13.0
+ * (tests/test_oracle_primitives.py), and the whole operator() also against an independent Python assembly of cv2 calls
+ * (tests/test_oracle_e2e.py).
  */
 #ifndef SDORB_ORACLE_H
 #define SDORB_ORACLE_H

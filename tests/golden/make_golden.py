@@ -1,9 +1,11 @@
 #!/usr/bin/env python3
-"""Generate tests/golden/*.npz with the INDEPENDENT cv2 pipeline (tests/cv2_pipeline.py), i.e. with real
-OpenCV 4.13 pixel operations.  Run in the build container:  python tests/golden/make_golden.py
-Each file holds the input image, the parameters, keypoints, descriptors and a SHA-256 per pyramid level.  The oracle is
-checked against these on CPU; the CUDA library is checked against them on the GPU box (where neither
-/root/reference nor this script is needed).
+"""Generate tests/golden/*.npz FROM THE REFERENCE ITSELF: /root/reference/src/ORBextractor.cc compiled unmodified into
+oracle/_ref/libsdorb_ref.so (oracle/ref_build/Makefile, cv:: surface = oracle/ref_compat).  Every case is cross-checked while it
+is generated against the independent pipeline assembled from real OpenCV 4.13 calls (tests/cv2_pipeline.py): the file is only
+written when both agree byte for byte.  Run in the build container:  python tests/golden/make_golden.py
+Each file holds the input image, the parameters, keypoints, descriptors, a SHA-256 per pyramid level (and per padded level
+buffer) and the generator tag.  The oracle is checked against these on CPU; the CUDA library is checked against them on the GPU
+box (where neither /root/reference nor this script is needed).
 """
 import hashlib
 import os
@@ -15,6 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 import cv2_pipeline as cvp  # noqa: E402
+from oracle import ref_binding as ref  # noqa: E402
 from sdslam_b200 import synth  # noqa: E402
 
 
@@ -24,6 +27,9 @@ def checker(w, h, s=9):
 
 
 CASES = {
+    "wide_kitti_1241x376": (synth.smooth_noise(8, 1241, 376), (2000, 1.2, 8, 20)),
+    "noise_th7_400x300": (np.random.default_rng(48).integers(0, 256, (300, 400), dtype=np.uint8), (1500, 1.2, 8, 7)),
+    "ties_binary_260x200": ((np.random.default_rng(7).integers(0, 2, (200, 260)) * 255).astype(np.uint8), (300, 1.2, 4, 20)),
     "c1_smooth_640x480": (synth.smooth_noise(0), (1000, 1.2, 8, 20)),
     "c1_rects_640x480": (synth.rects(0), (1000, 1.2, 8, 20)),
     "c0_default_640x480": (synth.smooth_noise(1), (1000, 2.0, 5, 20)),
@@ -37,10 +43,15 @@ CASES = {
 
 if __name__ == "__main__":
     for name, (img, params) in CASES.items():
-        k, d, pyr = cvp.extract(img, *params)
+        k, d, pyr, padded = ref.Extractor(*params).extract(img, pyramid=True)  # the reference's own compiled text
+        ck, cd, cpyr = cvp.extract(img, *params)                               # real OpenCV 4.13 calls, independent control flow
+        assert k.tobytes() == ck.tobytes() and np.array_equal(d, cd.reshape(-1, 32)), name
+        assert all(np.array_equal(a, b) for a, b in zip(pyr, cpyr)) and len(pyr) == len(cpyr), name
         np.savez_compressed(os.path.join(HERE, name + ".npz"), image=img, params=np.array(params, np.float64),
                             kps=k, desc=d, pyramid_shape=np.array([p.shape for p in pyr], np.int32),
-                            pyramid_sha256=np.array([hashlib.sha256(p.tobytes()).hexdigest() for p in pyr]))
+                            pyramid_sha256=np.array([hashlib.sha256(np.ascontiguousarray(p).tobytes()).hexdigest() for p in pyr]),
+                            padded_sha256=np.array([hashlib.sha256(np.ascontiguousarray(p).tobytes()).hexdigest() for p in padded]),
+                            generator=np.array("reference: /root/reference/src/ORBextractor.cc via oracle/_ref (cross-checked with cv2 %s)" % cvp.cv2.__version__))
         print(name, img.shape, params, len(k))
     # Hamming golden: distances by numpy bit counting (independent of the SWAR restatement)
     rng = np.random.default_rng(77)
