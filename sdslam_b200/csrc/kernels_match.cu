@@ -32,8 +32,10 @@ __global__ void __launch_bounds__(M_THREADS) match_kernel(const uint8_t* __restr
   // device-resident counts are clamped to the slab like the guided-search kernels do (the host form validates them)
   const int na = min(max(nA[pair], 0), strideA), nb = min(max(nB[pair], 0), strideB);
   const int qi = blockIdx.y * M_THREADS + threadIdx.x;
-  if (blockIdx.y * M_THREADS >= na) return;
   const bool active = qi < na;
+  // rows past the pair's count still get a defined result ("no candidate"), so a caller may reduce over whole slabs
+  if (!active && qi < strideA) out[(int64_t)pair * strideA + qi] = MatchOut{-1, 256, 256, 0};
+  if (blockIdx.y * M_THREADS >= na) return;
   uint32_t q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (active) {
     const uint4* qa = reinterpret_cast<const uint4*>(A + ((int64_t)pair * strideA + qi) * 32);
@@ -113,6 +115,7 @@ __global__ void __launch_bounds__(32) match_greedy_kernel(const uint8_t* __restr
     }
     __syncwarp();
   }
+  for (int qi = na + lane; qi < strideA; qi += 32) out[(int64_t)pair * strideA + qi] = MatchOut{-1, 256, 256, 0};
 }
 
 __global__ void __launch_bounds__(256) hamming_matrix_kernel(const uint8_t* __restrict__ A, int nA,
