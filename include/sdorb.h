@@ -132,6 +132,29 @@ SDORB_API int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, in
 SDORB_API int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height,
                         size_t row_stride, size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors,
                         int32_t* counts, int capacity, int mem, void* stream);
+
+/* ---- the batch operator with the reference's FIFTH output, imagePyramid (src/ORBextractor.cc:620-621, consumed by
+ * src/ImageAlign.cc:57,93) ----
+ * pyramid: NULL (then identical to sdorb_extract_batch) or a frame-major slab in the same memory space as the other buffers:
+ * level l of frame f starts at pyramid + f * frame_bytes + level_offset[l] with tightly packed rows (stride = level width);
+ * sdorb_pyramid_layout() gives level_offset[nlevels] and frame_bytes for an input size (all multiples of 16; a device slab
+ * must be 16-byte aligned).  first_level = 0 writes every level (level 0 = a copy of the input, as the reference returns it),
+ * first_level = 1 leaves the level-0 bytes of every frame untouched (the caller already holds level 0: its input). */
+SDORB_API int sdorb_pyramid_layout(const sdorb_handle* h, int width, int height, size_t* level_offset, size_t* frame_bytes);
+
+/* ---- one batch over several GPUs of one node, from C / C++ ----
+ * handles[g]: one handle per GPU (sdorb_params.device), all created with the same extractor parameters.  Handle g extracts
+ * the contiguous frame range sdorb_shard_range(g, ndev, nframes) = [g * nframes / ndev, (g + 1) * nframes / ndev) on its own host
+ * thread, through the host pipeline of sdorb_extract_batch_pyr (host buffers; pinned memory gives full copy speed), straight
+ * into the caller's slabs: the result is byte-identical to one GPU doing the whole batch.  No collective, no exchange.
+ * Returns the first error in handle order; pyramid may be NULL. */
+SDORB_API int sdorb_shard_range(int shard, int nshards, int nframes, int* first, int* last);
+SDORB_API int sdorb_extract_batch_multi(sdorb_handle* const* handles, int ndev, const uint8_t* images, int nframes, int width,
+                              int height, size_t row_stride, size_t frame_stride, sdorb_keypoint* keypoints,
+                              uint8_t* descriptors, int32_t* counts, int capacity, uint8_t* pyramid, int first_level);
+SDORB_API int sdorb_extract_batch_pyr(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height,
+                            size_t row_stride, size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors,
+                            int32_t* counts, int capacity, uint8_t* pyramid, int first_level, int mem, void* stream);
 /* After synchronising: SDORB_OK, or the first deferred device-side error (SDORB_ERR_OVERFLOW / _CUDA). */
 SDORB_API int sdorb_batch_status(sdorb_handle* h);
 
@@ -410,6 +433,10 @@ SDORB_API int64_t sdorb_debug_read(sdorb_handle* h, int what, int frame, int lev
  * KeyPointsFilter::retainBest (src/ORBextractor.cc:586, 602) -- on n packed entries (low 8 bits = response) in host
  * memory, in place (parity tests against the real libstdc++ algorithm). */
 SDORB_API int sdorb_debug_nth_element(sdorb_handle* h, uint32_t* entries, int n, int nth);
+/* Measured peak of an execution pipe on the handle's GPU (a saturating micro-benchmark, kernels_probe.cu), for the roofline
+ * figures of bench.py: pipe 0 = POPC (bounds the Hamming matcher), 1 = the integer ALU pipe on VIMNMX3.U16x2 (bounds FAST),
+ * 2 = PRMT.  Rates in warp-instructions per second (whole GPU) and per SM clock per SM. */
+SDORB_API int sdorb_debug_pipe_probe(sdorb_handle* h, int pipe, double* warp_instr_per_s, double* warp_instr_per_clk_per_sm);
 
 #ifdef __cplusplus
 }

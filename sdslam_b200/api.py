@@ -98,6 +98,10 @@ def lib():
     L.sdorb_level_size.argtypes = [vp, i, i, i, C.POINTER(i), C.POINTER(i)]
     L.sdorb_extract.argtypes = [vp, vp, i, i, sz, vp, vp, i, C.POINTER(i), vp]
     L.sdorb_extract_batch.argtypes = [vp, vp, i, i, i, sz, sz, vp, vp, vp, i, i, vp]
+    L.sdorb_extract_batch_pyr.argtypes = [vp, vp, i, i, i, sz, sz, vp, vp, vp, i, vp, i, i, vp]
+    L.sdorb_pyramid_layout.argtypes = [vp, i, i, vp, vp]
+    L.sdorb_shard_range.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+    L.sdorb_extract_batch_multi.argtypes = [vp, i, vp, i, i, i, sz, sz, vp, vp, vp, i, vp, i]
     L.sdorb_batch_status.argtypes = [vp]
     L.sdorb_match_batch.argtypes = [vp, vp, vp, i, vp, vp, i, i, f, i, vp, i, vp]
     L.sdorb_match_greedy_batch.argtypes = [vp, vp, vp, i, vp, vp, i, i, f, i, vp, i, vp]
@@ -126,6 +130,7 @@ def lib():
     L.sdorb_debug_read.argtypes = [vp, i, i, i, vp, sz]
     L.sdorb_debug_read.restype = i64
     L.sdorb_debug_nth_element.argtypes = [vp, vp, i, i]
+    L.sdorb_debug_pipe_probe.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -172,6 +177,34 @@ def host_image_bounds(cols, rows, K4, dist):
     if rc:
         raise SdorbError(rc, lib().sdorb_strerror(rc).decode())
     return b
+
+
+def shard_range(shard, nshards, nframes):
+    a, b = C.c_int(), C.c_int()
+    rc = lib().sdorb_shard_range(shard, nshards, nframes, C.byref(a), C.byref(b))
+    if rc:
+        raise SdorbError(rc, lib().sdorb_strerror(rc).decode())
+    return a.value, b.value
+
+
+def extract_batch_multi(extractors, images, keypoints=None, descriptors=None, counts=None, pyramid=None, first_level=1):
+    """sdorb_extract_batch_multi: one host batch over several handles (one per GPU), each on its own host thread inside the
+    library.  images: uint8 [F,H,W] host array / pinned tensor.  Returns (kps[F,cap], desc[F,cap,32], counts[F])."""
+    nf, h, w = images.shape
+    cap = max(extractors[0].max_keypoints, 1)
+    is_t = hasattr(images, "data_ptr")
+    if keypoints is None:
+        keypoints = np.zeros((nf, cap), KP_DTYPE)
+        descriptors = np.zeros((nf, cap, 32), np.uint8)
+        counts = np.zeros(nf, np.int32)
+    row = images.stride(1) if is_t else images.strides[1]
+    frame = images.stride(0) if is_t else images.strides[0]
+    hs = (C.c_void_p * len(extractors))(*[e._h for e in extractors])
+    rc = lib().sdorb_extract_batch_multi(C.cast(hs, C.c_void_p), len(extractors), _ptr(images), nf, w, h, row, frame, _ptr(keypoints),
+                                         _ptr(descriptors), _ptr(counts), cap, _ptr(pyramid), first_level)
+    if rc:
+        extractors[0]._check(rc)
+    return keypoints, descriptors, counts
 
 
 class ORBextractor:
@@ -267,8 +300,57 @@ class ORBextractor:
                                          C.byref(n), C.cast(views, C.c_void_p) if views is not None else None))
         return kps[:n.value], desc[:n.value], pyr
 
-    def extract_batch_host(self, images, keypoints=None, descriptors=None, counts=None):
-        """images: uint8 [F,H,W] host array (or pinned torch CPU tensor).  Returns (kps[F,cap], desc[F,cap,32], counts[F])."""
+    def single_frame_call(self, width, height, want_pyramid=True):
+        """A reusable single-frame call with every output buffer allocated once (what a C++ caller that keeps its cv::Mat
+        buffers does): returns f(image) -> (count, kps, desc, pyramid views) with the arrays overwritten by every call."""
+        cap = max(self.max_keypoints, 1)
+        kps = np.zeros(cap, KP_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        views, pyr, keep = None, None, []
+        if want_pyramid:
+            views = (_PyrView * self.nlevels)()
+            pyr = []
+            for l in range(self.nlevels):
+                lw, lh = self.level_size(width, height, l)
+                buf = np.zeros((max(lh, 0) + 2 * EDGE_THRESHOLD, max(lw, 0) + 2 * EDGE_THRESHOLD), np.uint8)
+                inner = buf[EDGE_THRESHOLD:EDGE_THRESHOLD + lh, EDGE_THRESHOLD:EDGE_THRESHOLD + lw]
+                keep.append(buf)
+                pyr.append(inner)
+                views[l] = _PyrView(inner.ctypes.data if inner.size else None, lw, lh, buf.strides[0], EDGE_THRESHOLD)
+        vp = C.cast(views, C.c_void_p) if views is not None else None
+        fn, hnd, pk, pd, pn = lib().sdorb_extract, self._h, _ptr(kps), _ptr(desc), C.byref(n)
+
+        def call(image):
+            rc = fn(hnd, image.ctypes.data_as(C.c_void_p), width, height, image.strides[0], pk, pd, cap, pn, vp)
+            if rc:
+                self._check(rc)
+            return n.value, kps, desc, pyr
+
+        call._keep = keep
+        return call
+
+    def pyramid_layout(self, width, height):
+        """(level_offset[nlevels], frame_bytes) of the imagePyramid slab of the batch calls (sdorb_pyramid_layout)."""
+        off = (C.c_size_t * self.nlevels)()
+        fb = C.c_size_t(0)
+        self._check(lib().sdorb_pyramid_layout(self._h, width, height, C.cast(off, C.c_void_p), C.cast(C.byref(fb), C.c_void_p)))
+        return [int(o) for o in off], int(fb.value)
+
+    def pyramid_levels(self, slab, frame, width, height):
+        """Views of the levels of `frame` in a host slab filled by extract_batch_host(..., pyramid=slab)."""
+        off, fb = self.pyramid_layout(width, height)
+        out = []
+        for l in range(self.nlevels):
+            lw, lh = self.level_size(width, height, l)
+            a = frame * fb + off[l]
+            out.append(slab[a:a + lw * lh].reshape(lh, lw))
+        return out
+
+    def extract_batch_host(self, images, keypoints=None, descriptors=None, counts=None, pyramid=None, first_level=1):
+        """images: uint8 [F,H,W] host array (or pinned torch CPU tensor).  Returns (kps[F,cap], desc[F,cap,32], counts[F]).
+        pyramid: None, or a flat uint8 host buffer of F * frame_bytes (pyramid_layout) that receives imagePyramid of every frame
+        (levels first_level ..; first_level = 0 includes the copy of the input the reference returns as level 0)."""
         nf, h, w = images.shape
         cap = max(self.max_keypoints, 1)
         is_t = hasattr(images, "data_ptr")
@@ -278,11 +360,11 @@ class ORBextractor:
             counts = np.zeros(nf, np.int32)
         row = images.stride(1) if is_t else images.strides[1]
         frame = images.stride(0) if is_t else images.strides[0]
-        self._check(lib().sdorb_extract_batch(self._h, _ptr(images), nf, w, h, row, frame, _ptr(keypoints),
-                                               _ptr(descriptors), _ptr(counts), cap, MEM_HOST, None))
+        self._check(lib().sdorb_extract_batch_pyr(self._h, _ptr(images), nf, w, h, row, frame, _ptr(keypoints),
+                                                   _ptr(descriptors), _ptr(counts), cap, _ptr(pyramid), first_level, MEM_HOST, None))
         return keypoints, descriptors, counts
 
-    def extract_batch_device(self, images, keypoints, descriptors, counts, stream=None):
+    def extract_batch_device(self, images, keypoints, descriptors, counts, stream=None, pyramid=None, first_level=1):
         """All arguments are torch CUDA tensors on this handle's device: images uint8 [F,H,W]; keypoints
         [F,cap,7] float32 (cv::KeyPoint layout, octave / class_id as int bits); descriptors uint8 [F,cap,32];
         counts int32 [F].  Work is enqueued on `stream` (a raw cudaStream_t int; None = torch's current)."""
@@ -291,9 +373,9 @@ class ORBextractor:
         cap = keypoints.shape[1]
         if stream is None:
             stream = torch.cuda.current_stream(images.device).cuda_stream
-        self._check(lib().sdorb_extract_batch(self._h, _ptr(images), nf, w, h, images.stride(1), images.stride(0),
-                                               _ptr(keypoints), _ptr(descriptors), _ptr(counts), cap, MEM_DEVICE,
-                                               C.c_void_p(stream)))
+        self._check(lib().sdorb_extract_batch_pyr(self._h, _ptr(images), nf, w, h, images.stride(1), images.stride(0),
+                                                   _ptr(keypoints), _ptr(descriptors), _ptr(counts), cap, _ptr(pyramid), first_level,
+                                                   MEM_DEVICE, C.c_void_p(stream)))
 
     def batch_status(self):
         self._check(lib().sdorb_batch_status(self._h))
@@ -561,6 +643,13 @@ class ORBextractor:
         launches = np.zeros(len(STAGES), np.int64)
         self._check(lib().sdorb_get_stage_times(self._h, _ptr(ms), _ptr(launches), int(reset)))
         return dict(zip(STAGES, ms.tolist())), dict(zip(STAGES, launches.tolist()))
+
+    def pipe_probe(self, pipe):
+        """Measured peak of an execution pipe (0 POPC, 1 VIMNMX3.U16x2 on the ALU pipe, 2 PRMT): (warp-instructions / s,
+        warp-instructions / clk / SM)."""
+        a, b = C.c_double(0), C.c_double(0)
+        self._check(lib().sdorb_debug_pipe_probe(self._h, pipe, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def kernel_launches(self):
         return int(lib().sdorb_kernel_launches(self._h))

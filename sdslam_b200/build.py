@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libsdorb.so")
 SOURCES = ["sdorb_api.cu", "kernels_image.cu", "kernels_fast.cu", "kernels_select.cu", "kernels_describe.cu",
-           "kernels_match.cu", "kernels_frame.cu", "kernels_search.cu", "kernels_octree.cu", "geometry.cc"]
+           "kernels_match.cu", "kernels_frame.cu", "kernels_search.cu", "kernels_octree.cu", "kernels_probe.cu", "geometry.cc"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC,-O2,-Wall,-fvisibility=hidden", "-Xptxas", "-v"]
 

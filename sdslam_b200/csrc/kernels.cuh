@@ -4,10 +4,41 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "sdorb_internal.h"
 
 namespace sdorb {
+
+// ---- programmatic dependent launch (sm_90+): the kernels of a pass form one dependency chain on one stream.  Each is launched
+// with cudaLaunchAttributeProgrammaticStreamSerialization and begins with pdl_wait() -- griddepcontrol.wait blocks until the
+// preceding grid has completed and flushed its writes, so no kernel touches memory earlier than it would have without the
+// attribute -- followed by pdl_trigger() (griddepcontrol.launch_dependents): once every CTA of a grid has started, the CTAs of
+// the next grid may take the SM slots its last wave leaves free and sit at their own pdl_wait().  What is saved is the launch
+// latency and CTA ramp-up at each of the 12 kernel boundaries of a pass (it matters for small passes and the single-frame call).
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_wait();
+  pdl_trigger();
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
 
 // Where the planes of a batch live.  Level 0 is the caller's image (or a staged copy); levels >= 1 and all
 // blurred levels are level-major scratch: level l of frame f starts at base + lv[l].plane_base * batch_cap + f * lv[l].plane_bytes.
@@ -34,6 +65,14 @@ struct SelectBuffers {
 // ComputePyramid: level l from level l-1 for every frame (cv::resize INTER_LINEAR fixed point).
 void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level, const BatchPlanes& p,
                          const ResizeTap* d_taps, const ResizeGroup* d_groups, int nframes, cudaStream_t s);
+// imagePyramid of a batch into the caller's frame-major slab (levels first_level .. nlevels-1); layout: pyramid_layout().
+void pyramid_layout(const FrameGeom& g, int64_t* offset, int64_t* frame_bytes);
+void launch_pack_pyramid(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int first_level, uint8_t* dst, int nframes,
+                         cudaStream_t s);
+// Frame 0's pyramid in the reference's padded form (19 px of BORDER_REFLECT_101 around every level), level after level.
+int64_t padded_pyramid_layout(const FrameGeom& g, int64_t* offset);
+void launch_pack_padded(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int first_level, uint8_t* dst,
+                        cudaStream_t s);
 // cv::GaussianBlur(7x7, sigma 2, BORDER_REFLECT_101), 8-bit fixed point, all levels of all frames in one launch.
 void launch_blur_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s);
 // cv::FAST(cell, thFAST, nonmax=true) for every cell of every level of every frame, one launch; writes the keypoint
@@ -152,6 +191,9 @@ void launch_search_projection(const SearchProjArgs& a, int npairs, cudaStream_t 
 size_t search_init_smem(int capacity);
 size_t search_projection_smem(int capacity);
 int configure_search_kernels();
+
+// Pipe micro-benchmarks (kernels_probe.cu): 0 = POPC, 1 = VIMNMX3.U16x2, 2 = PRMT; warp-instructions per second and per clk per SM.
+int run_pipe_probe(int pipe, cudaStream_t s, double* rate_per_s, double* per_clk_sm);
 
 size_t select_smem_bytes(const FrameGeom& g);
 int configure_kernels();  // one-time cudaFuncSetAttribute calls; returns cudaError_t as int

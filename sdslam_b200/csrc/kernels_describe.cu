@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(DESC_THREADS) describe_kernel(const FrameGeom*
                                                                 float* __restrict__ kps_out, uint8_t* __restrict__ desc_out,
                                                                 int32_t* __restrict__ counts_out, int capacity) {
   __shared__ uint32_t s_patch[DESC_THREADS / 32][PATCH_ROWS * PATCH_WORDS];
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int slot = blockIdx.x * (DESC_THREADS / 32) + (threadIdx.x >> 5);
   const int frame = blockIdx.y;
@@ -225,8 +226,8 @@ void launch_describe(const FrameGeom* d_geom, const FrameGeom& g, const BatchPla
                      int nframes, cudaStream_t s) {
   const int slots = g.sel_total > 0 ? g.sel_total : 1;
   const int per_block = DESC_THREADS / 32;
-  describe_kernel<<<dim3((slots + per_block - 1) / per_block, nframes), DESC_THREADS, 0, s>>>(
-      d_geom, p, b, d_umax, (float*)kps_out, desc_out, counts_out, capacity);
+  launch_pdl(describe_kernel, dim3((slots + per_block - 1) / per_block, nframes), dim3(DESC_THREADS), 0, s, d_geom, p, b, d_umax,
+             (float*)kps_out, desc_out, counts_out, capacity);
 }
 
 }  // namespace sdorb

@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) fast_tiles_kernel(const FrameGe
   __shared__ __align__(16) uint32_t s_t[SROWS][TWORDS];
   __shared__ uint32_t s_rowflags[OH];
   __shared__ int s_level;
+  pdl_enter();
   const bool narrow = (int)blockIdx.x >= n_full;  // CTA-uniform
   const int t = narrow ? (int)blockIdx.x - n_full : (int)blockIdx.x;
   if (threadIdx.x == 0) {
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(NT, 1024 / NT) fast_tiles_kernel(const FrameGe
 
 void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s) {
   const int total = g.tiles_total_fast + g.tiles_total_fastn;
-  if (total > 0) fast_tiles_kernel<<<dim3(total, nframes), NT, 0, s>>>(d_geom, p, g.tiles_total_fast);
+  if (total > 0) launch_pdl(fast_tiles_kernel, dim3(total, nframes), dim3(NT), 0, s, d_geom, p, g.tiles_total_fast);
 }
 
 }  // namespace sdorb

@@ -65,6 +65,7 @@ __device__ __forceinline__ void resize_hrow(const ResizeRaw& r, int shift, const
 __global__ void __launch_bounds__(128) resize_level_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
                                                            const ResizeTap* __restrict__ taps,
                                                            const ResizeGroup* __restrict__ groups) {
+  pdl_enter();
   const LevelGeom& D = geom->lv[level];
   const LevelGeom& S = geom->lv[level - 1];
   const int gi = blockIdx.x * 32 + threadIdx.x;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* 
                                                                const ResizeTap* __restrict__ taps,
                                                                const ResizeGroup* __restrict__ groups) {
   __shared__ int4 s_emit[4][KMAX];  // per warp and source row k: {destination row or -1, c0, c1, -}
+  pdl_enter();
   const LevelGeom& D = geom->lv[level];
   const LevelGeom& S = geom->lv[level - 1];
   const int lane = threadIdx.x;
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* 
 // Generic path for scale factors whose taps do not fit the 8-byte window (scale > ~2): one thread = 4 pixels of one row.
 __global__ void __launch_bounds__(256) resize_level_generic_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
                                                                    const ResizeTap* __restrict__ taps) {
+  pdl_enter();
   const LevelGeom& D = geom->lv[level];
   const LevelGeom& S = geom->lv[level - 1];
   const int x4 = (blockIdx.x * 64 + threadIdx.x) * 4;
@@ -234,15 +237,15 @@ void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level,
   if (D.group_base >= 0 && D.rz_span > 0 && D.rz_span <= 11) {
     dim3 block(32, 4);
     dim3 grid((D.w + 127) / 128, (D.h + 4 * RZP_ROWS - 1) / (4 * RZP_ROWS), nframes);
-    resize_level_pre_kernel<11><<<grid, block, 0, s>>>(d_geom, level, p, d_taps, d_groups);
+    launch_pdl(resize_level_pre_kernel<11>, grid, block, 0, s, d_geom, level, p, d_taps, d_groups);
   } else if (D.group_base >= 0) {
     dim3 block(32, 4);
     dim3 grid((D.w + 127) / 128, (D.h + 4 * RZ_ROWS - 1) / (4 * RZ_ROWS), nframes);
-    resize_level_kernel<<<grid, block, 0, s>>>(d_geom, level, p, d_taps, d_groups);
+    launch_pdl(resize_level_kernel, grid, block, 0, s, d_geom, level, p, d_taps, d_groups);
   } else {
     dim3 block(64, 4);
     dim3 grid((D.w + 255) / 256, (D.h + 3) / 4, nframes);
-    resize_level_generic_kernel<<<grid, block, 0, s>>>(d_geom, level, p, d_taps);
+    launch_pdl(resize_level_generic_kernel, grid, block, 0, s, d_geom, level, p, d_taps);
   }
 }
 
@@ -261,6 +264,7 @@ static_assert(BTW == 128, "one warp spans a strip row");
 
 struct BlurTileBases {
   int nlevels;
+  int bth;                         // output rows per strip: SDORB_BLUR_TH for batches, short strips for a handful of frames
   int base[SDORB_MAX_LEVELS + 1];  // first strip tile of each level; base[nlevels] = total
 };
 
@@ -367,6 +371,7 @@ __device__ __forceinline__ void blur_walk(const BlurLane& B, uint8_t* __restrict
 }
 
 __global__ void __launch_bounds__(B_WARPS * 32, 5) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, BlurTileBases tb) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x * B_WARPS + (threadIdx.x >> 5);
   if (tile >= tb.base[tb.nlevels]) return;
@@ -376,7 +381,7 @@ __global__ void __launch_bounds__(B_WARPS * 32, 5) blur_all_kernel(const FrameGe
   const int frame = blockIdx.y;
   const int t = tile - tb.base[level];
   const int tx = t % L.tiles_x_blur, ty = t / L.tiles_x_blur;
-  const int x0 = tx * BTW, y0 = ty * BTH;
+  const int x0 = tx * BTW, y0 = ty * tb.bth;
   const int w = L.w, h = L.h;
   const int gx = x0 + 4 * lane;
   const int lastw = (w - 1) & ~3;
@@ -394,7 +399,7 @@ __global__ void __launch_bounds__(B_WARPS * 32, 5) blur_all_kernel(const FrameGe
   B.edge_warp = x0 == 0 || x0 + BTW + 4 > lastw;
   B.sel_last = L.blur_sel_last;
   B.sel_beyond = L.blur_sel_beyond;
-  const int nout = min(BTH, h - y0);
+  const int nout = min(tb.bth, h - y0);
   uint8_t* dst = p.blur + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes + (int64_t)y0 * L.pitch + gx;
   const int dpitch = L.pitch;
 
@@ -402,13 +407,146 @@ __global__ void __launch_bounds__(B_WARPS * 32, 5) blur_all_kernel(const FrameGe
   else blur_walk<false>(B, dst, dpitch, nout);
 }
 
+// ---- imagePyramid for a batch (src/ORBextractor.cc:620-621: the pyramid is an output of operator()).  The scratch planes are
+// level-major with padded pitches; the caller's slab is frame-major with tightly packed rows: level l of frame f starts at
+// slab + f * frame_bytes + offset[l] (offsets and frame_bytes are multiples of 16, sdorb_pyramid_layout).  One thread moves 16
+// destination bytes with one aligned store; its source bytes may straddle a row end, so they are fetched byte by byte (L1).
+struct PackLayout {
+  int nlevels, first_level;
+  int64_t frame_bytes;
+  int64_t offset[SDORB_MAX_LEVELS];
+  int chunk_base[SDORB_MAX_LEVELS + 1];  // first 16-byte chunk of each level in the per-frame chunk numbering
+};
+
+__global__ void __launch_bounds__(256) pack_pyramid_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, PackLayout lay,
+                                                           uint8_t* __restrict__ dst) {
+  pdl_enter();
+  const int chunk = blockIdx.x * 256 + threadIdx.x, frame = blockIdx.y;
+  if (chunk >= lay.chunk_base[lay.nlevels]) return;
+  int level = lay.first_level;
+  while (chunk >= lay.chunk_base[level + 1]) ++level;
+  const LevelGeom& L = geom->lv[level];
+  int spitch;
+  const uint8_t* src = level_plane(p, L, level, frame, &spitch);
+  const int i0 = (chunk - lay.chunk_base[level]) * 16, total = L.w * L.h;
+  int y = i0 / L.w, x = i0 - y * L.w;
+  uint32_t wds[4] = {0u, 0u, 0u, 0u};
+  const uint8_t* row = src + (int64_t)y * spitch;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (i0 + k < total) wds[k >> 2] |= (uint32_t)row[x] << (8 * (k & 3));
+    if (++x == L.w) {
+      x = 0;
+      row += spitch;
+    }
+  }
+  *reinterpret_cast<uint4*>(dst + (int64_t)frame * lay.frame_bytes + lay.offset[level] + i0) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+}
+
+// The single-frame call returns imagePyramid the way the reference holds it: every level inside a buffer padded by 19 pixels
+// of BORDER_REFLECT_101 (src/ORBextractor.cc:684-696).  This kernel lays frame 0's levels out in exactly that form, level after
+// level ((w + 38) x (h + 38) bytes each, 16-byte aligned starts), so that the host side is one plain copy per level.
+struct PadLayout {
+  int nlevels, first_level;
+  int64_t offset[SDORB_MAX_LEVELS];
+  int chunk_base[SDORB_MAX_LEVELS + 1];
+};
+
+__device__ __forceinline__ int reflect101(int p, int len) {
+  if (len == 1) return 0;
+  while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * (len - 1) - p;
+  return p;
+}
+
+__global__ void __launch_bounds__(256) pack_padded_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, PadLayout lay,
+                                                          uint8_t* __restrict__ dst) {
+  pdl_enter();
+  const int chunk = blockIdx.x * 256 + threadIdx.x;
+  if (chunk >= lay.chunk_base[lay.nlevels]) return;
+  int level = lay.first_level;
+  while (chunk >= lay.chunk_base[level + 1]) ++level;
+  const LevelGeom& L = geom->lv[level];
+  int spitch;
+  const uint8_t* src = level_plane(p, L, level, 0, &spitch);
+  const int pw = L.w + 2 * SDORB_EDGE, total = pw * (L.h + 2 * SDORB_EDGE);
+  const int i0 = (chunk - lay.chunk_base[level]) * 16;
+  int Y = i0 / pw, X = i0 - Y * pw;
+  uint32_t wds[4] = {0u, 0u, 0u, 0u};
+  const uint8_t* row = src + (int64_t)reflect101(Y - SDORB_EDGE, L.h) * spitch;
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    if (i0 + k < total) wds[k >> 2] |= (uint32_t)row[reflect101(X - SDORB_EDGE, L.w)] << (8 * (k & 3));
+    if (++X == pw) {
+      X = 0;
+      ++Y;
+      row = src + (int64_t)reflect101(Y - SDORB_EDGE, L.h) * spitch;
+    }
+  }
+  *reinterpret_cast<uint4*>(dst + lay.offset[level] + i0) = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+}
+
+int64_t padded_pyramid_layout(const FrameGeom& g, int64_t* offset) {
+  int64_t off = 0;
+  for (int l = 0; l < g.nlevels; ++l) {
+    if (offset) offset[l] = off;
+    off += ((int64_t)(g.lv[l].w + 2 * SDORB_EDGE) * (g.lv[l].h + 2 * SDORB_EDGE) + 15) / 16 * 16;
+  }
+  return off;
+}
+
+void launch_pack_padded(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int first_level, uint8_t* dst,
+                        cudaStream_t s) {
+  PadLayout lay{};
+  lay.nlevels = g.nlevels;
+  lay.first_level = first_level;
+  padded_pyramid_layout(g, lay.offset);
+  int c = 0;
+  for (int l = 0; l <= SDORB_MAX_LEVELS; ++l) {
+    lay.chunk_base[l] = c;
+    if (l < g.nlevels && l >= first_level) c += ((g.lv[l].w + 2 * SDORB_EDGE) * (g.lv[l].h + 2 * SDORB_EDGE) + 15) / 16;
+  }
+  if (c == 0) return;
+  pack_padded_kernel<<<(c + 255) / 256, 256, 0, s>>>(d_geom, p, lay, dst);
+}
+
+void pyramid_layout(const FrameGeom& g, int64_t* offset, int64_t* frame_bytes) {
+  int64_t off = 0;
+  for (int l = 0; l < g.nlevels; ++l) {
+    offset[l] = off;
+    off += ((int64_t)g.lv[l].w * g.lv[l].h + 15) / 16 * 16;
+  }
+  *frame_bytes = off;
+}
+
+void launch_pack_pyramid(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int first_level, uint8_t* dst, int nframes,
+                         cudaStream_t s) {
+  PackLayout lay{};
+  lay.nlevels = g.nlevels;
+  lay.first_level = first_level;
+  pyramid_layout(g, lay.offset, &lay.frame_bytes);
+  int c = 0;
+  for (int l = 0; l <= g.nlevels; ++l) {
+    lay.chunk_base[l] = c;
+    if (l < g.nlevels && l >= first_level) c += (g.lv[l].w * g.lv[l].h + 15) / 16;
+  }
+  for (int l = g.nlevels + 1; l <= SDORB_MAX_LEVELS; ++l) lay.chunk_base[l] = c;
+  if (c == 0 || nframes <= 0) return;
+  launch_pdl(pack_pyramid_kernel, dim3((c + 255) / 256, nframes), dim3(256), 0, s, d_geom, p, lay, dst);
+}
+
 void launch_blur_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s) {
   if (g.tiles_total_blur == 0) return;
+  // A strip is walked by one warp, seven halo rows on top of its output rows: 128-row strips for batches (5 % halo, plenty of
+  // warps), 28-row strips when there are only a few frames (the single-frame call had 21 warps on the whole GPU otherwise).
   BlurTileBases tb;
   tb.nlevels = g.nlevels;
-  for (int l = 0; l < g.nlevels; ++l) tb.base[l] = g.lv[l].tile_base_blur;
-  for (int l = g.nlevels; l <= SDORB_MAX_LEVELS; ++l) tb.base[l] = g.tiles_total_blur;
-  blur_all_kernel<<<dim3((g.tiles_total_blur + B_WARPS - 1) / B_WARPS, nframes), B_WARPS * 32, 0, s>>>(d_geom, p, tb);
+  tb.bth = nframes <= 8 ? 28 : BTH;
+  int total = 0;
+  for (int l = 0; l <= SDORB_MAX_LEVELS; ++l) {
+    tb.base[l] = total;
+    if (l < g.nlevels && g.lv[l].tiles_y_blur > 0) total += g.lv[l].tiles_x_blur * ((g.lv[l].h + tb.bth - 1) / tb.bth);
+  }
+  launch_pdl(blur_all_kernel, dim3((total + B_WARPS - 1) / B_WARPS, nframes), dim3(B_WARPS * 32), 0, s, d_geom, p, tb);
 }
 
 }  // namespace sdorb

@@ -40,6 +40,7 @@ __device__ __forceinline__ int oct_child(uint32_t e, const OctNode& nd) {
 __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const FrameGeom* __restrict__ geom, SelectBuffers buf, int max_cells,
                                                              int max_nodes) {
   extern __shared__ __align__(16) uint32_t smem[];
+  pdl_enter();
   int* offs = reinterpret_cast<int*>(smem);                              // [max_cells + 1]
   OctNode* const nodes_a = reinterpret_cast<OctNode*>(offs + ((max_cells + 2) & ~1));  // [max_nodes] x 2
   OctNode* const nodes_b = nodes_a + max_nodes;
@@ -283,7 +284,7 @@ static size_t octree_smem_bytes(int mc, int mn) {
 void launch_octree(const FrameGeom* d_geom, const FrameGeom& g, const SelectBuffers& b, int nframes, cudaStream_t s) {
   int mc, mn;
   octree_caps(g, &mc, &mn);
-  octree_kernel<<<dim3(g.nlevels, nframes), OCT_THREADS, octree_smem_bytes(mc, mn), s>>>(d_geom, b, mc, mn);
+  launch_pdl(octree_kernel, dim3(g.nlevels, nframes), dim3(OCT_THREADS), octree_smem_bytes(mc, mn), s, d_geom, b, mc, mn);
 }
 
 int configure_octree_kernel() {

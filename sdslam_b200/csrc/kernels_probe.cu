@@ -1,0 +1,86 @@
+// kernels_probe.cu -- micro-benchmarks of the two execution pipes the hot kernels of this library are bound by, so that bench.py
+// quotes MEASURED peaks on the device it runs on ("popc peak to be measured"):
+//   pipe 0  POPC (the pipe match_kernel saturates: DescriptorDistance, /root/reference/src/ORBmatcher.cc:1459-1473)
+//   pipe 1  the integer ALU pipe with VIMNMX3.U16x2 (the arc min / max network of fast_tiles_kernel)
+//   pipe 2  PRMT (the ring / tap windows of the FAST, pyramid and blur kernels; same ALU pipe)
+// Eight independent dependency chains per thread, 8 resident 256-thread CTAs per SM: enough ILP and warps to saturate a pipe.
+// The rate is reported per second (CUDA events) and per SM clock (clock64 inside the kernel, so it does not depend on what
+// nvidia-smi samples): warp-instructions / clk / SM.
+#include "kernels.cuh"
+
+namespace sdorb {
+
+template <int PIPE>
+__global__ void __launch_bounds__(256) pipe_probe_kernel(uint32_t* __restrict__ out, const uint32_t* __restrict__ in, int iters,
+                                                         long long* __restrict__ cycles) {
+  uint32_t v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = in[(threadIdx.x + 8 * i) & 1023];
+  __syncthreads();
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (PIPE == 0) asm volatile("popc.b32 %0, %0;" : "+r"(v[i]));
+      if (PIPE == 1) v[i] = __vimax3_u16x2(v[i], v[(i + 1) & 7], v[(i + 2) & 7]);
+      if (PIPE == 2) v[i] = __byte_perm(v[i], v[(i + 1) & 7], 0x5140);
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+}
+
+// Runs the probe on stream s; returns 0 or a cudaError_t.  rate_per_s: warp-instructions per second over the whole GPU;
+// per_clk_sm: warp-instructions per SM clock per SM (median CTA duration in clock64 ticks as the denominator).
+int run_pipe_probe(int pipe, cudaStream_t s, double* rate_per_s, double* per_clk_sm) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ctas = sms * 8, iters = 8192;
+  uint32_t *out = nullptr, *in = nullptr;
+  long long* cyc = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(uint32_t) * (size_t)ctas * 256);
+  if (e == cudaSuccess) e = cudaMalloc(&in, sizeof(uint32_t) * 1024);
+  if (e == cudaSuccess) e = cudaMalloc(&cyc, sizeof(long long) * (size_t)ctas);
+  if (e == cudaSuccess) e = cudaMemsetAsync(in, 0x35, sizeof(uint32_t) * 1024, s);
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (e == cudaSuccess) e = cudaEventCreate(&e0);
+  if (e == cudaSuccess) e = cudaEventCreate(&e1);
+  float ms = 0.f;
+  if (e == cudaSuccess) {
+    auto launch = [&](int n) {
+      if (pipe == 0) pipe_probe_kernel<0><<<ctas, 256, 0, s>>>(out, in, n, cyc);
+      else if (pipe == 1) pipe_probe_kernel<1><<<ctas, 256, 0, s>>>(out, in, n, cyc);
+      else pipe_probe_kernel<2><<<ctas, 256, 0, s>>>(out, in, n, cyc);
+    };
+    launch(64);  // warm-up
+    cudaEventRecord(e0, s);
+    launch(iters);
+    cudaEventRecord(e1, s);
+    e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+  }
+  if (e == cudaSuccess) {
+    std::vector<long long> h((size_t)ctas);
+    e = cudaMemcpy(h.data(), cyc, sizeof(long long) * (size_t)ctas, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) {
+      std::nth_element(h.begin(), h.begin() + ctas / 2, h.end());
+      const double warp_instr_per_sm = 8.0 /*CTAs*/ * 8 /*warps*/ * 8 /*chains*/ * (double)iters;
+      if (per_clk_sm) *per_clk_sm = warp_instr_per_sm / (double)h[(size_t)ctas / 2];
+      if (rate_per_s) *rate_per_s = warp_instr_per_sm * sms / ((double)ms * 1e-3);
+    }
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(out);
+  cudaFree(in);
+  cudaFree(cyc);
+  return (int)e;
+}
+
+}  // namespace sdorb

@@ -27,8 +27,9 @@
 
 namespace sdorb {
 
-constexpr int SEL_THREADS = 128;
-constexpr int SEL_WARPS = SEL_THREADS / 32;
+// select_kernel comes in two shapes: 4 warps per (level, frame) CTA for batches (many CTAs: throughput), 16 warps for a handful
+// of frames (the single-frame call of Frame.cc:195: 8 CTAs in all, so the cells of a level are trimmed 16 at a time)
+constexpr int SEL_WARPS_BATCH = 4, SEL_WARPS_FEW = 16, SEL_FEW_FRAMES = 8;
 constexpr int SEL_WORK_CAP = 1024;  // entries of per-warp shared scratch; larger lists fall back to global memory + one lane
 
 // std::nth_element(a + first, a + nth, a + last, response >) by one warp; indices must stay below 65536.
@@ -202,6 +203,7 @@ constexpr int GATHER_WARPS = 4;
 
 __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_cells_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p,
                                                                          SelectBuffers buf) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int gcell = blockIdx.x * GATHER_WARPS + (threadIdx.x >> 5);  // cell index over all levels of the frame
   const int frame = blockIdx.y;
@@ -243,9 +245,12 @@ __global__ void __launch_bounds__(GATHER_WARPS * 32) gather_cells_kernel(const F
   }
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) select_kernel(const FrameGeom* __restrict__ geom, SelectBuffers buf,
-                                                             int max_cells, int lvl_cap) {
+template <int SEL_WARPS>
+__global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const FrameGeom* __restrict__ geom, SelectBuffers buf,
+                                                                int max_cells, int lvl_cap) {
+  constexpr int SEL_THREADS = SEL_WARPS * 32;
   extern __shared__ __align__(16) uint32_t smem[];
+  pdl_enter();
   int* n_total = reinterpret_cast<int*>(smem);
   int* n_retain = n_total + max_cells;
   int* offs = n_retain + max_cells;  // max_cells + 1 entries
@@ -383,24 +388,30 @@ static void select_caps(const FrameGeom& g, int* max_cells, int* lvl_cap) {
   *lvl_cap = lc;
 }
 
-size_t select_smem_bytes(const FrameGeom& g) {
+static size_t select_smem_bytes_w(const FrameGeom& g, int warps) {
   int mc, lc;
   select_caps(g, &mc, &lc);
-  return sizeof(uint32_t) * ((size_t)3 * mc + 1 + lc + (size_t)SEL_WARPS * SEL_WORK_CAP) +
-         sizeof(uint16_t) * (size_t)SEL_WARPS * 2 * SEL_WORK_CAP + 16;
+  return sizeof(uint32_t) * ((size_t)3 * mc + 1 + lc + (size_t)warps * SEL_WORK_CAP) +
+         sizeof(uint16_t) * (size_t)warps * 2 * SEL_WORK_CAP + 16;
 }
+size_t select_smem_bytes(const FrameGeom& g) { return select_smem_bytes_w(g, SEL_WARPS_FEW); }
 
 void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, const SelectBuffers& b, int nframes,
                    cudaStream_t s) {
   int mc, lc;
   select_caps(g, &mc, &lc);
   if (g.cells_total > 0)
-    gather_cells_kernel<<<dim3((g.cells_total + GATHER_WARPS - 1) / GATHER_WARPS, nframes), GATHER_WARPS * 32, 0, s>>>(d_geom, p, b);
+    launch_pdl(gather_cells_kernel, dim3((g.cells_total + GATHER_WARPS - 1) / GATHER_WARPS, nframes), dim3(GATHER_WARPS * 32), 0, s, d_geom, p, b);
   if (g.octree) {
     launch_octree(d_geom, g, b, nframes, s);
     return;
   }
-  select_kernel<<<dim3(g.nlevels, nframes), SEL_THREADS, select_smem_bytes(g), s>>>(d_geom, b, mc, lc);
+  if (nframes <= SEL_FEW_FRAMES && select_smem_bytes_w(g, SEL_WARPS_FEW) <= 200 * 1024)
+    launch_pdl(select_kernel<SEL_WARPS_FEW>, dim3(g.nlevels, nframes), dim3(SEL_WARPS_FEW * 32), select_smem_bytes_w(g, SEL_WARPS_FEW), s,
+               d_geom, b, mc, lc);
+  else
+    launch_pdl(select_kernel<SEL_WARPS_BATCH>, dim3(g.nlevels, nframes), dim3(SEL_WARPS_BATCH * 32), select_smem_bytes_w(g, SEL_WARPS_BATCH), s,
+               d_geom, b, mc, lc);
 }
 
 // ---- test hook
@@ -423,7 +434,9 @@ void launch_debug_nth_element(uint32_t* d_entries, int n, int nth, cudaStream_t 
 }
 
 int configure_kernels() {
-  return (int)cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = cudaFuncSetAttribute(select_kernel<SEL_WARPS_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(select_kernel<SEL_WARPS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  return (int)e;
 }
 
 }  // namespace sdorb

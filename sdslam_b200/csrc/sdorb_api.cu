@@ -13,6 +13,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sdorb.h"
@@ -56,6 +57,9 @@ struct sdorb_handle {
   uint32_t *d_cell_list = nullptr, *d_sel = nullptr;
   uint32_t* d_okeys = nullptr;  // ORB-SLAM2-style mode only
   uint16_t* d_onode = nullptr;
+  // imagePyramid staging of the host pipeline (2 slots of max_batch frames each, allocated when a caller asks for the pyramid)
+  uint8_t* d_pyr_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_pyr_pack[2]{};
   // output staging for the host path (2 slots)
   sdorb_keypoint* d_kps[2] = {nullptr, nullptr};
   uint8_t* d_desc[2] = {nullptr, nullptr};
@@ -67,6 +71,21 @@ struct sdorb_handle {
   // pinned staging for the pyramid read-back of the single-frame entry point
   uint8_t* h_pyr = nullptr;
   size_t h_pyr_bytes = 0;
+  uint8_t* d_pyr_pad = nullptr;  // frame 0's levels in the reference's padded form (launch_pack_padded), mirrored in h_pyr
+  size_t d_pyr_pad_bytes = 0;
+  // single-frame entry point (sdorb_extract, the call of Frame.cc:195): pinned result block, the event that says "the pyramid
+  // levels are in h_pyr", and the whole call captured once per geometry as a CUDA graph ([0] without, [1] with the pyramid)
+  uint8_t* h_res = nullptr;
+  size_t h_res_bytes = 0;
+  uint8_t* h_in = nullptr;  // pinned image staging: a strided / pitched upload becomes one linear copy
+  size_t h_in_bytes = 0;
+  cudaEvent_t ev_pyr_host = nullptr;
+  struct SingleGraph {
+    cudaGraphExec_t exec = nullptr;
+    int capacity = 0;
+    int64_t launches = 0, stage_launches[SDORB_NUM_STAGES] = {0};
+  } sg[2];
+  bool use_graph = true;  // SDORB_GRAPH=0 replays the same enqueue sequence on the streams instead
   // bookkeeping
   int64_t launches = 0;
   int64_t stage_launches[SDORB_NUM_STAGES] = {0};
@@ -108,7 +127,15 @@ void dfree(T*& p) {
   p = nullptr;
 }
 
+void free_single_graphs(sdorb_handle* h) {
+  for (auto& g : h->sg) {
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+    g = sdorb_handle::SingleGraph{};
+  }
+}
+
 void free_geometry_scratch(sdorb_handle* h) {
+  free_single_graphs(h);
   dfree(h->d_geom);
   dfree(h->d_taps);
   dfree(h->d_groups);
@@ -117,6 +144,10 @@ void free_geometry_scratch(sdorb_handle* h) {
   dfree(h->d_nms);
   dfree(h->d_stage_in[0]);
   dfree(h->d_stage_in[1]);
+  dfree(h->d_pyr_out[0]);
+  dfree(h->d_pyr_out[1]);
+  dfree(h->d_pyr_pad);
+  h->d_pyr_pad_bytes = 0;
   dfree(h->d_cell_seen);
   dfree(h->d_cell_list);
   dfree(h->d_okeys);
@@ -185,6 +216,7 @@ int ensure_host_staging(sdorb_handle* h, int capacity) {
     for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_stage_in[i], (size_t)h->geom.lv[0].plane_bytes * B + 256));
   }
   if (h->out_cap != capacity) {
+    free_single_graphs(h);
     for (int i = 0; i < 2; ++i) {
       dfree(h->d_kps[i]);
       dfree(h->d_desc[i]);
@@ -234,20 +266,36 @@ struct StageScope {
 };
 
 // Enqueue ORBextractor::operator() for `n` frames (n <= max_batch) whose level 0 is described by `planes`.
+enum { PASS_PYRAMID = 1, PASS_REST = 2, PASS_ALL = 3 };  // the pyramid is an output of its own (imagePyramid): it can be read back while the rest runs
+struct PyrOut {           // where enqueue_pass leaves imagePyramid for the n frames of the pass (nullptr: nowhere)
+  uint8_t* dst = nullptr;  // frame-major slab (sdorb_pyramid_layout), frame 0 of the pass
+  int first_level = 1;
+  cudaEvent_t done = nullptr;  // recorded on the stream once the slab is written (before FAST starts)
+};
 int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts,
-                 int capacity, cudaStream_t s) {
+                 int capacity, cudaStream_t s, int parts = PASS_ALL, const PyrOut* pyr = nullptr) {
   const FrameGeom& g = h->geom;
   planes.pyr = h->d_pyr;
   planes.blur = h->d_blur;
   planes.nms = h->d_nms;
   planes.batch_cap = h->prm.max_batch;
   SelectBuffers sb{h->d_cell_seen, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error, h->d_okeys, h->d_onode};
-  {
+  if (parts & PASS_PYRAMID) {
     StageScope st(h, s, SDORB_STAGE_PYRAMID);
     for (int l = 1; l < g.nlevels; ++l) {
       launch_resize_level(h->d_geom, g, l, planes, h->d_taps, h->d_groups, n, s);
       st.launched();
     }
+  }
+  if ((parts & PASS_PYRAMID) && pyr && pyr->dst) {
+    StageScope st(h, s, SDORB_STAGE_PYRAMID);
+    launch_pack_pyramid(h->d_geom, g, planes, pyr->first_level, pyr->dst, n, s);
+    st.launched();
+    if (pyr->done) CU(cudaEventRecord(pyr->done, s));
+  }
+  if (!(parts & PASS_REST)) {
+    CU(cudaGetLastError());
+    return SDORB_OK;
   }
   // The blur only needs the pyramid, FAST + selection only the pyramid too: the blur (byte dot products, FMA pipe) runs
   // on a second stream beside FAST (min / max, ALU pipe) and joins before the descriptors.
@@ -302,7 +350,8 @@ int check_deferred(sdorb_handle* h) {
 bool aligned16(const void* p, size_t a, size_t b) { return ((uintptr_t)p % 16 == 0) && (a % 16 == 0) && (b % 16 == 0); }
 
 int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height, size_t row_stride,
-                  size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int capacity);
+                  size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int capacity,
+                  uint8_t* pyramid, int first_level);
 
 }  // namespace
 
@@ -360,6 +409,8 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (cudaEventCreateWithFlags(&h->ev_pyr_host, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (const char* e = getenv("SDORB_GRAPH")) h->use_graph = e[0] != '0';
   if (const char* e = getenv("SDORB_OVERLAP")) h->overlap = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_TAPER")) h->pipe_taper = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_GROWTH")) h->pipe_growth_pct = std::min(std::max(atoi(e), 101), 1000);
@@ -371,6 +422,7 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
     if (cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
     if (cudaEventCreateWithFlags(&h->ev_compute[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
     if (cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+    if (cudaEventCreateWithFlags(&h->ev_pyr_pack[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   }
   if (cudaMalloc(&h->d_umax, sizeof(int) * 16) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
   if (cudaMemcpy(h->d_umax, h->tables.umax, sizeof(int) * 16, cudaMemcpyHostToDevice) != cudaSuccess) return fail(SDORB_ERR_CUDA);
@@ -397,6 +449,9 @@ void sdorb_destroy(sdorb_handle* h) {
     dfree(h->d_error);
     if (h->d_match_buf) cudaFree(h->d_match_buf);
     if (h->h_pyr) cudaFreeHost(h->h_pyr);
+    if (h->h_res) cudaFreeHost(h->h_res);
+    if (h->h_in) cudaFreeHost(h->h_in);
+    if (h->ev_pyr_host) cudaEventDestroy(h->ev_pyr_host);
     for (auto& p : h->pending) {
       cudaEventDestroy(p.a);
       cudaEventDestroy(p.b);
@@ -406,6 +461,7 @@ void sdorb_destroy(sdorb_handle* h) {
       if (h->ev_in[i]) cudaEventDestroy(h->ev_in[i]);
       if (h->ev_compute[i]) cudaEventDestroy(h->ev_compute[i]);
       if (h->ev_out[i]) cudaEventDestroy(h->ev_out[i]);
+      if (h->ev_pyr_pack[i]) cudaEventDestroy(h->ev_pyr_pack[i]);
     }
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -454,10 +510,77 @@ int sdorb_batch_status(sdorb_handle* h) {
   return e;
 }
 
+int sdorb_shard_range(int shard, int nshards, int nframes, int* first, int* last) {
+  if (shard < 0 || nshards <= 0 || shard >= nshards || nframes < 0 || !first || !last) return SDORB_ERR_BAD_ARG;
+  *first = (int)((int64_t)shard * nframes / nshards);
+  *last = (int)((int64_t)(shard + 1) * nframes / nshards);
+  return SDORB_OK;
+}
+
+// Frames are independent (operator() keeps no state, src/ORBextractor.cc:620-678): handle g of ndev -- one per GPU -- extracts the
+// contiguous range sdorb_shard_range(g, ndev, nframes) on its own host thread through the host pipeline, straight into the
+// caller's slabs.  No exchange between the GPUs; the "gather" is that all threads write disjoint ranges of one host result.
+int sdorb_extract_batch_multi(sdorb_handle* const* handles, int ndev, const uint8_t* images, int nframes, int width, int height,
+                              size_t row_stride, size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors,
+                              int32_t* counts, int capacity, uint8_t* pyramid, int first_level) {
+  if (!handles || ndev <= 0 || nframes < 0) return SDORB_ERR_BAD_ARG;
+  for (int g = 0; g < ndev; ++g) {
+    if (!handles[g]) return SDORB_ERR_BAD_ARG;
+    for (int k = 0; k < g; ++k)
+      if (handles[k] == handles[g]) return SDORB_ERR_BAD_ARG;  // a handle is not re-entrant
+  }
+  if (nframes == 0) return SDORB_OK;
+  size_t pyr_frame = 0;
+  if (pyramid) {
+    const int rc = sdorb_pyramid_layout(handles[0], width, height, nullptr, &pyr_frame);
+    if (rc) return rc;
+  }
+  std::vector<int> rcs((size_t)ndev, SDORB_OK);
+  auto work = [&](int g) {
+    int lo = 0, hi = 0;
+    sdorb_shard_range(g, ndev, nframes, &lo, &hi);
+    if (hi <= lo) return;
+    rcs[(size_t)g] = sdorb_extract_batch_pyr(handles[g], images + (size_t)lo * frame_stride, hi - lo, width, height, row_stride, frame_stride,
+                                             keypoints ? keypoints + (size_t)lo * capacity : nullptr,
+                                             descriptors ? descriptors + (size_t)lo * capacity * 32 : nullptr, counts ? counts + lo : nullptr,
+                                             capacity, pyramid ? pyramid + (size_t)lo * pyr_frame : nullptr, first_level, SDORB_MEM_HOST,
+                                             nullptr);
+  };
+  std::vector<std::thread> pool;
+  for (int g = 1; g < ndev; ++g) pool.emplace_back(work, g);
+  work(0);  // the calling thread drives the first GPU
+  for (auto& t : pool) t.join();
+  for (int g = 0; g < ndev; ++g)
+    if (rcs[(size_t)g]) return rcs[(size_t)g];
+  return SDORB_OK;
+}
+
+int sdorb_pyramid_layout(const sdorb_handle* h, int width, int height, size_t* level_offset, size_t* frame_bytes) {
+  if (!h || width <= 0 || height <= 0) return SDORB_ERR_BAD_ARG;
+  size_t off = 0;
+  for (int l = 0; l < h->tables.nlevels; ++l) {
+    int lw = 0, lh = 0;
+    const int rc = sdorb_level_size(h, width, height, l, &lw, &lh);
+    if (rc) return rc;
+    if (level_offset) level_offset[l] = off;
+    off += ((size_t)std::max(lw, 0) * (size_t)std::max(lh, 0) + 15) / 16 * 16;
+  }
+  if (frame_bytes) *frame_bytes = off;
+  return SDORB_OK;
+}
+
 int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height, size_t row_stride,
                         size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts,
                         int capacity, int mem, void* stream) {
+  return sdorb_extract_batch_pyr(h, images, nframes, width, height, row_stride, frame_stride, keypoints, descriptors, counts, capacity,
+                                 nullptr, 1, mem, stream);
+}
+
+int sdorb_extract_batch_pyr(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height, size_t row_stride,
+                            size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts,
+                            int capacity, uint8_t* pyramid, int first_level, int mem, void* stream) {
   if (!h || nframes < 0 || (mem != SDORB_MEM_HOST && mem != SDORB_MEM_DEVICE)) return SDORB_ERR_BAD_ARG;
+  if (pyramid && (first_level < 0 || first_level > 1 || (mem == SDORB_MEM_DEVICE && (uintptr_t)pyramid % 16))) return SDORB_ERR_BAD_ARG;
   if (nframes == 0) return SDORB_OK;
   if (!images || !keypoints || !descriptors || !counts || width <= 0 || height <= 0 || row_stride < (size_t)width ||
       (nframes > 1 && frame_stride < row_stride * (size_t)(height - 1) + (size_t)width))
@@ -488,8 +611,15 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
         pl.img0_frame_stride = L0.plane_bytes;
         pl.img0_pitch = L0.pitch;
       }
+      PyrOut po;
+      if (pyramid) {
+        int64_t off[SDORB_MAX_LEVELS], fb = 0;
+        pyramid_layout(h->geom, off, &fb);
+        po.dst = pyramid + (size_t)f0 * (size_t)fb;
+        po.first_level = first_level;
+      }
       rc = enqueue_pass(h, pl, n, keypoints + (size_t)f0 * capacity, descriptors + (size_t)f0 * capacity * 32, counts + f0,
-                        capacity, s);
+                        capacity, s, PASS_ALL, &po);
       if (rc) return rc;
     }
     return SDORB_OK;
@@ -504,7 +634,8 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
   if (rc) return rc;
   // Any failure after the first enqueue leaves copies into / out of the caller's buffers in flight on three (four) streams:
   // drain them before the error is returned, so that the caller may free or reuse its buffers right away.
-  rc = host_pipeline(h, images, nframes, width, height, row_stride, frame_stride, keypoints, descriptors, counts, capacity);
+  rc = host_pipeline(h, images, nframes, width, height, row_stride, frame_stride, keypoints, descriptors, counts, capacity, pyramid,
+                     first_level);
   if (rc) {
     cudaStreamSynchronize(h->s_in);
     cudaStreamSynchronize(h->s_compute);
@@ -519,10 +650,15 @@ int sdorb_extract_batch(sdorb_handle* h, const uint8_t* images, int nframes, int
 
 namespace {
 int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width, int height, size_t row_stride,
-                  size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int capacity) {
+                  size_t frame_stride, sdorb_keypoint* keypoints, uint8_t* descriptors, int32_t* counts, int capacity,
+                  uint8_t* pyramid, int first_level) {
   const int B = h->prm.max_batch;
   const LevelGeom& L0 = h->geom.lv[0];
   int rc = SDORB_OK;
+  int64_t pyr_off[SDORB_MAX_LEVELS], pyr_frame = 0;
+  pyramid_layout(h->geom, pyr_off, &pyr_frame);
+  if (pyramid && !h->d_pyr_out[0])
+    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_pyr_out[i], (size_t)pyr_frame * B + 256));
   int pass = 0;
   const int n_min = std::max(B / 8, 1);
   int ramp = n_min;
@@ -569,10 +705,25 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
     pl.img0 = h->d_stage_in[slot];
     pl.img0_frame_stride = L0.plane_bytes;
     pl.img0_pitch = L0.pitch;
-    rc = enqueue_pass(hc, pl, n, h->d_kps[slot], h->d_desc[slot], h->d_counts[slot], capacity, cs);
+    PyrOut po;
+    po.dst = pyramid ? h->d_pyr_out[slot] : nullptr;
+    po.first_level = first_level;
+    po.done = h->ev_pyr_pack[slot];
+    rc = enqueue_pass(hc, pl, n, h->d_kps[slot], h->d_desc[slot], h->d_counts[slot], capacity, cs, PASS_ALL, &po);
     if (rc) {
       if (hc != h) h->cuda_error = hc->cuda_error;
       return rc;
+    }
+    if (pyramid) {
+      // the pyramid slab of the pass is complete before FAST starts: its (large) copy to the host runs beside the other kernels
+      CU(cudaStreamWaitEvent(h->s_out, h->ev_pyr_pack[slot], 0));
+      if (first_level == 0) {
+        CU(cudaMemcpyAsync(pyramid + (size_t)f0 * pyr_frame, h->d_pyr_out[slot], (size_t)pyr_frame * n, cudaMemcpyDeviceToHost, h->s_out));
+      } else {  // level 0 is the caller's own input: skip its bytes of every frame
+        const size_t skip = (size_t)pyr_off[first_level];
+        CU(cudaMemcpy2DAsync(pyramid + (size_t)f0 * pyr_frame + skip, (size_t)pyr_frame, h->d_pyr_out[slot] + skip, (size_t)pyr_frame,
+                             (size_t)pyr_frame - skip, (size_t)n, cudaMemcpyDeviceToHost, h->s_out));
+      }
     }
     CU(cudaEventRecord(h->ev_compute[slot], cs));
     CU(cudaStreamWaitEvent(h->s_out, h->ev_compute[slot], 0));
@@ -613,6 +764,23 @@ extern "C" {
 
 void sdorb_fill_border_reflect101(uint8_t* origin, int width, int height, size_t stride, int border) {
   if (!origin || width <= 0 || height <= 0 || border <= 0) return;
+  if (border < width && border < height) {  // the usual case: one reflection, no index arithmetic per pixel
+    for (int y = 0; y < height; ++y) {
+      uint8_t* row = origin + (ptrdiff_t)y * (ptrdiff_t)stride;
+      uint8_t* re = row + width - 1;
+      for (int x = 1; x <= border; ++x) {
+        row[-x] = row[x];
+        re[x] = re[-x];
+      }
+    }
+    const size_t n = (size_t)width + 2 * (size_t)border;
+    for (int y = 1; y <= border; ++y) {
+      memcpy(origin - (ptrdiff_t)y * (ptrdiff_t)stride - border, origin + (ptrdiff_t)y * (ptrdiff_t)stride - border, n);
+      memcpy(origin + (ptrdiff_t)(height - 1 + y) * (ptrdiff_t)stride - border,
+             origin + (ptrdiff_t)(height - 1 - y) * (ptrdiff_t)stride - border, n);
+    }
+    return;
+  }
   auto refl = [](int p, int len) {
     if (len == 1) return 0;
     while ((unsigned)p >= (unsigned)len) p = p < 0 ? -p : 2 * (len - 1) - p;
@@ -667,62 +835,233 @@ int sdorb_host_level_geometry(int nfeatures, float scale_factor, int nlevels, in
   return SDORB_OK;
 }
 
+}  // extern "C"
+
+namespace {
+size_t up64(size_t v) { return (v + 63) / 64 * 64; }
+
+// One single-frame call after the upload of the image, in two parts that are each captured once per geometry as a CUDA graph
+// (or enqueued on the stream as they are): part 0 = the pyramid kernels, part 1 = FAST .. describe and the copies of the
+// results, the count and the error flag into the pinned block.  Frame 0 of staging slot 0 is the frame.  Between the two the
+// caller forks the read-back of the pyramid levels onto s_out with ordinary stream calls: a host thread can wait on an event
+// recorded by a stream call, while an event-record NODE inside a graph only changes the event's state when it executes.
+int enqueue_single_part(sdorb_handle* h, int capacity, int part) {
+  cudaStream_t s = h->s_compute;
+  const LevelGeom& L0 = h->geom.lv[0];
+  BatchPlanes pl{};
+  pl.img0 = h->d_stage_in[0];
+  pl.img0_frame_stride = L0.plane_bytes;
+  pl.img0_pitch = L0.pitch;
+  int rc = enqueue_pass(h, pl, 1, h->d_kps[0], h->d_desc[0], h->d_counts[0], capacity, s, part == 0 ? PASS_PYRAMID : PASS_REST);
+  if (rc || part == 0) return rc;
+  uint8_t* r = h->h_res;
+  const size_t bK = sizeof(sdorb_keypoint) * (size_t)capacity, bD = (size_t)32 * capacity;
+  CU(cudaMemcpyAsync(r, h->d_kps[0], bK, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(r + up64(bK), h->d_desc[0], bD, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(r + up64(bK) + up64(bD), h->d_counts[0], sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(r + up64(bK) + up64(bD) + 64, h->d_error, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  return SDORB_OK;
+}
+
+// Runs one part: replays its graph (capturing it first if needed), or enqueues it directly when graphs are off / profiling is on.
+int run_single_part(sdorb_handle* h, int capacity, int part) {
+  cudaStream_t s = h->s_compute;
+  if (!h->use_graph || h->profiling) return enqueue_single_part(h, capacity, part);
+  sdorb_handle::SingleGraph& sg = h->sg[part];
+  if (sg.exec && sg.capacity != capacity) {
+    cudaGraphExecDestroy(sg.exec);
+    sg = sdorb_handle::SingleGraph{};
+  }
+  if (!sg.exec) {
+    // every pointer in the capture belongs to the handle and is stable until the geometry or the capacity changes
+    const int64_t l0 = h->launches;
+    int64_t st0[SDORB_NUM_STAGES];
+    for (int i = 0; i < SDORB_NUM_STAGES; ++i) st0[i] = h->stage_launches[i];
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = enqueue_single_part(h, capacity, part);
+    const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+    sg.launches = h->launches - l0;
+    h->launches = l0;
+    for (int i = 0; i < SDORB_NUM_STAGES; ++i) {
+      sg.stage_launches[i] = h->stage_launches[i] - st0[i];
+      h->stage_launches[i] = st0[i];
+    }
+    if (rc || ce != cudaSuccess || !graph) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc) return rc;
+      h->cuda_error = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(ce);
+      return SDORB_ERR_CUDA;
+    }
+    const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) {
+      sg.exec = nullptr;
+      h->cuda_error = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie);
+      return SDORB_ERR_CUDA;
+    }
+    sg.capacity = capacity;
+  }
+  CU(cudaGraphLaunch(sg.exec, s));
+  h->launches += sg.launches;
+  for (int i = 0; i < SDORB_NUM_STAGES; ++i) h->stage_launches[i] += sg.stage_launches[i];
+  return SDORB_OK;
+}
+}  // namespace
+
+extern "C" {
+
 int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, size_t stride, sdorb_keypoint* keypoints,
                   uint8_t* descriptors, int capacity, int* count, const sdorb_pyr_view* pyramid) {
   if (!h) return SDORB_ERR_BAD_ARG;
   if (!image || width <= 0 || height <= 0) return SDORB_OK;  // empty image: outputs untouched (src/ORBextractor.cc:622-623)
-  if (!keypoints || !descriptors || !count) return SDORB_ERR_BAD_ARG;
-  int32_t n = 0;
-  int rc = sdorb_extract_batch(h, image, 1, width, height, stride, stride * (size_t)height, keypoints, descriptors, &n,
-                               capacity, SDORB_MEM_HOST, nullptr);
+  if (!keypoints || !descriptors || !count || stride < (size_t)width) return SDORB_ERR_BAD_ARG;
+  if (capacity < sdorb_max_keypoints(h)) return SDORB_ERR_CAPACITY;
+  DeviceGuard guard(h->device);
+  int rc = ensure_geometry(h, width, height);
   if (rc) return rc;
-  *count = n;
-  if (pyramid) {
-    // imagePyramid (src/ORBextractor.cc:684-696).  Level 0 is the caller's own image: host-to-host.  Levels >= 1 come back
-    // through one pinned staging buffer with all copies in flight at once, then are laid into the caller's views.
-    DeviceGuard guard(h->device);
-    const int nl = h->geom.nlevels;
-    size_t need = 0;
-    for (int l = 1; l < nl; ++l) need += (size_t)h->geom.lv[l].w * h->geom.lv[l].h;
-    if (need > h->h_pyr_bytes) {
+  rc = ensure_host_staging(h, capacity);
+  if (rc) return rc;
+  const FrameGeom& g = h->geom;
+  const LevelGeom& L0 = g.lv[0];
+  const int nl = g.nlevels;
+  const bool with_pyr = pyramid != nullptr;
+  const size_t bK = sizeof(sdorb_keypoint) * (size_t)capacity, bD = (size_t)32 * capacity;
+  const size_t need_res = up64(bK) + up64(bD) + 128;
+  if (need_res > h->h_res_bytes) {
+    free_single_graphs(h);
+    if (h->h_res) cudaFreeHost(h->h_res);
+    h->h_res = nullptr;
+    h->h_res_bytes = 0;
+    CU(cudaMallocHost(&h->h_res, need_res));
+    h->h_res_bytes = need_res;
+  }
+  int64_t pad_off[SDORB_MAX_LEVELS];
+  const size_t pad_bytes = (size_t)padded_pyramid_layout(g, pad_off);
+  if (with_pyr) {
+    if (pad_bytes > h->h_pyr_bytes) {
       if (h->h_pyr) cudaFreeHost(h->h_pyr);
       h->h_pyr = nullptr;
       h->h_pyr_bytes = 0;
-      CU(cudaMallocHost(&h->h_pyr, need));
-      h->h_pyr_bytes = need;
+      CU(cudaMallocHost(&h->h_pyr, pad_bytes));
+      h->h_pyr_bytes = pad_bytes;
+    }
+    if (pad_bytes > h->d_pyr_pad_bytes) {
+      dfree(h->d_pyr_pad);
+      h->d_pyr_pad_bytes = 0;
+      CU(cudaMalloc(&h->d_pyr_pad, pad_bytes));
+      h->d_pyr_pad_bytes = pad_bytes;
     }
     for (int l = 0; l < nl; ++l) {
-      const LevelGeom& L = h->geom.lv[l];
+      const LevelGeom& L = g.lv[l];
       const sdorb_pyr_view& v = pyramid[l];
       if (v.data && (v.width != L.w || v.height != L.h || v.stride < (size_t)L.w)) return SDORB_ERR_BAD_ARG;
     }
-    size_t off = 0;
-    for (int l = 1; l < nl; ++l) {
-      const LevelGeom& L = h->geom.lv[l];
-      if (pyramid[l].data)
-        CU(cudaMemcpy2DAsync(h->h_pyr + off, L.w, h->d_pyr + (size_t)L.plane_base * h->prm.max_batch, L.pitch, L.w, L.h,
-                             cudaMemcpyDeviceToHost, h->s_compute));
-      off += (size_t)L.w * L.h;
+  }
+  cudaStream_t s = h->s_compute;
+  if (stride == (size_t)width && (size_t)L0.pitch == stride) {
+    CU(cudaMemcpyAsync(h->d_stage_in[0], image, (size_t)width * height, cudaMemcpyHostToDevice, s));
+  } else {
+    // a 2-D copy from pageable memory is issued row by row (measured: +70 us at 752x480): repack the rows into a pinned
+    // buffer with the device pitch and send them as one linear copy
+    const size_t need_in = (size_t)L0.pitch * height;
+    if (need_in > h->h_in_bytes) {
+      if (h->h_in) cudaFreeHost(h->h_in);
+      h->h_in = nullptr;
+      h->h_in_bytes = 0;
+      CU(cudaMallocHost(&h->h_in, need_in));
+      h->h_in_bytes = need_in;
     }
-    if (pyramid[0].data) {  // overlaps the copies above
-      const sdorb_pyr_view& v = pyramid[0];
-      for (int y = 0; y < height; ++y) memcpy(v.data + (size_t)y * v.stride, image + (size_t)y * stride, (size_t)width);
-      if (v.border > 0) sdorb_fill_border_reflect101(v.data, width, height, v.stride, v.border);
+    for (int y = 0; y < height; ++y) memcpy(h->h_in + (size_t)y * L0.pitch, image + (size_t)y * stride, (size_t)width);
+    CU(cudaMemcpyAsync(h->d_stage_in[0], h->h_in, need_in, cudaMemcpyHostToDevice, s));
+  }
+  auto drain = [&](int code) {  // nothing of a failed call may stay in flight
+    cudaStreamSynchronize(s);
+    cudaStreamSynchronize(h->s_out);
+    cudaGetLastError();
+    return code;
+  };
+  rc = run_single_part(h, capacity, 0);
+  if (rc) return drain(rc);
+  if (with_pyr && cudaEventRecord(h->ev_fork, s) != cudaSuccess) return drain(SDORB_ERR_CUDA);
+  rc = run_single_part(h, capacity, 1);  // queued right behind the pyramid: the compute chain has no gap
+  if (rc) return drain(rc);
+  if (with_pyr) {
+    // imagePyramid is complete after part 0.  On s_out, beside FAST .. describe: one kernel lays all levels out in the padded
+    // form the reference returns (19 px of BORDER_REFLECT_101 around each), one copy brings them to the pinned buffer.
+    cudaError_t e = cudaStreamWaitEvent(h->s_out, h->ev_fork, 0);
+    if (e == cudaSuccess) {
+      BatchPlanes pl{};
+      pl.img0 = h->d_stage_in[0];
+      pl.img0_frame_stride = L0.plane_bytes;
+      pl.img0_pitch = L0.pitch;
+      pl.pyr = h->d_pyr;
+      pl.batch_cap = h->prm.max_batch;
+      launch_pack_padded(h->d_geom, g, pl, 1, h->d_pyr_pad, h->s_out);
+      ++h->launches;
+      ++h->stage_launches[SDORB_STAGE_PYRAMID];
+      e = cudaGetLastError();
     }
-    CU(cudaStreamSynchronize(h->s_compute));
-    off = 0;
-    for (int l = 1; l < nl; ++l) {
-      const LevelGeom& L = h->geom.lv[l];
-      const sdorb_pyr_view& v = pyramid[l];
-      if (v.data) {
-        for (int y = 0; y < L.h; ++y) memcpy(v.data + (size_t)y * v.stride, h->h_pyr + off + (size_t)y * L.w, (size_t)L.w);
-        if (v.border > 0) sdorb_fill_border_reflect101(v.data, L.w, L.h, v.stride, v.border);
-      }
-      off += (size_t)L.w * L.h;
+    if (e == cudaSuccess && nl > 1)
+      e = cudaMemcpyAsync(h->h_pyr + pad_off[1], h->d_pyr_pad + pad_off[1], pad_bytes - (size_t)pad_off[1], cudaMemcpyDeviceToHost, h->s_out);
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev_pyr_host, h->s_out);
+    if (e != cudaSuccess) {
+      h->cuda_error = std::string("pyramid read-back: ") + cudaGetErrorString(e);
+      return drain(SDORB_ERR_CUDA);
     }
   }
+  if (with_pyr) {
+    // imagePyramid (src/ORBextractor.cc:684-696), laid into the caller's views while FAST .. describe still run.  A view
+    // with the reference's own layout (19 px of border, rows w + 38 apart) takes its whole padded buffer in one copy.
+    // Level 0 is the caller's own image: host to host, while the other levels are still on their way.
+    if (pyramid[0].data) {
+      const sdorb_pyr_view& v = pyramid[0];
+      if (v.stride == stride && stride == (size_t)width)
+        memcpy(v.data, image, (size_t)width * height);
+      else
+        for (int y = 0; y < height; ++y) memcpy(v.data + (size_t)y * v.stride, image + (size_t)y * stride, (size_t)width);
+      if (v.border > 0) sdorb_fill_border_reflect101(v.data, width, height, v.stride, v.border);
+    }
+    CU(cudaEventSynchronize(h->ev_pyr_host));
+    for (int l = 1; l < nl; ++l) {
+      const LevelGeom& L = g.lv[l];
+      const sdorb_pyr_view& v = pyramid[l];
+      if (!v.data) continue;
+      const size_t pw = (size_t)L.w + 2 * SDORB_EDGE;
+      const uint8_t* src = h->h_pyr + pad_off[l];
+      if (v.border == SDORB_EDGE && v.stride == pw) {
+        memcpy(v.data - (size_t)SDORB_EDGE * pw - SDORB_EDGE, src, pw * ((size_t)L.h + 2 * SDORB_EDGE));
+      } else if (v.border >= 0 && v.border <= SDORB_EDGE) {  // any smaller border is a sub-rectangle of the padded level
+        const int b = v.border;
+        for (int y = -b; y < L.h + b; ++y)
+          memcpy(v.data + (ptrdiff_t)y * (ptrdiff_t)v.stride - b, src + (size_t)(y + SDORB_EDGE) * pw + SDORB_EDGE - b, (size_t)L.w + 2 * (size_t)b);
+      } else {
+        for (int y = 0; y < L.h; ++y) memcpy(v.data + (size_t)y * v.stride, src + (size_t)(y + SDORB_EDGE) * pw + SDORB_EDGE, (size_t)L.w);
+        sdorb_fill_border_reflect101(v.data, L.w, L.h, v.stride, v.border);
+      }
+    }
+  }
+  CU(cudaStreamSynchronize(s));
+  const uint8_t* r = h->h_res;
+  int32_t n = 0, err = 0;
+  memcpy(&n, r + up64(bK) + up64(bD), sizeof(n));
+  memcpy(&err, r + up64(bK) + up64(bD) + 64, sizeof(err));
+  if (err) {
+    int zero = 0;
+    CU(cudaMemcpy(h->d_error, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    return -err;
+  }
+  if (n < 0 || n > capacity) return SDORB_ERR_OVERFLOW;
+  memcpy(keypoints, r, sizeof(sdorb_keypoint) * (size_t)n);
+  memcpy(descriptors, r + up64(bK), (size_t)32 * n);
+  *count = n;
   return SDORB_OK;
 }
+
+}  // extern "C"
+
+extern "C" {
 
 namespace {
 // scratch for the host-memory forms of the small batched entry points: one growing device buffer, carved by the caller
@@ -1464,6 +1803,18 @@ int sdorb_get_stage_times(sdorb_handle* h, double* ms, int64_t* launches, int re
 }
 
 int64_t sdorb_kernel_launches(const sdorb_handle* h) { return h ? h->launches : 0; }
+
+int sdorb_debug_pipe_probe(sdorb_handle* h, int pipe, double* warp_instr_per_s, double* warp_instr_per_clk_per_sm) {
+  if (!h || pipe < 0 || pipe > 2) return SDORB_ERR_BAD_ARG;
+  DeviceGuard guard(h->device);
+  const int e = run_pipe_probe(pipe, h->s_compute, warp_instr_per_s, warp_instr_per_clk_per_sm);
+  h->launches += 2;
+  if (e) {
+    h->cuda_error = std::string("pipe probe: ") + cudaGetErrorString((cudaError_t)e);
+    return SDORB_ERR_CUDA;
+  }
+  return SDORB_OK;
+}
 
 int sdorb_debug_nth_element(sdorb_handle* h, uint32_t* entries, int n, int nth) {
   if (!h || !entries || n <= 0 || nth < 0 || nth >= n || n > 65535) return SDORB_ERR_BAD_ARG;

@@ -401,6 +401,158 @@ def test_pyramid_then_match_then_pyramid_on_one_handle():
     ex.close()
 
 
+@pytest.mark.parametrize("first_level", [0, 1])
+def test_batch_pyramid_output_equals_oracle(first_level):
+    """sdorb_extract_batch_pyr: the reference's fifth output (imagePyramid, src/ORBextractor.cc:620-621) for a batch, host and
+    device memory, more frames than one pass, levels compared byte for byte with the oracle's pyramid."""
+    import torch
+    w, h, nf = 333, 257, 11
+    params = (700, 1.2, 6, 12)
+    imgs = synth.frames(nf, w, h, start=300)
+    ex = api.ORBextractor(*params, max_width=w, max_height=h, max_batch=4)
+    off, fb = ex.pyramid_layout(w, h)
+    assert fb % 16 == 0 and all(o % 16 == 0 for o in off)
+    slab = np.full(nf * fb, 0xAB, np.uint8)
+    k, d, c = ex.extract_batch_host(imgs, pyramid=slab, first_level=first_level)
+    o = orc.Extractor(*params)
+    dev = torch.device("cuda", 0)
+    dimgs = torch.from_numpy(imgs).to(dev)
+    cap = ex.max_keypoints
+    dk = torch.zeros((nf, cap, 7), dtype=torch.float32, device=dev)
+    dd = torch.zeros((nf, cap, 32), dtype=torch.uint8, device=dev)
+    dc = torch.zeros(nf, dtype=torch.int32, device=dev)
+    dslab = torch.full((nf * fb,), 0xAB, dtype=torch.uint8, device=dev)
+    ex.extract_batch_device(dimgs, dk, dd, dc, pyramid=dslab, first_level=first_level)
+    torch.cuda.synchronize()
+    ex.batch_status()
+    hslab = dslab.cpu().numpy()
+    for f in range(nf):
+        ok, od, st = o.extract(imgs[f], dump=True)
+        assert c[f] == len(ok) and k[f, :c[f]].tobytes() == ok.tobytes() and np.array_equal(d[f, :c[f]], od)
+        po = 0
+        for which, sl in (("host", slab), ("device", hslab)):
+            lv = ex.pyramid_levels(sl, f, w, h)
+            po = 0
+            for l, g in enumerate(st["geometry"]):
+                lw, lh = int(g["width"]), int(g["height"])
+                exp = st["pyramid"][po:po + lw * lh].reshape(lh, lw)
+                po += lw * lh
+                if l == 0 and first_level == 1:
+                    assert (lv[0] == 0xAB).all(), "level 0 must stay untouched with first_level = 1"
+                else:
+                    assert np.array_equal(lv[l], exp), "%s slab: frame %d level %d" % (which, f, l)
+    ex.close()
+
+
+@pytest.mark.parametrize("border,extra_stride", [(0, 0), (0, 13), (5, 0), (5, 7), (19, 3), (25, 0)])
+def test_pyramid_views_of_any_border_and_stride(border, extra_stride):
+    """sdorb_pyr_view with layouts other than the reference's own (19 px border, rows w + 38 apart): tight levels, smaller and
+    larger borders, padded strides -- the level bytes and the BORDER_REFLECT_101 margin must equal the oracle's."""
+    w, h = 200, 160
+    params = (300, 1.2, 4, 20)
+    img = synth.smooth_noise(810, w, h)
+    ex = api.ORBextractor(*params, max_width=w, max_height=h, max_batch=1)
+    cap = ex.max_keypoints
+    kps, desc, n = np.zeros(cap, api.KP_DTYPE), np.zeros((cap, 32), np.uint8), C.c_int(0)
+    views = (api._PyrView * 4)()
+    bufs = []
+    for l in range(4):
+        lw, lh = ex.level_size(w, h, l)
+        buf = np.full((lh + 2 * border, lw + 2 * border + extra_stride), 0xCD, np.uint8)
+        bufs.append(buf)
+        inner = buf[border:border + lh, border:border + lw]
+        views[l] = api._PyrView(inner.ctypes.data, lw, lh, buf.strides[0], border)
+    rc = api.lib().sdorb_extract(ex._h, img.ctypes.data_as(C.c_void_p), w, h, img.strides[0], kps.ctypes.data_as(C.c_void_p),
+                                 desc.ctypes.data_as(C.c_void_p), cap, C.byref(n), C.cast(views, C.c_void_p))
+    assert rc == 0
+    ok, od, st = orc.Extractor(*params).extract(img, dump=True)
+    assert kps[:n.value].tobytes() == ok.tobytes()
+    po = 0
+    for l, g in enumerate(st["geometry"]):
+        lw, lh = int(g["width"]), int(g["height"])
+        exp = st["pyramid"][po:po + lw * lh].reshape(lh, lw)
+        po += lw * lh
+        got = bufs[l][:, :lw + 2 * border]
+        want = orc.border_reflect101(np.ascontiguousarray(exp), border) if border else exp
+        assert np.array_equal(got, want), "level %d" % l
+        if extra_stride:
+            assert (bufs[l][:, lw + 2 * border:] == 0xCD).all(), "bytes beyond the view were written"
+    ex.close()
+
+
+def test_single_frame_call_with_and_without_graph(monkeypatch):
+    """sdorb_extract replays two captured CUDA graphs per call (pyramid | FAST .. describe + result copies); SDORB_GRAPH=0
+    enqueues the same sequence on the streams.  Same bytes either way, over changing images, sizes and pyramid on / off."""
+    o = orc.Extractor(*C1)
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("SDORB_GRAPH", mode)
+        ex = api.ORBextractor(*C1, max_width=752, max_height=480, max_batch=1)
+        res = []
+        for i, (w, h, want) in enumerate([(640, 480, True), (640, 480, False), (640, 480, True), (752, 480, True), (752, 480, False),
+                                          (640, 480, True), (320, 240, True)]):
+            img = synth.smooth_noise(700 + i, w, h)
+            k, d, pyr = ex(img, want_pyramid=want)
+            ok, od, st = o.extract(img, dump=True)
+            assert_same(ok, od, k, d, "graph=%s call %d" % (mode, i))
+            if want:
+                po = 0
+                for l, g in enumerate(st["geometry"]):
+                    lw, lh = int(g["width"]), int(g["height"])
+                    assert np.array_equal(pyr[l], st["pyramid"][po:po + lw * lh].reshape(lh, lw)), "graph=%s call %d level %d" % (mode, i, l)
+                    assert np.array_equal(pyr[l].base, orc.border_reflect101(np.ascontiguousarray(pyr[l]), 19))
+                    po += lw * lh
+            res.append((k.tobytes(), d.tobytes()))
+        assert ex.kernel_launches() > 0
+        outs[mode] = res
+        ex.close()
+    assert outs["1"] == outs["0"]
+
+
+@pytest.mark.parametrize("ndev", [2, 3])
+def test_multi_handle_driver_equals_single_handle(ndev):
+    """sdorb_extract_batch_multi (the C-level multi-GPU driver): handles on their own host threads over contiguous frame ranges
+    of ONE host batch.  With a single B200 the handles share device 0 (two contexts' worth of streams running concurrently);
+    with several devices each handle gets its own (N-GPU output == 1-GPU output byte for byte)."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    params = (500, 1.2, 6, 20)
+    w, h, nf = 320, 240, 23
+    imgs = synth.frames(nf, w, h, start=900)
+    single = api.ORBextractor(*params, device=0, max_width=w, max_height=h, max_batch=5)
+    off, fb = single.pyramid_layout(w, h)
+    slab1 = np.zeros(nf * fb, np.uint8)
+    k1, d1, c1 = single.extract_batch_host(imgs, pyramid=slab1, first_level=0)
+    single.close()
+    exs = [api.ORBextractor(*params, device=g % ngpu, max_width=w, max_height=h, max_batch=4) for g in range(ndev)]
+    slab = np.zeros(nf * fb, np.uint8)
+    k, d, c = api.extract_batch_multi(exs, imgs, pyramid=slab, first_level=0)
+    for e in exs:
+        e.close()
+    assert np.array_equal(c, c1) and k.tobytes() == k1.tobytes() and d.tobytes() == d1.tobytes() and slab.tobytes() == slab1.tobytes()
+    o = orc.Extractor(*params)
+    for f in (0, nf // ndev, nf - 1):
+        ok, od = o.extract(imgs[f])
+        assert c[f] == len(ok) and k[f, :c[f]].tobytes() == ok.tobytes() and np.array_equal(d[f, :c[f]], od)
+
+
+def test_every_device_gives_identical_bytes():
+    """Hardware N-GPU == 1-GPU identity: the same frames extracted on every visible device (skips below two devices)."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two GPUs")
+    imgs = synth.frames(16, start=40)
+    ref = None
+    for g in range(ngpu):
+        ex = api.ORBextractor(*C1, device=g, max_width=640, max_height=480, max_batch=16)
+        out = ex.extract_batch_host(imgs)
+        ex.close()
+        blob = out[0].tobytes() + out[1].tobytes() + out[2].tobytes()
+        ref = ref or blob
+        assert blob == ref, "device %d differs from device 0" % g
+
+
 def test_oversized_batches_are_rejected(ex_c1):
     """Entry points whose batch index rides on gridDim.y refuse more than SDORB_MAX_GRID_BATCH frames up front."""
     n = 65536

@@ -28,6 +28,17 @@ def test_frame_range_partitions():
         sharding.frame_range(2, 2, 10)
 
 
+def test_c_abi_shard_range_equals_python():
+    """sdorb_shard_range (the split sdorb_extract_batch_multi uses) == sharding.frame_range; needs no GPU."""
+    from sdslam_b200 import api
+    for world in (1, 2, 3, 4, 8):
+        for n in (0, 1, 5, 8, 4096, 4099):
+            for r in range(world):
+                assert api.shard_range(r, world, n) == sharding.frame_range(r, world, n)
+    with pytest.raises(api.SdorbError):
+        api.shard_range(2, 2, 10)
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
