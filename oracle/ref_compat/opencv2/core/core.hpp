@@ -31,6 +31,9 @@
 #include <cstring>
 #include <exception>
 #include <iterator>
+#include <list>
+#include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -43,10 +46,16 @@ typedef unsigned short ushort;
 #define CV_CN_SHIFT 3
 #define CV_DEPTH_MAX (1 << CV_CN_SHIFT)
 #define CV_8U 0
+#define CV_32F 5
+#define CV_64F 6
 #define CV_MAT_DEPTH_MASK (CV_DEPTH_MAX - 1)
 #define CV_MAT_DEPTH(flags) ((flags) & CV_MAT_DEPTH_MASK)
 #define CV_MAKETYPE(depth, cn) (CV_MAT_DEPTH(depth) + (((cn) - 1) << CV_CN_SHIFT))
+#define CV_MAT_CN(flags) ((((flags) >> CV_CN_SHIFT) & 63) + 1)
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_32FC2 CV_MAKETYPE(CV_32F, 2)
+#define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
 
 /* OpenCV: SSE2 cvtsd2si / cvtss2si, i.e. round to nearest even in the default rounding mode == lrint / lrintf */
 static inline int cvRound(double value) { return (int)lrint(value); }
@@ -137,7 +146,14 @@ struct MatExpr {
   int rows, cols, type;
 };
 
-/* 8-bit single-channel matrices only (the path asserts CV_8UC1, src/ORBextractor.cc:626). */
+/* Dense 2-D matrices of 8U / 32F / 64F elements with 1..4 channels (the path itself asserts CV_8UC1, src/ORBextractor.cc:626;
+ * src/Frame.cc also keeps the distortion coefficients and the point list of cv::undistortPoints in CV_32F matrices). */
+static inline size_t sdorb_elem_size(int type) {
+  const int depth = CV_MAT_DEPTH(type);
+  SDORB_CV_ASSERT(depth == CV_8U || depth == CV_32F || depth == CV_64F);
+  return (size_t)(depth == CV_8U ? 1 : depth == CV_32F ? 4 : 8) * (size_t)CV_MAT_CN(type);
+}
+
 class Mat {
  public:
   Mat() : rows(0), cols(0), data(0), step(0), datastart(0), whole_rows(0), whole_cols(0), refcount(0), type_(CV_8UC1) {}
@@ -149,10 +165,8 @@ class Mat {
   }
   /* user-allocated data: no ownership (cv::Mat(rows, cols, type, void* data, size_t step)) */
   Mat(int r, int c, int type, void* d, size_t st = 0)
-      : rows(r), cols(c), data((uchar*)d), step(st ? st : (size_t)c), datastart((uchar*)d), whole_rows(r), whole_cols(c), refcount(0),
-        type_(type) {
-    SDORB_CV_ASSERT(type == CV_8UC1);
-  }
+      : rows(r), cols(c), data((uchar*)d), step(st ? st : (size_t)c * sdorb_elem_size(type)), datastart((uchar*)d), whole_rows(r),
+        whole_cols(c), refcount(0), type_(type) {}
   Mat(const Mat& m)
       : rows(m.rows), cols(m.cols), data(m.data), step(m.step), datastart(m.datastart), whole_rows(m.whole_rows),
         whole_cols(m.whole_cols), refcount(m.refcount), type_(m.type_) {
@@ -172,7 +186,7 @@ class Mat {
       if (!(cr == Range::all()) && !(cr == Range(0, cols))) {
         SDORB_CV_ASSERT(0 <= cr.start && cr.start <= cr.end && cr.end <= m.cols);
         cols = cr.end - cr.start;
-        data += (size_t)cr.start;
+        data += (size_t)cr.start * elemSize();
       }
     } catch (...) {
       release();
@@ -181,7 +195,7 @@ class Mat {
   }
   /* cv::Mat(const Mat&, const Rect&) */
   Mat(const Mat& m, const Rect& roi)
-      : rows(roi.height), cols(roi.width), data(m.data + (size_t)roi.y * m.step + (size_t)roi.x), step(m.step),
+      : rows(roi.height), cols(roi.width), data(m.data + (size_t)roi.y * m.step + (size_t)roi.x * m.elemSize()), step(m.step),
         datastart(m.datastart), whole_rows(m.whole_rows), whole_cols(m.whole_cols), refcount(m.refcount), type_(m.type_) {
     if (refcount) ++*refcount;
     try {
@@ -206,19 +220,20 @@ class Mat {
    * view into another matrix) followed by m = Scalar(0): the zeros are written THROUGH an existing header. */
   Mat& operator=(const MatExpr& e) {
     create(e.rows, e.cols, e.type);
-    for (int y = 0; y < rows; ++y) memset(data + (size_t)y * step, 0, (size_t)cols);
+    for (int y = 0; y < rows; ++y) memset(data + (size_t)y * step, 0, (size_t)cols * elemSize());
     return *this;
   }
   static MatExpr zeros(int rows, int cols, int type) { MatExpr e = {rows, cols, type}; return e; }
 
   void create(int r, int c, int type) {
-    SDORB_CV_ASSERT(type == CV_8UC1 && r >= 0 && c >= 0);
+    SDORB_CV_ASSERT(r >= 0 && c >= 0);
+    const size_t esz = sdorb_elem_size(type);
     if (data && rows == r && cols == c && type_ == type) return;
     if (!data && r == 0 && c == 0 && rows == 0 && cols == 0) { type_ = type; return; }
     release();
-    rows = r; cols = c; type_ = type; step = (size_t)c;
+    rows = r; cols = c; type_ = type; step = (size_t)c * esz;
     whole_rows = r; whole_cols = c;
-    const size_t bytes = (size_t)r * (size_t)c;
+    const size_t bytes = (size_t)r * (size_t)c * esz;
     uchar* block = (uchar*)malloc(sizeof(long) * 2 + (bytes ? bytes : 1));
     if (!block) throw Exception("out of memory");
     refcount = (long*)block;
@@ -238,18 +253,34 @@ class Mat {
     Mat m;
     if (rows > 0 && cols > 0) {
       m.create(rows, cols, type_);
-      for (int y = 0; y < rows; ++y) memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols);
+      for (int y = 0; y < rows; ++y) memcpy(m.data + (size_t)y * m.step, data + (size_t)y * step, (size_t)cols * elemSize());
+    } else {
+      m.type_ = type_;
     }
     return m;
   }
   void copyTo(Mat& dst) const {
     dst.create(rows, cols, type_);
-    for (int y = 0; y < rows; ++y) memmove(dst.data + (size_t)y * dst.step, data + (size_t)y * step, (size_t)cols);
+    for (int y = 0; y < rows; ++y) memmove(dst.data + (size_t)y * dst.step, data + (size_t)y * step, (size_t)cols * elemSize());
   }
+  Mat row(int y) const { return Mat(*this, Range(y, y + 1), Range::all()); }
+  Mat col(int x) const { return Mat(*this, Range::all(), Range(x, x + 1)); }
   Mat rowRange(int startrow, int endrow) const { return Mat(*this, Range(startrow, endrow), Range::all()); }
   Mat colRange(int startcol, int endcol) const { return Mat(*this, Range::all(), Range(startcol, endcol)); }
   Mat operator()(const Rect& roi) const { return Mat(*this, roi); }
   Mat operator()(Range rr, Range cr) const { return Mat(*this, rr, cr); }
+  /* cv::Mat::reshape(cn): same data, another channel count (continuous matrices only, rows kept) */
+  Mat reshape(int cn, int new_rows = 0) const {
+    SDORB_CV_ASSERT(new_rows == 0 && isContinuous() && cn >= 1 && cn <= 4);
+    const int total_scalars = cols * channels();
+    SDORB_CV_ASSERT(total_scalars % cn == 0);
+    Mat m(*this);
+    m.cols = total_scalars / cn;
+    m.type_ = CV_MAKETYPE(depth(), cn);
+    m.whole_rows = m.rows;
+    m.whole_cols = m.cols;
+    return m;
+  }
   /* size of the whole matrix this header views and the view's offset in it */
   void locateROI(Size& wholeSize, Point& ofs) const {
     const ptrdiff_t delta = data - datastart;
@@ -257,7 +288,7 @@ class Mat {
       ofs.x = ofs.y = 0;
     } else {
       ofs.y = (int)(delta / (ptrdiff_t)step);
-      ofs.x = (int)(delta - (ptrdiff_t)step * ofs.y);
+      ofs.x = (int)((delta - (ptrdiff_t)step * ofs.y) / (ptrdiff_t)elemSize());
     }
     wholeSize.height = whole_rows;
     wholeSize.width = whole_cols;
@@ -265,20 +296,23 @@ class Mat {
   bool isSubmatrix() const { return rows != whole_rows || cols != whole_cols; }
   int type() const { return type_; }
   int depth() const { return CV_MAT_DEPTH(type_); }
-  int channels() const { return 1; }
-  size_t elemSize() const { return 1; }
-  size_t elemSize1() const { return 1; }
-  size_t step1(int = 0) const { return step; }
+  int channels() const { return CV_MAT_CN(type_); }
+  size_t elemSize() const { return sdorb_elem_size(type_); }
+  size_t elemSize1() const { return elemSize() / (size_t)channels(); }
+  size_t step1(int = 0) const { return step / elemSize1(); }
   bool empty() const { return data == 0 || rows == 0 || cols == 0; }
   size_t total() const { return (size_t)rows * (size_t)cols; }
   Size size() const { return Size(cols, rows); }
-  bool isContinuous() const { return step == (size_t)cols || rows <= 1; }
+  bool isContinuous() const { return step == (size_t)cols * elemSize() || rows <= 1; }
   uchar* ptr(int y = 0) { return data + (size_t)y * step; }
   const uchar* ptr(int y = 0) const { return data + (size_t)y * step; }
   template <typename T> T* ptr(int y = 0) { return (T*)(data + (size_t)y * step); }
   template <typename T> const T* ptr(int y = 0) const { return (const T*)(data + (size_t)y * step); }
   template <typename T> T& at(int y, int x) { return ((T*)(data + (size_t)y * step))[x]; }
   template <typename T> const T& at(int y, int x) const { return ((const T*)(data + (size_t)y * step))[x]; }
+  /* single index: element i of a single-row or single-column matrix (Mat::at(int i0)) */
+  template <typename T> T& at(int i) { return rows == 1 ? ((T*)data)[i] : *(T*)(data + (size_t)i * step); }
+  template <typename T> const T& at(int i) const { return rows == 1 ? ((const T*)data)[i] : *(const T*)(data + (size_t)i * step); }
 
   int rows, cols;
   uchar* data;
@@ -332,7 +366,7 @@ static inline int sdorb_reflect101(int p, int len) {
 static inline void copyMakeBorder(InputArray _src, OutputArray _dst, int top, int bottom, int left, int right, int borderType) {
   SDORB_CV_ASSERT(top >= 0 && bottom >= 0 && left >= 0 && right >= 0);
   Mat src = _src.getMat();
-  SDORB_CV_ASSERT(src.type() == CV_8UC1);
+  SDORB_CV_ASSERT(src.type() == CV_8UC1);  /* one byte per pixel below */
   if (src.isSubmatrix() && (borderType & BORDER_ISOLATED) == 0) {
     Size wholeSize;
     Point ofs;

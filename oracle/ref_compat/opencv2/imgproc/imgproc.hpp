@@ -42,5 +42,38 @@ static inline void GaussianBlur(InputArray _src, OutputArray _dst, Size ksize, d
   orc_gaussian_blur_7x7_s2(in.data, in.cols, in.rows, in.step, dst.data, dst.step);
 }
 
+/* cv::undistortPoints(src, dst, K, dist, R = noArray(), P): src / dst are N x 1 CV_32FC2 point lists (src/Frame.cc:353-356, 384-387
+ * pass K as P and no R).  Forwards to the oracle's restatement of OpenCV 4.13's iteration, which tests/test_oracle_primitives.py
+ * pins against the real cv2.undistortPoints. */
+static inline void undistortPoints(InputArray _src, OutputArray _dst, InputArray _K, InputArray _dist, InputArray _R, InputArray _P) {
+  Mat src = _src.getMat(), K = _K.getMat(), dist = _dist.getMat(), P = _P.getMat();
+  SDORB_CV_ASSERT(_R.empty() && src.type() == CV_32FC2 && src.isContinuous() && (src.cols == 1 || src.rows == 1));
+  SDORB_CV_ASSERT(K.type() == CV_32F && K.rows == 3 && K.cols == 3 && P.type() == CV_32F && P.rows == 3 && P.cols == 3);
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) SDORB_CV_ASSERT(K.at<float>(i, j) == P.at<float>(i, j));
+  SDORB_CV_ASSERT(dist.type() == CV_32F && (dist.rows == 1 || dist.cols == 1));
+  const int n = (int)src.total(), nd = (int)dist.total();
+  const float k4[4] = {K.at<float>(0, 0), K.at<float>(1, 1), K.at<float>(0, 2), K.at<float>(1, 2)};
+  std::vector<float> d((size_t)nd);
+  for (int i = 0; i < nd; ++i) d[(size_t)i] = dist.at<float>(i);
+  std::vector<orc_keypoint> in((size_t)n), out((size_t)n);
+  const float* sp = src.ptr<float>();
+  for (int i = 0; i < n; ++i) {
+    in[(size_t)i].x = sp[2 * i];
+    in[(size_t)i].y = sp[2 * i + 1];
+  }
+  if (n > 0) orc_undistort_keypoints(&in[0], n, k4, nd ? &d[0] : 0, nd, &out[0]);
+  _dst.create(src.rows, src.cols, src.type());
+  Mat dst = _dst.getMat();
+  float* dp = dst.ptr<float>();
+  for (int i = 0; i < n; ++i) {
+    dp[2 * i] = out[(size_t)i].x;
+    dp[2 * i + 1] = out[(size_t)i].y;
+  }
+}
+
+/* cv::undistort: declared for src/Frame.cc:433-436 (Frame::Undistort, an image warp outside this path); never executed here. */
+static inline void undistort(InputArray, OutputArray, InputArray, InputArray) { throw Exception("cv::undistort is outside the parity library"); }
+
 }  // namespace cv
 #endif

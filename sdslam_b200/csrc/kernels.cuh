@@ -24,6 +24,12 @@ __device__ __forceinline__ void pdl_enter() {
   pdl_trigger();
 }
 
+// Set by the host runtime per pass (thread-local: one handle per thread).  Measured on B200 (profiles/r2_pdl_probe.log): with 512-
+// and 2048-frame passes the attribute COSTS 3-4 % -- the kernels run tens to hundreds of waves, nothing is gained at the
+// boundaries and every CTA pays for its griddepcontrol.wait -- and the single-frame call, whose kernels are replayed from CUDA
+// graphs, does not change.  So it is off unless SDORB_PDL_MAX_FRAMES asks for it; the evidence stays with the switch.
+extern thread_local bool g_pdl_enabled;
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg{};
@@ -35,7 +41,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = g_pdl_enabled ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 #endif

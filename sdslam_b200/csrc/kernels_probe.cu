@@ -3,9 +3,9 @@
 //   pipe 0  POPC (the pipe match_kernel saturates: DescriptorDistance, /root/reference/src/ORBmatcher.cc:1459-1473)
 //   pipe 1  the integer ALU pipe with VIMNMX3.U16x2 (the arc min / max network of fast_tiles_kernel)
 //   pipe 2  PRMT (the ring / tap windows of the FAST, pyramid and blur kernels; same ALU pipe)
-// Eight independent dependency chains per thread, 8 resident 256-thread CTAs per SM: enough ILP and warps to saturate a pipe.
-// The rate is reported per second (CUDA events) and per SM clock (clock64 inside the kernel, so it does not depend on what
-// nvidia-smi samples): warp-instructions / clk / SM.
+// Eight independent dependency chains per thread, 8 x 256 threads per SM: enough ILP and warps to saturate a pipe.  The rate is
+// reported per second (CUDA events around the launch) and per SM clock, with the SM clock itself measured inside the kernel
+// (clock64 ticks per %globaltimer nanosecond, median over the CTAs) instead of taken from nvidia-smi.
 #include "kernels.cuh"
 
 namespace sdorb {
@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(uint32_t* __restrict__ 
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = in[(threadIdx.x + 8 * i) & 1023];
   __syncthreads();
+  unsigned long long g0, g1;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
   const long long t0 = clock64();
   for (int it = 0; it < iters; ++it) {
 #pragma unroll
@@ -27,11 +29,15 @@ __global__ void __launch_bounds__(256) pipe_probe_kernel(uint32_t* __restrict__ 
     }
   }
   const long long t1 = clock64();
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
   uint32_t s = 0;
 #pragma unroll
   for (int i = 0; i < 8; ++i) s += v[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-  if (threadIdx.x == 0) cycles[blockIdx.x] = t1 - t0;
+  if (threadIdx.x == 0) {  // ticks and nanoseconds of this CTA's loop
+    cycles[2 * blockIdx.x] = t1 - t0;
+    cycles[2 * blockIdx.x + 1] = (long long)(g1 - g0);
+  }
 }
 
 // Runs the probe on stream s; returns 0 or a cudaError_t.  rate_per_s: warp-instructions per second over the whole GPU;
@@ -45,7 +51,7 @@ int run_pipe_probe(int pipe, cudaStream_t s, double* rate_per_s, double* per_clk
   long long* cyc = nullptr;
   cudaError_t e = cudaMalloc(&out, sizeof(uint32_t) * (size_t)ctas * 256);
   if (e == cudaSuccess) e = cudaMalloc(&in, sizeof(uint32_t) * 1024);
-  if (e == cudaSuccess) e = cudaMalloc(&cyc, sizeof(long long) * (size_t)ctas);
+  if (e == cudaSuccess) e = cudaMalloc(&cyc, sizeof(long long) * 2 * (size_t)ctas);
   if (e == cudaSuccess) e = cudaMemsetAsync(in, 0x35, sizeof(uint32_t) * 1024, s);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (e == cudaSuccess) e = cudaEventCreate(&e0);
@@ -66,13 +72,18 @@ int run_pipe_probe(int pipe, cudaStream_t s, double* rate_per_s, double* per_clk
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
   }
   if (e == cudaSuccess) {
-    std::vector<long long> h((size_t)ctas);
-    e = cudaMemcpy(h.data(), cyc, sizeof(long long) * (size_t)ctas, cudaMemcpyDeviceToHost);
+    std::vector<long long> h(2 * (size_t)ctas);
+    e = cudaMemcpy(h.data(), cyc, sizeof(long long) * 2 * (size_t)ctas, cudaMemcpyDeviceToHost);
     if (e == cudaSuccess) {
-      std::nth_element(h.begin(), h.begin() + ctas / 2, h.end());
-      const double warp_instr_per_sm = 8.0 /*CTAs*/ * 8 /*warps*/ * 8 /*chains*/ * (double)iters;
-      if (per_clk_sm) *per_clk_sm = warp_instr_per_sm / (double)h[(size_t)ctas / 2];
-      if (rate_per_s) *rate_per_s = warp_instr_per_sm * sms / ((double)ms * 1e-3);
+      std::vector<double> ghz;
+      for (int c = 0; c < ctas; ++c)
+        if (h[2 * (size_t)c + 1] > 0) ghz.push_back((double)h[2 * (size_t)c] / (double)h[2 * (size_t)c + 1]);
+      std::nth_element(ghz.begin(), ghz.begin() + ghz.size() / 2, ghz.end());
+      const double clk_hz = ghz.empty() ? 0.0 : ghz[ghz.size() / 2] * 1e9;
+      const double warp_instr = (double)ctas * 8 /*warps*/ * 8 /*chains*/ * (double)iters;
+      const double rate = warp_instr / ((double)ms * 1e-3);
+      if (rate_per_s) *rate_per_s = rate;
+      if (per_clk_sm) *per_clk_sm = clk_hz > 0 ? rate / sms / clk_hz : 0.0;
     }
   }
   if (e0) cudaEventDestroy(e0);

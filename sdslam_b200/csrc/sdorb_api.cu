@@ -22,6 +22,10 @@
 
 using namespace sdorb;
 
+namespace sdorb {
+thread_local bool g_pdl_enabled = false;
+}
+
 struct StageEvent {
   int stage;
   cudaEvent_t a, b;
@@ -85,7 +89,12 @@ struct sdorb_handle {
     int capacity = 0;
     int64_t launches = 0, stage_launches[SDORB_NUM_STAGES] = {0};
   } sg[2];
+  bool sg_tight = false;  // the captured kernels read level 0 with pitch == width (a contiguous caller image, uploaded linearly)
   bool use_graph = true;  // SDORB_GRAPH=0 replays the same enqueue sequence on the streams instead
+  // passes of at most this many frames use programmatic dependent launch (SDORB_PDL_MAX_FRAMES).  Default 0 = never: measured on
+  // B200 (tools/pdl_probe.sh, profiles/r2_pdl_probe.log) it costs 3-4 % on 512 / 2048-frame passes and changes the single-frame
+  // call by less than its run-to-run spread (inside the captured graphs the kernel boundaries are already short).
+  int pdl_max_frames = 0;
   // bookkeeping
   int64_t launches = 0;
   int64_t stage_launches[SDORB_NUM_STAGES] = {0};
@@ -275,6 +284,7 @@ struct PyrOut {           // where enqueue_pass leaves imagePyramid for the n fr
 int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_kps, uint8_t* d_desc, int32_t* d_counts,
                  int capacity, cudaStream_t s, int parts = PASS_ALL, const PyrOut* pyr = nullptr) {
   const FrameGeom& g = h->geom;
+  g_pdl_enabled = n <= h->pdl_max_frames;
   planes.pyr = h->d_pyr;
   planes.blur = h->d_blur;
   planes.nms = h->d_nms;
@@ -411,6 +421,7 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_pyr_host, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (const char* e = getenv("SDORB_GRAPH")) h->use_graph = e[0] != '0';
+  if (const char* e = getenv("SDORB_PDL_MAX_FRAMES")) h->pdl_max_frames = std::max(atoi(e), 0);
   if (const char* e = getenv("SDORB_OVERLAP")) h->overlap = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_TAPER")) h->pipe_taper = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_GROWTH")) h->pipe_growth_pct = std::min(std::max(atoi(e), 101), 1000);
@@ -685,8 +696,10 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
     sdorb_handle* hc = (dual && slot) ? h->twin : h;  // the lane: scratch arena + compute stream
     cudaStream_t cs = hc->s_compute;
     if (pass >= 2) CU(cudaStreamWaitEvent(h->s_in, h->ev_compute[slot], 0));
-    if (frame_stride == row_stride * (size_t)height && row_stride == (size_t)width && (size_t)L0.pitch == row_stride) {
-      // contiguous on both sides: one linear copy (a 2D copy of 640-byte rows is issued row by row)
+    const bool tight = frame_stride == row_stride * (size_t)height && row_stride == (size_t)width && width % 16 == 0;
+    if (tight) {
+      // contiguous host frames whose rows stay 16-byte aligned: one linear copy, and the kernels read level 0 with the image
+      // width as its pitch (a 2-D copy is issued row by row: measured 6.5 GB/s at 752x480 against 54 GB/s linear)
       CU(cudaMemcpyAsync(h->d_stage_in[slot], images + (size_t)f0 * frame_stride, frame_stride * (size_t)n, cudaMemcpyHostToDevice,
                          h->s_in));
     } else if (frame_stride == row_stride * (size_t)height) {
@@ -703,8 +716,8 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
     if (pass >= 2) CU(cudaStreamWaitEvent(cs, h->ev_out[slot], 0));
     BatchPlanes pl{};
     pl.img0 = h->d_stage_in[slot];
-    pl.img0_frame_stride = L0.plane_bytes;
-    pl.img0_pitch = L0.pitch;
+    pl.img0_frame_stride = tight ? (int64_t)frame_stride : L0.plane_bytes;
+    pl.img0_pitch = tight ? width : L0.pitch;
     PyrOut po;
     po.dst = pyramid ? h->d_pyr_out[slot] : nullptr;
     po.first_level = first_level;
@@ -851,7 +864,7 @@ int enqueue_single_part(sdorb_handle* h, int capacity, int part) {
   BatchPlanes pl{};
   pl.img0 = h->d_stage_in[0];
   pl.img0_frame_stride = L0.plane_bytes;
-  pl.img0_pitch = L0.pitch;
+  pl.img0_pitch = h->sg_tight ? L0.w : L0.pitch;
   int rc = enqueue_pass(h, pl, 1, h->d_kps[0], h->d_desc[0], h->d_counts[0], capacity, s, part == 0 ? PASS_PYRAMID : PASS_REST);
   if (rc || part == 0) return rc;
   uint8_t* r = h->h_res;
@@ -960,7 +973,12 @@ int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, 
     }
   }
   cudaStream_t s = h->s_compute;
-  if (stride == (size_t)width && (size_t)L0.pitch == stride) {
+  const bool tight = stride == (size_t)width && width % 16 == 0;
+  if (tight != h->sg_tight) {
+    free_single_graphs(h);
+    h->sg_tight = tight;
+  }
+  if (tight) {  // a contiguous image whose rows stay 16-byte aligned: one linear copy, the kernels read it with pitch == width
     CU(cudaMemcpyAsync(h->d_stage_in[0], image, (size_t)width * height, cudaMemcpyHostToDevice, s));
   } else {
     // a 2-D copy from pageable memory is issued row by row (measured: +70 us at 752x480): repack the rows into a pinned
@@ -995,7 +1013,7 @@ int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, 
       BatchPlanes pl{};
       pl.img0 = h->d_stage_in[0];
       pl.img0_frame_stride = L0.plane_bytes;
-      pl.img0_pitch = L0.pitch;
+      pl.img0_pitch = tight ? width : L0.pitch;
       pl.pyr = h->d_pyr;
       pl.batch_cap = h->prm.max_batch;
       launch_pack_padded(h->d_geom, g, pl, 1, h->d_pyr_pad, h->s_out);

@@ -24,7 +24,9 @@ def max_shard(world, nframes):
 def gather_slabs(slabs, nframes, group=None, dst=0):
     """slabs: list of tensors whose first dimension is this rank's frame count (keypoints [n,cap,7] f32,
     descriptors [n,cap,32] u8, counts [n] i32 ...).  Returns, on rank `dst`, the list of [nframes, ...] tensors in
-    global frame order; None elsewhere.  Shards are padded to the largest shard so one all_gather per slab suffices."""
+    global frame order; None elsewhere.  A gather TO ONE RANK: every other rank sends its slab, rank `dst` receives each one
+    straight into its place in the result (point-to-point, one batch of isend / irecv) -- no padding, no copy, and nobody but
+    `dst` receives anything."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     lo, hi = frame_range(rank, world, nframes)
@@ -33,17 +35,19 @@ def gather_slabs(slabs, nframes, group=None, dst=0):
             raise ValueError("slab has %d frames, shard [%d,%d) expects %d" % (t.shape[0], lo, hi, hi - lo))
     if world == 1:
         return list(slabs)
-    pad = max_shard(world, nframes)
-    out = []
-    for t in slabs:
-        buf = torch.zeros((pad,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        buf[:hi - lo] = t
-        allb = torch.empty((world * pad,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        dist.all_gather_into_tensor(allb, buf, group=group)
-        if rank == dst:
-            parts = []
+    ops, out = [], None
+    if rank == dst:
+        out = [torch.empty((nframes,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device) for t in slabs]
+        for o, t in zip(out, slabs):
+            o[lo:hi].copy_(t)
             for r in range(world):
                 a, b = frame_range(r, world, nframes)
-                parts.append(allb[r * pad:r * pad + (b - a)])
-            out.append(torch.cat(parts, 0))
-    return out if rank == dst else None
+                if r != dst and b > a:
+                    ops.append(dist.P2POp(dist.irecv, o[a:b], r, group))
+    elif hi > lo:
+        for t in slabs:
+            ops.append(dist.P2POp(dist.isend, t.contiguous(), dst, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    return out

@@ -43,14 +43,18 @@ for r in out:
     t["dram_bytes_per_launch"] += float(r[ix["dram__bytes_read.sum"]]) + float(r[ix["dram__bytes_write.sum"]])
     t["kernels_per_pass"] += 1
     t["us_per_pass_under_ncu"] += float(r[ix["gpu__time_duration.sum"]]) / 1e3
+    for key, col in (("alu_warp_inst_per_launch", "smsp__inst_executed_pipe_alu.sum"), ("xu_warp_inst_per_launch", "smsp__inst_executed_pipe_xu.sum"),
+                     ("warp_inst_per_launch", "smsp__inst_executed.sum")):
+        if col in ix and r[ix[col]] not in ("", "n/a"):
+            t[key] = t.get(key, 0.0) + float(r[ix[col]])
     # busiest launch of the stage: what actually bounds it (none of these kernels waits on HBM)
     for key, col in (("alu_pipe_pct", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                      ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
                      ("dram_throughput_pct", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")):
         t[key] = max(t.get(key, 0.0), float(r[ix[col]]))
 for k, v in traffic.items():
-    v["frames_per_pass"] = 256 if k.startswith("search") else 512
-    v["source"] = "profiles/%s_ncu_full_summary.csv (ncu --set full --clock-control none, one pass of 512 frames 640x480; tools/profile_r1d.sh)" % tag
+    v["frames_per_pass"] = 256 if k.startswith("search") or k.startswith("match") else 512
+    v["source"] = "profiles/%s_ncu_full_summary.csv (ncu --set full --clock-control none, one pass of 512 frames 640x480; tools/profile_%s.sh)" % (tag, tag[:2] if tag.startswith("r2") else tag)
     print("%-26s %d kernels %8.1f us %8.1f MB" % (k, v["kernels_per_pass"], v["us_per_pass_under_ncu"], v["dram_bytes_per_launch"] / 1e6))
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
 for r in out:
