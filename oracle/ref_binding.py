@@ -164,3 +164,134 @@ def hamming_matrix(A, B, native=False):
     out = np.zeros((len(A), len(B)), np.uint16)
     lib(native).ref_hamming_matrix(_p(A), len(A), _p(B), len(B), _p(out))
     return out
+
+
+# ---------------------------------------------------------------- matcher / Frame object graph (oracle/ref_build/ref_matcher_shim.cc)
+_MATCHER_SIGS_SET = set()
+
+
+def _mlib(native=False):
+    L = lib(native)
+    if id(L) not in _MATCHER_SIGS_SET:
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.ref_assign_grid.argtypes = [vp, i, f, f, f, f, vp, vp]
+        L.ref_features_in_area.restype = i
+        L.ref_features_in_area.argtypes = [vp, i, f, f, f, f, f, f, f, i, i, vp]
+        L.ref_undistort_keypoints.argtypes = [vp, i, vp, vp, i, vp]
+        L.ref_image_bounds.argtypes = [i, i, vp, vp, i, vp]
+        L.ref_stereo_from_rgbd.argtypes = [vp, vp, i, vp, i, i, f, vp, vp]
+        L.ref_three_maxima.argtypes = [vp, i, vp, vp, vp]
+        L.ref_search_for_initialization.restype = i
+        L.ref_search_for_initialization.argtypes = [vp, vp, i, vp, vp, i, f, f, f, f, vp, i, f, i, vp]
+        L.ref_search_by_points.restype = i
+        L.ref_search_by_points.argtypes = [vp, vp, vp, i, vp, vp, vp, i, f, i, vp]
+        L.ref_distinctive.restype = i
+        L.ref_distinctive.argtypes = [vp, i]
+        L.ref_search_by_projection.restype = i
+        L.ref_search_by_projection.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, i, vp, f, f, f, f, i, i, vp]
+        L.ref_search_map_points.restype = i
+        L.ref_search_map_points.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, i, vp, f, f, f, f, vp]
+        _MATCHER_SIGS_SET.add(id(L))
+    return L
+
+
+def _k(a):
+    return np.ascontiguousarray(a, KP_DTYPE)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, np.uint8)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def assign_grid(kps_un, min_x, min_y, inv_w, inv_h):
+    """Frame::AssignFeaturesToGrid of the reference: (cell_start[64*48+1], indices)."""
+    k = _k(kps_un)
+    cs = np.zeros(64 * 48 + 1, np.int32)
+    idx = np.zeros(max(len(k), 1), np.int32)
+    _mlib().ref_assign_grid(_p(k), len(k), min_x, min_y, inv_w, inv_h, _p(cs), _p(idx))
+    return cs, idx[:cs[-1]]
+
+
+def features_in_area(kps_un, gp, x, y, r, min_level, max_level=-1):
+    """Frame::GetFeaturesInArea of the reference; gp = (min_x, min_y, inv_w, inv_h)."""
+    k = _k(kps_un)
+    out = np.zeros(max(len(k), 1), np.int32)
+    n = _mlib().ref_features_in_area(_p(k), len(k), gp[0], gp[1], gp[2], gp[3], x, y, r, min_level, max_level, _p(out))
+    return out[:n]
+
+
+def undistort_keypoints(kps, K4, dist):
+    k, K4, dist = _k(kps), _f32(K4), _f32(dist)
+    out = np.zeros(len(k), KP_DTYPE)
+    _mlib().ref_undistort_keypoints(_p(k), len(k), _p(K4), _p(dist), len(dist), _p(out))
+    return out
+
+
+def image_bounds(cols, rows, K4, dist):
+    K4, dist = _f32(K4), _f32(dist)
+    b = np.zeros(4, np.float32)
+    _mlib().ref_image_bounds(cols, rows, _p(K4), _p(dist), len(dist), _p(b))
+    return b
+
+
+def stereo_from_rgbd(kps, kps_un, depth, mbf):
+    k, ku, depth = _k(kps), _k(kps_un), _f32(depth)
+    ur, z = np.zeros(len(k), np.float32), np.zeros(len(k), np.float32)
+    _mlib().ref_stereo_from_rgbd(_p(k), _p(ku), len(k), _p(depth), depth.shape[1], depth.shape[0], mbf, _p(ur), _p(z))
+    return ur, z
+
+
+def three_maxima(sizes):
+    s = np.ascontiguousarray(sizes, np.int32)
+    a, b, c = C.c_int(-1), C.c_int(-1), C.c_int(-1)
+    _mlib().ref_three_maxima(_p(s), len(s), C.addressof(a), C.addressof(b), C.addressof(c))
+    return a.value, b.value, c.value
+
+
+def search_for_initialization(kps1_un, desc1, kps2_un, desc2, gp, prev_matched, window_size=100, nnratio=0.9, check_orientation=True):
+    k1, k2, d1, d2 = _k(kps1_un), _k(kps2_un), _u8(desc1), _u8(desc2)
+    prev = np.array(prev_matched, np.float32).reshape(-1, 2).copy()
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = _mlib().ref_search_for_initialization(_p(k1), _p(d1), len(k1), _p(k2), _p(d2), len(k2), gp[0], gp[1], gp[2], gp[3], _p(prev),
+                                              window_size, nnratio, int(check_orientation), _p(m12))
+    return n, m12[:len(k1)], prev
+
+
+def search_by_points(kps1_un, desc1, valid1, kps2_un, desc2, valid2, nnratio=0.75, check_orientation=True):
+    k1, k2, d1, d2, v1, v2 = _k(kps1_un), _k(kps2_un), _u8(desc1), _u8(desc2), _u8(valid1), _u8(valid2)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = _mlib().ref_search_by_points(_p(k1), _p(d1), _p(v1), len(k1), _p(k2), _p(d2), _p(v2), len(k2), nnratio, int(check_orientation), _p(m12))
+    return n, m12[:len(k1)]
+
+
+def distinctive(desc):
+    d = _u8(desc).reshape(-1, 32)
+    return _mlib().ref_distinctive(_p(d), len(d))
+
+
+def search_by_projection(kps_last, kps_last_un, proj, flags_last, desc_mp, kps_cur_un, desc_cur, u_right_cur, occupied_cur, gp,
+                         scale_factors, bounds, th, mbf, mode, check_orientation=True):
+    """SearchByProjection(CurrentFrame, LastFrame, th, bMono = false); proj[:, 2] (invzc) must be 1 (see the shim)."""
+    kl, klu, kc = _k(kps_last), _k(kps_last_un), _k(kps_cur_un)
+    pr = _f32(proj).reshape(-1, 3)
+    assert (pr[:, 2] == 1).all()
+    fl, oc, dm, dc, ur = _u8(flags_last), _u8(occupied_cur), _u8(desc_mp), _u8(desc_cur), _f32(u_right_cur)
+    sf, bd = _f32(scale_factors), _f32(bounds)
+    asg = np.full(max(len(kc), 1), -1, np.int32)
+    n = _mlib().ref_search_by_projection(_p(kl), _p(klu), _p(pr), _p(fl), _p(dm), len(kl), _p(kc), _p(dc), _p(ur), _p(oc), len(kc), _p(sf), len(sf),
+                                         _p(bd), gp[2], gp[3], th, mbf, mode, int(check_orientation), _p(asg))
+    return n, asg[:len(kc)]
+
+
+def search_map_points(proj, view_cos, level, flags, desc_mp, kps_un, desc, u_right, occupied, gp, scale_factors, bounds, th, nnratio=0.8):
+    pr = _f32(proj).reshape(-1, 3)
+    vc, lv, fl, dm = _f32(view_cos), np.ascontiguousarray(level, np.int32), _u8(flags), _u8(desc_mp)
+    k, d, ur, oc, sf, bd = _k(kps_un), _u8(desc), _f32(u_right), _u8(occupied), _f32(scale_factors), _f32(bounds)
+    asg = np.full(max(len(k), 1), -1, np.int32)
+    n = _mlib().ref_search_map_points(_p(pr), _p(vc), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(ur), _p(oc), len(k), _p(sf), len(sf),
+                                      _p(bd), gp[2], gp[3], th, nnratio, _p(asg))
+    return n, asg[:len(k)]

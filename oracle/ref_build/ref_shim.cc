@@ -2,7 +2,8 @@
 //
 // TEST INFRASTRUCTURE ONLY.  This file is ours; the code it drives is the reference's own text:
 //   /root/reference/src/ORBextractor.{h,cc}   (compiled where it lies, never copied into this repository)
-//   /root/reference/src/ORBmatcher.cc:1459-1473 DescriptorDistance (extracted into oracle/_ref/gen/ at build time, see Makefile)
+//   /root/reference/src/ORBmatcher.cc (the whole translation unit; DescriptorDistance :1459-1473 is called from here, the
+//   search routines from ref_matcher_shim.cc)
 // against the cv:: surface of oracle/ref_compat.  Built into oracle/_ref/libsdorb_ref.so by oracle/ref_build/Makefile.
 #include <stdint.h>
 
@@ -11,12 +12,8 @@
 #include <thread>
 #include <vector>
 
-#include "ORBextractor.h"  // the reference's header (-I/root/reference/src)
-
-namespace SD_SLAM {
-// declared in the generated translation unit oracle/_ref/gen/descriptor_distance.cc (class stub + the reference's function body)
-int sdorb_ref_descriptor_distance(const cv::Mat& a, const cv::Mat& b);
-}  // namespace SD_SLAM
+#include "ORBextractor.h"  // the reference's headers (links in oracle/_ref/gen/src, see the Makefile)
+#include "ORBmatcher.h"
 
 namespace {
 // reaches the protected tables of the reference class (src/ORBextractor.h:72-89) without touching its text
@@ -134,7 +131,7 @@ long ref_extract_many(void* ev, const uint8_t* imgs, int nframes, int w, int h, 
 // ORBmatcher::DescriptorDistance (src/ORBmatcher.cc:1459-1473) on two 32-byte rows
 int ref_descriptor_distance(const uint8_t* a, const uint8_t* b) {
   cv::Mat ma(1, 32, CV_8UC1, const_cast<uint8_t*>(a)), mb(1, 32, CV_8UC1, const_cast<uint8_t*>(b));
-  return SD_SLAM::sdorb_ref_descriptor_distance(ma, mb);
+  return SD_SLAM::ORBmatcher::DescriptorDistance(ma, mb);
 }
 void ref_hamming_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB, uint16_t* out) {
   for (int i = 0; i < nA; ++i)

@@ -43,10 +43,16 @@ for r in out:
     t["dram_bytes_per_launch"] += float(r[ix["dram__bytes_read.sum"]]) + float(r[ix["dram__bytes_write.sum"]])
     t["kernels_per_pass"] += 1
     t["us_per_pass_under_ncu"] += float(r[ix["gpu__time_duration.sum"]]) / 1e3
-    for key, col in (("alu_warp_inst_per_launch", "smsp__inst_executed_pipe_alu.sum"), ("xu_warp_inst_per_launch", "smsp__inst_executed_pipe_xu.sum"),
-                     ("warp_inst_per_launch", "smsp__inst_executed.sum")):
-        if col in ix and r[ix[col]] not in ("", "n/a"):
-            t[key] = t.get(key, 0.0) + float(r[ix[col]])
+    if "smsp__inst_executed.sum" in ix:
+        t["warp_inst_per_launch"] = t.get("warp_inst_per_launch", 0.0) + float(r[ix["smsp__inst_executed.sum"]])
+    # ncu --set full has no per-pipe instruction COUNT, only the pipe's utilisation: ALU-pipe warp-instructions of the launch =
+    # utilisation x the pipe's issue rate (one warp-instruction per 2 clk per SM sub-partition = 2 / clk / SM: what the percentage
+    # is of, and what tools/probe/pipe_probe2.cu and kernels_probe.cu measure) x the active SM cycles x 148 SMs.  Same for XU
+    # (POPC: 16 lanes / clk / SM = 0.5 warp-instructions / clk / SM).
+    if "sm__cycles_active.avg" in ix:
+        cyc = float(r[ix["sm__cycles_active.avg"]])
+        t["alu_warp_inst_per_launch"] = t.get("alu_warp_inst_per_launch", 0.0) + float(r[ix["sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"]]) / 100 * 2.0 * cyc * 148
+        t["xu_warp_inst_per_launch"] = t.get("xu_warp_inst_per_launch", 0.0) + float(r[ix["sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"]]) / 100 * 0.5 * cyc * 148
     # busiest launch of the stage: what actually bounds it (none of these kernels waits on HBM)
     for key, col in (("alu_pipe_pct", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                      ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
