@@ -295,3 +295,59 @@ def search_map_points(proj, view_cos, level, flags, desc_mp, kps_un, desc, u_rig
     n = _mlib().ref_search_map_points(_p(pr), _p(vc), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(ur), _p(oc), len(k), _p(sf), len(sf),
                                       _p(bd), gp[2], gp[3], th, nnratio, _p(asg))
     return n, asg[:len(k)]
+
+
+def _msigs2():
+    L = _mlib()
+    if not getattr(L, "_sdorb_sigs2", False):
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.ref_search_for_triangulation.restype = i
+        L.ref_search_for_triangulation.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, f, f, vp, i, i, vp]
+        L.ref_fuse_search.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, i, f, f, f, f, vp, i, f, f, vp]
+        L.ref_search_by_sim3.restype = i
+        L.ref_search_by_sim3.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, vp, vp, vp, f, f, f, f, vp, i, f, vp]
+        L._sdorb_sigs2 = True
+    return L
+
+
+def search_for_triangulation(kps1_un, desc1, has_mp1, u_right1, kps2_un, desc2, has_mp2, u_right2, F12, ex, ey, scale_factors,
+                             level_sigma2=None, check_orientation=True):
+    """ORBmatcher::SearchForTriangulation of the reference: (nmatches, vMatches12).  level_sigma2 must be scale_factors ** 2 (the
+    KeyFrame derives it)."""
+    k1, k2, d1, d2 = _k(kps1_un), _k(kps2_un), _u8(desc1), _u8(desc2)
+    m1, m2, r1, r2 = _u8(has_mp1), _u8(has_mp2), _f32(u_right1), _f32(u_right2)
+    F = np.ascontiguousarray(F12, np.float64).reshape(9)
+    sf = _f32(scale_factors)
+    if level_sigma2 is not None:
+        assert np.array_equal(_f32(level_sigma2), sf * sf)
+    m12 = np.full(max(len(k1), 1), -1, np.int32)
+    n = _msigs2().ref_search_for_triangulation(_p(k1), _p(d1), _p(m1), _p(r1), len(k1), _p(k2), _p(d2), _p(m2), _p(r2), len(k2), _p(F),
+                                               float(ex), float(ey), _p(sf), len(sf), int(check_orientation), _p(m12))
+    return n, m12[:len(k1)]
+
+
+def fuse_search(proj, invz, level, flags, desc_mp, kps_un, desc, u_right, gp, scale_factors, th, bf):
+    """The keypoint search of ORBmatcher::Fuse(pKF, vpMapPoints, th): best_idx per map point (-1: nothing fused).  proj[:, :2] =
+    (u, v); the right coordinate the reference derives is u - bf * invz (invz: powers of two)."""
+    pr, iz = _f32(proj).reshape(-1, 3), _f32(invz)
+    lv, fl, dm = np.ascontiguousarray(level, np.int32), _u8(flags), _u8(desc_mp)
+    k, d, ur, sf = _k(kps_un), _u8(desc), _f32(u_right), _f32(scale_factors)
+    out = np.full(max(len(pr), 1), -1, np.int32)
+    _msigs2().ref_fuse_search(_p(pr), _p(iz), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(ur), len(k), gp[0], gp[1], gp[2], gp[3], _p(sf),
+                              len(sf), th, bf, _p(out))
+    return out[:len(pr)]
+
+
+def search_by_sim3(side1, side2, gp, scale_factors, th):
+    """ORBmatcher::SearchBySim3 of the reference at the identity transform; side = (proj, level, flags, desc_mp, kps_un, desc):
+    (nFound, matches12)."""
+    p1, l1, f1, m1, k1, d1 = side1[:6]
+    p2, l2, f2, m2, k2, d2 = side2[:6]
+    p1, p2 = _f32(p1).reshape(-1, 3), _f32(p2).reshape(-1, 3)
+    l1, l2 = np.ascontiguousarray(l1, np.int32), np.ascontiguousarray(l2, np.int32)
+    f1, f2, m1, m2 = _u8(f1), _u8(f2), _u8(m1), _u8(m2)
+    k1, k2, d1, d2, sf = _k(k1), _k(k2), _u8(d1), _u8(d2), _f32(scale_factors)
+    out = np.full(max(len(k1), 1), -1, np.int32)
+    n = _msigs2().ref_search_by_sim3(_p(p1), _p(l1), _p(f1), _p(m1), len(k1), _p(p2), _p(l2), _p(f2), _p(m2), len(k2), _p(k1), _p(d1), _p(k2), _p(d2),
+                                     gp[0], gp[1], gp[2], gp[3], _p(sf), len(sf), th, _p(out))
+    return n, out[:len(k1)]

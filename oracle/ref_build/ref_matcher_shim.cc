@@ -67,7 +67,7 @@ void set_frame_statics(const GridParams& g, float fx, float fy, float cx, float 
 std::vector<cv::KeyPoint> to_kps(const orc_keypoint* k, int n) {
   std::vector<cv::KeyPoint> v((size_t)n);
   static_assert(sizeof(cv::KeyPoint) == sizeof(orc_keypoint), "cv::KeyPoint layout");
-  if (n > 0) memcpy(&v[0], k, sizeof(orc_keypoint) * (size_t)n);
+  if (n > 0) memcpy(static_cast<void*>(&v[0]), k, sizeof(orc_keypoint) * (size_t)n);
   return v;
 }
 
@@ -437,6 +437,127 @@ int ref_search_map_points(const float* proj, const float* view_cos, const int32_
     assigned[k] = (p && p != pre[(size_t)k] && index.count(p)) ? index[p] : -1;
   }
   return nm;
+}
+
+// ---- ORBmatcher::SearchForTriangulation (src/ORBmatcher.cc:359-462) with CheckDistEpipolarLine (:128-144).  KF2 sits at the
+// identity pose, KF1's camera centre at (ex, ey, 1): the epipole of :366-368 is exactly (ex, ey).  F12 row-major.
+// has_mp: the keypoint already has a map point.  matches12[i] = index in KF2 or -1 (vMatchedPairs flattened); returns nmatches.
+int ref_search_for_triangulation(const orc_keypoint* kps1_un, const uint8_t* desc1, const uint8_t* has_mp1, const float* u_right1, int n1,
+                                 const orc_keypoint* kps2_un, const uint8_t* desc2, const uint8_t* has_mp2, const float* u_right2, int n2,
+                                 const double* F12, float ex, float ey, const float* scale_factors, int nlevels, int check_orientation,
+                                 int32_t* matches12) {
+  std::lock_guard<std::mutex> lk(g_lock);
+  GridParams g = {0, 640, 0, 480, 64.f / 640.f, 48.f / 480.f};
+  set_frame_statics(g, 1, 1, 0, 0);
+  Arena A;
+  Frame F1, F2;
+  fill_frame(F1, NULL, kps1_un, desc1, n1, scale_factors, nlevels, u_right1, 40.f);
+  fill_frame(F2, NULL, kps2_un, desc2, n2, scale_factors, nlevels, u_right2, 40.f);
+  Eigen::Matrix4d T1 = Eigen::Matrix4d::Identity();
+  T1(0, 3) = -(double)ex;
+  T1(1, 3) = -(double)ey;
+  T1(2, 3) = -1.0;
+  F1.SetPose(T1);
+  KeyFrame* k1 = A.keyframe(F1);
+  KeyFrame* k2 = A.keyframe(F2);
+  for (int i = 0; i < n1; ++i)
+    if (has_mp1[i]) k1->AddMapPoint(A.point(Eigen::Vector3d(0, 0, 1), k1), (size_t)i);
+  for (int i = 0; i < n2; ++i)
+    if (has_mp2[i]) k2->AddMapPoint(A.point(Eigen::Vector3d(0, 0, 1), k2), (size_t)i);
+  Eigen::Matrix3d F;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) F(r, c) = F12[3 * r + c];
+  std::vector<std::pair<size_t, size_t> > pairs;
+  ORBmatcher matcher(0.6f, check_orientation != 0);
+  const int nm = matcher.SearchForTriangulation(k1, k2, F, pairs);
+  for (int i = 0; i < n1; ++i) matches12[i] = -1;
+  for (size_t k = 0; k < pairs.size(); ++k) matches12[pairs[k].first] = (int32_t)pairs[k].second;
+  return nm;
+}
+
+namespace {
+// A map point that ORBmatcher::Fuse / SearchBySim3 project to exactly (u, v) in a keyframe at the identity pose with fx = fy = 1,
+// cx = cy = 0, at depth z (a power of two: u * z, 1 / z and (u * z) * (1 / z) are all exact), whose PredictScale() is `level`,
+// which passes the distance-invariance and viewing-angle checks, and which carries the given descriptor.
+MapPoint* posed_point(Arena& A, KeyFrame* ref, float u, float v, double z, int level, const uint8_t* desc, float log_scale_factor) {
+  const Eigen::Vector3d pos((double)u * z, (double)v * z, z);
+  MapPoint* p = A.point(pos, ref);
+  p->mDescriptor = to_desc(desc, 1);
+  const float dist = (float)pos.norm();
+  // ratio = mfMaxDistance / dist = scaleFactor^(level - 0.5): ceil(log(ratio) / log(scaleFactor)) = level (0 for level 0)
+  p->mfMaxDistance = dist * std::exp(((float)level - 0.5f) * log_scale_factor);
+  p->mfMinDistance = 0.f;
+  if (p->mfMaxDistance * 1.2f < dist) p->mfMaxDistance = dist;  // level 0: keep dist3D <= 1.2 * mfMaxDistance
+  p->mNormalVector = pos / pos.norm();
+  return p;
+}
+}  // namespace
+
+// ---- the keypoint search of ORBmatcher::Fuse(KeyFrame*, vpMapPoints, th) (src/ORBmatcher.cc:477-615).  Map point i projects to
+// (proj[3i], proj[3i+1]) at depth 1 / invz[i] (powers of two), so ur = u - bf * invz of :520; flags bit 0 clear: the point is
+// bad (skipped).  The keyframe has no map points of its own, so every accepted match goes through AddObservation / AddMapPoint,
+// or -- when an earlier point took the keypoint -- through Replace(): best_idx[i] is read back from either.  min_x / min_y are
+// the grid origin (KeyFrame keeps them as int), the image is unbounded to the right / below.
+void ref_fuse_search(const float* proj, const float* invz, const int32_t* level, const uint8_t* flags, const uint8_t* desc_mp, int n_mp,
+                     const orc_keypoint* kps_un, const uint8_t* desc, const float* u_right, int n_kf, float min_x, float min_y, float inv_w,
+                     float inv_h, const float* scale_factors, int nlevels, float th, float bf, int32_t* best_idx) {
+  std::lock_guard<std::mutex> lk(g_lock);
+  GridParams g = {min_x, 1e6f, min_y, 1e6f, inv_w, inv_h};
+  set_frame_statics(g, 1, 1, 0, 0);
+  Arena A;
+  Frame F;
+  fill_frame(F, NULL, kps_un, desc, n_kf, scale_factors, nlevels, u_right, bf);
+  KeyFrame* kf = A.keyframe(F);
+  KeyFrame* obs = A.observer(scale_factors, nlevels);
+  std::vector<MapPoint*> pts((size_t)n_mp);
+  for (int i = 0; i < n_mp; ++i) {
+    MapPoint* p = posed_point(A, obs, proj[3 * i], proj[3 * i + 1], 1.0 / (double)invz[i], level[i], desc_mp + (size_t)i * 32, kf->mfLogScaleFactor);
+    if (!(flags[i] & 1)) p->mbBad = true;
+    pts[(size_t)i] = p;
+  }
+  ORBmatcher matcher(0.6f, true);
+  matcher.Fuse(kf, pts, th);
+  for (int i = 0; i < n_mp; ++i) {
+    MapPoint* p = pts[(size_t)i];
+    int idx = p->GetIndexInKeyFrame(kf);
+    if (idx < 0 && p->GetReplaced()) idx = p->GetReplaced()->GetIndexInKeyFrame(kf);  // the keypoint was taken: this point was replaced by its owner
+    best_idx[i] = idx;
+  }
+}
+
+// ---- ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:734-944) with s12 = 1, R12 = I, t12 = 0 and both keyframes at the identity pose:
+// the map point of keypoint i1 of KF1 (flags1 bit 0) lies at (proj1[3 i1], proj1[3 i1 + 1], 1) and so projects there in KF2, and
+// vice versa.  matches12[i1] = index in KF2 of the map point the call stores in vpMatches12[i1], else -1; returns nFound.
+int ref_search_by_sim3(const float* proj1, const int32_t* level1, const uint8_t* flags1, const uint8_t* desc_mp1, int n1, const float* proj2,
+                       const int32_t* level2, const uint8_t* flags2, const uint8_t* desc_mp2, int n2, const orc_keypoint* kps1_un,
+                       const uint8_t* desc1, const orc_keypoint* kps2_un, const uint8_t* desc2, float min_x, float min_y, float inv_w,
+                       float inv_h, const float* scale_factors, int nlevels, float th, int32_t* matches12) {
+  std::lock_guard<std::mutex> lk(g_lock);
+  GridParams g = {min_x, 1e6f, min_y, 1e6f, inv_w, inv_h};
+  set_frame_statics(g, 1, 1, 0, 0);
+  Arena A;
+  Frame F1, F2;
+  fill_frame(F1, NULL, kps1_un, desc1, n1, scale_factors, nlevels, NULL, 40.f);
+  fill_frame(F2, NULL, kps2_un, desc2, n2, scale_factors, nlevels, NULL, 40.f);
+  KeyFrame* k1 = A.keyframe(F1);
+  KeyFrame* k2 = A.keyframe(F2);
+  KeyFrame* obs = A.observer(scale_factors, nlevels);
+  std::map<MapPoint*, int> index2;
+  for (int i = 0; i < n1; ++i)
+    if (flags1[i] & 1)
+      k1->AddMapPoint(posed_point(A, obs, proj1[3 * i], proj1[3 * i + 1], 1.0, level1[i], desc_mp1 + (size_t)i * 32, k2->mfLogScaleFactor), (size_t)i);
+  for (int i = 0; i < n2; ++i)
+    if (flags2[i] & 1) {
+      MapPoint* p = posed_point(A, obs, proj2[3 * i], proj2[3 * i + 1], 1.0, level2[i], desc_mp2 + (size_t)i * 32, k1->mfLogScaleFactor);
+      k2->AddMapPoint(p, (size_t)i);
+      index2[p] = i;
+    }
+  std::vector<MapPoint*> m12((size_t)n1, static_cast<MapPoint*>(NULL));
+  ORBmatcher matcher(0.75f, true);
+  const float s12 = 1.0f;
+  const int nf = matcher.SearchBySim3(k1, k2, m12, s12, Eigen::Matrix3d::Identity(), Eigen::Vector3d::Zero(), th);
+  for (int i = 0; i < n1; ++i) matches12[i] = m12[(size_t)i] ? index2[m12[(size_t)i]] : -1;
+  return nf;
 }
 
 }  // extern "C"

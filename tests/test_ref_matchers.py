@@ -195,3 +195,74 @@ def test_distinctive_descriptors_equal_reference():
         medians = np.sort(D, axis=1)[:, int(0.5 * (n - 1))]
         assert medians[r] == medians.min() == med[0], "n = %d: the reference's pick does not have the least median" % n
         assert medians[best[0]] == medians.min()
+
+
+# ------------------------------------------------------------------ the keyframe-side searches (rows f2 / f4)
+@pytest.mark.parametrize("seed,n1,n2,orient", [(0, 140, 150, True), (1, 120, 90, False), (2, 60, 200, True), (3, 0, 40, True), (4, 40, 0, True),
+                                               (5, 150, 150, True), (6, 300, 320, True)])
+def test_search_for_triangulation_equals_reference(seed, n1, n2, orient):
+    """ORBmatcher::SearchForTriangulation + CheckDistEpipolarLine (src/ORBmatcher.cc:128-144, 359-462): the epipolar gate in the
+    float / double mix and with the FMA contraction g++ applies to the reference's own expression under its own flags."""
+    case = sc.triangulation_case(seed, n1, n2, dup=0.3 if seed == 5 else 0.1)
+    n, m12 = orc.search_for_triangulation(*case, orient)
+    rn, rm12 = ref.search_for_triangulation(*case, orient)
+    assert n == rn and np.array_equal(m12, rm12)
+    if seed in (0, 6):
+        assert n > 10
+
+
+def _fuse_case(seed, nf, nmp, stereo, dup, gp, bf=40.0):
+    """fuse_inputs of tests/search_cases.py, with the right coordinate in the form the reference can produce: ur = u - bf * invz
+    for a depth that is a power of two, the stereo keypoints' own right coordinates placed around it."""
+    _, _, kf, df = sc.frame_pair(seed + 140, 10, nf, dup=dup, level0=0.3)
+    proj, lvl, fl, ur_kf = sc.fuse_inputs(seed, kf, nmp, stereo=stereo)
+    dmp = sc.fuse_descriptors(seed, df, nf, nmp)
+    rng = np.random.default_rng(seed + 77)
+    invz = rng.choice(np.array([0.25, 0.5, 1.0, 2.0], np.float32), nmp)
+    proj[:, 0] = np.maximum(proj[:, 0], np.float32(gp[0] + 1))  # KeyFrame::IsInImage: inside the (integer) lower bounds
+    proj[:, 1] = np.maximum(proj[:, 1], np.float32(gp[1] + 1))
+    proj[:, 2] = proj[:, 0] - np.float32(bf) * invz                # one rounding, like the reference's (contracted) u - bf * invz
+    if nf and stereo:  # every stereo keypoint's right coordinate near the ur of some point projected next to it
+        r0 = np.random.default_rng(seed + 1300)
+        r0.integers(0, 8, nmp)
+        r0.random(nf), r0.uniform(0, 30, nf)
+        src = r0.integers(0, nf, nmp)
+        ur_kf = np.where(ur_kf >= 0, ur_kf, -1).astype(np.float32)
+        for i in range(nmp):
+            if ur_kf[src[i]] >= 0:
+                ur_kf[src[i]] = max(np.float32(proj[i, 2] + rng.uniform(-1.5, 1.5)), np.float32(0))
+    return kf, df, proj, invz, lvl, fl, dmp, ur_kf.astype(np.float32)
+
+
+@pytest.mark.parametrize("seed,nf,nmp,th,stereo,dup,origin", [(0, 600, 500, 3.0, True, 0.0, (0.0, 0.0)), (1, 500, 700, 2.5, False, 0.0, (0.0, 0.0)),
+                                                              (2, 0, 50, 3.0, True, 0.0, (0.0, 0.0)), (3, 200, 0, 3.0, True, 0.0, (0.0, 0.0)),
+                                                              (4, 700, 900, 4.0, True, 0.3, (0.0, 0.0)), (6, 600, 600, 4.0, True, 0.0, (-12.0, -7.0))])
+def test_fuse_search_equals_reference(seed, nf, nmp, th, stereo, dup, origin):
+    """The keypoint search of ORBmatcher::Fuse (src/ORBmatcher.cc:477-615) on real KeyFrame / MapPoint objects: projection,
+    PredictScale, KeyFrame::GetFeaturesInArea, the level window, the chi-square gate as the reference build contracts it, the
+    first-minimum rule; read back through the map surgery Fuse performs (AddMapPoint / Replace)."""
+    gp = sc.grid_params(640, 480, *origin)
+    kf, df, proj, invz, lvl, fl, dmp, ur = _fuse_case(seed, nf, nmp, stereo, dup, gp)
+    inv = (np.float32(1) / (SF * SF)).astype(np.float32)
+    bi, bd = orc.fuse_search(proj, lvl, fl, dmp, kf, df, ur, _orc_grid(kf, gp), SF, inv, th)
+    rbi = ref.fuse_search(proj, invz, lvl, fl, dmp, kf, df, ur, gp, SF, th, 40.0)
+    assert np.array_equal(bi, rbi)
+    if seed == 0:
+        assert (bi >= 0).sum() > 100
+
+
+@pytest.mark.parametrize("seed,n1,n2,th,dup", [(0, 500, 520, 7.5, 0.0), (1, 300, 400, 7.5, 0.3), (2, 0, 100, 7.5, 0.0), (3, 100, 0, 7.5, 0.0),
+                                               (4, 640, 600, 3.0, 0.1)])
+def test_search_by_sim3_equals_reference(seed, n1, n2, th, dup):
+    """ORBmatcher::SearchBySim3 (src/ORBmatcher.cc:734-944) at the identity transform: both directed searches and the agreement check."""
+    s1, s2 = sc.sim3_case(seed, n1, n2, dup=dup)
+    gp = sc.grid_params()
+    for s in (s1, s2):  # inside the lower image bounds (KeyFrame::IsInImage)
+        s[0][:, 0] = np.maximum(s[0][:, 0], np.float32(1))
+        s[0][:, 1] = np.maximum(s[0][:, 1], np.float32(1))
+        s[0][:, 2] = 1.0
+    n, m12, m1, m2 = orc.search_by_sim3(s1 + (_orc_grid(s1[4], gp),), s2 + (_orc_grid(s2[4], gp),), SF, th)
+    rn, rm12 = ref.search_by_sim3(s1, s2, gp, SF, th)
+    assert n == rn and np.array_equal(m12, rm12)
+    if seed == 0:
+        assert n > 100
