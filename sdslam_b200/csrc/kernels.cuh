@@ -71,6 +71,10 @@ struct SelectBuffers {
 // ComputePyramid: level l from level l-1 for every frame (cv::resize INTER_LINEAR fixed point).
 void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level, const BatchPlanes& p,
                          const ResizeTap* d_taps, const ResizeGroup* d_groups, int nframes, cudaStream_t s);
+// The small upper levels (first_level .. nlevels - 1, resize_tail_first_level) of every frame in one launch.
+int resize_tail_first_level(const FrameGeom& g);
+void launch_resize_tail(const FrameGeom* d_geom, const FrameGeom& g, int first_level, const BatchPlanes& p, const ResizeTap* d_taps,
+                        const ResizeGroup* d_groups, int nframes, cudaStream_t s);
 // imagePyramid of a batch into the caller's frame-major slab (levels first_level .. nlevels-1); layout: pyramid_layout().
 void pyramid_layout(const FrameGeom& g, int64_t* offset, int64_t* frame_bytes);
 void launch_pack_pyramid(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int first_level, uint8_t* dst, int nframes,

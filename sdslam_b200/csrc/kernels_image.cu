@@ -35,15 +35,28 @@ __device__ __forceinline__ uint32_t ldg_word_if(const uint8_t* ptr, int on) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(v) : "l"(ptr), "r"(on));
   return v;
 }
+// the same through the coherent path: for a kernel that reads what its own CTA wrote earlier (resize_tail_kernel)
+__device__ __forceinline__ uint32_t ld_word_if(const uint8_t* ptr, int on) {
+  uint32_t v;
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.global.b32 %0, [%1];\n\t}" : "=r"(v) : "l"(ptr), "r"(on) : "memory");
+  return v;
+}
 
 // The three source words that hold every tap of four destination pixels in one source row.
 struct ResizeRaw {
   uint32_t w0, w1, w2;
 };
+template <bool NC = true>
 __device__ __forceinline__ void resize_fetch(const uint8_t* __restrict__ row, int on, int ld1, int ld2, ResizeRaw& r) {
-  r.w0 = ldg_word_if(row, on);
-  r.w1 = ldg_word_if(row + 4, on & ld1);
-  r.w2 = ldg_word_if(row + 8, on & ld2);
+  if (NC) {
+    r.w0 = ldg_word_if(row, on);
+    r.w1 = ldg_word_if(row + 4, on & ld1);
+    r.w2 = ldg_word_if(row + 8, on & ld2);
+  } else {
+    r.w0 = ld_word_if(row, on);
+    r.w1 = ld_word_if(row + 4, on & ld1);
+    r.w2 = ld_word_if(row + 8, on & ld2);
+  }
 }
 // horizontal pass of one source row for four destination pixels, already shifted: a[i] = (c0*s0 + c1*s1) >> 4
 __device__ __forceinline__ void resize_hrow(const ResizeRaw& r, int shift, const ResizeGroup& G, uint32_t (&a)[4]) {
@@ -141,26 +154,23 @@ __global__ void __launch_bounds__(128) resize_level_kernel(const FrameGeom* __re
 // k is computed once, and the destination row that ends on row k -- looked up in a per-warp table in shared memory, filled
 // from the vertical taps by the lanes that hold them -- is emitted from H(k-1) / H(k).
 constexpr int RZP_ROWS = 8;
-template <int KMAX>
-__global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
-                                                               const ResizeTap* __restrict__ taps,
-                                                               const ResizeGroup* __restrict__ groups) {
-  __shared__ int4 s_emit[4][KMAX];  // per warp and source row k: {destination row or -1, c0, c1, -}
-  pdl_enter();
+// One warp: 128 destination pixels (word column block bx) x RZP_ROWS rows starting at y0 of `level` of `frame`.  emit = KMAX
+// int4 of this warp's shared memory.  NC: the source level was written by an earlier kernel (non-coherent loads are fine).
+template <int KMAX, bool NC>
+__device__ __forceinline__ void resize_pre_tile(const FrameGeom* __restrict__ geom, const int level, const BatchPlanes& p,
+                                                const ResizeTap* __restrict__ taps, const ResizeGroup* __restrict__ groups, const int bx,
+                                                const int y0, const int frame, int4* emit, const int lane) {
   const LevelGeom& D = geom->lv[level];
   const LevelGeom& S = geom->lv[level - 1];
-  const int lane = threadIdx.x;
   // lanes beyond the row redo the row's last group: same loads, same bytes stored to the same place
-  const int gi = min(blockIdx.x * 32 + lane, ((D.w + 3) >> 2) - 1);
-  const int y0 = (blockIdx.y * 4 + threadIdx.y) * RZP_ROWS;  // warp-uniform
-  const int frame = blockIdx.z;
+  const int gi = min(bx * 32 + lane, ((D.w + 3) >> 2) - 1);
   const int dh = D.h;
   if (y0 >= dh) return;
   const int jn = min(RZP_ROWS, dh - y0);
   // vertical taps {s0 | s1 << 16, c0 | c1 << 16} of row y0 + lane, for the lanes < jn
   const uint2 tl = reinterpret_cast<const uint2*>(taps + D.coef_y_base + y0)[min(lane, jn - 1)];
   const uint32_t row0 = __shfl_sync(0xffffffffu, tl.x, 0) & 0xFFFFu, rowl = __shfl_sync(0xffffffffu, tl.x, jn - 1) >> 16;
-  int4* emit = s_emit[threadIdx.y];
+  __syncwarp();  // the previous tile of this warp is done with the table
   if (lane < KMAX) emit[lane] = make_int4(-1, 0, 0, 0);
   __syncwarp();
   // a row with both taps on one source row (s0 == s1, the clamped first row of a level) is always the first of its group of
@@ -179,7 +189,7 @@ __global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* 
   {
     const uint8_t* rp = src;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k, rp += spitch) resize_fetch(rp, row0 + k <= rowl, ld1, ld2, raw[k]);
+    for (int k = 0; k < KMAX; ++k, rp += spitch) resize_fetch<NC>(rp, row0 + k <= rowl, ld1, ld2, raw[k]);
   }
   uint32_t ap[4] = {0, 0, 0, 0}, ac[4] = {0, 0, 0, 0};
 #pragma unroll
@@ -198,6 +208,40 @@ __global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* 
       const uint32_t v01 = (u01 + l01 + 0x00020002u) >> 2, v23 = (u23 + l23 + 0x00020002u) >> 2;  // lanes <= 1022: no carry
       *reinterpret_cast<uint32_t*>(dst + (uint32_t)e.x * (uint32_t)dpitch) = __byte_perm(v01, v23, 0x6420);  // the pitch absorbs the tail
     }
+  }
+}
+
+template <int KMAX>
+__global__ void __launch_bounds__(128) resize_level_pre_kernel(const FrameGeom* __restrict__ geom, int level, BatchPlanes p,
+                                                               const ResizeTap* __restrict__ taps,
+                                                               const ResizeGroup* __restrict__ groups) {
+  __shared__ int4 s_emit[4][KMAX];  // per warp and source row k: {destination row or -1, c0, c1, -}
+  pdl_enter();
+  resize_pre_tile<KMAX, true>(geom, level, p, taps, groups, blockIdx.x, (blockIdx.y * 4 + threadIdx.y) * RZP_ROWS, blockIdx.z,
+                              s_emit[threadIdx.y], threadIdx.x);
+}
+
+// The small upper levels of the chained pyramid in ONE launch: level l needs all of level l - 1, so a CTA owns a frame and
+// walks the levels first_level .. nlevels - 1 with a block barrier between them (its own global writes are visible to its own
+// threads after the barrier; the loads of these levels take the coherent path).  At 640x480 levels 4-7 together are 11 % of the
+// level-0 pixels: four launches of 18-38 us per 512 frames at 14-22 % of the DRAM throughput become one, and the single-frame
+// call loses three kernel boundaries.
+constexpr int RZT_WARPS = 16;
+template <int KMAX>
+__global__ void __launch_bounds__(RZT_WARPS * 32, 2) resize_tail_kernel(const FrameGeom* __restrict__ geom, int first_level, BatchPlanes p,
+                                                                     const ResizeTap* __restrict__ taps,
+                                                                     const ResizeGroup* __restrict__ groups) {
+  __shared__ int4 s_emit[RZT_WARPS][KMAX];
+  pdl_enter();
+  const int frame = blockIdx.x, lane = threadIdx.x, warp = threadIdx.y;
+  for (int level = first_level; level < geom->nlevels; ++level) {
+    const LevelGeom& D = geom->lv[level];
+    const int tiles_x = (D.w + 127) >> 7, tiles_y = (D.h + RZP_ROWS - 1) / RZP_ROWS;
+    for (int t = warp; t < tiles_x * tiles_y; t += RZT_WARPS) {
+      const int ty = t / tiles_x, bx = t - ty * tiles_x;
+      resize_pre_tile<KMAX, false>(geom, level, p, taps, groups, bx, ty * RZP_ROWS, frame, s_emit[warp], lane);
+    }
+    __syncthreads();
   }
 }
 
@@ -229,6 +273,23 @@ __global__ void __launch_bounds__(256) resize_level_generic_kernel(const FrameGe
     out |= (uint32_t)v << (8 * i);
   }
   *reinterpret_cast<uint32_t*>(dst + (int64_t)y * D.pitch + x4) = out;
+}
+
+// First level of the fused tail launch: the smallest l >= 2 from which every level is small (at most 96 K pixels) and runs on
+// the pre-loading path; nlevels when there is no such tail of at least two levels.
+int resize_tail_first_level(const FrameGeom& g) {
+  int first = g.nlevels;
+  for (int l = g.nlevels - 1; l >= 2; --l) {
+    const LevelGeom& D = g.lv[l];
+    if (!(D.group_base >= 0 && D.rz_span > 0 && D.rz_span <= 11 && D.w * D.h <= 96 * 1024)) break;
+    first = l;
+  }
+  return g.nlevels - first >= 2 ? first : g.nlevels;
+}
+
+void launch_resize_tail(const FrameGeom* d_geom, const FrameGeom& g, int first_level, const BatchPlanes& p, const ResizeTap* d_taps,
+                        const ResizeGroup* d_groups, int nframes, cudaStream_t s) {
+  launch_pdl(resize_tail_kernel<11>, dim3(nframes), dim3(32, RZT_WARPS), 0, s, d_geom, first_level, p, d_taps, d_groups);
 }
 
 void launch_resize_level(const FrameGeom* d_geom, const FrameGeom& g, int level, const BatchPlanes& p,

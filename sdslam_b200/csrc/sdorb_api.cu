@@ -91,6 +91,11 @@ struct sdorb_handle {
   } sg[2];
   bool sg_tight = false;  // the captured kernels read level 0 with pitch == width (a contiguous caller image, uploaded linearly)
   bool use_graph = true;  // SDORB_GRAPH=0 replays the same enqueue sequence on the streams instead
+  // SDORB_PYRAMID_TAIL=1: the small upper pyramid levels in one launch (resize_tail_kernel).  Off by default: measured on B200
+  // (profiles/r2_pyramid_tail_probe.log) the pyramid stage gets SLOWER, 2.47 -> 2.59 ms per 4096 frames in 512-frame passes and
+  // 0.169 -> 0.185 ms for the single-frame call -- one CTA per frame walking four levels behind block barriers loses more than
+  // the three saved kernel boundaries give.
+  bool fuse_pyramid_tail = false;
   // passes of at most this many frames use programmatic dependent launch (SDORB_PDL_MAX_FRAMES).  Default 0 = never: measured on
   // B200 (tools/pdl_probe.sh, profiles/r2_pdl_probe.log) it costs 3-4 % on 512 / 2048-frame passes and changes the single-frame
   // call by less than its run-to-run spread (inside the captured graphs the kernel boundaries are already short).
@@ -292,8 +297,13 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
   SelectBuffers sb{h->d_cell_seen, h->d_cell_list, h->d_sel, h->d_sel_count, h->d_error, h->d_okeys, h->d_onode};
   if (parts & PASS_PYRAMID) {
     StageScope st(h, s, SDORB_STAGE_PYRAMID);
-    for (int l = 1; l < g.nlevels; ++l) {
+    const int tail = h->fuse_pyramid_tail ? resize_tail_first_level(g) : g.nlevels;
+    for (int l = 1; l < tail; ++l) {
       launch_resize_level(h->d_geom, g, l, planes, h->d_taps, h->d_groups, n, s);
+      st.launched();
+    }
+    if (tail < g.nlevels) {  // the small upper levels in one launch
+      launch_resize_tail(h->d_geom, g, tail, planes, h->d_taps, h->d_groups, n, s);
       st.launched();
     }
   }
@@ -421,6 +431,7 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaEventCreateWithFlags(&h->ev_pyr_host, cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (const char* e = getenv("SDORB_GRAPH")) h->use_graph = e[0] != '0';
+  if (const char* e = getenv("SDORB_PYRAMID_TAIL")) h->fuse_pyramid_tail = e[0] != '0';
   if (const char* e = getenv("SDORB_PDL_MAX_FRAMES")) h->pdl_max_frames = std::max(atoi(e), 0);
   if (const char* e = getenv("SDORB_OVERLAP")) h->overlap = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_TAPER")) h->pipe_taper = e[0] != '0';

@@ -480,6 +480,29 @@ def test_pyramid_views_of_any_border_and_stride(border, extra_stride):
     ex.close()
 
 
+def test_fused_pyramid_tail_is_bit_identical(monkeypatch):
+    """SDORB_PYRAMID_TAIL=1 (the upper pyramid levels in one launch; measured slower, so opt-in): same pyramid, same keypoints."""
+    monkeypatch.setenv("SDORB_PYRAMID_TAIL", "1")
+    for (w, h, params) in ((640, 480, C1), (333, 257, (700, 1.2, 6, 12)), (960, 540, (4000, 1.2, 12, 20))):
+        imgs = synth.frames(3, w, h, start=650)
+        ex = api.ORBextractor(*params, max_width=w, max_height=h, max_batch=3)
+        before = ex.kernel_launches()
+        k, d, c = ex.extract_batch_host(imgs)
+        assert ex.kernel_launches() - before < 5 + params[2]  # fewer launches than one per level + the five other kernels
+        o = orc.Extractor(*params)
+        for f in range(3):
+            ok, od = o.extract(imgs[f])
+            assert_same(ok, od, k[f, :c[f]], d[f, :c[f]], "%dx%d frame %d" % (w, h, f))
+        k1, d1, pyr = ex(imgs[0])
+        ok, od, st = o.extract(imgs[0], dump=True)
+        po = 0
+        for l, g in enumerate(st["geometry"]):
+            lw, lh = int(g["width"]), int(g["height"])
+            assert np.array_equal(pyr[l], st["pyramid"][po:po + lw * lh].reshape(lh, lw)), "level %d" % l
+            po += lw * lh
+        ex.close()
+
+
 def test_single_frame_call_with_and_without_graph(monkeypatch):
     """sdorb_extract replays two captured CUDA graphs per call (pyramid | FAST .. describe + result copies); SDORB_GRAPH=0
     enqueues the same sequence on the streams.  Same bytes either way, over changing images, sizes and pyramid on / off."""

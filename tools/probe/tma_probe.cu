@@ -6,11 +6,14 @@
 // 640 x 480 (157 MB, larger than the 126 MB L2) in both forms, consumes the tile from shared memory with one XOR per staged word
 // (so the loads cannot be elided), and reports the time and the staged GB/s of each:
 //   manual : 128 threads, every lane loads aligned words of its rows, __syncthreads, consume
-//   tma    : thread 0 arms an mbarrier and issues one cp.async.bulk.tensor.2d for the 128 x 68 box, everybody waits on the
-//            barrier, consume
+//   tma    : thread 0 arms an mbarrier and issues one cp.async.bulk.tensor.2d, everybody waits on the barrier, consume.
+//            A TMA box must START ON A 16-BYTE BOUNDARY in global memory (an unaligned x coordinate raises "illegal
+//            instruction": first version of this probe).  FAST tiles start at column 12 + 120 * tx -- 4-byte aligned only --
+//            so the box is 144 bytes wide from (x0 & ~15) and the tile is read at a word offset: 12.5 % more bytes staged.
 // What to compare the result with: fast_tiles_kernel needs ~1.7 ms for the same 512 frames (ncu, profiles/r2_ncu_full_summary.csv)
 // with the integer ALU pipe 89 % busy.  Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o bin/tma_probe tma_probe.cu
 #include <cuda.h>
+#include <cuda/barrier>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -18,6 +21,7 @@
 #include <cstdlib>
 
 constexpr int W = 640, H = 480, TW = 128, TH = 68, OW = 120, OH = 60;
+constexpr int TWB = 144;  // TMA box width: TW plus the up to 12 bytes in front of an unaligned tile start, rounded to 16
 constexpr int TILES_X = (W - 38 + OW - 1) / OW, TILES_Y = (H - 38 + OH - 1) / OH;
 
 __global__ void __launch_bounds__(128, 8) stage_manual(const uint8_t* __restrict__ img, uint32_t* __restrict__ out) {
@@ -41,30 +45,35 @@ __global__ void __launch_bounds__(128, 8) stage_manual(const uint8_t* __restrict
   out[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 + threadIdx.x] = acc;
 }
 
+// The TMA form, written with libcu++'s wrappers (cuda::barrier + cuda::device::experimental::cp_async_bulk_tensor_2d_global_to_shared,
+// the form of the CUDA programming guide): SASS shows UTMALDG.2D + SYNCS (mbarrier).
+namespace cde = cuda::device::experimental;
+using block_barrier = cuda::barrier<cuda::thread_scope_block>;
+
 __global__ void __launch_bounds__(128, 8) stage_tma(const __grid_constant__ CUtensorMap tmap, uint32_t* __restrict__ out) {
-  __shared__ __align__(128) uint32_t tile[TH][TW / 4];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ alignas(128) uint32_t tile[TH][TWB / 4];
+#pragma nv_diag_suppress static_var_with_dynamic_init
+  __shared__ block_barrier bar;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int tx = blockIdx.x % TILES_X, ty = blockIdx.x / TILES_X, frame = blockIdx.y;
   const int x0 = 12 + tx * OW, y0 = 15 + ty * OH + frame * H;  // frames are stacked rows of one 640 x (480 * N) tensor
-  const uint32_t bar_a = (uint32_t)__cvta_generic_to_shared(&bar), tile_a = (uint32_t)__cvta_generic_to_shared(&tile[0][0]);
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    init(&bar, blockDim.x);
+    cde::fence_proxy_async_shared_cta();  // the barrier's initialisation becomes visible to the async (TMA) proxy
   }
   __syncthreads();
+  block_barrier::arrival_token token;
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(TW * TH) : "memory");
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(tile_a),
-                 "l"(&tmap), "r"(x0), "r"(y0), "r"(bar_a)
-                 : "memory");
+    cde::cp_async_bulk_tensor_2d_global_to_shared(&tile[0][0], &tmap, x0 & ~15, y0, bar);
+    token = cuda::device::barrier_arrive_tx(bar, 1, sizeof(tile));
+  } else {
+    token = bar.arrive();
   }
-  asm volatile(
-      "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n@!p bra WAIT_%=;\n}" ::"r"(bar_a)
-      : "memory");
+  bar.wait(std::move(token));
+  const int wo = (x0 & 15) >> 2;  // the tile's first word inside the box
   uint32_t acc = 0;
 #pragma unroll 4
-  for (int r = warp; r < TH; r += 4) acc ^= tile[r][(lane + r) & 31];
+  for (int r = warp; r < TH; r += 4) acc ^= tile[r][wo + ((lane + r) & 31)];
   out[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 128 + threadIdx.x] = acc;
 }
 
@@ -101,7 +110,7 @@ int main(int argc, char** argv) {
   }
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)W, (cuuint64_t)H * N}, strides[1] = {(cuuint64_t)W};
-  const cuuint32_t box[2] = {TW, TH}, estr[2] = {1, 1};
+  const cuuint32_t box[2] = {TWB, TH}, estr[2] = {1, 1};
   const CUresult r = ((EncodeFn)fn)(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, img, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -112,6 +121,12 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
+  stage_manual<<<grid, 128>>>(img, out_a);
+  CK(cudaDeviceSynchronize());
+  printf("manual staging kernel ran\n");
+  stage_tma<<<grid, 128>>>(tmap, out_b);
+  CK(cudaDeviceSynchronize());
+  printf("TMA staging kernel ran\n");
   float ms_a = 1e9f, ms_b = 1e9f;
   for (int rep = 0; rep < 6; ++rep) {
     float ms;
