@@ -681,6 +681,10 @@ def run_ours(args):
             e2e["platform_ceiling"] = ceil
             e2e["h2d_gbs"] = e2e_fps * w * h / 1e9
             e2e["frac_of_h2d_ceiling"] = e2e_fps * w * h / 1e9 / ceil["h2d_gbs"]
+            # both directions together against the same figure of the bare copies (the leg moves frames up and results down at once)
+            e2e["both_directions_gbs"] = (m["h2d_bytes"] + m["d2h_bytes"]) * m["e2e_steps"] / m["e2e_s"] / 1e9
+            e2e["frac_of_both_directions_ceiling"] = e2e["both_directions_gbs"] / ceil["both_directions_wall_gbs"]
+            e2e["frac_of_resident"] = e2e_fps / fps  # at N = 1 the kernels, not the copies, bound the leg
         line = {
             "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3),
             "ms_per_step": m["ms_total"] / steps, "higher_is_better": True, "scaling": "strong" if world > 1 else "weak",
