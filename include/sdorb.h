@@ -433,6 +433,10 @@ SDORB_API int64_t sdorb_debug_read(sdorb_handle* h, int what, int frame, int lev
  * KeyPointsFilter::retainBest (src/ORBextractor.cc:586, 602) -- on n packed entries (low 8 bits = response) in host
  * memory, in place (parity tests against the real libstdc++ algorithm). */
 SDORB_API int sdorb_debug_nth_element(sdorb_handle* h, uint32_t* entries, int n, int nth);
+/* Guarded run (SDORB_GUARD=1 in the environment when the library makes its first allocation): every device buffer has a 256 KB
+ * guard band on either side and a poisoned payload.  Returns the number of guard bytes any kernel has overwritten so far (0 = all
+ * bands intact; the first damaged buffer is named by sdorb_last_cuda_error), -1000 when the run is not guarded. */
+SDORB_API int64_t sdorb_debug_guard_check(sdorb_handle* h);
 /* Measured peak of an execution pipe on the handle's GPU (a saturating micro-benchmark, kernels_probe.cu), for the roofline
  * figures of bench.py: pipe 0 = POPC (bounds the Hamming matcher), 1 = the integer ALU pipe on VIMNMX3.U16x2 (bounds FAST),
  * 2 = PRMT.  Rates in warp-instructions per second (whole GPU) and per SM clock per SM. */

@@ -131,6 +131,8 @@ def lib():
     L.sdorb_debug_read.restype = i64
     L.sdorb_debug_nth_element.argtypes = [vp, vp, i, i]
     L.sdorb_debug_pipe_probe.argtypes = [vp, i, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.sdorb_debug_guard_check.argtypes = [vp]
+    L.sdorb_debug_guard_check.restype = i64
     _lib = L
     return L
 
@@ -643,6 +645,17 @@ class ORBextractor:
         launches = np.zeros(len(STAGES), np.int64)
         self._check(lib().sdorb_get_stage_times(self._h, _ptr(ms), _ptr(launches), int(reset)))
         return dict(zip(STAGES, ms.tolist())), dict(zip(STAGES, launches.tolist()))
+
+    def guard_check(self):
+        """Guarded run (SDORB_GUARD=1): overwritten guard bytes over all live device buffers (0 = intact); None when not guarded."""
+        n = int(lib().sdorb_debug_guard_check(self._h))
+        if n == -1000:
+            return None
+        if n < 0:
+            self._check(n)
+        if n:
+            raise SdorbError(-6, lib().sdorb_last_cuda_error(self._h).decode())
+        return n
 
     def pipe_probe(self, pipe):
         """Measured peak of an execution pipe (0 POPC, 1 VIMNMX3.U16x2 on the ALU pipe, 2 PRMT): (warp-instructions / s,

@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -25,6 +27,96 @@ using namespace sdorb;
 namespace sdorb {
 thread_local bool g_pdl_enabled = false;
 }
+
+
+// ---- guarded device allocations: the debug build that stands in for compute-sanitizer (closed on this pool).  With SDORB_GUARD=1
+// in the environment every device buffer of the library is allocated with a 256 KB guard band on each side filled with 0xA5 and its
+// payload poisoned with 0xCD (nothing may rely on cudaMalloc handing out zeros); sdorb_debug_guard_check() verifies every band of
+// every live buffer.  An out-of-bounds WRITE of any kernel lands in a band and is reported with the buffer's name; an
+// out-of-bounds or uninitialised READ brings 0xA5 / 0xCD bytes into the results, where the bit-exact parity tests see it.
+// tests/test_gpu_parity.py::test_guarded_allocations_stay_intact runs the parity suite that way.
+namespace {
+struct GuardRec {
+  void* base;
+  size_t bytes;
+  const char* what;
+};
+constexpr size_t kGuard = 256 * 1024;
+std::mutex g_guard_mu;
+std::map<void*, GuardRec> g_guard_live;  // user pointer -> record
+int g_guard_on = -1;
+
+bool guard_on() {
+  if (g_guard_on < 0) {
+    const char* e = getenv("SDORB_GUARD");
+    g_guard_on = (e && e[0] != '0') ? 1 : 0;
+  }
+  return g_guard_on == 1;
+}
+
+template <class T>
+cudaError_t sd_malloc_named(T** p, size_t bytes, const char* what) {
+  if (!guard_on()) return cudaMalloc(p, bytes);
+  uint8_t* base = nullptr;
+  cudaError_t e = cudaMalloc(&base, bytes + 2 * kGuard);
+  if (e != cudaSuccess) return e;
+  cudaMemset(base, 0xA5, kGuard);
+  cudaMemset(base + kGuard, 0xCD, bytes);
+  cudaMemset(base + kGuard + bytes, 0xA5, kGuard);
+  cudaDeviceSynchronize();  // the fills run on the legacy stream, the library's streams do not wait for it
+  *p = reinterpret_cast<T*>(base + kGuard);
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  g_guard_live[base + kGuard] = GuardRec{base, bytes, what};
+  return cudaSuccess;
+}
+#define sd_malloc(p, bytes) sd_malloc_named(p, bytes, #p)
+
+int64_t g_guard_bad_freed = 0;   // damage found in buffers that have been freed since the last check
+std::string g_guard_freed_msg;
+
+// bytes of the two bands of one buffer that no longer hold 0xA5; describes the first damage in *msg when it is empty
+int64_t guard_scan(const GuardRec& r, std::string* msg) {
+  std::vector<uint8_t> band(kGuard);
+  int64_t bad = 0;
+  for (int side = 0; side < 2; ++side) {
+    const uint8_t* src = side == 0 ? (const uint8_t*)r.base : (const uint8_t*)r.base + kGuard + r.bytes;
+    if (cudaMemcpy(band.data(), src, kGuard, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    int64_t n = 0, first = -1;
+    for (size_t i = 0; i < kGuard; ++i)
+      if (band[i] != 0xA5) {
+        if (first < 0) first = (int64_t)i;
+        ++n;
+      }
+    if (n) {
+      bad += n;
+      if (msg && msg->empty()) {
+        char text[256];
+        snprintf(text, sizeof text, "guard band %s %s (%zu bytes): %lld bytes overwritten, first at offset %lld", side ? "after" : "before",
+                 r.what, r.bytes, (long long)n, (long long)(side ? first : first - (int64_t)kGuard));
+        *msg = text;
+      }
+    }
+  }
+  return bad;
+}
+
+cudaError_t sd_free(void* p) {
+  if (!p || !guard_on()) return cudaFree(p);
+  void* base = p;
+  {
+    std::lock_guard<std::mutex> lk(g_guard_mu);
+    auto it = g_guard_live.find(p);
+    if (it != g_guard_live.end()) {
+      cudaDeviceSynchronize();
+      const int64_t bad = guard_scan(it->second, &g_guard_freed_msg);  // a buffer is checked once more before it goes away
+      if (bad > 0) g_guard_bad_freed += bad;
+      base = it->second.base;
+      g_guard_live.erase(it);
+    }
+  }
+  return cudaFree(base);
+}
+}  // namespace
 
 struct StageEvent {
   int stage;
@@ -137,7 +229,7 @@ struct DeviceGuard {
 
 template <class T>
 void dfree(T*& p) {
-  if (p) cudaFree(p);
+  if (p) sd_free(p);
   p = nullptr;
 }
 
@@ -198,26 +290,28 @@ int ensure_geometry(sdorb_handle* h, int width, int height) {
   CU(cudaStreamSynchronize(h->s_compute));
   free_geometry_scratch(h);
   const size_t B = (size_t)h->prm.max_batch;
-  CU(cudaMalloc(&h->d_geom, sizeof(FrameGeom)));
+  CU(sd_malloc(&h->d_geom, sizeof(FrameGeom)));
   CU(cudaMemcpy(h->d_geom, &g, sizeof(FrameGeom), cudaMemcpyHostToDevice));
-  CU(cudaMalloc(&h->d_taps, sizeof(ResizeTap) * std::max<size_t>(taps.size(), 1)));
+  CU(sd_malloc(&h->d_taps, sizeof(ResizeTap) * std::max<size_t>(taps.size(), 1)));
   if (!taps.empty()) CU(cudaMemcpy(h->d_taps, taps.data(), sizeof(ResizeTap) * taps.size(), cudaMemcpyHostToDevice));
-  CU(cudaMalloc(&h->d_groups, sizeof(ResizeGroup) * std::max<size_t>(groups.size(), 1)));
+  CU(sd_malloc(&h->d_groups, sizeof(ResizeGroup) * std::max<size_t>(groups.size(), 1)));
   if (!groups.empty())
     CU(cudaMemcpy(h->d_groups, groups.data(), sizeof(ResizeGroup) * groups.size(), cudaMemcpyHostToDevice));
-  CU(cudaMalloc(&h->d_pyr, (size_t)g.plane_total * B + 256));
-  CU(cudaMalloc(&h->d_blur, (size_t)g.plane_total * B + 256));
-  CU(cudaMalloc(&h->d_nms, (size_t)g.plane_total * B + 256));
+  CU(sd_malloc(&h->d_pyr, (size_t)g.plane_total * B + 256));
+  CU(sd_malloc(&h->d_blur, (size_t)g.plane_total * B + 256));
+  CU(sd_malloc(&h->d_nms, (size_t)g.plane_total * B + 256));
   const size_t cells_bytes = sizeof(int32_t) * std::max<size_t>((size_t)g.cells_total * B, 1);
-  CU(cudaMalloc(&h->d_cell_seen, cells_bytes));
+  CU(sd_malloc(&h->d_cell_seen, cells_bytes));
   CU(cudaMemset(h->d_cell_seen, 0, cells_bytes));
-  CU(cudaMalloc(&h->d_cell_list, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
+  CU(sd_malloc(&h->d_cell_list, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
   if (g.octree) {
-    CU(cudaMalloc(&h->d_okeys, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
-    CU(cudaMalloc(&h->d_onode, sizeof(uint16_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
+    CU(sd_malloc(&h->d_okeys, sizeof(uint32_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
+    CU(sd_malloc(&h->d_onode, sizeof(uint16_t) * std::max<size_t>((size_t)g.list_total * B, 1)));
   }
-  CU(cudaMalloc(&h->d_sel, sizeof(uint32_t) * std::max<size_t>((size_t)g.sel_total * B, 1)));
-  CU(cudaMalloc(&h->d_sel_count, sizeof(int32_t) * (size_t)g.nlevels * B));
+  CU(sd_malloc(&h->d_sel, sizeof(uint32_t) * std::max<size_t>((size_t)g.sel_total * B, 1)));
+  CU(sd_malloc(&h->d_sel_count, sizeof(int32_t) * (size_t)g.nlevels * B));
+  // the uploads and fills above ran on the legacy stream; the handle's streams are non-blocking and would not wait for them
+  CU(cudaStreamSynchronize(cudaStreamLegacy));
   h->geom = g;
   h->gw = width;
   h->gh = height;
@@ -227,7 +321,7 @@ int ensure_geometry(sdorb_handle* h, int width, int height) {
 int ensure_host_staging(sdorb_handle* h, int capacity) {
   const size_t B = (size_t)h->prm.max_batch;
   if (!h->d_stage_in[0]) {
-    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_stage_in[i], (size_t)h->geom.lv[0].plane_bytes * B + 256));
+    for (int i = 0; i < 2; ++i) CU(sd_malloc(&h->d_stage_in[i], (size_t)h->geom.lv[0].plane_bytes * B + 256));
   }
   if (h->out_cap != capacity) {
     free_single_graphs(h);
@@ -235,9 +329,9 @@ int ensure_host_staging(sdorb_handle* h, int capacity) {
       dfree(h->d_kps[i]);
       dfree(h->d_desc[i]);
       dfree(h->d_counts[i]);
-      CU(cudaMalloc(&h->d_kps[i], sizeof(sdorb_keypoint) * (size_t)capacity * B));
-      CU(cudaMalloc(&h->d_desc[i], (size_t)32 * capacity * B));
-      CU(cudaMalloc(&h->d_counts[i], sizeof(int32_t) * B));
+      CU(sd_malloc(&h->d_kps[i], sizeof(sdorb_keypoint) * (size_t)capacity * B));
+      CU(sd_malloc(&h->d_desc[i], (size_t)32 * capacity * B));
+      CU(sd_malloc(&h->d_counts[i], sizeof(int32_t) * B));
     }
     h->out_cap = capacity;
   }
@@ -446,10 +540,11 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
     if (cudaEventCreateWithFlags(&h->ev_out[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
     if (cudaEventCreateWithFlags(&h->ev_pyr_pack[i], cudaEventDisableTiming) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   }
-  if (cudaMalloc(&h->d_umax, sizeof(int) * 16) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
+  if (sd_malloc(&h->d_umax, sizeof(int) * 16) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
   if (cudaMemcpy(h->d_umax, h->tables.umax, sizeof(int) * 16, cudaMemcpyHostToDevice) != cudaSuccess) return fail(SDORB_ERR_CUDA);
-  if (cudaMalloc(&h->d_error, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
+  if (sd_malloc(&h->d_error, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_NOMEM);
   if (cudaMemset(h->d_error, 0, sizeof(int)) != cudaSuccess) return fail(SDORB_ERR_CUDA);
+  if (cudaStreamSynchronize(cudaStreamLegacy) != cudaSuccess) return fail(SDORB_ERR_CUDA);  // the fills above, before any stream of the handle runs
   if (configure_kernels() != 0 || configure_frame_kernels() != 0 || configure_search_kernels() != 0 || configure_octree_kernel() != 0)
     return fail(SDORB_ERR_CUDA);
   *out = h;
@@ -469,7 +564,7 @@ void sdorb_destroy(sdorb_handle* h) {
     free_geometry_scratch(h);
     dfree(h->d_umax);
     dfree(h->d_error);
-    if (h->d_match_buf) cudaFree(h->d_match_buf);
+    if (h->d_match_buf) sd_free(h->d_match_buf);
     if (h->h_pyr) cudaFreeHost(h->h_pyr);
     if (h->h_res) cudaFreeHost(h->h_res);
     if (h->h_in) cudaFreeHost(h->h_in);
@@ -680,7 +775,7 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
   int64_t pyr_off[SDORB_MAX_LEVELS], pyr_frame = 0;
   pyramid_layout(h->geom, pyr_off, &pyr_frame);
   if (pyramid && !h->d_pyr_out[0])
-    for (int i = 0; i < 2; ++i) CU(cudaMalloc(&h->d_pyr_out[i], (size_t)pyr_frame * B + 256));
+    for (int i = 0; i < 2; ++i) CU(sd_malloc(&h->d_pyr_out[i], (size_t)pyr_frame * B + 256));
   int pass = 0;
   const int n_min = std::max(B / 8, 1);
   int ramp = n_min;
@@ -974,7 +1069,7 @@ int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, 
     if (pad_bytes > h->d_pyr_pad_bytes) {
       dfree(h->d_pyr_pad);
       h->d_pyr_pad_bytes = 0;
-      CU(cudaMalloc(&h->d_pyr_pad, pad_bytes));
+      CU(sd_malloc(&h->d_pyr_pad, pad_bytes));
       h->d_pyr_pad_bytes = pad_bytes;
     }
     for (int l = 0; l < nl; ++l) {
@@ -1096,10 +1191,10 @@ namespace {
 // scratch for the host-memory forms of the small batched entry points: one growing device buffer, carved by the caller
 int ensure_match_buf(sdorb_handle* h, size_t need) {
   if (need > h->match_buf_bytes) {
-    if (h->d_match_buf) cudaFree(h->d_match_buf);
+    if (h->d_match_buf) sd_free(h->d_match_buf);
     h->d_match_buf = nullptr;
     h->match_buf_bytes = 0;
-    CU(cudaMalloc(&h->d_match_buf, need));
+    CU(sd_malloc(&h->d_match_buf, need));
     h->match_buf_bytes = need;
   }
   return SDORB_OK;
@@ -1833,6 +1928,24 @@ int sdorb_get_stage_times(sdorb_handle* h, double* ms, int64_t* launches, int re
 
 int64_t sdorb_kernel_launches(const sdorb_handle* h) { return h ? h->launches : 0; }
 
+int64_t sdorb_debug_guard_check(sdorb_handle* h) {
+  if (!h) return SDORB_ERR_BAD_ARG;
+  if (!guard_on()) return -1000;  // not a guarded run
+  DeviceGuard guard(h->device);
+  if (cudaDeviceSynchronize() != cudaSuccess) return SDORB_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(g_guard_mu);
+  h->cuda_error = g_guard_freed_msg;
+  int64_t bad = g_guard_bad_freed;
+  g_guard_bad_freed = 0;
+  g_guard_freed_msg.clear();
+  for (const auto& kv : g_guard_live) {
+    const int64_t n = guard_scan(kv.second, &h->cuda_error);
+    if (n < 0) return SDORB_ERR_CUDA;
+    bad += n;
+  }
+  return bad;
+}
+
 int sdorb_debug_pipe_probe(sdorb_handle* h, int pipe, double* warp_instr_per_s, double* warp_instr_per_clk_per_sm) {
   if (!h || pipe < 0 || pipe > 2) return SDORB_ERR_BAD_ARG;
   DeviceGuard guard(h->device);
@@ -1849,7 +1962,7 @@ int sdorb_debug_nth_element(sdorb_handle* h, uint32_t* entries, int n, int nth) 
   if (!h || !entries || n <= 0 || nth < 0 || nth >= n || n > 65535) return SDORB_ERR_BAD_ARG;
   DeviceGuard guard(h->device);
   uint32_t* d = nullptr;
-  CU(cudaMalloc(&d, sizeof(uint32_t) * (size_t)n));
+  CU(sd_malloc(&d, sizeof(uint32_t) * (size_t)n));
   int rc = SDORB_OK;
   if (cudaMemcpy(d, entries, sizeof(uint32_t) * (size_t)n, cudaMemcpyHostToDevice) != cudaSuccess) rc = SDORB_ERR_CUDA;
   if (rc == SDORB_OK) {
@@ -1858,7 +1971,7 @@ int sdorb_debug_nth_element(sdorb_handle* h, uint32_t* entries, int n, int nth) 
     if (cudaStreamSynchronize(h->s_compute) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = SDORB_ERR_CUDA;
   }
   if (rc == SDORB_OK && cudaMemcpy(entries, d, sizeof(uint32_t) * (size_t)n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = SDORB_ERR_CUDA;
-  cudaFree(d);
+  sd_free(d);
   return rc;
 }
 

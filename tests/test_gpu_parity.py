@@ -577,6 +577,29 @@ def test_every_device_gives_identical_bytes():
         assert blob == ref, "device %d differs from device 0" % g
 
 
+def test_guarded_allocations_stay_intact():
+    """The bounds-checked debug mode (compute-sanitizer is closed on this pool): a second pytest process runs the extraction,
+    matcher and search suites with SDORB_GUARD=1 -- 256 KB guard bands around every device buffer of the library, payloads
+    poisoned -- and tests/conftest.py checks all bands after every test (buffers freed meanwhile are checked as they go).  An
+    out-of-bounds write of any kernel fails there by name; an out-of-bounds or uninitialised read shows up as a parity failure."""
+    import subprocess
+    import sys
+    env = dict(os.environ, SDORB_GUARD="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sel = ("stages_match or odd_sizes or batch_host or ragged_tail or device_entry or strided or geometry_switch or zero_corner or fewer_corners "
+           "or massive or extreme or pyramid or match_batch or match_greedy or hamming or distinctive or frame_post or undistort or multi_handle "
+           "or single_frame")
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "-k", sel, os.path.join(root, "tests", "test_gpu_parity.py"),
+                        os.path.join(root, "tests", "test_gpu_search.py"), os.path.join(root, "tests", "test_orbslam2_mode.py")],
+                       env=env, cwd=root, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
+    assert " passed" in r.stdout
+    # and the mode really was on in that process
+    probe = subprocess.run([sys.executable, "-c", "from sdslam_b200 import api; e = api.ORBextractor(10, 1.2, 2, 20, max_width=64, max_height=64, "
+                            "max_batch=1); print('guard', e.guard_check())"], env=env, cwd=root, capture_output=True, text=True, timeout=300)
+    assert "guard 0" in probe.stdout, probe.stdout + probe.stderr
+
+
 def test_oversized_batches_are_rejected(ex_c1):
     """Entry points whose batch index rides on gridDim.y refuse more than SDORB_MAX_GRID_BATCH frames up front."""
     n = 65536
