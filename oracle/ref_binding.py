@@ -188,7 +188,7 @@ def _mlib(native=False):
         L.ref_distinctive.restype = i
         L.ref_distinctive.argtypes = [vp, i]
         L.ref_search_by_projection.restype = i
-        L.ref_search_by_projection.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, i, vp, f, f, f, f, i, i, vp]
+        L.ref_search_by_projection.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, i, vp, f, f, f, f, i, i, vp, i]
         L.ref_search_map_points.restype = i
         L.ref_search_map_points.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, vp, i, vp, i, vp, f, f, f, f, vp]
         _MATCHER_SIGS_SET.add(id(L))
@@ -274,8 +274,9 @@ def distinctive(desc):
 
 
 def search_by_projection(kps_last, kps_last_un, proj, flags_last, desc_mp, kps_cur_un, desc_cur, u_right_cur, occupied_cur, gp,
-                         scale_factors, bounds, th, mbf, mode, check_orientation=True):
-    """SearchByProjection(CurrentFrame, LastFrame, th, bMono = false); proj[:, 2] (invzc) must be 1 (see the shim)."""
+                         scale_factors, bounds, th, mbf, mode, check_orientation=True, keyframe_overload=False):
+    """SearchByProjection(CurrentFrame, LastFrame, th, bMono = false) -- or, keyframe_overload, its KeyFrame twin (:1077-1207);
+    proj[:, 2] (invzc) must be 1 (see the shim)."""
     kl, klu, kc = _k(kps_last), _k(kps_last_un), _k(kps_cur_un)
     pr = _f32(proj).reshape(-1, 3)
     assert (pr[:, 2] == 1).all()
@@ -283,7 +284,7 @@ def search_by_projection(kps_last, kps_last_un, proj, flags_last, desc_mp, kps_c
     sf, bd = _f32(scale_factors), _f32(bounds)
     asg = np.full(max(len(kc), 1), -1, np.int32)
     n = _mlib().ref_search_by_projection(_p(kl), _p(klu), _p(pr), _p(fl), _p(dm), len(kl), _p(kc), _p(dc), _p(ur), _p(oc), len(kc), _p(sf), len(sf),
-                                         _p(bd), gp[2], gp[3], th, mbf, mode, int(check_orientation), _p(asg))
+                                         _p(bd), gp[2], gp[3], th, mbf, mode, int(check_orientation), _p(asg), int(keyframe_overload))
     return n, asg[:len(kc)]
 
 
@@ -351,3 +352,52 @@ def search_by_sim3(side1, side2, gp, scale_factors, th):
     n = _msigs2().ref_search_by_sim3(_p(p1), _p(l1), _p(f1), _p(m1), len(k1), _p(p2), _p(l2), _p(f2), _p(m2), len(k2), _p(k1), _p(d1), _p(k2), _p(d2),
                                      gp[0], gp[1], gp[2], gp[3], _p(sf), len(sf), th, _p(out))
     return n, out[:len(k1)]
+
+
+def _msigs3():
+    L = _msigs2()
+    if not getattr(L, "_sdorb_sigs3", False):
+        vp, i, f = C.c_void_p, C.c_int, C.c_float
+        L.ref_fuse_sim3_search.argtypes = [vp, vp, vp, vp, i, vp, vp, i, f, f, f, f, vp, i, f, vp]
+        L.ref_search_by_projection_sim3.restype = i
+        L.ref_search_by_projection_sim3.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, i, f, f, f, f, vp, i, i, vp]
+        L.ref_search_by_projection_reloc.restype = i
+        L.ref_search_by_projection_reloc.argtypes = [vp, vp, vp, vp, vp, i, vp, vp, vp, i, vp, i, vp, f, f, f, i, i, vp]
+        L._sdorb_sigs3 = True
+    return L
+
+
+def fuse_sim3_search(proj, level, flags, desc_mp, kps_un, desc, gp, scale_factors, th):
+    """The keypoint search of ORBmatcher::Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) at Scw = identity: best_idx per point."""
+    pr = _f32(proj).reshape(-1, 3)
+    lv, fl, dm = np.ascontiguousarray(level, np.int32), _u8(flags), _u8(desc_mp)
+    k, d, sf = _k(kps_un), _u8(desc), _f32(scale_factors)
+    out = np.full(max(len(pr), 1), -1, np.int32)
+    _msigs3().ref_fuse_sim3_search(_p(pr), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), len(k), gp[0], gp[1], gp[2], gp[3], _p(sf), len(sf), th,
+                                   _p(out))
+    return out[:len(pr)]
+
+
+def search_by_projection_sim3(proj, level, flags, desc_mp, kps_un, desc, matched, gp, scale_factors, th):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) at Scw = identity: (nmatches, assigned)."""
+    pr = _f32(proj).reshape(-1, 3)
+    lv, fl, dm = np.ascontiguousarray(level, np.int32), _u8(flags), _u8(desc_mp)
+    k, d, mt, sf = _k(kps_un), _u8(desc), _u8(matched), _f32(scale_factors)
+    out = np.full(max(len(k), 1), -1, np.int32)
+    n = _msigs3().ref_search_by_projection_sim3(_p(pr), _p(lv), _p(fl), _p(dm), len(pr), _p(k), _p(d), _p(mt), len(k), gp[0], gp[1], gp[2], gp[3],
+                                                _p(sf), len(sf), int(th), _p(out))
+    return n, out[:len(k)]
+
+
+def search_by_projection_reloc(kps_kf_un, proj, valid, pred_level, desc_mp, kps_cur_un, desc_cur, has_mp_cur, gp, scale_factors, bounds, th,
+                               orb_dist, check_orientation=True):
+    """ORBmatcher::SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist): (nmatches, assigned)."""
+    kk, kc = _k(kps_kf_un), _k(kps_cur_un)
+    pr = _f32(proj).reshape(-1, 3)
+    assert (pr[:, 2] == 1).all()
+    vl, pl, dm = _u8(valid), np.ascontiguousarray(pred_level, np.int32), _u8(desc_mp)
+    dc, hm, sf, bd = _u8(desc_cur), _u8(has_mp_cur), _f32(scale_factors), _f32(bounds)
+    out = np.full(max(len(kc), 1), -1, np.int32)
+    n = _msigs3().ref_search_by_projection_reloc(_p(kk), _p(pr), _p(vl), _p(pl), _p(dm), len(kk), _p(kc), _p(dc), _p(hm), len(kc), _p(sf), len(sf),
+                                                 _p(bd), gp[2], gp[3], th, int(orb_dist), int(check_orientation), _p(out))
+    return n, out[:len(kc)]

@@ -343,7 +343,7 @@ int ref_search_by_projection(const orc_keypoint* kps_last, const orc_keypoint* k
                              const uint8_t* desc_mp, int n_last, const orc_keypoint* kps_cur_un, const uint8_t* desc_cur,
                              const float* u_right_cur, const uint8_t* occupied_cur, int n_cur, const float* scale_factors, int nlevels,
                              const float bounds[4], float inv_w, float inv_h, float th, float mbf, int mode, int check_orientation,
-                             int32_t* assigned) {
+                             int32_t* assigned, int keyframe_overload) {
   std::lock_guard<std::mutex> lk(g_lock);
   GridParams g = {bounds[0], bounds[1], bounds[2], bounds[3], inv_w, inv_h};
   set_frame_statics(g, 1, 1, 0, 0);
@@ -382,7 +382,17 @@ int ref_search_by_projection(const orc_keypoint* kps_last, const orc_keypoint* k
       pre[(size_t)i] = p;
     }
   ORBmatcher matcher(0.9f, check_orientation != 0);
-  const int nm = matcher.SearchByProjection(Cur, Last, th, false);
+  int nm;
+  if (keyframe_overload) {
+    // SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, th, bMono) (:1077-1207): the same text with pKF for LastFrame and
+    // pMP->isBad() for mvbOutlier[i] -- the outlier associations of the frame become bad map points of the keyframe
+    for (int i = 0; i < n_last; ++i)
+      if (Last.mvbOutlier[(size_t)i] && Last.mvpMapPoints[(size_t)i]) Last.mvpMapPoints[(size_t)i]->mbBad = true;
+    KeyFrame* kl = A.keyframe(Last);
+    nm = matcher.SearchByProjection(Cur, kl, th, false);
+  } else {
+    nm = matcher.SearchByProjection(Cur, Last, th, false);
+  }
   for (int i = 0; i < n_cur; ++i) {
     MapPoint* p = Cur.mvpMapPoints[(size_t)i];
     assigned[i] = (p && p != pre[(size_t)i] && owner.count(p)) ? owner[p] : -1;
@@ -558,6 +568,112 @@ int ref_search_by_sim3(const float* proj1, const int32_t* level1, const uint8_t*
   const int nf = matcher.SearchBySim3(k1, k2, m12, s12, Eigen::Matrix3d::Identity(), Eigen::Vector3d::Zero(), th);
   for (int i = 0; i < n1; ++i) matches12[i] = m12[(size_t)i] ? index2[m12[(size_t)i]] : -1;
   return nf;
+}
+
+// ---- ORBmatcher::Fuse(KeyFrame*, Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:617-732) with Scw = identity (scw = 1, Rcw = I,
+// tcw = 0: exact); map points as in ref_fuse_search at unit depth.  best_idx[i] = keypoint the point was fused to (directly, or the
+// keypoint of the point it is to replace), else -1.
+void ref_fuse_sim3_search(const float* proj, const int32_t* level, const uint8_t* flags, const uint8_t* desc_mp, int n_mp,
+                          const orc_keypoint* kps_un, const uint8_t* desc, int n_kf, float min_x, float min_y, float inv_w, float inv_h,
+                          const float* scale_factors, int nlevels, float th, int32_t* best_idx) {
+  std::lock_guard<std::mutex> lk(g_lock);
+  GridParams g = {min_x, 1e6f, min_y, 1e6f, inv_w, inv_h};
+  set_frame_statics(g, 1, 1, 0, 0);
+  Arena A;
+  Frame F;
+  fill_frame(F, NULL, kps_un, desc, n_kf, scale_factors, nlevels, NULL, 40.f);
+  KeyFrame* kf = A.keyframe(F);
+  KeyFrame* obs = A.observer(scale_factors, nlevels);
+  std::vector<MapPoint*> pts((size_t)n_mp);
+  for (int i = 0; i < n_mp; ++i) {
+    MapPoint* p = posed_point(A, obs, proj[3 * i], proj[3 * i + 1], 1.0, level[i], desc_mp + (size_t)i * 32, kf->mfLogScaleFactor);
+    if (!(flags[i] & 1)) p->mbBad = true;
+    pts[(size_t)i] = p;
+  }
+  std::vector<MapPoint*> replace((size_t)n_mp, static_cast<MapPoint*>(NULL));
+  ORBmatcher matcher(0.8f, true);
+  matcher.Fuse(kf, Eigen::Matrix4d::Identity(), pts, th, replace);
+  for (int i = 0; i < n_mp; ++i) {
+    int idx = pts[(size_t)i]->GetIndexInKeyFrame(kf);
+    if (idx < 0 && replace[(size_t)i]) idx = replace[(size_t)i]->GetIndexInKeyFrame(kf);
+    best_idx[i] = idx;
+  }
+}
+
+// ---- ORBmatcher::SearchByProjection(KeyFrame*, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:146-254) with Scw = identity.
+// matched_in[k]: vpMatched[k] is set on entry (to a point that is not among vpPoints).  assigned[k] = index of the point the call
+// stores in vpMatched[k], else -1; returns nmatches.
+int ref_search_by_projection_sim3(const float* proj, const int32_t* level, const uint8_t* flags, const uint8_t* desc_mp, int n_mp,
+                                  const orc_keypoint* kps_un, const uint8_t* desc, const uint8_t* matched_in, int n_kf, float min_x,
+                                  float min_y, float inv_w, float inv_h, const float* scale_factors, int nlevels, int th, int32_t* assigned) {
+  std::lock_guard<std::mutex> lk(g_lock);
+  GridParams g = {min_x, 1e6f, min_y, 1e6f, inv_w, inv_h};
+  set_frame_statics(g, 1, 1, 0, 0);
+  Arena A;
+  Frame F;
+  fill_frame(F, NULL, kps_un, desc, n_kf, scale_factors, nlevels, NULL, 40.f);
+  KeyFrame* kf = A.keyframe(F);
+  KeyFrame* obs = A.observer(scale_factors, nlevels);
+  std::vector<MapPoint*> pts((size_t)n_mp);
+  std::map<MapPoint*, int> index;
+  for (int i = 0; i < n_mp; ++i) {
+    MapPoint* p = posed_point(A, obs, proj[3 * i], proj[3 * i + 1], 1.0, level[i], desc_mp + (size_t)i * 32, kf->mfLogScaleFactor);
+    if (!(flags[i] & 1)) p->mbBad = true;
+    pts[(size_t)i] = p;
+    index[p] = i;
+  }
+  std::vector<MapPoint*> matched((size_t)n_kf, static_cast<MapPoint*>(NULL));
+  for (int k = 0; k < n_kf; ++k)
+    if (matched_in[k]) matched[(size_t)k] = A.point(Eigen::Vector3d(0, 0, 1), obs);
+  ORBmatcher matcher(0.75f, true);
+  const int nm = matcher.SearchByProjection(kf, Eigen::Matrix4d::Identity(), pts, matched, th);
+  for (int k = 0; k < n_kf; ++k) assigned[k] = (matched[(size_t)k] && index.count(matched[(size_t)k])) ? index[matched[(size_t)k]] : -1;
+  return nm;
+}
+
+// ---- ORBmatcher::SearchByProjection(Frame& CurrentFrame, KeyFrame* pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1306-1421), the
+// relocalisation search, with the current frame at the identity pose.  Keyframe keypoint i carries a map point when valid[i] & 1
+// (bad or already found when the bit is clear, alternately), at (proj[3i], proj[3i+1], 1) with PredictScale = pred_level[i].
+// has_mp_cur[k]: CurrentFrame.mvpMapPoints[k] is set on entry.  assigned[k] = keyframe keypoint whose point the call stores there.
+int ref_search_by_projection_reloc(const orc_keypoint* kps_kf_un, const float* proj, const uint8_t* valid, const int32_t* pred_level,
+                                   const uint8_t* desc_mp, int n_kf, const orc_keypoint* kps_cur_un, const uint8_t* desc_cur,
+                                   const uint8_t* has_mp_cur, int n_cur, const float* scale_factors, int nlevels, const float bounds[4],
+                                   float inv_w, float inv_h, float th, int orb_dist, int check_orientation, int32_t* assigned) {
+  std::lock_guard<std::mutex> lk(g_lock);
+  GridParams g = {bounds[0], bounds[1], bounds[2], bounds[3], inv_w, inv_h};
+  set_frame_statics(g, 1, 1, 0, 0);
+  Arena A;
+  Frame Fk, Cur;
+  std::vector<uint8_t> dk((size_t)n_kf * 32 + 32, 0);
+  fill_frame(Fk, NULL, kps_kf_un, &dk[0], n_kf, scale_factors, nlevels, NULL, 40.f);
+  fill_frame(Cur, NULL, kps_cur_un, desc_cur, n_cur, scale_factors, nlevels, NULL, 40.f);
+  KeyFrame* kf = A.keyframe(Fk);
+  KeyFrame* obs = A.observer(scale_factors, nlevels);
+  std::set<MapPoint*> found;
+  std::map<MapPoint*, int> owner;
+  for (int i = 0; i < n_kf; ++i) {
+    if (!(valid[i] & 1) && (i % 3 == 0)) continue;  // no map point at all
+    MapPoint* p = posed_point(A, obs, proj[3 * i], proj[3 * i + 1], 1.0, pred_level[i], desc_mp + (size_t)i * 32, Cur.mfLogScaleFactor);
+    if (!(valid[i] & 1)) {
+      if (i % 3 == 1) p->mbBad = true;
+      else found.insert(p);
+    }
+    kf->AddMapPoint(p, (size_t)i);
+    owner[p] = i;
+  }
+  std::vector<MapPoint*> pre((size_t)n_cur, static_cast<MapPoint*>(NULL));
+  for (int k = 0; k < n_cur; ++k)
+    if (has_mp_cur[k]) {
+      pre[(size_t)k] = A.point(Eigen::Vector3d(0, 0, 1), obs);
+      Cur.mvpMapPoints[(size_t)k] = pre[(size_t)k];
+    }
+  ORBmatcher matcher(0.9f, check_orientation != 0);
+  const int nm = matcher.SearchByProjection(Cur, kf, found, th, orb_dist);
+  for (int k = 0; k < n_cur; ++k) {
+    MapPoint* p = Cur.mvpMapPoints[(size_t)k];
+    assigned[k] = (p && p != pre[(size_t)k] && owner.count(p)) ? owner[p] : -1;
+  }
+  return nm;
 }
 
 }  // extern "C"

@@ -157,6 +157,9 @@ def test_search_by_projection_equals_reference(seed, nl, nc, th, mode, orient, s
     n, asg = orc.search_by_projection(kl, klu, proj, flags, dmp, kc, dc, ur, occ, _orc_grid(kc, gp), SF, bounds, th, 40.0, mode, orient)
     rn, rasg = ref.search_by_projection(kl, klu, proj, flags, dmp, kc, dc, ur, occ, gp, SF, bounds, th, 40.0, mode, orient)
     assert n == rn and np.array_equal(asg, rasg)
+    # the KeyFrame twin SearchByProjection(Frame&, KeyFrame*, th, bMono) (:1077-1207) gives the same result on the same data
+    kn, kasg = ref.search_by_projection(kl, klu, proj, flags, dmp, kc, dc, ur, occ, gp, SF, bounds, th, 40.0, mode, orient, keyframe_overload=True)
+    assert n == kn and np.array_equal(asg, kasg)
     if seed == 0:
         assert n > 100
 
@@ -264,5 +267,61 @@ def test_search_by_sim3_equals_reference(seed, n1, n2, th, dup):
     n, m12, m1, m2 = orc.search_by_sim3(s1 + (_orc_grid(s1[4], gp),), s2 + (_orc_grid(s2[4], gp),), SF, th)
     rn, rm12 = ref.search_by_sim3(s1, s2, gp, SF, th)
     assert n == rn and np.array_equal(m12, rm12)
+    if seed == 0:
+        assert n > 100
+
+
+def _inside(proj):
+    proj[:, 0] = np.maximum(proj[:, 0], np.float32(1))  # KeyFrame::IsInImage: inside the lower bounds
+    proj[:, 1] = np.maximum(proj[:, 1], np.float32(1))
+    return proj
+
+
+@pytest.mark.parametrize("seed,nf,nmp,th", [(0, 600, 500, 3.0), (1, 500, 700, 4.0), (2, 0, 50, 3.0), (4, 700, 900, 4.0)])
+def test_fuse_sim3_form_equals_reference(seed, nf, nmp, th):
+    """The keypoint search of the Sim3 overload Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) (src/ORBmatcher.cc:617-732): no
+    reprojection gate, TH_LOW; read back through AddMapPoint / vpReplacePoint."""
+    _, _, kf, df = sc.frame_pair(seed + 140, 10, nf, dup=0.3 if seed == 4 else 0.0, level0=0.3)
+    proj, lvl, fl, _ = sc.fuse_inputs(seed, kf, nmp, stereo=False)
+    proj = _inside(proj)
+    dmp = sc.fuse_descriptors(seed, df, nf, nmp)
+    gp = sc.grid_params()
+    bi, bd = orc.fuse_search(proj, lvl, fl, dmp, kf, df, None, _orc_grid(kf, gp), SF, None, th, False, 50)
+    rbi = ref.fuse_sim3_search(proj, lvl, fl, dmp, kf, df, gp, SF, th)
+    assert np.array_equal(bi, rbi)
+    if seed < 2:
+        assert (bi >= 0).sum() > 100
+
+
+@pytest.mark.parametrize("seed,nf,nmp,th,dup", [(0, 600, 500, 10, 0.0), (1, 500, 700, 4, 0.0), (2, 0, 50, 10, 0.0), (3, 200, 0, 10, 0.0),
+                                                (4, 700, 900, 10, 0.3)])
+def test_search_by_projection_sim3_equals_reference(seed, nf, nmp, th, dup):
+    """ORBmatcher::SearchByProjection(pKF, Scw, vpPoints, vpMatched, th) (src/ORBmatcher.cc:146-254): keypoints taken on entry or
+    earlier in the call are skipped."""
+    _, _, kf, df = sc.frame_pair(seed + 140, 10, nf, dup=dup, level0=0.3)
+    proj, lvl, fl, _ = sc.fuse_inputs(seed, kf, nmp, stereo=False)
+    proj = _inside(proj)
+    dmp = sc.fuse_descriptors(seed, df, nf, nmp)
+    matched = (np.random.default_rng(seed).random(nf) < 0.15).astype(np.uint8)
+    gp = sc.grid_params()
+    n, asg = orc.search_by_projection_sim3(proj, lvl, fl, dmp, kf, df, matched, _orc_grid(kf, gp), SF, th)
+    rn, rasg = ref.search_by_projection_sim3(proj, lvl, fl, dmp, kf, df, matched, gp, SF, th)
+    assert n == rn and np.array_equal(asg, rasg)
+    if seed == 0:
+        assert n > 100
+
+
+@pytest.mark.parametrize("seed,nk,nc,th,orb_dist,orient", [(0, 500, 520, 10.0, 100, True), (1, 400, 300, 3.0, 64, True), (2, 300, 400, 10.0, 64, False),
+                                                           (3, 0, 100, 10.0, 100, True)])
+def test_relocalisation_projection_search_equals_reference(seed, nk, nc, th, orb_dist, orient):
+    """The relocalisation overload SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist) (src/ORBmatcher.cc:1306-1421)
+    against the oracle's Frame / Frame function driven with the mapping of sdorb_projection_search::orb_dist."""
+    a = sc.kf_projection_args(seed, nk, nc)
+    gp, bounds = sc.grid_params(), (0.0, 640.0, 0.0, 480.0)
+    n, asg = orc.search_by_projection(a["k_level"], a["kk"], a["proj"], a["flags"], a["dmp"], a["kc"], a["dc"], a["ur"], a["has_mp"],
+                                      _orc_grid(a["kc"], gp), SF, bounds, th, 0.0, 0, orient, orb_dist=orb_dist)
+    rn, rasg = ref.search_by_projection_reloc(a["kk"], a["proj"], a["valid"], a["pred"], a["dmp"], a["kc"], a["dc"], a["has_mp"], gp, SF, bounds, th,
+                                              orb_dist, orient)
+    assert n == rn and np.array_equal(asg, rasg)
     if seed == 0:
         assert n > 100
