@@ -1158,7 +1158,10 @@ int sdorb_extract(sdorb_handle* h, const uint8_t* image, int width, int height, 
         for (int y = 0; y < height; ++y) memcpy(v.data + (size_t)y * v.stride, image + (size_t)y * stride, (size_t)width);
       if (v.border > 0) sdorb_fill_border_reflect101(v.data, width, height, v.stride, v.border);
     }
-    CU(cudaEventSynchronize(h->ev_pyr_host));
+    if (cudaEventSynchronize(h->ev_pyr_host) != cudaSuccess) {
+      h->cuda_error = "pyramid read-back: cudaEventSynchronize failed";
+      return drain(SDORB_ERR_CUDA);
+    }
     for (int l = 1; l < nl; ++l) {
       const LevelGeom& L = g.lv[l];
       const sdorb_pyr_view& v = pyramid[l];
