@@ -8,7 +8,7 @@
  *
  * Parity pin (round 2: PINNED to the reference itself).  The reference has no tests or golden vectors,
  * but its own ORBextractor.cc compiles unmodified against oracle/ref_compat (a cv:: surface whose pixel primitives are the
- * ones below) into oracle/_ref/libsdorb_ref.so (oracle/ref_build/Makefile).  tests/test_ref_parity.py and tools/ref_sweep.py
+ * ones below) into oracle/_ref/libsdorb_ref.so (oracle/ref_build/Makefile).  tests/test_ref_parity.py and tests/tools/ref_sweep.py
  * assert  restatement == reference  byte for byte (keypoints incl. order, angles, descriptors, pyramid and its borders,
  * constructor tables, where it throws) on every fixture, the staged configurations, random sizes / parameters and 6560 bench
  * frames; the fixtures under tests/golden/ are generated from the reference (tests/golden/make_golden.py).  The OpenCV / glibc /

@@ -91,7 +91,7 @@ def test_staged_configs_equal_reference(label, img, params):
 
 
 def test_c3_frames_equal_reference():
-    """256 frames of the bench workload (C3: 640x480, 1000 kp), frame-parallel; tools/ref_sweep.py runs 4096 + the other
+    """256 frames of the bench workload (C3: 640x480, 1000 kp), frame-parallel; tests/tools/ref_sweep.py runs 4096 + the other
     shapes (log under profiles/)."""
     imgs = synth.frames(256)
     n = os.cpu_count() or 1

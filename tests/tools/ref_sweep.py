@@ -1,21 +1,21 @@
 #!/usr/bin/env python3
 """Oracle-versus-reference sweep on the CPU: the restatement (oracle/libsdorb_oracle.so) against the reference's own sources
 compiled unmodified (oracle/_ref/libsdorb_ref.so, oracle/ref_build/Makefile) on thousands of synthetic frames -- the same frame
-generators, seeds and shapes tools/sweep.py feeds to the GPU, so   GPU == oracle (tools/sweep.py)   and   oracle == reference
+generators, seeds and shapes tests/tools/sweep.py feeds to the GPU, so   GPU == oracle (tests/tools/sweep.py)   and   oracle == reference
 (this file)   meet on identical inputs.  Prints one line per configuration; exit code 1 on any mismatch.
-Usage: python tools/ref_sweep.py [scale]   (scale 1.0 = 4096 C3 frames; log committed under profiles/)"""
+Usage: python tests/tools/ref_sweep.py [scale]   (scale 1.0 = 4096 C3 frames; log committed under profiles/)"""
 import os
 import sys
 import time
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import binding as orc  # noqa: E402
 from oracle import ref_binding as ref  # noqa: E402
 from sdslam_b200 import synth  # noqa: E402
 
-CONFIGS = [  # label, generator, width, height, params, frames  (the reference-mode rows of tools/sweep.py)
+CONFIGS = [  # label, generator, width, height, params, frames  (the reference-mode rows of tests/tools/sweep.py)
     ("C3 smooth_noise", "smooth_noise", 640, 480, (1000, 1.2, 8, 20), 4096),
     ("C3 rects", "rects", 640, 480, (1000, 1.2, 8, 20), 1024),
     ("C2 euroc", "smooth_noise", 752, 480, (1000, 1.2, 8, 20), 512),
