@@ -21,9 +21,11 @@
  * (:43-119, :146-254, :256-357, :359-462, :535-586, :682-708, :734-944, :946-1207, :1209-1304, :1306-1421, :1423-1454),
  * Frame::GetFeaturesInArea / AssignFeaturesToGrid / UndistortKeyPoints / ComputeStereoFromRGBD (src/Frame.cc), MapPoint::
  * ComputeDistinctiveDescriptors (src/MapPoint.cc:225-284) and the ORB-SLAM2-style extractor mode.  The reference holds no tests
- * or vectors for any of them and cannot be built here: the matcher functions are pinned against separately written Python
- * restatements (tests/search_cases.py) and committed fixtures made from those; the ORB-SLAM2-style mode is PARITY UNPINNED
- * against ORB-SLAM2 itself (its source is not in this image).
+ * or vectors for any of them.  PARITY PIN: every function here that restates reference text is compared byte for byte with that
+ * text itself -- src/{ORBextractor,ORBmatcher,Frame,KeyFrame,MapPoint,Map}.cc compiled unmodified into oracle/_ref by
+ * oracle/ref_build/Makefile on the cv:: / Eigen surface of oracle/ref_compat (tests/test_ref_parity.py, tests/test_ref_matchers.py,
+ * tests/tools/ref_sweep.py) -- and additionally against separately written Python restatements (tests/search_cases.py).  The
+ * ORB-SLAM2-style mode alone is PARITY UNPINNED against ORB-SLAM2 itself (its source is not in this image).
  *
  * Build: g++ -O2 -std=c++17 -ffp-contract=off (see Makefile).  -ffp-contract=off matters: every
  * fused multiply-add the reference's build performs is written as an explicit fmaf() here.

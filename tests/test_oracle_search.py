@@ -1,7 +1,8 @@
 """Pins the oracle's guided matchers (oracle/sdorb_oracle.cc: orc_features_in_area, orc_three_maxima,
 orc_search_for_initialization, orc_search_by_projection) against a second, independent restatement of
 /root/reference/src/ORBmatcher.cc:256-357, 946-1075, 1423-1454 and src/Frame.cc:271-321 (tests/search_cases.py).
-The reference has no tests or fixtures for these functions and cannot be compiled here (Eigen / OpenCV C++ headers are
+(Round 2: the same oracle functions are also compared with the reference's own compiled text, tests/test_ref_matchers.py.)
+The reference has no tests or fixtures for these functions and its own build cannot run here (Eigen / OpenCV C++ headers are
 absent), so two independently written restatements agreeing is the pin; a committed fixture (tests/golden/matcher/search_pairs.npz,
 made by tests/golden/make_search_golden.py from the Python restatement) freezes it.  CPU only."""
 import os
