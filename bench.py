@@ -694,7 +694,7 @@ def run_ours(args):
                         "l2": "batch (%.0f MB of frames per GPU per step) larger than the 126 MB L2; no flush" % (frames_per_gpu * w * h / 1e6),
                         "sharding": "ONE batch of %d frames split into contiguous ranges over the ranks (strong scaling); no collective in "
                                     "the loop; final NCCL gather to rank 0 timed separately" % frames_global,
-                        "profiling": "headline loop runs without stage events (programmatic dependent launch active); stages from a second loop",
+                        "profiling": "headline loop runs without stage events; the per-stage table comes from a second loop with them",
                         "ms_per_step_with_stage_events": m["ms_profiled"] / steps},
             "e2e": e2e,
             "gpu_launches": int(m["launches"]),
