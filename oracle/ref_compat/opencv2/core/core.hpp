@@ -46,6 +46,7 @@ typedef unsigned short ushort;
 #define CV_CN_SHIFT 3
 #define CV_DEPTH_MAX (1 << CV_CN_SHIFT)
 #define CV_8U 0
+#define CV_16U 2
 #define CV_32F 5
 #define CV_64F 6
 #define CV_MAT_DEPTH_MASK (CV_DEPTH_MAX - 1)
@@ -53,6 +54,7 @@ typedef unsigned short ushort;
 #define CV_MAKETYPE(depth, cn) (CV_MAT_DEPTH(depth) + (((cn) - 1) << CV_CN_SHIFT))
 #define CV_MAT_CN(flags) ((((flags) >> CV_CN_SHIFT) & 63) + 1)
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC2 CV_MAKETYPE(CV_32F, 2)
 #define CV_64FC1 CV_MAKETYPE(CV_64F, 1)
@@ -78,6 +80,7 @@ class Exception : public std::exception {
   std::string msg;
 };
 #define SDORB_CV_ASSERT(expr) do { if (!(expr)) throw cv::Exception("OpenCV assertion failed: " #expr); } while (0)
+#define CV_Assert(expr) SDORB_CV_ASSERT(expr)
 
 template <typename T> static inline T saturate_cast(float v) { return T(v); }
 template <typename T> static inline T saturate_cast(double v) { return T(v); }
@@ -150,8 +153,8 @@ struct MatExpr {
  * src/Frame.cc also keeps the distortion coefficients and the point list of cv::undistortPoints in CV_32F matrices). */
 static inline size_t sdorb_elem_size(int type) {
   const int depth = CV_MAT_DEPTH(type);
-  SDORB_CV_ASSERT(depth == CV_8U || depth == CV_32F || depth == CV_64F);
-  return (size_t)(depth == CV_8U ? 1 : depth == CV_32F ? 4 : 8) * (size_t)CV_MAT_CN(type);
+  SDORB_CV_ASSERT(depth == CV_8U || depth == CV_16U || depth == CV_32F || depth == CV_64F);
+  return (size_t)(depth == CV_8U ? 1 : depth == CV_16U ? 2 : depth == CV_32F ? 4 : 8) * (size_t)CV_MAT_CN(type);
 }
 
 class Mat {

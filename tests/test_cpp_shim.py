@@ -15,12 +15,18 @@ from sdslam_b200 import synth
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.fixture(scope="module")
-def driver(tmp_path_factory):
+# The shim is compiled against TWO independently written cv:: surfaces (OpenCV's own C++ headers are not in this image): the
+# 100-line mock of tests/helpers/cv_mock and oracle/ref_compat, the surface the reference's own sources are compiled against for
+# the parity library (ref-counted Mat with ROI views, InputArray / OutputArray proxies, CV_Assert throwing cv::Exception).
+CV_SURFACES = {"cv_mock": os.path.join(ROOT, "tests", "helpers", "cv_mock"), "ref_compat": os.path.join(ROOT, "oracle", "ref_compat")}
+
+
+@pytest.fixture(scope="module", params=sorted(CV_SURFACES))
+def driver(request, tmp_path_factory):
     so = sbuild.build()
-    exe = str(tmp_path_factory.mktemp("shim") / "shim_driver")
+    exe = str(tmp_path_factory.mktemp("shim_" + request.param) / "shim_driver")
     subprocess.check_call(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
-                           "-I", os.path.join(ROOT, "tests", "helpers", "cv_mock"), "-o", exe,
+                           "-I", CV_SURFACES[request.param], "-o", exe,
                            os.path.join(ROOT, "tests", "helpers", "shim_driver.cc"), so,
                            "-Wl,-rpath," + os.path.dirname(so)])
     return exe
