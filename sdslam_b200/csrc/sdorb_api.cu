@@ -1961,7 +1961,7 @@ int64_t sdorb_debug_guard_check(sdorb_handle* h) {
 }
 
 int sdorb_debug_pipe_probe(sdorb_handle* h, int pipe, double* warp_instr_per_s, double* warp_instr_per_clk_per_sm) {
-  if (!h || pipe < 0 || pipe > 2) return SDORB_ERR_BAD_ARG;
+  if (!h || pipe < 0 || pipe > 7) return SDORB_ERR_BAD_ARG;
   DeviceGuard guard(h->device);
   const int e = run_pipe_probe(pipe, h->s_compute, warp_instr_per_s, warp_instr_per_clk_per_sm);
   h->launches += 2;
