@@ -39,7 +39,8 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(bdir, os.path.splitext(src)[0] + ".o")
-        cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = ([_nvcc()] + [f for f in NVCC_FLAGS if f != "--use_fast_math=false"] + os.environ.get("SDORB_NVCC_EXTRA", "").split() +
+               ["-c", os.path.join(CSRC, src), "-o", obj])  # SDORB_NVCC_EXTRA: -D switches of tuning experiments
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     log = []

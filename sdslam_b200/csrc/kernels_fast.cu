@@ -46,7 +46,9 @@ constexpr int HW = 2 * PWORDS;                         // words per row of one f
 constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in words (one zero word on each side)
 constexpr int NT = 128;
 static_assert(OH <= 64, "row flags are two 32-bit ballots");
-constexpr int CTAS_PER_SM = 5;                         // 45.4 KB of shared memory per CTA
+constexpr int SMEM_BYTES = 4 * (2 * PROWS * HW + SROWS * TWORDS + 4 + 1);  // the two pixel copies, the score tile, row flags, level
+constexpr int CTAS_BY_SMEM = 232448 / (SMEM_BYTES + 1024);                 // 227 KB per SM, 1 KB reserved per CTA
+constexpr int CTAS_PER_SM = CTAS_BY_SMEM < 7 ? CTAS_BY_SMEM : 7;           // 7 x 128 threads x 72 registers fit the register file
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(a, b, s); }
 
@@ -418,6 +420,50 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
   // ---- phase N: cell-bounded strict non-max suppression on the score tile; the survivors' t bytes go to the map
   uint8_t* map = p.nms + L.plane_base * p.batch_cap + (int64_t)frame * L.plane_bytes;
   const bool out_lane = k >= 1 && k <= nw - 2 && xw < L.pitch;
+  if (!NARROW) {
+    // Full tile: a warp takes a band of OH / 4 consecutive output rows and walks down the score tile once.  The 3x3 maximum is
+    // taken row-wise: H(row) = max of the row's three columns (left / right masked by the cell's column limits) serves the
+    // output rows above and below it, M(row) = max of its left and right columns serves the row itself, so a score row costs
+    // three window PRMT and four min / max once instead of once per output row that looks at it.
+    constexpr int BAND = OH / (NT / 32);
+    static_assert(OH % (NT / 32) == 0, "bands of whole rows");
+    const int o0 = warp * BAND;  // first output row of the band = score row o0 + 1
+    const uint32_t up0 = s_rowflags[0][0], up1 = s_rowflags[1][0], dn0 = s_rowflags[0][1], dn1 = s_rowflags[1][1];
+    uint32_t H[BAND + 2][2], M[BAND + 2][2], Cw[BAND + 2];
+#pragma unroll
+    for (int i = 0; i < BAND + 2; ++i) {
+      const int sr = o0 + i;  // score rows o0 .. o0 + BAND + 1
+      const uint32_t T0 = s_t[sr][k], T1 = s_t[sr][k + 1], T2 = s_t[sr][k + 2];
+      Cw[i] = T1;
+      H[i][0] = H[i][1] = M[i][0] = M[i][1] = 0;
+      if (__any_sync(0xffffffffu, T1 != 0)) {  // lanes 0 / 31 see the tile's zero words as T0 / T2
+        const uint32_t l0 = window_at<0, -1>(T0, T1, T2) & lm[0], l1 = window_at<1, -1>(T0, T1, T2) & lm[1];
+        const uint32_t r0 = window_at<0, 1>(T0, T1, T2) & rm[0], r1 = window_at<1, 1>(T0, T1, T2) & rm[1];
+        M[i][0] = __vmaxu2(l0, r0);
+        M[i][1] = __vmaxu2(l1, r1);
+        H[i][0] = __vimax3_u16x2(l0, r0, window_at<0, 0>(T0, T1, T2));
+        H[i][1] = __vimax3_u16x2(l1, r1, window_at<1, 0>(T0, T1, T2));
+      }
+      if (i >= 2) {  // output row o: score row sr - 1, rows above / below are entries i - 2 / i
+        const int o = o0 + i - 2, y = b + o;
+        const uint32_t cw = Cw[i - 1];
+        uint32_t keep_bytes = 0;
+        if (__any_sync(0xffffffffu, cw != 0)) {
+          const bool up = (((o < 32 ? up0 : up1) >> (o & 31)) & 1u) != 0, down = (((o < 32 ? dn0 : dn1) >> (o & 31)) & 1u) != 0;
+          uint32_t res[2];
+#pragma unroll
+          for (int P = 0; P < 2; ++P) {
+            const uint32_t nb = __vimax3_u16x2(up ? H[i - 2][P] : 0u, down ? H[i][P] : 0u, M[i - 1][P]) | 0x00FF00FFu;
+            const uint32_t c = prmt(cw, 0u, P == 0 ? 0x2404 : 0x3414);  // score << 8 of pixels (0, 2) / (1, 3)
+            res[P] = c - __vminu2(c, nb);                               // low byte 1 for a survivor, else the lane is 0
+          }
+          keep_bytes = prmt(res[0], res[1], 0x6240) * 0xFFu;
+        }
+        if (y < h && out_lane) *reinterpret_cast<uint32_t*>(map + (int64_t)y * L.pitch + xw) = cw & keep_bytes;
+      }
+    }
+    return;
+  }
   for (int base = 0; base < OH; base += (NT / 32) * rps) {
     const int orow = base + warp * rps + sub;
     const int y = b + orow;

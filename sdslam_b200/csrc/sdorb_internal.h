@@ -15,7 +15,9 @@
 // (60 rows and four warps per tile instead of 30 and two: 3 % fewer halo rows at the same 32 warps per SM.)
 // What is left of a level's width after the full tiles goes to one column of narrow tiles (16, 32 or 64 pixels scored).
 #define SDORB_FAST_TW 120
+#ifndef SDORB_FAST_TH
 #define SDORB_FAST_TH 60
+#endif
 #define SDORB_BLUR_TW 128
 #define SDORB_BLUR_TH 128
 
