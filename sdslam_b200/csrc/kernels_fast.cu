@@ -369,40 +369,19 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
     svalid[i] = (x >= SDORB_EDGE && x < vx1 ? 0x00FFu : 0u) | (x + 1 >= SDORB_EDGE && x + 1 < vx1 ? 0xFF00u : 0u);
   }
   uint16_t* const s_t16 = reinterpret_cast<uint16_t*>(&s_t[0][0]);
-  bool use_compass = true;  // warp-uniform
-  int dense_rows = 0;
-  for (int base = 0; base < SROWS; base += (NT / 32) * rpw) {
-    if (!NARROW && !use_compass) {
-      // dense path of a full tile: the warp's row is the same for all lanes, and both pair slots are scored in one block
-      const int sr = base + warp;
-      const int gy = b - 1 + sr;
-      if (sr < SROWS) {
-        uint32_t T0 = 0, T1 = 0;
-        if (gy >= SDORB_EDGE && gy < vy1) {
-          const uint32_t* const row = &s_h[0][sr][lane];
-          uint32_t r0[16], r1[16];
-          load_ring(row, r0, true);
-          load_ring(row + 32, r1, true);
-          const uint32_t v0 = ring_at<0, 0>(row), v1 = ring_at<0, 0>(row + 32);
-          T0 = score_word(score_pair(r0, v0, th_h, th_back)) & svalid[0];
-          T1 = score_word(score_pair(r1, v1, th_h, th_back)) & svalid[1];
-        }
-        s_t16[sr * (2 * TWORDS) + 2 + lane] = (uint16_t)T0;
-        s_t16[sr * (2 * TWORDS) + 2 + 32 + lane] = (uint16_t)T1;
-      }
-      continue;
-    }
+  const int sr_lo = max(SDORB_EDGE - (b - 1), 0), sr_hi = min(vy1 - (b - 1), SROWS);  // the scored rows inside the detectable area
+  int dense_rows = 0, base = 0;
+  // Steps with the compass test.  On corner-dense tiles the test never skips anything, so a warp of a full tile that needed
+  // both of its slots in two consecutive steps stops testing for the rest of the tile (scoring a pair is always correct).
+  for (; base < SROWS && (NARROW || dense_rows < 2); base += (NT / 32) * rpw) {
     bool all_needed = true;
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int sr = base + warp * rpw + srow[i];
-      const int gy = b - 1 + sr;
       const bool in_tile = sr < SROWS;
-      const bool live = in_tile && gy >= SDORB_EDGE && gy < vy1 && svalid[i] != 0u;
+      const bool live = sr >= sr_lo && sr < sr_hi && svalid[i] != 0u;
       uint32_t T = 0;
       if (__any_sync(0xffffffffu, live)) {
-        // On corner-dense tiles the compass test never skips anything, so a warp of a full tile that needed both of its
-        // slots in two consecutive steps stops testing for the rest of the tile (scoring a pair is always correct).
         bool needed;
         T = score_slot_tested(&s_h[0][min(sr, SROWS - 1)][sq[i]], live, needed, th_h, th_back);
         all_needed = all_needed && needed;
@@ -413,7 +392,23 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
       if (in_tile) s_t16[sr * (2 * TWORDS) + 2 + sq[i]] = (uint16_t)T;
     }
     dense_rows = all_needed ? dense_rows + 1 : 0;
-    use_compass = dense_rows < 2;
+  }
+  // Dense steps of a full tile: the warp's row is the same for all lanes, and both pair slots are scored in one block.
+  if (!NARROW) {
+    for (int sr = base + warp; sr < SROWS; sr += NT / 32) {
+      uint32_t T0 = 0, T1 = 0;
+      if (sr >= sr_lo && sr < sr_hi) {
+        const uint32_t* const row = &s_h[0][sr][lane];
+        uint32_t r0[16], r1[16];
+        load_ring(row, r0, true);
+        load_ring(row + 32, r1, true);
+        const uint32_t v0 = ring_at<0, 0>(row), v1 = ring_at<0, 0>(row + 32);
+        T0 = score_word(score_pair(r0, v0, th_h, th_back)) & svalid[0];
+        T1 = score_word(score_pair(r1, v1, th_h, th_back)) & svalid[1];
+      }
+      s_t16[sr * (2 * TWORDS) + 2 + lane] = (uint16_t)T0;
+      s_t16[sr * (2 * TWORDS) + 2 + 32 + lane] = (uint16_t)T1;
+    }
   }
   __syncthreads();
 
@@ -428,38 +423,46 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
     constexpr int BAND = OH / (NT / 32);
     static_assert(OH % (NT / 32) == 0, "bands of whole rows");
     const int o0 = warp * BAND;  // first output row of the band = score row o0 + 1
-    const uint32_t up0 = s_rowflags[0][0], up1 = s_rowflags[1][0], dn0 = s_rowflags[0][1], dn1 = s_rowflags[1][1];
-    uint32_t H[BAND + 2][2], M[BAND + 2][2], Cw[BAND + 2];
+    // Row flags of the band as bits 0 .. BAND-1.  (A second, flag-free copy of the loop below for bands inside one cell row made
+    // the kernel 7 % slower: 4200 instead of 3100 instructions of code, profiles/r2_define_probe.log.)
+    const uint64_t upw = ((uint64_t)s_rowflags[1][0] << 32) | s_rowflags[0][0], dnw = ((uint64_t)s_rowflags[1][1] << 32) | s_rowflags[0][1];
+    const uint32_t band_mask = (1u << BAND) - 1u, upb = (uint32_t)(upw >> o0) & band_mask, dnb = (uint32_t)(dnw >> o0) & band_mask;
+    uint8_t* mrow = map + (int64_t)(b + o0) * L.pitch + xw;
+    const int rows_left = h - (b + o0);  // output rows of the band that exist in the image
+    {
+      uint32_t H[BAND + 2][2], M[BAND + 2][2], Cw[BAND + 2];
 #pragma unroll
-    for (int i = 0; i < BAND + 2; ++i) {
-      const int sr = o0 + i;  // score rows o0 .. o0 + BAND + 1
-      const uint32_t T0 = s_t[sr][k], T1 = s_t[sr][k + 1], T2 = s_t[sr][k + 2];
-      Cw[i] = T1;
-      H[i][0] = H[i][1] = M[i][0] = M[i][1] = 0;
-      if (__any_sync(0xffffffffu, T1 != 0)) {  // lanes 0 / 31 see the tile's zero words as T0 / T2
-        const uint32_t l0 = window_at<0, -1>(T0, T1, T2) & lm[0], l1 = window_at<1, -1>(T0, T1, T2) & lm[1];
-        const uint32_t r0 = window_at<0, 1>(T0, T1, T2) & rm[0], r1 = window_at<1, 1>(T0, T1, T2) & rm[1];
-        M[i][0] = __vmaxu2(l0, r0);
-        M[i][1] = __vmaxu2(l1, r1);
-        H[i][0] = __vimax3_u16x2(l0, r0, window_at<0, 0>(T0, T1, T2));
-        H[i][1] = __vimax3_u16x2(l1, r1, window_at<1, 0>(T0, T1, T2));
-      }
-      if (i >= 2) {  // output row o: score row sr - 1, rows above / below are entries i - 2 / i
-        const int o = o0 + i - 2, y = b + o;
-        const uint32_t cw = Cw[i - 1];
-        uint32_t keep_bytes = 0;
-        if (__any_sync(0xffffffffu, cw != 0)) {
-          const bool up = (((o < 32 ? up0 : up1) >> (o & 31)) & 1u) != 0, down = (((o < 32 ? dn0 : dn1) >> (o & 31)) & 1u) != 0;
-          uint32_t res[2];
-#pragma unroll
-          for (int P = 0; P < 2; ++P) {
-            const uint32_t nb = __vimax3_u16x2(up ? H[i - 2][P] : 0u, down ? H[i][P] : 0u, M[i - 1][P]) | 0x00FF00FFu;
-            const uint32_t c = prmt(cw, 0u, P == 0 ? 0x2404 : 0x3414);  // score << 8 of pixels (0, 2) / (1, 3)
-            res[P] = c - __vminu2(c, nb);                               // low byte 1 for a survivor, else the lane is 0
-          }
-          keep_bytes = prmt(res[0], res[1], 0x6240) * 0xFFu;
+      for (int i = 0; i < BAND + 2; ++i) {
+        const int sr = o0 + i;  // score rows o0 .. o0 + BAND + 1
+        const uint32_t T0 = s_t[sr][k], T1 = s_t[sr][k + 1], T2 = s_t[sr][k + 2];
+        Cw[i] = T1;
+        H[i][0] = H[i][1] = M[i][0] = M[i][1] = 0;
+        if (__any_sync(0xffffffffu, T1 != 0)) {  // lanes 0 / 31 see the tile's zero words as T0 / T2
+          const uint32_t l0 = window_at<0, -1>(T0, T1, T2) & lm[0], l1 = window_at<1, -1>(T0, T1, T2) & lm[1];
+          const uint32_t r0 = window_at<0, 1>(T0, T1, T2) & rm[0], r1 = window_at<1, 1>(T0, T1, T2) & rm[1];
+          M[i][0] = __vmaxu2(l0, r0);
+          M[i][1] = __vmaxu2(l1, r1);
+          H[i][0] = __vimax3_u16x2(l0, r0, window_at<0, 0>(T0, T1, T2));
+          H[i][1] = __vimax3_u16x2(l1, r1, window_at<1, 0>(T0, T1, T2));
         }
-        if (y < h && out_lane) *reinterpret_cast<uint32_t*>(map + (int64_t)y * L.pitch + xw) = cw & keep_bytes;
+        if (i >= 2) {  // output row o0 + j: score row sr - 1, the rows above / below are entries i - 2 / i
+          const int j = i - 2;
+          const uint32_t cw = Cw[i - 1];
+          uint32_t keep_bytes = 0;
+          if (__any_sync(0xffffffffu, cw != 0)) {
+            const bool up = ((upb >> j) & 1u) != 0, down = ((dnb >> j) & 1u) != 0;
+            uint32_t res[2];
+#pragma unroll
+            for (int P = 0; P < 2; ++P) {
+              const uint32_t nb = __vimax3_u16x2(up ? H[i - 2][P] : 0u, down ? H[i][P] : 0u, M[i - 1][P]) | 0x00FF00FFu;
+              const uint32_t c = prmt(cw, 0u, P == 0 ? 0x2404 : 0x3414);  // score << 8 of pixels (0, 2) / (1, 3)
+              res[P] = c - __vminu2(c, nb);                               // low byte 1 for a survivor, else the lane is 0
+            }
+            keep_bytes = prmt(res[0], res[1], 0x6240) * 0xFFu;
+          }
+          if (j < rows_left && out_lane) *reinterpret_cast<uint32_t*>(mrow) = cw & keep_bytes;
+          mrow += L.pitch;
+        }
       }
     }
     return;
