@@ -424,7 +424,7 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
     static_assert(OH % (NT / 32) == 0, "bands of whole rows");
     const int o0 = warp * BAND;  // first output row of the band = score row o0 + 1
     // Row flags of the band as bits 0 .. BAND-1.  (A second, flag-free copy of the loop below for bands inside one cell row made
-    // the kernel 7 % slower: 4200 instead of 3100 instructions of code, profiles/r2_define_probe.log.)
+    // the kernel 7 % slower, and rolling the loop up did not make it faster: profiles/r2_define_probe.log.)
     const uint64_t upw = ((uint64_t)s_rowflags[1][0] << 32) | s_rowflags[0][0], dnw = ((uint64_t)s_rowflags[1][1] << 32) | s_rowflags[0][1];
     const uint32_t band_mask = (1u << BAND) - 1u, upb = (uint32_t)(upw >> o0) & band_mask, dnb = (uint32_t)(dnw >> o0) & band_mask;
     uint8_t* mrow = map + (int64_t)(b + o0) * L.pitch + xw;
