@@ -229,7 +229,7 @@ __device__ __forceinline__ int div_magic(int n, int d, uint32_t magic) {  // n /
 template <bool NARROW>
 __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, const BatchPlanes& p, const int level, const LevelGeom& L,
                                           const int tile, uint32_t (&s_h)[2][PROWS][HW], uint32_t (&s_t)[SROWS][TWORDS],
-                                          uint32_t (&s_rowflags)[2][2]) {
+                                          uint32_t (&s_rowflags)[2][2], uint32_t& s_any) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int frame = blockIdx.y;
   const int t = tile - (NARROW ? L.tile_base_fastn : L.tile_base_fast);
@@ -313,6 +313,7 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
     s_t[tid][0] = 0;
     s_t[tid][nw + 1] = 0;
   }
+  if (tid == NT - 1) s_any = 0;
   if (tid < 64) {  // which vertical neighbours of output row tid lie in the same cell (none for rows below the detectable area):
     const int y = b + tid;  // one bit per row, s_rowflags[row / 32][0] for the row above, [1] for the row below
     uint32_t f = 0;
@@ -371,6 +372,7 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
   uint16_t* const s_t16 = reinterpret_cast<uint16_t*>(&s_t[0][0]);
   const int sr_lo = max(SDORB_EDGE - (b - 1), 0), sr_hi = min(vy1 - (b - 1), SROWS);  // the scored rows inside the detectable area
   int dense_rows = 0, base = 0;
+  uint32_t any_score = 0;
   // Steps with the compass test.  On corner-dense tiles the test never skips anything, so a warp of a full tile that needed
   // both of its slots in two consecutive steps stops testing for the rest of the tile (scoring a pair is always correct).
   for (; base < SROWS && (NARROW || dense_rows < 2); base += (NT / 32) * rpw) {
@@ -389,27 +391,32 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
       } else {
         all_needed = false;
       }
+      any_score |= T;
       if (in_tile) s_t16[sr * (2 * TWORDS) + 2 + sq[i]] = (uint16_t)T;
     }
     dense_rows = all_needed ? dense_rows + 1 : 0;
   }
-  // Dense steps of a full tile: the warp's row is the same for all lanes, and both pair slots are scored in one block.
+  // Dense steps of a full tile: the warp's row is the same for all lanes, and both pair slots are scored in one block.  (The
+  // steps above have covered rows 0 .. 7 at least, so the rows left are at or below the first detectable row.)
   if (!NARROW) {
-    for (int sr = base + warp; sr < SROWS; sr += NT / 32) {
-      uint32_t T0 = 0, T1 = 0;
-      if (sr >= sr_lo && sr < sr_hi) {
-        const uint32_t* const row = &s_h[0][sr][lane];
-        uint32_t r0[16], r1[16];
-        load_ring(row, r0, true);
-        load_ring(row + 32, r1, true);
-        const uint32_t v0 = ring_at<0, 0>(row), v1 = ring_at<0, 0>(row + 32);
-        T0 = score_word(score_pair(r0, v0, th_h, th_back)) & svalid[0];
-        T1 = score_word(score_pair(r1, v1, th_h, th_back)) & svalid[1];
-      }
+    for (int sr = base + warp; sr < sr_hi; sr += NT / 32) {
+      const uint32_t* const row = &s_h[0][sr][lane];
+      uint32_t r0[16], r1[16];
+      load_ring(row, r0, true);
+      load_ring(row + 32, r1, true);
+      const uint32_t v0 = ring_at<0, 0>(row), v1 = ring_at<0, 0>(row + 32);
+      const uint32_t T0 = score_word(score_pair(r0, v0, th_h, th_back)) & svalid[0];
+      const uint32_t T1 = score_word(score_pair(r1, v1, th_h, th_back)) & svalid[1];
+      any_score |= T0 | T1;
       s_t16[sr * (2 * TWORDS) + 2 + lane] = (uint16_t)T0;
       s_t16[sr * (2 * TWORDS) + 2 + 32 + lane] = (uint16_t)T1;
     }
+    for (int sr = max(sr_hi, base) + warp; sr < SROWS; sr += NT / 32) {  // rows below the detectable area score 0
+      s_t16[sr * (2 * TWORDS) + 2 + lane] = 0;
+      s_t16[sr * (2 * TWORDS) + 2 + 32 + lane] = 0;
+    }
   }
+  if (__any_sync(0xffffffffu, any_score != 0u) && lane == 0) s_any = 1u;
   __syncthreads();
 
   // ---- phase N: cell-bounded strict non-max suppression on the score tile; the survivors' t bytes go to the map
@@ -429,37 +436,39 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
     const uint32_t band_mask = (1u << BAND) - 1u, upb = (uint32_t)(upw >> o0) & band_mask, dnb = (uint32_t)(dnw >> o0) & band_mask;
     uint8_t* mrow = map + (int64_t)(b + o0) * L.pitch + xw;
     const int rows_left = h - (b + o0);  // output rows of the band that exist in the image
+    if (s_any == 0u) {  // a tile without any corner (flat image region): the map is all zero
+#pragma unroll 1
+      for (int j = 0; j < BAND; ++j) {
+        if (j < rows_left && out_lane) *reinterpret_cast<uint32_t*>(mrow) = 0u;
+        mrow += L.pitch;
+      }
+      return;
+    }
     {
       uint32_t H[BAND + 2][2], M[BAND + 2][2], Cw[BAND + 2];
 #pragma unroll
       for (int i = 0; i < BAND + 2; ++i) {
-        const int sr = o0 + i;  // score rows o0 .. o0 + BAND + 1
+        const int sr = o0 + i;  // score rows o0 .. o0 + BAND + 1; lanes 0 / 31 see the tile's zero words as T0 / T2
         const uint32_t T0 = s_t[sr][k], T1 = s_t[sr][k + 1], T2 = s_t[sr][k + 2];
         Cw[i] = T1;
-        H[i][0] = H[i][1] = M[i][0] = M[i][1] = 0;
-        if (__any_sync(0xffffffffu, T1 != 0)) {  // lanes 0 / 31 see the tile's zero words as T0 / T2
-          const uint32_t l0 = window_at<0, -1>(T0, T1, T2) & lm[0], l1 = window_at<1, -1>(T0, T1, T2) & lm[1];
-          const uint32_t r0 = window_at<0, 1>(T0, T1, T2) & rm[0], r1 = window_at<1, 1>(T0, T1, T2) & rm[1];
-          M[i][0] = __vmaxu2(l0, r0);
-          M[i][1] = __vmaxu2(l1, r1);
-          H[i][0] = __vimax3_u16x2(l0, r0, window_at<0, 0>(T0, T1, T2));
-          H[i][1] = __vimax3_u16x2(l1, r1, window_at<1, 0>(T0, T1, T2));
-        }
+        const uint32_t l0 = window_at<0, -1>(T0, T1, T2) & lm[0], l1 = window_at<1, -1>(T0, T1, T2) & lm[1];
+        const uint32_t r0 = window_at<0, 1>(T0, T1, T2) & rm[0], r1 = window_at<1, 1>(T0, T1, T2) & rm[1];
+        M[i][0] = __vmaxu2(l0, r0);
+        M[i][1] = __vmaxu2(l1, r1);
+        H[i][0] = __vimax3_u16x2(l0, r0, window_at<0, 0>(T0, T1, T2));
+        H[i][1] = __vimax3_u16x2(l1, r1, window_at<1, 0>(T0, T1, T2));
         if (i >= 2) {  // output row o0 + j: score row sr - 1, the rows above / below are entries i - 2 / i
           const int j = i - 2;
           const uint32_t cw = Cw[i - 1];
-          uint32_t keep_bytes = 0;
-          if (__any_sync(0xffffffffu, cw != 0)) {
-            const bool up = ((upb >> j) & 1u) != 0, down = ((dnb >> j) & 1u) != 0;
-            uint32_t res[2];
+          const bool up = ((upb >> j) & 1u) != 0, down = ((dnb >> j) & 1u) != 0;
+          uint32_t res[2];
 #pragma unroll
-            for (int P = 0; P < 2; ++P) {
-              const uint32_t nb = __vimax3_u16x2(up ? H[i - 2][P] : 0u, down ? H[i][P] : 0u, M[i - 1][P]) | 0x00FF00FFu;
-              const uint32_t c = prmt(cw, 0u, P == 0 ? 0x2404 : 0x3414);  // score << 8 of pixels (0, 2) / (1, 3)
-              res[P] = c - __vminu2(c, nb);                               // low byte 1 for a survivor, else the lane is 0
-            }
-            keep_bytes = prmt(res[0], res[1], 0x6240) * 0xFFu;
+          for (int P = 0; P < 2; ++P) {
+            const uint32_t nb = __vimax3_u16x2(up ? H[i - 2][P] : 0u, down ? H[i][P] : 0u, M[i - 1][P]) | 0x00FF00FFu;
+            const uint32_t c = prmt(cw, 0u, P == 0 ? 0x2404 : 0x3414);  // score << 8 of pixels (0, 2) / (1, 3)
+            res[P] = c - __vminu2(c, nb);                               // low byte 1 for a survivor, else the lane is 0
           }
+          const uint32_t keep_bytes = prmt(res[0], res[1], 0x6240) * 0xFFu;
           if (j < rows_left && out_lane) *reinterpret_cast<uint32_t*>(mrow) = cw & keep_bytes;
           mrow += L.pitch;
         }
@@ -500,6 +509,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fast_tiles_kernel(const Frame
   __shared__ __align__(16) uint32_t s_t[SROWS][TWORDS];
   __shared__ uint32_t s_rowflags[2][2];
   __shared__ int s_level;
+  __shared__ uint32_t s_any;  // does the tile hold a non-zero score at all?
   pdl_enter();
   const bool narrow = (int)blockIdx.x >= n_full;  // CTA-uniform
   const int t = narrow ? (int)blockIdx.x - n_full : (int)blockIdx.x;
@@ -511,9 +521,9 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) fast_tiles_kernel(const Frame
   __syncthreads();
   const int level = s_level;
   if (narrow)
-    fast_tile<true>(geom, p, level, geom->lv[level], t, s_h, s_t, s_rowflags);
+    fast_tile<true>(geom, p, level, geom->lv[level], t, s_h, s_t, s_rowflags, s_any);
   else
-    fast_tile<false>(geom, p, level, geom->lv[level], t, s_h, s_t, s_rowflags);
+    fast_tile<false>(geom, p, level, geom->lv[level], t, s_h, s_t, s_rowflags, s_any);
 }
 
 void launch_fast_all(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlanes& p, int nframes, cudaStream_t s) {
