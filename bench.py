@@ -668,6 +668,16 @@ def run_ours(args):
                 alu = {"bound": "alu", "achieved": inst / avg_launch_s, "peak": alu_s, "unit": "warp-instructions/s", "frac": inst / avg_launch_s / alu_s,
                        "peak_per_clk_per_sm": alu_clk, "peak_source": "measured in this run (VIMNMX3.U16x2 probe, kernels_probe.cu)",
                        "alu_warp_inst_per_launch": inst, "instructions_source": "ncu smsp__inst_executed_pipe_alu.sum, profiles/traffic.json"}
+            if prof.get("warp_inst_per_launch") is not None and alu_clk > 0:
+                # the second limit of an instruction-bound kernel: issue slots, one warp-instruction per clock per SM sub-partition
+                # (4 / clk / SM); alu_s / alu_clk = SM clock x SMs as measured by the probe of this run.  An instruction with three
+                # register sources (VIMNMX3, HFMA2) takes two slots on this SM (profiles/r2_pipe_probe_fma.log), which the plain
+                # count below does not weigh.
+                winst = prof["warp_inst_per_launch"] / fpp * frames_per_launch
+                issue_peak = 4.0 * alu_s / alu_clk
+                alu["issue"] = {"achieved": winst / avg_launch_s, "peak": issue_peak, "unit": "warp-instructions/s",
+                                "frac": winst / avg_launch_s / issue_peak, "warp_inst_per_launch": winst,
+                                "instructions_source": "ncu smsp__inst_executed.sum, profiles/traffic.json"}
         except Exception:
             pass
         fps = frames_global * steps / (m["ms_total"] * 1e-3)

@@ -261,15 +261,18 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
   if (!NARROW) {
     static_assert(PROWS % (NT / 32) == 0 && 2 * PROWS <= 2 * NT, "staging loop shape");
     const int gx = a - 4 + 4 * lane;
-    const uint8_t* colp = src + gx + (int64_t)(b - 4 + warp) * pitch;
-    const bool col_ok = gx < w;
+    // word index of (row b - 4 + warp, column gx) in the plane (a plane is far below 2^31 bytes; pitch and gx are multiples of 4);
+    // rows [0, rows_ok) of the tile exist in the image -- none for a lane whose column lies beyond the row
+    const uint32_t* const plane = reinterpret_cast<const uint32_t*>(src);
+    int widx = ((b - 4 + warp) * pitch + gx) >> 2;
+    const int wstep = (NT / 32) * (pitch >> 2);
+    const int rows_ok = gx < w ? h - (b - 4) : 0;
     uint32_t v[PROWS / (NT / 32)];
 #pragma unroll
     for (int j = 0; j < PROWS / (NT / 32); ++j) {  // all loads of the thread in flight together
-      const int gy = b - 4 + warp + (NT / 32) * j;
       v[j] = 0;
-      if (col_ok && gy < h) v[j] = *reinterpret_cast<const uint32_t*>(colp);
-      colp += (NT / 32) * pitch;
+      if (warp + (NT / 32) * j < rows_ok) v[j] = plane[widx];
+      widx += wstep;
     }
 #pragma unroll
     for (int j = 0; j < PROWS / (NT / 32); ++j) {

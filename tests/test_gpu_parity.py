@@ -277,6 +277,37 @@ def test_zero_corner_images(ex_c1):
         assert d.shape == (len(ok), 32)
 
 
+def test_flat_and_corner_dense_regions_in_one_frame(ex_c1):
+    """The FAST kernel skips pair slots whose compass test fails, stops testing where every slot is needed, and writes the map
+    of a tile without any score straight away: a frame with flat halves / quadrants / stripes next to noise exercises all three
+    paths and their borders (tiles are 120 x 60 outputs, half rows of 64 pixels are the skip unit)."""
+    rng = np.random.default_rng(77)
+    noise = rng.integers(0, 256, (480, 752), dtype=np.uint8)
+    cases = []
+    a = np.full((480, 752), 128, np.uint8)
+    a[:, 376:] = noise[:, 376:]                      # right half noise
+    cases.append(a)
+    b = np.full((480, 752), 30, np.uint8)
+    b[240:, :] = noise[240:, :]                      # lower half noise
+    cases.append(b)
+    c = noise.copy()
+    c[100:380, 150:600] = 200                        # a flat window inside noise
+    cases.append(c)
+    d = np.full((480, 752), 90, np.uint8)
+    d[::97, :] = 255                                 # thin lines on a flat background
+    d[:, ::131] = 0
+    d[200:203, 300:303] = 255                        # and one isolated blob
+    cases.append(d)
+    e = np.full((480, 640), 128, np.uint8)
+    e[200:280, 250:390] = noise[200:280, 250:390]    # noise only in the middle tiles
+    cases.append(e)
+    for i, img in enumerate(cases):
+        k, dsc, _ = ex_c1(img)
+        ok, od = orc.Extractor(*C1).extract(img)
+        assert len(ok) > 0
+        assert_same(ok, od, k, dsc, "case %d" % i)
+
+
 def test_fewer_corners_than_quota():
     img = np.full((240, 320), 90, np.uint8)
     img[60:100, 80:140] = 200
