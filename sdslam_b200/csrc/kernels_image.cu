@@ -371,15 +371,24 @@ __device__ __forceinline__ void blur_hrow(const BlurLane& B, const uint32_t (&wi
   h[3] = __dp4a(w1, KA, __dp4a(w2, KB, 128u));
 }
 
-// Source row r (slot S = r mod 7) has arrived in H[S]: emit output row r - 6, whose rows r-6 .. r sit in slots S+1 .. S+7.
-template <int S>
-__device__ __forceinline__ uint32_t blur_vrow(const uint32_t (&H)[7][4]) {
+// The vertical filter works on ROW PAIRS: the horizontal sums of source rows 2j and 2j + 1 (16 bits each, the +128 included) share
+// one register per pixel, and IDP.2A multiplies such a pair with two of the seven weights at once.  Output row o needs source rows
+// o .. o + 6: an even o = 2m takes the pairs m .. m+3 with the weights (k0,k1) (k2,k3) (k4,k5) (k6,0), an odd o = 2m + 1 the same
+// pairs with (0,k0) (k1,k2) (k3,k4) (k5,k6) -- four IDP.2A per pixel instead of four IMAD + three IADD, and a window of four pair
+// slots instead of seven rows.  S = slot of the newest pair (j); the older pairs j-3, j-2, j-1 sit in slots S+1, S+2, S+3 (mod 4).
+template <int S, bool ODD>
+__device__ __forceinline__ uint32_t blur_vrow(const uint32_t (&P)[4][4]) {
+  constexpr uint32_t K0 = 18, K1 = 34, K2 = 48, K3 = 56;  // k = K0 K1 K2 K3 K2 K1 K0
+  // weights of the four pairs, two pairs per constant (low / high half-word: __dp2a_lo / __dp2a_hi)
+  constexpr uint32_t WA = ODD ? ((0u | K0 << 8) | (K1 | K2 << 8) << 16) : ((K0 | K1 << 8) | (K2 | K3 << 8) << 16);
+  constexpr uint32_t WB = ODD ? ((K3 | K2 << 8) | (K1 | K0 << 8) << 16) : ((K2 | K1 << 8) | (K0 | 0u << 8) << 16);
   uint32_t acc[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const uint32_t s3 = H[(S + 1) % 7][q] + H[S][q], s2 = H[(S + 2) % 7][q] + H[(S + 6) % 7][q];
-    const uint32_t s1 = H[(S + 3) % 7][q] + H[(S + 5) % 7][q];
-    acc[q] = 56u * H[(S + 4) % 7][q] + 48u * s1 + 34u * s2 + 18u * s3;  // includes 256 * 128 = 2^15
+    uint32_t v = __dp2a_lo(P[(S + 1) % 4][q], WA, 0u);
+    v = __dp2a_hi(P[(S + 2) % 4][q], WA, v);
+    v = __dp2a_lo(P[(S + 3) % 4][q], WB, v);
+    acc[q] = __dp2a_hi(P[S][q], WB, v);  // includes 256 * 128 = 2^15
   }
   // byte 2 of each accumulator is (v + 2^15) >> 16 (v < 2^24)
   return __byte_perm(__byte_perm(acc[0], acc[1], 0x0062), __byte_perm(acc[2], acc[3], 0x0062), 0x5410);
@@ -387,48 +396,42 @@ __device__ __forceinline__ uint32_t blur_vrow(const uint32_t (&H)[7][4]) {
 
 template <bool EDGE>
 __device__ __forceinline__ void blur_walk(const BlurLane& B, uint8_t* __restrict__ dst, const int dpitch, const int nout) {
-  uint32_t H[7][4];
-  uint32_t cur[3], nx1[3], nxt[3];  // loads run two rows ahead of the arithmetic
-  // source rows 0..5 of the strip fill the window; from row 6 on every source row completes one output row
-  blur_load_row(B, 0, cur);
-  blur_load_row(B, 1, nx1);
-#define SDORB_BLUR_FILL(S)          \
-  blur_load_row(B, S + 2, nxt);     \
-  blur_hrow<EDGE>(B, cur, H[S]);          \
-  cur[0] = nx1[0];                  \
-  cur[1] = nx1[1];                  \
-  cur[2] = nx1[2];                  \
-  nx1[0] = nxt[0];                  \
-  nx1[1] = nxt[1];                  \
-  nx1[2] = nxt[2];
-  SDORB_BLUR_FILL(0)
-  SDORB_BLUR_FILL(1)
-  SDORB_BLUR_FILL(2)
-  SDORB_BLUR_FILL(3)
-  SDORB_BLUR_FILL(4)
-  SDORB_BLUR_FILL(5)
-#undef SDORB_BLUR_FILL
-  // output row o + K from source row o + K + 6 (slot (K + 6) mod 7); rows past the strip are read clamped and not stored
-#define SDORB_BLUR_STEP(K)                                                                      \
-  blur_load_row(B, o + K + 8, nxt);                                                             \
-  blur_hrow<EDGE>(B, cur, H[(K + 6) % 7]);                                                            \
-  if (o + K < nout && B.ld1) *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)(o + K) * (uint32_t)dpitch)) = blur_vrow<(K + 6) % 7>(H); \
-  cur[0] = nx1[0];                                                                              \
-  cur[1] = nx1[1];                                                                              \
-  cur[2] = nx1[2];                                                                              \
-  nx1[0] = nxt[0];                                                                              \
-  nx1[1] = nxt[1];                                                                              \
-  nx1[2] = nxt[2];
-  for (int o = 0; o < nout; o += 7) {
+  uint32_t P[4][4];
+  uint32_t ra[3], rb[3], na[3], nb[3];  // the rows of the pair in work, and of the next pair (loads run one pair ahead)
+  blur_load_row(B, 0, ra);
+  blur_load_row(B, 1, rb);
+  // source rows R, R + 1 (already in ra / rb) become the pair in slot S; the rows R + 2, R + 3 are requested first
+#define SDORB_BLUR_PAIR(S, R)                                                   \
+  blur_load_row(B, (R) + 2, na);                                                \
+  blur_load_row(B, (R) + 3, nb);                                                \
+  {                                                                             \
+    uint32_t h0[4], h1[4];                                                      \
+    blur_hrow<EDGE>(B, ra, h0);                                                 \
+    blur_hrow<EDGE>(B, rb, h1);                                                 \
+    _Pragma("unroll") for (int q = 0; q < 4; ++q) P[S][q] = __byte_perm(h0[q], h1[q], 0x5410); \
+  }                                                                             \
+  ra[0] = na[0], ra[1] = na[1], ra[2] = na[2];                                  \
+  rb[0] = nb[0], rb[1] = nb[1], rb[2] = nb[2];
+  // source rows 0..5 of the strip fill three pair slots; from then on every pair completes two output rows
+  SDORB_BLUR_PAIR(0, 0)
+  SDORB_BLUR_PAIR(1, 2)
+  SDORB_BLUR_PAIR(2, 4)
+  // output rows o + 2K, o + 2K + 1 from the pair of source rows o + 2K + 6, o + 2K + 7 (slot (K + 3) mod 4); rows past the strip are
+  // read clamped and not stored
+#define SDORB_BLUR_STEP(K)                                                                                                          \
+  SDORB_BLUR_PAIR((K + 3) % 4, o + 2 * K + 6)                                                                                       \
+  if (o + 2 * K < nout && B.ld1)                                                                                                    \
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)(o + 2 * K) * (uint32_t)dpitch)) = blur_vrow<(K + 3) % 4, false>(P);     \
+  if (o + 2 * K + 1 < nout && B.ld1)                                                                                                \
+    *reinterpret_cast<uint32_t*>(dst + (uint64_t)((uint32_t)(o + 2 * K + 1) * (uint32_t)dpitch)) = blur_vrow<(K + 3) % 4, true>(P);
+  for (int o = 0; o < nout; o += 8) {
     SDORB_BLUR_STEP(0)
     SDORB_BLUR_STEP(1)
     SDORB_BLUR_STEP(2)
     SDORB_BLUR_STEP(3)
-    SDORB_BLUR_STEP(4)
-    SDORB_BLUR_STEP(5)
-    SDORB_BLUR_STEP(6)
   }
 #undef SDORB_BLUR_STEP
+#undef SDORB_BLUR_PAIR
 }
 
 __global__ void __launch_bounds__(B_WARPS * 32, 5) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, BlurTileBases tb) {

@@ -141,7 +141,8 @@ struct sdorb_handle {
   int pipe_const = 0;        // > 0: passes of this many frames after the first (SDORB_PIPE_CONST) instead of the geometric ramp
   sdorb_handle* twin = nullptr;
   bool is_twin = false;
-  bool overlap = false;  // measured: +0.5 % at best (every kernel here is issue-bound, so co-residency buys nothing); SDORB_OVERLAP=1 enables it
+  int overlap = 0;  // SDORB_OVERLAP: 1 = blur on a second stream beside FAST (measured: +0.5 % at best, both are issue-bound),
+                    // 2 = beside gather + select (latency-bound, half of the issue slots idle)
   // geometry of the current image size
   int gw = 0, gh = 0;
   FrameGeom geom{};
@@ -415,13 +416,18 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
   }
   // The blur only needs the pyramid, FAST + selection only the pyramid too: the blur (byte dot products, FMA pipe) runs
   // on a second stream beside FAST (min / max, ALU pipe) and joins before the descriptors.
-  const bool fork = h->overlap;
-  if (fork) {
+  const bool fork = h->overlap != 0;
+  auto fork_blur = [&]() -> int {
     CU(cudaEventRecord(h->ev_fork, s));
     CU(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
     StageScope st(h, h->s_aux, SDORB_STAGE_BLUR);
     launch_blur_all(h->d_geom, g, planes, n, h->s_aux);
     st.launched();
+    return SDORB_OK;
+  };
+  if (h->overlap == 1) {
+    const int rc = fork_blur();
+    if (rc) return rc;
   }
   {
     StageScope st(h, s, SDORB_STAGE_FAST);
@@ -430,10 +436,21 @@ int enqueue_pass(sdorb_handle* h, BatchPlanes planes, int n, sdorb_keypoint* d_k
       st.launched();  // full tiles and the narrow last-column tiles in one grid
     }
   }
+  if (h->overlap == 2) {
+    const int rc = fork_blur();
+    if (rc) return rc;
+  }
+  if (h->overlap == 3) CU(cudaEventRecord(h->ev_fork, s));  // the blur is launched behind gather + select but waits for FAST only
   {
     StageScope st(h, s, SDORB_STAGE_SELECT);
     launch_select(h->d_geom, g, planes, sb, n, s);
     st.launched(g.cells_total > 0 ? 2 : 1);  // gather_cells_kernel + select_kernel
+  }
+  if (h->overlap == 3) {
+    CU(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
+    StageScope st(h, h->s_aux, SDORB_STAGE_BLUR);
+    launch_blur_all(h->d_geom, g, planes, n, h->s_aux);
+    st.launched();
   }
   if (fork) {
     CU(cudaEventRecord(h->ev_join, h->s_aux));
@@ -529,7 +546,7 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (const char* e = getenv("SDORB_GRAPH")) h->use_graph = e[0] != '0';
   if (const char* e = getenv("SDORB_PYRAMID_TAIL")) h->fuse_pyramid_tail = e[0] != '0';
   if (const char* e = getenv("SDORB_PDL_MAX_FRAMES")) h->pdl_max_frames = std::max(atoi(e), 0);
-  if (const char* e = getenv("SDORB_OVERLAP")) h->overlap = e[0] != '0';
+  if (const char* e = getenv("SDORB_OVERLAP")) h->overlap = atoi(e);
   if (const char* e = getenv("SDORB_PIPE_TAPER")) h->pipe_taper = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_GROWTH")) h->pipe_growth_pct = std::min(std::max(atoi(e), 101), 1000);
   if (const char* e = getenv("SDORB_PIPE_DUAL")) h->pipe_dual = e[0] != '0';
