@@ -266,7 +266,10 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
     const uint32_t* const plane = reinterpret_cast<const uint32_t*>(src);
     int widx = ((b - 4 + warp) * pitch + gx) >> 2;
     const int wstep = (NT / 32) * (pitch >> 2);
-    const int rows_ok = gx < w ? h - (b - 4) : 0;
+    // Only the staged rows that a scored row inside the detectable area reads are needed (the last tile row of a level is
+    // rarely full): rows [0, rows_used); they all exist in the image (det_y1 + 3 <= h).
+    const int rows_used = min(L.det_y1 - (b - 1), SROWS) + 6;
+    const int rows_ok = gx < w ? rows_used : 0;
     uint32_t v[PROWS / (NT / 32)];
 #pragma unroll
     for (int j = 0; j < PROWS / (NT / 32); ++j) {  // all loads of the thread in flight together
@@ -276,8 +279,10 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
     }
 #pragma unroll
     for (int j = 0; j < PROWS / (NT / 32); ++j) {
-      const uint32_t hi = pair23(v[j]);
-      stage_word(s_h, warp + (NT / 32) * j, lane, v[j], hi, __shfl_up_sync(0xffffffffu, hi, 1));
+      if (warp + (NT / 32) * j < rows_used) {  // warp-uniform
+        const uint32_t hi = pair23(v[j]);
+        stage_word(s_h, warp + (NT / 32) * j, lane, v[j], hi, __shfl_up_sync(0xffffffffu, hi, 1));
+      }
     }
     for (int i = tid; i < 2 * PROWS; i += NT) {  // the two words to the right of the 32 (words 32, 33 of each row)
       const int r = i >> 1, kk = 32 + (i & 1);
@@ -438,7 +443,7 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
     const uint64_t upw = ((uint64_t)s_rowflags[1][0] << 32) | s_rowflags[0][0], dnw = ((uint64_t)s_rowflags[1][1] << 32) | s_rowflags[0][1];
     const uint32_t band_mask = (1u << BAND) - 1u, upb = (uint32_t)(upw >> o0) & band_mask, dnb = (uint32_t)(dnw >> o0) & band_mask;
     uint8_t* mrow = map + (int64_t)(b + o0) * L.pitch + xw;
-    const int rows_left = h - (b + o0);  // output rows of the band that exist in the image
+    const int rows_left = L.det_y1 - (b + o0);  // output rows of the band inside the detectable area (nobody reads the map below it)
     if (s_any == 0u) {  // a tile without any corner (flat image region): the map is all zero
 #pragma unroll 1
       for (int j = 0; j < BAND; ++j) {
@@ -462,6 +467,7 @@ __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, co
         H[i][1] = __vimax3_u16x2(l1, r1, window_at<1, 0>(T0, T1, T2));
         if (i >= 2) {  // output row o0 + j: score row sr - 1, the rows above / below are entries i - 2 / i
           const int j = i - 2;
+          if (j >= rows_left) break;  // warp-uniform: the rest of the band lies below the detectable area
           const uint32_t cw = Cw[i - 1];
           const bool up = ((upb >> j) & 1u) != 0, down = ((dnb >> j) & 1u) != 0;
           uint32_t res[2];

@@ -434,7 +434,10 @@ __device__ __forceinline__ void blur_walk(const BlurLane& B, uint8_t* __restrict
 #undef SDORB_BLUR_PAIR
 }
 
-__global__ void __launch_bounds__(B_WARPS * 32, 5) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, BlurTileBases tb) {
+#ifndef SDORB_BLUR_MIN_CTAS
+#define SDORB_BLUR_MIN_CTAS 5
+#endif
+__global__ void __launch_bounds__(B_WARPS * 32, SDORB_BLUR_MIN_CTAS) blur_all_kernel(const FrameGeom* __restrict__ geom, BatchPlanes p, BlurTileBases tb) {
   pdl_enter();
   const int lane = threadIdx.x & 31;
   const int tile = blockIdx.x * B_WARPS + (threadIdx.x >> 5);
