@@ -134,7 +134,8 @@ struct sdorb_handle {
   int in_slots = 3;  // measured on B200: 2 -> 3 slots +2.1 % end to end (138.4 k -> 141.3 k frames/s), a fourth adds nothing
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // the blur runs beside FAST + selection on s_aux
   bool pipe_taper = false;   // host pipeline: shrink the last passes (SDORB_PIPE_TAPER=1; measured: -1.5 %)
-  int pipe_growth_pct = 125; // ... and grow the first ones by this factor (SDORB_PIPE_GROWTH, percent)
+  int pipe_min = 0;           // first pass of the host pipeline in frames (0: max_batch / 8; SDORB_PIPE_MIN)
+  int pipe_growth_pct = 112; // ... and grow the first ones by this factor (SDORB_PIPE_GROWTH, percent)
   // host pipeline, two compute lanes: odd passes run on a twin handle (own scratch arena, own stream) so that the tail of pass p
   // (partial last waves of its 13 launches, the small upper pyramid levels) is filled by the start of pass p+1.  SDORB_PIPE_DUAL
   bool pipe_dual = false;
@@ -551,6 +552,7 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (const char* e = getenv("SDORB_PIPE_GROWTH")) h->pipe_growth_pct = std::min(std::max(atoi(e), 101), 1000);
   if (const char* e = getenv("SDORB_PIPE_DUAL")) h->pipe_dual = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_CONST")) h->pipe_const = std::max(atoi(e), 0);
+  if (const char* e = getenv("SDORB_PIPE_MIN")) h->pipe_min = std::max(atoi(e), 0);
   if (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (const char* e = getenv("SDORB_PIPE_SLOTS")) h->in_slots = std::min(std::max(atoi(e), 2), (int)sdorb_handle::kMaxInSlots);
@@ -769,10 +771,11 @@ int sdorb_extract_batch_pyr(sdorb_handle* h, const uint8_t* images, int nframes,
   }
 
   // host path: three-stream pipeline over passes of up to max_batch frames.  Only the first upload and the last
-  // download are exposed, so the passes start at max_batch / 8.  A pass can only start once it is uploaded completely, and
-  // PCIe delivers frames only a little faster than the kernels consume them (5.6 vs 7 us per 640x480 frame), so the passes
-  // grow by that ratio (1.25): the upload of pass p+1 then ends when pass p does.  Doubling stalled the kernels for 2 ms per
-  // 4096-frame call; tapering the last passes costs more in small-pass efficiency than the shorter last download saves.
+  // download are exposed, so the passes start at max_batch / 8.  A pass can only start once it is uploaded completely, and on
+  // this platform PCIe delivers 640x480 frames about as fast as the kernels consume them (5.65 vs 5.5 us per frame; 5.6 vs 7 us
+  // before the kernels of round 2), so the passes grow slowly: by 1.12 per pass (measured best of 1.05 ... 1.25 and of constant
+  // pass sizes, profiles/r2_e2e_schedule_probe.log: 153.9 k frames/s against 144.5 k at 1.25).  Doubling stalled the kernels for
+  // 2 ms per 4096-frame call; tapering the last passes costs more in small-pass efficiency than the shorter last download saves.
   rc = ensure_host_staging(h, capacity);
   if (rc) return rc;
   // Any failure after the first enqueue leaves copies into / out of the caller's buffers in flight on three (four) streams:
@@ -803,7 +806,7 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
   if (pyramid && !h->d_pyr_out[0])
     for (int i = 0; i < 2; ++i) CU(sd_malloc(&h->d_pyr_out[i], (size_t)pyr_frame * B + 256));
   int pass = 0;
-  const int n_min = std::max(B / 8, 1);
+  const int n_min = h->pipe_min > 0 ? std::min(h->pipe_min, B) : std::max(B / 8, 1);
   int ramp = n_min;
   // two compute lanes (see pipe_dual): staging slot 1 belongs to the twin's scratch arena and stream
   const bool dual = h->pipe_dual && !h->is_twin && nframes > n_min;
