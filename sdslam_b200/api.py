@@ -238,7 +238,11 @@ class ORBextractor:
             lib().sdorb_destroy(self._h)
             self._h = C.c_void_p()
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except TypeError:  # interpreter shutdown: the module globals are gone, and so is the process
+            pass
 
     def _check(self, rc):
         if rc != 0:

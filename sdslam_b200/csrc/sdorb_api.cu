@@ -134,6 +134,7 @@ struct sdorb_handle {
   int in_slots = 3;  // measured on B200: 2 -> 3 slots +2.1 % end to end (138.4 k -> 141.3 k frames/s), a fourth adds nothing
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // the blur runs beside FAST + selection on s_aux
   bool pipe_taper = false;   // host pipeline: shrink the last passes (SDORB_PIPE_TAPER=1; measured: -1.5 %)
+  bool pipe_trace = false;    // SDORB_PIPE_TRACE=1: timed events around every upload / pass / download of a host batch, printed to stderr
   int pipe_min = 0;           // first pass of the host pipeline in frames (0: max_batch / 8; SDORB_PIPE_MIN)
   int pipe_growth_pct = 112; // ... and grow the first ones by this factor (SDORB_PIPE_GROWTH, percent)
   // host pipeline, two compute lanes: odd passes run on a twin handle (own scratch arena, own stream) so that the tail of pass p
@@ -553,6 +554,7 @@ int sdorb_create(const sdorb_params* params, sdorb_handle** out) {
   if (const char* e = getenv("SDORB_PIPE_DUAL")) h->pipe_dual = e[0] != '0';
   if (const char* e = getenv("SDORB_PIPE_CONST")) h->pipe_const = std::max(atoi(e), 0);
   if (const char* e = getenv("SDORB_PIPE_MIN")) h->pipe_min = std::max(atoi(e), 0);
+  if (const char* e = getenv("SDORB_PIPE_TRACE")) h->pipe_trace = e[0] != '0';
   if (cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking) != cudaSuccess) return fail(SDORB_ERR_CUDA);
   if (const char* e = getenv("SDORB_PIPE_SLOTS")) h->in_slots = std::min(std::max(atoi(e), 2), (int)sdorb_handle::kMaxInSlots);
@@ -805,6 +807,17 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
   pyramid_layout(h->geom, pyr_off, &pyr_frame);
   if (pyramid && !h->d_pyr_out[0])
     for (int i = 0; i < 2; ++i) CU(sd_malloc(&h->d_pyr_out[i], (size_t)pyr_frame * B + 256));
+  // opt-in timeline (debugging aid): six timed events per pass, all relative to the start of the first upload
+  struct PassTrace {
+    int n;
+    cudaEvent_t e[6];  // upload begin / end, kernels begin / end, download begin / end
+  };
+  std::vector<PassTrace> trace;
+  auto mark = [&](int which, cudaStream_t st) {
+    if (!h->pipe_trace) return;
+    cudaEventCreate(&trace.back().e[which]);
+    cudaEventRecord(trace.back().e[which], st);
+  };
   int pass = 0;
   const int n_min = h->pipe_min > 0 ? std::min(h->pipe_min, B) : std::max(B / 8, 1);
   int ramp = n_min;
@@ -832,6 +845,8 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
     cudaStream_t cs = hc->s_compute;
     const int si = pass % h->in_slots;  // input staging slot: free again once the pass that last used it has run its kernels
     if (pass >= h->in_slots) CU(cudaStreamWaitEvent(h->s_in, h->ev_in_free[si], 0));
+    if (h->pipe_trace) trace.push_back(PassTrace{n, {}});
+    mark(0, h->s_in);
     const bool tight = frame_stride == row_stride * (size_t)height && row_stride == (size_t)width && width % 16 == 0;
     if (tight) {
       // contiguous host frames whose rows stay 16-byte aligned: one linear copy, and the kernels read level 0 with the image
@@ -847,9 +862,11 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
                              images + (size_t)(f0 + f) * frame_stride, row_stride, width, height, cudaMemcpyHostToDevice,
                              h->s_in));
     }
+    mark(1, h->s_in);
     CU(cudaEventRecord(h->ev_in[si], h->s_in));
     CU(cudaStreamWaitEvent(cs, h->ev_in[si], 0));
     if (pass >= 2) CU(cudaStreamWaitEvent(cs, h->ev_out[slot], 0));
+    mark(2, cs);
     BatchPlanes pl{};
     pl.img0 = h->d_stage_in[si];
     pl.img0_frame_stride = tight ? (int64_t)frame_stride : L0.plane_bytes;
@@ -874,18 +891,32 @@ int host_pipeline(sdorb_handle* h, const uint8_t* images, int nframes, int width
                              (size_t)pyr_frame - skip, (size_t)n, cudaMemcpyDeviceToHost, h->s_out));
       }
     }
+    mark(3, cs);
     CU(cudaEventRecord(h->ev_compute[slot], cs));
     CU(cudaEventRecord(h->ev_in_free[si], cs));
     CU(cudaStreamWaitEvent(h->s_out, h->ev_compute[slot], 0));
+    mark(4, h->s_out);
     CU(cudaMemcpyAsync(keypoints + (size_t)f0 * capacity, h->d_kps[slot], sizeof(sdorb_keypoint) * (size_t)capacity * n,
                        cudaMemcpyDeviceToHost, h->s_out));
     CU(cudaMemcpyAsync(descriptors + (size_t)f0 * capacity * 32, h->d_desc[slot], (size_t)32 * capacity * n,
                        cudaMemcpyDeviceToHost, h->s_out));
     CU(cudaMemcpyAsync(counts + f0, h->d_counts[slot], sizeof(int32_t) * n, cudaMemcpyDeviceToHost, h->s_out));
+    mark(5, h->s_out);
     CU(cudaEventRecord(h->ev_out[slot], h->s_out));
   }
   CU(cudaStreamSynchronize(h->s_out));
   CU(cudaStreamSynchronize(h->s_compute));
+  if (h->pipe_trace && !trace.empty()) {
+    fprintf(stderr, "sdorb host pipeline: %d frames in %zu passes; ms since the first upload began\n", nframes, trace.size());
+    fprintf(stderr, "  pass frames   upload          kernels         download\n");
+    for (size_t i = 0; i < trace.size(); ++i) {
+      float t[6] = {0, 0, 0, 0, 0, 0};
+      for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&t[k], trace[0].e[0], trace[i].e[k]);
+      fprintf(stderr, "  %4zu %6d   %6.2f-%6.2f   %6.2f-%6.2f   %6.2f-%6.2f\n", i, trace[i].n, t[0], t[1], t[2], t[3], t[4], t[5]);
+    }
+    for (auto& p : trace)
+      for (int k = 0; k < 6; ++k) cudaEventDestroy(p.e[k]);
+  }
   if (dual) {
     CU(cudaStreamSynchronize(h->twin->s_compute));
     h->launches += h->twin->launches;
