@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(OCT_THREADS) octree_kernel(const FrameGeom* __
   __shared__ int s_warp_sums[OCT_THREADS / 32];
   __shared__ int s_nalive, s_ncand, s_finish, s_sorted, s_total;
 
-  const int level = blockIdx.x, frame = blockIdx.y;
+  const int level = blockIdx.y, frame = blockIdx.x;  // level-major grid: the longest CTAs first
   const LevelGeom& L = geom->lv[level];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_cells = (L.cols > 0 && L.rows > 0) ? L.cols * L.rows : 0;
@@ -284,7 +284,7 @@ static size_t octree_smem_bytes(int mc, int mn) {
 void launch_octree(const FrameGeom* d_geom, const FrameGeom& g, const SelectBuffers& b, int nframes, cudaStream_t s) {
   int mc, mn;
   octree_caps(g, &mc, &mn);
-  launch_pdl(octree_kernel, dim3(g.nlevels, nframes), dim3(OCT_THREADS), octree_smem_bytes(mc, mn), s, d_geom, b, mc, mn);
+  launch_pdl(octree_kernel, dim3(nframes, g.nlevels), dim3(OCT_THREADS), octree_smem_bytes(mc, mn), s, d_geom, b, mc, mn);
 }
 
 int configure_octree_kernel() {

@@ -27,9 +27,13 @@
 
 namespace sdorb {
 
-// select_kernel comes in two shapes: 4 warps per (level, frame) CTA for batches (many CTAs: throughput), 16 warps for a handful
-// of frames (the single-frame call of Frame.cc:195: 8 CTAs in all, so the cells of a level are trimmed 16 at a time)
-constexpr int SEL_WARPS_BATCH = 4, SEL_WARPS_FEW = 16, SEL_FEW_FRAMES = 8;
+// select_kernel comes in three shapes: 4 warps per (level, frame) CTA for batches (many CTAs: throughput), 16 warps for a handful
+// of frames (the single-frame call of Frame.cc:195: 8 CTAs in all, so the cells of a level are trimmed 16 at a time), 8 warps for
+// the small first passes of the host pipeline (measured: 96-frame passes 6.8 -> 5.2 ms per 4096 frames, 256-frame passes 3.9 -> 4.3)
+constexpr int SEL_WARPS_BATCH = 4, SEL_WARPS_MID = 8, SEL_WARPS_FEW = 16, SEL_FEW_FRAMES = 8;
+#ifndef SDORB_SEL_MID_FRAMES
+#define SDORB_SEL_MID_FRAMES 128  // passes up to this many frames take 8 warps per CTA: their time is the longest CTA's, not the sum
+#endif
 constexpr int SEL_WORK_CAP = 1024;  // entries of per-warp shared scratch; larger lists fall back to global memory + one lane
 
 // std::nth_element(a + first, a + nth, a + last, response >) by one warp; indices must stay below 65536.
@@ -259,7 +263,8 @@ __global__ void __launch_bounds__(SEL_WARPS * 32) select_kernel(const FrameGeom*
   uint16_t* idx_scratch = reinterpret_cast<uint16_t*>(work + SEL_WARPS * SEL_WORK_CAP);
   __shared__ int s_total;
 
-  const int level = blockIdx.x, frame = blockIdx.y;
+  // level-major grid: the CTAs of level 0 (the longest lists) are dispatched first, the short top levels fill the tail
+  const int level = blockIdx.y, frame = blockIdx.x;
   const LevelGeom& L = geom->lv[level];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n_cells = (L.cols > 0 && L.rows > 0) ? L.cols * L.rows : 0;
@@ -407,10 +412,13 @@ void launch_select(const FrameGeom* d_geom, const FrameGeom& g, const BatchPlane
     return;
   }
   if (nframes <= SEL_FEW_FRAMES && select_smem_bytes_w(g, SEL_WARPS_FEW) <= 200 * 1024)
-    launch_pdl(select_kernel<SEL_WARPS_FEW>, dim3(g.nlevels, nframes), dim3(SEL_WARPS_FEW * 32), select_smem_bytes_w(g, SEL_WARPS_FEW), s,
+    launch_pdl(select_kernel<SEL_WARPS_FEW>, dim3(nframes, g.nlevels), dim3(SEL_WARPS_FEW * 32), select_smem_bytes_w(g, SEL_WARPS_FEW), s,
+               d_geom, b, mc, lc);
+  else if (nframes <= SDORB_SEL_MID_FRAMES && select_smem_bytes_w(g, SEL_WARPS_MID) <= 200 * 1024)
+    launch_pdl(select_kernel<SEL_WARPS_MID>, dim3(nframes, g.nlevels), dim3(SEL_WARPS_MID * 32), select_smem_bytes_w(g, SEL_WARPS_MID), s,
                d_geom, b, mc, lc);
   else
-    launch_pdl(select_kernel<SEL_WARPS_BATCH>, dim3(g.nlevels, nframes), dim3(SEL_WARPS_BATCH * 32), select_smem_bytes_w(g, SEL_WARPS_BATCH), s,
+    launch_pdl(select_kernel<SEL_WARPS_BATCH>, dim3(nframes, g.nlevels), dim3(SEL_WARPS_BATCH * 32), select_smem_bytes_w(g, SEL_WARPS_BATCH), s,
                d_geom, b, mc, lc);
 }
 
@@ -435,6 +443,7 @@ void launch_debug_nth_element(uint32_t* d_entries, int n, int nth, cudaStream_t 
 
 int configure_kernels() {
   cudaError_t e = cudaFuncSetAttribute(select_kernel<SEL_WARPS_BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(select_kernel<SEL_WARPS_MID>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(select_kernel<SEL_WARPS_FEW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   return (int)e;
 }
