@@ -25,9 +25,13 @@
 //     issue slots on this SM, which is why moving MORE of the network to the FMA pipe does not pay (same log);
 //   * 64 three-input min / max equivalents per pixel pair (the arcs j-1 and j share eight pixels, see score_pair);
 //   * a lane owns the pairs q and q + 32 of a 128-pixel row (conflict-free LDS), scores are kept as t = max(score + 1 - th, 0)
-//     in one byte per pixel in a second tile; the 3x3 strict non-max test runs on that tile word-wise (neighbour windows
-//     with junk low bytes against a centre with a zero low byte, see nms_pair) with per-column / per-row cell-boundary masks;
-//   * survivors are written back as map words (coalesced 120-byte row segments).
+//     in one byte per pixel in a second tile;
+//   * the 3x3 strict non-max test runs on that tile in bands: a warp walks 15 consecutive output rows, H(row) = max of a row's
+//     three columns serves the rows above and below it, M(row) = max of its left and right columns the row itself (neighbour
+//     windows with junk low bytes against a centre with a zero low byte, per-column / per-row cell-boundary masks); the narrow
+//     tiles of the last tile column keep the per-row form (nms_pair); a tile without any score writes zeros straight away;
+//   * survivors are written back as map words (coalesced 120-byte row segments); rows below the detectable area are neither
+//     staged nor written (nobody reads the map there).
 // A compass test on the same fp16 lanes (a 9-arc contains one of ring {0, 8} and one of ring {4, 12}) is kept only to skip
 // 64-pixel half rows in which no pixel can be a corner (flat image regions).  The kernel is bound by instruction issue and
 // the integer ALU pipe, not by HBM: see DESIGN.md.
@@ -46,7 +50,7 @@ constexpr int HW = 2 * PWORDS;                         // words per row of one f
 constexpr int TWORDS = SWORDS + 2;                     // score tile pitch in words (one zero word on each side)
 constexpr int NT = 128;
 static_assert(OH <= 64, "row flags are two 32-bit ballots");
-constexpr int SMEM_BYTES = 4 * (2 * PROWS * HW + SROWS * TWORDS + 4 + 1);  // the two pixel copies, the score tile, row flags, level
+constexpr int SMEM_BYTES = 4 * (2 * PROWS * HW + SROWS * TWORDS + 4 + 2);  // the two pixel copies, the score tile, row flags, level + flag
 constexpr int CTAS_BY_SMEM = 232448 / (SMEM_BYTES + 1024);                 // 227 KB per SM, 1 KB reserved per CTA
 constexpr int CTAS_PER_SM = CTAS_BY_SMEM < 7 ? CTAS_BY_SMEM : 7;           // 7 x 128 threads x 72 registers fit the register file
 
