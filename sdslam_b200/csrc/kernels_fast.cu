@@ -229,7 +229,7 @@ __device__ __forceinline__ int div_magic(int n, int d, uint32_t magic) {  // n /
 }
 
 // One tile.  NARROW = false: 32 scored words per row, one warp per row (all index arithmetic folds to constants).
-// NARROW = true: the last tile column of a level, fast_last_words (4, 8 or 16) words per row, 32 / nw rows per warp step.
+// NARROW = true: the last tile column of a level, fastn_words (4, 8 or 16) words per row, several rows per warp step.
 template <bool NARROW>
 __device__ __forceinline__ void fast_tile(const FrameGeom* __restrict__ geom, const BatchPlanes& p, const int level, const LevelGeom& L,
                                           const int tile, uint32_t (&s_h)[2][PROWS][HW], uint32_t (&s_t)[SROWS][TWORDS],
