@@ -190,11 +190,13 @@ __device__ int scan_cell(const uint8_t* __restrict__ map, int pitch, const CellR
                      b2 = __ballot_sync(0xffffffffu, c & 4), b3 = __ballot_sync(0xffffffffu, c & 8);
       if (b0 | b1 | b2 | b3) {
         int idx = count + __popc(b0 & lt) + 2 * __popc(b1 & lt) + 4 * __popc(b2 & lt) + 8 * __popc(b3 & lt);
+        // SDORB_ENTRY(y, x + q, t + th - 1) = the segment's entry + (q << 8) + t: the fields cannot carry into each other
+        const uint32_t ebase = ((uint32_t)ys[u] << 20) + ((uint32_t)xs[u] << 8) + (uint32_t)(th - 1);
         for (uint32_t m = m16; m; m &= m - 1, ++idx) {
           const int q = __ffs(m) - 1;
           const uint32_t lo8 = __byte_perm(wv[0], wv[1], q & 7), hi8 = __byte_perm(wv[2], wv[3], q & 7);
           const uint32_t t = ((q & 8) ? hi8 : lo8) & 0xFFu;
-          if (idx < cap) dst[idx] = SDORB_ENTRY(ys[u], xs[u] + q, (int)t + th - 1);
+          if (idx < cap) dst[idx] = ebase + ((uint32_t)q << 8) + t;
         }
         count += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2) + 8 * __popc(b3);
       }
