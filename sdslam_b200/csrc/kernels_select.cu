@@ -178,8 +178,8 @@ __device__ int scan_cell(const uint8_t* __restrict__ map, int pitch, const CellR
       uint32_t m16 = 0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t nz = ((((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wv[j]) >> 7) & 0x01010101u;
-        m16 |= ((nz * 0x10204080u) >> 28) << (4 * j);
+        const uint32_t msb = (((wv[j] & 0x7f7f7f7fu) + 0x7f7f7f7fu) | wv[j]) & 0x80808080u;  // bit 7 of a byte: the byte is not 0
+        m16 |= ((msb * 0x00204081u) >> 28) << (4 * j);                                        // bits 7, 15, 23, 31 -> 28 .. 31
       }
       // pixels outside [x0, x1) belong to the neighbouring cells
       const int lo = min(max(r.x0 - xs[u], 0), 16), hi = min(max(r.x1 - xs[u], 0), 16);
